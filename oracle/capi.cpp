@@ -1,0 +1,236 @@
+// ORACLE (test infrastructure only — never linked into the product path).
+// Flat C entry points over the CPU restatement so tests/ and bench.py's cpu_baseline leg can drive
+// it through ctypes. Field elements cross as 32-byte Montgomery LE limbs, G1 points as 64-byte
+// (x, y) Montgomery — the halo2curves in-memory layout.
+#include <chrono>
+#include <cstdio>
+
+#include "lasso.hpp"
+
+using namespace oracle;
+
+// Documented synthetic-input PRNG: stateless splitmix64.
+static inline uint64_t sm64(uint64_t seed, uint64_t i) {
+  uint64_t z = seed + (i + 1) * 0x9E3779B97F4A7C15ULL;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+  return z ^ (z >> 31);
+}
+
+extern "C" {
+
+int orc_num_threads() { return omp_get_max_threads(); }
+void orc_set_num_threads(int n) { omp_set_num_threads(n); }
+
+uint64_t orc_rand_u64(uint64_t seed, uint64_t i) { return sm64(seed, i); }
+void orc_rand_u64s(uint64_t seed, uint64_t n, uint64_t* out) {
+  for (uint64_t i = 0; i < n; ++i) out[i] = sm64(seed, i);
+}
+// element i = limbs sm64(seed, 4i..4i+3), top limb masked to 61 bits (value < 2^253 < r), Montgomery
+void orc_rand_fr(uint64_t seed, uint64_t n, Fr* out) {
+#pragma omp parallel for
+  for (long i = 0; i < (long)n; ++i) {
+    uint64_t raw[4] = {sm64(seed, 4 * i), sm64(seed, 4 * i + 1), sm64(seed, 4 * i + 2),
+                       sm64(seed, 4 * i + 3) & 0x1fffffffffffffffULL};
+    out[i] = Fr::from_raw(raw);
+  }
+}
+
+// ---- field ------------------------------------------------------------------------------------
+#define FIELD_API(NAME, F)                                                                   \
+  void orc_##NAME##_mul(const F* a, const F* b, F* o, uint64_t n) {                          \
+    for (uint64_t i = 0; i < n; ++i) o[i] = a[i] * b[i];                                     \
+  }                                                                                          \
+  void orc_##NAME##_add(const F* a, const F* b, F* o, uint64_t n) {                          \
+    for (uint64_t i = 0; i < n; ++i) o[i] = a[i] + b[i];                                     \
+  }                                                                                          \
+  void orc_##NAME##_sub(const F* a, const F* b, F* o, uint64_t n) {                          \
+    for (uint64_t i = 0; i < n; ++i) o[i] = a[i] - b[i];                                     \
+  }                                                                                          \
+  void orc_##NAME##_inv(const F* a, F* o, uint64_t n) {                                      \
+    for (uint64_t i = 0; i < n; ++i) o[i] = a[i].inv();                                      \
+  }                                                                                          \
+  void orc_##NAME##_from_raw(const uint64_t* raw, F* o, uint64_t n) {                        \
+    for (uint64_t i = 0; i < n; ++i) o[i] = F::from_raw(raw + 4 * i);                        \
+  }                                                                                          \
+  void orc_##NAME##_to_raw(const F* a, uint64_t* raw, uint64_t n) {                          \
+    for (uint64_t i = 0; i < n; ++i) a[i].to_raw(raw + 4 * i);                               \
+  }
+FIELD_API(fr, Fr)
+FIELD_API(fq, Fq)
+
+// ---- keccak / transcript -----------------------------------------------------------------------
+void orc_keccak256(const uint8_t* data, uint64_t n, uint8_t pad, uint8_t out[32]) {
+  Keccak256 k(pad);
+  k.update(data, n);
+  k.finalize_reset(out);
+}
+void* orc_tr_new() { return new Transcript(); }
+void* orc_tr_from_proof(const uint8_t* proof, uint64_t n) {
+  return new Transcript(std::vector<uint8_t>(proof, proof + n));
+}
+void orc_tr_free(void* h) { delete (Transcript*)h; }
+uint64_t orc_tr_proof_len(void* h) { return ((Transcript*)h)->stream.size(); }
+void orc_tr_proof(void* h, uint8_t* out) {
+  auto& s = ((Transcript*)h)->stream;
+  memcpy(out, s.data(), s.size());
+}
+void orc_tr_common_fe(void* h, const Fr* fe) { ((Transcript*)h)->common_field_element(*fe); }
+void orc_tr_write_fe(void* h, const Fr* fe) { ((Transcript*)h)->write_field_element(*fe); }
+int orc_tr_read_fe(void* h, Fr* fe) { return ((Transcript*)h)->read_field_element(fe) ? 0 : 1; }
+void orc_tr_squeeze(void* h, Fr* out) { *out = ((Transcript*)h)->squeeze_challenge(); }
+int orc_tr_write_comm(void* h, const G1Affine* p) { return ((Transcript*)h)->write_commitment(*p) ? 0 : 1; }
+int orc_tr_read_comm(void* h, G1Affine* p) { return ((Transcript*)h)->read_commitment(p) ? 0 : 1; }
+
+// ---- G1 ----------------------------------------------------------------------------------------
+void orc_g1_generator(G1Affine* out) { *out = G1Affine::generator(); }
+void orc_g1_mul(const G1Affine* p, const Fr* k, G1Affine* out) { *out = G1::from_affine(*p).mul(*k).to_affine(); }
+void orc_g1_add(const G1Affine* a, const G1Affine* b, G1Affine* out) {
+  *out = G1::from_affine(*a).add_affine(*b).to_affine();
+}
+int orc_g1_on_curve(const G1Affine* p) { return p->on_curve() ? 1 : 0; }
+
+// ---- MLE ---------------------------------------------------------------------------------------
+void orc_eq_xy(const Fr* y, int n, Fr* out) {
+  Poly e = eq_xy(std::vector<Fr>(y, y + n));
+  memcpy(out, e.data(), e.size() * sizeof(Fr));
+}
+void orc_evaluate(const Fr* p, int nv, const Fr* x, Fr* out) {
+  *out = evaluate(Poly(p, p + ((size_t)1 << nv)), std::vector<Fr>(x, x + nv));
+}
+void orc_fix_var(const Fr* p, int nv, const Fr* r, Fr* out) {
+  Poly o = fix_var(Poly(p, p + ((size_t)1 << nv)), *r);
+  memcpy(out, o.data(), o.size() * sizeof(Fr));
+}
+void orc_eq_xy_eval(const Fr* x, const Fr* y, int n, Fr* out) {
+  *out = eq_xy_eval(std::vector<Fr>(x, x + n), std::vector<Fr>(y, y + n));
+}
+
+// ---- sum-check ---------------------------------------------------------------------------------
+// EVAL shape. polys: npolys pointers to 2^num_vars tables. term k multiplies coeffs[k] by the
+// tables idx[off[k] .. off[k+1]). Returns challenges (num_vars) and evals (npolys).
+void orc_sumcheck_prove_evals(void* tr, int num_vars, int npolys, const Fr* const* polys, int has_eq,
+                              const Fr* y, int nterms, const Fr* coeffs, const int* off,
+                              const int* idx, const Fr* sum, Fr* challenges, Fr* evals) {
+  std::vector<Poly> tabs(npolys);
+  VirtualPoly vp;
+  for (int i = 0; i < npolys; ++i) tabs[i].assign(polys[i], polys[i] + ((size_t)1 << num_vars));
+  for (int i = 0; i < npolys; ++i) vp.polys.push_back(&tabs[i]);
+  vp.has_eq = has_eq != 0;
+  if (has_eq) vp.y.assign(y, y + num_vars);
+  for (int k = 0; k < nterms; ++k) vp.terms.push_back(Term{coeffs[k], std::vector<int>(idx + off[k], idx + off[k + 1])});
+  SumCheckOutput o = sumcheck_prove_evals(num_vars, vp, *sum, *(Transcript*)tr);
+  memcpy(challenges, o.challenges.data(), num_vars * sizeof(Fr));
+  memcpy(evals, o.evals.data(), npolys * sizeof(Fr));
+}
+// COEFF shape: Σ_k scalars[k] * eq(x, ys[k]) * polys[poly_idx[k]]
+void orc_sumcheck_prove_coeffs(void* tr, int num_vars, int npolys, const Fr* const* polys, int nprods,
+                               const Fr* scalars, const Fr* ys, const int* poly_idx, const Fr* sum,
+                               Fr* challenges, Fr* evals) {
+  std::vector<Poly> tabs(npolys);
+  std::vector<const Poly*> ptrs;
+  for (int i = 0; i < npolys; ++i) tabs[i].assign(polys[i], polys[i] + ((size_t)1 << num_vars));
+  for (int i = 0; i < npolys; ++i) ptrs.push_back(&tabs[i]);
+  std::vector<CoeffProduct> prods;
+  for (int k = 0; k < nprods; ++k)
+    prods.push_back(CoeffProduct{scalars[k], std::vector<Fr>(ys + k * num_vars, ys + (k + 1) * num_vars), poly_idx[k]});
+  SumCheckOutput o = sumcheck_prove_coeffs(num_vars, prods, ptrs, *sum, *(Transcript*)tr);
+  memcpy(challenges, o.challenges.data(), num_vars * sizeof(Fr));
+  memcpy(evals, o.evals.data(), npolys * sizeof(Fr));
+}
+int orc_sumcheck_verify(void* tr, int num_vars, int degree, const Fr* sum, int coeffs, Fr* final_claim,
+                        Fr* challenges) {
+  std::vector<Fr> ch;
+  if (!sumcheck_verify(num_vars, degree, *sum, coeffs != 0, *(Transcript*)tr, final_claim, &ch)) return 1;
+  memcpy(challenges, ch.data(), num_vars * sizeof(Fr));
+  return 0;
+}
+// cfg2 claim: Σ_b eq(b,y) a(b) b(b)
+void orc_sum_eq_ab(int num_vars, const Fr* y, const Fr* a, const Fr* b, Fr* out) {
+  Poly e = eq_xy(std::vector<Fr>(y, y + num_vars));
+  Fr acc = Fr::zero();
+  for (size_t i = 0; i < e.size(); ++i) acc = acc + e[i] * a[i] * b[i];
+  *out = acc;
+}
+
+// ---- MSM / KZG ---------------------------------------------------------------------------------
+void orc_msm(const Fr* scalars, const G1Affine* bases, uint64_t n, G1Affine* out) {
+  *out = variable_base_msm(scalars, bases, n).to_affine();
+}
+void* orc_kzg_setup(const Fr* ss, int n) { return new KzgParams(kzg_setup(std::vector<Fr>(ss, ss + n))); }
+void orc_kzg_free(void* h) { delete (KzgParams*)h; }
+void orc_kzg_eqs(void* h, int level, G1Affine* out) {
+  auto& e = ((KzgParams*)h)->eqs[level];
+  memcpy(out, e.data(), e.size() * sizeof(G1Affine));
+}
+void orc_kzg_commit(void* h, const Fr* poly, int nv, G1Affine* out) {
+  *out = kzg_commit(*(KzgParams*)h, Poly(poly, poly + ((size_t)1 << nv)));
+}
+int orc_kzg_open(void* h, void* tr, const Fr* poly, int nv, const Fr* point, Fr* eval) {
+  bool ok;
+  *eval = kzg_open(*(KzgParams*)h, Poly(poly, poly + ((size_t)1 << nv)), std::vector<Fr>(point, point + nv),
+                   *(Transcript*)tr, &ok);
+  return ok ? 0 : 1;
+}
+int orc_kzg_verify(void* h, void* tr, const G1Affine* comm, int nv, const Fr* point, const Fr* eval) {
+  return kzg_verify(*(KzgParams*)h, *comm, std::vector<Fr>(point, point + nv), *eval, *(Transcript*)tr) ? 0 : 1;
+}
+static void unpack_batch(int nv, int npoints, const Fr* points, int nevals, const int* ev_poly,
+                         const int* ev_point, const Fr* ev_value, std::vector<std::vector<Fr>>* pts,
+                         std::vector<Evaluation>* evs) {
+  for (int i = 0; i < npoints; ++i) pts->push_back(std::vector<Fr>(points + i * nv, points + (i + 1) * nv));
+  for (int k = 0; k < nevals; ++k) evs->push_back(Evaluation{ev_poly[k], ev_point[k], ev_value[k]});
+}
+int orc_kzg_batch_open(void* h, void* tr, int nv, int npolys, const Fr* const* polys, int npoints,
+                       const Fr* points, int nevals, const int* ev_poly, const int* ev_point,
+                       const Fr* ev_value) {
+  std::vector<Poly> tabs(npolys);
+  std::vector<const Poly*> ptrs;
+  for (int i = 0; i < npolys; ++i) tabs[i].assign(polys[i], polys[i] + ((size_t)1 << nv));
+  for (int i = 0; i < npolys; ++i) ptrs.push_back(&tabs[i]);
+  std::vector<std::vector<Fr>> pts;
+  std::vector<Evaluation> evs;
+  unpack_batch(nv, npoints, points, nevals, ev_poly, ev_point, ev_value, &pts, &evs);
+  return kzg_batch_open(*(KzgParams*)h, nv, ptrs, pts, evs, *(Transcript*)tr) ? 0 : 1;
+}
+int orc_kzg_batch_verify(void* h, void* tr, int nv, int ncomms, const G1Affine* comms, int npoints,
+                         const Fr* points, int nevals, const int* ev_poly, const int* ev_point,
+                         const Fr* ev_value) {
+  std::vector<std::vector<Fr>> pts;
+  std::vector<Evaluation> evs;
+  unpack_batch(nv, npoints, points, nevals, ev_poly, ev_point, ev_value, &pts, &evs);
+  return kzg_batch_verify(*(KzgParams*)h, nv, std::vector<G1Affine>(comms, comms + ncomms), pts, evs,
+                          *(Transcript*)tr) ? 0 : 1;
+}
+
+// ---- Lasso -------------------------------------------------------------------------------------
+int orc_lasso_prove(void* kzg, void* tr, int kind, int chunks, int mu, const uint64_t* xs, const uint64_t* ys) {
+  LassoTable tb{kind, chunks};
+  return lasso_prove(*(KzgParams*)kzg, tb, mu, xs, ys, *(Transcript*)tr) ? 0 : 1;
+}
+int orc_lasso_verify(void* kzg, void* tr, int kind, int chunks, int mu) {
+  LassoTable tb{kind, chunks};
+  return lasso_verify(*(KzgParams*)kzg, tb, mu, *(Transcript*)tr) ? 0 : 1;
+}
+// witness tables, flattened: a | dim[c] | e[c] | read_ts[c] (each 2^mu) then final_cts[c] (each 2^16)
+void orc_lasso_witness(int kind, int chunks, int mu, const uint64_t* xs, const uint64_t* ys, Fr* mtabs, Fr* stabs) {
+  LassoTable tb{kind, chunks};
+  LassoWitness w = lasso_witness(tb, mu, xs, ys);
+  const size_t m = (size_t)1 << mu, S = (size_t)1 << SUBTABLE_VARS;
+  size_t k = 0;
+  memcpy(mtabs + (k++) * m, w.a.data(), m * sizeof(Fr));
+  for (auto& p : w.dim) memcpy(mtabs + (k++) * m, p.data(), m * sizeof(Fr));
+  for (auto& p : w.e) memcpy(mtabs + (k++) * m, p.data(), m * sizeof(Fr));
+  for (auto& p : w.read_ts) memcpy(mtabs + (k++) * m, p.data(), m * sizeof(Fr));
+  for (int t = 0; t < chunks; ++t) memcpy(stabs + t * S, w.final_cts[t].data(), S * sizeof(Fr));
+}
+// grand product alone (for kernel-level parity): leaves = T tables of 2^h
+void orc_grand_product_prove(void* tr, int T, int h, const Fr* const* leaves, Fr* claims, Fr* point) {
+  std::vector<Poly> lv(T);
+  for (int t = 0; t < T; ++t) lv[t].assign(leaves[t], leaves[t] + ((size_t)1 << h));
+  GrandProductOutput o = grand_product_prove(lv, *(Transcript*)tr, nullptr);
+  memcpy(claims, o.claims.data(), T * sizeof(Fr));
+  memcpy(point, o.point.data(), h * sizeof(Fr));
+}
+
+}  // extern "C"
