@@ -1,0 +1,276 @@
+"""halo2-lasso_b200 — host-side mirror of the reference's prover interfaces over libb200lasso.so.
+
+The reference is Rust and no Rust toolchain exists in this image, so the host layer above the C ABI
+(include/b200_lasso.h) is this thin ctypes binding whose class / method names follow the reference:
+
+    Keccak256Transcript      pb/util/transcript.rs   (write_field_elements, squeeze_challenges, into_proof)
+    MultilinearPolynomial    pb/poly/multilinear.rs  (eq_xy, fix_var, evaluate)
+    ClassicSumCheck          pb/piop/sum_check/classic.rs (prove; EvaluationsProver / CoefficientsProver)
+
+Field elements are numpy uint64 arrays (..., 4): Montgomery limbs, the halo2curves memory layout.
+There is NO CPU fallback: importing works anywhere (symbol checks), but every compute call needs the
+CUDA library and a GPU and raises otherwise.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_DIR = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_DIR, "libb200lasso.so")
+HEADER_PATH = os.path.join(os.path.dirname(_DIR), "include", "b200_lasso.h")
+
+B200_OK, B200_ERR_CUDA, B200_ERR_ARG, B200_ERR_TRANSCRIPT, B200_ERR_NOMEM = range(5)
+
+
+class B200Error(RuntimeError):
+    """Maps the C status codes onto the reference's `Error` variants (pb/lib.rs:12-20)."""
+
+    NAMES = {1: "Cuda", 2: "InvalidPcsParam/InvalidSumcheck (bad argument)", 3: "Transcript", 4: "OutOfMemory"}
+
+    def __init__(self, code, where):
+        super().__init__(f"{where}: {self.NAMES.get(code, code)}")
+        self.code = code
+
+
+def build(force=False):
+    """Compile the sm_100a library in-tree (nvcc cross-compiles without a GPU)."""
+    if force:
+        subprocess.check_call(["make", "-C", _DIR, "clean"])
+    subprocess.check_call(["make", "-C", _DIR, "-j8", "-s"])
+    return LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    """Load libb200lasso.so; fails loudly when it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise FileNotFoundError(f"{LIB_PATH} missing: run `python -c 'import __graft_entry__ as g; g.build()'`")
+        _lib = C.CDLL(LIB_PATH)
+        _lib.b200_launch_count.restype = C.c_uint64
+        _lib.b200_stream.restype = C.c_void_p
+    return _lib
+
+
+def _chk(rc, where):
+    if rc != 0:
+        raise B200Error(rc, where)
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _fr(a):
+    a = np.ascontiguousarray(a, dtype=np.uint64)
+    assert a.shape[-1] == 4
+    return a
+
+
+class Context:
+    """b200_ctx: one per process / GPU."""
+
+    def __init__(self, device=0):
+        self.h = C.c_void_p()
+        _chk(lib().b200_ctx_create(C.c_int(device), C.byref(self.h)), "ctx_create")
+
+    def close(self):
+        if getattr(self, "h", None) and self.h:
+            lib().b200_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def sync(self):
+        _chk(lib().b200_sync(self.h), "sync")
+
+    def launch_count(self, reset=False):
+        return int(lib().b200_launch_count(self.h, C.c_int(int(reset))))
+
+    @property
+    def stream(self):
+        return lib().b200_stream(self.h)
+
+
+class MultilinearPolynomial:
+    """Device-resident `MultilinearPolynomial<Fr>` (pb/poly/multilinear.rs:20-24)."""
+
+    def __init__(self, ctx, dev, num_vars, owned=True):
+        self.ctx, self.dev, self.num_vars, self.owned = ctx, dev, num_vars, owned
+
+    @classmethod
+    def new(cls, ctx, evals):
+        evals = _fr(evals)
+        n = evals.shape[0]
+        assert n & (n - 1) == 0 and n > 0
+        dev = C.c_void_p()
+        _chk(lib().b200_poly_upload(ctx.h, _p(evals), C.c_uint64(n), C.byref(dev)), "poly_upload")
+        ctx.sync()  # the host array may be pageable and die before the copy is staged
+        return cls(ctx, dev, n.bit_length() - 1)
+
+    @classmethod
+    def alloc(cls, ctx, num_vars):
+        dev = C.c_void_p()
+        _chk(lib().b200_poly_alloc(ctx.h, C.c_uint64(1 << num_vars), C.byref(dev)), "poly_alloc")
+        return cls(ctx, dev, num_vars)
+
+    @classmethod
+    def eq_xy(cls, ctx, y):
+        y = _fr(y)
+        out = cls.alloc(ctx, y.shape[0])
+        _chk(lib().b200_eq_xy(ctx.h, _p(y), C.c_int(y.shape[0]), out.dev), "eq_xy")
+        return out
+
+    def __len__(self):
+        return 1 << self.num_vars
+
+    def evals(self):
+        out = np.zeros((len(self), 4), dtype=np.uint64)
+        _chk(lib().b200_poly_download(self.ctx.h, self.dev, C.c_uint64(len(self)), _p(out)), "poly_download")
+        return out
+
+    def fix_var(self, r):
+        out = MultilinearPolynomial.alloc(self.ctx, self.num_vars - 1)
+        _chk(lib().b200_fix_var(self.ctx.h, self.dev, C.c_int(self.num_vars), _p(_fr(r)), out.dev), "fix_var")
+        return out
+
+    def evaluate(self, x):
+        return evaluate_many(self.ctx, [self], x)[0]
+
+    def free(self):
+        if self.owned and self.dev:
+            lib().b200_poly_free(self.ctx.h, self.dev)
+            self.dev = None
+
+    def __del__(self):
+        try:
+            if self.ctx.h:
+                self.free()
+        except Exception:
+            pass
+
+
+def evaluate_many(ctx, polys, x):
+    x = _fr(x)
+    ptrs = (C.c_void_p * len(polys))(*[p.dev for p in polys])
+    out = np.zeros((len(polys), 4), dtype=np.uint64)
+    _chk(lib().b200_evaluate(ctx.h, ptrs, C.c_int(len(polys)), C.c_int(x.shape[0]), _p(x), _p(out)), "evaluate")
+    return out
+
+
+class Keccak256Transcript:
+    """FiatShamirTranscript<Keccak256, Cursor<Vec<u8>>> living on the device inside the context."""
+
+    def __init__(self, ctx):
+        self.ctx = ctx
+        _chk(lib().b200_transcript_reset(ctx.h), "transcript_reset")
+
+    def common_field_elements(self, fes):
+        fes = _fr(fes).reshape(-1, 4)
+        _chk(lib().b200_transcript_common_field_elements(self.ctx.h, _p(fes), C.c_int(fes.shape[0])), "common_fe")
+
+    def write_field_elements(self, fes):
+        fes = _fr(fes).reshape(-1, 4)
+        _chk(lib().b200_transcript_write_field_elements(self.ctx.h, _p(fes), C.c_int(fes.shape[0])), "write_fe")
+
+    def squeeze_challenges(self, n):
+        out = np.zeros((n, 4), dtype=np.uint64)
+        _chk(lib().b200_transcript_squeeze_challenges(self.ctx.h, C.c_int(n), _p(out)), "squeeze")
+        return out
+
+    def squeeze_challenge(self):
+        return self.squeeze_challenges(1)[0]
+
+    def write_commitments(self, pts):
+        pts = np.ascontiguousarray(pts, dtype=np.uint64).reshape(-1, 8)
+        _chk(lib().b200_transcript_write_commitments(self.ctx.h, _p(pts), C.c_int(pts.shape[0])), "write_commitments")
+
+    def into_proof(self) -> bytes:
+        n = C.c_uint64()
+        cap = 8 << 20
+        buf = (C.c_uint8 * cap)()
+        _chk(lib().b200_transcript_proof(self.ctx.h, buf, C.c_uint64(cap), C.byref(n)), "into_proof")
+        return bytes(buf[: n.value])
+
+
+class ClassicSumCheck:
+    """`SumCheck::prove` (pb/piop/sum_check.rs:39-58) for the expression shapes of the Lasso hot path."""
+
+    @staticmethod
+    def prove_evals(ctx, num_vars, polys, weights, y, claimed_sum, np_per_term=2):
+        """EvaluationsProver:  eq(x,y) * Σ_t w_t Π_k P[t*np+k](x). Returns (challenges, evals)."""
+        nterms = len(polys) // np_per_term
+        ptrs = (C.c_void_p * len(polys))(*[p.dev for p in polys])
+        ch = np.zeros((num_vars, 4), dtype=np.uint64)
+        ev = np.zeros((len(polys), 4), dtype=np.uint64)
+        _chk(lib().b200_sumcheck_prove_evals(ctx.h, C.c_int(num_vars), C.c_int(nterms), C.c_int(np_per_term), ptrs,
+                                             _p(_fr(weights)), _p(_fr(y)), _p(_fr(claimed_sum)), _p(ch), _p(ev)),
+             "sumcheck_prove_evals")
+        return ch, ev
+
+    @staticmethod
+    def prove_evals_host(ctx, num_vars, host_tables, weights, y, claimed_sum, np_per_term=2):
+        """Same with HOST tables (pinned or pageable); host<->device copies happen inside the call."""
+        nterms = len(host_tables) // np_per_term
+        ptrs = (C.c_void_p * len(host_tables))(*[int(t) if isinstance(t, int) else t.ctypes.data for t in host_tables])
+        ch = np.zeros((num_vars, 4), dtype=np.uint64)
+        ev = np.zeros((len(host_tables), 4), dtype=np.uint64)
+        _chk(lib().b200_sumcheck_prove_evals_host(ctx.h, C.c_int(num_vars), C.c_int(nterms), C.c_int(np_per_term), ptrs,
+                                                  _p(_fr(weights)), _p(_fr(y)), _p(_fr(claimed_sum)), _p(ch), _p(ev)),
+             "sumcheck_prove_evals_host")
+        return ch, ev
+
+    @staticmethod
+    def prove_coeffs(ctx, num_vars, polys, scalars, ys, claimed_sum):
+        """CoefficientsProver:  Σ_k s_k eq(x, y_k) P_k(x). Returns (challenges, evals)."""
+        K = len(polys)
+        ptrs = (C.c_void_p * K)(*[p.dev for p in polys])
+        ys = _fr(ys).reshape(K * num_vars, 4)
+        ch = np.zeros((num_vars, 4), dtype=np.uint64)
+        ev = np.zeros((K, 4), dtype=np.uint64)
+        _chk(lib().b200_sumcheck_prove_coeffs(ctx.h, C.c_int(num_vars), C.c_int(K), ptrs, _p(_fr(scalars)), _p(ys),
+                                              _p(_fr(claimed_sum)), _p(ch), _p(ev)), "sumcheck_prove_coeffs")
+        return ch, ev
+
+
+def profile_rounds(ctx, fn, num_vars=20, tables=3):
+    """Time every sum-check round launch of `fn()` with CUDA events on the library stream and return the
+    roofline entry of the dominant launch (round 1: the first fused bind+evaluate over full tables)."""
+    _chk(lib().b200_profile_enable(ctx.h, C.c_int(1)), "profile_enable")
+    fn()
+    cap = 4096
+    ms = (C.c_float * cap)()
+    tags = (C.c_int * cap)()
+    n = C.c_int()
+    _chk(lib().b200_profile_read(ctx.h, ms, tags, C.c_int(cap), C.byref(n)), "profile_read")
+    _chk(lib().b200_profile_enable(ctx.h, C.c_int(0)), "profile_enable")
+    rounds = {}
+    for i in range(min(n.value, cap)):
+        rounds.setdefault(tags[i], []).append(ms[i])
+    per_round = [sum(v) / len(v) for _, v in sorted(rounds.items())]
+    if len(per_round) < 2:
+        return None
+    # round 1 reads `tables` tables of 2^n and writes them bound to 2^(n-1): the algorithmic bytes of that launch
+    algo = 32 * tables * ((1 << num_vars) + (1 << (num_vars - 1)))
+    t = per_round[1]
+    return {"kernel": "sc_eval_round_kernel<2,true> (round 1: fused bind + evaluate)", "launch_ms": t,
+            "algorithmic_bytes_per_launch": algo, "achieved": algo / (t * 1e-3) / 1e9,
+            "round_ms": [round(x, 5) for x in per_round]}
+
+
+def declared_symbols():
+    """Every function name include/b200_lasso.h declares (used by the CPU-side ABI test)."""
+    import re
+
+    src = open(HEADER_PATH).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(b200_[a-z0-9_]+)\s*\(", src)))

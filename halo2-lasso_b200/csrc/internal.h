@@ -1,0 +1,106 @@
+// Host-side internal interface between the translation units of libb200lasso.so.
+// Everything here is asynchronous on ctx->stream; scalars (claims, challenges, evaluations) stay in
+// device memory so that no step of a proof needs a host round trip.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <vector>
+
+#include "common.cuh"
+
+namespace b200 {
+
+struct ScState {
+  Fr claim;  // running claimed sum
+  Fr r;      // challenge of the previous round
+  unsigned int counter;
+  unsigned int pad[7];
+};
+
+struct G1Aff {  // 64 bytes, (x, y) Montgomery; identity = (0, 0)
+  Fq x, y;
+};
+struct G1Xyzz {  // x = X/ZZ, y = Y/ZZZ; identity has ZZ == 0
+  Fq x, y, zz, zzz;
+};
+
+struct Ctx {
+  int device;
+  cudaStream_t stream;
+  Transcript* d_tr;
+  uint8_t* d_proof;
+  uint32_t proof_cap;
+  BaryTable* d_bary;
+  ScState* d_sc;
+  Fr* d_partial;       // per-CTA partial sums of the round kernels
+  size_t partial_elems;
+  uint64_t launches;   // kernels launched since the last reset (bench "gpu_launches")
+  // optional per-launch CUDA-event timing of the sum-check round kernels (bench roofline leg)
+  bool profile;
+  std::vector<cudaEvent_t> prof_events;  // pairs (start, stop)
+  std::vector<int> prof_tags;            // round index per pair
+  // SRS: eqs[k] = 2^k affine points (MultilinearKzgProverParams::eqs, kzg.rs:36-53)
+  std::vector<G1Aff*> srs;
+};
+
+static const int SC_MAX_TERMS = 32;
+static const int SC_MAX_TABLES = 64;
+
+// EVAL shape  F(x) = eq(x, y) * Σ_t w_t * Π_{k<NP} P_{t,k}(x)       (NP = 1 or 2)
+struct ScEvalJob {
+  int num_vars, T, NP;
+  const Fr* tables[SC_MAX_TABLES];  // [t*NP + k], each 2^num_vars, read-only
+  const Fr* weights;                // device, T
+  const Fr* eq_point;               // device, num_vars
+  const Fr* claim;                  // device, 1
+  Fr* challenges_out;               // device, num_vars
+  Fr* evals_out;                    // device, T*NP
+};
+int sumcheck_prove_evals(Ctx* c, const ScEvalJob& job);
+
+// COEFF shape  F(x) = Σ_k s_k * eq(x, y_k) * P_k(x)   (CoefficientsProver, degree 2)
+struct ScCoeffJob {
+  int num_vars, K;
+  const Fr* tables[SC_MAX_TERMS];     // P_k
+  const Fr* eq_points[SC_MAX_TERMS];  // device, num_vars each
+  const Fr* scalars;                  // device, K
+  const Fr* claim;
+  Fr* challenges_out;
+  Fr* evals_out;  // K
+};
+int sumcheck_prove_coeffs(Ctx* c, const ScCoeffJob& job);
+
+// mle.cu
+int eq_build(Ctx* c, const Fr* d_y, int n, Fr* d_out);                         // eq_xy
+int fix_var(Ctx* c, const Fr* d_in, int n, const Fr* d_r, Fr* d_out);          // one bind
+int mle_eval_many(Ctx* c, const Fr* const* h_tables, int ntables, int n, const Fr* d_point,
+                  Fr* d_out);                                                   // evaluate
+int fr_lincomb(Ctx* c, const Fr* const* h_tables, int k, const Fr* d_scalars, size_t len,
+               Fr* d_out);                                                      // Σ s_i P_i
+int fr_convert(Ctx* c, const Fr* d_in, Fr* d_out, size_t n, int to_mont);
+int fr_from_u64(Ctx* c, const uint64_t* d_in, Fr* d_out, size_t n);
+int quotient_step(Ctx* c, Fr* d_rem, size_t half, const Fr* d_x, Fr* d_q);     // pcs/multilinear.rs:72-107
+int eq_xy_eval_dev(Ctx* c, const Fr* d_x, const Fr* d_y, int n, Fr* d_out);    // sum_check.rs:111-121
+int transcript_op(Ctx* c, int op, const Fr* d_in, Fr* d_out, int n);           // 0 common, 1 write, 2 squeeze
+int transcript_write_points(Ctx* c, const G1Aff* d_pts, int n);
+
+enum { TR_COMMON = 0, TR_WRITE = 1, TR_SQUEEZE = 2 };
+
+inline void count_launch(Ctx* c, int n = 1) { c->launches += n; }
+inline void prof_begin(Ctx* c, int tag) {
+  if (!c->profile) return;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  c->prof_events.push_back(e0);
+  c->prof_events.push_back(e1);
+  c->prof_tags.push_back(tag);
+  cudaEventRecord(e0, c->stream);
+}
+inline void prof_end(Ctx* c) {
+  if (!c->profile) return;
+  cudaEventRecord(c->prof_events.back(), c->stream);
+}
+
+}  // namespace b200

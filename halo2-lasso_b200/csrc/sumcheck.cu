@@ -1,0 +1,359 @@
+// ClassicSumCheck on the GPU: one kernel per round that FUSES
+//   (1) the bind of the previous round's challenge (ProverState::next_round / fix_var_in_place,
+//       pb/piop/sum_check/classic.rs:90-141, pb/poly/multilinear.rs:599-618),
+//   (2) the round evaluation at x = 1..d over hypercube pairs (EvaluationsProver::evals,
+//       pb/piop/sum_check/classic/eval.rs:102-131; p(0) DERIVED as sum - p(1), :129), or the
+//       Karatsuba coefficients of CoefficientsProver (classic/coeff.rs:136-203),
+//   (3) the Fiat-Shamir step (write d+1 elements, squeeze r: classic.rs:225-236) and the claim fold
+//       (barycentric_interpolate / horner), executed by the last CTA to finish.
+// Tables are read with 256-bit loads (4 consecutive elements per thread when binding), bound values
+// are written once (ping-pong scratch), so a table element moves 3 times over a whole sum-check
+// instead of the reference's 5 (32*P*(4*2^n - 3) bytes).
+#include "internal.h"
+
+namespace b200 {
+
+struct ScEvalArgs {
+  const Fr* eq_in;
+  Fr* eq_out;
+  const Fr* in[SC_MAX_TABLES];
+  Fr* out[SC_MAX_TABLES];
+  const Fr* weights;
+  ScState* st;
+  Fr* partial;
+  Transcript* tr;
+  const BaryTable* bary;
+  Fr* challenges_out;
+  uint32_t pairs;
+  int round;
+};
+
+// Load the pair (u0, u1) = (t[2b], t[2b+1]) of the CURRENT round. With BIND the table still has the
+// previous round's size: bind 4 consecutive elements with r first and store the bound pair.
+template <bool BIND>
+__device__ __forceinline__ void load_pair(const Fr* __restrict__ in, Fr* __restrict__ out, uint32_t b,
+                                          const Fr& r, bool store, Fr& u0, Fr& u1) {
+  if (BIND) {
+    const Fr* p = in + 4 * (size_t)b;
+    Fr x0 = fe_ldg(p), x1 = fe_ldg(p + 1), x2 = fe_ldg(p + 2), x3 = fe_ldg(p + 3);
+    u0 = (x1 - x0) * r + x0;
+    u1 = (x3 - x2) * r + x2;
+    if (store) {
+      fe_st(out + 2 * (size_t)b, u0);
+      fe_st(out + 2 * (size_t)b + 1, u1);
+    }
+  } else {
+    const Fr* p = in + 2 * (size_t)b;
+    u0 = fe_ldg(p);
+    u1 = fe_ldg(p + 1);
+  }
+}
+
+// p(r) from p(0..d) with precomputed weights: Σ_i e_i * w_i * Π_{j != i} (r - j)
+__device__ __forceinline__ Fr interpolate_at(const Fr* ev, int d, const Fr& r, const BaryTable* bary) {
+  Fr diff[7], pre[8], acc = fe_zero<FrP>();
+  Fr j = fe_zero<FrP>(), one = fe_one<FrP>();
+  for (int i = 0; i <= d; ++i) {
+    diff[i] = r - j;
+    j = j + one;
+  }
+  pre[0] = one;
+  for (int i = 0; i <= d; ++i) pre[i + 1] = pre[i] * diff[i];
+  Fr suf = one;
+  for (int i = d; i >= 0; --i) {
+    acc = acc + ev[i] * bary->w[d][i] * pre[i] * suf;
+    suf = suf * diff[i];
+  }
+  return acc;
+}
+
+template <int NP, bool BIND>
+__global__ void __launch_bounds__(SC_THREADS) sc_eval_round_kernel(ScEvalArgs a) {
+  constexpr int D = NP + 1;  // degree; evaluations at 1..D are computed, p(0) derived
+  __shared__ Fr smem[(SC_THREADS / 32) * D];
+  const int t = blockIdx.y;
+  Fr acc[D];
+#pragma unroll
+  for (int x = 0; x < D; ++x) acc[x] = fe_zero<FrP>();
+  Fr r = fe_zero<FrP>();
+  if (BIND) r = fe_ld(&a.st->r);
+
+  const Fr* __restrict__ in0 = a.in[t * NP];
+  Fr* __restrict__ out0 = a.out[t * NP];
+  const Fr* __restrict__ in1 = NP == 2 ? a.in[t * NP + 1] : nullptr;
+  Fr* __restrict__ out1 = NP == 2 ? a.out[t * NP + 1] : nullptr;
+
+  for (uint32_t b = blockIdx.x * blockDim.x + threadIdx.x; b < a.pairs; b += gridDim.x * blockDim.x) {
+    Fr e0, e1, p0, p1, q0, q1;
+    load_pair<BIND>(a.eq_in, a.eq_out, b, r, t == 0, e0, e1);
+    load_pair<BIND>(in0, out0, b, r, true, p0, p1);
+    if (NP == 2) load_pair<BIND>(in1, out1, b, r, true, q0, q1);
+    // eval = t[2b+1], step = t[2b+1] - t[2b]; x -> x+1 adds the step (eval.rs:228-286)
+    e0 = e1 - e0;
+    p0 = p1 - p0;
+    if (NP == 2) q0 = q1 - q0;
+#pragma unroll
+    for (int x = 0; x < D; ++x) {
+      Fr prod = e1 * p1;
+      if (NP == 2) prod = prod * q1;
+      acc[x] = acc[x] + prod;
+      if (x + 1 < D) {
+        e1 = e1 + e0;
+        p1 = p1 + p0;
+        if (NP == 2) q1 = q1 + q0;
+      }
+    }
+  }
+  block_reduce_fr<D>(acc, smem);
+  if (threadIdx.x == 0) {
+    const Fr w = fe_ld(a.weights + t);
+    Fr* dst = a.partial + ((size_t)t * gridDim.x + blockIdx.x) * D;
+#pragma unroll
+    for (int x = 0; x < D; ++x) fe_st(dst + x, acc[x] * w);
+  }
+  if (!last_cta_ticket(&a.st->counter)) return;
+
+  // ---- last CTA: total, derive p(0), Fiat-Shamir, fold the claim -------------------------------
+  const uint32_t nparts = gridDim.x * gridDim.y;
+#pragma unroll
+  for (int x = 0; x < D; ++x) acc[x] = fe_zero<FrP>();
+  for (uint32_t i = threadIdx.x; i < nparts; i += blockDim.x) {
+#pragma unroll
+    for (int x = 0; x < D; ++x) acc[x] = acc[x] + fr_ld_cg(a.partial + (size_t)i * D + x);
+  }
+  block_reduce_fr<D>(acc, smem);
+  if (threadIdx.x == 0) {
+    Fr ev[D + 1];
+#pragma unroll
+    for (int x = 0; x < D; ++x) ev[x + 1] = acc[x];
+    const Fr claim = fe_ld(&a.st->claim);
+    ev[0] = claim - ev[1];
+    for (int x = 0; x <= D; ++x) tr_write_fe(a.tr, ev[x]);
+    const Fr ch = tr_squeeze(a.tr);
+    fe_st(a.challenges_out + a.round, ch);
+    fe_st(&a.st->r, ch);
+    fe_st(&a.st->claim, interpolate_at(ev, D, ch, a.bary));
+  }
+}
+
+// After the last round every table has 2 entries: bind them with the last challenge.
+__global__ void sc_final_bind_kernel(const Fr* const* tabs, int ntabs, const ScState* st, Fr* evals_out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= ntabs) return;
+  const Fr r = fe_ld(&st->r);
+  const Fr x0 = fe_ld(tabs[i]), x1 = fe_ld(tabs[i] + 1);
+  fe_st(evals_out + i, (x1 - x0) * r + x0);
+}
+
+__global__ void sc_init_kernel(ScState* st, const Fr* claim) {
+  if (threadIdx.x == 0) {
+    fe_st(&st->claim, fe_ld(claim));
+    fe_st(&st->r, fe_zero<FrP>());
+    st->counter = 0;
+  }
+}
+
+static inline int blocks_for(uint32_t pairs, int rows) {
+  int per_row = (2 * NUM_SMS + rows - 1) / rows;  // ~2 CTAs per SM over the whole grid
+  if (per_row < 1) per_row = 1;
+  int need = (int)((pairs + SC_THREADS - 1) / SC_THREADS);
+  if (need < 1) need = 1;
+  return need < per_row ? need : per_row;
+}
+
+int sumcheck_prove_evals(Ctx* c, const ScEvalJob& job) {
+  const int n = job.num_vars, T = job.T, NP = job.NP, ntab = T * NP;
+  if (n < 1 || n > 30 || T < 1 || T > SC_MAX_TERMS || (NP != 1 && NP != 2)) return B200_ERR_ARG;
+  cudaStream_t s = c->stream;
+  const size_t N = (size_t)1 << n;
+  // scratch: eq table (N) + ping-pong halves for eq and every table
+  const size_t szA = N / 2, szB = N / 4 ? N / 4 : 1;
+  Fr *eq0 = nullptr, *bufA = nullptr, *bufB = nullptr;
+  CUDA_TRY(cudaMallocAsync(&eq0, N * sizeof(Fr), s));
+  CUDA_TRY(cudaMallocAsync(&bufA, (size_t)(ntab + 1) * szA * sizeof(Fr), s));
+  CUDA_TRY(cudaMallocAsync(&bufB, (size_t)(ntab + 1) * szB * sizeof(Fr), s));
+  int rc = eq_build(c, job.eq_point, n, eq0);
+  if (rc) return rc;
+  sc_init_kernel<<<1, 32, 0, s>>>(c->d_sc, job.claim);
+  count_launch(c);
+
+  ScEvalArgs a;
+  a.weights = job.weights;
+  a.st = c->d_sc;
+  a.partial = c->d_partial;
+  a.tr = c->d_tr;
+  a.bary = c->d_bary;
+  a.challenges_out = job.challenges_out;
+  const Fr* cur[SC_MAX_TABLES + 1];  // current (unbound) tables; slot ntab = eq
+  for (int i = 0; i < ntab; ++i) cur[i] = job.tables[i];
+  cur[ntab] = eq0;
+  for (int round = 0; round < n; ++round) {
+    a.round = round;
+    a.pairs = (uint32_t)(N >> (round + 1));
+    Fr* dst_base = (round & 1) ? bufA : bufB;  // round 1 writes A, round 2 writes B, ...
+    const size_t dst_sz = (round & 1) ? szA : szB;
+    a.eq_in = cur[ntab];
+    a.eq_out = dst_base + (size_t)ntab * dst_sz;
+    for (int i = 0; i < ntab; ++i) {
+      a.in[i] = cur[i];
+      a.out[i] = dst_base + (size_t)i * dst_sz;
+    }
+    dim3 grid(blocks_for(a.pairs, T), T);
+    if ((size_t)grid.x * grid.y * (NP + 1) > c->partial_elems) return B200_ERR_NOMEM;
+    prof_begin(c, round);
+    if (round == 0) {
+      if (NP == 1) sc_eval_round_kernel<1, false><<<grid, SC_THREADS, 0, s>>>(a);
+      else sc_eval_round_kernel<2, false><<<grid, SC_THREADS, 0, s>>>(a);
+    } else {
+      if (NP == 1) sc_eval_round_kernel<1, true><<<grid, SC_THREADS, 0, s>>>(a);
+      else sc_eval_round_kernel<2, true><<<grid, SC_THREADS, 0, s>>>(a);
+      for (int i = 0; i <= ntab; ++i) cur[i] = (i < ntab) ? a.out[i] : a.eq_out;
+    }
+    prof_end(c);
+    count_launch(c);
+  }
+  // final bind -> evals (eq excluded: ProverState::into_evals returns the polys only, classic.rs:143-149)
+  const Fr** d_ptrs = nullptr;
+  CUDA_TRY(cudaMallocAsync(&d_ptrs, ntab * sizeof(Fr*), s));
+  CUDA_TRY(cudaMemcpyAsync(d_ptrs, cur, ntab * sizeof(Fr*), cudaMemcpyHostToDevice, s));
+  sc_final_bind_kernel<<<(ntab + 63) / 64, 64, 0, s>>>(d_ptrs, ntab, c->d_sc, job.evals_out);
+  count_launch(c);
+  CUDA_TRY(cudaFreeAsync(d_ptrs, s));
+  CUDA_TRY(cudaFreeAsync(eq0, s));
+  CUDA_TRY(cudaFreeAsync(bufA, s));
+  CUDA_TRY(cudaFreeAsync(bufB, s));
+  CUDA_TRY(cudaGetLastError());
+  return B200_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// CoefficientsProver: per product k, c0 = Σ l0*r0, c2 = Σ (l1-l0)(r1-r0) with l = eq_k, r = P_k;
+// message (c0, c1, c2) with c1 = sum - 2 c0 - c2 (coeff.rs:136-149); next claim by Horner (:36-38).
+// ---------------------------------------------------------------------------------------------
+struct ScCoeffArgs {
+  const Fr* eq_in[SC_MAX_TERMS];
+  Fr* eq_out[SC_MAX_TERMS];
+  const Fr* in[SC_MAX_TERMS];
+  Fr* out[SC_MAX_TERMS];
+  const Fr* scalars;
+  ScState* st;
+  Fr* partial;
+  Transcript* tr;
+  Fr* challenges_out;
+  uint32_t pairs;
+  int round;
+};
+
+template <bool BIND>
+__global__ void __launch_bounds__(SC_THREADS) sc_coeff_round_kernel(ScCoeffArgs a) {
+  __shared__ Fr smem[(SC_THREADS / 32) * 2];
+  const int k = blockIdx.y;
+  Fr acc[2] = {fe_zero<FrP>(), fe_zero<FrP>()};
+  Fr r = fe_zero<FrP>();
+  if (BIND) r = fe_ld(&a.st->r);
+  const Fr* __restrict__ eq_in = a.eq_in[k];
+  Fr* __restrict__ eq_out = a.eq_out[k];
+  const Fr* __restrict__ in = a.in[k];
+  Fr* __restrict__ out = a.out[k];
+  for (uint32_t b = blockIdx.x * blockDim.x + threadIdx.x; b < a.pairs; b += gridDim.x * blockDim.x) {
+    Fr l0, l1, r0, r1;
+    load_pair<BIND>(eq_in, eq_out, b, r, true, l0, l1);
+    load_pair<BIND>(in, out, b, r, true, r0, r1);
+    acc[0] = acc[0] + l0 * r0;
+    acc[1] = acc[1] + (l1 - l0) * (r1 - r0);
+  }
+  block_reduce_fr<2>(acc, smem);
+  if (threadIdx.x == 0) {
+    const Fr w = fe_ld(a.scalars + k);
+    Fr* dst = a.partial + ((size_t)k * gridDim.x + blockIdx.x) * 2;
+    fe_st(dst, acc[0] * w);
+    fe_st(dst + 1, acc[1] * w);
+  }
+  if (!last_cta_ticket(&a.st->counter)) return;
+  const uint32_t nparts = gridDim.x * gridDim.y;
+  acc[0] = fe_zero<FrP>();
+  acc[1] = fe_zero<FrP>();
+  for (uint32_t i = threadIdx.x; i < nparts; i += blockDim.x) {
+    acc[0] = acc[0] + fr_ld_cg(a.partial + (size_t)i * 2);
+    acc[1] = acc[1] + fr_ld_cg(a.partial + (size_t)i * 2 + 1);
+  }
+  block_reduce_fr<2>(acc, smem);
+  if (threadIdx.x == 0) {
+    const Fr claim = fe_ld(&a.st->claim);
+    const Fr c0 = acc[0], c2 = acc[1];
+    const Fr c1 = claim - (c0 + c0 + c2);
+    tr_write_fe(a.tr, c0);
+    tr_write_fe(a.tr, c1);
+    tr_write_fe(a.tr, c2);
+    const Fr ch = tr_squeeze(a.tr);
+    fe_st(a.challenges_out + a.round, ch);
+    fe_st(&a.st->r, ch);
+    fe_st(&a.st->claim, (c2 * ch + c1) * ch + c0);
+  }
+}
+
+int sumcheck_prove_coeffs(Ctx* c, const ScCoeffJob& job) {
+  const int n = job.num_vars, K = job.K;
+  if (n < 1 || n > 30 || K < 1 || K > SC_MAX_TERMS) return B200_ERR_ARG;
+  cudaStream_t s = c->stream;
+  const size_t N = (size_t)1 << n;
+  const size_t szA = N / 2, szB = N / 4 ? N / 4 : 1;
+  Fr *eq0 = nullptr, *bufA = nullptr, *bufB = nullptr;
+  CUDA_TRY(cudaMallocAsync(&eq0, (size_t)K * N * sizeof(Fr), s));
+  CUDA_TRY(cudaMallocAsync(&bufA, (size_t)2 * K * szA * sizeof(Fr), s));
+  CUDA_TRY(cudaMallocAsync(&bufB, (size_t)2 * K * szB * sizeof(Fr), s));
+  for (int k = 0; k < K; ++k) {
+    int rc = eq_build(c, job.eq_points[k], n, eq0 + (size_t)k * N);
+    if (rc) return rc;
+  }
+  sc_init_kernel<<<1, 32, 0, s>>>(c->d_sc, job.claim);
+  count_launch(c);
+  ScCoeffArgs a;
+  a.scalars = job.scalars;
+  a.st = c->d_sc;
+  a.partial = c->d_partial;
+  a.tr = c->d_tr;
+  a.challenges_out = job.challenges_out;
+  const Fr* cur[2 * SC_MAX_TERMS];  // [k] poly, [K + k] eq
+  for (int k = 0; k < K; ++k) {
+    cur[k] = job.tables[k];
+    cur[K + k] = eq0 + (size_t)k * N;
+  }
+  for (int round = 0; round < n; ++round) {
+    a.round = round;
+    a.pairs = (uint32_t)(N >> (round + 1));
+    Fr* dst_base = (round & 1) ? bufA : bufB;
+    const size_t dst_sz = (round & 1) ? szA : szB;
+    for (int k = 0; k < K; ++k) {
+      a.in[k] = cur[k];
+      a.eq_in[k] = cur[K + k];
+      a.out[k] = dst_base + (size_t)k * dst_sz;
+      a.eq_out[k] = dst_base + (size_t)(K + k) * dst_sz;
+    }
+    dim3 grid(blocks_for(a.pairs, K), K);
+    if ((size_t)grid.x * grid.y * 2 > c->partial_elems) return B200_ERR_NOMEM;
+    if (round == 0) {
+      sc_coeff_round_kernel<false><<<grid, SC_THREADS, 0, s>>>(a);
+    } else {
+      sc_coeff_round_kernel<true><<<grid, SC_THREADS, 0, s>>>(a);
+      for (int k = 0; k < K; ++k) {
+        cur[k] = a.out[k];
+        cur[K + k] = a.eq_out[k];
+      }
+    }
+    count_launch(c);
+  }
+  const Fr** d_ptrs = nullptr;
+  CUDA_TRY(cudaMallocAsync(&d_ptrs, K * sizeof(Fr*), s));
+  CUDA_TRY(cudaMemcpyAsync(d_ptrs, cur, K * sizeof(Fr*), cudaMemcpyHostToDevice, s));
+  sc_final_bind_kernel<<<1, 64, 0, s>>>(d_ptrs, K, c->d_sc, job.evals_out);
+  count_launch(c);
+  CUDA_TRY(cudaFreeAsync(d_ptrs, s));
+  CUDA_TRY(cudaFreeAsync(eq0, s));
+  CUDA_TRY(cudaFreeAsync(bufA, s));
+  CUDA_TRY(cudaFreeAsync(bufB, s));
+  CUDA_TRY(cudaGetLastError());
+  return B200_OK;
+}
+
+}  // namespace b200

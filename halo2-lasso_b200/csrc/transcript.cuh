@@ -1,0 +1,156 @@
+// Device-resident Fiat-Shamir transcript: FiatShamirTranscript<Keccak256, Cursor<Vec<u8>>> of
+// pb/util/transcript.rs:99-238 (+ pb/util/hash.rs:19-21, pb/util/arithmetic.rs:150-152).
+//
+// B200 design point: the reference interleaves every prover step with a Keccak absorb/squeeze on
+// the CPU. Here the sponge state AND the proof byte stream live in HBM; the last CTA of each round
+// kernel absorbs the round message, squeezes the challenge and folds the claim, so a whole
+// sum-check (and the whole Lasso proof) is enqueued without a single host round trip.
+// All functions are single-thread code (one elected thread runs them).
+#pragma once
+#include "ff32.cuh"
+
+namespace b200 {
+
+struct Transcript {
+  uint64_t s[25];      // Keccak-f[1600] state
+  uint32_t pos;        // bytes absorbed into the current rate block (0..135)
+  uint32_t proof_len;  // bytes appended to the proof stream
+  uint32_t proof_cap;
+  uint32_t error;      // sticky: 1 = proof overflow, 2 = identity commitment (transcript.rs:174-179)
+  uint8_t* proof;      // device buffer
+};
+
+FF_HD uint64_t rotl64(uint64_t x, int n) { return (x << n) | (x >> (64 - n)); }
+
+FF_HD void keccak_f1600(uint64_t* s) {
+  const uint64_t RC[24] = {
+      0x0000000000000001ULL, 0x0000000000008082ULL, 0x800000000000808aULL, 0x8000000080008000ULL,
+      0x000000000000808bULL, 0x0000000080000001ULL, 0x8000000080008081ULL, 0x8000000000008009ULL,
+      0x000000000000008aULL, 0x0000000000000088ULL, 0x0000000080008009ULL, 0x000000008000000aULL,
+      0x000000008000808bULL, 0x800000000000008bULL, 0x8000000000008089ULL, 0x8000000000008003ULL,
+      0x8000000000008002ULL, 0x8000000000000080ULL, 0x000000000000800aULL, 0x800000008000000aULL,
+      0x8000000080008081ULL, 0x8000000000008080ULL, 0x0000000080000001ULL, 0x8000000080008008ULL};
+  uint64_t a[25];
+#pragma unroll
+  for (int i = 0; i < 25; ++i) a[i] = s[i];
+#pragma unroll 1
+  for (int round = 0; round < 24; ++round) {
+    uint64_t c0 = a[0] ^ a[5] ^ a[10] ^ a[15] ^ a[20];
+    uint64_t c1 = a[1] ^ a[6] ^ a[11] ^ a[16] ^ a[21];
+    uint64_t c2 = a[2] ^ a[7] ^ a[12] ^ a[17] ^ a[22];
+    uint64_t c3 = a[3] ^ a[8] ^ a[13] ^ a[18] ^ a[23];
+    uint64_t c4 = a[4] ^ a[9] ^ a[14] ^ a[19] ^ a[24];
+    uint64_t d0 = c4 ^ rotl64(c1, 1), d1 = c0 ^ rotl64(c2, 1), d2 = c1 ^ rotl64(c3, 1);
+    uint64_t d3 = c2 ^ rotl64(c4, 1), d4 = c3 ^ rotl64(c0, 1);
+#pragma unroll
+    for (int j = 0; j < 25; j += 5) {
+      a[j] ^= d0; a[j + 1] ^= d1; a[j + 2] ^= d2; a[j + 3] ^= d3; a[j + 4] ^= d4;
+    }
+    // rho + pi (explicit lane schedule: b[y, 2x+3y] = rot(a[x, y]))
+    uint64_t b[25];
+    b[0] = a[0];
+    b[10] = rotl64(a[1], 1);   b[20] = rotl64(a[2], 62);  b[5] = rotl64(a[3], 28);   b[15] = rotl64(a[4], 27);
+    b[16] = rotl64(a[5], 36);  b[1] = rotl64(a[6], 44);   b[11] = rotl64(a[7], 6);   b[21] = rotl64(a[8], 55);
+    b[6] = rotl64(a[9], 20);   b[7] = rotl64(a[10], 3);   b[17] = rotl64(a[11], 10); b[2] = rotl64(a[12], 43);
+    b[12] = rotl64(a[13], 25); b[22] = rotl64(a[14], 39); b[23] = rotl64(a[15], 41); b[8] = rotl64(a[16], 45);
+    b[18] = rotl64(a[17], 15); b[3] = rotl64(a[18], 21);  b[13] = rotl64(a[19], 8);  b[14] = rotl64(a[20], 18);
+    b[24] = rotl64(a[21], 2);  b[9] = rotl64(a[22], 61);  b[19] = rotl64(a[23], 56); b[4] = rotl64(a[24], 14);
+#pragma unroll
+    for (int j = 0; j < 25; j += 5) {
+      a[j] = b[j] ^ (~b[j + 1] & b[j + 2]);
+      a[j + 1] = b[j + 1] ^ (~b[j + 2] & b[j + 3]);
+      a[j + 2] = b[j + 2] ^ (~b[j + 3] & b[j + 4]);
+      a[j + 3] = b[j + 3] ^ (~b[j + 4] & b[j]);
+      a[j + 4] = b[j + 4] ^ (~b[j] & b[j + 1]);
+    }
+    a[0] ^= RC[round];
+  }
+#pragma unroll
+  for (int i = 0; i < 25; ++i) s[i] = a[i];
+}
+
+FF_HD void tr_init(Transcript* t, uint8_t* proof, uint32_t cap) {
+  for (int i = 0; i < 25; ++i) t->s[i] = 0;
+  t->pos = 0;
+  t->proof_len = 0;
+  t->proof_cap = cap;
+  t->error = 0;
+  t->proof = proof;
+}
+
+// absorb 32 little-endian bytes given as 8 u32 words (pos is always a multiple of 4 here because
+// every absorbed item is 32 bytes; the rate is 136 = 34 words)
+FF_HD void tr_absorb_words(Transcript* t, const uint32_t* w, int nwords) {
+  for (int i = 0; i < nwords; ++i) {
+    uint32_t p = t->pos;
+    t->s[p >> 3] ^= (uint64_t)w[i] << (8 * (p & 7));
+    p += 4;
+    if (p == 136) {
+      keccak_f1600(t->s);
+      p = 0;
+    }
+    t->pos = p;
+  }
+}
+
+// squeeze_challenge (transcript.rs:127-131): hash = finalize; reset; absorb(hash); int_LE(hash) mod r
+FF_HD Fr tr_squeeze(Transcript* t) {
+  uint32_t p = t->pos;
+  t->s[p >> 3] ^= (uint64_t)0x01 << (8 * (p & 7));
+  t->s[16] ^= 0x8000000000000000ULL;
+  keccak_f1600(t->s);
+  Fr h;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    h.v[2 * i] = (uint32_t)t->s[i];
+    h.v[2 * i + 1] = (uint32_t)(t->s[i] >> 32);
+  }
+  for (int i = 0; i < 25; ++i) t->s[i] = 0;
+  t->pos = 0;
+  tr_absorb_words(t, h.v, 8);
+  return fe_from_canonical<FrP>(h);
+}
+
+// append the byte-reversed (big-endian) canonical repr to the proof stream
+FF_HD void tr_stream_be(Transcript* t, const uint32_t* canon) {
+  if (t->proof_len + 32 > t->proof_cap) {
+    t->error |= 1;
+    return;
+  }
+  uint8_t* o = t->proof + t->proof_len;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    uint32_t w = canon[7 - i];
+    o[4 * i] = (uint8_t)(w >> 24);
+    o[4 * i + 1] = (uint8_t)(w >> 16);
+    o[4 * i + 2] = (uint8_t)(w >> 8);
+    o[4 * i + 3] = (uint8_t)w;
+  }
+  t->proof_len += 32;
+}
+
+// common_field_element (transcript.rs:133-136)
+FF_HD void tr_common_fe(Transcript* t, const Fr& fe) {
+  Fr c = fe_to_canonical<FrP>(fe);
+  tr_absorb_words(t, c.v, 8);
+}
+// write_field_element (transcript.rs:158-165)
+FF_HD void tr_write_fe(Transcript* t, const Fr& fe) {
+  Fr c = fe_to_canonical<FrP>(fe);
+  tr_absorb_words(t, c.v, 8);
+  tr_stream_be(t, c.v);
+}
+// write_commitment (transcript.rs:171-183, 216-227); (x, y) Montgomery Fq; identity -> error
+FF_HD void tr_write_commitment(Transcript* t, const Fq& x, const Fq& y) {
+  if (fe_is_zero<FqP>(x) && fe_is_zero<FqP>(y)) {
+    t->error |= 2;
+    return;
+  }
+  Fq cx = fe_to_canonical<FqP>(x), cy = fe_to_canonical<FqP>(y);
+  tr_absorb_words(t, cx.v, 8);
+  tr_absorb_words(t, cy.v, 8);
+  tr_stream_be(t, cx.v);
+  tr_stream_be(t, cy.v);
+}
+
+}  // namespace b200

@@ -1,0 +1,106 @@
+/* libb200lasso — C ABI of the B200-native Lasso / HyperPlonk hot path.
+ *
+ * The reference (plonkish_backend) is 100% Rust with no FFI layer; its seams are the
+ * generic traits cited next to each entry point below. A Rust shim binds these
+ * symbols with `extern "C"` and implements `SumCheck`, `PolynomialCommitmentScheme` and the
+ * transcript traits on top of them.
+ *
+ * Conventions
+ *  - b200_fr  : 32 bytes, BN254 scalar, Montgomery form, little-endian u64 limbs — the in-memory
+ *               layout of halo2_curves::bn256::Fr, so `&[Fr]` is passed as-is.
+ *  - b200_g1  : 64 bytes, affine (x, y), each coordinate an Fq in the same Montgomery layout
+ *               (halo2_curves::bn256::G1Affine); the identity is (0, 0).
+ *  - "dev" pointers are device buffers owned by the library (b200_poly_*); "host" pointers are
+ *    caller-owned. Nothing is retained after a call returns.
+ *  - Every function returns 0 on success or a B200_ERR_* code; there are no panics/exceptions
+ *    across the boundary. One host thread per context.
+ *  - The Fiat-Shamir transcript (Keccak-256, pb/util/transcript.rs:99-238) lives ON THE DEVICE inside
+ *    the context: provers append to it without host round trips; b200_transcript_* are the
+ *    FieldTranscript / TranscriptWrite operations for the host-side caller.
+ */
+#ifndef B200_LASSO_H
+#define B200_LASSO_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200_OK 0
+#define B200_ERR_CUDA 1       /* CUDA runtime failure (message on stderr) */
+#define B200_ERR_ARG 2        /* invalid argument -> Error::InvalidPcsParam / InvalidSumcheck */
+#define B200_ERR_TRANSCRIPT 3 /* identity commitment or proof overflow -> Error::Transcript */
+#define B200_ERR_NOMEM 4
+
+typedef struct b200_ctx b200_ctx;
+
+/* ---- context ----------------------------------------------------------------------------- */
+int b200_ctx_create(int device, b200_ctx** out);
+void b200_ctx_destroy(b200_ctx* ctx);
+int b200_sync(b200_ctx* ctx);
+/* kernels launched by this context since the last reset (bench "gpu_launches") */
+uint64_t b200_launch_count(b200_ctx* ctx, int reset);
+/* raw CUDA stream of the context (cudaStream_t), for event timing by the caller */
+void* b200_stream(b200_ctx* ctx);
+/* per-launch CUDA-event timing of the sum-check round kernels (the reference's `sum_check_prove_round-i`
+ * timers, classic.rs:226): enable, run a prove, then read (ms[i], round tag[i]) pairs */
+int b200_profile_enable(b200_ctx* ctx, int on);
+int b200_profile_read(b200_ctx* ctx, float* ms, int* tags, int cap, int* n);
+
+/* ---- device polynomials: MultilinearPolynomial<Fr>::evals (pb/poly/multilinear.rs:20-24) ---- */
+int b200_poly_alloc(b200_ctx* ctx, uint64_t len, void** dev);
+int b200_poly_upload(b200_ctx* ctx, const void* host_fr, uint64_t len, void** dev);
+int b200_poly_write(b200_ctx* ctx, void* dev, const void* host_fr, uint64_t len);
+int b200_poly_download(b200_ctx* ctx, const void* dev, uint64_t len, void* host_fr);
+int b200_poly_free(b200_ctx* ctx, void* dev);
+/* canonical 256-bit integers <-> Montgomery residues, on the device (to_mont != 0: into Montgomery) */
+int b200_fr_convert(b200_ctx* ctx, const void* dev_in, void* dev_out, uint64_t len, int to_mont);
+
+/* ---- transcript: FiatShamirTranscript<Keccak256, _> (pb/util/transcript.rs:99-238) ---------- */
+int b200_transcript_reset(b200_ctx* ctx);
+/* FieldTranscript::common_field_elements (:133-136) */
+int b200_transcript_common_field_elements(b200_ctx* ctx, const void* host_fr, int n);
+/* FieldTranscriptWrite::write_field_elements (:158-165) */
+int b200_transcript_write_field_elements(b200_ctx* ctx, const void* host_fr, int n);
+/* FieldTranscript::squeeze_challenges (:127-131) */
+int b200_transcript_squeeze_challenges(b200_ctx* ctx, int n, void* host_fr_out);
+/* TranscriptWrite::write_commitments (:216-227); B200_ERR_TRANSCRIPT for the identity (:174-179) */
+int b200_transcript_write_commitments(b200_ctx* ctx, const void* host_g1, int n);
+/* InMemoryTranscript::into_proof (:112-114): copies the stream, *len = its length */
+int b200_transcript_proof(b200_ctx* ctx, uint8_t* out, uint64_t cap, uint64_t* len);
+
+/* ---- MultilinearPolynomial (pb/poly/multilinear.rs) ---------------------------------------- */
+/* eq_xy (:91-127): dev_out[2^n] */
+int b200_eq_xy(b200_ctx* ctx, const void* host_y, int n, void* dev_out);
+/* fix_var (:179-183): dev_out[2^(n-1)] */
+int b200_fix_var(b200_ctx* ctx, const void* dev_in, int n, const void* host_r, void* dev_out);
+/* evaluate (:137-156) for `ntables` polynomials at one point */
+int b200_evaluate(b200_ctx* ctx, const void* const* dev_tables, int ntables, int n, const void* host_x,
+                  void* host_fr_out);
+
+/* ---- SumCheck::prove (pb/piop/sum_check.rs:39-58), ClassicSumCheck (classic.rs:208-240) ------ */
+/* EvaluationsProver (classic/eval.rs) for  F(x) = eq(x, y) * sum_t w[t] * prod_{k<np} P[t*np+k](x),
+ * np in {1, 2}, degree np+1. Writes num_vars * (np+2) field elements to the context transcript and
+ * squeezes num_vars challenges, exactly as the reference does for the same Expression.
+ * Outputs: challenges[num_vars], evals[nterms*np] (= ProverState::into_evals). Tables untouched. */
+int b200_sumcheck_prove_evals(b200_ctx* ctx, int num_vars, int nterms, int np,
+                              const void* const* dev_tables, const void* host_weights,
+                              const void* host_y, const void* host_sum, void* host_challenges_out,
+                              void* host_evals_out);
+/* same, tables in HOST memory (uploaded inside the call): the end-to-end entry a Rust caller holding
+ * `Vec<Fr>` uses */
+int b200_sumcheck_prove_evals_host(b200_ctx* ctx, int num_vars, int nterms, int np,
+                                   const void* const* host_tables, const void* host_weights,
+                                   const void* host_y, const void* host_sum,
+                                   void* host_challenges_out, void* host_evals_out);
+/* CoefficientsProver (classic/coeff.rs) for  F(x) = sum_k s[k] * eq(x, y_k) * P_k(x)  (degree 2).
+ * host_ys: nprods * num_vars elements. */
+int b200_sumcheck_prove_coeffs(b200_ctx* ctx, int num_vars, int nprods, const void* const* dev_tables,
+                               const void* host_scalars, const void* host_ys, const void* host_sum,
+                               void* host_challenges_out, void* host_evals_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
