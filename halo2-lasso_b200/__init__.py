@@ -274,3 +274,56 @@ def declared_symbols():
     src = open(HEADER_PATH).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
     return sorted(set(re.findall(r"\b(b200_[a-z0-9_]+)\s*\(", src)))
+
+
+def variable_base_msm(ctx, scalars, bases):
+    """`variable_base_msm(scalars, bases)` (pb/util/arithmetic/msm.rs:84-87) with host inputs."""
+    scalars = _fr(scalars).reshape(-1, 4)
+    bases = np.ascontiguousarray(bases, dtype=np.uint64).reshape(-1, 8)
+    assert scalars.shape[0] == bases.shape[0]
+    out = np.zeros(8, dtype=np.uint64)
+    _chk(lib().b200_variable_base_msm(ctx.h, _p(scalars), _p(bases), C.c_uint64(scalars.shape[0]), _p(out)), "msm")
+    return out
+
+
+class MultilinearKzg:
+    """`MultilinearKzg<Bn256>` prover side (pb/pcs/multilinear/kzg.rs): the ProverParam (eqs levels) is
+    uploaded once; commit / open / batch_open run on the device and append to the context transcript."""
+
+    def __init__(self, ctx, eqs_levels):
+        """eqs_levels[k]: (2^k, 8) uint64 affine points = MultilinearKzgProverParams::eqs[k]."""
+        self.ctx = ctx
+        self.num_vars = len(eqs_levels) - 1
+        for k, lv in enumerate(eqs_levels):
+            lv = np.ascontiguousarray(lv, dtype=np.uint64).reshape(-1, 8)
+            assert lv.shape[0] == 1 << k
+            _chk(lib().b200_kzg_srs_upload(ctx.h, C.c_int(k), _p(lv)), "srs_upload")
+
+    def batch_commit(self, polys, write=False):
+        ptrs = (C.c_void_p * len(polys))(*[p.dev for p in polys])
+        nv = (C.c_int * len(polys))(*[p.num_vars for p in polys])
+        out = np.zeros((len(polys), 8), dtype=np.uint64)
+        _chk(lib().b200_kzg_batch_commit(self.ctx.h, ptrs, nv, C.c_int(len(polys)), C.c_int(int(write)), _p(out)),
+             "batch_commit")
+        return out
+
+    def commit(self, poly):
+        return self.batch_commit([poly])[0]
+
+    def batch_commit_and_write(self, polys):
+        return self.batch_commit(polys, write=True)
+
+    def open(self, poly, point):
+        point = _fr(point).reshape(-1, 4)
+        _chk(lib().b200_kzg_open(self.ctx.h, poly.dev, C.c_int(point.shape[0]), _p(point)), "open")
+
+    def batch_open(self, polys, points, evals):
+        """evals: list of (poly idx, point idx, value) — `Evaluation` (pb/pcs.rs:132-155)."""
+        points = _fr(np.stack(points))
+        nv = points.shape[1]
+        ptrs = (C.c_void_p * len(polys))(*[p.dev for p in polys])
+        ep = (C.c_int * len(evals))(*[e[0] for e in evals])
+        ept = (C.c_int * len(evals))(*[e[1] for e in evals])
+        ev = _fr(np.stack([e[2] for e in evals]))
+        _chk(lib().b200_kzg_batch_open(self.ctx.h, C.c_int(nv), ptrs, C.c_int(len(polys)), _p(points),
+                                       C.c_int(points.shape[0]), ep, ept, _p(ev), C.c_int(len(evals))), "batch_open")

@@ -10,10 +10,6 @@
 
 using namespace b200;
 
-struct b200_ctx {
-  Ctx c;
-};
-
 static const uint32_t PROOF_CAP = 8u << 20;
 static const size_t PARTIAL_ELEMS = 1u << 16;
 

@@ -1,0 +1,110 @@
+// extern "C" boundary, part 2: MSM and MultilinearKzg (include/b200_lasso.h).
+#include <vector>
+
+#include "../../include/b200_lasso.h"
+#include "internal.h"
+
+using namespace b200;
+
+extern "C" {
+
+int b200_variable_base_msm(b200_ctx* h, const void* host_scalars_fr, const void* host_bases_g1, uint64_t n,
+                           void* host_out_g1) {
+  Ctx* c = &h->c;
+  if (n == 0) {  // empty sum = identity, as variable_base_msm returns
+    memset(host_out_g1, 0, sizeof(G1Aff));
+    return B200_OK;
+  }
+  cudaStream_t s = c->stream;
+  Fr* ds = nullptr;
+  G1Aff *db = nullptr, *dout = nullptr;
+  CUDA_TRY(cudaMallocAsync(&ds, n * sizeof(Fr), s));
+  CUDA_TRY(cudaMallocAsync(&db, n * sizeof(G1Aff), s));
+  CUDA_TRY(cudaMallocAsync(&dout, sizeof(G1Aff), s));
+  CUDA_TRY(cudaMemcpyAsync(ds, host_scalars_fr, n * sizeof(Fr), cudaMemcpyHostToDevice, s));
+  CUDA_TRY(cudaMemcpyAsync(db, host_bases_g1, n * sizeof(G1Aff), cudaMemcpyHostToDevice, s));
+  MsmJob job{ds, db, n, MSM_FR_MONT, 254};
+  int rc = msm_batch(c, &job, 1, dout);
+  if (rc) return rc;
+  CUDA_TRY(cudaMemcpyAsync(host_out_g1, dout, sizeof(G1Aff), cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  CUDA_TRY(cudaFreeAsync(ds, s));
+  CUDA_TRY(cudaFreeAsync(db, s));
+  CUDA_TRY(cudaFreeAsync(dout, s));
+  return B200_OK;
+}
+
+int b200_kzg_srs_upload(b200_ctx* h, int level, const void* host_g1) {
+  Ctx* c = &h->c;
+  if (level < 0 || level > 30 || level != (int)c->srs.size()) return B200_ERR_ARG;
+  G1Aff* d = nullptr;
+  const size_t bytes = ((size_t)1 << level) * sizeof(G1Aff);
+  CUDA_TRY(cudaMalloc(&d, bytes));
+  CUDA_TRY(cudaMemcpy(d, host_g1, bytes, cudaMemcpyHostToDevice));
+  c->srs.push_back(d);
+  return B200_OK;
+}
+
+int b200_kzg_batch_commit(b200_ctx* h, const void* const* dev_polys, const int* num_vars, int npolys,
+                          int write_transcript, void* host_out_g1) {
+  Ctx* c = &h->c;
+  if (npolys < 1 || npolys > 64) return B200_ERR_ARG;
+  std::vector<MsmJob> jobs(npolys);
+  for (int i = 0; i < npolys; ++i) {
+    if (num_vars[i] < 0 || num_vars[i] >= (int)c->srs.size()) return B200_ERR_ARG;  // "Too many variates"
+    jobs[i] = MsmJob{dev_polys[i], c->srs[num_vars[i]], (uint64_t)1 << num_vars[i], MSM_FR_MONT, 254};
+  }
+  G1Aff* dout = nullptr;
+  CUDA_TRY(cudaMallocAsync(&dout, npolys * sizeof(G1Aff), c->stream));
+  int rc = kzg_commit_batch(c, jobs.data(), npolys, write_transcript != 0, dout);
+  if (rc) return rc;
+  CUDA_TRY(cudaMemcpyAsync(host_out_g1, dout, npolys * sizeof(G1Aff), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  CUDA_TRY(cudaFreeAsync(dout, c->stream));
+  if (write_transcript) {
+    Transcript t;
+    CUDA_TRY(cudaMemcpy(&t, c->d_tr, sizeof(t), cudaMemcpyDeviceToHost));
+    if (t.error) return B200_ERR_TRANSCRIPT;
+  }
+  return B200_OK;
+}
+
+int b200_kzg_open(b200_ctx* h, const void* dev_poly, int num_vars, const void* host_point) {
+  Ctx* c = &h->c;
+  if (num_vars < 1 || num_vars > 30) return B200_ERR_ARG;
+  Fr* dp = nullptr;
+  CUDA_TRY(cudaMallocAsync(&dp, num_vars * sizeof(Fr), c->stream));
+  CUDA_TRY(cudaMemcpyAsync(dp, host_point, num_vars * sizeof(Fr), cudaMemcpyHostToDevice, c->stream));
+  int rc = kzg_open(c, (const Fr*)dev_poly, num_vars, dp);
+  CUDA_TRY(cudaFreeAsync(dp, c->stream));
+  return rc;
+}
+
+int b200_kzg_batch_open(b200_ctx* h, int num_vars, const void* const* dev_polys, int npolys,
+                        const void* host_points, int npoints, const int* ev_poly, const int* ev_point,
+                        const void* host_ev_values, int nevals) {
+  Ctx* c = &h->c;
+  if (num_vars < 1 || num_vars > 30 || npolys < 1 || npoints < 1 || nevals < 2) return B200_ERR_ARG;
+  for (int k = 0; k < nevals; ++k)
+    if (ev_poly[k] < 0 || ev_poly[k] >= npolys || ev_point[k] < 0 || ev_point[k] >= npoints) return B200_ERR_ARG;
+  Fr* d = nullptr;
+  const size_t npt = (size_t)npoints * num_vars;
+  CUDA_TRY(cudaMallocAsync(&d, (npt + nevals) * sizeof(Fr), c->stream));
+  CUDA_TRY(cudaMemcpyAsync(d, host_points, npt * sizeof(Fr), cudaMemcpyHostToDevice, c->stream));
+  CUDA_TRY(cudaMemcpyAsync(d + npt, host_ev_values, nevals * sizeof(Fr), cudaMemcpyHostToDevice, c->stream));
+  BatchOpenJob job;
+  job.num_vars = num_vars;
+  job.npolys = npolys;
+  job.npoints = npoints;
+  job.nevals = nevals;
+  job.polys = (const Fr* const*)dev_polys;
+  job.points = d;
+  job.ev_poly = ev_poly;
+  job.ev_point = ev_point;
+  job.ev_values = d + npt;
+  int rc = kzg_batch_open(c, job);
+  CUDA_TRY(cudaFreeAsync(d, c->stream));
+  return rc;
+}
+
+}  // extern "C"

@@ -8,6 +8,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "g1.cuh"
 
 namespace b200 {
 
@@ -16,13 +17,6 @@ struct ScState {
   Fr r;      // challenge of the previous round
   unsigned int counter;
   unsigned int pad[7];
-};
-
-struct G1Aff {  // 64 bytes, (x, y) Montgomery; identity = (0, 0)
-  Fq x, y;
-};
-struct G1Xyzz {  // x = X/ZZ, y = Y/ZZZ; identity has ZZ == 0
-  Fq x, y, zz, zzz;
 };
 
 struct Ctx {
@@ -87,6 +81,30 @@ int transcript_write_points(Ctx* c, const G1Aff* d_pts, int n);
 
 enum { TR_COMMON = 0, TR_WRITE = 1, TR_SQUEEZE = 2 };
 
+// msm.cu — variable_base_msm (pb/util/arithmetic/msm.rs:84-181), batched
+enum MsmScalarKind { MSM_FR_MONT = 0, MSM_FR_CANON = 1, MSM_U64 = 2, MSM_U32 = 3 };
+struct MsmJob {
+  const void* scalars;  // device
+  const G1Aff* bases;   // device
+  uint64_t n;
+  int kind;             // MsmScalarKind
+  int bits;             // significant bits of the largest scalar (254 for arbitrary Fr)
+};
+int msm_batch(Ctx* c, const MsmJob* jobs, int J, G1Aff* d_out);
+
+// kzg.cu — MultilinearKzg (pb/pcs/multilinear/kzg.rs) + additive::batch_open (pb/pcs/multilinear.rs:134-235)
+struct BatchOpenJob {
+  int num_vars, npolys, npoints, nevals;
+  const Fr* const* polys;  // host array of device pointers
+  const Fr* points;        // device, npoints * num_vars
+  const int* ev_poly;      // host
+  const int* ev_point;     // host
+  const Fr* ev_values;     // device, nevals
+};
+int kzg_commit_batch(Ctx* c, const MsmJob* jobs, int J, bool write_transcript, G1Aff* d_out);
+int kzg_open(Ctx* c, const Fr* d_poly, int n, const Fr* d_point);
+int kzg_batch_open(Ctx* c, const BatchOpenJob& job);
+
 inline void count_launch(Ctx* c, int n = 1) { c->launches += n; }
 inline void prof_begin(Ctx* c, int tag) {
   if (!c->profile) return;
@@ -104,3 +122,8 @@ inline void prof_end(Ctx* c) {
 }
 
 }  // namespace b200
+
+// opaque handle of include/b200_lasso.h
+struct b200_ctx {
+  b200::Ctx c;
+};

@@ -1,0 +1,149 @@
+// MultilinearKzg on the GPU (pb/pcs/multilinear/kzg.rs:252-315) and the additive batch opening
+// (pb/pcs/multilinear.rs:72-107 quotients, :134-235 batch_open). Every step stays on the device:
+// challenges are squeezed into device memory, merged polynomials / g' are built by the linear-
+// combination kernel, the degree-2 CoefficientsProver sum-check runs with the fused round kernel,
+// and all n quotient commitments of an opening go through ONE batched MSM.
+#include "internal.h"
+
+namespace b200 {
+
+int kzg_commit_batch(Ctx* c, const MsmJob* jobs, int J, bool write_transcript, G1Aff* d_out) {
+  int rc = msm_batch(c, jobs, J, d_out);
+  if (rc) return rc;
+  if (write_transcript) return transcript_write_points(c, d_out, J);
+  return B200_OK;
+}
+
+// kzg.rs:276-302 (sanity-check off): quotients top variable first, commit q_i with eqs[i], write them
+int kzg_open(Ctx* c, const Fr* d_poly, int n, const Fr* d_point) {
+  if (n < 1 || n > 30 || (int)c->srs.size() <= n - 1) return B200_ERR_ARG;
+  cudaStream_t s = c->stream;
+  const size_t N = (size_t)1 << n;
+  Fr *rem = nullptr, *q = nullptr;
+  G1Aff* comms = nullptr;
+  CUDA_TRY(cudaMallocAsync(&rem, N * sizeof(Fr), s));
+  CUDA_TRY(cudaMallocAsync(&q, N * sizeof(Fr), s));  // level nv lives at [2^nv, 2^(nv+1))
+  CUDA_TRY(cudaMallocAsync(&comms, n * sizeof(G1Aff), s));
+  CUDA_TRY(cudaMemcpyAsync(rem, d_poly, N * sizeof(Fr), cudaMemcpyDeviceToDevice, s));
+  MsmJob jobs[32];
+  for (int nv = n - 1; nv >= 0; --nv) {
+    const size_t half = (size_t)1 << nv;
+    int rc = quotient_step(c, rem, half, d_point + nv, q + half);
+    if (rc) return rc;
+    jobs[nv] = MsmJob{q + half, c->srs[nv], half, MSM_FR_MONT, 254};
+  }
+  int rc = kzg_commit_batch(c, jobs, n, true, comms);
+  if (rc) return rc;
+  CUDA_TRY(cudaFreeAsync(rem, s));
+  CUDA_TRY(cudaFreeAsync(q, s));
+  CUDA_TRY(cudaFreeAsync(comms, s));
+  return B200_OK;
+}
+
+__global__ void gather_fr_kernel(const Fr* src, const int* idx, int n, Fr* dst) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) fe_st(dst + i, fe_ld(src + idx[i]));
+}
+// out = Σ_k a[k] * b[k]  (tiny, single thread)
+__global__ void dot_small_kernel(const Fr* a, const Fr* b, int n, Fr* out) {
+  if (threadIdx.x || blockIdx.x) return;
+  Fr acc = fe_zero<FrP>();
+  for (int k = 0; k < n; ++k) acc = acc + fe_ld(a + k) * fe_ld(b + k);
+  fe_st(out, acc);
+}
+__global__ void fill_one_kernel(Fr* out, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) fe_st(out + i, fe_one<FrP>());
+}
+
+int kzg_batch_open(Ctx* c, const BatchOpenJob& job) {
+  const int n = job.num_vars, P = job.npoints, E = job.nevals;
+  if (n < 1 || n > 30 || P < 1 || P > SC_MAX_TERMS || E < 2 || E > SC_MAX_TABLES) return B200_ERR_ARG;
+  cudaStream_t s = c->stream;
+  const size_t N = (size_t)1 << n;
+  int ell = 0;
+  while ((1 << ell) < E) ++ell;
+  // scalar arena: t[ell] | eq_xt[2^ell] | gathered[E] | tilde | ones[P] | challenges[n] | evals[P] | eqev[P]
+  const size_t arena_n = (size_t)ell + ((size_t)1 << ell) + E + 1 + P + n + P + P;
+  Fr* arena = nullptr;
+  CUDA_TRY(cudaMallocAsync(&arena, arena_n * sizeof(Fr), s));
+  Fr* t = arena;
+  Fr* eq_xt = t + ell;
+  Fr* gathered = eq_xt + ((size_t)1 << ell);
+  Fr* tilde = gathered + E;
+  Fr* ones = tilde + 1;
+  Fr* challenges = ones + P;
+  Fr* sc_evals = challenges + n;
+  Fr* eqev = sc_evals + P;
+  int rc = transcript_op(c, TR_SQUEEZE, nullptr, t, ell);
+  if (rc) return rc;
+  rc = eq_build(c, t, ell, eq_xt);
+  if (rc) return rc;
+
+  // merged_i = Σ_{k : point(k) = i} eq_xt[k] * poly(k)      (pb/pcs/multilinear.rs:155-170)
+  Fr* merged = nullptr;
+  CUDA_TRY(cudaMallocAsync(&merged, (size_t)P * N * sizeof(Fr), s));
+  int h_idx[SC_MAX_TABLES];
+  int* d_idx = nullptr;
+  CUDA_TRY(cudaMallocAsync(&d_idx, E * sizeof(int), s));
+  int pos = 0, start[SC_MAX_TERMS + 1];
+  const Fr* tabs[SC_MAX_TABLES];
+  std::vector<std::vector<const Fr*>> per_point(P);
+  for (int i = 0; i < P; ++i) {
+    start[i] = pos;
+    for (int k = 0; k < E; ++k)
+      if (job.ev_point[k] == i) {
+        h_idx[pos++] = k;
+        per_point[i].push_back(job.polys[job.ev_poly[k]]);
+      }
+    if (pos == start[i]) return B200_ERR_ARG;  // a point nobody is evaluated at
+  }
+  start[P] = pos;
+  CUDA_TRY(cudaMemcpyAsync(d_idx, h_idx, E * sizeof(int), cudaMemcpyHostToDevice, s));
+  gather_fr_kernel<<<1, 64, 0, s>>>(eq_xt, d_idx, E, gathered);
+  count_launch(c);
+  for (int i = 0; i < P; ++i) {
+    const int k = start[i + 1] - start[i];
+    for (int j = 0; j < k; ++j) tabs[j] = per_point[i][j];
+    rc = fr_lincomb(c, tabs, k, gathered + start[i], N, merged + (size_t)i * N);
+    if (rc) return rc;
+  }
+  // tilde_gs_sum = <evals.value, eq_xt[..E]>   (:195-196)
+  dot_small_kernel<<<1, 32, 0, s>>>(job.ev_values, eq_xt, E, tilde);
+  fill_one_kernel<<<1, 64, 0, s>>>(ones, P);
+  count_launch(c, 2);
+
+  ScCoeffJob sj;
+  sj.num_vars = n;
+  sj.K = P;
+  for (int i = 0; i < P; ++i) {
+    sj.tables[i] = merged + (size_t)i * N;
+    sj.eq_points[i] = job.points + (size_t)i * n;
+  }
+  sj.scalars = ones;
+  sj.claim = tilde;
+  sj.challenges_out = challenges;
+  sj.evals_out = sc_evals;
+  rc = sumcheck_prove_coeffs(c, sj);
+  if (rc) return rc;
+
+  // g' = Σ_i eq(challenges, point_i) * merged_i      (:203-212)
+  for (int i = 0; i < P; ++i) {
+    rc = eq_xy_eval_dev(c, challenges, job.points + (size_t)i * n, n, eqev + i);
+    if (rc) return rc;
+    tabs[i] = merged + (size_t)i * N;
+  }
+  Fr* gprime = nullptr;
+  CUDA_TRY(cudaMallocAsync(&gprime, N * sizeof(Fr), s));
+  rc = fr_lincomb(c, tabs, P, eqev, N, gprime);
+  if (rc) return rc;
+  rc = kzg_open(c, gprime, n, challenges);
+  if (rc) return rc;
+  CUDA_TRY(cudaFreeAsync(gprime, s));
+  CUDA_TRY(cudaFreeAsync(merged, s));
+  CUDA_TRY(cudaFreeAsync(d_idx, s));
+  CUDA_TRY(cudaFreeAsync(arena, s));
+  return B200_OK;
+}
+
+}  // namespace b200

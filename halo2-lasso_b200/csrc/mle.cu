@@ -245,11 +245,13 @@ int eq_xy_eval_dev(Ctx* c, const Fr* d_x, const Fr* d_y, int n, Fr* d_out) {
 
 __global__ void transcript_kernel(Transcript* tr, int op, const Fr* in, Fr* out, int n) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  Transcript lt = *tr;
   for (int i = 0; i < n; ++i) {
-    if (op == TR_COMMON) tr_common_fe(tr, fe_ld(in + i));
-    else if (op == TR_WRITE) tr_write_fe(tr, fe_ld(in + i));
-    else fe_st(out + i, tr_squeeze(tr));
+    if (op == TR_COMMON) tr_common_fe(&lt, fe_ld(in + i));
+    else if (op == TR_WRITE) tr_write_fe(&lt, fe_ld(in + i));
+    else fe_st(out + i, tr_squeeze(&lt));
   }
+  *tr = lt;
 }
 int transcript_op(Ctx* c, int op, const Fr* d_in, Fr* d_out, int n) {
   if (n <= 0) return B200_OK;
@@ -261,10 +263,12 @@ int transcript_op(Ctx* c, int op, const Fr* d_in, Fr* d_out, int n) {
 
 __global__ void transcript_points_kernel(Transcript* tr, const G1Aff* pts, int n) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  Transcript lt = *tr;
   for (int i = 0; i < n; ++i) {
     const Fq x = fe_ld(&pts[i].x), y = fe_ld(&pts[i].y);
-    tr_write_commitment(tr, x, y);
+    tr_write_commitment(&lt, x, y);
   }
+  *tr = lt;
 }
 int transcript_write_points(Ctx* c, const G1Aff* d_pts, int n) {
   if (n <= 0) return B200_OK;

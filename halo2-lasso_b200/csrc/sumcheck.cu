@@ -128,8 +128,10 @@ __global__ void __launch_bounds__(SC_THREADS) sc_eval_round_kernel(ScEvalArgs a)
     for (int x = 0; x < D; ++x) ev[x + 1] = acc[x];
     const Fr claim = fe_ld(&a.st->claim);
     ev[0] = claim - ev[1];
-    for (int x = 0; x <= D; ++x) tr_write_fe(a.tr, ev[x]);
-    const Fr ch = tr_squeeze(a.tr);
+    Transcript lt = *a.tr;  // work on a thread-local copy of the sponge: no global round trips per word
+    for (int x = 0; x <= D; ++x) tr_write_fe(&lt, ev[x]);
+    const Fr ch = tr_squeeze(&lt);
+    *a.tr = lt;
     fe_st(a.challenges_out + a.round, ch);
     fe_st(&a.st->r, ch);
     fe_st(&a.st->claim, interpolate_at(ev, D, ch, a.bary));
@@ -282,10 +284,12 @@ __global__ void __launch_bounds__(SC_THREADS) sc_coeff_round_kernel(ScCoeffArgs 
     const Fr claim = fe_ld(&a.st->claim);
     const Fr c0 = acc[0], c2 = acc[1];
     const Fr c1 = claim - (c0 + c0 + c2);
-    tr_write_fe(a.tr, c0);
-    tr_write_fe(a.tr, c1);
-    tr_write_fe(a.tr, c2);
-    const Fr ch = tr_squeeze(a.tr);
+    Transcript lt = *a.tr;
+    tr_write_fe(&lt, c0);
+    tr_write_fe(&lt, c1);
+    tr_write_fe(&lt, c2);
+    const Fr ch = tr_squeeze(&lt);
+    *a.tr = lt;
     fe_st(a.challenges_out + a.round, ch);
     fe_st(&a.st->r, ch);
     fe_st(&a.st->claim, (c2 * ch + c1) * ch + c0);

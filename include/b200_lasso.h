@@ -100,6 +100,28 @@ int b200_sumcheck_prove_coeffs(b200_ctx* ctx, int num_vars, int nprods, const vo
                                const void* host_scalars, const void* host_ys, const void* host_sum,
                                void* host_challenges_out, void* host_evals_out);
 
+/* ---- variable_base_msm (pb/util/arithmetic/msm.rs:84-115) ------------------------------------- */
+/* Σ scalars[i] * bases[i] with HOST inputs (the free function's signature); out = affine point.
+ * An identity result is returned as (0, 0). */
+int b200_variable_base_msm(b200_ctx* ctx, const void* host_scalars_fr, const void* host_bases_g1,
+                           uint64_t n, void* host_out_g1);
+
+/* ---- MultilinearKzg (pb/pcs/multilinear/kzg.rs) --------------------------------------------------- */
+/* ProverParam: upload eqs[level] (2^level affine points, kzg.rs:36-53, :230-245 trim). Levels must be
+ * uploaded in increasing order starting from 0. */
+int b200_kzg_srs_upload(b200_ctx* ctx, int level, const void* host_g1);
+/* batch_commit (kzg.rs:259-274): one MSM per polynomial against eqs[num_vars[i]]; out[npolys] affine.
+ * write_transcript != 0 also performs write_commitments (Pcs::batch_commit_and_write, pcs.rs:62-75). */
+int b200_kzg_batch_commit(b200_ctx* ctx, const void* const* dev_polys, const int* num_vars, int npolys,
+                          int write_transcript, void* host_out_g1);
+/* open (kzg.rs:276-302): writes num_vars quotient commitments to the context transcript */
+int b200_kzg_open(b200_ctx* ctx, const void* dev_poly, int num_vars, const void* host_point);
+/* batch_open (kzg.rs:304-315 -> pb/pcs/multilinear.rs:134-235). host_points: npoints*num_vars elements;
+ * evaluation k = (ev_poly[k], ev_point[k], host_ev_values[k]) mirrors `Evaluation` (pcs.rs:132-155). */
+int b200_kzg_batch_open(b200_ctx* ctx, int num_vars, const void* const* dev_polys, int npolys,
+                        const void* host_points, int npoints, const int* ev_poly, const int* ev_point,
+                        const void* host_ev_values, int nevals);
+
 #ifdef __cplusplus
 }
 #endif

@@ -28,3 +28,19 @@ extern "C" int h32_transcript_run(const Fr* fes, int n, const Fq* pt_xy, uint8_t
   ch[2] = tr_squeeze(&t);
   return t.error ? -1 : (int)t.proof_len;
 }
+
+// G1 (csrc/g1.cuh) on the host: Σ k_i * P_i with small k via mul_small / add / add_affine paths.
+#include "../../halo2-lasso_b200/csrc/g1.cuh"
+extern "C" void h32_g1_lincomb(const G1Aff* pts, const int32_t* ks, int n, G1Aff* out) {
+  G1Xyzz acc = g1_identity();
+  for (int i = 0; i < n; ++i) {
+    int32_t k = ks[i];
+    if (k == 1 || k == -1) {
+      acc = g1_add_affine(acc, pts[i], k < 0);  // mixed path
+    } else {
+      G1Xyzz t = g1_mul_small(g1_from_affine(pts[i]), (uint32_t)(k < 0 ? -k : k));
+      acc = g1_add(acc, k < 0 ? g1_neg(t) : t);
+    }
+  }
+  *out = g1_to_affine(acc);
+}
