@@ -327,3 +327,44 @@ class MultilinearKzg:
         ev = _fr(np.stack([e[2] for e in evals]))
         _chk(lib().b200_kzg_batch_open(self.ctx.h, C.c_int(nv), ptrs, C.c_int(len(polys)), _p(points),
                                        C.c_int(points.shape[0]), ep, ept, _p(ev), C.c_int(len(evals))), "batch_open")
+
+
+TABLE_RANGE, TABLE_AND, TABLE_XOR = 0, 1, 2
+
+
+class LassoProver:
+    """Lasso / Surge lookup prover (north_star; DESIGN.md "Lasso protocol"). `table` mirrors a
+    `DecomposableTable`: kind (range / and / xor) + number of 16-bit-addressed chunks."""
+
+    def __init__(self, ctx, kzg, kind, chunks):
+        self.ctx, self.kzg, self.kind, self.chunks = ctx, kzg, kind, chunks
+
+    def prove(self, xs, ys=None):
+        """Appends the whole proof for the 2^mu lookups to the context transcript."""
+        xs = np.ascontiguousarray(xs, dtype=np.uint64)
+        mu = int(xs.shape[0]).bit_length() - 1
+        assert xs.shape[0] == 1 << mu
+        if ys is not None:
+            ys = np.ascontiguousarray(ys, dtype=np.uint64)
+        _chk(lib().b200_lasso_prove(self.ctx.h, C.c_int(self.kind), C.c_int(self.chunks), C.c_int(mu), _p(xs),
+                                    _p(ys) if ys is not None else None), "lasso_prove")
+
+    def witness(self, xs, ys=None):
+        """(a | dim | E | read_ts) tables [1+3c, 2^mu, 4] and final_cts [c, 2^16, 4] as computed on the device."""
+        xs = np.ascontiguousarray(xs, dtype=np.uint64)
+        mu = int(xs.shape[0]).bit_length() - 1
+        if ys is not None:
+            ys = np.ascontiguousarray(ys, dtype=np.uint64)
+        c = self.chunks
+        mt, st = C.c_void_p(), C.c_void_p()
+        _chk(lib().b200_poly_alloc(self.ctx.h, C.c_uint64((1 + 3 * c) << mu), C.byref(mt)), "alloc")
+        _chk(lib().b200_poly_alloc(self.ctx.h, C.c_uint64(c << 16), C.byref(st)), "alloc")
+        _chk(lib().b200_lasso_witness(self.ctx.h, C.c_int(self.kind), C.c_int(c), C.c_int(mu), _p(xs),
+                                      _p(ys) if ys is not None else None, mt, st), "lasso_witness")
+        m_out = np.zeros((1 + 3 * c, 1 << mu, 4), dtype=np.uint64)
+        s_out = np.zeros((c, 1 << 16, 4), dtype=np.uint64)
+        _chk(lib().b200_poly_download(self.ctx.h, mt, C.c_uint64((1 + 3 * c) << mu), _p(m_out)), "download")
+        _chk(lib().b200_poly_download(self.ctx.h, st, C.c_uint64(c << 16), _p(s_out)), "download")
+        lib().b200_poly_free(self.ctx.h, mt)
+        lib().b200_poly_free(self.ctx.h, st)
+        return m_out, s_out

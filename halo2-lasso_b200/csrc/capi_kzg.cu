@@ -108,3 +108,55 @@ int b200_kzg_batch_open(b200_ctx* h, int num_vars, const void* const* dev_polys,
 }
 
 }  // extern "C"
+
+// ---- Lasso ------------------------------------------------------------------------------------
+extern "C" {
+
+static int upload_operands(Ctx* c, int mu, const uint64_t* host_xs, const uint64_t* host_ys, uint64_t** dx,
+                           uint64_t** dy) {
+  const size_t bytes = ((size_t)1 << mu) * 8;
+  *dy = nullptr;
+  CUDA_TRY(cudaMallocAsync(dx, bytes, c->stream));
+  CUDA_TRY(cudaMemcpyAsync(*dx, host_xs, bytes, cudaMemcpyHostToDevice, c->stream));
+  if (host_ys) {
+    CUDA_TRY(cudaMallocAsync(dy, bytes, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(*dy, host_ys, bytes, cudaMemcpyHostToDevice, c->stream));
+  }
+  return B200_OK;
+}
+
+int b200_lasso_prove_dev(b200_ctx* h, int kind, int chunks, int mu, const void* dev_xs, const void* dev_ys) {
+  if (kind != 0 && !dev_ys) return B200_ERR_ARG;
+  return lasso_prove(&h->c, kind, chunks, mu, (const uint64_t*)dev_xs, (const uint64_t*)dev_ys);
+}
+
+int b200_lasso_prove(b200_ctx* h, int kind, int chunks, int mu, const uint64_t* host_xs, const uint64_t* host_ys) {
+  Ctx* c = &h->c;
+  if (mu < 1 || mu > 26 || !host_xs || (kind != 0 && !host_ys)) return B200_ERR_ARG;
+  uint64_t *dx, *dy;
+  int rc = upload_operands(c, mu, host_xs, host_ys, &dx, &dy);
+  if (rc) return rc;
+  rc = lasso_prove(c, kind, chunks, mu, dx, dy);
+  CUDA_TRY(cudaFreeAsync(dx, c->stream));
+  if (dy) CUDA_TRY(cudaFreeAsync(dy, c->stream));
+  if (rc) return rc;
+  Transcript t;
+  CUDA_TRY(cudaMemcpyAsync(&t, c->d_tr, sizeof(t), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  return t.error ? B200_ERR_TRANSCRIPT : B200_OK;
+}
+
+int b200_lasso_witness(b200_ctx* h, int kind, int chunks, int mu, const uint64_t* host_xs, const uint64_t* host_ys,
+                       void* dev_mtabs, void* dev_stabs) {
+  Ctx* c = &h->c;
+  if (mu < 1 || mu > 26 || !host_xs || (kind != 0 && !host_ys)) return B200_ERR_ARG;
+  uint64_t *dx, *dy;
+  int rc = upload_operands(c, mu, host_xs, host_ys, &dx, &dy);
+  if (rc) return rc;
+  rc = lasso_witness(c, kind, chunks, mu, dx, dy, (Fr*)dev_mtabs, (Fr*)dev_stabs);
+  CUDA_TRY(cudaFreeAsync(dx, c->stream));
+  if (dy) CUDA_TRY(cudaFreeAsync(dy, c->stream));
+  return rc;
+}
+
+}  // extern "C"

@@ -105,6 +105,11 @@ int kzg_commit_batch(Ctx* c, const MsmJob* jobs, int J, bool write_transcript, G
 int kzg_open(Ctx* c, const Fr* d_poly, int n, const Fr* d_point);
 int kzg_batch_open(Ctx* c, const BatchOpenJob& job);
 
+// lasso.cu — Lasso / Surge prover (DESIGN.md §Lasso protocol; oracle/lasso.hpp)
+int lasso_prove(Ctx* c, int kind, int chunks, int mu, const uint64_t* d_xs, const uint64_t* d_ys);
+int lasso_witness(Ctx* c, int kind, int chunks, int mu, const uint64_t* d_xs, const uint64_t* d_ys, Fr* d_mt,
+                  Fr* d_st);
+
 inline void count_launch(Ctx* c, int n = 1) { c->launches += n; }
 inline void prof_begin(Ctx* c, int tag) {
   if (!c->profile) return;

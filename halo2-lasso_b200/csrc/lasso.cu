@@ -1,0 +1,530 @@
+// Lasso / Surge lookup argument on the GPU. The mounted reference has no Lasso code,
+// so the protocol is the one written down in DESIGN.md §"Lasso protocol" and restated on the CPU in
+// oracle/lasso.hpp; the layered grand-product argument follows the in-tree template
+// pb/piop/gkr/fractional_sum_check.rs:41-190,272-296 (top-bit halves, batched with powers of gamma).
+//
+// Everything is enqueued on one stream with no host round trip:
+//   witness   : chunk extraction, subtable gather, DETERMINISTIC read/final counters
+//               (per-chunk shared-memory histograms -> column scan -> in-order warp ranking; no
+//               order-dependent atomics, so read_ts is bit-identical run to run)
+//   commit    : one batched MSM over the raw integer witnesses (16-/8-/21-/64-bit scalars populate only
+//               the windows they need)
+//   sum-checks: primary Surge (degree 2) and one degree-3 batched sum-check per tree layer, all with
+//               the fused bind+round kernel and the on-device transcript
+//   openings  : leaf evaluations + two additive batch openings (mu-variate and 16-variate)
+#include "internal.h"
+
+namespace b200 {
+
+static const int SUB_VARS = 16;
+static const uint32_t SUB_SIZE = 1u << SUB_VARS;
+
+__device__ __forceinline__ uint32_t lasso_subtable(int kind, uint32_t x) {
+  if (kind == 0) return x;
+  const uint32_t p = x >> 8, q = x & 0xff;
+  return kind == 1 ? (p & q) : (p ^ q);
+}
+__device__ __forceinline__ uint32_t lasso_dim(int kind, uint64_t x, uint64_t y, int t) {
+  if (kind == 0) return (uint32_t)((x >> (16 * t)) & 0xffff);
+  return (uint32_t)((((x >> (8 * t)) & 0xff) << 8) | ((y >> (8 * t)) & 0xff));
+}
+
+// dims[t][j], e[t][j] (u32) and the lookup output a[j] (u64)
+__global__ void lasso_chunks_kernel(int kind, int c, uint32_t m, const uint64_t* __restrict__ xs,
+                                    const uint64_t* __restrict__ ys, uint32_t* __restrict__ dims,
+                                    uint32_t* __restrict__ es, uint64_t* __restrict__ a) {
+  const uint32_t stride = gridDim.x * blockDim.x;
+  const int out_bits = kind == 0 ? 16 : 8;
+  for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < m; j += stride) {
+    const uint64_t x = xs[j], y = ys ? ys[j] : 0;
+    uint64_t out = 0;
+    for (int t = 0; t < c; ++t) {
+      const uint32_t d = lasso_dim(kind, x, y, t);
+      const uint32_t e = lasso_subtable(kind, d);
+      dims[(size_t)t * m + j] = d;
+      es[(size_t)t * m + j] = e;
+      out |= (uint64_t)e << (out_bits * t);
+    }
+    a[j] = out;
+  }
+}
+
+// pass 1: per (chunk-of-lookups, dim) histogram over the 2^16 addresses, 16-bit counters packed in
+// 32-bit shared-memory words (a chunk holds < 65536 lookups)
+__global__ void __launch_bounds__(256) lasso_hist_kernel(uint32_t m, uint32_t chunk_len,
+                                                         const uint32_t* __restrict__ dims,
+                                                         uint32_t* __restrict__ hist) {
+  extern __shared__ uint32_t sh[];  // 32768 words
+  const uint32_t ch = blockIdx.x, t = blockIdx.y, nch = gridDim.x;
+  for (uint32_t i = threadIdx.x; i < SUB_SIZE / 2; i += blockDim.x) sh[i] = 0;
+  __syncthreads();
+  const uint32_t* d = dims + (size_t)t * m + (size_t)ch * chunk_len;
+  for (uint32_t i = threadIdx.x; i < chunk_len; i += blockDim.x) {
+    const uint32_t addr = d[i];
+    atomicAdd(&sh[addr >> 1], 1u << (16 * (addr & 1)));
+  }
+  __syncthreads();
+  uint32_t* out = hist + ((size_t)t * nch + ch) * (SUB_SIZE / 2);
+  for (uint32_t i = threadIdx.x; i < SUB_SIZE / 2; i += blockDim.x) out[i] = sh[i];
+}
+
+// pass 2: per (dim, address) exclusive scan over chunks -> base[t][chunk][addr]; total -> final_cts
+__global__ void lasso_colscan_kernel(uint32_t nch, const uint32_t* __restrict__ hist, uint32_t* __restrict__ base,
+                                     uint32_t* __restrict__ final_cts) {
+  const uint32_t addr = blockIdx.x * blockDim.x + threadIdx.x, t = blockIdx.y;
+  if (addr >= SUB_SIZE) return;
+  uint32_t run = 0;
+  for (uint32_t ch = 0; ch < nch; ++ch) {
+    const uint32_t w = hist[((size_t)t * nch + ch) * (SUB_SIZE / 2) + (addr >> 1)];
+    const uint32_t cnt = (w >> (16 * (addr & 1))) & 0xffff;
+    base[((size_t)t * nch + ch) * SUB_SIZE + addr] = run;
+    run += cnt;
+  }
+  final_cts[(size_t)t * SUB_SIZE + addr] = run;
+}
+
+// pass 3: ONE warp per (chunk, dim) walks its lookups in order, 32 at a time:
+// read_ts[j] = base + (#earlier in chunk) + (#earlier lanes of this step with the same address)
+__global__ void __launch_bounds__(32) lasso_rank_kernel(uint32_t m, uint32_t chunk_len,
+                                                        const uint32_t* __restrict__ dims,
+                                                        const uint32_t* __restrict__ base,
+                                                        uint32_t* __restrict__ read_ts) {
+  extern __shared__ uint32_t sh[];
+  uint16_t* local = reinterpret_cast<uint16_t*>(sh);
+  const uint32_t ch = blockIdx.x, t = blockIdx.y, nch = gridDim.x, lane = threadIdx.x;
+  for (uint32_t i = lane; i < SUB_SIZE / 2; i += 32) sh[i] = 0;
+  __syncwarp();
+  const size_t off = (size_t)t * m + (size_t)ch * chunk_len;
+  const uint32_t* b = base + ((size_t)t * nch + ch) * SUB_SIZE;
+  for (uint32_t i0 = 0; i0 < chunk_len; i0 += 32) {
+    const uint32_t i = i0 + lane;
+    const bool valid = i < chunk_len;
+    const uint32_t addr = valid ? dims[off + i] : (0x80000000u | lane);  // invalid lanes never match
+    const uint32_t mask = __match_any_sync(0xffffffffu, addr);
+    const uint32_t before = __popc(mask & ((1u << lane) - 1));
+    if (valid) {
+      const uint32_t seen = local[addr];
+      read_ts[off + i] = b[addr] + seen + before;
+      __syncwarp(mask);
+      if (before == 0) local[addr] = (uint16_t)(seen + __popc(mask));
+    }
+    __syncwarp();
+  }
+}
+
+__global__ void u32_to_fr_kernel(const uint32_t* __restrict__ in, Fr* __restrict__ out, size_t n) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    fe_st(out + i, fe_from_u64<FrP>(in[i]));
+}
+
+// m-sized leaves: read = dim*g^2 + e*g + ts - tau, write = read + 1 (trees 2t, 2t+1), stored in the
+// leaf layer [2^h, 2^(h+1)) of each tree array
+__global__ void __launch_bounds__(256) lasso_leaves_m_kernel(int c, uint32_t m, const Fr* __restrict__ dim_fr,
+                                                             const Fr* __restrict__ e_fr, const Fr* __restrict__ ts_fr,
+                                                             const Fr* __restrict__ gt, Fr* __restrict__ trees) {
+  const Fr g = fe_ld(gt), tau = fe_ld(gt + 1);
+  const Fr g2 = g * g, one = fe_one<FrP>();
+  const int t = blockIdx.y;
+  const uint32_t stride = gridDim.x * blockDim.x;
+  Fr* rd = trees + (size_t)(2 * t) * 2 * m + m;
+  Fr* wr = trees + (size_t)(2 * t + 1) * 2 * m + m;
+  for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < m; j += stride) {
+    const size_t k = (size_t)t * m + j;
+    const Fr v = fe_ldg(dim_fr + k) * g2 + fe_ldg(e_fr + k) * g + fe_ldg(ts_fr + k) - tau;
+    fe_st(rd + j, v);
+    fe_st(wr + j, v + one);
+  }
+}
+// S-sized leaves: init = x*g^2 + T[x]*g - tau, final = init + final_cts
+__global__ void __launch_bounds__(256) lasso_leaves_s_kernel(int kind, int c, const Fr* __restrict__ cts_fr,
+                                                             const Fr* __restrict__ gt, Fr* __restrict__ trees) {
+  const Fr g = fe_ld(gt), tau = fe_ld(gt + 1);
+  const Fr g2 = g * g;
+  const int t = blockIdx.y;
+  const uint32_t x = blockIdx.x * blockDim.x + threadIdx.x;
+  if (x >= SUB_SIZE) return;
+  Fr* in = trees + (size_t)(2 * t) * 2 * SUB_SIZE + SUB_SIZE;
+  Fr* fi = trees + (size_t)(2 * t + 1) * 2 * SUB_SIZE + SUB_SIZE;
+  const Fr v = fe_from_u64<FrP>(x) * g2 + fe_from_u64<FrP>(lasso_subtable(kind, x)) * g - tau;
+  fe_st(in + x, v);
+  fe_st(fi + x, v + fe_ldg(cts_fr + (size_t)t * SUB_SIZE + x));
+}
+
+// one tree layer for all trees: V_k[i] = V_{k+1}[i] * V_{k+1}[i + 2^k]; tree arrays are heap-ordered
+// (layer k at [2^k, 2^(k+1)))
+__global__ void __launch_bounds__(256) tree_up_kernel(Fr* __restrict__ trees, size_t tree_stride, uint32_t half) {
+  Fr* tr = trees + (size_t)blockIdx.y * tree_stride;
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < half; i += stride)
+    fe_st(tr + half + i, fe_ld(tr + 2 * (size_t)half + i) * fe_ld(tr + 3 * (size_t)half + i));
+}
+
+// ---- grand-product bookkeeping kernels (single warp, warp-cooperative transcript) ----------------
+struct GpState {
+  Fr claims[SC_MAX_TERMS];
+  Fr weights[SC_MAX_TERMS];
+  Fr claim;
+  Fr y[32];
+  Fr evals[2 * SC_MAX_TERMS];
+};
+
+// write the roots, which are the first claims
+__global__ void gp_roots_kernel(Transcript* tr, const Fr* trees, size_t tree_stride, int T, GpState* st) {
+  __shared__ Transcript sh_tr;
+  if (threadIdx.x == 0) sh_tr = *tr;
+  __syncwarp();
+  for (int t = 0; t < T; ++t) {
+    const Fr root = fe_ld(trees + (size_t)t * tree_stride + 1);
+    if (threadIdx.x == 0) fe_st(&st->claims[t], root);
+    trw_write_fe(&sh_tr, root);
+  }
+  __syncwarp();
+  if (threadIdx.x == 0) *tr = sh_tr;
+}
+
+// layer k transition. before_sumcheck: (k == 0) gather the two children as evals; (k > 0) squeeze gamma,
+// weights = gamma^t, claim = Σ weights*claims.   after_sumcheck: write evals, squeeze mu, fold claims,
+// y = x || mu.
+__global__ void gp_before_kernel(Transcript* tr, const Fr* trees, size_t tree_stride, int T, int k, GpState* st) {
+  __shared__ Transcript sh_tr;
+  const int lane = threadIdx.x;
+  if (k == 0) {
+    for (int i = lane; i < 2 * T; i += 32) {
+      const Fr v = fe_ld(trees + (size_t)(i >> 1) * tree_stride + 2 + (i & 1));
+      fe_st(&st->evals[i], v);
+    }
+    return;
+  }
+  if (lane == 0) sh_tr = *tr;
+  __syncwarp();
+  const Fr gamma = trw_squeeze(&sh_tr);
+  Fr pw = fe_one<FrP>(), claim = fe_zero<FrP>();
+  for (int t = 0; t < T; ++t) {
+    if (lane == 0) fe_st(&st->weights[t], pw);
+    claim = claim + fr_mul_ni(pw, fe_ld(&st->claims[t]));
+    pw = fr_mul_ni(pw, gamma);
+  }
+  if (lane == 0) {
+    fe_st(&st->claim, claim);
+    *tr = sh_tr;
+  }
+}
+__global__ void gp_after_kernel(Transcript* tr, int T, int k, const Fr* x /* k challenges, may be null */,
+                                GpState* st) {
+  __shared__ Transcript sh_tr;
+  const int lane = threadIdx.x;
+  if (lane == 0) sh_tr = *tr;
+  __syncwarp();
+  for (int i = 0; i < 2 * T; ++i) trw_write_fe(&sh_tr, fe_ld(&st->evals[i]));
+  const Fr mu = trw_squeeze(&sh_tr);
+  for (int t = lane; t < T; t += 32) {
+    const Fr l = fe_ld(&st->evals[2 * t]), r = fe_ld(&st->evals[2 * t + 1]);
+    fe_st(&st->claims[t], l + fr_mul_ni(mu, r - l));
+  }
+  for (int i = lane; i < k; i += 32) fe_st(&st->y[i], fe_ld(x + i));
+  if (lane == 0) {
+    fe_st(&st->y[k], mu);
+    *tr = sh_tr;
+  }
+}
+
+// Batched product argument over T heap-ordered trees of height h. Leaves claims in st->claims and the
+// point in st->y[0..h).
+static int grand_product_prove(Ctx* c, Fr* trees, size_t tree_stride, int T, int h, GpState* st, Fr* scratch_x) {
+  cudaStream_t s = c->stream;
+  for (int k = h - 1; k >= 0; --k) {
+    const uint32_t half = 1u << k;
+    int bx = (int)((half + 255) / 256);
+    int cap = (4 * NUM_SMS + T - 1) / T;
+    if (bx > cap) bx = cap;
+    tree_up_kernel<<<dim3(bx, T), 256, 0, s>>>(trees, tree_stride, half);
+    count_launch(c);
+  }
+  gp_roots_kernel<<<1, 32, 0, s>>>(c->d_tr, trees, tree_stride, T, st);
+  count_launch(c);
+  for (int k = 0; k < h; ++k) {
+    gp_before_kernel<<<1, 32, 0, s>>>(c->d_tr, trees, tree_stride, T, k, st);
+    count_launch(c);
+    if (k > 0) {
+      ScEvalJob job;
+      job.num_vars = k;
+      job.T = T;
+      job.NP = 2;
+      for (int t = 0; t < T; ++t) {
+        const Fr* l = trees + (size_t)t * tree_stride + ((size_t)2 << k);
+        job.tables[2 * t] = l;
+        job.tables[2 * t + 1] = l + ((size_t)1 << k);
+      }
+      job.weights = st->weights;
+      job.eq_point = st->y;
+      job.claim = &st->claim;
+      job.challenges_out = scratch_x;
+      job.evals_out = st->evals;
+      int rc = sumcheck_prove_evals(c, job);
+      if (rc) return rc;
+    }
+    gp_after_kernel<<<1, 32, 0, s>>>(c->d_tr, T, k, scratch_x, st);
+    count_launch(c);
+  }
+  CUDA_TRY(cudaGetLastError());
+  return B200_OK;
+}
+
+__global__ void copy_fr_kernel(const Fr* src, Fr* dst, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) fe_st(dst + i, fe_ld(src + i));
+}
+
+int lasso_prove(Ctx* c, int kind, int chunks, int mu, const uint64_t* d_xs, const uint64_t* d_ys) {
+  if (kind < 0 || kind > 2 || chunks < 1 || chunks > 8 || mu < 1 || mu > 26) return B200_ERR_ARG;
+  if (kind == 0 && chunks > 4) return B200_ERR_ARG;
+  if (chunks < 2) return B200_ERR_ARG;  // additive batch_open needs >= 2 evaluations (pcs/multilinear.rs:150)
+  if ((int)c->srs.size() <= (mu > SUB_VARS ? mu : SUB_VARS)) return B200_ERR_ARG;
+  cudaStream_t s = c->stream;
+  const int C_ = chunks;
+  const uint32_t m = 1u << mu;
+  const size_t S = SUB_SIZE;
+
+  // ---- 1. witness -------------------------------------------------------------------------------
+  uint32_t *dims, *es, *ts, *cts, *hist, *base;
+  uint64_t* a_u64;
+  const uint32_t nch = m >= (1u << 13) ? (m / 32768 > 128 ? m / 32768 : 128) : 1;
+  const uint32_t chunk_len = m / nch;
+  CUDA_TRY(cudaMallocAsync(&dims, (size_t)C_ * m * 4, s));
+  CUDA_TRY(cudaMallocAsync(&es, (size_t)C_ * m * 4, s));
+  CUDA_TRY(cudaMallocAsync(&ts, (size_t)C_ * m * 4, s));
+  CUDA_TRY(cudaMallocAsync(&cts, (size_t)C_ * S * 4, s));
+  CUDA_TRY(cudaMallocAsync(&a_u64, (size_t)m * 8, s));
+  CUDA_TRY(cudaMallocAsync(&hist, (size_t)C_ * nch * (S / 2) * 4, s));
+  CUDA_TRY(cudaMallocAsync(&base, (size_t)C_ * nch * S * 4, s));
+  {
+    int bx = (int)((m + 255) / 256);
+    if (bx > NUM_SMS * 8) bx = NUM_SMS * 8;
+    lasso_chunks_kernel<<<bx, 256, 0, s>>>(kind, C_, m, d_xs, d_ys, dims, es, a_u64);
+    const int smem = (int)(S / 2) * 4;  // 128 KiB
+    CUDA_TRY(cudaFuncSetAttribute(lasso_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CUDA_TRY(cudaFuncSetAttribute(lasso_rank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    lasso_hist_kernel<<<dim3(nch, C_), 256, smem, s>>>(m, chunk_len, dims, hist);
+    lasso_colscan_kernel<<<dim3(S / 256, C_), 256, 0, s>>>(nch, hist, base, cts);
+    lasso_rank_kernel<<<dim3(nch, C_), 32, smem, s>>>(m, chunk_len, dims, base, ts);
+    count_launch(c, 4);
+  }
+  // field-element tables: a | dim[c] | e[c] | ts[c] (m each), cts[c] (S each)
+  const int NM = 1 + 3 * C_;
+  Fr *mt, *st_tabs;
+  CUDA_TRY(cudaMallocAsync(&mt, (size_t)NM * m * sizeof(Fr), s));
+  CUDA_TRY(cudaMallocAsync(&st_tabs, (size_t)C_ * S * sizeof(Fr), s));
+  Fr* a_fr = mt;
+  Fr* dim_fr = mt + (size_t)m;
+  Fr* e_fr = dim_fr + (size_t)C_ * m;
+  Fr* ts_fr = e_fr + (size_t)C_ * m;
+  int rc = fr_from_u64(c, a_u64, a_fr, m);
+  if (rc) return rc;
+  {
+    const int bx = NUM_SMS * 8;
+    u32_to_fr_kernel<<<bx, 256, 0, s>>>(dims, dim_fr, (size_t)C_ * m);
+    u32_to_fr_kernel<<<bx, 256, 0, s>>>(es, e_fr, (size_t)C_ * m);
+    u32_to_fr_kernel<<<bx, 256, 0, s>>>(ts, ts_fr, (size_t)C_ * m);
+    u32_to_fr_kernel<<<bx, 256, 0, s>>>(cts, st_tabs, (size_t)C_ * S);
+    count_launch(c, 4);
+  }
+
+  // ---- scalar arena -------------------------------------------------------------------------------
+  // stmt[3] | r[mu] | v_a | pw[c] | x_p[mu] | e_p[c] | gt[2] | x_scratch[32] | ev_m[3c] | ev_s[c] | pts[3*mu]
+  const size_t arena_n = 3 + mu + 1 + C_ + mu + C_ + 2 + 32 + 3 * C_ + C_ + 3 * (size_t)mu + SUB_VARS;
+  Fr* arena;
+  CUDA_TRY(cudaMallocAsync(&arena, arena_n * sizeof(Fr), s));
+  Fr* stmt = arena;
+  Fr* r = stmt + 3;
+  Fr* v_a = r + mu;
+  Fr* pw = v_a + 1;
+  Fr* x_p = pw + C_;
+  Fr* e_p = x_p + mu;
+  Fr* gt = e_p + C_;
+  Fr* x_scratch = gt + 2;
+  Fr* ev_m = x_scratch + 32;
+  Fr* ev_s = ev_m + 3 * C_;
+  Fr* pts = ev_s + C_;
+  Fr* pt_s = pts + 3 * (size_t)mu;
+  GpState* gp;
+  CUDA_TRY(cudaMallocAsync(&gp, sizeof(GpState), s));
+  {
+    Fr h[3 + 8];
+    h[0] = fe_from_u64<FrP>((uint64_t)kind);
+    h[1] = fe_from_u64<FrP>((uint64_t)C_);
+    h[2] = fe_from_u64<FrP>((uint64_t)mu);
+    const int out_bits = kind == 0 ? 16 : 8;
+    for (int t = 0; t < C_; ++t) h[3 + t] = fe_from_u64<FrP>((uint64_t)1 << (out_bits * t));
+    CUDA_TRY(cudaMemcpyAsync(stmt, h, 3 * sizeof(Fr), cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(pw, h + 3, C_ * sizeof(Fr), cudaMemcpyHostToDevice, s));
+  }
+  rc = transcript_op(c, TR_COMMON, stmt, nullptr, 3);
+  if (rc) return rc;
+
+  // ---- 2. commitments: a, dim_*, E_*, read_ts_* (level mu), final_cts_* (level 16) -----------------
+  {
+    MsmJob jobs[1 + 4 * 8];
+    int J = 0;
+    const int e_bits = kind == 0 ? 16 : 8;
+    jobs[J++] = MsmJob{a_u64, c->srs[mu], m, MSM_U64, e_bits * C_};
+    for (int t = 0; t < C_; ++t) jobs[J++] = MsmJob{dims + (size_t)t * m, c->srs[mu], m, MSM_U32, 16};
+    for (int t = 0; t < C_; ++t) jobs[J++] = MsmJob{es + (size_t)t * m, c->srs[mu], m, MSM_U32, e_bits};
+    for (int t = 0; t < C_; ++t) jobs[J++] = MsmJob{ts + (size_t)t * m, c->srs[mu], m, MSM_U32, mu + 1};
+    for (int t = 0; t < C_; ++t) jobs[J++] = MsmJob{cts + (size_t)t * S, c->srs[SUB_VARS], S, MSM_U32, mu + 1};
+    G1Aff* comms;
+    CUDA_TRY(cudaMallocAsync(&comms, J * sizeof(G1Aff), s));
+    rc = kzg_commit_batch(c, jobs, J, true, comms);
+    if (rc) return rc;
+    CUDA_TRY(cudaFreeAsync(comms, s));
+  }
+
+  // ---- 3-5. primary Surge sum-check ----------------------------------------------------------------
+  rc = transcript_op(c, TR_SQUEEZE, nullptr, r, mu);
+  if (rc) return rc;
+  {
+    const Fr* tab[1] = {a_fr};
+    rc = mle_eval_many(c, tab, 1, mu, r, v_a);
+    if (rc) return rc;
+  }
+  rc = transcript_op(c, TR_WRITE, v_a, nullptr, 1);
+  if (rc) return rc;
+  {
+    ScEvalJob job;
+    job.num_vars = mu;
+    job.T = C_;
+    job.NP = 1;
+    for (int t = 0; t < C_; ++t) job.tables[t] = e_fr + (size_t)t * m;
+    job.weights = pw;
+    job.eq_point = r;
+    job.claim = v_a;
+    job.challenges_out = x_p;
+    job.evals_out = e_p;
+    rc = sumcheck_prove_evals(c, job);
+    if (rc) return rc;
+  }
+  rc = transcript_op(c, TR_WRITE, e_p, nullptr, C_);
+  if (rc) return rc;
+
+  // ---- 6-8. memory checking -------------------------------------------------------------------------
+  rc = transcript_op(c, TR_SQUEEZE, nullptr, gt, 2);
+  if (rc) return rc;
+  const int T = 2 * C_;
+  Fr *mtrees, *strees;
+  CUDA_TRY(cudaMallocAsync(&mtrees, (size_t)T * 2 * m * sizeof(Fr), s));
+  CUDA_TRY(cudaMallocAsync(&strees, (size_t)T * 2 * S * sizeof(Fr), s));
+  {
+    int bx = (int)((m + 255) / 256);
+    int cap = (8 * NUM_SMS + C_ - 1) / C_;
+    if (bx > cap) bx = cap;
+    lasso_leaves_m_kernel<<<dim3(bx, C_), 256, 0, s>>>(C_, m, dim_fr, e_fr, ts_fr, gt, mtrees);
+    lasso_leaves_s_kernel<<<dim3(S / 256, C_), 256, 0, s>>>(kind, C_, st_tabs, gt, strees);
+    count_launch(c, 2);
+  }
+  rc = grand_product_prove(c, mtrees, (size_t)2 * m, T, mu, gp, x_scratch);
+  if (rc) return rc;
+  // x_m = gp->y[0..mu)
+  copy_fr_kernel<<<1, 64, 0, s>>>(gp->y, pts + 2 * (size_t)mu, mu);
+  rc = grand_product_prove(c, strees, (size_t)2 * S, T, SUB_VARS, gp, x_scratch);
+  if (rc) return rc;
+  copy_fr_kernel<<<1, 64, 0, s>>>(gp->y, pt_s, SUB_VARS);
+  count_launch(c, 2);
+  CUDA_TRY(cudaFreeAsync(mtrees, s));
+  CUDA_TRY(cudaFreeAsync(strees, s));
+
+  // ---- 9. leaf openings -----------------------------------------------------------------------------
+  {
+    const Fr* tabs[3 * 8];
+    for (int i = 0; i < 3 * C_; ++i) tabs[i] = dim_fr + (size_t)i * m;  // dim*, e*, ts* are contiguous
+    rc = mle_eval_many(c, tabs, 3 * C_, mu, pts + 2 * (size_t)mu, ev_m);
+    if (rc) return rc;
+    for (int t = 0; t < C_; ++t) tabs[t] = st_tabs + (size_t)t * S;
+    rc = mle_eval_many(c, tabs, C_, SUB_VARS, pt_s, ev_s);
+    if (rc) return rc;
+  }
+  rc = transcript_op(c, TR_WRITE, ev_m, nullptr, 3 * C_);  // dims, E, read_ts
+  if (rc) return rc;
+  rc = transcript_op(c, TR_WRITE, ev_s, nullptr, C_);
+  if (rc) return rc;
+
+  // ---- 10. batch openings ---------------------------------------------------------------------------
+  {
+    copy_fr_kernel<<<1, 64, 0, s>>>(r, pts, mu);
+    copy_fr_kernel<<<1, 64, 0, s>>>(x_p, pts + mu, mu);
+    count_launch(c, 2);
+    const int E = 1 + 4 * C_;
+    Fr* vals;
+    CUDA_TRY(cudaMallocAsync(&vals, E * sizeof(Fr), s));
+    copy_fr_kernel<<<1, 64, 0, s>>>(v_a, vals, 1);
+    copy_fr_kernel<<<1, 64, 0, s>>>(e_p, vals + 1, C_);
+    copy_fr_kernel<<<1, 64, 0, s>>>(ev_m, vals + 1 + C_, 3 * C_);
+    count_launch(c, 3);
+    const Fr* polys[1 + 3 * 8];
+    for (int i = 0; i < NM; ++i) polys[i] = mt + (size_t)i * m;
+    int ev_poly[1 + 4 * 8], ev_point[1 + 4 * 8], k = 0;
+    ev_poly[k] = 0, ev_point[k++] = 0;
+    for (int t = 0; t < C_; ++t) ev_poly[k] = 1 + C_ + t, ev_point[k++] = 1;
+    for (int t = 0; t < C_; ++t) ev_poly[k] = 1 + t, ev_point[k++] = 2;
+    for (int t = 0; t < C_; ++t) ev_poly[k] = 1 + C_ + t, ev_point[k++] = 2;
+    for (int t = 0; t < C_; ++t) ev_poly[k] = 1 + 2 * C_ + t, ev_point[k++] = 2;
+    BatchOpenJob bj{mu, NM, 3, E, polys, pts, ev_poly, ev_point, vals};
+    rc = kzg_batch_open(c, bj);
+    if (rc) return rc;
+    const Fr* spolys[8];
+    int sp[8], spt[8];
+    for (int t = 0; t < C_; ++t) spolys[t] = st_tabs + (size_t)t * S, sp[t] = t, spt[t] = 0;
+    BatchOpenJob sj{SUB_VARS, C_, 1, C_, spolys, pt_s, sp, spt, ev_s};
+    rc = kzg_batch_open(c, sj);
+    if (rc) return rc;
+    CUDA_TRY(cudaFreeAsync(vals, s));
+  }
+  for (void* p : {(void*)dims, (void*)es, (void*)ts, (void*)cts, (void*)a_u64, (void*)hist, (void*)base, (void*)mt,
+                  (void*)st_tabs, (void*)arena, (void*)gp})
+    CUDA_TRY(cudaFreeAsync(p, s));
+  CUDA_TRY(cudaGetLastError());
+  return B200_OK;
+}
+
+// witness only (parity of dims / E / read_ts / final_cts / a against the oracle)
+int lasso_witness(Ctx* c, int kind, int chunks, int mu, const uint64_t* d_xs, const uint64_t* d_ys, Fr* d_mt,
+                  Fr* d_st) {
+  if (kind < 0 || kind > 2 || chunks < 1 || chunks > 8 || mu < 1 || mu > 26) return B200_ERR_ARG;
+  cudaStream_t s = c->stream;
+  const int C_ = chunks;
+  const uint32_t m = 1u << mu;
+  const size_t S = SUB_SIZE;
+  uint32_t *dims, *es, *ts, *cts, *hist, *base;
+  uint64_t* a_u64;
+  const uint32_t nch = m >= (1u << 13) ? (m / 32768 > 128 ? m / 32768 : 128) : 1;
+  const uint32_t chunk_len = m / nch;
+  CUDA_TRY(cudaMallocAsync(&dims, (size_t)C_ * m * 4, s));
+  CUDA_TRY(cudaMallocAsync(&es, (size_t)C_ * m * 4, s));
+  CUDA_TRY(cudaMallocAsync(&ts, (size_t)C_ * m * 4, s));
+  CUDA_TRY(cudaMallocAsync(&cts, (size_t)C_ * S * 4, s));
+  CUDA_TRY(cudaMallocAsync(&a_u64, (size_t)m * 8, s));
+  CUDA_TRY(cudaMallocAsync(&hist, (size_t)C_ * nch * (S / 2) * 4, s));
+  CUDA_TRY(cudaMallocAsync(&base, (size_t)C_ * nch * S * 4, s));
+  int bx = (int)((m + 255) / 256);
+  if (bx > NUM_SMS * 8) bx = NUM_SMS * 8;
+  lasso_chunks_kernel<<<bx, 256, 0, s>>>(kind, C_, m, d_xs, d_ys, dims, es, a_u64);
+  const int smem = (int)(S / 2) * 4;
+  CUDA_TRY(cudaFuncSetAttribute(lasso_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  CUDA_TRY(cudaFuncSetAttribute(lasso_rank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  lasso_hist_kernel<<<dim3(nch, C_), 256, smem, s>>>(m, chunk_len, dims, hist);
+  lasso_colscan_kernel<<<dim3(S / 256, C_), 256, 0, s>>>(nch, hist, base, cts);
+  lasso_rank_kernel<<<dim3(nch, C_), 32, smem, s>>>(m, chunk_len, dims, base, ts);
+  int rc = fr_from_u64(c, a_u64, d_mt, m);
+  if (rc) return rc;
+  const int gx = NUM_SMS * 8;
+  u32_to_fr_kernel<<<gx, 256, 0, s>>>(dims, d_mt + (size_t)m, (size_t)C_ * m);
+  u32_to_fr_kernel<<<gx, 256, 0, s>>>(es, d_mt + (size_t)(1 + C_) * m, (size_t)C_ * m);
+  u32_to_fr_kernel<<<gx, 256, 0, s>>>(ts, d_mt + (size_t)(1 + 2 * C_) * m, (size_t)C_ * m);
+  u32_to_fr_kernel<<<gx, 256, 0, s>>>(cts, d_st, (size_t)C_ * S);
+  count_launch(c, 9);
+  for (void* p : {(void*)dims, (void*)es, (void*)ts, (void*)cts, (void*)a_u64, (void*)hist, (void*)base})
+    CUDA_TRY(cudaFreeAsync(p, s));
+  CUDA_TRY(cudaGetLastError());
+  return B200_OK;
+}
+
+}  // namespace b200

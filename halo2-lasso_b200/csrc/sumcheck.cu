@@ -49,24 +49,6 @@ __device__ __forceinline__ void load_pair(const Fr* __restrict__ in, Fr* __restr
   }
 }
 
-// p(r) from p(0..d) with precomputed weights: Σ_i e_i * w_i * Π_{j != i} (r - j)
-__device__ __forceinline__ Fr interpolate_at(const Fr* ev, int d, const Fr& r, const BaryTable* bary) {
-  Fr diff[7], pre[8], acc = fe_zero<FrP>();
-  Fr j = fe_zero<FrP>(), one = fe_one<FrP>();
-  for (int i = 0; i <= d; ++i) {
-    diff[i] = r - j;
-    j = j + one;
-  }
-  pre[0] = one;
-  for (int i = 0; i <= d; ++i) pre[i + 1] = pre[i] * diff[i];
-  Fr suf = one;
-  for (int i = d; i >= 0; --i) {
-    acc = acc + ev[i] * bary->w[d][i] * pre[i] * suf;
-    suf = suf * diff[i];
-  }
-  return acc;
-}
-
 template <int NP, bool BIND>
 __global__ void __launch_bounds__(SC_THREADS) sc_eval_round_kernel(ScEvalArgs a) {
   constexpr int D = NP + 1;  // degree; evaluations at 1..D are computed, p(0) derived
@@ -105,11 +87,16 @@ __global__ void __launch_bounds__(SC_THREADS) sc_eval_round_kernel(ScEvalArgs a)
     }
   }
   block_reduce_fr<D>(acc, smem);
-  if (threadIdx.x == 0) {
-    const Fr w = fe_ld(a.weights + t);
-    Fr* dst = a.partial + ((size_t)t * gridDim.x + blockIdx.x) * D;
+  if (threadIdx.x < 32) {  // lane x scales and stores partial x (one multiplication deep, not D)
+    const int lane = threadIdx.x;
+    Fr v = fe_zero<FrP>();
 #pragma unroll
-    for (int x = 0; x < D; ++x) fe_st(dst + x, acc[x] * w);
+    for (int x = 0; x < D; ++x) {
+      const Fr tmp = fr_bcast(acc[x], 0);
+      if (lane == x) v = tmp;
+    }
+    v = fr_mul_ni(v, fe_ld(a.weights + t));
+    if (lane < D) fe_st(a.partial + ((size_t)t * gridDim.x + blockIdx.x) * D + lane, v);
   }
   if (!last_cta_ticket(&a.st->counter)) return;
 
@@ -122,19 +109,46 @@ __global__ void __launch_bounds__(SC_THREADS) sc_eval_round_kernel(ScEvalArgs a)
     for (int x = 0; x < D; ++x) acc[x] = acc[x] + fr_ld_cg(a.partial + (size_t)i * D + x);
   }
   block_reduce_fr<D>(acc, smem);
-  if (threadIdx.x == 0) {
-    Fr ev[D + 1];
+  if (threadIdx.x < 32) {  // warp 0, warp-uniform control flow; lane i owns p(i)
+    const int lane = threadIdx.x;
+    __shared__ Transcript sh_tr;
+    if (lane == 0) sh_tr = *a.tr;
+    __syncwarp();
+    const Fr p1 = fr_bcast(acc[0], 0);
+    Fr mine = fe_zero<FrP>();
 #pragma unroll
-    for (int x = 0; x < D; ++x) ev[x + 1] = acc[x];
-    const Fr claim = fe_ld(&a.st->claim);
-    ev[0] = claim - ev[1];
-    Transcript lt = *a.tr;  // work on a thread-local copy of the sponge: no global round trips per word
-    for (int x = 0; x <= D; ++x) tr_write_fe(&lt, ev[x]);
-    const Fr ch = tr_squeeze(&lt);
-    *a.tr = lt;
-    fe_st(a.challenges_out + a.round, ch);
-    fe_st(&a.st->r, ch);
-    fe_st(&a.st->claim, interpolate_at(ev, D, ch, a.bary));
+    for (int x = 0; x < D; ++x) {
+      const Fr tmp = fr_bcast(acc[x], 0);
+      if (lane == x + 1) mine = tmp;
+    }
+    if (lane == 0) mine = fe_ld(&a.st->claim) - p1;  // p(0) = sum - p(1)   (eval.rs:129)
+    const Fr canon = fr_canon_ni(mine);              // D+1 conversions in parallel lanes
+    for (int x = 0; x <= D; ++x) trw_write_canon_from_lane(&sh_tr, canon, x, true);
+    const Fr ch = trw_squeeze(&sh_tr);
+    // next claim p(ch) = Σ_i p(i) w_i Π_{j != i} (ch - j): lane i builds its own term
+    const Fr one = fe_one<FrP>();
+    Fr num = lane <= D ? a.bary->w[D][lane <= D ? lane : 0] : fe_zero<FrP>();
+    Fr jf = fe_zero<FrP>();
+    for (int j = 0; j <= D; ++j) {
+      const Fr f = (j == lane) ? one : ch - jf;
+      num = fr_mul_ni(num, f);
+      jf = jf + one;
+    }
+    Fr term = fr_mul_ni(num, mine);
+    if (lane > D) term = fe_zero<FrP>();
+#pragma unroll
+    for (int off = 1; off < 8; off <<= 1) {
+      Fr o;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o.v[i] = __shfl_xor_sync(0xffffffffu, term.v[i], off);
+      term = term + o;
+    }
+    if (lane == 0) {
+      *a.tr = sh_tr;
+      fe_st(a.challenges_out + a.round, ch);
+      fe_st(&a.st->r, ch);
+      fe_st(&a.st->claim, term);
+    }
   }
 }
 
@@ -265,11 +279,11 @@ __global__ void __launch_bounds__(SC_THREADS) sc_coeff_round_kernel(ScCoeffArgs 
     acc[1] = acc[1] + (l1 - l0) * (r1 - r0);
   }
   block_reduce_fr<2>(acc, smem);
-  if (threadIdx.x == 0) {
-    const Fr w = fe_ld(a.scalars + k);
-    Fr* dst = a.partial + ((size_t)k * gridDim.x + blockIdx.x) * 2;
-    fe_st(dst, acc[0] * w);
-    fe_st(dst + 1, acc[1] * w);
+  if (threadIdx.x < 32) {
+    const int lane = threadIdx.x;
+    const Fr t0 = fr_bcast(acc[0], 0), t1 = fr_bcast(acc[1], 0);
+    const Fr v = fr_mul_ni(lane == 0 ? t0 : t1, fe_ld(a.scalars + k));
+    if (lane < 2) fe_st(a.partial + ((size_t)k * gridDim.x + blockIdx.x) * 2 + lane, v);
   }
   if (!last_cta_ticket(&a.st->counter)) return;
   const uint32_t nparts = gridDim.x * gridDim.y;
@@ -280,19 +294,24 @@ __global__ void __launch_bounds__(SC_THREADS) sc_coeff_round_kernel(ScCoeffArgs 
     acc[1] = acc[1] + fr_ld_cg(a.partial + (size_t)i * 2 + 1);
   }
   block_reduce_fr<2>(acc, smem);
-  if (threadIdx.x == 0) {
+  if (threadIdx.x < 32) {
+    const int lane = threadIdx.x;
+    __shared__ Transcript sh_tr;
+    if (lane == 0) sh_tr = *a.tr;
+    __syncwarp();
     const Fr claim = fe_ld(&a.st->claim);
-    const Fr c0 = acc[0], c2 = acc[1];
-    const Fr c1 = claim - (c0 + c0 + c2);
-    Transcript lt = *a.tr;
-    tr_write_fe(&lt, c0);
-    tr_write_fe(&lt, c1);
-    tr_write_fe(&lt, c2);
-    const Fr ch = tr_squeeze(&lt);
-    *a.tr = lt;
-    fe_st(a.challenges_out + a.round, ch);
-    fe_st(&a.st->r, ch);
-    fe_st(&a.st->claim, (c2 * ch + c1) * ch + c0);
+    const Fr c0 = fr_bcast(acc[0], 0), c2 = fr_bcast(acc[1], 0);
+    const Fr c1 = claim - (c0 + c0 + c2);  // coeff.rs:147
+    const Fr canon = fr_canon_ni(lane == 0 ? c0 : (lane == 1 ? c1 : c2));
+    for (int x = 0; x < 3; ++x) trw_write_canon_from_lane(&sh_tr, canon, x, true);
+    const Fr ch = trw_squeeze(&sh_tr);
+    const Fr next = fr_mul_ni(fr_mul_ni(c2, ch) + c1, ch) + c0;  // horner (coeff.rs:36-38)
+    if (lane == 0) {
+      *a.tr = sh_tr;
+      fe_st(a.challenges_out + a.round, ch);
+      fe_st(&a.st->r, ch);
+      fe_st(&a.st->claim, next);
+    }
   }
 }
 

@@ -153,4 +153,160 @@ FF_HD void tr_write_commitment(Transcript* t, const Fq& x, const Fq& y) {
   tr_stream_be(t, cy.v);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Warp-cooperative transcript (device only). A single GPU thread needs ~14k instructions per
+// Keccak-f[1600]; with one 64-bit lane of the state per thread of a warp the permutation is ~20
+// shuffles + ~20 ALU instructions per round. ALL 32 lanes of one warp must call these functions with
+// identical arguments (the code is warp-uniform; only lane 0 writes memory).
+// ---------------------------------------------------------------------------------------------
+#if defined(__CUDACC__)
+__device__ __forceinline__ uint64_t rotl64v(uint64_t x, unsigned n) {
+  return n ? (x << n) | (x >> (64 - n)) : x;
+}
+
+// One shared, NON-inlined copy of the Montgomery product for cold latency-bound code (round
+// finalisation, transcript): executed once per launch by a single warp, such code is instruction-
+// fetch bound, so it must stay small enough to live in the instruction cache.
+static __device__ __noinline__ Fr fr_mul_ni(Fr a, Fr b) { return fe_mul<FrP>(a, b); }
+static __device__ __noinline__ Fq fq_mul_ni(Fq a, Fq b) { return fe_mul<FqP>(a, b); }
+__device__ __forceinline__ Fr fr_bcast(const Fr& a, int src) {
+  Fr r;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) r.v[i] = __shfl_sync(0xffffffffu, a.v[i], src);
+  return r;
+}
+__device__ __forceinline__ Fr fr_canon_ni(const Fr& a) {
+  Fr one = fe_zero<FrP>();
+  one.v[0] = 1;
+  return fr_mul_ni(a, one);
+}
+
+static __device__ __noinline__ void keccak_f1600_warp(uint64_t* s) {
+  const uint64_t RC[24] = {
+      0x0000000000000001ULL, 0x0000000000008082ULL, 0x800000000000808aULL, 0x8000000080008000ULL,
+      0x000000000000808bULL, 0x0000000080000001ULL, 0x8000000080008081ULL, 0x8000000000008009ULL,
+      0x000000000000008aULL, 0x0000000000000088ULL, 0x0000000080008009ULL, 0x000000008000000aULL,
+      0x000000008000808bULL, 0x800000000000008bULL, 0x8000000000008089ULL, 0x8000000000008003ULL,
+      0x8000000000008002ULL, 0x8000000000000080ULL, 0x000000000000800aULL, 0x800000008000000aULL,
+      0x8000000080008081ULL, 0x8000000000008080ULL, 0x0000000080000001ULL, 0x8000000080008008ULL};
+  // rho offsets indexed by lane = x + 5y
+  const unsigned RHO[25] = {0, 1, 62, 28, 27, 36, 44, 6, 55, 20, 3, 10, 43, 25, 39, 41, 45, 15, 21, 8, 18, 2, 61, 56, 14};
+  const unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const int l = lane < 25 ? lane : 0;  // lanes 25..31 shadow lane 0 and never store
+  const int x = l % 5, y = l / 5;
+  uint64_t a = s[l];
+  const unsigned rho = RHO[l];
+  // pi: dest (X, Y) <- src ((X + 3Y) mod 5, X)
+  const int pi_src = ((x + 3 * y) % 5) + 5 * x;
+  const int col1 = x + 5 * ((y + 1) % 5), col2 = x + 5 * ((y + 2) % 5), col3 = x + 5 * ((y + 3) % 5),
+            col4 = x + 5 * ((y + 4) % 5);
+  const int cl = (x + 4) % 5, cr = (x + 1) % 5;
+  const int row1 = 5 * y + (x + 1) % 5, row2 = 5 * y + (x + 2) % 5;
+#pragma unroll 1
+  for (int round = 0; round < 24; ++round) {
+    uint64_t c = a ^ __shfl_sync(FULL, a, col1) ^ __shfl_sync(FULL, a, col2) ^ __shfl_sync(FULL, a, col3) ^
+                 __shfl_sync(FULL, a, col4);
+    const uint64_t c_l = __shfl_sync(FULL, c, cl), c_r = __shfl_sync(FULL, c, cr);
+    a ^= c_l ^ rotl64v(c_r, 1);
+    const uint64_t rot = rotl64v(a, rho);
+    const uint64_t b = __shfl_sync(FULL, rot, pi_src);
+    const uint64_t b1 = __shfl_sync(FULL, b, row1), b2 = __shfl_sync(FULL, b, row2);
+    a = b ^ (~b1 & b2);
+    if (l == 0) a ^= RC[round];
+  }
+  if (lane < 25) s[lane] = a;
+}
+
+// `t` must be in shared memory (or global) visible to the whole warp
+static __device__ __noinline__ void trw_absorb_words(Transcript* t, const uint32_t* w, int nwords) {
+  const int lane = threadIdx.x & 31;
+  uint32_t p = t->pos;
+  for (int i = 0; i < nwords; ++i) {
+    if (lane == 0) t->s[p >> 3] ^= (uint64_t)w[i] << (8 * (p & 7));
+    p += 4;
+    if (p == 136) {
+      __syncwarp();
+      keccak_f1600_warp(t->s);
+      __syncwarp();
+      p = 0;
+    }
+  }
+  __syncwarp();
+  if (lane == 0) t->pos = p;
+  __syncwarp();
+}
+__device__ __forceinline__ Fr trw_squeeze(Transcript* t) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t p = t->pos;
+  if (lane == 0) {
+    t->s[p >> 3] ^= (uint64_t)0x01 << (8 * (p & 7));
+    t->s[16] ^= 0x8000000000000000ULL;
+  }
+  __syncwarp();
+  keccak_f1600_warp(t->s);
+  __syncwarp();
+  Fr h;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const uint64_t v = t->s[i];
+    h.v[2 * i] = (uint32_t)v;
+    h.v[2 * i + 1] = (uint32_t)(v >> 32);
+  }
+  __syncwarp();
+  if (lane < 25) t->s[lane] = 0;
+  if (lane == 0) t->pos = 0;
+  __syncwarp();
+  trw_absorb_words(t, h.v, 8);
+  Fr r2;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) r2.v[i] = FrP::r2(i);
+  return fr_mul_ni(r2, h);  // (hash mod r) in Montgomery form; the raw 256-bit operand is the scanned one
+}
+// absorb (and stream) the element whose CANONICAL limbs lane `src` holds: lets the caller convert
+// several elements to canonical form in parallel lanes
+__device__ __forceinline__ void trw_write_canon_from_lane(Transcript* t, const Fr& canon_mine, int src, bool stream) {
+  const Fr c = fr_bcast(canon_mine, src);
+  trw_absorb_words(t, c.v, 8);
+  if (stream) {
+    if ((threadIdx.x & 31) == 0) tr_stream_be(t, c.v);
+    __syncwarp();
+  }
+}
+__device__ __forceinline__ void trw_stream_be(Transcript* t, const uint32_t* canon) {
+  if ((threadIdx.x & 31) == 0) tr_stream_be(t, canon);
+  __syncwarp();
+}
+__device__ __forceinline__ void trw_common_fe(Transcript* t, const Fr& fe) {
+  const Fr c = fr_canon_ni(fe);
+  trw_absorb_words(t, c.v, 8);
+}
+__device__ __forceinline__ void trw_write_fe(Transcript* t, const Fr& fe) {
+  const Fr c = fr_canon_ni(fe);
+  trw_absorb_words(t, c.v, 8);
+  trw_stream_be(t, c.v);
+}
+__device__ __forceinline__ void trw_write_commitment(Transcript* t, const Fq& x, const Fq& y) {
+  if (fe_is_zero<FqP>(x) && fe_is_zero<FqP>(y)) {
+    if ((threadIdx.x & 31) == 0) t->error |= 2;
+    __syncwarp();
+    return;
+  }
+  Fq one = fe_zero<FqP>();
+  one.v[0] = 1;
+  const Fq cx = fq_mul_ni(x, one), cy = fq_mul_ni(y, one);
+  trw_absorb_words(t, cx.v, 8);
+  trw_absorb_words(t, cy.v, 8);
+  trw_stream_be(t, cx.v);
+  trw_stream_be(t, cy.v);
+}
+// broadcast a field element from lane 0 to the whole warp
+__device__ __forceinline__ Fr fr_bcast0(const Fr& a) {
+  Fr r;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) r.v[i] = __shfl_sync(0xffffffffu, a.v[i], 0);
+  return r;
+}
+#endif
+
 }  // namespace b200

@@ -122,6 +122,22 @@ int b200_kzg_batch_open(b200_ctx* ctx, int num_vars, const void* const* dev_poly
                         const void* host_points, int npoints, const int* ev_poly, const int* ev_point,
                         const void* host_ev_values, int nevals);
 
+/* ---- Lasso / Surge lookup argument (north_star; no counterpart in the mounted snapshot).
+ * Specification: DESIGN.md "Lasso protocol"; CPU restatement: oracle/lasso.hpp. ---------------------- */
+#define B200_TABLE_RANGE 0 /* chunks x 16-bit limbs, identity subtable, g = sum 2^(16 t) E_t */
+#define B200_TABLE_AND 1   /* chunks x (8|8)-bit operand bytes, subtable p & q, g = sum 2^(8 t) E_t */
+#define B200_TABLE_XOR 2
+/* Proves 2^mu lookups (host_xs[, host_ys] operands, u64 each) and appends the whole proof to the context
+ * transcript: commitments to a, dim_*, E_*, read_ts_*, final_cts_*; primary Surge sum-check; memory-
+ * checking grand products; leaf evaluations; two batch openings. The SRS must cover max(mu, 16) levels. */
+int b200_lasso_prove(b200_ctx* ctx, int table_kind, int chunks, int mu, const uint64_t* host_xs,
+                     const uint64_t* host_ys);
+/* same with operands already on the device (u64 arrays) */
+int b200_lasso_prove_dev(b200_ctx* ctx, int table_kind, int chunks, int mu, const void* dev_xs, const void* dev_ys);
+/* witness tables only: dev_mtabs = a | dim[c] | E[c] | read_ts[c] (2^mu each), dev_stabs = final_cts[c] (2^16 each) */
+int b200_lasso_witness(b200_ctx* ctx, int table_kind, int chunks, int mu, const uint64_t* host_xs,
+                       const uint64_t* host_ys, void* dev_mtabs, void* dev_stabs);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,87 @@
+"""GPU parity: the Lasso / Surge prover vs the CPU oracle (byte-identical proofs) and vs the oracle
+verifier (proofs accepted; tampered proofs rejected)."""
+import numpy as np
+import pytest
+
+import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+NV = 16
+
+
+@pytest.fixture(scope="module")
+def hl():
+    import halo2_lasso_b200 as m
+
+    return m
+
+
+@pytest.fixture(scope="module")
+def env(hl):
+    ctx = hl.Context(0)
+    okzg = O.Kzg(O.rand_fr(7, NV))
+    kzg = hl.MultilinearKzg(ctx, [okzg.eqs(k) for k in range(NV + 1)])
+    yield ctx, okzg, kzg
+    ctx.close()
+
+
+def operands(kind, chunks, mu, seed):
+    xs, ys = O.rand_u64s(seed, 1 << mu), O.rand_u64s(seed + 1, 1 << mu)
+    bits = (16 if kind == O.TABLE_RANGE else 8) * chunks
+    if bits < 64:
+        xs &= np.uint64((1 << bits) - 1)
+        ys &= np.uint64((1 << bits) - 1)
+    # repeat some lookups so that read counters are non-trivial even for tiny mu
+    xs[1::4] = xs[0::4]
+    ys[1::4] = ys[0::4]
+    return xs, (None if kind == O.TABLE_RANGE else ys)
+
+
+@pytest.mark.parametrize("kind,chunks,mu", [(O.TABLE_RANGE, 4, 5), (O.TABLE_AND, 8, 7), (O.TABLE_XOR, 2, 13),
+                                            (O.TABLE_RANGE, 2, 14)])
+def test_witness_parity(hl, env, kind, chunks, mu):
+    """dims / E / deterministic read_ts / final_cts / a, incl. the multi-chunk counter path (mu >= 13)."""
+    ctx, okzg, kzg = env
+    xs, ys = operands(kind, chunks, mu, 40 + mu)
+    if mu >= 13:  # hot addresses: many repeats of a few lookups, spread over all chunks
+        xs[::7] = xs[0]
+        if ys is not None:
+            ys[::7] = ys[0]
+    mt, st = hl.LassoProver(ctx, kzg, kind, chunks).witness(xs, ys)
+    mo, so = O.lasso_witness(kind, chunks, mu, xs, ys)
+    assert (mt == mo).all()
+    assert (st == so).all()
+
+
+@pytest.mark.parametrize("kind,chunks,mu", [(O.TABLE_RANGE, 4, 4), (O.TABLE_AND, 8, 6), (O.TABLE_XOR, 2, 9),
+                                            (O.TABLE_RANGE, 4, 13)])
+def test_lasso_proof_parity_and_verifies(hl, env, kind, chunks, mu):
+    ctx, okzg, kzg = env
+    xs, ys = operands(kind, chunks, mu, 60 + mu)
+    to = O.Transcript()
+    assert O.lasso_prove(okzg, to, kind, chunks, mu, xs, ys)
+    tr = hl.Keccak256Transcript(ctx)
+    hl.LassoProver(ctx, kzg, kind, chunks).prove(xs, ys)
+    proof = tr.into_proof()
+    ref = to.proof()
+    if proof != ref:
+        first = next(i for i in range(min(len(proof), len(ref))) if proof[i] != ref[i])
+        pytest.fail(f"proof differs from the oracle at byte {first} (lengths {len(proof)} vs {len(ref)})")
+    assert O.lasso_verify(okzg, O.Transcript(proof), kind, chunks, mu)
+    bad = bytearray(proof)
+    bad[len(bad) // 3] ^= 0x40
+    assert not O.lasso_verify(okzg, O.Transcript(bytes(bad)), kind, chunks, mu)
+
+
+def test_lasso_all_distinct_addresses_is_transcript_error(hl, env):
+    """read_ts == 0 everywhere -> identity commitment -> Error::Transcript, as in the reference transcript."""
+    ctx, okzg, kzg = env
+    mu = 3
+    xs = np.arange(1 << mu, dtype=np.uint64) * np.uint64(0x0001000100010001) + np.uint64(0x0003000200010000)
+    hl.Keccak256Transcript(ctx)
+    with pytest.raises(hl.B200Error) as e:
+        hl.LassoProver(ctx, kzg, O.TABLE_RANGE, 4).prove(xs)
+    assert e.value.code == hl.B200_ERR_TRANSCRIPT
+    assert not O.lasso_prove(okzg, O.Transcript(), O.TABLE_RANGE, 4, mu, xs, None)
+    hl.Keccak256Transcript(ctx)
