@@ -1,12 +1,16 @@
 #!/usr/bin/env python
 """bench.py — one JSON line per run (contract in the task statement).
 
-Workload (BASELINE.json configs[1], "cfg2"): standalone ClassicSumCheck of degree 3, eq(x,y)*a(x)*b(x)
-over n = 20 variables, synthetic seeded tables, fresh Keccak transcript; one step = one whole
-sum-check proof (20 rounds, 2560 proof bytes) on one GPU. `value` is the whole-job algorithmic
-throughput in GB/s (32*P*(4*2^n - 3) bytes per proof, P = 3 tables), inputs resident in
-HBM. `e2e` is the same proof through the host-buffer C-ABI entry (pinned host tables, H2D inside).
-N > 1: every rank proves an independent instance (weak scaling, no collective on the data path).
+Headline workload (BASELINE.json configs[2], "cfg3", the configuration the metric "Lasso prove ms
+@2^20 lookups" is quoted on; it fits one GPU): 64-bit range check via Surge, c = 4 chunks of 16 bits,
+one 2^16 identity subtable, m = 2^20 synthetic lookups, bn256 MultilinearKzg; one step = one FULL
+Lasso proof (commitments, primary sum-check, memory-checking grand products, two batch openings).
+  value : prove time in ms with the operands already resident in HBM (lower is better)
+  e2e   : the same proof through b200_lasso_prove with HOST operands (pinned) + proof bytes read back
+The same run also measures BASELINE configs[1] ("cfg2": ClassicSumCheck eq*a*b, n = 20) because the
+metric's second half is "sumcheck GB/s vs HBM peak": reported under "sumcheck" and used for
+`roofline` (dominant sum-check launch, timed live with CUDA events on the library stream).
+N > 1: every rank proves an independent instance (weak scaling; no collective on the data path yet).
 """
 import argparse
 import json
@@ -19,12 +23,17 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-NUM_VARS = 20
-P_TABLES = 3  # eq, a, b
-ALGO_BYTES = 32 * P_TABLES * (4 * (1 << NUM_VARS) - 3)  # 402,652,896
-METRIC = "ClassicSumCheck prove throughput (deg-3 eq*a*b, n=20; algorithmic bytes / time)"
-UNIT = "GB/s"
-WORKLOAD = "cfg2: standalone ClassicSumCheck degree-3 (eq*a*b) over 20 variables, byte-identical transcript"
+MU = 20
+CHUNKS = 4
+KIND_RANGE = 0
+SC_VARS = 20
+SC_TABLES = 3
+SC_ALGO_BYTES = 32 * SC_TABLES * (4 * (1 << SC_VARS) - 3)  # 402,652,896
+METRIC = "Lasso prove time @2^20 lookups (64-bit range via Surge, c=4x16-bit, bn256 MultilinearKzg)"
+UNIT = "ms"
+WORKLOAD = ("cfg3: 64-bit range check via Surge, C=4 x 16-bit subtables, 2^20 lookups, full Lasso proof; "
+            "plus cfg2 sum-check (deg-3 eq*a*b, n=20) for the roofline")
+SRS_SEED, X_SEED = 7, 5
 
 
 # ---- synthetic inputs without the oracle: the documented splitmix64 stream (oracle/capi.cpp) -------
@@ -36,6 +45,12 @@ def sm64(seed, idx):
         z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
         z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
         return z ^ (z >> np.uint64(31))
+
+
+def rand_u64s(seed, n):
+    import numpy as np
+
+    return sm64(seed, np.arange(n, dtype=np.uint64))
 
 
 def rand_canonical(seed, n):
@@ -73,7 +88,7 @@ class ClockSampler:
         time.sleep(0.15)
         self.proc.terminate()
         self.th.join(timeout=2)
-        sm, mx, reasons = [], [], set()
+        sm, mx, pw, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for l in self.lines:
             f = [x.strip() for x in l.split(",")]
@@ -82,6 +97,7 @@ class ClockSampler:
             try:
                 sm.append(float(f[0]))
                 mx.append(float(f[1]))
+                pw.append(float(f[2]))
             except ValueError:
                 continue
             for nm, v in zip(names, f[3:7]):
@@ -89,38 +105,45 @@ class ClockSampler:
                     reasons.add(nm)
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def cpu_reference_leg(steps, warmup, threads=None):
-    """The restated reference algorithm (oracle/, C++ + OpenMP) on the host cores: whole n=20 proof."""
+def mont_one():
+    import numpy as np
+
+    return np.array([0xAC96341C4FFFFFFB, 0x36FC76959F60CD29, 0x666EA36F7879462E, 0x0E0A77C19A07DF2F], dtype=np.uint64)
+
+
+def cpu_lasso(steps, warmup, srs=None):
+    """Restated reference algorithms (oracle/, C++ + OpenMP, all host threads): full 2^20 Lasso proof."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import oracle as O
 
-    if threads:
-        O.set_num_threads(threads)
-    n = NUM_VARS
-    a, b, y = O.rand_fr(1, 1 << n), O.rand_fr(2, 1 << n), O.rand_fr(3, n)
-    s = O.sum_eq_ab(y, a, b)
-    one = O.fr_from_ints([1])[0]
-    times = []
+    ss = O.rand_fr(SRS_SEED, MU)
+    t0 = time.perf_counter()
+    kz = O.Kzg.from_eqs(ss, srs) if srs is not None else O.Kzg(ss)
+    setup_s = time.perf_counter() - t0
+    xs = rand_u64s(X_SEED, 1 << MU)
+    times, plen = [], 0
     for it in range(warmup + steps):
         tr = O.Transcript()
         t0 = time.perf_counter()
-        O.sumcheck_prove_evals(tr, n, [a, b], y, [(one, [0, 1])], s)
+        ok = O.lasso_prove(kz, tr, KIND_RANGE, CHUNKS, MU, xs, None)
         dt = time.perf_counter() - t0
+        assert ok
+        plen = len(tr.proof())
         if it >= warmup:
             times.append(dt)
-    ms = 1e3 * sum(times) / len(times)
-    return ms, O.num_threads()
+    return 1e3 * sum(times) / len(times), O.num_threads(), setup_s, plen
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -129,23 +152,24 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        steps, warmup = min(args.steps, 5), min(args.warmup, 1)
-        ms, cores = cpu_reference_leg(steps, warmup)
-        val = ALGO_BYTES / (ms * 1e-3) / 1e9
-        sample = f"whole n={NUM_VARS} proof, {steps} timed repetitions"
+        steps, warmup = max(1, min(args.steps, 2)), 0
+        ms, cores, setup_s, plen = cpu_lasso(steps, warmup)
+        sample = f"whole 2^{MU}-lookup proof, {steps} timed repetition(s); SRS setup {setup_s:.1f} s untimed"
         print(json.dumps({
-            "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
-            "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "u256 (BN254 Fr, Montgomery)", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "impl_note": "restated reference algorithm (C++/OpenMP oracle); the Rust "
-                       "rayon prover cannot be built here (no cargo)"},
-            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
-            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+            "impl": "reference", "metric": METRIC, "value": ms, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+            "warmup": warmup, "ms_per_step": ms, "higher_is_better": False, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u256 (BN254 Fr/Fq, Montgomery)", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "impl_note": "restated reference algorithms (C++/OpenMP oracle: the Rust "
+                       "rayon prover cannot be built here, no cargo; Lasso itself is absent from the snapshot)",
+                       "proof_bytes": plen},
+            "cpu_baseline": {"value": ms, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": ms, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
         return
+
+    import ctypes as C
 
     import numpy as np
     import torch
-    import ctypes as C
 
     import halo2_lasso_b200 as hl
 
@@ -157,38 +181,46 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     ctx = hl.Context(local_rank)
     stream = torch.cuda.ExternalStream(ctx.stream, device=local_rank)
-    n, N = NUM_VARS, 1 << NUM_VARS
+    dev = f"cuda:{local_rank}"
+    m = 1 << MU
 
-    # inputs: canonical ints from the documented PRNG, converted to Montgomery on the device
-    pin = [torch.empty((N, 4), dtype=torch.int64).pin_memory() for _ in range(2)]  # Montgomery, pinned (e2e)
-    polys = []
-    for k, seed in enumerate((1 + 10 * rank, 2 + 10 * rank)):
-        raw = rand_canonical(seed, N)
+    def to_mont(raw):
         p = hl.MultilinearPolynomial.new(ctx, raw)
-        hl._chk(hl.lib().b200_fr_convert(ctx.h, p.dev, p.dev, C.c_uint64(N), C.c_int(1)), "fr_convert")
-        polys.append(p)
-        pin[k].numpy().view(np.uint64)[:] = p.evals()
-    ymont = hl.MultilinearPolynomial.new(ctx, np.concatenate([rand_canonical(3 + 10 * rank, n),
-                                                              np.zeros((32 - n, 4), dtype=np.uint64)]))
-    hl._chk(hl.lib().b200_fr_convert(ctx.h, ymont.dev, ymont.dev, C.c_uint64(32), C.c_int(1)), "fr_convert")
-    y = ymont.evals()[:n]
-    one = np.array([0xAC96341C4FFFFFFB, 0x36FC76959F60CD29, 0x666EA36F7879462E, 0x0E0A77C19A07DF2F], dtype=np.uint64)
-    # claimed sum = Σ_b eq*a*b = <eq*a, b>: computed on the device with the library's own kernels
-    eq = hl.MultilinearPolynomial.eq_xy(ctx, y)
-    # evaluate(b ⊙ ?, ·) is not available as one call; use the sum-check identity instead: a first proof with an
-    # arbitrary claim is still a well-formed transcript (p(0) is derived), so timing does not depend on it.
-    claim = one.copy()
+        hl._chk(hl.lib().b200_fr_convert(ctx.h, p.dev, p.dev, C.c_uint64(raw.shape[0]), C.c_int(1)), "fr_convert")
+        return p
 
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{local_rank}")  # > 126 MB L2
+    # SRS: MultilinearKzg::setup on the device from seeded trapdoor scalars (one-off, untimed)
+    ss = to_mont(np.concatenate([rand_canonical(SRS_SEED, MU), np.zeros((32 - MU, 4), dtype=np.uint64)])).evals()[:MU]
+    t0 = time.perf_counter()
+    kzg = hl.MultilinearKzg.setup(ctx, ss)
+    ctx.sync()
+    setup_ms = 1e3 * (time.perf_counter() - t0)
+    prover = hl.LassoProver(ctx, kzg, KIND_RANGE, CHUNKS)
 
-    def step_device():
+    xs_host = torch.from_numpy(rand_u64s(X_SEED + 100 * rank, m).view(np.int64)).pin_memory()
+    xs_dev = xs_host.to(dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    proof_len = [0]
+
+    def lasso_device():
+        hl.Keccak256Transcript(ctx)
+        prover.prove_dev(MU, xs_dev.data_ptr())
+
+    def lasso_e2e():
         tr = hl.Keccak256Transcript(ctx)
-        return hl.ClassicSumCheck.prove_evals(ctx, n, polys, one.reshape(1, 4), y, claim)
+        prover.prove(xs_host.numpy().view(np.uint64))
+        proof_len[0] = len(tr.into_proof())
 
-    def step_e2e():
-        tr = hl.Keccak256Transcript(ctx)
-        out = hl.ClassicSumCheck.prove_evals_host(ctx, n, [p.data_ptr() for p in pin], one.reshape(1, 4), y, claim)
-        return out, tr.into_proof()
+    # cfg2 sum-check on resident tables
+    n, N = SC_VARS, 1 << SC_VARS
+    polys = [to_mont(rand_canonical(seed + 10 * rank, N)) for seed in (1, 2)]
+    y = to_mont(np.concatenate([rand_canonical(3 + 10 * rank, n), np.zeros((32 - n, 4), dtype=np.uint64)])).evals()[:n]
+    one = mont_one()
+
+    def sumcheck_device():
+        hl.Keccak256Transcript(ctx)
+        # any claim yields a well-formed transcript (p(0) is derived, eval.rs:129); timing is claim-independent
+        hl.ClassicSumCheck.prove_evals(ctx, n, polys, one.reshape(1, 4), y, one)
 
     def timed(fn, steps, warmup):
         for _ in range(warmup):
@@ -213,18 +245,23 @@ def main():
     sampler = ClockSampler(local_rank)
     sampler.start()
     ctx.launch_count(reset=True)
-    ms = timed(step_device, args.steps, args.warmup)
-    launches = ctx.launch_count(reset=True) // (args.steps + args.warmup)
-    ms_e2e = timed(step_e2e, max(3, args.steps // 4), 3)
+    ms = timed(lasso_device, args.steps, max(3, args.warmup))
+    launches = ctx.launch_count(reset=True) // (args.steps + max(3, args.warmup))
+    ms_e2e = timed(lasso_e2e, max(3, args.steps // 2), 3)
+    ms_sc = timed(sumcheck_device, 20, 5)
     clocks = sampler.stop()
 
-    # dominant kernel (round-1 fused bind+eval launch), timed live with CUDA events inside the library
-    prof = hl.profile_rounds(ctx, step_device) if hasattr(hl, "profile_rounds") else None
+    prof = hl.profile_rounds(ctx, sumcheck_device, SC_VARS, SC_TABLES)
+    phases = {}
+    for tag, t in hl.profile(ctx, lasso_device):
+        if tag >= 1000:
+            nm = hl.PHASE_NAMES.get(tag, str(tag))
+            phases[nm] = round(phases.get(nm, 0.0) + t, 4)
 
     if world > 1:
-        t = torch.tensor([ms, ms_e2e], device=f"cuda:{local_rank}")
+        t = torch.tensor([ms, ms_e2e, ms_sc], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, ms_e2e = t.tolist()
+        ms, ms_e2e, ms_sc = t.tolist()
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -236,31 +273,42 @@ def main():
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
-    peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
-    value = world * ALGO_BYTES / (ms * 1e-3) / 1e9
-    e2e = world * ALGO_BYTES / (ms_e2e * 1e-3) / 1e9
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
     roof = {"bound": "hbm", "achieved": None, "peak": peak, "unit": "GB/s", "frac": None, "traffic": None,
             "peak_source": peak_src}
     if prof:
         roof.update(prof)
         roof["frac"] = roof["achieved"] / peak
+    # per-launch DRAM traffic of that kernel from the committed `ncu --set full` capture (profiles/), if present
+    try:
+        roof["traffic"] = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))["dram_bytes_per_launch"]
+    except Exception:
+        pass
 
     cpu = None
-    if world == 1:
-        cms, cores = cpu_reference_leg(2, 1)
-        cpu = {"value": ALGO_BYTES / (cms * 1e-3) / 1e9, "unit": UNIT, "cores": cores, "kind": "port",
-               "ms_per_step": cms, "sample": f"whole n={NUM_VARS} proof, 2 timed repetitions (C++/OpenMP oracle)"}
+    if world == 1 and not args.no_cpu_baseline:
+        srs = [kzg.eqs(k) for k in range(MU + 1)]  # reuse the device SRS so the CPU leg skips its slow setup
+        cms, cores, _, plen = cpu_lasso(1, 0, srs)
+        cpu = {"value": cms, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"whole 2^{MU}-lookup proof once (C++/OpenMP restatement of the reference algorithms)",
+               "proof_bytes": plen}
 
     print(json.dumps({
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "u256 (BN254 Fr, 8x32-bit Montgomery limbs)", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "num_vars": n, "tables": P_TABLES, "algorithmic_bytes_per_step": ALGO_BYTES,
-                   "l2": "flushed between timed iterations (256 MiB write)", "replicas_per_gpu": 1},
+        "metric": METRIC, "value": ms, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+        "ms_per_step": ms, "higher_is_better": False, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u256 (BN254 Fr/Fq, 8x32-bit Montgomery limbs)", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "lookups": m, "chunks": CHUNKS, "subtable": 1 << 16, "proof_bytes": proof_len[0],
+                   "l2": "flushed between timed iterations (256 MiB write)", "replicas_per_gpu": 1,
+                   "srs_setup_ms_untimed": round(setup_ms, 1)},
+        "lookups_per_s": world * m / (ms * 1e-3),
         "clocks": clocks,
-        "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": 2 * N * 32 + (n + 2) * 32,
-                "d2h_bytes_per_step": (n + 2) * 32 + n * 4 * 32},
-        "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu}))
+        "e2e": {"value": ms_e2e, "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": m * 8,
+                "d2h_bytes_per_step": proof_len[0]},
+        "gpu_launches": launches, "phases_ms": phases,
+        "sumcheck": {"workload": "cfg2: ClassicSumCheck deg-3 eq*a*b, n=20, 2560 proof bytes", "ms_per_proof": ms_sc,
+                     "algorithmic_bytes": SC_ALGO_BYTES, "GBps": world * SC_ALGO_BYTES / (ms_sc * 1e-3) / 1e9,
+                     "frac_of_hbm_peak": SC_ALGO_BYTES / (ms_sc * 1e-3) / 1e9 / peak},
+        "roofline": roof, "cpu_baseline": cpu}))
     if world > 1:
         dist.destroy_process_group()
 

@@ -242,6 +242,24 @@ class ClassicSumCheck:
         return ch, ev
 
 
+PHASE_NAMES = {1000: "witness", 1001: "commit", 1002: "primary_sumcheck", 1004: "grand_product_m", 1006: "grand_product_s",
+               1007: "leaf_evals", 1008: "open_m", 1009: "open_s", 1100: "msm_sort", 1101: "msm_accumulate",
+               1102: "msm_reduce"}
+
+
+def profile(ctx, fn):
+    """Run fn() with the library's CUDA-event markers on; returns [(tag, ms), ...] in launch order."""
+    _chk(lib().b200_profile_enable(ctx.h, C.c_int(1)), "profile_enable")
+    fn()
+    cap = 1 << 16
+    ms = (C.c_float * cap)()
+    tags = (C.c_int * cap)()
+    n = C.c_int()
+    _chk(lib().b200_profile_read(ctx.h, ms, tags, C.c_int(cap), C.byref(n)), "profile_read")
+    _chk(lib().b200_profile_enable(ctx.h, C.c_int(0)), "profile_enable")
+    return [(tags[i], ms[i]) for i in range(min(n.value, cap))]
+
+
 def profile_rounds(ctx, fn, num_vars=20, tables=3):
     """Time every sum-check round launch of `fn()` with CUDA events on the library stream and return the
     roofline entry of the dominant launch (round 1: the first fused bind+evaluate over full tables)."""
@@ -299,6 +317,20 @@ class MultilinearKzg:
             assert lv.shape[0] == 1 << k
             _chk(lib().b200_kzg_srs_upload(ctx.h, C.c_int(k), _p(lv)), "srs_upload")
 
+    @classmethod
+    def setup(cls, ctx, ss):
+        """`MultilinearKzg::setup` + `trim` on the device from the trapdoor scalars ss (kzg.rs:166-250)."""
+        ss = _fr(ss).reshape(-1, 4)
+        self = cls.__new__(cls)
+        self.ctx, self.num_vars = ctx, ss.shape[0]
+        _chk(lib().b200_kzg_setup(ctx.h, _p(ss), C.c_int(ss.shape[0])), "kzg_setup")
+        return self
+
+    def eqs(self, level):
+        out = np.zeros((1 << level, 8), dtype=np.uint64)
+        _chk(lib().b200_kzg_srs_download(self.ctx.h, C.c_int(level), _p(out)), "srs_download")
+        return out
+
     def batch_commit(self, polys, write=False):
         ptrs = (C.c_void_p * len(polys))(*[p.dev for p in polys])
         nv = (C.c_int * len(polys))(*[p.num_vars for p in polys])
@@ -338,6 +370,11 @@ class LassoProver:
 
     def __init__(self, ctx, kzg, kind, chunks):
         self.ctx, self.kzg, self.kind, self.chunks = ctx, kzg, kind, chunks
+
+    def prove_dev(self, mu, dev_xs, dev_ys=None):
+        """Operands already resident on the device (raw pointers to u64 arrays); fully asynchronous."""
+        _chk(lib().b200_lasso_prove_dev(self.ctx.h, C.c_int(self.kind), C.c_int(self.chunks), C.c_int(mu),
+                                        C.c_void_p(dev_xs), C.c_void_p(dev_ys) if dev_ys else None), "lasso_prove_dev")
 
     def prove(self, xs, ys=None):
         """Appends the whole proof for the 2^mu lookups to the context transcript."""

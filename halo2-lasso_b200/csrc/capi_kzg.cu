@@ -45,6 +45,25 @@ int b200_kzg_srs_upload(b200_ctx* h, int level, const void* host_g1) {
   return B200_OK;
 }
 
+int b200_kzg_setup(b200_ctx* h, const void* host_ss_fr, int num_vars) {
+  Ctx* c = &h->c;
+  if (num_vars < 1 || num_vars > 28) return B200_ERR_ARG;
+  Fr* dss = nullptr;
+  CUDA_TRY(cudaMallocAsync(&dss, num_vars * sizeof(Fr), c->stream));
+  CUDA_TRY(cudaMemcpyAsync(dss, host_ss_fr, num_vars * sizeof(Fr), cudaMemcpyHostToDevice, c->stream));
+  int rc = kzg_setup(c, dss, num_vars);
+  CUDA_TRY(cudaFreeAsync(dss, c->stream));
+  return rc;
+}
+
+int b200_kzg_srs_download(b200_ctx* h, int level, void* host_g1_out) {
+  Ctx* c = &h->c;
+  if (level < 0 || level >= (int)c->srs.size()) return B200_ERR_ARG;
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  CUDA_TRY(cudaMemcpy(host_g1_out, c->srs[level], ((size_t)1 << level) * sizeof(G1Aff), cudaMemcpyDeviceToHost));
+  return B200_OK;
+}
+
 int b200_kzg_batch_commit(b200_ctx* h, const void* const* dev_polys, const int* num_vars, int npolys,
                           int write_transcript, void* host_out_g1) {
   Ctx* c = &h->c;

@@ -104,6 +104,7 @@ struct BatchOpenJob {
 int kzg_commit_batch(Ctx* c, const MsmJob* jobs, int J, bool write_transcript, G1Aff* d_out);
 int kzg_open(Ctx* c, const Fr* d_poly, int n, const Fr* d_point);
 int kzg_batch_open(Ctx* c, const BatchOpenJob& job);
+int kzg_setup(Ctx* c, const Fr* d_ss, int n);
 
 // lasso.cu — Lasso / Surge prover (DESIGN.md §Lasso protocol; oracle/lasso.hpp)
 int lasso_prove(Ctx* c, int kind, int chunks, int mu, const uint64_t* d_xs, const uint64_t* d_ys);
@@ -111,8 +112,9 @@ int lasso_witness(Ctx* c, int kind, int chunks, int mu, const uint64_t* d_xs, co
                   Fr* d_st);
 
 inline void count_launch(Ctx* c, int n = 1) { c->launches += n; }
-inline void prof_begin(Ctx* c, int tag) {
-  if (!c->profile) return;
+// returns the index of the (start, stop) event pair, or -1 when profiling is off; pairs may nest
+inline int prof_begin(Ctx* c, int tag) {
+  if (!c->profile) return -1;
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0);
   cudaEventCreate(&e1);
@@ -120,11 +122,16 @@ inline void prof_begin(Ctx* c, int tag) {
   c->prof_events.push_back(e1);
   c->prof_tags.push_back(tag);
   cudaEventRecord(e0, c->stream);
+  return (int)c->prof_tags.size() - 1;
 }
-inline void prof_end(Ctx* c) {
-  if (!c->profile) return;
-  cudaEventRecord(c->prof_events.back(), c->stream);
+inline void prof_end(Ctx* c, int idx) {
+  if (idx < 0) return;
+  cudaEventRecord(c->prof_events[2 * idx + 1], c->stream);
 }
+enum {  // phase tags (>= 1000) of lasso_prove; tags < 1000 are sum-check round indices
+  PH_WITNESS = 1000, PH_COMMIT, PH_PRIMARY, PH_TREES_M, PH_GKR_M, PH_TREES_S, PH_GKR_S, PH_LEAF_EVALS,
+  PH_OPEN_M, PH_OPEN_S, PH_MSM_SORT = 1100, PH_MSM_ACC, PH_MSM_REDUCE
+};
 
 }  // namespace b200
 

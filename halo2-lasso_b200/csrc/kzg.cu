@@ -146,4 +146,85 @@ int kzg_batch_open(Ctx* c, const BatchOpenJob& job) {
   return B200_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// MultilinearKzg::setup (kzg.rs:166-213): eqs[k][b] = g1 * Π_{j<k} (b_j ? s_j : 1 - s_j), k = 0..n.
+// The reference builds the scalar tables by doubling and runs `fixed_base_msm` with a window table;
+// here eq_build produces each level's scalars and one thread per point adds 32 byte-window table
+// entries (mixed adds) and normalises. One-off cost, not on the prove path.
+// ---------------------------------------------------------------------------------------------
+__global__ void srs_window_bases_kernel(G1Xyzz* bases) {  // bases[w] = 2^(8w) * G, w < 32
+  const int w = threadIdx.x;
+  if (w >= 32) return;
+  G1Aff g;
+  g.x = fe_from_u64<FqP>(1);
+  g.y = fe_from_u64<FqP>(2);
+  G1Xyzz acc = g1_from_affine(g);
+  for (int k = 0; k < 8 * w; ++k) acc = g1_dbl(acc);
+  bases[w] = acc;
+}
+__global__ void srs_window_table_kernel(const G1Xyzz* bases, G1Aff* table) {  // table[w*255 + d-1] = d * bases[w]
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 32 * 255) return;
+  const int w = i / 255, d = i % 255 + 1;
+  table[i] = g1_to_affine(g1_mul_small(bases[w], (uint32_t)d));
+}
+__global__ void __launch_bounds__(128) srs_fixed_base_kernel(const Fr* __restrict__ scalars, size_t n,
+                                                             const G1Aff* __restrict__ table, G1Aff* __restrict__ out) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const Fr s = fe_to_canonical<FrP>(fe_ldg(scalars + i));
+    G1Xyzz acc = g1_identity();
+    for (int w = 0; w < 32; ++w) {
+      const uint32_t byte = (s.v[w >> 2] >> (8 * (w & 3))) & 0xff;
+      if (byte) {
+        G1Aff p;
+        p.x = fe_ldg(&table[w * 255 + byte - 1].x);
+        p.y = fe_ldg(&table[w * 255 + byte - 1].y);
+        acc = g1_add_affine(acc, p, false);
+      }
+    }
+    const G1Aff a = g1_to_affine(acc);
+    fe_st(&out[i].x, a.x);
+    fe_st(&out[i].y, a.y);
+  }
+}
+__global__ void fill_one_fr_kernel(Fr* out) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) fe_st(out, fe_one<FrP>());
+}
+
+int kzg_setup(Ctx* c, const Fr* d_ss, int n) {
+  if (n < 1 || n > 28 || !c->srs.empty()) return B200_ERR_ARG;
+  cudaStream_t s = c->stream;
+  G1Xyzz* bases = nullptr;
+  G1Aff* table = nullptr;
+  Fr* eq = nullptr;
+  CUDA_TRY(cudaMallocAsync(&bases, 32 * sizeof(G1Xyzz), s));
+  CUDA_TRY(cudaMallocAsync(&table, 32 * 255 * sizeof(G1Aff), s));
+  CUDA_TRY(cudaMallocAsync(&eq, ((size_t)1 << n) * sizeof(Fr), s));
+  srs_window_bases_kernel<<<1, 32, 0, s>>>(bases);
+  srs_window_table_kernel<<<(32 * 255 + 127) / 128, 128, 0, s>>>(bases, table);
+  count_launch(c, 2);
+  for (int k = 0; k <= n; ++k) {
+    const size_t N = (size_t)1 << k;
+    G1Aff* lvl = nullptr;
+    CUDA_TRY(cudaMalloc(&lvl, N * sizeof(G1Aff)));
+    if (k == 0) {
+      fill_one_fr_kernel<<<1, 32, 0, s>>>(eq);
+    } else {
+      int rc = eq_build(c, d_ss, k, eq);
+      if (rc) return rc;
+    }
+    int blocks = (int)((N + 127) / 128);
+    if (blocks > NUM_SMS * 16) blocks = NUM_SMS * 16;
+    srs_fixed_base_kernel<<<blocks, 128, 0, s>>>(eq, N, table, lvl);
+    count_launch(c, 2);
+    c->srs.push_back(lvl);
+  }
+  CUDA_TRY(cudaFreeAsync(bases, s));
+  CUDA_TRY(cudaFreeAsync(table, s));
+  CUDA_TRY(cudaFreeAsync(eq, s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  return B200_OK;
+}
+
 }  // namespace b200

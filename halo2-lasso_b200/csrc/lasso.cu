@@ -287,6 +287,7 @@ int lasso_prove(Ctx* c, int kind, int chunks, int mu, const uint64_t* d_xs, cons
   const size_t S = SUB_SIZE;
 
   // ---- 1. witness -------------------------------------------------------------------------------
+  int ph = prof_begin(c, PH_WITNESS);
   uint32_t *dims, *es, *ts, *cts, *hist, *base;
   uint64_t* a_u64;
   const uint32_t nch = m >= (1u << 13) ? (m / 32768 > 128 ? m / 32768 : 128) : 1;
@@ -361,6 +362,8 @@ int lasso_prove(Ctx* c, int kind, int chunks, int mu, const uint64_t* d_xs, cons
   }
   rc = transcript_op(c, TR_COMMON, stmt, nullptr, 3);
   if (rc) return rc;
+  prof_end(c, ph);
+  ph = prof_begin(c, PH_COMMIT);
 
   // ---- 2. commitments: a, dim_*, E_*, read_ts_* (level mu), final_cts_* (level 16) -----------------
   {
@@ -379,6 +382,8 @@ int lasso_prove(Ctx* c, int kind, int chunks, int mu, const uint64_t* d_xs, cons
     CUDA_TRY(cudaFreeAsync(comms, s));
   }
 
+  prof_end(c, ph);
+  ph = prof_begin(c, PH_PRIMARY);
   // ---- 3-5. primary Surge sum-check ----------------------------------------------------------------
   rc = transcript_op(c, TR_SQUEEZE, nullptr, r, mu);
   if (rc) return rc;
@@ -406,6 +411,8 @@ int lasso_prove(Ctx* c, int kind, int chunks, int mu, const uint64_t* d_xs, cons
   rc = transcript_op(c, TR_WRITE, e_p, nullptr, C_);
   if (rc) return rc;
 
+  prof_end(c, ph);
+  ph = prof_begin(c, PH_GKR_M);
   // ---- 6-8. memory checking -------------------------------------------------------------------------
   rc = transcript_op(c, TR_SQUEEZE, nullptr, gt, 2);
   if (rc) return rc;
@@ -425,6 +432,8 @@ int lasso_prove(Ctx* c, int kind, int chunks, int mu, const uint64_t* d_xs, cons
   if (rc) return rc;
   // x_m = gp->y[0..mu)
   copy_fr_kernel<<<1, 64, 0, s>>>(gp->y, pts + 2 * (size_t)mu, mu);
+  prof_end(c, ph);
+  ph = prof_begin(c, PH_GKR_S);
   rc = grand_product_prove(c, strees, (size_t)2 * S, T, SUB_VARS, gp, x_scratch);
   if (rc) return rc;
   copy_fr_kernel<<<1, 64, 0, s>>>(gp->y, pt_s, SUB_VARS);
@@ -432,6 +441,8 @@ int lasso_prove(Ctx* c, int kind, int chunks, int mu, const uint64_t* d_xs, cons
   CUDA_TRY(cudaFreeAsync(mtrees, s));
   CUDA_TRY(cudaFreeAsync(strees, s));
 
+  prof_end(c, ph);
+  ph = prof_begin(c, PH_LEAF_EVALS);
   // ---- 9. leaf openings -----------------------------------------------------------------------------
   {
     const Fr* tabs[3 * 8];
@@ -447,6 +458,8 @@ int lasso_prove(Ctx* c, int kind, int chunks, int mu, const uint64_t* d_xs, cons
   rc = transcript_op(c, TR_WRITE, ev_s, nullptr, C_);
   if (rc) return rc;
 
+  prof_end(c, ph);
+  ph = prof_begin(c, PH_OPEN_M);
   // ---- 10. batch openings ---------------------------------------------------------------------------
   {
     copy_fr_kernel<<<1, 64, 0, s>>>(r, pts, mu);
@@ -470,12 +483,15 @@ int lasso_prove(Ctx* c, int kind, int chunks, int mu, const uint64_t* d_xs, cons
     BatchOpenJob bj{mu, NM, 3, E, polys, pts, ev_poly, ev_point, vals};
     rc = kzg_batch_open(c, bj);
     if (rc) return rc;
+    prof_end(c, ph);
+    ph = prof_begin(c, PH_OPEN_S);
     const Fr* spolys[8];
     int sp[8], spt[8];
     for (int t = 0; t < C_; ++t) spolys[t] = st_tabs + (size_t)t * S, sp[t] = t, spt[t] = 0;
     BatchOpenJob sj{SUB_VARS, C_, 1, C_, spolys, pt_s, sp, spt, ev_s};
     rc = kzg_batch_open(c, sj);
     if (rc) return rc;
+    prof_end(c, ph);
     CUDA_TRY(cudaFreeAsync(vals, s));
   }
   for (void* p : {(void*)dims, (void*)es, (void*)ts, (void*)cts, (void*)a_u64, (void*)hist, (void*)base, (void*)mt,

@@ -451,6 +451,7 @@ int msm_batch(Ctx* c, const MsmJob* jobs, int J, G1Aff* d_out) {
   CUDA_TRY(cudaMemsetAsync(heavy_count, 0, 4, s));
 
   dim3 grid((max_n + 255) / 256, J);
+  int pi = prof_begin(c, PH_MSM_SORT);
   msm_digits_kernel<0><<<grid, 256, 0, s>>>(plan, cnt, nullptr, ranks, nullptr);
   count_launch(c);
   int rc = exclusive_scan(c, cnt, nbuckets, boff, scratch, 0);
@@ -458,13 +459,18 @@ int msm_batch(Ctx* c, const MsmJob* jobs, int J, G1Aff* d_out) {
   rc = exclusive_scan(c, cnt, nbuckets, toff, scratch, 1);
   if (rc) return rc;
   msm_digits_kernel<1><<<grid, 256, 0, s>>>(plan, nullptr, boff, ranks, sorted);
+  prof_end(c, pi);
+  pi = prof_begin(c, PH_MSM_ACC);
   // persistent-style grids: a multiple of the SM count, tasks are grid-strided
   msm_accumulate_kernel<<<NUM_SMS * 16, 128, 0, s>>>(plan, nbuckets, cnt, boff, toff, sorted, partial);
+  prof_end(c, pi);
+  pi = prof_begin(c, PH_MSM_REDUCE);
   msm_bucket_kernel<<<(nbuckets + 127) / 128, 128, 0, s>>>(nbuckets, toff, partial, bucket_sum, heavy, heavy_count);
   msm_heavy_kernel<<<NUM_SMS * 4, 128, 0, s>>>(toff, partial, bucket_sum, heavy, heavy_count);
   msm_group_kernel<<<(ngroups + 127) / 128, 128, 0, s>>>(plan, ngroups, bucket_sum, group_sum);
   msm_window_kernel<<<nwin, 128, 0, s>>>(plan, group_sum, window_sum);
   msm_finish_kernel<<<(J + 31) / 32, 32, 0, s>>>(plan, window_sum, d_out);
+  prof_end(c, pi);
   count_launch(c, 7);
   CUDA_TRY(cudaGetLastError());
   for (void* p : {(void*)cnt, (void*)boff, (void*)toff, (void*)ranks, (void*)sorted, (void*)scratch, (void*)heavy,

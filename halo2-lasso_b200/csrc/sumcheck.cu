@@ -216,7 +216,7 @@ int sumcheck_prove_evals(Ctx* c, const ScEvalJob& job) {
     }
     dim3 grid(blocks_for(a.pairs, T), T);
     if ((size_t)grid.x * grid.y * (NP + 1) > c->partial_elems) return B200_ERR_NOMEM;
-    prof_begin(c, round);
+    const int pi = prof_begin(c, round);
     if (round == 0) {
       if (NP == 1) sc_eval_round_kernel<1, false><<<grid, SC_THREADS, 0, s>>>(a);
       else sc_eval_round_kernel<2, false><<<grid, SC_THREADS, 0, s>>>(a);
@@ -225,7 +225,7 @@ int sumcheck_prove_evals(Ctx* c, const ScEvalJob& job) {
       else sc_eval_round_kernel<2, true><<<grid, SC_THREADS, 0, s>>>(a);
       for (int i = 0; i <= ntab; ++i) cur[i] = (i < ntab) ? a.out[i] : a.eq_out;
     }
-    prof_end(c);
+    prof_end(c, pi);
     count_launch(c);
   }
   // final bind -> evals (eq excluded: ProverState::into_evals returns the polys only, classic.rs:143-149)

@@ -110,6 +110,11 @@ int b200_variable_base_msm(b200_ctx* ctx, const void* host_scalars_fr, const voi
 /* ProverParam: upload eqs[level] (2^level affine points, kzg.rs:36-53, :230-245 trim). Levels must be
  * uploaded in increasing order starting from 0. */
 int b200_kzg_srs_upload(b200_ctx* ctx, int level, const void* host_g1);
+/* setup + trim (kzg.rs:166-250) on the device from the trapdoor scalars ss[0..num_vars) (the reference
+ * samples them from its RNG; here the caller supplies them): builds eqs[0..=num_vars]. */
+int b200_kzg_setup(b200_ctx* ctx, const void* host_ss_fr, int num_vars);
+/* copy eqs[level] (2^level affine points) back to the host */
+int b200_kzg_srs_download(b200_ctx* ctx, int level, void* host_g1_out);
 /* batch_commit (kzg.rs:259-274): one MSM per polynomial against eqs[num_vars[i]]; out[npolys] affine.
  * write_transcript != 0 also performs write_commitments (Pcs::batch_commit_and_write, pcs.rs:62-75). */
 int b200_kzg_batch_commit(b200_ctx* ctx, const void* const* dev_polys, const int* num_vars, int npolys,

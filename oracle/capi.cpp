@@ -158,6 +158,19 @@ void orc_msm(const Fr* scalars, const G1Affine* bases, uint64_t n, G1Affine* out
   *out = variable_base_msm(scalars, bases, n).to_affine();
 }
 void* orc_kzg_setup(const Fr* ss, int n) { return new KzgParams(kzg_setup(std::vector<Fr>(ss, ss + n))); }
+// import an SRS produced elsewhere (e.g. downloaded from the GPU): eqs_flat = eqs[0] | eqs[1] | ... | eqs[n]
+void* orc_kzg_import(const Fr* ss, int n, const G1Affine* eqs_flat) {
+  KzgParams* p = new KzgParams();
+  p->num_vars = n;
+  p->ss.assign(ss, ss + n);
+  p->eqs.resize(n + 1);
+  size_t off = 0;
+  for (int k = 0; k <= n; ++k) {
+    p->eqs[k].assign(eqs_flat + off, eqs_flat + off + ((size_t)1 << k));
+    off += (size_t)1 << k;
+  }
+  return p;
+}
 void orc_kzg_free(void* h) { delete (KzgParams*)h; }
 void orc_kzg_eqs(void* h, int level, G1Affine* out) {
   auto& e = ((KzgParams*)h)->eqs[level];

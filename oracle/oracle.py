@@ -34,6 +34,7 @@ def lib():
         _lib.orc_tr_new.restype = C.c_void_p
         _lib.orc_tr_from_proof.restype = C.c_void_p
         _lib.orc_kzg_setup.restype = C.c_void_p
+        _lib.orc_kzg_import.restype = C.c_void_p
         _lib.orc_tr_proof_len.restype = C.c_uint64
         _lib.orc_rand_u64.restype = C.c_uint64
     return _lib
@@ -298,6 +299,16 @@ class Kzg:
         self.num_vars = ss.shape[0]
         self.ss = ss
         self.h = C.c_void_p(lib().orc_kzg_setup(_p(ss), C.c_int(self.num_vars)))
+
+    @classmethod
+    def from_eqs(cls, ss, levels):
+        """Wrap an SRS computed elsewhere (levels[k]: (2^k, 8) affine points)."""
+        ss = np.ascontiguousarray(ss, dtype=np.uint64).reshape(-1, 4)
+        flat = np.ascontiguousarray(np.concatenate([np.asarray(l, dtype=np.uint64).reshape(-1, 8) for l in levels]))
+        self = cls.__new__(cls)
+        self.num_vars, self.ss = ss.shape[0], ss
+        self.h = C.c_void_p(lib().orc_kzg_import(_p(ss), C.c_int(ss.shape[0]), _p(flat)))
+        return self
 
     def __del__(self):
         if getattr(self, "h", None):
