@@ -1,0 +1,147 @@
+"""Oracle self-consistency: the reference's own test shapes (prove -> verify round trips) and
+its `sanity-check` invariants, plus the Lasso specification's soundness negatives."""
+import numpy as np
+import pytest
+
+import oracle as O
+
+
+@pytest.fixture(scope="module")
+def kz16():
+    return O.Kzg(O.rand_fr(7, 16))
+
+
+@pytest.mark.parametrize("n", [1, 2, 7, 11])
+def test_sumcheck_roundtrip_like_reference(n):
+    """pb/piop/sum_check.rs:140-177: prove, re-read, verify, recompute the virtual polynomial at x."""
+    a, b, y = O.rand_fr(1, 1 << n), O.rand_fr(2, 1 << n), O.rand_fr(3, n)
+    s = O.sum_eq_ab(y, a, b)
+    one = O.fr_from_ints([1])[0]
+    tr = O.Transcript()
+    ch, ev = O.sumcheck_prove_evals(tr, n, [a, b], y, [(one, [0, 1])], s)
+    assert len(tr.proof()) == n * 4 * 32
+    fin, chv = O.sumcheck_verify(O.Transcript(tr.proof()), n, 3, s)
+    assert (chv == ch).all()
+    assert (O.evaluate(a, ch) == ev[0]).all() and (O.evaluate(b, ch) == ev[1]).all()
+    assert (O.field_op("mul", O.field_op("mul", O.eq_xy_eval(ch, y), ev[0]), ev[1])[0] == fin).all()
+    # a wrong claimed sum is caught at round 0 ("Expect sum ... but get ...", classic.rs:185-190)?  No:
+    # p(0) is derived from the claim, so the transcript stays consistent and only the final check fails.
+    bad = O.field_op("add", s, one)[0]
+    tr2 = O.Transcript()
+    ch2, ev2 = O.sumcheck_prove_evals(tr2, n, [a, b], y, [(one, [0, 1])], bad)
+    fin2, _ = O.sumcheck_verify(O.Transcript(tr2.proof()), n, 3, bad)
+    assert not (O.field_op("mul", O.field_op("mul", O.eq_xy_eval(ch2, y), ev2[0]), ev2[1])[0] == fin2).all()
+
+
+def test_mle_fix_var_evaluate_agree():
+    """pb/poly/multilinear.rs:663-712: evaluate == iterated fix_var, incl. boolean coordinates."""
+    n = 9
+    p = O.rand_fr(4, 1 << n)
+    x = O.rand_fr(5, n)
+    x[2] = O.fr_from_ints([0])[0]
+    x[5] = O.fr_from_ints([1])[0]
+    cur = p
+    for i in range(n):
+        cur = O.fix_var(cur, x[i])
+    assert (cur[0] == O.evaluate(p, x)).all()
+    eq = O.eq_xy(x)
+    acc = O.fr_from_ints([0])
+    acc = O.fr_from_ints([sum(a * b for a, b in zip(O.fr_to_ints(p), O.fr_to_ints(eq))) % O.R_MOD])
+    assert (acc[0] == O.evaluate(p, x)).all()  # <p, eq(., x)> — the identity the GPU evaluate uses
+
+
+@pytest.mark.parametrize("nv", [3, 8])
+def test_kzg_commit_open_verify(kz16, nv):
+    """pb/pcs/multilinear.rs:293-338 harness shape + sanity-check invariants of kzg.rs:286-297."""
+    poly, pt = O.rand_fr(10 + nv, 1 << nv), O.rand_fr(20 + nv, nv)
+    cm = kz16.commit(poly)
+    tr = O.Transcript()
+    ev = kz16.open(tr, poly, pt)
+    assert (ev == O.evaluate(poly, pt)).all()
+    assert kz16.verify(O.Transcript(tr.proof()), cm, pt, ev)
+    wrong = O.field_op("add", ev, O.fr_from_ints([1]))[0]
+    assert not kz16.verify(O.Transcript(tr.proof()), cm, pt, wrong)
+    # commitment homomorphism (pcs/multilinear.rs:215-226)
+    q = O.rand_fr(30 + nv, 1 << nv)
+    assert (O.g1_add(cm, kz16.commit(q)) == kz16.commit(O.field_op("add", poly, q))).all()
+
+
+def test_msm_matches_naive(kz16):
+    n = 70
+    sc = O.rand_fr(40, n)
+    bases = kz16.eqs(7)[:n]
+    acc = np.zeros(8, dtype=np.uint64)
+    for s, b in zip(sc, bases):
+        acc = O.g1_add(acc, O.g1_mul(b, s))
+    assert (O.msm(sc, bases) == acc).all()
+    assert (O.msm(sc[:0], bases[:0]) == 0).all()
+
+
+def test_batch_open_verify_roundtrip(kz16):
+    """pb/pcs/multilinear.rs:340-406: 8 polys, 4 points, random (poly, point) pairs."""
+    nv = 6
+    polys = [O.rand_fr(50 + i, 1 << nv) for i in range(8)]
+    points = [O.rand_fr(60 + i, nv) for i in range(4)]
+    pairs = [(i % 8, (3 * i) % 4) for i in range(11)]
+    evals = [(p, q, O.evaluate(polys[p], points[q])) for p, q in pairs]
+    tr = O.Transcript()
+    kz16.batch_open(tr, polys, points, evals)
+    comms = [kz16.commit(p) for p in polys]
+    assert kz16.batch_verify(O.Transcript(tr.proof()), comms, points, evals)
+    evals[3] = (evals[3][0], evals[3][1], O.field_op("add", evals[3][2], O.fr_from_ints([1]))[0])
+    assert not kz16.batch_verify(O.Transcript(tr.proof()), comms, points, evals)
+
+
+def test_grand_product_claims_are_leaf_evaluations():
+    """template invariant (fractional_sum_check.rs:184-187): returned claims == leaf MLEs at the point."""
+    T, h = 3, 5
+    leaves = [O.rand_fr(70 + t, 1 << h) for t in range(T)]
+    tr = O.Transcript()
+    claims, point = O.grand_product_prove(tr, leaves)
+    for t in range(T):
+        assert (claims[t] == O.evaluate(leaves[t], point)).all()
+
+
+def _ops(kind, chunks, mu, seed):
+    xs, ys = O.rand_u64s(seed, 1 << mu), O.rand_u64s(seed + 1, 1 << mu)
+    bits = (16 if kind == O.TABLE_RANGE else 8) * chunks
+    if bits < 64:
+        xs &= np.uint64((1 << bits) - 1)
+        ys &= np.uint64((1 << bits) - 1)
+    xs[1::2], ys[1::2] = xs[0::2], ys[0::2]
+    return xs, (None if kind == O.TABLE_RANGE else ys)
+
+
+@pytest.mark.parametrize("kind,chunks,mu", [(O.TABLE_RANGE, 4, 5), (O.TABLE_AND, 8, 4), (O.TABLE_XOR, 2, 6)])
+def test_lasso_prove_verify_and_negatives(kz16, kind, chunks, mu):
+    xs, ys = _ops(kind, chunks, mu, 80 + mu)
+    tr = O.Transcript()
+    assert O.lasso_prove(kz16, tr, kind, chunks, mu, xs, ys)
+    proof = tr.proof()
+    assert O.lasso_verify(kz16, O.Transcript(proof), kind, chunks, mu)
+    for pos in (10, len(proof) // 4, len(proof) // 2, len(proof) - 5):
+        bad = bytearray(proof)
+        bad[pos] ^= 0x01
+        assert not O.lasso_verify(kz16, O.Transcript(bytes(bad)), kind, chunks, mu), pos
+    assert not O.lasso_verify(kz16, O.Transcript(proof[:-64]), kind, chunks, mu)  # truncated
+    assert not O.lasso_verify(kz16, O.Transcript(proof), kind, chunks, mu + 1) if mu < 15 else True
+
+
+def test_lasso_witness_semantics():
+    """read_ts = # earlier accesses, final_cts = total accesses, E = T[dim], a = g(E)."""
+    mu, c = 6, 4
+    xs, _ = _ops(O.TABLE_RANGE, c, mu, 90)
+    mt, st = O.lasso_witness(O.TABLE_RANGE, c, mu, xs)
+    a = O.fr_to_ints(mt[0])
+    assert a == [int(x) for x in xs]
+    for t in range(c):
+        dim = O.fr_to_ints(mt[1 + t])
+        assert dim == [(int(x) >> (16 * t)) & 0xFFFF for x in xs]
+        assert O.fr_to_ints(mt[1 + c + t]) == dim  # identity subtable
+        seen, ts = {}, []
+        for d in dim:
+            ts.append(seen.get(d, 0))
+            seen[d] = seen.get(d, 0) + 1
+        assert O.fr_to_ints(mt[1 + 2 * c + t]) == ts
+        cts = O.fr_to_ints(st[t])
+        assert all(cts[d] == n for d, n in seen.items()) and sum(cts) == 1 << mu
