@@ -151,8 +151,8 @@ __global__ void __launch_bounds__(256) lasso_leaves_s_kernel(int kind, int c, co
   fe_st(fi + x, v + fe_ldg(cts_fr + (size_t)t * SUB_SIZE + x));
 }
 
-// one tree layer for all trees: V_k[i] = V_{k+1}[i] * V_{k+1}[i + 2^k]; tree arrays are heap-ordered
-// (layer k at [2^k, 2^(k+1)))
+// one tree layer for a group of equally sized trees: V_k[i] = V_{k+1}[i] * V_{k+1}[i + 2^k]; tree
+// arrays are heap-ordered (layer k at [2^k, 2^(k+1)))
 __global__ void __launch_bounds__(256) tree_up_kernel(Fr* __restrict__ trees, size_t tree_stride, uint32_t half) {
   Fr* tr = trees + (size_t)blockIdx.y * tree_stride;
   const uint32_t stride = gridDim.x * blockDim.x;
@@ -162,20 +162,25 @@ __global__ void __launch_bounds__(256) tree_up_kernel(Fr* __restrict__ trees, si
 
 // ---- grand-product bookkeeping kernels (single warp, warp-cooperative transcript) ----------------
 struct GpState {
-  Fr claims[SC_MAX_TERMS];
-  Fr weights[SC_MAX_TERMS];
+  Fr claims[SC_MAX_TERMS];   // indexed by TREE id
+  Fr weights[SC_MAX_TERMS];  // indexed by slot in the active list of the current layer
   Fr claim;
   Fr y[32];
-  Fr evals[2 * SC_MAX_TERMS];
+  Fr evals[2 * SC_MAX_TERMS];  // (l, r) per active slot
+};
+struct GpTrees {
+  const Fr* base[SC_MAX_TERMS];  // heap-ordered tree arrays
+  int height[SC_MAX_TERMS];
+  int T;
 };
 
 // write the roots, which are the first claims
-__global__ void gp_roots_kernel(Transcript* tr, const Fr* trees, size_t tree_stride, int T, GpState* st) {
+__global__ void gp_roots_kernel(Transcript* tr, GpTrees trees, GpState* st) {
   __shared__ Transcript sh_tr;
   if (threadIdx.x == 0) sh_tr = *tr;
   __syncwarp();
-  for (int t = 0; t < T; ++t) {
-    const Fr root = fe_ld(trees + (size_t)t * tree_stride + 1);
+  for (int t = 0; t < trees.T; ++t) {
+    const Fr root = fe_ld(trees.base[t] + 1);
     if (threadIdx.x == 0) fe_st(&st->claims[t], root);
     trw_write_fe(&sh_tr, root);
   }
@@ -183,16 +188,17 @@ __global__ void gp_roots_kernel(Transcript* tr, const Fr* trees, size_t tree_str
   if (threadIdx.x == 0) *tr = sh_tr;
 }
 
-// layer k transition. before_sumcheck: (k == 0) gather the two children as evals; (k > 0) squeeze gamma,
-// weights = gamma^t, claim = Σ weights*claims.   after_sumcheck: write evals, squeeze mu, fold claims,
-// y = x || mu.
-__global__ void gp_before_kernel(Transcript* tr, const Fr* trees, size_t tree_stride, int T, int k, GpState* st) {
+// Layer k, before the sum-check. k == 0: the two children are the evaluations. k > 0: squeeze gamma,
+// weights = gamma^slot over the ACTIVE trees (height > k, input order), claim = Σ weights * claims.
+__global__ void gp_before_kernel(Transcript* tr, GpTrees trees, int k, GpState* st) {
   __shared__ Transcript sh_tr;
   const int lane = threadIdx.x;
   if (k == 0) {
-    for (int i = lane; i < 2 * T; i += 32) {
-      const Fr v = fe_ld(trees + (size_t)(i >> 1) * tree_stride + 2 + (i & 1));
-      fe_st(&st->evals[i], v);
+    int slot = 0;
+    for (int t = 0; t < trees.T; ++t) {
+      if (trees.height[t] <= 0) continue;
+      if (lane < 2) fe_st(&st->evals[2 * slot + lane], fe_ld(trees.base[t] + 2 + lane));
+      ++slot;
     }
     return;
   }
@@ -200,27 +206,43 @@ __global__ void gp_before_kernel(Transcript* tr, const Fr* trees, size_t tree_st
   __syncwarp();
   const Fr gamma = trw_squeeze(&sh_tr);
   Fr pw = fe_one<FrP>(), claim = fe_zero<FrP>();
-  for (int t = 0; t < T; ++t) {
-    if (lane == 0) fe_st(&st->weights[t], pw);
+  int slot = 0;
+  for (int t = 0; t < trees.T; ++t) {
+    if (trees.height[t] <= k) continue;
+    if (lane == 0) fe_st(&st->weights[slot], pw);
     claim = claim + fr_mul_ni(pw, fe_ld(&st->claims[t]));
     pw = fr_mul_ni(pw, gamma);
+    ++slot;
   }
   if (lane == 0) {
     fe_st(&st->claim, claim);
     *tr = sh_tr;
   }
 }
-__global__ void gp_after_kernel(Transcript* tr, int T, int k, const Fr* x /* k challenges, may be null */,
-                                GpState* st) {
+// after the sum-check: write the 2A evaluations, squeeze mu, fold the active claims, y = x || mu
+__global__ void gp_after_kernel(Transcript* tr, GpTrees trees, int k, const Fr* x /* k challenges */, GpState* st) {
   __shared__ Transcript sh_tr;
   const int lane = threadIdx.x;
   if (lane == 0) sh_tr = *tr;
   __syncwarp();
-  for (int i = 0; i < 2 * T; ++i) trw_write_fe(&sh_tr, fe_ld(&st->evals[i]));
+  int A = 0;
+  for (int t = 0; t < trees.T; ++t) A += trees.height[t] > k;
+  // canonical forms of up to 32 evaluations per pass in parallel lanes
+  for (int base = 0; base < 2 * A; base += 32) {
+    const int i = base + lane;
+    const Fr canon = fr_canon_ni(i < 2 * A ? fe_ld(&st->evals[i]) : fe_zero<FrP>());
+    const int cnt = 2 * A - base < 32 ? 2 * A - base : 32;
+    for (int j = 0; j < cnt; ++j) trw_write_canon_from_lane(&sh_tr, canon, j, true);
+  }
   const Fr mu = trw_squeeze(&sh_tr);
-  for (int t = lane; t < T; t += 32) {
-    const Fr l = fe_ld(&st->evals[2 * t]), r = fe_ld(&st->evals[2 * t + 1]);
-    fe_st(&st->claims[t], l + fr_mul_ni(mu, r - l));
+  int slot = 0;
+  for (int t = 0; t < trees.T; ++t) {
+    if (trees.height[t] <= k) continue;
+    if (lane == (slot & 31)) {
+      const Fr l = fe_ld(&st->evals[2 * slot]), r = fe_ld(&st->evals[2 * slot + 1]);
+      fe_st(&st->claims[t], l + (r - l) * mu);
+    }
+    ++slot;
   }
   for (int i = lane; i < k; i += 32) fe_st(&st->y[i], fe_ld(x + i));
   if (lane == 0) {
@@ -229,33 +251,36 @@ __global__ void gp_after_kernel(Transcript* tr, int T, int k, const Fr* x /* k c
   }
 }
 
-// Batched product argument over T heap-ordered trees of height h. Leaves claims in st->claims and the
-// point in st->y[0..h).
-static int grand_product_prove(Ctx* c, Fr* trees, size_t tree_stride, int T, int h, GpState* st, Fr* scratch_x) {
+__global__ void copy_fr_kernel(const Fr* src, Fr* dst, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) fe_st(dst + i, fe_ld(src + i));
+}
+
+// Batched product argument over heap-ordered trees of possibly DIFFERENT heights (oracle/lasso.hpp
+// grand_product_prove). After layer h-1 the running point (h coordinates) is copied to point_out[h]
+// when that pointer is non-null; the per-tree claims stay in st->claims.
+static int grand_product_prove(Ctx* c, const GpTrees& trees, GpState* st, Fr* scratch_x, Fr* const* point_out) {
   cudaStream_t s = c->stream;
-  for (int k = h - 1; k >= 0; --k) {
-    const uint32_t half = 1u << k;
-    int bx = (int)((half + 255) / 256);
-    int cap = (4 * NUM_SMS + T - 1) / T;
-    if (bx > cap) bx = cap;
-    tree_up_kernel<<<dim3(bx, T), 256, 0, s>>>(trees, tree_stride, half);
-    count_launch(c);
-  }
-  gp_roots_kernel<<<1, 32, 0, s>>>(c->d_tr, trees, tree_stride, T, st);
+  int h = 0;
+  for (int t = 0; t < trees.T; ++t) h = trees.height[t] > h ? trees.height[t] : h;
+  gp_roots_kernel<<<1, 32, 0, s>>>(c->d_tr, trees, st);
   count_launch(c);
   for (int k = 0; k < h; ++k) {
-    gp_before_kernel<<<1, 32, 0, s>>>(c->d_tr, trees, tree_stride, T, k, st);
+    gp_before_kernel<<<1, 32, 0, s>>>(c->d_tr, trees, k, st);
     count_launch(c);
     if (k > 0) {
       ScEvalJob job;
       job.num_vars = k;
-      job.T = T;
       job.NP = 2;
-      for (int t = 0; t < T; ++t) {
-        const Fr* l = trees + (size_t)t * tree_stride + ((size_t)2 << k);
-        job.tables[2 * t] = l;
-        job.tables[2 * t + 1] = l + ((size_t)1 << k);
+      int A = 0;
+      for (int t = 0; t < trees.T; ++t) {
+        if (trees.height[t] <= k) continue;
+        const Fr* l = trees.base[t] + ((size_t)2 << k);
+        job.tables[2 * A] = l;
+        job.tables[2 * A + 1] = l + ((size_t)1 << k);
+        ++A;
       }
+      job.T = A;
       job.weights = st->weights;
       job.eq_point = st->y;
       job.claim = &st->claim;
@@ -264,17 +289,17 @@ static int grand_product_prove(Ctx* c, Fr* trees, size_t tree_stride, int T, int
       int rc = sumcheck_prove_evals(c, job);
       if (rc) return rc;
     }
-    gp_after_kernel<<<1, 32, 0, s>>>(c->d_tr, T, k, scratch_x, st);
+    gp_after_kernel<<<1, 32, 0, s>>>(c->d_tr, trees, k, scratch_x, st);
     count_launch(c);
+    if (point_out[k + 1]) {
+      copy_fr_kernel<<<1, 64, 0, s>>>(st->y, point_out[k + 1], k + 1);
+      count_launch(c);
+    }
   }
   CUDA_TRY(cudaGetLastError());
   return B200_OK;
 }
 
-__global__ void copy_fr_kernel(const Fr* src, Fr* dst, int n) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) fe_st(dst + i, fe_ld(src + i));
-}
 
 int lasso_prove(Ctx* c, int kind, int chunks, int mu, const uint64_t* d_xs, const uint64_t* d_ys) {
   if (kind < 0 || kind > 2 || chunks < 1 || chunks > 8 || mu < 1 || mu > 26) return B200_ERR_ARG;
@@ -428,16 +453,44 @@ int lasso_prove(Ctx* c, int kind, int chunks, int mu, const uint64_t* d_xs, cons
     lasso_leaves_s_kernel<<<dim3(S / 256, C_), 256, 0, s>>>(kind, C_, st_tabs, gt, strees);
     count_launch(c, 2);
   }
-  rc = grand_product_prove(c, mtrees, (size_t)2 * m, T, mu, gp, x_scratch);
-  if (rc) return rc;
-  // x_m = gp->y[0..mu)
-  copy_fr_kernel<<<1, 64, 0, s>>>(gp->y, pts + 2 * (size_t)mu, mu);
-  prof_end(c, ph);
-  ph = prof_begin(c, PH_GKR_S);
-  rc = grand_product_prove(c, strees, (size_t)2 * S, T, SUB_VARS, gp, x_scratch);
-  if (rc) return rc;
-  copy_fr_kernel<<<1, 64, 0, s>>>(gp->y, pt_s, SUB_VARS);
-  count_launch(c, 2);
+  {
+    // product trees (all layers of all trees), then ONE batched GKR over the 4c trees
+    for (int k = mu - 1; k >= 0; --k) {
+      const uint32_t half = 1u << k;
+      int bx = (int)((half + 255) / 256), cap = (4 * NUM_SMS + T - 1) / T;
+      if (bx > cap) bx = cap;
+      tree_up_kernel<<<dim3(bx, T), 256, 0, s>>>(mtrees, (size_t)2 * m, half);
+    }
+    for (int k = SUB_VARS - 1; k >= 0; --k) {
+      const uint32_t half = 1u << k;
+      int bx = (int)((half + 255) / 256), cap = (4 * NUM_SMS + T - 1) / T;
+      if (bx > cap) bx = cap;
+      tree_up_kernel<<<dim3(bx, T), 256, 0, s>>>(strees, (size_t)2 * S, half);
+    }
+    count_launch(c, mu + SUB_VARS);
+    GpTrees trees;
+    trees.T = 2 * T;
+    for (int t = 0; t < T; ++t) {
+      trees.base[t] = mtrees + (size_t)t * 2 * m;
+      trees.height[t] = mu;
+      trees.base[T + t] = strees + (size_t)t * 2 * S;
+      trees.height[T + t] = SUB_VARS;
+    }
+    Fr* point_out[33] = {nullptr};
+    point_out[mu] = pts + 2 * (size_t)mu;  // x_m
+    Fr* xs_tmp = nullptr;
+    if (mu == SUB_VARS) {  // both leaf layers are reached at the same point
+      rc = grand_product_prove(c, trees, gp, x_scratch, point_out);
+      if (rc) return rc;
+      copy_fr_kernel<<<1, 64, 0, s>>>(pts + 2 * (size_t)mu, pt_s, SUB_VARS);
+      count_launch(c);
+    } else {
+      point_out[SUB_VARS] = pt_s;  // x_s
+      rc = grand_product_prove(c, trees, gp, x_scratch, point_out);
+      if (rc) return rc;
+    }
+    (void)xs_tmp;
+  }
   CUDA_TRY(cudaFreeAsync(mtrees, s));
   CUDA_TRY(cudaFreeAsync(strees, s));
 

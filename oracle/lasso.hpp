@@ -93,45 +93,63 @@ inline LassoWitness lasso_witness(const LassoTable& tb, int mu, const uint64_t* 
 }
 
 struct GrandProductOutput {
-  std::vector<Fr> claims;  // per tree: leaf-layer MLE at `point`
-  std::vector<Fr> point;
+  std::vector<Fr> claims;                  // per tree: leaf-layer MLE at points[height of that tree]
+  std::vector<std::vector<Fr>> points;     // points[h] = the point after h layers (h variables)
+  std::vector<Fr> point;                   // == points[max height]
 };
 
-// Batched layered product argument over T trees of 2^h leaves (template: fractional_sum_check.rs).
+// Batched layered product argument over T trees (template: fractional_sum_check.rs). Trees may have
+// DIFFERENT heights h_t = log2(#leaves): all roots sit at layer 0, layer k batches the trees that are
+// still running (h_t > k), in input order, with weights gamma^i over that active list. A tree's claim
+// freezes when its leaf layer is reached; its point is the running point after h_t layers.
 inline GrandProductOutput grand_product_prove(const std::vector<Poly>& leaves, Transcript& tr,
                                               std::vector<Fr>* roots_out) {
   const int T = (int)leaves.size();
-  const int h = log2_exact(leaves[0].size());
-  // layers[k][t]: 2^k nodes; node i = child[i] * child[i + 2^k]
-  std::vector<std::vector<Poly>> layers(h + 1, std::vector<Poly>(T));
-  layers[h] = leaves;
-  for (int k = h - 1; k >= 0; --k)
-    for (int t = 0; t < T; ++t) {
-      const Poly& ch = layers[k + 1][t];
+  std::vector<int> hs(T);
+  int h = 0;
+  for (int t = 0; t < T; ++t) {
+    hs[t] = log2_exact(leaves[t].size());
+    h = hs[t] > h ? hs[t] : h;
+  }
+  // layers[t][k]: 2^k nodes; node i = child[i] * child[i + 2^k]
+  std::vector<std::vector<Poly>> layers(T);
+  for (int t = 0; t < T; ++t) {
+    layers[t].resize(hs[t] + 1);
+    layers[t][hs[t]] = leaves[t];
+    for (int k = hs[t] - 1; k >= 0; --k) {
+      const Poly& ch = layers[t][k + 1];
       const long half = 1L << k;
       Poly up(half);
 #pragma omp parallel for if (half >= 4096)
       for (long i = 0; i < half; ++i) up[i] = ch[i] * ch[i + half];
-      layers[k][t] = up;
+      layers[t][k] = up;
     }
+  }
   std::vector<Fr> claims(T);
-  for (int t = 0; t < T; ++t) claims[t] = layers[0][t][0];
+  for (int t = 0; t < T; ++t) claims[t] = layers[t][0][0];
   tr.write_field_elements(claims.data(), T);
   if (roots_out) *roots_out = claims;
 
+  GrandProductOutput out;
+  out.points.resize(h + 1);
   std::vector<Fr> y;
   for (int k = 0; k < h; ++k) {
     const size_t half = (size_t)1 << k;
-    std::vector<Poly> ls(T), rs(T);
-    for (int t = 0; t < T; ++t) {
-      ls[t].assign(layers[k + 1][t].begin(), layers[k + 1][t].begin() + half);
-      rs[t].assign(layers[k + 1][t].begin() + half, layers[k + 1][t].end());
+    std::vector<int> act;
+    for (int t = 0; t < T; ++t)
+      if (hs[t] > k) act.push_back(t);
+    const int A = (int)act.size();
+    std::vector<Poly> ls(A), rs(A);
+    for (int i = 0; i < A; ++i) {
+      const Poly& ch = layers[act[i]][k + 1];
+      ls[i].assign(ch.begin(), ch.begin() + half);
+      rs[i].assign(ch.begin() + half, ch.end());
     }
     std::vector<Fr> x, evals;
     if (k == 0) {
-      for (int t = 0; t < T; ++t) {
-        evals.push_back(ls[t][0]);
-        evals.push_back(rs[t][0]);
+      for (int i = 0; i < A; ++i) {
+        evals.push_back(ls[i][0]);
+        evals.push_back(rs[i][0]);
       }
     } else {
       Fr gamma = tr.squeeze_challenge();
@@ -139,11 +157,11 @@ inline GrandProductOutput grand_product_prove(const std::vector<Poly>& leaves, T
       vp.has_eq = true;
       vp.y = y;
       Fr pw = Fr::one(), claim = Fr::zero();
-      for (int t = 0; t < T; ++t) {
-        vp.polys.push_back(&ls[t]);
-        vp.polys.push_back(&rs[t]);
-        vp.terms.push_back(Term{pw, {2 * t, 2 * t + 1}});
-        claim = claim + pw * claims[t];
+      for (int i = 0; i < A; ++i) {
+        vp.polys.push_back(&ls[i]);
+        vp.polys.push_back(&rs[i]);
+        vp.terms.push_back(Term{pw, {2 * i, 2 * i + 1}});
+        claim = claim + pw * claims[act[i]];
         pw = pw * gamma;
       }
       SumCheckOutput sc = sumcheck_prove_evals(k, vp, claim, tr);
@@ -152,32 +170,43 @@ inline GrandProductOutput grand_product_prove(const std::vector<Poly>& leaves, T
     }
     tr.write_field_elements(evals.data(), evals.size());
     Fr mu = tr.squeeze_challenge();
-    for (int t = 0; t < T; ++t) claims[t] = evals[2 * t] + mu * (evals[2 * t + 1] - evals[2 * t]);
+    for (int i = 0; i < A; ++i) claims[act[i]] = evals[2 * i] + mu * (evals[2 * i + 1] - evals[2 * i]);
     x.push_back(mu);
     y = x;
+    out.points[k + 1] = y;
   }
-  return GrandProductOutput{claims, y};
+  out.claims = claims;
+  out.point = y;
+  return out;
 }
 
-inline bool grand_product_verify(int T, int h, Transcript& tr, std::vector<Fr>* roots,
+inline bool grand_product_verify(const std::vector<int>& hs, Transcript& tr, std::vector<Fr>* roots,
                                  GrandProductOutput* out) {
+  const int T = (int)hs.size();
+  int h = 0;
+  for (int t = 0; t < T; ++t) h = hs[t] > h ? hs[t] : h;
   std::vector<Fr> claims(T);
   for (int t = 0; t < T; ++t)
     if (!tr.read_field_element(&claims[t])) return false;
   *roots = claims;
+  out->points.assign(h + 1, std::vector<Fr>());
   std::vector<Fr> y;
   for (int k = 0; k < h; ++k) {
-    std::vector<Fr> x, evals(2 * T);
+    std::vector<int> act;
+    for (int t = 0; t < T; ++t)
+      if (hs[t] > k) act.push_back(t);
+    const int A = (int)act.size();
+    std::vector<Fr> x, evals(2 * A);
     if (k == 0) {
       for (auto& e : evals)
         if (!tr.read_field_element(&e)) return false;
-      for (int t = 0; t < T; ++t)
-        if (claims[t] != evals[2 * t] * evals[2 * t + 1]) return false;
+      for (int i = 0; i < A; ++i)
+        if (claims[act[i]] != evals[2 * i] * evals[2 * i + 1]) return false;
     } else {
       Fr gamma = tr.squeeze_challenge();
       Fr pw = Fr::one(), claim = Fr::zero();
-      for (int t = 0; t < T; ++t) {
-        claim = claim + pw * claims[t];
+      for (int i = 0; i < A; ++i) {
+        claim = claim + pw * claims[act[i]];
         pw = pw * gamma;
       }
       Fr fin;
@@ -186,16 +215,17 @@ inline bool grand_product_verify(int T, int h, Transcript& tr, std::vector<Fr>* 
         if (!tr.read_field_element(&e)) return false;
       Fr s = Fr::zero();
       pw = Fr::one();
-      for (int t = 0; t < T; ++t) {
-        s = s + pw * evals[2 * t] * evals[2 * t + 1];
+      for (int i = 0; i < A; ++i) {
+        s = s + pw * evals[2 * i] * evals[2 * i + 1];
         pw = pw * gamma;
       }
       if (fin != s * eq_xy_eval(x, y)) return false;
     }
     Fr mu = tr.squeeze_challenge();
-    for (int t = 0; t < T; ++t) claims[t] = evals[2 * t] + mu * (evals[2 * t + 1] - evals[2 * t]);
+    for (int i = 0; i < A; ++i) claims[act[i]] = evals[2 * i] + mu * (evals[2 * i + 1] - evals[2 * i]);
     x.push_back(mu);
     y = x;
+    out->points[k + 1] = y;
   }
   out->claims = claims;
   out->point = y;
@@ -260,9 +290,14 @@ inline bool lasso_prove(const KzgParams& pp, const LassoTable& tb, int mu, const
       sleaves[2 * t + 1][x] = in + w.final_cts[t][x];
     }
   }
-  // 8. grand products: m-sized (read,write per memory) then S-sized (init,final per memory)
-  GrandProductOutput gm = grand_product_prove(mleaves, tr, nullptr);
-  GrandProductOutput gs = grand_product_prove(sleaves, tr, nullptr);
+  // 8. ONE batched grand product over all 4c trees: [Read_t, Write_t]_t (height mu) then
+  //    [Init_t, Final_t]_t (height 16); x_m / x_s are the running points after mu / 16 layers
+  std::vector<Poly> all_leaves = mleaves;
+  all_leaves.insert(all_leaves.end(), sleaves.begin(), sleaves.end());
+  GrandProductOutput gp = grand_product_prove(all_leaves, tr, nullptr);
+  GrandProductOutput gm, gs;
+  gm.point = gp.points[mu];
+  gs.point = gp.points[SUBTABLE_VARS];
 
   // 9. leaf openings
   std::vector<Fr> ev_dim(c), ev_e(c), ev_ts(c), ev_cts(c);
@@ -316,10 +351,16 @@ inline bool lasso_verify(const KzgParams& vp, const LassoTable& tb, int mu, Tran
 
   Fr gamma = tr.squeeze_challenge(), tau = tr.squeeze_challenge();
   Fr gamma2 = gamma.sqr();
-  std::vector<Fr> mroots, sroots;
-  GrandProductOutput gm, gs;
-  if (!grand_product_verify(2 * c, mu, tr, &mroots, &gm)) return false;
-  if (!grand_product_verify(2 * c, SUBTABLE_VARS, tr, &sroots, &gs)) return false;
+  std::vector<Fr> roots;
+  GrandProductOutput gp, gm, gs;
+  std::vector<int> hs(4 * c, mu);
+  for (int t = 2 * c; t < 4 * c; ++t) hs[t] = SUBTABLE_VARS;
+  if (!grand_product_verify(hs, tr, &roots, &gp)) return false;
+  std::vector<Fr> mroots(roots.begin(), roots.begin() + 2 * c), sroots(roots.begin() + 2 * c, roots.end());
+  gm.point = gp.points[mu];
+  gs.point = gp.points[SUBTABLE_VARS];
+  gm.claims.assign(gp.claims.begin(), gp.claims.begin() + 2 * c);
+  gs.claims.assign(gp.claims.begin() + 2 * c, gp.claims.end());
   // multiset equality  Init * Write == Read * Final  per memory
   for (int t = 0; t < c; ++t)
     if (sroots[2 * t] * mroots[2 * t + 1] != mroots[2 * t] * sroots[2 * t + 1]) return false;
