@@ -91,6 +91,7 @@ void b200_ctx_destroy(b200_ctx* h) {
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   for (auto p : c->srs) cudaFree(p);
+  for (auto p : c->srs_ext) cudaFree(p);
   cudaFree(c->d_tr);
   cudaFree(c->d_proof);
   cudaFree(c->d_bary);

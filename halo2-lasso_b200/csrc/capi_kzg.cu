@@ -23,7 +23,7 @@ int b200_variable_base_msm(b200_ctx* h, const void* host_scalars_fr, const void*
   CUDA_TRY(cudaMallocAsync(&dout, sizeof(G1Aff), s));
   CUDA_TRY(cudaMemcpyAsync(ds, host_scalars_fr, n * sizeof(Fr), cudaMemcpyHostToDevice, s));
   CUDA_TRY(cudaMemcpyAsync(db, host_bases_g1, n * sizeof(G1Aff), cudaMemcpyHostToDevice, s));
-  MsmJob job{ds, db, n, MSM_FR_MONT, 254};
+  MsmJob job{ds, db, n, MSM_FR_MONT, 254, nullptr};
   int rc = msm_batch(c, &job, 1, dout);
   if (rc) return rc;
   CUDA_TRY(cudaMemcpyAsync(host_out_g1, dout, sizeof(G1Aff), cudaMemcpyDeviceToHost, s));
@@ -42,7 +42,7 @@ int b200_kzg_srs_upload(b200_ctx* h, int level, const void* host_g1) {
   CUDA_TRY(cudaMalloc(&d, bytes));
   CUDA_TRY(cudaMemcpy(d, host_g1, bytes, cudaMemcpyHostToDevice));
   c->srs.push_back(d);
-  return B200_OK;
+  return kzg_build_ext(c, level);
 }
 
 int b200_kzg_setup(b200_ctx* h, const void* host_ss_fr, int num_vars) {
@@ -71,7 +71,8 @@ int b200_kzg_batch_commit(b200_ctx* h, const void* const* dev_polys, const int* 
   std::vector<MsmJob> jobs(npolys);
   for (int i = 0; i < npolys; ++i) {
     if (num_vars[i] < 0 || num_vars[i] >= (int)c->srs.size()) return B200_ERR_ARG;  // "Too many variates"
-    jobs[i] = MsmJob{dev_polys[i], c->srs[num_vars[i]], (uint64_t)1 << num_vars[i], MSM_FR_MONT, 254};
+    jobs[i] = MsmJob{dev_polys[i], c->srs[num_vars[i]], (uint64_t)1 << num_vars[i], MSM_FR_MONT, 254,
+                     c->srs_ext[num_vars[i]]};
   }
   G1Aff* dout = nullptr;
   CUDA_TRY(cudaMallocAsync(&dout, npolys * sizeof(G1Aff), c->stream));

@@ -73,6 +73,16 @@ __device__ __forceinline__ void block_reduce_fr(Fr* acc, Fr* smem) {
   __syncthreads();
 }
 
+// warp-only reduction (result valid in lane 0)
+template <int D>
+__device__ __forceinline__ void warp_reduce_fr(Fr* acc) {
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+#pragma unroll
+    for (int x = 0; x < D; ++x) acc[x] = acc[x] + fr_shfl_down(acc[x], off);
+  }
+}
+
 // Returns true in every thread of the LAST CTA of the grid to arrive (all CTAs must call it after
 // publishing their partial results). Resets the counter so the next launch can reuse it.
 __device__ __forceinline__ bool last_cta_ticket(unsigned int* counter) {

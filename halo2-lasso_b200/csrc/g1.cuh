@@ -128,7 +128,9 @@ FF_HD G1Xyzz g1_neg(const G1Xyzz& a) {
 // k * P for a small non-negative k (double-and-add, MSB first)
 FF_HD G1Xyzz g1_mul_small(const G1Xyzz& p, uint32_t k) {
   G1Xyzz acc = g1_identity();
-  for (int i = 31; i >= 0; --i) {
+  int top = 31;
+  while (top >= 0 && !((k >> top) & 1)) --top;  // skip the leading zero bits
+  for (int i = top; i >= 0; --i) {
     acc = g1_dbl(acc);
     if ((k >> i) & 1) acc = g1_add(acc, p);
   }

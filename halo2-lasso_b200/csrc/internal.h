@@ -36,7 +36,13 @@ struct Ctx {
   std::vector<int> prof_tags;            // round index per pair
   // SRS: eqs[k] = 2^k affine points (MultilinearKzgProverParams::eqs, kzg.rs:36-53)
   std::vector<G1Aff*> srs;
+  // precomputed window multiples: srs_ext[k][w * 2^k + i] = 2^(16 w) * srs[k][i], w < EXT_WINDOWS.
+  // With them every window of a full-width scalar lands in ONE shared bucket set, which removes the
+  // per-window reduction and the 254 dependent doublings of the final Horner pass.
+  std::vector<G1Aff*> srs_ext;
 };
+static const int EXT_C = 16;        // window bits of the precomputed tables
+static const int EXT_WINDOWS = 16;  // ceil(255 / 16)
 
 static const int SC_MAX_TERMS = 32;
 static const int SC_MAX_TABLES = 64;
@@ -89,6 +95,7 @@ struct MsmJob {
   uint64_t n;
   int kind;             // MsmScalarKind
   int bits;             // significant bits of the largest scalar (254 for arbitrary Fr)
+  const G1Aff* ext;     // optional precomputed window multiples of `bases` (Ctx::srs_ext layout), or null
 };
 int msm_batch(Ctx* c, const MsmJob* jobs, int J, G1Aff* d_out);
 
@@ -105,6 +112,7 @@ int kzg_commit_batch(Ctx* c, const MsmJob* jobs, int J, bool write_transcript, G
 int kzg_open(Ctx* c, const Fr* d_poly, int n, const Fr* d_point);
 int kzg_batch_open(Ctx* c, const BatchOpenJob& job);
 int kzg_setup(Ctx* c, const Fr* d_ss, int n);
+int kzg_build_ext(Ctx* c, int level);  // fills c->srs_ext[level]
 
 // lasso.cu — Lasso / Surge prover (DESIGN.md §Lasso protocol; oracle/lasso.hpp)
 int lasso_prove(Ctx* c, int kind, int chunks, int mu, const uint64_t* d_xs, const uint64_t* d_ys);

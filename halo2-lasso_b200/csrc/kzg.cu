@@ -30,7 +30,7 @@ int kzg_open(Ctx* c, const Fr* d_poly, int n, const Fr* d_point) {
     const size_t half = (size_t)1 << nv;
     int rc = quotient_step(c, rem, half, d_point + nv, q + half);
     if (rc) return rc;
-    jobs[nv] = MsmJob{q + half, c->srs[nv], half, MSM_FR_MONT, 254};
+    jobs[nv] = MsmJob{q + half, c->srs[nv], half, MSM_FR_MONT, 254, c->srs_ext[nv]};
   }
   int rc = kzg_commit_batch(c, jobs, n, true, comms);
   if (rc) return rc;
@@ -188,6 +188,60 @@ __global__ void __launch_bounds__(128) srs_fixed_base_kernel(const Fr* __restric
     fe_st(&out[i].y, a.y);
   }
 }
+// ext[w*n + i] = 2^(16 w) * base[i]: 16 doublings per window, then ONE shared inversion per base point
+// (Montgomery's trick over its 15 multiples).
+__global__ void __launch_bounds__(128) srs_ext_kernel(const G1Aff* __restrict__ base, size_t n, G1Aff* __restrict__ ext) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    G1Aff p;
+    p.x = fe_ldg(&base[i].x);
+    p.y = fe_ldg(&base[i].y);
+    fe_st(&ext[i].x, p.x);
+    fe_st(&ext[i].y, p.y);
+    if (g1_aff_is_identity(p)) {
+      for (int w = 1; w < EXT_WINDOWS; ++w) {
+        fe_st(&ext[(size_t)w * n + i].x, p.x);
+        fe_st(&ext[(size_t)w * n + i].y, p.y);
+      }
+      continue;
+    }
+    G1Xyzz pts[EXT_WINDOWS - 1];
+    Fq pre[EXT_WINDOWS - 1];  // prefix products of d_w = zz_w * zzz_w
+    G1Xyzz acc = g1_from_affine(p);
+    Fq run = fe_one<FqP>();
+    for (int w = 0; w < EXT_WINDOWS - 1; ++w) {
+      for (int k = 0; k < EXT_C; ++k) acc = g1_dbl(acc);
+      pts[w] = acc;
+      pre[w] = run;
+      run = run * (acc.zz * acc.zzz);
+    }
+    Fq inv = fe_inv<FqP>(run);  // 1 / Π d_w   (points of prime order never double to the identity)
+    for (int w = EXT_WINDOWS - 2; w >= 0; --w) {
+      const Fq d = pts[w].zz * pts[w].zzz;
+      const Fq dinv = inv * pre[w];  // 1 / d_w
+      inv = inv * d;
+      fe_st(&ext[(size_t)(w + 1) * n + i].x, pts[w].x * (dinv * pts[w].zzz));
+      fe_st(&ext[(size_t)(w + 1) * n + i].y, pts[w].y * (dinv * pts[w].zz));
+    }
+  }
+}
+
+int kzg_build_ext(Ctx* c, int level) {
+  if (level < 0 || level >= (int)c->srs.size()) return B200_ERR_ARG;
+  if ((int)c->srs_ext.size() <= level) c->srs_ext.resize(level + 1, nullptr);
+  if (c->srs_ext[level]) return B200_OK;
+  const size_t n = (size_t)1 << level;
+  G1Aff* ext = nullptr;
+  CUDA_TRY(cudaMalloc(&ext, (size_t)EXT_WINDOWS * n * sizeof(G1Aff)));
+  int blocks = (int)((n + 127) / 128);
+  if (blocks > NUM_SMS * 16) blocks = NUM_SMS * 16;
+  srs_ext_kernel<<<blocks, 128, 0, c->stream>>>(c->srs[level], n, ext);
+  count_launch(c);
+  CUDA_TRY(cudaGetLastError());
+  c->srs_ext[level] = ext;
+  return B200_OK;
+}
+
 __global__ void fill_one_fr_kernel(Fr* out) {
   if (threadIdx.x == 0 && blockIdx.x == 0) fe_st(out, fe_one<FrP>());
 }
@@ -219,6 +273,8 @@ int kzg_setup(Ctx* c, const Fr* d_ss, int n) {
     srs_fixed_base_kernel<<<blocks, 128, 0, s>>>(eq, N, table, lvl);
     count_launch(c, 2);
     c->srs.push_back(lvl);
+    int rc = kzg_build_ext(c, k);
+    if (rc) return rc;
   }
   CUDA_TRY(cudaFreeAsync(bases, s));
   CUDA_TRY(cudaFreeAsync(table, s));

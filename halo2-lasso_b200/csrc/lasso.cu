@@ -96,19 +96,30 @@ __global__ void __launch_bounds__(32) lasso_rank_kernel(uint32_t m, uint32_t chu
   __syncwarp();
   const size_t off = (size_t)t * m + (size_t)ch * chunk_len;
   const uint32_t* b = base + ((size_t)t * nch + ch) * SUB_SIZE;
-  for (uint32_t i0 = 0; i0 < chunk_len; i0 += 32) {
-    const uint32_t i = i0 + lane;
-    const bool valid = i < chunk_len;
-    const uint32_t addr = valid ? dims[off + i] : (0x80000000u | lane);  // invalid lanes never match
-    const uint32_t mask = __match_any_sync(0xffffffffu, addr);
-    const uint32_t before = __popc(mask & ((1u << lane) - 1));
-    if (valid) {
-      const uint32_t seen = local[addr];
-      read_ts[off + i] = b[addr] + seen + before;
-      __syncwarp(mask);
-      if (before == 0) local[addr] = (uint16_t)(seen + __popc(mask));
+  constexpr int U = 8;  // steps whose address + base loads are issued together (hides the global latency)
+  for (uint32_t i0 = 0; i0 < chunk_len; i0 += 32 * U) {
+    uint32_t addr[U], bs[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const uint32_t i = i0 + u * 32 + lane;
+      addr[u] = i < chunk_len ? dims[off + i] : (0x80000000u | lane);  // invalid lanes never match
     }
-    __syncwarp();
+#pragma unroll
+    for (int u = 0; u < U; ++u) bs[u] = addr[u] < SUB_SIZE ? b[addr[u]] : 0;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const bool valid = addr[u] < SUB_SIZE;
+      const uint32_t mask = __match_any_sync(0xffffffffu, addr[u]);
+      const uint32_t before = __popc(mask & ((1u << lane) - 1));
+      uint32_t seen = 0;
+      if (valid) seen = local[addr[u]];
+      __syncwarp();
+      if (valid) {
+        read_ts[off + i0 + u * 32 + lane] = bs[u] + seen + before;
+        if (before == 0) local[addr[u]] = (uint16_t)(seen + __popc(mask));
+      }
+      __syncwarp();
+    }
   }
 }
 
@@ -177,15 +188,13 @@ struct GpTrees {
 // write the roots, which are the first claims
 __global__ void gp_roots_kernel(Transcript* tr, GpTrees trees, GpState* st) {
   __shared__ Transcript sh_tr;
-  if (threadIdx.x == 0) sh_tr = *tr;
-  __syncwarp();
+  trw_copy(&sh_tr, tr);
   for (int t = 0; t < trees.T; ++t) {
     const Fr root = fe_ld(trees.base[t] + 1);
     if (threadIdx.x == 0) fe_st(&st->claims[t], root);
     trw_write_fe(&sh_tr, root);
   }
-  __syncwarp();
-  if (threadIdx.x == 0) *tr = sh_tr;
+  trw_copy(tr, &sh_tr);
 }
 
 // Layer k, before the sum-check. k == 0: the two children are the evaluations. k > 0: squeeze gamma,
@@ -202,8 +211,7 @@ __global__ void gp_before_kernel(Transcript* tr, GpTrees trees, int k, GpState* 
     }
     return;
   }
-  if (lane == 0) sh_tr = *tr;
-  __syncwarp();
+  trw_copy(&sh_tr, tr);
   const Fr gamma = trw_squeeze(&sh_tr);
   Fr pw = fe_one<FrP>(), claim = fe_zero<FrP>();
   int slot = 0;
@@ -214,17 +222,14 @@ __global__ void gp_before_kernel(Transcript* tr, GpTrees trees, int k, GpState* 
     pw = fr_mul_ni(pw, gamma);
     ++slot;
   }
-  if (lane == 0) {
-    fe_st(&st->claim, claim);
-    *tr = sh_tr;
-  }
+  trw_copy(tr, &sh_tr);
+  if (lane == 0) fe_st(&st->claim, claim);
 }
 // after the sum-check: write the 2A evaluations, squeeze mu, fold the active claims, y = x || mu
 __global__ void gp_after_kernel(Transcript* tr, GpTrees trees, int k, const Fr* x /* k challenges */, GpState* st) {
   __shared__ Transcript sh_tr;
   const int lane = threadIdx.x;
-  if (lane == 0) sh_tr = *tr;
-  __syncwarp();
+  trw_copy(&sh_tr, tr);
   int A = 0;
   for (int t = 0; t < trees.T; ++t) A += trees.height[t] > k;
   // canonical forms of up to 32 evaluations per pass in parallel lanes
@@ -245,10 +250,8 @@ __global__ void gp_after_kernel(Transcript* tr, GpTrees trees, int k, const Fr* 
     ++slot;
   }
   for (int i = lane; i < k; i += 32) fe_st(&st->y[i], fe_ld(x + i));
-  if (lane == 0) {
-    fe_st(&st->y[k], mu);
-    *tr = sh_tr;
-  }
+  trw_copy(tr, &sh_tr);
+  if (lane == 0) fe_st(&st->y[k], mu);
 }
 
 __global__ void copy_fr_kernel(const Fr* src, Fr* dst, int n) {
@@ -395,11 +398,11 @@ int lasso_prove(Ctx* c, int kind, int chunks, int mu, const uint64_t* d_xs, cons
     MsmJob jobs[1 + 4 * 8];
     int J = 0;
     const int e_bits = kind == 0 ? 16 : 8;
-    jobs[J++] = MsmJob{a_u64, c->srs[mu], m, MSM_U64, e_bits * C_};
-    for (int t = 0; t < C_; ++t) jobs[J++] = MsmJob{dims + (size_t)t * m, c->srs[mu], m, MSM_U32, 16};
-    for (int t = 0; t < C_; ++t) jobs[J++] = MsmJob{es + (size_t)t * m, c->srs[mu], m, MSM_U32, e_bits};
-    for (int t = 0; t < C_; ++t) jobs[J++] = MsmJob{ts + (size_t)t * m, c->srs[mu], m, MSM_U32, mu + 1};
-    for (int t = 0; t < C_; ++t) jobs[J++] = MsmJob{cts + (size_t)t * S, c->srs[SUB_VARS], S, MSM_U32, mu + 1};
+    jobs[J++] = MsmJob{a_u64, c->srs[mu], m, MSM_U64, e_bits * C_, c->srs_ext[mu]};
+    for (int t = 0; t < C_; ++t) jobs[J++] = MsmJob{dims + (size_t)t * m, c->srs[mu], m, MSM_U32, 16, nullptr};
+    for (int t = 0; t < C_; ++t) jobs[J++] = MsmJob{es + (size_t)t * m, c->srs[mu], m, MSM_U32, e_bits, nullptr};
+    for (int t = 0; t < C_; ++t) jobs[J++] = MsmJob{ts + (size_t)t * m, c->srs[mu], m, MSM_U32, mu + 1, nullptr};
+    for (int t = 0; t < C_; ++t) jobs[J++] = MsmJob{cts + (size_t)t * S, c->srs[SUB_VARS], S, MSM_U32, mu + 1, nullptr};
     G1Aff* comms;
     CUDA_TRY(cudaMallocAsync(&comms, J * sizeof(G1Aff), s));
     rc = kzg_commit_batch(c, jobs, J, true, comms);

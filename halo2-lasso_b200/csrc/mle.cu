@@ -245,8 +245,7 @@ int eq_xy_eval_dev(Ctx* c, const Fr* d_x, const Fr* d_y, int n, Fr* d_out) {
 
 __global__ void transcript_kernel(Transcript* tr, int op, const Fr* in, Fr* out, int n) {
   __shared__ Transcript sh_tr;  // one warp, warp-cooperative Keccak
-  if (threadIdx.x == 0) sh_tr = *tr;
-  __syncwarp();
+  trw_copy(&sh_tr, tr);
   for (int i = 0; i < n; ++i) {
     if (op == TR_COMMON) trw_common_fe(&sh_tr, fe_ld(in + i));
     else if (op == TR_WRITE) trw_write_fe(&sh_tr, fe_ld(in + i));
@@ -255,8 +254,7 @@ __global__ void transcript_kernel(Transcript* tr, int op, const Fr* in, Fr* out,
       if (threadIdx.x == 0) fe_st(out + i, ch);
     }
   }
-  __syncwarp();
-  if (threadIdx.x == 0) *tr = sh_tr;
+  trw_copy(tr, &sh_tr);
 }
 int transcript_op(Ctx* c, int op, const Fr* d_in, Fr* d_out, int n) {
   if (n <= 0) return B200_OK;
@@ -268,14 +266,12 @@ int transcript_op(Ctx* c, int op, const Fr* d_in, Fr* d_out, int n) {
 
 __global__ void transcript_points_kernel(Transcript* tr, const G1Aff* pts, int n) {
   __shared__ Transcript sh_tr;
-  if (threadIdx.x == 0) sh_tr = *tr;
-  __syncwarp();
+  trw_copy(&sh_tr, tr);
   for (int i = 0; i < n; ++i) {
     const Fq x = fe_ld(&pts[i].x), y = fe_ld(&pts[i].y);
     trw_write_commitment(&sh_tr, x, y);
   }
-  __syncwarp();
-  if (threadIdx.x == 0) *tr = sh_tr;
+  trw_copy(tr, &sh_tr);
 }
 int transcript_write_points(Ctx* c, const G1Aff* d_pts, int n) {
   if (n <= 0) return B200_OK;

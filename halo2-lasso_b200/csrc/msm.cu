@@ -22,7 +22,7 @@ namespace b200 {
 
 static const int TASK_LEN = 64;
 static const int SEQ_TASKS = 8;     // buckets with more task partials than this go to the warp kernel
-static const int GROUP = 16;        // buckets per thread in the window reduction
+static const int GROUP = 32;        // buckets per thread in the window reduction
 static const int MSM_MAX_JOBS = 64;
 static const int MSM_MAX_WINDOWS = 128;
 
@@ -33,6 +33,8 @@ struct MsmJobDev {
   int kind;           // MsmScalarKind
   int c, W;           // window bits, number of windows
   uint32_t B;         // buckets per window = 2^(c-1)
+  int precomp;        // 1: bases = precomputed window multiples, all windows share one bucket set
+  int Wred;           // windows that need a bucket reduction (1 when precomp, else W)
   uint32_t bucket_base;
   uint64_t pair_base;
   uint32_t group_base;  // first reduction group of this job
@@ -111,7 +113,7 @@ __global__ void __launch_bounds__(256) msm_digits_kernel(MsmPlanDev plan, uint32
       uint32_t code = 0xffffffffu;
       if (d != 0) {
         const uint32_t mag = d < 0 ? (uint32_t)(-d) : (uint32_t)d;
-        const uint32_t gb = jb.bucket_base + (uint32_t)w * jb.B + (mag - 1);
+        const uint32_t gb = jb.bucket_base + (jb.precomp ? 0u : (uint32_t)w * jb.B) + (mag - 1);
         const uint32_t rank = atomicAdd(&cnt[gb], 1u);
         // 2 words per pair: bucket, rank|sign
         ranks[2 * (jb.pair_base + (uint64_t)w * jb.n + i)] = gb;
@@ -127,7 +129,8 @@ __global__ void __launch_bounds__(256) msm_digits_kernel(MsmPlanDev plan, uint32
       const uint32_t gb = ranks[p];
       if (gb == 0xffffffffu) continue;
       const uint32_t code = ranks[p + 1];
-      sorted[boff[gb] + (code & 0x7fffffffu)] = i | (code & 0x80000000u);
+      // with precomputed tables the point of window w is entry i + w*n of the extended table
+      sorted[boff[gb] + (code & 0x7fffffffu)] = (jb.precomp ? i + (uint32_t)w * jb.n : i) | (code & 0x80000000u);
     }
   }
 }
@@ -308,21 +311,27 @@ __device__ __forceinline__ G1Xyzz warp_sum_xyzz(G1Xyzz acc) {
   return acc;  // valid in lane 0
 }
 
+// one CTA per heavy bucket: threads stride over the task partials, then warp + shared-memory reduction
 __global__ void __launch_bounds__(128) msm_heavy_kernel(const uint32_t* __restrict__ toff,
                                                         const G1Xyzz* __restrict__ partial,
                                                         G1Xyzz* __restrict__ bucket_sum,
                                                         const uint32_t* __restrict__ heavy,
                                                         const uint32_t* __restrict__ heavy_count) {
+  __shared__ G1Xyzz sh[4];
   const uint32_t nheavy = *heavy_count;
-  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
-  for (uint32_t h = warp; h < nheavy; h += nwarps) {
+  for (uint32_t h = blockIdx.x; h < nheavy; h += gridDim.x) {
     const uint32_t gb = heavy[h];
     const uint32_t t0 = toff[gb], nt = toff[gb + 1] - t0;
     G1Xyzz acc = g1_identity();
-    for (uint32_t k = lane; k < nt; k += 32) acc = g1_add(acc, ld_xyzz(partial + t0 + k));
+    for (uint32_t k = threadIdx.x; k < nt; k += blockDim.x) acc = g1_add(acc, ld_xyzz(partial + t0 + k));
     acc = warp_sum_xyzz(acc);
-    if (lane == 0) st_xyzz(bucket_sum + gb, acc);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      for (int k = 1; k < 4; ++k) acc = g1_add(acc, sh[k]);
+      st_xyzz(bucket_sum + gb, acc);
+    }
+    __syncthreads();
   }
 }
 
@@ -380,7 +389,7 @@ __global__ void msm_finish_kernel(MsmPlanDev plan, const G1Xyzz* __restrict__ wi
   if (j >= plan.J) return;
   const MsmJobDev& jb = plan.job[j];
   G1Xyzz acc = g1_identity();
-  for (int w = jb.W - 1; w >= 0; --w) {
+  for (int w = jb.Wred - 1; w >= 0; --w) {
     for (int k = 0; k < jb.c; ++k) acc = g1_dbl(acc);
     acc = g1_add(acc, ld_xyzz(window_sum + jb.win_base + w));
   }
@@ -410,23 +419,33 @@ int msm_batch(Ctx* c, const MsmJob* jobs, int J, G1Aff* d_out) {
     jb.bases = in.bases;
     jb.n = (uint32_t)in.n;
     jb.kind = in.kind;
-    int cmax = ilog2_floor(in.n) - 3;
-    if (cmax < 3) cmax = 3;
-    if (cmax > 17) cmax = 17;
     const int need = in.bits + 1;  // signed digits may carry one bit past the top
-    jb.W = (need + cmax - 1) / cmax;
-    jb.c = (need + jb.W - 1) / jb.W;
-    if (jb.c < 2) jb.c = 2;
+    jb.precomp = (in.ext != nullptr && in.bits > 2 * EXT_C + 2) ? 1 : 0;
+    if (jb.precomp) {
+      jb.bases = in.ext;
+      jb.c = EXT_C;
+      jb.W = (need + EXT_C - 1) / EXT_C;
+      if (jb.W > EXT_WINDOWS) return B200_ERR_ARG;
+      jb.Wred = 1;
+    } else {
+      int cmax = ilog2_floor(in.n) - 3;
+      if (cmax < 3) cmax = 3;
+      if (cmax > 17) cmax = 17;
+      jb.W = (need + cmax - 1) / cmax;
+      jb.c = (need + jb.W - 1) / jb.W;
+      if (jb.c < 2) jb.c = 2;
+      jb.Wred = jb.W;
+    }
     if (jb.W > MSM_MAX_WINDOWS) return B200_ERR_ARG;
     jb.B = 1u << (jb.c - 1);
     jb.bucket_base = nbuckets;
     jb.pair_base = pairs;
     jb.group_base = ngroups;
     jb.win_base = nwin;
-    nbuckets += jb.B * jb.W;
+    nbuckets += jb.B * jb.Wred;
     pairs += (uint64_t)jb.n * jb.W;
-    ngroups += ((jb.B + GROUP - 1) / GROUP) * jb.W;
-    nwin += jb.W;
+    ngroups += ((jb.B + GROUP - 1) / GROUP) * jb.Wred;
+    nwin += jb.Wred;
     if (jb.n > max_n) max_n = jb.n;
   }
   if (pairs >= (1ull << 31)) return B200_ERR_ARG;

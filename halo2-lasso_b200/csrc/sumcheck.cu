@@ -104,16 +104,24 @@ __global__ void __launch_bounds__(SC_THREADS) sc_eval_round_kernel(ScEvalArgs a)
   const uint32_t nparts = gridDim.x * gridDim.y;
 #pragma unroll
   for (int x = 0; x < D; ++x) acc[x] = fe_zero<FrP>();
-  for (uint32_t i = threadIdx.x; i < nparts; i += blockDim.x) {
+  if (nparts <= 32) {  // small rounds: one warp sums the partials, no block-wide barrier
+    if (threadIdx.x >= 32) return;
+    if (threadIdx.x < nparts) {
 #pragma unroll
-    for (int x = 0; x < D; ++x) acc[x] = acc[x] + fr_ld_cg(a.partial + (size_t)i * D + x);
+      for (int x = 0; x < D; ++x) acc[x] = fr_ld_cg(a.partial + (size_t)threadIdx.x * D + x);
+    }
+    warp_reduce_fr<D>(acc);
+  } else {
+    for (uint32_t i = threadIdx.x; i < nparts; i += blockDim.x) {
+#pragma unroll
+      for (int x = 0; x < D; ++x) acc[x] = acc[x] + fr_ld_cg(a.partial + (size_t)i * D + x);
+    }
+    block_reduce_fr<D>(acc, smem);
   }
-  block_reduce_fr<D>(acc, smem);
   if (threadIdx.x < 32) {  // warp 0, warp-uniform control flow; lane i owns p(i)
     const int lane = threadIdx.x;
     __shared__ Transcript sh_tr;
-    if (lane == 0) sh_tr = *a.tr;
-    __syncwarp();
+    trw_copy(&sh_tr, a.tr);
     const Fr p1 = fr_bcast(acc[0], 0);
     Fr mine = fe_zero<FrP>();
 #pragma unroll
@@ -143,8 +151,8 @@ __global__ void __launch_bounds__(SC_THREADS) sc_eval_round_kernel(ScEvalArgs a)
       for (int i = 0; i < 8; ++i) o.v[i] = __shfl_xor_sync(0xffffffffu, term.v[i], off);
       term = term + o;
     }
+    trw_copy(a.tr, &sh_tr);
     if (lane == 0) {
-      *a.tr = sh_tr;
       fe_st(a.challenges_out + a.round, ch);
       fe_st(&a.st->r, ch);
       fe_st(&a.st->claim, term);
@@ -289,16 +297,24 @@ __global__ void __launch_bounds__(SC_THREADS) sc_coeff_round_kernel(ScCoeffArgs 
   const uint32_t nparts = gridDim.x * gridDim.y;
   acc[0] = fe_zero<FrP>();
   acc[1] = fe_zero<FrP>();
-  for (uint32_t i = threadIdx.x; i < nparts; i += blockDim.x) {
-    acc[0] = acc[0] + fr_ld_cg(a.partial + (size_t)i * 2);
-    acc[1] = acc[1] + fr_ld_cg(a.partial + (size_t)i * 2 + 1);
+  if (nparts <= 32) {
+    if (threadIdx.x >= 32) return;
+    if (threadIdx.x < nparts) {
+      acc[0] = fr_ld_cg(a.partial + (size_t)threadIdx.x * 2);
+      acc[1] = fr_ld_cg(a.partial + (size_t)threadIdx.x * 2 + 1);
+    }
+    warp_reduce_fr<2>(acc);
+  } else {
+    for (uint32_t i = threadIdx.x; i < nparts; i += blockDim.x) {
+      acc[0] = acc[0] + fr_ld_cg(a.partial + (size_t)i * 2);
+      acc[1] = acc[1] + fr_ld_cg(a.partial + (size_t)i * 2 + 1);
+    }
+    block_reduce_fr<2>(acc, smem);
   }
-  block_reduce_fr<2>(acc, smem);
   if (threadIdx.x < 32) {
     const int lane = threadIdx.x;
     __shared__ Transcript sh_tr;
-    if (lane == 0) sh_tr = *a.tr;
-    __syncwarp();
+    trw_copy(&sh_tr, a.tr);
     const Fr claim = fe_ld(&a.st->claim);
     const Fr c0 = fr_bcast(acc[0], 0), c2 = fr_bcast(acc[1], 0);
     const Fr c1 = claim - (c0 + c0 + c2);  // coeff.rs:147
@@ -306,8 +322,8 @@ __global__ void __launch_bounds__(SC_THREADS) sc_coeff_round_kernel(ScCoeffArgs 
     for (int x = 0; x < 3; ++x) trw_write_canon_from_lane(&sh_tr, canon, x, true);
     const Fr ch = trw_squeeze(&sh_tr);
     const Fr next = fr_mul_ni(fr_mul_ni(c2, ch) + c1, ch) + c0;  // horner (coeff.rs:36-38)
+    trw_copy(a.tr, &sh_tr);
     if (lane == 0) {
-      *a.tr = sh_tr;
       fe_st(a.challenges_out + a.round, ch);
       fe_st(&a.st->r, ch);
       fe_st(&a.st->claim, next);

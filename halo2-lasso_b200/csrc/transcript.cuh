@@ -263,18 +263,39 @@ __device__ __forceinline__ Fr trw_squeeze(Transcript* t) {
   for (int i = 0; i < 8; ++i) r2.v[i] = FrP::r2(i);
   return fr_mul_ni(r2, h);  // (hash mod r) in Montgomery form; the raw 256-bit operand is the scanned one
 }
+// big-endian proof bytes of one element, written as 8 byte-swapped words by 8 lanes
+__device__ __forceinline__ void trw_stream_be(Transcript* t, const uint32_t* canon);
 // absorb (and stream) the element whose CANONICAL limbs lane `src` holds: lets the caller convert
 // several elements to canonical form in parallel lanes
 __device__ __forceinline__ void trw_write_canon_from_lane(Transcript* t, const Fr& canon_mine, int src, bool stream) {
   const Fr c = fr_bcast(canon_mine, src);
   trw_absorb_words(t, c.v, 8);
-  if (stream) {
-    if ((threadIdx.x & 31) == 0) tr_stream_be(t, c.v);
-    __syncwarp();
-  }
+  if (stream) trw_stream_be(t, c.v);
+}
+// cooperative copy of the transcript struct between global and shared memory (56 words)
+__device__ __forceinline__ void trw_copy(Transcript* dst, const Transcript* src) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t* s32 = reinterpret_cast<const uint32_t*>(src);
+  uint32_t* d32 = reinterpret_cast<uint32_t*>(dst);
+  constexpr int W = (int)(sizeof(Transcript) / 4);
+  for (int i = lane; i < W; i += 32) d32[i] = s32[i];
+  __syncwarp();
 }
 __device__ __forceinline__ void trw_stream_be(Transcript* t, const uint32_t* canon) {
-  if ((threadIdx.x & 31) == 0) tr_stream_be(t, canon);
+  const int lane = threadIdx.x & 31;
+  const uint32_t len = t->proof_len;
+  if (len + 32 > t->proof_cap) {
+    if (lane == 0) t->error |= 1;
+    __syncwarp();
+    return;
+  }
+  uint32_t w = 0;
+#pragma unroll
+  for (int k = 0; k < 8; ++k)
+    if (7 - k == lane) w = canon[k];
+  if (lane < 8) reinterpret_cast<uint32_t*>(t->proof + len)[lane] = __byte_perm(w, 0, 0x0123);
+  __syncwarp();
+  if (lane == 0) t->proof_len = len + 32;
   __syncwarp();
 }
 __device__ __forceinline__ void trw_common_fe(Transcript* t, const Fr& fe) {
