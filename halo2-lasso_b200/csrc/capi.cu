@@ -1,6 +1,7 @@
 // extern "C" boundary (include/b200_lasso.h): context, device polynomials, transcript, MLE and
 // sum-check entry points. Host buffers are staged with stream-ordered copies; the only host syncs
 // are the ones that return results to the caller.
+#include <stdlib.h>
 #include <string.h>
 
 #include <vector>
@@ -62,6 +63,11 @@ int b200_ctx_create(int device, b200_ctx** out) {
   c->device = device;
   c->launches = 0;
   c->profile = false;
+  c->dbg_clocks = nullptr;
+  if (getenv("B200_DEBUG_CLOCKS")) {
+    CUDA_TRY(cudaMalloc(&c->dbg_clocks, 32 * 16 * sizeof(long long)));
+    CUDA_TRY(cudaMemset(c->dbg_clocks, 0, 32 * 16 * sizeof(long long)));
+  }
   CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   // keep freed blocks cached in the stream-ordered pool: proofs reuse the same sizes over and over
   cudaMemPool_t pool;
@@ -114,6 +120,13 @@ uint64_t b200_launch_count(b200_ctx* h, int reset) {
 
 void* b200_stream(b200_ctx* h) { return (void*)h->c.stream; }
 
+int b200_debug_clocks(b200_ctx* h, long long* out) {
+  Ctx* c = &h->c;
+  if (!c->dbg_clocks) return B200_ERR_ARG;
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  CUDA_TRY(cudaMemcpy(out, c->dbg_clocks, 32 * 16 * sizeof(long long), cudaMemcpyDeviceToHost));
+  return B200_OK;
+}
 int b200_profile_enable(b200_ctx* h, int on) {
   Ctx* c = &h->c;
   for (auto e : c->prof_events) cudaEventDestroy(e);

@@ -32,6 +32,7 @@ struct Ctx {
   uint64_t launches;   // kernels launched since the last reset (bench "gpu_launches")
   // optional per-launch CUDA-event timing of the sum-check round kernels (bench roofline leg)
   bool profile;
+  long long* dbg_clocks;  // device, 32 rounds x 16 stamps (null unless B200_DEBUG_CLOCKS is set)
   std::vector<cudaEvent_t> prof_events;  // pairs (start, stop)
   std::vector<int> prof_tags;            // round index per pair
   // SRS: eqs[k] = 2^k affine points (MultilinearKzgProverParams::eqs, kzg.rs:36-53)

@@ -254,6 +254,12 @@ __global__ void gp_after_kernel(Transcript* tr, GpTrees trees, int k, const Fr* 
   if (lane == 0) fe_st(&st->y[k], mu);
 }
 
+__global__ void gather_points_kernel(const G1Aff* src, const int* idx, int n, G1Aff* dst) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  fe_st(&dst[i].x, fe_ld(&src[idx[i]].x));
+  fe_st(&dst[i].y, fe_ld(&src[idx[i]].y));
+}
 __global__ void copy_fr_kernel(const Fr* src, Fr* dst, int n) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) fe_st(dst + i, fe_ld(src + i));
@@ -400,13 +406,34 @@ int lasso_prove(Ctx* c, int kind, int chunks, int mu, const uint64_t* d_xs, cons
     const int e_bits = kind == 0 ? 16 : 8;
     jobs[J++] = MsmJob{a_u64, c->srs[mu], m, MSM_U64, e_bits * C_, c->srs_ext[mu]};
     for (int t = 0; t < C_; ++t) jobs[J++] = MsmJob{dims + (size_t)t * m, c->srs[mu], m, MSM_U32, 16, nullptr};
-    for (int t = 0; t < C_; ++t) jobs[J++] = MsmJob{es + (size_t)t * m, c->srs[mu], m, MSM_U32, e_bits, nullptr};
+    // identity subtable (range): E_t == dim_t as polynomials, so their commitments are the same point —
+    // the MSM is run once and the point is written twice
+    const bool e_is_dim = kind == 0;
+    if (!e_is_dim)
+      for (int t = 0; t < C_; ++t) jobs[J++] = MsmJob{es + (size_t)t * m, c->srs[mu], m, MSM_U32, e_bits, nullptr};
     for (int t = 0; t < C_; ++t) jobs[J++] = MsmJob{ts + (size_t)t * m, c->srs[mu], m, MSM_U32, mu + 1, nullptr};
     for (int t = 0; t < C_; ++t) jobs[J++] = MsmJob{cts + (size_t)t * S, c->srs[SUB_VARS], S, MSM_U32, mu + 1, nullptr};
-    G1Aff* comms;
+    G1Aff *comms, *all;
+    const int NC = 1 + 4 * C_;
     CUDA_TRY(cudaMallocAsync(&comms, J * sizeof(G1Aff), s));
-    rc = kzg_commit_batch(c, jobs, J, true, comms);
+    CUDA_TRY(cudaMallocAsync(&all, NC * sizeof(G1Aff), s));
+    rc = msm_batch(c, jobs, J, comms);
     if (rc) return rc;
+    // transcript order: a | dim[c] | E[c] | read_ts[c] | final_cts[c]
+    int h_src[1 + 4 * 8];
+    for (int i = 0; i < NC; ++i) {
+      if (!e_is_dim) h_src[i] = i;
+      else h_src[i] = i < 1 + C_ ? i : (i < 1 + 2 * C_ ? i - C_ : i - C_);
+    }
+    int* d_src;
+    CUDA_TRY(cudaMallocAsync(&d_src, NC * sizeof(int), s));
+    CUDA_TRY(cudaMemcpyAsync(d_src, h_src, NC * sizeof(int), cudaMemcpyHostToDevice, s));
+    gather_points_kernel<<<1, 64, 0, s>>>(comms, d_src, NC, all);
+    count_launch(c);
+    rc = transcript_write_points(c, all, NC);
+    if (rc) return rc;
+    CUDA_TRY(cudaFreeAsync(d_src, s));
+    CUDA_TRY(cudaFreeAsync(all, s));
     CUDA_TRY(cudaFreeAsync(comms, s));
   }
 

@@ -26,7 +26,12 @@ struct ScEvalArgs {
   Fr* challenges_out;
   uint32_t pairs;
   int round;
+  long long* dbg;  // optional clock64() trace of the last CTA (debug builds of the bench only)
 };
+#define DBG_CLK(i)                                                     \
+  do {                                                                 \
+    if (a.dbg && threadIdx.x == 0) a.dbg[a.round * 16 + (i)] = clock64(); \
+  } while (0)
 
 // Load the pair (u0, u1) = (t[2b], t[2b+1]) of the CURRENT round. With BIND the table still has the
 // previous round's size: bind 4 consecutive elements with r first and store the bound pair.
@@ -59,6 +64,8 @@ __global__ void __launch_bounds__(SC_THREADS) sc_eval_round_kernel(ScEvalArgs a)
   for (int x = 0; x < D; ++x) acc[x] = fe_zero<FrP>();
   Fr r = fe_zero<FrP>();
   if (BIND) r = fe_ld(&a.st->r);
+  const bool dbg_cta = a.dbg && gridDim.x * gridDim.y == 1;
+  if (dbg_cta) DBG_CLK(0);
 
   const Fr* __restrict__ in0 = a.in[t * NP];
   Fr* __restrict__ out0 = a.out[t * NP];
@@ -86,7 +93,9 @@ __global__ void __launch_bounds__(SC_THREADS) sc_eval_round_kernel(ScEvalArgs a)
       }
     }
   }
+  if (dbg_cta) DBG_CLK(1);
   block_reduce_fr<D>(acc, smem);
+  if (dbg_cta) DBG_CLK(2);
   if (threadIdx.x < 32) {  // lane x scales and stores partial x (one multiplication deep, not D)
     const int lane = threadIdx.x;
     Fr v = fe_zero<FrP>();
@@ -98,7 +107,9 @@ __global__ void __launch_bounds__(SC_THREADS) sc_eval_round_kernel(ScEvalArgs a)
     v = fr_mul_ni(v, fe_ld(a.weights + t));
     if (lane < D) fe_st(a.partial + ((size_t)t * gridDim.x + blockIdx.x) * D + lane, v);
   }
+  if (dbg_cta) DBG_CLK(3);
   if (!last_cta_ticket(&a.st->counter)) return;
+  if (dbg_cta) DBG_CLK(4);
 
   // ---- last CTA: total, derive p(0), Fiat-Shamir, fold the claim -------------------------------
   const uint32_t nparts = gridDim.x * gridDim.y;
@@ -121,7 +132,9 @@ __global__ void __launch_bounds__(SC_THREADS) sc_eval_round_kernel(ScEvalArgs a)
   if (threadIdx.x < 32) {  // warp 0, warp-uniform control flow; lane i owns p(i)
     const int lane = threadIdx.x;
     __shared__ Transcript sh_tr;
+    if (dbg_cta) DBG_CLK(5);
     trw_copy(&sh_tr, a.tr);
+    if (dbg_cta) DBG_CLK(6);
     const Fr p1 = fr_bcast(acc[0], 0);
     Fr mine = fe_zero<FrP>();
 #pragma unroll
@@ -131,8 +144,11 @@ __global__ void __launch_bounds__(SC_THREADS) sc_eval_round_kernel(ScEvalArgs a)
     }
     if (lane == 0) mine = fe_ld(&a.st->claim) - p1;  // p(0) = sum - p(1)   (eval.rs:129)
     const Fr canon = fr_canon_ni(mine);              // D+1 conversions in parallel lanes
+    if (dbg_cta) DBG_CLK(7);
     for (int x = 0; x <= D; ++x) trw_write_canon_from_lane(&sh_tr, canon, x, true);
+    if (dbg_cta) DBG_CLK(8);
     const Fr ch = trw_squeeze(&sh_tr);
+    if (dbg_cta) DBG_CLK(9);
     // next claim p(ch) = Σ_i p(i) w_i Π_{j != i} (ch - j): lane i builds its own term
     const Fr one = fe_one<FrP>();
     Fr num = lane <= D ? a.bary->w[D][lane <= D ? lane : 0] : fe_zero<FrP>();
@@ -151,12 +167,14 @@ __global__ void __launch_bounds__(SC_THREADS) sc_eval_round_kernel(ScEvalArgs a)
       for (int i = 0; i < 8; ++i) o.v[i] = __shfl_xor_sync(0xffffffffu, term.v[i], off);
       term = term + o;
     }
+    if (dbg_cta) DBG_CLK(10);
     trw_copy(a.tr, &sh_tr);
     if (lane == 0) {
       fe_st(a.challenges_out + a.round, ch);
       fe_st(&a.st->r, ch);
       fe_st(&a.st->claim, term);
     }
+    if (dbg_cta) DBG_CLK(11);
   }
 }
 
@@ -208,6 +226,7 @@ int sumcheck_prove_evals(Ctx* c, const ScEvalJob& job) {
   a.tr = c->d_tr;
   a.bary = c->d_bary;
   a.challenges_out = job.challenges_out;
+  a.dbg = c->dbg_clocks;
   const Fr* cur[SC_MAX_TABLES + 1];  // current (unbound) tables; slot ntab = eq
   for (int i = 0; i < ntab; ++i) cur[i] = job.tables[i];
   cur[ntab] = eq0;

@@ -219,21 +219,41 @@ static __device__ __noinline__ void keccak_f1600_warp(uint64_t* s) {
 }
 
 // `t` must be in shared memory (or global) visible to the whole warp
+// Absorb `nwords` (<= 32) little-endian u32 words held identically by every lane: lane i XORs word i
+// into the rate (viewed as 34 u32 words); if the block fills up, permute and let the remaining lanes
+// continue at the start of the rate.
 static __device__ __noinline__ void trw_absorb_words(Transcript* t, const uint32_t* w, int nwords) {
   const int lane = threadIdx.x & 31;
-  uint32_t p = t->pos;
-  for (int i = 0; i < nwords; ++i) {
-    if (lane == 0) t->s[p >> 3] ^= (uint64_t)w[i] << (8 * (p & 7));
-    p += 4;
-    if (p == 136) {
+  uint32_t* s32 = reinterpret_cast<uint32_t*>(t->s);
+  const uint32_t p = t->pos >> 2;  // word position inside the 34-word rate
+  uint32_t mine = 0;
+#pragma unroll
+  for (int k = 0; k < 8; ++k)
+    if (k == lane) mine = w[k];
+  if (nwords > 8) {  // generic path (not used on the hot path): sequential
+    for (int i = 0; i < nwords; ++i) {
+      uint32_t q = (t->pos >> 2);
+      if (lane == 0) s32[q] ^= w[i];
       __syncwarp();
-      keccak_f1600_warp(t->s);
+      if (lane == 0) t->pos = (q + 1 == 34) ? 0 : 4 * (q + 1);
       __syncwarp();
-      p = 0;
+      if (q + 1 == 34) {
+        keccak_f1600_warp(t->s);
+        __syncwarp();
+      }
     }
+    return;
   }
+  const uint32_t j = p + lane;
+  if (lane < nwords && j < 34) s32[j] ^= mine;
   __syncwarp();
-  if (lane == 0) t->pos = p;
+  if (p + nwords >= 34) {
+    keccak_f1600_warp(t->s);
+    __syncwarp();
+    if (lane < nwords && j >= 34) s32[j - 34] ^= mine;
+    __syncwarp();
+  }
+  if (lane == 0) t->pos = 4 * ((p + nwords) % 34);
   __syncwarp();
 }
 __device__ __forceinline__ Fr trw_squeeze(Transcript* t) {

@@ -45,6 +45,8 @@ uint64_t b200_launch_count(b200_ctx* ctx, int reset);
 void* b200_stream(b200_ctx* ctx);
 /* per-launch CUDA-event timing of the sum-check round kernels (the reference's `sum_check_prove_round-i`
  * timers, classic.rs:226): enable, run a prove, then read (ms[i], round tag[i]) pairs */
+/* debug: clock64() stamps of single-CTA round kernels (needs env B200_DEBUG_CLOCKS=1 at ctx creation); out[32*16] */
+int b200_debug_clocks(b200_ctx* ctx, long long* out);
 int b200_profile_enable(b200_ctx* ctx, int on);
 int b200_profile_read(b200_ctx* ctx, float* ms, int* tags, int cap, int* n);
 
