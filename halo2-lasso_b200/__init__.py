@@ -405,3 +405,58 @@ class LassoProver:
         lib().b200_poly_free(self.ctx.h, mt)
         lib().b200_poly_free(self.ctx.h, st)
         return m_out, s_out
+
+
+# ---- multi-GPU (one process per GPU) ---------------------------------------------------------
+def dist_init(ctx, rank=None, world=None):
+    """Map every rank's mailbox over CUDA IPC / NVLink. Needs an initialised torch.distributed group
+    (any backend: only 64-byte handles are exchanged)."""
+    import torch.distributed as dist
+
+    rank = dist.get_rank() if rank is None else rank
+    world = dist.get_world_size() if world is None else world
+    mine = (C.c_uint8 * 64)()
+    _chk(lib().b200_dist_mailbox_handle(ctx.h, mine), "dist_mailbox_handle")
+    handles = exchange_handles(bytes(mine), world)
+    blob = b"".join(handles)
+    _chk(lib().b200_dist_init(ctx.h, C.c_int(rank), C.c_int(world), blob), "dist_init")
+    dist.barrier()
+    return rank, world
+
+
+def exchange_handles(mine: bytes, world: int):
+    """all-gather of fixed-size byte strings in rank order (host-side plumbing, testable with gloo)."""
+    import torch.distributed as dist
+
+    out = [None] * world
+    dist.all_gather_object(out, mine)
+    assert all(isinstance(h, (bytes, bytearray)) and len(h) == len(mine) for h in out)
+    return [bytes(h) for h in out]
+
+
+def shard_slice(n_total_vars: int, rank: int, world: int):
+    """[lo, hi) of the hypercube slice owned by `rank` when sharding on the TOP log2(world) variables."""
+    g = world.bit_length() - 1
+    assert 1 << g == world and n_total_vars > g
+    size = 1 << (n_total_vars - g)
+    return rank * size, (rank + 1) * size
+
+
+def sumcheck_prove_evals_sharded(ctx, num_vars_total, local_polys, weights, y, claimed_sum, np_per_term=2):
+    nterms = len(local_polys) // np_per_term
+    ptrs = (C.c_void_p * len(local_polys))(*[p.dev for p in local_polys])
+    ch = np.zeros((num_vars_total, 4), dtype=np.uint64)
+    ev = np.zeros((len(local_polys), 4), dtype=np.uint64)
+    _chk(lib().b200_sumcheck_prove_evals_sharded(ctx.h, C.c_int(num_vars_total), C.c_int(nterms), C.c_int(np_per_term),
+                                                 ptrs, _p(_fr(weights)), _p(_fr(y)), _p(_fr(claimed_sum)), _p(ch), _p(ev)),
+         "sumcheck_prove_evals_sharded")
+    return ch, ev
+
+
+def variable_base_msm_sharded(ctx, local_scalars, local_bases):
+    local_scalars = _fr(local_scalars).reshape(-1, 4)
+    local_bases = np.ascontiguousarray(local_bases, dtype=np.uint64).reshape(-1, 8)
+    out = np.zeros(8, dtype=np.uint64)
+    _chk(lib().b200_variable_base_msm_sharded(ctx.h, _p(local_scalars), _p(local_bases),
+                                              C.c_uint64(local_scalars.shape[0]), _p(out)), "msm_sharded")
+    return out

@@ -63,6 +63,10 @@ int b200_ctx_create(int device, b200_ctx** out) {
   c->device = device;
   c->launches = 0;
   c->profile = false;
+  c->peer.rank = 0;
+  c->peer.world = 1;
+  c->my_mailbox = nullptr;
+  c->peer_seq = 0;
   c->dbg_clocks = nullptr;
   if (getenv("B200_DEBUG_CLOCKS")) {
     CUDA_TRY(cudaMalloc(&c->dbg_clocks, 32 * 16 * sizeof(long long)));
@@ -98,6 +102,9 @@ void b200_ctx_destroy(b200_ctx* h) {
   cudaStreamSynchronize(c->stream);
   for (auto p : c->srs) cudaFree(p);
   for (auto p : c->srs_ext) cudaFree(p);
+  for (int r = 0; r < c->peer.world; ++r)
+    if (c->my_mailbox && r != c->peer.rank) cudaIpcCloseMemHandle(c->peer.box[r]);
+  if (c->my_mailbox) cudaFree(c->my_mailbox);
   cudaFree(c->d_tr);
   cudaFree(c->d_proof);
   cudaFree(c->d_bary);

@@ -9,6 +9,7 @@
 
 #include "common.cuh"
 #include "g1.cuh"
+#include "peer.cuh"
 
 namespace b200 {
 
@@ -41,6 +42,10 @@ struct Ctx {
   // With them every window of a full-width scalar lands in ONE shared bucket set, which removes the
   // per-window reduction and the 254 dependent doublings of the final Horner pass.
   std::vector<G1Aff*> srs_ext;
+  // multi-GPU (one process per GPU): peer mailboxes mapped over NVLink, see peer.cuh
+  PeerCtx peer;            // world == 1 when not initialised
+  Mailbox* my_mailbox;     // cudaMalloc'ed, exported through CUDA IPC
+  unsigned int peer_seq;   // collectives issued so far (identical on every rank)
 };
 static const int EXT_C = 16;        // window bits of the precomputed tables
 static const int EXT_WINDOWS = 16;  // ceil(255 / 16)
@@ -56,9 +61,16 @@ struct ScEvalJob {
   const Fr* eq_point;               // device, num_vars
   const Fr* claim;                  // device, 1
   Fr* challenges_out;               // device, num_vars
-  Fr* evals_out;                    // device, T*NP
+  Fr* evals_out;                    // device, T*NP (+1 when want_eq_eval: the bound eq value last)
+  const Fr* eq_table = nullptr;     // optional prebuilt eq table (2^num_vars); eq_point is then unused
+  const Fr* eq_scale = nullptr;     // optional device scalar multiplied into the eq table built from eq_point
+  bool sharded = false;             // sum the per-round partials over all ranks (peer mailboxes)
+  bool want_eq_eval = false;
 };
 int sumcheck_prove_evals(Ctx* c, const ScEvalJob& job);
+// shard.cu — hypercube-sharded sum-check and point-sharded MSM over peer memory
+int sumcheck_prove_evals_sharded(Ctx* c, const ScEvalJob& job_local, int num_vars_total);
+
 
 // COEFF shape  F(x) = Σ_k s_k * eq(x, y_k) * P_k(x)   (CoefficientsProver, degree 2)
 struct ScCoeffJob {
@@ -80,6 +92,7 @@ int mle_eval_many(Ctx* c, const Fr* const* h_tables, int ntables, int n, const F
 int fr_lincomb(Ctx* c, const Fr* const* h_tables, int k, const Fr* d_scalars, size_t len,
                Fr* d_out);                                                      // Σ s_i P_i
 int fr_convert(Ctx* c, const Fr* d_in, Fr* d_out, size_t n, int to_mont);
+int fr_scale(Ctx* c, Fr* d_tab, size_t n, const Fr* d_scalar);  // tab[i] *= scalar
 int fr_from_u64(Ctx* c, const uint64_t* d_in, Fr* d_out, size_t n);
 int quotient_step(Ctx* c, Fr* d_rem, size_t half, const Fr* d_x, Fr* d_q);     // pcs/multilinear.rs:72-107
 int eq_xy_eval_dev(Ctx* c, const Fr* d_x, const Fr* d_y, int n, Fr* d_out);    // sum_check.rs:111-121
@@ -99,6 +112,7 @@ struct MsmJob {
   const G1Aff* ext;     // optional precomputed window multiples of `bases` (Ctx::srs_ext layout), or null
 };
 int msm_batch(Ctx* c, const MsmJob* jobs, int J, G1Aff* d_out);
+int msm_sharded(Ctx* c, const MsmJob& local, G1Aff* d_out);  // shard.cu
 
 // kzg.cu — MultilinearKzg (pb/pcs/multilinear/kzg.rs) + additive::batch_open (pb/pcs/multilinear.rs:134-235)
 struct BatchOpenJob {

@@ -170,6 +170,20 @@ int fr_lincomb(Ctx* c, const Fr* const* h_tables, int k, const Fr* d_scalars, si
   return B200_OK;
 }
 
+__global__ void scale_kernel(Fr* __restrict__ tab, size_t n, const Fr* __restrict__ scalar) {
+  const Fr sc = fe_ld(scalar);
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) fe_st(tab + i, fe_ld(tab + i) * sc);
+}
+int fr_scale(Ctx* c, Fr* d_tab, size_t n, const Fr* d_scalar) {
+  int blocks = (int)((n + 255) / 256);
+  if (blocks > NUM_SMS * 8) blocks = NUM_SMS * 8;
+  scale_kernel<<<blocks, 256, 0, c->stream>>>(d_tab, n, d_scalar);
+  count_launch(c);
+  CUDA_TRY(cudaGetLastError());
+  return B200_OK;
+}
+
 __global__ void convert_kernel(const Fr* __restrict__ in, Fr* __restrict__ out, size_t n, int to_mont) {
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {

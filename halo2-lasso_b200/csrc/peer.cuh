@@ -1,0 +1,74 @@
+// Peer-memory collectives for the hypercube-sharded sum-check and the point-sharded MSM.
+// Every rank owns a small MAILBOX in its own HBM; all ranks map all mailboxes through CUDA IPC (NVLink 5 /
+// NVSwitch P2P). A collective is executed INSIDE the compute kernel by one warp of its last CTA:
+//   write my values into slot[my_rank] of every peer's mailbox  ->  __threadfence_system()  ->  publish the
+//   sequence number  ->  spin until every slot of MY mailbox carries that sequence number  ->  read.
+// Payloads are a few field elements (<= 192 B per round message), so this is latency- not bandwidth-bound;
+// fusing it into the round kernel removes the NCCL launch and the extra kernel a host-driven all-gather
+// would need. Slots are double-buffered on the parity of the sequence number: a rank can be at most one
+// collective ahead of any peer (it needs that peer's data to finish the current one).
+#pragma once
+#include "ff32.cuh"
+
+namespace b200 {
+
+static const int PEER_MAX_WORLD = 8;
+static const int PEER_MAX_VALS = 72;  // field elements per message
+
+struct MailSlot {
+  unsigned int seq[2];
+  unsigned int pad[6];
+  Fr data[2][PEER_MAX_VALS];
+};
+struct Mailbox {
+  MailSlot slot[PEER_MAX_WORLD];  // indexed by SOURCE rank
+};
+struct PeerCtx {
+  int rank, world;
+  Mailbox* box[PEER_MAX_WORLD];  // box[r] = rank r's mailbox as mapped in this process (box[rank] is local)
+};
+
+#if defined(__CUDACC__)
+__device__ __forceinline__ void st_sys_fr(Fr* p, const Fr& v) {
+  volatile uint32_t* q = reinterpret_cast<volatile uint32_t*>(p);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) q[i] = v.v[i];
+}
+__device__ __forceinline__ Fr ld_sys_fr(const Fr* p) {
+  const volatile uint32_t* q = reinterpret_cast<const volatile uint32_t*>(p);
+  Fr r;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) r.v[i] = q[i];
+  return r;
+}
+
+// All-gather `cnt` (<= 32) field elements per rank. Called by ALL 32 lanes of one warp; lane i < cnt
+// contributes `mine`. Afterwards lane i < cnt calls peer_read(pc, seq, r, i) for each source rank r.
+__device__ __forceinline__ void peer_publish(const PeerCtx& pc, unsigned int seq, const Fr& mine, int cnt) {
+  const int lane = threadIdx.x & 31;
+  const int par = seq & 1;
+  if (lane < cnt) {
+    for (int r = 0; r < pc.world; ++r) st_sys_fr(&pc.box[r]->slot[pc.rank].data[par][lane], mine);
+  }
+  __threadfence_system();
+  __syncwarp();
+  if (lane < pc.world) {
+    volatile unsigned int* f = &pc.box[lane]->slot[pc.rank].seq[par];
+    *f = seq;
+  }
+  __threadfence_system();
+  // wait for every source rank (lane r polls source r in MY mailbox)
+  if (lane < pc.world) {
+    const volatile unsigned int* f = &pc.box[pc.rank]->slot[lane].seq[par];
+    while (*f != seq) {
+    }
+  }
+  __syncwarp();
+  __threadfence_system();
+}
+__device__ __forceinline__ Fr peer_read(const PeerCtx& pc, unsigned int seq, int src, int idx) {
+  return ld_sys_fr(&pc.box[pc.rank]->slot[src].data[seq & 1][idx]);
+}
+#endif
+
+}  // namespace b200

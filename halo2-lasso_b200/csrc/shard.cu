@@ -1,0 +1,121 @@
+// Multi-GPU sharding of the two kernels BASELINE cfg4 names, one process per GPU.
+//
+// Sum-check: rank g owns the contiguous slice evals[g*N/G .. (g+1)*N/G) of every table, i.e. the TOP
+// log2 G variables are fixed to the bits of g. The reference binds bit 0 first (multilinear.rs:612-616), so
+// the first n - log2 G rounds only need the D per-rank partial sums of each round message: they are
+// exchanged INSIDE the round kernel through peer memory (peer.cuh) and every rank then runs the identical
+// Fiat-Shamir step on its own device transcript. After those rounds each table is down to one value per
+// rank; one more peer all-gather rebuilds the G-entry tables everywhere and the last log2 G rounds run
+// redundantly on every rank. The transcript is byte-identical to the single-GPU / reference proof.
+//
+// MSM: each rank commits its own point range; the G affine partial results are all-gathered and added.
+#include "internal.h"
+
+namespace b200 {
+
+// eq factor of the fixed top variables: Π_j (rank_j ? y_j : 1 - y_j)
+__global__ void shard_eq_factor_kernel(const Fr* y_top, int g, int rank, Fr* out) {
+  if (threadIdx.x || blockIdx.x) return;
+  const Fr one = fe_one<FrP>();
+  Fr acc = one;
+  for (int j = 0; j < g; ++j) {
+    const Fr yj = fe_ld(y_top + j);
+    acc = acc * (((rank >> j) & 1) ? yj : one - yj);
+  }
+  fe_st(out, acc);
+}
+
+// all-gather `cnt` (<= 32) values per rank; gathered[i * world + r] = value i of rank r
+__global__ void shard_gather_kernel(PeerCtx pc, unsigned int seq, const Fr* vals, int cnt, Fr* gathered) {
+  const int lane = threadIdx.x;
+  const Fr mine = lane < cnt ? fe_ld(vals + lane) : fe_zero<FrP>();
+  peer_publish(pc, seq, mine, cnt);
+  if (lane < cnt)
+    for (int r = 0; r < pc.world; ++r) fe_st(gathered + (size_t)lane * pc.world + r, peer_read(pc, seq, r, lane));
+}
+
+int sumcheck_prove_evals_sharded(Ctx* c, const ScEvalJob& job_local, int n) {
+  const int G = c->peer.world;
+  int g = 0;
+  while ((1 << g) < G) ++g;
+  if (G < 2 || (1 << g) != G || n - g < 1) return B200_ERR_ARG;
+  const int n_loc = n - g, ntab = job_local.T * job_local.NP;
+  if (ntab + 1 > 32) return B200_ERR_ARG;
+  cudaStream_t s = c->stream;
+  Fr* scratch = nullptr;  // factor | finals[ntab+1] | gathered[(ntab+1)*G] | evals2[ntab]
+  const size_t nscr = 1 + (ntab + 1) + (size_t)(ntab + 1) * G + ntab + 1;
+  CUDA_TRY(cudaMallocAsync(&scratch, nscr * sizeof(Fr), s));
+  Fr* factor = scratch;
+  Fr* finals = factor + 1;
+  Fr* gathered = finals + ntab + 1;
+  shard_eq_factor_kernel<<<1, 32, 0, s>>>(job_local.eq_point + n_loc, g, c->peer.rank, factor);
+  count_launch(c);
+
+  // phase 1: n_loc rounds on the local slices, partial sums exchanged inside the round kernel
+  ScEvalJob j1 = job_local;
+  j1.num_vars = n_loc;
+  j1.eq_scale = factor;
+  j1.sharded = true;
+  j1.want_eq_eval = true;
+  j1.evals_out = finals;
+  int rc = sumcheck_prove_evals(c, j1);
+  if (rc) return rc;
+
+  // phase 2: rebuild the G-entry tables everywhere and finish redundantly
+  shard_gather_kernel<<<1, 32, 0, s>>>(c->peer, ++c->peer_seq, finals, ntab + 1, gathered);
+  count_launch(c);
+  ScEvalJob j2 = job_local;
+  j2.num_vars = g;
+  for (int i = 0; i < ntab; ++i) j2.tables[i] = gathered + (size_t)i * G;
+  j2.eq_table = gathered + (size_t)ntab * G;
+  j2.claim = &c->d_sc->claim;  // the running claim after phase 1
+  j2.challenges_out = job_local.challenges_out + n_loc;
+  j2.evals_out = job_local.evals_out;
+  rc = sumcheck_prove_evals(c, j2);
+  if (rc) return rc;
+  CUDA_TRY(cudaFreeAsync(scratch, s));
+  return B200_OK;
+}
+
+__global__ void shard_point_sum_kernel(PeerCtx pc, unsigned int seq, const G1Aff* mine, G1Aff* out) {
+  // the affine point travels as two field-sized values (x, y); Fq and Fr share the 8x32-bit layout
+  const int lane = threadIdx.x;
+  Fr v = fe_zero<FrP>();
+  if (lane < 2) {
+    const Fq c = fe_ld(lane == 0 ? &mine->x : &mine->y);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v.v[i] = c.v[i];
+  }
+  peer_publish(pc, seq, v, 2);
+  if (lane == 0) {
+    G1Xyzz acc = g1_identity();
+    for (int r = 0; r < pc.world; ++r) {
+      const Fr x = peer_read(pc, seq, r, 0), y = peer_read(pc, seq, r, 1);
+      G1Aff p;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        p.x.v[i] = x.v[i];
+        p.y.v[i] = y.v[i];
+      }
+      acc = g1_add_affine(acc, p, false);
+    }
+    const G1Aff a = g1_to_affine(acc);
+    fe_st(&out->x, a.x);
+    fe_st(&out->y, a.y);
+  }
+}
+
+int msm_sharded(Ctx* c, const MsmJob& local, G1Aff* d_out) {
+  if (c->peer.world < 2) return B200_ERR_ARG;
+  G1Aff* part = nullptr;
+  CUDA_TRY(cudaMallocAsync(&part, sizeof(G1Aff), c->stream));
+  int rc = msm_batch(c, &local, 1, part);
+  if (rc) return rc;
+  shard_point_sum_kernel<<<1, 32, 0, c->stream>>>(c->peer, ++c->peer_seq, part, d_out);
+  count_launch(c);
+  CUDA_TRY(cudaFreeAsync(part, c->stream));
+  CUDA_TRY(cudaGetLastError());
+  return B200_OK;
+}
+
+}  // namespace b200

@@ -27,6 +27,8 @@ struct ScEvalArgs {
   uint32_t pairs;
   int round;
   long long* dbg;  // optional clock64() trace of the last CTA (debug builds of the bench only)
+  PeerCtx peer;    // world > 1: the round totals are summed over all ranks through the peer mailboxes
+  unsigned int seq;
 };
 #define DBG_CLK(i)                                                     \
   do {                                                                 \
@@ -135,11 +137,24 @@ __global__ void __launch_bounds__(SC_THREADS) sc_eval_round_kernel(ScEvalArgs a)
     if (dbg_cta) DBG_CLK(5);
     trw_copy(&sh_tr, a.tr);
     if (dbg_cta) DBG_CLK(6);
-    const Fr p1 = fr_bcast(acc[0], 0);
-    Fr mine = fe_zero<FrP>();
+    Fr tot = fe_zero<FrP>();  // lane x < D owns the total of evaluation point x+1
 #pragma unroll
     for (int x = 0; x < D; ++x) {
       const Fr tmp = fr_bcast(acc[x], 0);
+      if (lane == x) tot = tmp;
+    }
+    if (a.peer.world > 1) {  // fused collective: all-gather the D partials over NVLink and add them
+      peer_publish(a.peer, a.seq, tot, D);
+      Fr sum = fe_zero<FrP>();
+      if (lane < D)
+        for (int r = 0; r < a.peer.world; ++r) sum = sum + peer_read(a.peer, a.seq, r, lane);
+      tot = sum;
+    }
+    const Fr p1 = fr_bcast(tot, 0);
+    Fr mine = fe_zero<FrP>();
+#pragma unroll
+    for (int x = 0; x < D; ++x) {
+      const Fr tmp = fr_bcast(tot, x);
       if (lane == x + 1) mine = tmp;
     }
     if (lane == 0) mine = fe_ld(&a.st->claim) - p1;  // p(0) = sum - p(1)   (eval.rs:129)
@@ -211,11 +226,18 @@ int sumcheck_prove_evals(Ctx* c, const ScEvalJob& job) {
   // scratch: eq table (N) + ping-pong halves for eq and every table
   const size_t szA = N / 2, szB = N / 4 ? N / 4 : 1;
   Fr *eq0 = nullptr, *bufA = nullptr, *bufB = nullptr;
-  CUDA_TRY(cudaMallocAsync(&eq0, N * sizeof(Fr), s));
   CUDA_TRY(cudaMallocAsync(&bufA, (size_t)(ntab + 1) * szA * sizeof(Fr), s));
   CUDA_TRY(cudaMallocAsync(&bufB, (size_t)(ntab + 1) * szB * sizeof(Fr), s));
-  int rc = eq_build(c, job.eq_point, n, eq0);
-  if (rc) return rc;
+  int rc;
+  if (!job.eq_table) {
+    CUDA_TRY(cudaMallocAsync(&eq0, N * sizeof(Fr), s));
+    rc = eq_build(c, job.eq_point, n, eq0);
+    if (rc) return rc;
+    if (job.eq_scale) {
+      rc = fr_scale(c, eq0, N, job.eq_scale);
+      if (rc) return rc;
+    }
+  }
   sc_init_kernel<<<1, 32, 0, s>>>(c->d_sc, job.claim);
   count_launch(c);
 
@@ -227,11 +249,15 @@ int sumcheck_prove_evals(Ctx* c, const ScEvalJob& job) {
   a.bary = c->d_bary;
   a.challenges_out = job.challenges_out;
   a.dbg = c->dbg_clocks;
+  a.peer = c->peer;
+  if (!job.sharded) a.peer.world = 1;
+  a.seq = 0;
   const Fr* cur[SC_MAX_TABLES + 1];  // current (unbound) tables; slot ntab = eq
   for (int i = 0; i < ntab; ++i) cur[i] = job.tables[i];
-  cur[ntab] = eq0;
+  cur[ntab] = job.eq_table ? job.eq_table : eq0;
   for (int round = 0; round < n; ++round) {
     a.round = round;
+    if (a.peer.world > 1) a.seq = ++c->peer_seq;
     a.pairs = (uint32_t)(N >> (round + 1));
     Fr* dst_base = (round & 1) ? bufA : bufB;  // round 1 writes A, round 2 writes B, ...
     const size_t dst_sz = (round & 1) ? szA : szB;
@@ -257,12 +283,13 @@ int sumcheck_prove_evals(Ctx* c, const ScEvalJob& job) {
   }
   // final bind -> evals (eq excluded: ProverState::into_evals returns the polys only, classic.rs:143-149)
   const Fr** d_ptrs = nullptr;
-  CUDA_TRY(cudaMallocAsync(&d_ptrs, ntab * sizeof(Fr*), s));
-  CUDA_TRY(cudaMemcpyAsync(d_ptrs, cur, ntab * sizeof(Fr*), cudaMemcpyHostToDevice, s));
-  sc_final_bind_kernel<<<(ntab + 63) / 64, 64, 0, s>>>(d_ptrs, ntab, c->d_sc, job.evals_out);
+  const int nfinal = ntab + (job.want_eq_eval ? 1 : 0);
+  CUDA_TRY(cudaMallocAsync(&d_ptrs, nfinal * sizeof(Fr*), s));
+  CUDA_TRY(cudaMemcpyAsync(d_ptrs, cur, nfinal * sizeof(Fr*), cudaMemcpyHostToDevice, s));
+  sc_final_bind_kernel<<<(nfinal + 63) / 64, 64, 0, s>>>(d_ptrs, nfinal, c->d_sc, job.evals_out);
   count_launch(c);
   CUDA_TRY(cudaFreeAsync(d_ptrs, s));
-  CUDA_TRY(cudaFreeAsync(eq0, s));
+  if (eq0) CUDA_TRY(cudaFreeAsync(eq0, s));
   CUDA_TRY(cudaFreeAsync(bufA, s));
   CUDA_TRY(cudaFreeAsync(bufB, s));
   CUDA_TRY(cudaGetLastError());

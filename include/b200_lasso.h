@@ -129,6 +129,22 @@ int b200_kzg_batch_open(b200_ctx* ctx, int num_vars, const void* const* dev_poly
                         const void* host_points, int npoints, const int* ev_poly, const int* ev_point,
                         const void* host_ev_values, int nevals);
 
+/* ---- multi-GPU: one process per GPU, collectives through NVLink peer memory --------- */
+/* CUDA-IPC handle (64 bytes) of this context's mailbox; exchange the handles of all ranks out of band
+ * (e.g. torch.distributed.all_gather), then call b200_dist_init with the `world` handles in rank order. */
+int b200_dist_mailbox_handle(b200_ctx* ctx, void* out_handle64);
+int b200_dist_init(b200_ctx* ctx, int rank, int world, const void* handles);
+/* b200_sumcheck_prove_evals on a hypercube sharded over the TOP log2(world) variables: rank g passes the
+ * slices [g*2^n/world, (g+1)*2^n/world) of every table. All ranks must call it; all receive the same
+ * challenges / evals and append the same bytes to their transcripts (identical to the unsharded proof). */
+int b200_sumcheck_prove_evals_sharded(b200_ctx* ctx, int num_vars_total, int nterms, int np,
+                                      const void* const* dev_local_tables, const void* host_weights,
+                                      const void* host_y, const void* host_sum, void* host_challenges_out,
+                                      void* host_evals_out);
+/* variable_base_msm with the points sharded by range: every rank passes its slice, all get the full sum */
+int b200_variable_base_msm_sharded(b200_ctx* ctx, const void* host_scalars_fr, const void* host_bases_g1,
+                                   uint64_t n_local, void* host_out_g1);
+
 /* ---- Lasso / Surge lookup argument (north_star; no counterpart in the mounted snapshot).
  * Specification: DESIGN.md "Lasso protocol"; CPU restatement: oracle/lasso.hpp. ---------------------- */
 #define B200_TABLE_RANGE 0 /* chunks x 16-bit limbs, identity subtable, g = sum 2^(16 t) E_t */
