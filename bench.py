@@ -242,6 +242,20 @@ def main():
             dist.barrier()
         return sum(a.elapsed_time(b) for a, b in ev) / steps
 
+    # N > 1: the SAME cfg2 sum-check sharded over the top log2(N) variables (2^20 entries per rank, i.e.
+    # n = 20 + log2 N in total), partial sums exchanged inside the round kernels over NVLink peer memory
+    sharded = None
+    if world > 1 and world & (world - 1) == 0:
+        hl.dist_init(ctx, rank, world)
+        n_tot = SC_VARS + world.bit_length() - 1
+        y_tot = to_mont(np.concatenate([rand_canonical(3, n_tot), np.zeros((32 - n_tot, 4), dtype=np.uint64)])).evals()[:n_tot]
+
+        def sumcheck_sharded():
+            hl.Keccak256Transcript(ctx)
+            hl.sumcheck_prove_evals_sharded(ctx, n_tot, polys, one.reshape(1, 4), y_tot, one)
+
+        sharded = (n_tot, sumcheck_sharded)
+
     sampler = ClockSampler(local_rank)
     sampler.start()
     ctx.launch_count(reset=True)
@@ -249,6 +263,7 @@ def main():
     launches = ctx.launch_count(reset=True) // (args.steps + max(3, args.warmup))
     ms_e2e = timed(lasso_e2e, max(3, args.steps // 2), 3)
     ms_sc = timed(sumcheck_device, 20, 5)
+    ms_sh = timed(sharded[1], 20, 5) if sharded else 0.0
     clocks = sampler.stop()
 
     prof = hl.profile_rounds(ctx, sumcheck_device, SC_VARS, SC_TABLES)
@@ -259,9 +274,9 @@ def main():
             phases[nm] = round(phases.get(nm, 0.0) + t, 4)
 
     if world > 1:
-        t = torch.tensor([ms, ms_e2e, ms_sc], device=dev)
+        t = torch.tensor([ms, ms_e2e, ms_sc, ms_sh], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, ms_e2e, ms_sc = t.tolist()
+        ms, ms_e2e, ms_sc, ms_sh = t.tolist()
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -308,6 +323,11 @@ def main():
         "sumcheck": {"workload": "cfg2: ClassicSumCheck deg-3 eq*a*b, n=20, 2560 proof bytes", "ms_per_proof": ms_sc,
                      "algorithmic_bytes": SC_ALGO_BYTES, "GBps": world * SC_ALGO_BYTES / (ms_sc * 1e-3) / 1e9,
                      "frac_of_hbm_peak": SC_ALGO_BYTES / (ms_sc * 1e-3) / 1e9 / peak},
+        "sumcheck_sharded": None if not sharded else {
+            "workload": f"cfg2 shape sharded on the top {world.bit_length() - 1} variable(s): n={sharded[0]}, 2^20 entries per GPU, "
+                        "per-round partials exchanged inside the kernel over NVLink peer memory",
+            "ms_per_proof": ms_sh, "algorithmic_bytes": 32 * SC_TABLES * (4 * (1 << sharded[0]) - 3),
+            "GBps": 32 * SC_TABLES * (4 * (1 << sharded[0]) - 3) / (ms_sh * 1e-3) / 1e9},
         "roofline": roof, "cpu_baseline": cpu}))
     if world > 1:
         dist.destroy_process_group()
