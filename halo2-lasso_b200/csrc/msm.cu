@@ -22,7 +22,7 @@ namespace b200 {
 
 static const int TASK_LEN = 64;
 static const int SEQ_TASKS = 8;     // buckets with more task partials than this go to the warp kernel
-static const int GROUP = 32;        // buckets per thread in the window reduction
+static const int GROUP = 8;        // buckets per thread in the window reduction
 static const int MSM_MAX_JOBS = 64;
 static const int MSM_MAX_WINDOWS = 128;
 
