@@ -460,3 +460,71 @@ def variable_base_msm_sharded(ctx, local_scalars, local_bases):
     _chk(lib().b200_variable_base_msm_sharded(ctx.h, _p(local_scalars), _p(local_bases),
                                               C.c_uint64(local_scalars.shape[0]), _p(out)), "msm_sharded")
     return out
+
+
+# ---- generic expression sum-check (pb/piop/sum_check/classic/eval.rs for any Expression) -----------
+def _mont_consts(ctx, ints):
+    """canonical ints -> Montgomery limbs, converted on the device (no host field arithmetic in the product)."""
+    n = max(1, len(ints))
+    k = 1 << (n - 1).bit_length()
+    raw = np.zeros((k, 4), dtype=np.uint64)
+    for i, v in enumerate(ints):
+        for j in range(4):
+            raw[i, j] = (v >> (64 * j)) & 0xFFFFFFFFFFFFFFFF
+    p = MultilinearPolynomial.new(ctx, raw)
+    _chk(lib().b200_fr_convert(ctx.h, p.dev, p.dev, C.c_uint64(k), C.c_int(1)), "fr_convert")
+    return p.evals()[:n]
+
+
+def prove_expression(ctx, num_vars, expression, polys, challenges, ys, claimed_sum):
+    """`ClassicSumCheck::<EvaluationsProver>::prove(num_vars, VirtualPolynomial::new(expression, polys, challenges,
+    ys), sum, transcript)`. challenges: canonical Python ints; ys: list of (num_vars, 4) Montgomery arrays.
+    Returns (challenges, evals) with evals = every input polynomial bound at the challenges."""
+    from .expression import BooleanHypercube, compile_expression
+
+    leaves, consts, prog = compile_expression(expression, challenges)
+    bh_order = None
+    tables, keep = [], []
+    for leaf in leaves:
+        kind = leaf[0]
+        if kind == "poly":
+            _, p, rot = leaf
+            if rot == 0:
+                tables.append(polys[p])
+            else:
+                t = MultilinearPolynomial.alloc(ctx, num_vars)
+                _chk(lib().b200_poly_rotate(ctx.h, polys[p].dev, C.c_int(num_vars), C.c_int(rot), t.dev), "poly_rotate")
+                tables.append(t)
+        elif kind == "eq":
+            tables.append(MultilinearPolynomial.eq_xy(ctx, ys[leaf[1]]))
+        elif kind == "identity":
+            t = MultilinearPolynomial.alloc(ctx, num_vars)
+            _chk(lib().b200_poly_iota(ctx.h, C.c_int(num_vars), t.dev), "poly_iota")
+            tables.append(t)
+        else:  # lagrange(i): one-hot at the i-th row in BooleanHypercube order (classic.rs:44-55)
+            if bh_order is None:
+                bh_order = BooleanHypercube(num_vars).iter()
+            idx = bh_order[leaf[1] % (1 << num_vars)]
+            t = MultilinearPolynomial.alloc(ctx, num_vars)
+            _chk(lib().b200_poly_onehot(ctx.h, C.c_int(num_vars), C.c_uint64(idx), t.dev), "poly_onehot")
+            tables.append(t)
+    # polynomials that the expression never queries at rotation 0 are still bound and returned (classic.rs:143-149)
+    extra = [p for p in range(len(polys)) if ("poly", p, 0) not in leaves]
+    K = len(tables)
+    if extra:
+        # append them as tables the program never reads; slots shift by len(extra)
+        shift = len(extra)
+        prog = [(op, d + shift if d >= K else d, a + shift if a >= K else a, b + shift if b >= K else b) for op, d, a, b in prog]
+        tables += [polys[p] for p in extra]
+    cm = _mont_consts(ctx, consts)
+    ops = np.asarray(prog, dtype=np.int32).reshape(-1, 4)
+    ptrs = (C.c_void_p * len(tables))(*[t.dev for t in tables])
+    ch = np.zeros((num_vars, 4), dtype=np.uint64)
+    ev = np.zeros((len(tables), 4), dtype=np.uint64)
+    _chk(lib().b200_sumcheck_prove_generic(ctx.h, C.c_int(num_vars), C.c_int(expression.degree()), C.c_int(len(tables)), ptrs,
+                                           C.c_int(len(consts)), _p(cm), C.c_int(ops.shape[0]), _p(ops), _p(_fr(claimed_sum)),
+                                           _p(ch), _p(ev)), "sumcheck_prove_generic")
+    pos = {leaf: i for i, leaf in enumerate(leaves)}
+    for j, p in enumerate(extra):
+        pos[("poly", p, 0)] = K + j
+    return ch, np.stack([ev[pos[("poly", p, 0)]] for p in range(len(polys))])

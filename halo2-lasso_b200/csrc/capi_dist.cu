@@ -103,4 +103,51 @@ int b200_variable_base_msm_sharded(b200_ctx* h, const void* host_scalars_fr, con
   return B200_OK;
 }
 
+// ---- generic expression sum-check -------------------------------------------------------------------
+int b200_sumcheck_prove_generic(b200_ctx* h, int num_vars, int degree, int ntables, const void* const* dev_tables,
+                                int nconsts, const void* host_consts_fr, int nops, const int32_t* host_ops,
+                                const void* host_sum, void* host_challenges_out, void* host_evals_out) {
+  Ctx* c = &h->c;
+  if (num_vars < 1 || num_vars > 30 || ntables < 1 || ntables > 40 || nconsts < 0 || nops < 1) return B200_ERR_ARG;
+  const size_t nin = (size_t)nconsts + 1, nout = (size_t)num_vars + ntables;
+  std::vector<Fr> hbuf(nin);
+  if (nconsts) memcpy(hbuf.data(), host_consts_fr, nconsts * sizeof(Fr));
+  memcpy(hbuf.data() + nconsts, host_sum, sizeof(Fr));
+  Fr* d = nullptr;
+  int4* dops = nullptr;
+  CUDA_TRY(cudaMallocAsync(&d, (nin + nout) * sizeof(Fr), c->stream));
+  CUDA_TRY(cudaMallocAsync(&dops, (size_t)nops * sizeof(int4), c->stream));
+  CUDA_TRY(cudaMemcpyAsync(d, hbuf.data(), nin * sizeof(Fr), cudaMemcpyHostToDevice, c->stream));
+  CUDA_TRY(cudaMemcpyAsync(dops, host_ops, (size_t)nops * sizeof(int4), cudaMemcpyHostToDevice, c->stream));
+  GenericJob job;
+  job.num_vars = num_vars;
+  job.ntables = ntables;
+  job.nconsts = nconsts;
+  job.nops = nops;
+  job.degree = degree;
+  for (int i = 0; i < ntables; ++i) job.tables[i] = (const Fr*)dev_tables[i];
+  job.consts = d;
+  job.ops = dops;
+  job.claim = d + nconsts;
+  job.challenges_out = d + nin;
+  job.evals_out = d + nin + num_vars;
+  int rc = sumcheck_prove_generic(c, job);
+  if (rc) return rc;
+  std::vector<Fr> hout(nout);
+  CUDA_TRY(cudaMemcpyAsync(hout.data(), d + nin, nout * sizeof(Fr), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  memcpy(host_challenges_out, hout.data(), num_vars * sizeof(Fr));
+  memcpy(host_evals_out, hout.data() + num_vars, ntables * sizeof(Fr));
+  CUDA_TRY(cudaFreeAsync(d, c->stream));
+  CUDA_TRY(cudaFreeAsync(dops, c->stream));
+  return B200_OK;
+}
+int b200_poly_iota(b200_ctx* h, int num_vars, void* dev_out) { return poly_iota(&h->c, num_vars, (Fr*)dev_out); }
+int b200_poly_onehot(b200_ctx* h, int num_vars, uint64_t index, void* dev_out) {
+  return poly_onehot(&h->c, num_vars, index, (Fr*)dev_out);
+}
+int b200_poly_rotate(b200_ctx* h, const void* dev_in, int num_vars, int rotation, void* dev_out) {
+  return poly_rotate(&h->c, (const Fr*)dev_in, num_vars, rotation, (Fr*)dev_out);
+}
+
 }  // extern "C"

@@ -1,0 +1,270 @@
+// Generic EvaluationsProver round kernel (pb/piop/sum_check/classic/eval.rs:92-131, 210-323) for an
+// arbitrary `Expression`: the role of ExpressionRegistry's straight-line `Calculation` program
+// (pb/util/expression/evaluator.rs:22-228) is played by a bytecode program produced on the host
+// (halo2-lasso_b200/expression.py::compile_expression) and interpreted per hypercube pair.
+//
+// Every leaf of the expression is a dense device table (polynomial queries — rotated ones gathered
+// through the BooleanHypercube LFSR map, pb/util/arithmetic/bh.rs:105-141 —, eq_xy tables, the identity
+// polynomial, one-hot Lagrange tables), so one code path binds and evaluates all of them: per pair and
+// table (eval, step) = (t[2b+1], t[2b+1]-t[2b]), x -> x+1 adds the step, the program runs on the slot
+// file [tables | constants | temporaries] and its last slot is accumulated into p(x). The bind of the
+// previous challenge is fused exactly as in sumcheck.cu. Slots live in local memory (L1): the program for
+// the vanilla-plonk zero check has 13+ tables at degree 5, far beyond the register file.
+#include "internal.h"
+
+namespace b200 {
+
+static const int GEN_MAX_TABLES = 40;
+static const int GEN_MAX_SLOTS = 200;
+static const int GEN_MAX_DEG = 6;
+
+struct GenArgs {
+  const Fr* in[GEN_MAX_TABLES];
+  Fr* out[GEN_MAX_TABLES];
+  const Fr* consts;
+  const int4* ops;  // (opcode, dst, a, b)
+  int K, C, nops, D;
+  ScState* st;
+  Fr* partial;
+  Transcript* tr;
+  const BaryTable* bary;
+  Fr* challenges_out;
+  uint32_t pairs;
+  int round;
+};
+
+template <bool BIND>
+__global__ void __launch_bounds__(128) sc_generic_round_kernel(GenArgs a) {
+  __shared__ Fr smem[4];
+  __shared__ Fr s_tot[GEN_MAX_DEG];
+  Fr slots[GEN_MAX_SLOTS];
+  Fr step[GEN_MAX_TABLES];
+  Fr acc[GEN_MAX_DEG];
+  const int K = a.K, D = a.D;
+  for (int x = 0; x < D; ++x) acc[x] = fe_zero<FrP>();
+  for (int i = 0; i < a.C; ++i) slots[K + i] = fe_ld(a.consts + i);
+  Fr r = fe_zero<FrP>();
+  if (BIND) r = fe_ld(&a.st->r);
+  const int last = a.ops[a.nops - 1].y;
+
+  for (uint32_t b = blockIdx.x * blockDim.x + threadIdx.x; b < a.pairs; b += gridDim.x * blockDim.x) {
+    for (int k = 0; k < K; ++k) {
+      Fr u0, u1;
+      if (BIND) {
+        const Fr* p = a.in[k] + 4 * (size_t)b;
+        const Fr x0 = fe_ldg(p), x1 = fe_ldg(p + 1), x2 = fe_ldg(p + 2), x3 = fe_ldg(p + 3);
+        u0 = (x1 - x0) * r + x0;
+        u1 = (x3 - x2) * r + x2;
+        fe_st(a.out[k] + 2 * (size_t)b, u0);
+        fe_st(a.out[k] + 2 * (size_t)b + 1, u1);
+      } else {
+        const Fr* p = a.in[k] + 2 * (size_t)b;
+        u0 = fe_ldg(p);
+        u1 = fe_ldg(p + 1);
+      }
+      slots[k] = u1;
+      step[k] = u1 - u0;
+    }
+    for (int x = 0; x < D; ++x) {
+      if (x > 0)
+        for (int k = 0; k < K; ++k) slots[k] = slots[k] + step[k];
+      for (int i = 0; i < a.nops; ++i) {
+        const int4 op = a.ops[i];
+        const Fr lhs = slots[op.z], rhs = slots[op.w];
+        Fr res;
+        switch (op.x) {
+          case 0: res = lhs + rhs; break;
+          case 1: res = lhs - rhs; break;
+          case 2: res = lhs * rhs; break;
+          default: res = fe_neg<FrP>(lhs); break;
+        }
+        slots[op.y] = res;
+      }
+      acc[x] = acc[x] + slots[last];
+    }
+  }
+  // per-CTA partials
+  for (int x = 0; x < D; ++x) {
+    Fr t[1] = {acc[x]};
+    block_reduce_fr<1>(t, smem);
+    if (threadIdx.x == 0) fe_st(a.partial + (size_t)blockIdx.x * D + x, t[0]);
+  }
+  if (!last_cta_ticket(&a.st->counter)) return;
+  for (int x = 0; x < D; ++x) {
+    Fr t[1] = {fe_zero<FrP>()};
+    for (uint32_t i = threadIdx.x; i < gridDim.x; i += blockDim.x) t[0] = t[0] + fr_ld_cg(a.partial + (size_t)i * D + x);
+    block_reduce_fr<1>(t, smem);
+    if (threadIdx.x == 0) s_tot[x] = t[0];
+  }
+  __syncthreads();
+  if (threadIdx.x < 32) {  // warp 0: lane i owns p(i), i <= D (same scheme as sc_eval_round_kernel)
+    const int lane = threadIdx.x;
+    __shared__ Transcript sh_tr;
+    trw_copy(&sh_tr, a.tr);
+    Fr mine = fe_zero<FrP>();
+    if (lane >= 1 && lane <= D) mine = s_tot[lane - 1];
+    if (lane == 0) mine = fe_ld(&a.st->claim) - s_tot[0];  // p(0) = sum - p(1)
+    const Fr canon = fr_canon_ni(mine);
+    for (int x = 0; x <= D; ++x) trw_write_canon_from_lane(&sh_tr, canon, x, true);
+    const Fr ch = trw_squeeze(&sh_tr);
+    const Fr one = fe_one<FrP>();
+    Fr num = lane <= D ? a.bary->w[D][lane <= D ? lane : 0] : fe_zero<FrP>();
+    Fr jf = fe_zero<FrP>();
+    for (int j = 0; j <= D; ++j) {
+      const Fr f = (j == lane) ? one : ch - jf;
+      num = fr_mul_ni(num, f);
+      jf = jf + one;
+    }
+    Fr term = fr_mul_ni(num, mine);
+    if (lane > D) term = fe_zero<FrP>();
+#pragma unroll
+    for (int off = 1; off < 8; off <<= 1) {
+      Fr o;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o.v[i] = __shfl_xor_sync(0xffffffffu, term.v[i], off);
+      term = term + o;
+    }
+    trw_copy(a.tr, &sh_tr);
+    if (lane == 0) {
+      fe_st(a.challenges_out + a.round, ch);
+      fe_st(&a.st->r, ch);
+      fe_st(&a.st->claim, term);
+    }
+  }
+}
+
+__global__ void gen_final_bind_kernel(const Fr* const* tabs, int ntabs, const ScState* st, Fr* evals_out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= ntabs) return;
+  const Fr r = fe_ld(&st->r);
+  const Fr x0 = fe_ld(tabs[i]), x1 = fe_ld(tabs[i] + 1);
+  fe_st(evals_out + i, (x1 - x0) * r + x0);
+}
+__global__ void gen_init_kernel(ScState* st, const Fr* claim) {
+  if (threadIdx.x == 0) {
+    fe_st(&st->claim, fe_ld(claim));
+    fe_st(&st->r, fe_zero<FrP>());
+    st->counter = 0;
+  }
+}
+
+int sumcheck_prove_generic(Ctx* c, const GenericJob& job) {
+  const int n = job.num_vars, K = job.ntables;
+  if (n < 1 || n > 30 || K < 1 || K > GEN_MAX_TABLES || job.degree < 1 || job.degree > GEN_MAX_DEG || job.nops < 1 ||
+      K + job.nconsts + job.nops > GEN_MAX_SLOTS)
+    return B200_ERR_ARG;
+  cudaStream_t s = c->stream;
+  const size_t N = (size_t)1 << n;
+  const size_t szA = N / 2, szB = N / 4 ? N / 4 : 1;
+  Fr *bufA = nullptr, *bufB = nullptr;
+  CUDA_TRY(cudaMallocAsync(&bufA, (size_t)K * szA * sizeof(Fr), s));
+  CUDA_TRY(cudaMallocAsync(&bufB, (size_t)K * szB * sizeof(Fr), s));
+  gen_init_kernel<<<1, 32, 0, s>>>(c->d_sc, job.claim);
+  count_launch(c);
+  GenArgs a;
+  a.consts = job.consts;
+  a.ops = job.ops;
+  a.K = K;
+  a.C = job.nconsts;
+  a.nops = job.nops;
+  a.D = job.degree;
+  a.st = c->d_sc;
+  a.partial = c->d_partial;
+  a.tr = c->d_tr;
+  a.bary = c->d_bary;
+  a.challenges_out = job.challenges_out;
+  const Fr* cur[GEN_MAX_TABLES];
+  for (int i = 0; i < K; ++i) cur[i] = job.tables[i];
+  for (int round = 0; round < n; ++round) {
+    a.round = round;
+    a.pairs = (uint32_t)(N >> (round + 1));
+    Fr* dst_base = (round & 1) ? bufA : bufB;
+    const size_t dst_sz = (round & 1) ? szA : szB;
+    for (int i = 0; i < K; ++i) {
+      a.in[i] = cur[i];
+      a.out[i] = dst_base + (size_t)i * dst_sz;
+    }
+    int blocks = (int)((a.pairs + 127) / 128);
+    if (blocks > NUM_SMS * 4) blocks = NUM_SMS * 4;
+    if ((size_t)blocks * job.degree > c->partial_elems) return B200_ERR_NOMEM;
+    const int pi = prof_begin(c, round);
+    if (round == 0) {
+      sc_generic_round_kernel<false><<<blocks, 128, 0, s>>>(a);
+    } else {
+      sc_generic_round_kernel<true><<<blocks, 128, 0, s>>>(a);
+      for (int i = 0; i < K; ++i) cur[i] = a.out[i];
+    }
+    prof_end(c, pi);
+    count_launch(c);
+  }
+  const Fr** d_ptrs = nullptr;
+  CUDA_TRY(cudaMallocAsync(&d_ptrs, K * sizeof(Fr*), s));
+  CUDA_TRY(cudaMemcpyAsync(d_ptrs, cur, K * sizeof(Fr*), cudaMemcpyHostToDevice, s));
+  gen_final_bind_kernel<<<(K + 63) / 64, 64, 0, s>>>(d_ptrs, K, c->d_sc, job.evals_out);
+  count_launch(c);
+  CUDA_TRY(cudaFreeAsync(d_ptrs, s));
+  CUDA_TRY(cudaFreeAsync(bufA, s));
+  CUDA_TRY(cudaFreeAsync(bufB, s));
+  CUDA_TRY(cudaGetLastError());
+  return B200_OK;
+}
+
+// ---- leaf tables -----------------------------------------------------------------------------------
+// identity polynomial: out[b] = F::from(b)      (CommonPolynomial::Identity, sum_check.rs:123-125)
+__global__ void poly_iota_kernel(Fr* out, size_t n) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x; b < n; b += stride) fe_st(out + b, fe_from_u64<FrP>(b));
+}
+// Lagrange_i: one-hot at hypercube point `index`
+__global__ void poly_onehot_kernel(Fr* out, size_t n, size_t index) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x; b < n; b += stride)
+    fe_st(out + b, b == index ? fe_one<FrP>() : fe_zero<FrP>());
+}
+// rotated[b] = poly[bh.rotate(b, rotation)]   (classic.rs:105-126, bh.rs:105-153)
+__global__ void poly_rotate_kernel(const Fr* __restrict__ in, Fr* __restrict__ out, int num_vars, uint32_t primitive,
+                                   int rotation) {
+  const size_t n = (size_t)1 << num_vars, stride = (size_t)gridDim.x * blockDim.x;
+  const uint64_t x_inv = primitive >> 1;
+  for (size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x; b < n; b += stride) {
+    uint64_t s = b;
+    for (int i = 0; i < rotation; ++i) {
+      s <<= 1;
+      s ^= (s >> num_vars) * primitive;
+    }
+    for (int i = 0; i > rotation; --i) s = (s >> 1) ^ ((s & 1) * x_inv);
+    fe_st(out + b, fe_ldg(in + s));
+  }
+}
+static int grid_for(size_t n) {
+  int blocks = (int)((n + 255) / 256);
+  if (blocks > NUM_SMS * 8) blocks = NUM_SMS * 8;
+  return blocks < 1 ? 1 : blocks;
+}
+int poly_iota(Ctx* c, int num_vars, Fr* d_out) {
+  const size_t n = (size_t)1 << num_vars;
+  poly_iota_kernel<<<grid_for(n), 256, 0, c->stream>>>(d_out, n);
+  count_launch(c);
+  CUDA_TRY(cudaGetLastError());
+  return B200_OK;
+}
+int poly_onehot(Ctx* c, int num_vars, uint64_t index, Fr* d_out) {
+  const size_t n = (size_t)1 << num_vars;
+  if (index >= n) return B200_ERR_ARG;
+  poly_onehot_kernel<<<grid_for(n), 256, 0, c->stream>>>(d_out, n, index);
+  count_launch(c);
+  CUDA_TRY(cudaGetLastError());
+  return B200_OK;
+}
+int poly_rotate(Ctx* c, const Fr* d_in, int num_vars, int rotation, Fr* d_out) {
+  static const uint32_t PRIM[32] = {1, 3, 7, 11, 19, 37, 67, 131, 285, 529, 1033, 2053, 4179, 8219, 16427, 32771,
+                                    65581, 131081, 262183, 524327, 1048585, 2097157, 4194307, 8388641, 16777243,
+                                    33554441, 67108935, 134217767, 268435465, 536870917, 1073741907, 2147483657u};
+  if (num_vars < 1 || num_vars > 31 || rotation < -num_vars || rotation > num_vars) return B200_ERR_ARG;
+  poly_rotate_kernel<<<grid_for((size_t)1 << num_vars), 256, 0, c->stream>>>(d_in, d_out, num_vars, PRIM[num_vars], rotation);
+  count_launch(c);
+  CUDA_TRY(cudaGetLastError());
+  return B200_OK;
+}
+
+}  // namespace b200

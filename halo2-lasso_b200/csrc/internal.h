@@ -84,6 +84,21 @@ struct ScCoeffJob {
 };
 int sumcheck_prove_coeffs(Ctx* c, const ScCoeffJob& job);
 
+// generic.cu — EvaluationsProver for an arbitrary Expression compiled to bytecode on the host
+struct GenericJob {
+  int num_vars, ntables, nconsts, nops, degree;
+  const Fr* tables[64];  // every leaf of the expression as a dense 2^num_vars table
+  const Fr* consts;      // device, nconsts (Montgomery)
+  const int4* ops;       // device, nops x (opcode, dst, a, b)
+  const Fr* claim;       // device
+  Fr* challenges_out;    // device, num_vars
+  Fr* evals_out;         // device, ntables
+};
+int sumcheck_prove_generic(Ctx* c, const GenericJob& job);
+int poly_iota(Ctx* c, int num_vars, Fr* d_out);
+int poly_onehot(Ctx* c, int num_vars, uint64_t index, Fr* d_out);
+int poly_rotate(Ctx* c, const Fr* d_in, int num_vars, int rotation, Fr* d_out);
+
 // mle.cu
 int eq_build(Ctx* c, const Fr* d_y, int n, Fr* d_out);                         // eq_xy
 int fix_var(Ctx* c, const Fr* d_in, int n, const Fr* d_r, Fr* d_out);          // one bind

@@ -102,6 +102,21 @@ int b200_sumcheck_prove_coeffs(b200_ctx* ctx, int num_vars, int nprods, const vo
                                const void* host_scalars, const void* host_ys, const void* host_sum,
                                void* host_challenges_out, void* host_evals_out);
 
+/* EvaluationsProver for an ARBITRARY Expression (classic/eval.rs + util/expression/evaluator.rs): the host
+ * compiles the expression into a straight-line program over slots [tables | constants | temporaries]
+ * (ops = nops x {opcode 0 add / 1 sub / 2 mul / 3 neg, dst, a, b}); every leaf (polynomial query, rotated
+ * query, eq_xy, identity, Lagrange) is passed as a dense device table. degree = Expression::degree().
+ * evals_out[ntables] = every table bound at the challenges. */
+int b200_sumcheck_prove_generic(b200_ctx* ctx, int num_vars, int degree, int ntables,
+                                const void* const* dev_tables, int nconsts, const void* host_consts_fr, int nops,
+                                const int32_t* host_ops, const void* host_sum, void* host_challenges_out,
+                                void* host_evals_out);
+/* leaf tables: identity polynomial b -> F::from(b); one-hot Lagrange table; rotated[b] = poly[bh.rotate(b, rot)]
+ * (BooleanHypercube LFSR order, pb/util/arithmetic/bh.rs) */
+int b200_poly_iota(b200_ctx* ctx, int num_vars, void* dev_out);
+int b200_poly_onehot(b200_ctx* ctx, int num_vars, uint64_t index, void* dev_out);
+int b200_poly_rotate(b200_ctx* ctx, const void* dev_in, int num_vars, int rotation, void* dev_out);
+
 /* ---- variable_base_msm (pb/util/arithmetic/msm.rs:84-115) ------------------------------------- */
 /* Σ scalars[i] * bases[i] with HOST inputs (the free function's signature); out = affine point.
  * An identity result is returned as (0, 0). */

@@ -5,6 +5,7 @@
 #include <chrono>
 #include <cstdio>
 
+#include "expression.hpp"
 #include "lasso.hpp"
 
 using namespace oracle;
@@ -144,6 +145,29 @@ int orc_sumcheck_verify(void* tr, int num_vars, int degree, const Fr* sum, int c
   if (!sumcheck_verify(num_vars, degree, *sum, coeffs != 0, *(Transcript*)tr, final_claim, &ch)) return 1;
   memcpy(challenges, ch.data(), num_vars * sizeof(Fr));
   return 0;
+}
+// generic expression (prefix token stream, see oracle.py serialize_expression)
+void orc_sumcheck_prove_generic(void* tr, int num_vars, const int* tokens, const Fr* consts, int npolys,
+                                const Fr* const* polys, const Fr* challenges, int nchallenges, const Fr* ys, int nys,
+                                const Fr* sum, Fr* out_challenges, Fr* out_evals, int* out_degree) {
+  const int* t = tokens;
+  ExprP e = parse_expr(t, consts);
+  std::vector<Poly> tabs(npolys);
+  std::vector<const Poly*> ptrs;
+  for (int i = 0; i < npolys; ++i) tabs[i].assign(polys[i], polys[i] + ((size_t)1 << num_vars));
+  for (int i = 0; i < npolys; ++i) ptrs.push_back(&tabs[i]);
+  std::vector<std::vector<Fr>> yv;
+  for (int k = 0; k < nys; ++k) yv.push_back(std::vector<Fr>(ys + k * num_vars, ys + (k + 1) * num_vars));
+  *out_degree = expr_degree(e);
+  SumCheckOutput o = sumcheck_prove_generic(num_vars, e, ptrs, std::vector<Fr>(challenges, challenges + nchallenges), yv,
+                                            *sum, *(Transcript*)tr);
+  memcpy(out_challenges, o.challenges.data(), num_vars * sizeof(Fr));
+  memcpy(out_evals, o.evals.data(), npolys * sizeof(Fr));
+}
+uint64_t orc_bh_rotate(int num_vars, uint64_t b, int rotation) { return BooleanHypercube(num_vars).rotate(b, rotation); }
+void orc_bh_iter(int num_vars, uint64_t* out) {
+  auto v = BooleanHypercube(num_vars).iter();
+  memcpy(out, v.data(), v.size() * 8);
 }
 // cfg2 claim: Σ_b eq(b,y) a(b) b(b)
 void orc_sum_eq_ab(int num_vars, const Fr* y, const Fr* a, const Fr* b, Fr* out) {

@@ -277,6 +277,75 @@ def sumcheck_verify(tr, num_vars, degree, claimed_sum, coeffs=False):
     return fin, ch
 
 
+def serialize_expression(expr):
+    """Expression tree (halo2_lasso_b200.expression.Expression) -> (prefix int tokens, constants as Fr)."""
+    tokens, consts = [], []
+
+    def const_idx(v):
+        consts.append(v % R_MOD)
+        return len(consts) - 1
+
+    def walk(e):
+        k = e[0]
+        if k == "const":
+            tokens.extend([0, const_idx(e[1])])
+        elif k == "identity":
+            tokens.append(1)
+        elif k == "lagrange":
+            tokens.extend([2, e[1]])
+        elif k == "eq":
+            tokens.extend([3, e[1]])
+        elif k == "poly":
+            tokens.extend([4, e[1], e[2]])
+        elif k == "chal":
+            tokens.extend([5, e[1]])
+        elif k == "neg":
+            tokens.append(6)
+            walk(e[1])
+        elif k in ("sum", "prod"):
+            tokens.append(7 if k == "sum" else 8)
+            walk(e[1])
+            walk(e[2])
+        elif k == "scaled":
+            tokens.extend([9, const_idx(e[2])])
+            walk(e[1])
+        elif k == "dpow":
+            tokens.extend([10, len(e[1])])
+            for c in e[1]:
+                walk(c)
+            walk(e[2])
+        else:
+            raise ValueError(k)
+
+    walk(expr.node if hasattr(expr, "node") else expr)
+    return np.asarray(tokens, dtype=np.int32), fr_from_ints(consts if consts else [0])
+
+
+def sumcheck_prove_generic(tr, num_vars, expr, polys, challenges, ys, claimed_sum):
+    tokens, consts = serialize_expression(expr)
+    arrs, ptrs = _ptr_array(polys)
+    ch_in = np.ascontiguousarray(challenges, dtype=np.uint64).reshape(-1, 4)
+    ys = np.ascontiguousarray(np.stack(ys), dtype=np.uint64)
+    ch, ev = _fr(num_vars), _fr(len(polys))
+    deg = C.c_int()
+    s = np.ascontiguousarray(claimed_sum, dtype=np.uint64)
+    lib().orc_sumcheck_prove_generic(tr.h, C.c_int(num_vars), _p(tokens), _p(consts), C.c_int(len(polys)), ptrs,
+                                     _p(ch_in) if ch_in.shape[0] else None, C.c_int(ch_in.shape[0]), _p(ys),
+                                     C.c_int(ys.shape[0]), _p(s), _p(ch), _p(ev), C.byref(deg))
+    return ch, ev, deg.value
+
+
+def bh_rotate(num_vars, b, rotation):
+    lib().orc_bh_rotate.restype = C.c_uint64
+    return int(lib().orc_bh_rotate(C.c_int(num_vars), C.c_uint64(b), C.c_int(rotation)))
+
+
+def bh_iter(num_vars):
+    out = np.zeros(1 << num_vars, dtype=np.uint64)
+    lib().orc_bh_iter(C.c_int(num_vars), _p(out))
+    return out
+
+
 def sum_eq_ab(y, a, b):
     y = np.ascontiguousarray(y, dtype=np.uint64)
     out = _fr()
