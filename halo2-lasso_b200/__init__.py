@@ -502,9 +502,7 @@ def prove_expression(ctx, num_vars, expression, polys, challenges, ys, claimed_s
             _chk(lib().b200_poly_iota(ctx.h, C.c_int(num_vars), t.dev), "poly_iota")
             tables.append(t)
         else:  # lagrange(i): one-hot at the i-th row in BooleanHypercube order (classic.rs:44-55)
-            if bh_order is None:
-                bh_order = BooleanHypercube(num_vars).iter()
-            idx = bh_order[leaf[1] % (1 << num_vars)]
+            idx = BooleanHypercube(num_vars).nth(leaf[1])
             t = MultilinearPolynomial.alloc(ctx, num_vars)
             _chk(lib().b200_poly_onehot(ctx.h, C.c_int(num_vars), C.c_uint64(idx), t.dev), "poly_onehot")
             tables.append(t)

@@ -125,6 +125,16 @@ int b200_sumcheck_prove_generic(b200_ctx* h, int num_vars, int degree, int ntabl
   job.nconsts = nconsts;
   job.nops = nops;
   job.degree = degree;
+  int max_dst = ntables + nconsts;
+  for (int i = 0; i < nops; ++i) {
+    const int32_t* o = host_ops + 4 * i;
+    const int lim = ntables + nconsts;
+    if (o[0] < 0 || o[0] > 3 || o[1] < lim || o[2] < 0 || o[3] < 0 || o[2] > o[1] + 64 || o[3] > o[1] + 64) return B200_ERR_ARG;
+    if (o[1] > max_dst) max_dst = o[1];
+  }
+  job.ntemps = max_dst - (ntables + nconsts) + 1;
+  for (int i = 0; i < nops; ++i)
+    if (host_ops[4 * i + 2] > max_dst || host_ops[4 * i + 3] > max_dst) return B200_ERR_ARG;
   for (int i = 0; i < ntables; ++i) job.tables[i] = (const Fr*)dev_tables[i];
   job.consts = d;
   job.ops = dops;

@@ -33,19 +33,28 @@ struct GenArgs {
   int round;
 };
 
+// slot file in SHARED memory, one column per thread: [K values | K steps | T temporaries] x blockDim.x.
+// Constants are read from global memory (uniform address -> broadcast). The host's liveness-based slot reuse
+// keeps T tiny (5 for the vanilla-plonk zero check), so 128 threads fit in ~160 KB.
 template <bool BIND>
 __global__ void __launch_bounds__(128) sc_generic_round_kernel(GenArgs a) {
+  extern __shared__ __align__(32) unsigned char gen_smem_raw[];
+  Fr* sm = reinterpret_cast<Fr*>(gen_smem_raw);
   __shared__ Fr smem[4];
   __shared__ Fr s_tot[GEN_MAX_DEG];
-  Fr slots[GEN_MAX_SLOTS];
-  Fr step[GEN_MAX_TABLES];
   Fr acc[GEN_MAX_DEG];
-  const int K = a.K, D = a.D;
-  for (int x = 0; x < D; ++x) acc[x] = fe_zero<FrP>();
-  for (int i = 0; i < a.C; ++i) slots[K + i] = fe_ld(a.consts + i);
+  const int K = a.K, D = a.D, KC = a.K + a.C;
+  const int nth = blockDim.x, tid = threadIdx.x;
+#pragma unroll
+  for (int x = 0; x < GEN_MAX_DEG; ++x) acc[x] = fe_zero<FrP>();
   Fr r = fe_zero<FrP>();
   if (BIND) r = fe_ld(&a.st->r);
   const int last = a.ops[a.nops - 1].y;
+  auto rd = [&](int idx) -> Fr {
+    if (idx < K) return sm[idx * nth + tid];
+    if (idx < KC) return fe_ld(a.consts + (idx - K));
+    return sm[(2 * K + idx - KC) * nth + tid];
+  };
 
   for (uint32_t b = blockIdx.x * blockDim.x + threadIdx.x; b < a.pairs; b += gridDim.x * blockDim.x) {
     for (int k = 0; k < K; ++k) {
@@ -62,30 +71,37 @@ __global__ void __launch_bounds__(128) sc_generic_round_kernel(GenArgs a) {
         u0 = fe_ldg(p);
         u1 = fe_ldg(p + 1);
       }
-      slots[k] = u1;
-      step[k] = u1 - u0;
+      sm[k * nth + tid] = u1;
+      sm[(K + k) * nth + tid] = u1 - u0;
     }
+#pragma unroll 1
     for (int x = 0; x < D; ++x) {
       if (x > 0)
-        for (int k = 0; k < K; ++k) slots[k] = slots[k] + step[k];
+        for (int k = 0; k < K; ++k) sm[k * nth + tid] = sm[k * nth + tid] + sm[(K + k) * nth + tid];
       for (int i = 0; i < a.nops; ++i) {
         const int4 op = a.ops[i];
-        const Fr lhs = slots[op.z], rhs = slots[op.w];
+        const Fr lhs = rd(op.z);
         Fr res;
         switch (op.x) {
-          case 0: res = lhs + rhs; break;
-          case 1: res = lhs - rhs; break;
-          case 2: res = lhs * rhs; break;
+          case 0: res = lhs + rd(op.w); break;
+          case 1: res = lhs - rd(op.w); break;
+          case 2: res = lhs * rd(op.w); break;
           default: res = fe_neg<FrP>(lhs); break;
         }
-        slots[op.y] = res;
+        sm[(2 * K + op.y - KC) * nth + tid] = res;
       }
-      acc[x] = acc[x] + slots[last];
+      const Fr v = sm[(2 * K + last - KC) * nth + tid];
+#pragma unroll
+      for (int xx = 0; xx < GEN_MAX_DEG; ++xx)
+        if (xx == x) acc[xx] = acc[xx] + v;
     }
   }
   // per-CTA partials
   for (int x = 0; x < D; ++x) {
-    Fr t[1] = {acc[x]};
+    Fr t[1] = {fe_zero<FrP>()};
+#pragma unroll
+    for (int xx = 0; xx < GEN_MAX_DEG; ++xx)
+      if (xx == x) t[0] = acc[xx];
     block_reduce_fr<1>(t, smem);
     if (threadIdx.x == 0) fe_st(a.partial + (size_t)blockIdx.x * D + x, t[0]);
   }
@@ -151,7 +167,7 @@ __global__ void gen_init_kernel(ScState* st, const Fr* claim) {
 int sumcheck_prove_generic(Ctx* c, const GenericJob& job) {
   const int n = job.num_vars, K = job.ntables;
   if (n < 1 || n > 30 || K < 1 || K > GEN_MAX_TABLES || job.degree < 1 || job.degree > GEN_MAX_DEG || job.nops < 1 ||
-      K + job.nconsts + job.nops > GEN_MAX_SLOTS)
+      job.ntemps < 1 || job.ntemps > 64)
     return B200_ERR_ARG;
   cudaStream_t s = c->stream;
   const size_t N = (size_t)1 << n;
@@ -173,6 +189,14 @@ int sumcheck_prove_generic(Ctx* c, const GenericJob& job) {
   a.tr = c->d_tr;
   a.bary = c->d_bary;
   a.challenges_out = job.challenges_out;
+  // shared-memory slot file: (2K + T) field elements per thread
+  const int nslots = 2 * K + job.ntemps;
+  int nth = 128;
+  while (nth > 32 && (size_t)nslots * nth * sizeof(Fr) > 200 * 1024) nth -= 32;
+  const size_t smem_bytes = (size_t)nslots * nth * sizeof(Fr);
+  if (smem_bytes > 220 * 1024) return B200_ERR_ARG;
+  CUDA_TRY(cudaFuncSetAttribute(sc_generic_round_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+  CUDA_TRY(cudaFuncSetAttribute(sc_generic_round_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
   const Fr* cur[GEN_MAX_TABLES];
   for (int i = 0; i < K; ++i) cur[i] = job.tables[i];
   for (int round = 0; round < n; ++round) {
@@ -184,14 +208,14 @@ int sumcheck_prove_generic(Ctx* c, const GenericJob& job) {
       a.in[i] = cur[i];
       a.out[i] = dst_base + (size_t)i * dst_sz;
     }
-    int blocks = (int)((a.pairs + 127) / 128);
-    if (blocks > NUM_SMS * 4) blocks = NUM_SMS * 4;
+    int blocks = (int)((a.pairs + nth - 1) / nth);
+    if (blocks > NUM_SMS) blocks = NUM_SMS;  // one CTA per SM (the slot file takes most of the shared memory)
     if ((size_t)blocks * job.degree > c->partial_elems) return B200_ERR_NOMEM;
     const int pi = prof_begin(c, round);
     if (round == 0) {
-      sc_generic_round_kernel<false><<<blocks, 128, 0, s>>>(a);
+      sc_generic_round_kernel<false><<<blocks, nth, smem_bytes, s>>>(a);
     } else {
-      sc_generic_round_kernel<true><<<blocks, 128, 0, s>>>(a);
+      sc_generic_round_kernel<true><<<blocks, nth, smem_bytes, s>>>(a);
       for (int i = 0; i < K; ++i) cur[i] = a.out[i];
     }
     prof_end(c, pi);

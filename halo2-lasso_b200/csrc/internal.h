@@ -86,7 +86,7 @@ int sumcheck_prove_coeffs(Ctx* c, const ScCoeffJob& job);
 
 // generic.cu — EvaluationsProver for an arbitrary Expression compiled to bytecode on the host
 struct GenericJob {
-  int num_vars, ntables, nconsts, nops, degree;
+  int num_vars, ntables, nconsts, nops, degree, ntemps;
   const Fr* tables[64];  // every leaf of the expression as a dense 2^num_vars table
   const Fr* consts;      // device, nconsts (Montgomery)
   const int4* ops;       // device, nops x (opcode, dst, a, b)

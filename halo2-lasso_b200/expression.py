@@ -48,6 +48,22 @@ class BooleanHypercube:
             b = self.next(b)
         return out
 
+    def nth(self, i):
+        """i-th row in LFSR order without walking the whole cycle; negative i counts from the end
+        (`i.rem_euclid(1 << num_vars)`, classic.rs:50-53)."""
+        size = 1 << self.num_vars
+        i %= size
+        if i == 0:
+            return 0
+        b = 1
+        if i - 1 <= size - 1 - i:
+            for _ in range(i - 1):
+                b = self.next(b)
+        else:  # position size-j is prev^j(1): the non-zero rows form a cycle of length size-1
+            for _ in range(size - i):
+                b = self.prev(b)
+        return b
+
     def nth_map(self):
         m = [0] * (1 << self.num_vars)
         for nth, b in enumerate(self.iter()):
@@ -256,7 +272,24 @@ def compile_expression(expr, challenges):
         z = const_slot(0)
         C = len(consts)
         prog = [(OP_ADD, K + C, slot(root) if root[0] != "const" else K + root[1], K + z[1])]
-    return leaves, consts, prog
+    # liveness-based reuse of temporary slots (the kernel keeps the slot file in shared memory)
+    last_use = {}
+    for i, (_, d, a, b) in enumerate(prog):
+        last_use[a] = i
+        last_use[b] = i
+    free, mapping, next_tmp, out = [], {}, K + C, []
+    for i, (op, d, a, b) in enumerate(prog):
+        ra, rb = mapping.get(a, a), mapping.get(b, b)
+        for s in {a, b}:
+            if s >= K + C and last_use[s] == i:
+                free.append(mapping[s])
+        if free:
+            rd = free.pop()
+        else:
+            rd, next_tmp = next_tmp, next_tmp + 1
+        mapping[d] = rd
+        out.append((op, rd, ra, rb))
+    return leaves, consts, out
 
 
 # ---- vanilla plonk (pb/backend/hyperplonk/util.rs:30-62 + preprocessor.rs) -----------------------

@@ -43,6 +43,9 @@ def test_boolean_hypercube_matches_oracle():
                 if abs(rot) <= n:
                     assert bh.rotate(b, rot) == O.bh_rotate(n, b, rot)
         assert all(bh.prev(bh.next(b)) == b for b in range(1, 1 << n))
+        order = bh.iter()
+        for i in (0, 1, 2, 5, -1, -2, (1 << n) - 1, 1 << n):
+            assert bh.nth(i) == order[i % (1 << n)]
 
 
 def eval_tree(n, leaf_val, ch):

@@ -33,3 +33,5 @@ for it in range(6):
         times.append(s0.elapsed_time(s1))
 print(json.dumps({"bench": "zero_check (vanilla_plonk_expression, 17 tables, degree 5)", "num_vars": n,
                   "ms": sum(times) / len(times), "samples": len(times)}))
+prof = hl.profile(ctx, lambda: (hl.Keccak256Transcript(ctx), hl.prove_expression(ctx, n, expr, polys, ch, [y], zero)))
+print("round_ms", [round(t, 3) for tag, t in prof if tag < 1000])
