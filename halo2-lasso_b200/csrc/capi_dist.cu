@@ -152,6 +152,17 @@ int b200_sumcheck_prove_generic(b200_ctx* h, int num_vars, int degree, int ntabl
   CUDA_TRY(cudaFreeAsync(dops, c->stream));
   return B200_OK;
 }
+int b200_permutation_z(b200_ctx* h, int num_vars, int npolys, const void* const* dev_wires, const void* const* dev_sigmas,
+                       const uint64_t* id_offsets, const void* host_beta_gamma, void* dev_z_out) {
+  Ctx* c = &h->c;
+  Fr* bg = nullptr;
+  CUDA_TRY(cudaMallocAsync(&bg, 2 * sizeof(Fr), c->stream));
+  CUDA_TRY(cudaMemcpyAsync(bg, host_beta_gamma, 2 * sizeof(Fr), cudaMemcpyHostToDevice, c->stream));
+  int rc = permutation_z(c, num_vars, npolys, (const Fr* const*)dev_wires, (const Fr* const*)dev_sigmas, id_offsets, bg,
+                         (Fr*)dev_z_out);
+  CUDA_TRY(cudaFreeAsync(bg, c->stream));
+  return rc;
+}
 int b200_poly_iota(b200_ctx* h, int num_vars, void* dev_out) { return poly_iota(&h->c, num_vars, (Fr*)dev_out); }
 int b200_poly_onehot(b200_ctx* h, int num_vars, uint64_t index, void* dev_out) {
   return poly_onehot(&h->c, num_vars, index, (Fr*)dev_out);

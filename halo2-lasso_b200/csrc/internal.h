@@ -99,6 +99,10 @@ int poly_iota(Ctx* c, int num_vars, Fr* d_out);
 int poly_onehot(Ctx* c, int num_vars, uint64_t index, Fr* d_out);
 int poly_rotate(Ctx* c, const Fr* d_in, int num_vars, int rotation, Fr* d_out);
 
+// perm.cu — permutation_z_polys (prover.rs:252-345), one chunk
+int permutation_z(Ctx* c, int num_vars, int npolys, const Fr* const* wires, const Fr* const* sigmas,
+                  const uint64_t* id_offsets, const Fr* d_beta_gamma, Fr* d_z);
+
 // mle.cu
 int eq_build(Ctx* c, const Fr* d_y, int n, Fr* d_out);                         // eq_xy
 int fix_var(Ctx* c, const Fr* d_in, int n, const Fr* d_r, Fr* d_out);          // one bind

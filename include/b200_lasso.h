@@ -117,6 +117,13 @@ int b200_poly_iota(b200_ctx* ctx, int num_vars, void* dev_out);
 int b200_poly_onehot(b200_ctx* ctx, int num_vars, uint64_t index, void* dev_out);
 int b200_poly_rotate(b200_ctx* ctx, const void* dev_in, int num_vars, int rotation, void* dev_out);
 
+/* permutation_z_polys (pb/backend/hyperplonk/prover.rs:252-345) for one chunk of `npolys` wire columns:
+ * grand-product polynomial z in BooleanHypercube order; id_offsets[i] = (index of wire i among the permuted
+ * columns) << num_vars; host_beta_gamma = {beta, gamma}. dev_z_out[2^num_vars]. */
+int b200_permutation_z(b200_ctx* ctx, int num_vars, int npolys, const void* const* dev_wires,
+                       const void* const* dev_sigmas, const uint64_t* id_offsets, const void* host_beta_gamma,
+                       void* dev_z_out);
+
 /* ---- variable_base_msm (pb/util/arithmetic/msm.rs:84-115) ------------------------------------- */
 /* Σ scalars[i] * bases[i] with HOST inputs (the free function's signature); out = affine point.
  * An identity result is returned as (0, 0). */

@@ -6,6 +6,7 @@
 #include <cstdio>
 
 #include "expression.hpp"
+#include "hyperplonk.hpp"
 #include "lasso.hpp"
 
 using namespace oracle;
@@ -238,6 +239,61 @@ int orc_kzg_batch_verify(void* h, void* tr, int nv, int ncomms, const G1Affine* 
   unpack_batch(nv, npoints, points, nevals, ev_poly, ev_point, ev_value, &pts, &evs);
   return kzg_batch_verify(*(KzgParams*)h, nv, std::vector<G1Affine>(comms, comms + ncomms), pts, evs,
                           *(Transcript*)tr) ? 0 : 1;
+}
+
+// ---- HyperPlonk (no lookups) ---------------------------------------------------------------------
+// cycles_flat: [len, poly, row, poly, row, ..., len, ...]
+void* orc_hp_preprocess(void* kzg, int num_vars, const int* tokens, const Fr* consts, int num_instances,
+                        int num_witness, int npre, const Fr* const* pre, int nperm, const int* perm_idx,
+                        const int* cycles_flat, int ncycles, int num_z) {
+  const int* t = tokens;
+  ExprP e = parse_expr(t, consts);
+  std::vector<Poly> pre_polys(npre);
+  for (int i = 0; i < npre; ++i) pre_polys[i].assign(pre[i], pre[i] + ((size_t)1 << num_vars));
+  std::vector<std::vector<std::pair<int, int>>> cycles;
+  const int* c = cycles_flat;
+  for (int k = 0; k < ncycles; ++k) {
+    int len = *c++;
+    std::vector<std::pair<int, int>> cyc;
+    for (int i = 0; i < len; ++i) {
+      cyc.push_back({c[0], c[1]});
+      c += 2;
+    }
+    cycles.push_back(cyc);
+  }
+  return new HyperPlonkParams(hyperplonk_preprocess(*(KzgParams*)kzg, num_vars, e, {num_instances}, num_witness, pre_polys,
+                                                    std::vector<int>(perm_idx, perm_idx + nperm), cycles, num_z));
+}
+void orc_hp_free(void* h) { delete (HyperPlonkParams*)h; }
+void orc_hp_permutation_poly(void* h, int i, Fr* out) {
+  auto& p = ((HyperPlonkParams*)h)->permutation_polys[i];
+  memcpy(out, p.data(), p.size() * sizeof(Fr));
+}
+int orc_hp_prove(void* h, void* tr, const Fr* instances, int ninst, const Fr* const* witness, int nwit) {
+  HyperPlonkParams* pp = (HyperPlonkParams*)h;
+  std::vector<Poly> wit(nwit);
+  for (int i = 0; i < nwit; ++i) wit[i].assign(witness[i], witness[i] + ((size_t)1 << pp->num_vars));
+  return hyperplonk_prove(*pp, {std::vector<Fr>(instances, instances + ninst)}, wit, *(Transcript*)tr) ? 0 : 1;
+}
+int orc_hp_verify(void* h, void* tr, const Fr* instances, int ninst) {
+  return hyperplonk_verify(*(HyperPlonkParams*)h, {std::vector<Fr>(instances, instances + ninst)}, *(Transcript*)tr) ? 0 : 1;
+}
+void orc_permutation_z(int num_vars, int nperm, const Fr* const* perm_polys, const Fr* const* wires, const Fr* beta,
+                       const Fr* gamma, Fr* out) {
+  const size_t N = (size_t)1 << num_vars;
+  std::vector<Poly> perms(nperm), w(nperm);
+  std::vector<const Poly*> polys;
+  std::vector<int> idx;
+  for (int i = 0; i < nperm; ++i) {
+    perms[i].assign(perm_polys[i], perm_polys[i] + N);
+    w[i].assign(wires[i], wires[i] + N);
+  }
+  for (int i = 0; i < nperm; ++i) {
+    polys.push_back(&w[i]);
+    idx.push_back(i);
+  }
+  Poly z = permutation_z_polys(1, idx, perms, polys, *beta, *gamma)[0];
+  memcpy(out, z.data(), N * sizeof(Fr));
 }
 
 // ---- Lasso -------------------------------------------------------------------------------------

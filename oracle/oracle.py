@@ -35,6 +35,7 @@ def lib():
         _lib.orc_tr_from_proof.restype = C.c_void_p
         _lib.orc_kzg_setup.restype = C.c_void_p
         _lib.orc_kzg_import.restype = C.c_void_p
+        _lib.orc_hp_preprocess.restype = C.c_void_p
         _lib.orc_tr_proof_len.restype = C.c_uint64
         _lib.orc_rand_u64.restype = C.c_uint64
     return _lib
@@ -434,6 +435,56 @@ class Kzg:
         pts, ep, ept, ev = self._batch_args(points, evals)
         return lib().orc_kzg_batch_verify(self.h, tr.h, C.c_int(nv), C.c_int(comms.shape[0]), _p(comms),
                                           C.c_int(len(points)), _p(pts), C.c_int(len(evals)), _p(ep), _p(ept), _p(ev)) == 0
+
+
+# ---- HyperPlonk (no lookups) ----------------------------------------------------------------
+class HyperPlonk:
+    """Oracle `HyperPlonk<MultilinearKzg>`: preprocess at construction, then prove / verify."""
+
+    def __init__(self, kzg, num_vars, expression, num_instances, num_witness, preprocess_polys, perm_idx, cycles, num_z=1):
+        tokens, consts = serialize_expression(expression)
+        arrs, ptrs = _ptr_array(preprocess_polys)
+        flat = []
+        for cyc in cycles:
+            flat.append(len(cyc))
+            for (p, r) in cyc:
+                flat += [p, r]
+        flat = np.asarray(flat if flat else [0], dtype=np.int32)
+        pidx = np.asarray(perm_idx, dtype=np.int32)
+        self.kzg, self.num_vars, self.nperm = kzg, num_vars, len(perm_idx)
+        self.h = C.c_void_p(lib().orc_hp_preprocess(kzg.h, C.c_int(num_vars), _p(tokens), _p(consts), C.c_int(num_instances),
+                                                    C.c_int(num_witness), C.c_int(len(preprocess_polys)), ptrs,
+                                                    C.c_int(len(perm_idx)), _p(pidx), _p(flat), C.c_int(len(cycles)),
+                                                    C.c_int(num_z)))
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().orc_hp_free(self.h)
+            self.h = None
+
+    def permutation_poly(self, i):
+        out = _fr(1 << self.num_vars)
+        lib().orc_hp_permutation_poly(self.h, C.c_int(i), _p(out))
+        return out
+
+    def prove(self, tr, instances, witness_polys):
+        inst = np.ascontiguousarray(instances, dtype=np.uint64).reshape(-1, 4)
+        arrs, ptrs = _ptr_array(witness_polys)
+        return lib().orc_hp_prove(self.h, tr.h, _p(inst), C.c_int(inst.shape[0]), ptrs, C.c_int(len(witness_polys))) == 0
+
+    def verify(self, tr, instances):
+        inst = np.ascontiguousarray(instances, dtype=np.uint64).reshape(-1, 4)
+        return lib().orc_hp_verify(self.h, tr.h, _p(inst), C.c_int(inst.shape[0])) == 0
+
+
+def permutation_z(perm_polys, wires, beta, gamma):
+    a1, p1 = _ptr_array(perm_polys)
+    a2, p2 = _ptr_array(wires)
+    n = a1[0].shape[0]
+    out = _fr(n)
+    lib().orc_permutation_z(C.c_int(n.bit_length() - 1), C.c_int(len(perm_polys)), p1, p2,
+                            _p(np.ascontiguousarray(beta, dtype=np.uint64)), _p(np.ascontiguousarray(gamma, dtype=np.uint64)), _p(out))
+    return out
 
 
 # ---- Lasso ----------------------------------------------------------------------------------
