@@ -182,12 +182,13 @@ class HyperPlonk:
         tr.common_field_elements(inst_mont)
         # instance_polys (prover.rs:32-48): instance i sits on row bh[i+1]
         order = BooleanHypercube(k)
-        pi = [0] * (1 << k)
+        raw = np.zeros((1 << k, 4), dtype=np.uint64)
         b = 1
-        for v in instances:
-            pi[b] = v
+        for row in ints_to_raw(instances):
+            raw[b] = row
             b = order.next(b)
-        inst_poly = upload_ints(ctx, pi)
+        inst_poly = MultilinearPolynomial.new(ctx, raw)
+        _chk(lib().b200_fr_convert(ctx.h, inst_poly.dev, inst_poly.dev, C.c_uint64(1 << k), C.c_int(1)), "fr_convert")
         wit = witness_polys if witness_polys is not None else [upload_ints(ctx, w) for w in witness_ints]
         kzg.batch_commit_and_write(wit)
         beta, gamma = tr.squeeze_challenges(2)  # lookup_m commitments: none

@@ -66,3 +66,34 @@ def test_hyperplonk_proof_parity_and_verifies(hl, env, k):
         first = next(i for i in range(min(len(proof), len(ref))) if proof[i] != ref[i])
         pytest.fail(f"HyperPlonk proof differs from the oracle at byte {first} (lengths {len(proof)} vs {len(ref)})")
     assert ohp.verify(O.Transcript(proof), inst)
+
+
+def test_cfg1_hyperplonk_plus_lasso_on_one_transcript(hl):
+    """BASELINE cfg1 shape: a HyperPlonk proof (k = 10 vanilla plonk) followed by a Lasso range-check proof for
+    2^10 lookups into 2^16 subtables on the SAME Fiat-Shamir transcript (the Lasso section sits behind the
+    HyperPlonk section); byte-identical to the oracle running the same composition, and both
+    oracle verifiers accept when replayed in order."""
+    from halo2_lasso_b200 import hyperplonk as H
+    from halo2_lasso_b200.expression import compose
+
+    k, mu, chunks = 10, 10, 4
+    ctx = hl.Context(0)
+    ss = O.rand_fr(7, 16)
+    okzg = O.Kzg(ss)
+    kzg = hl.MultilinearKzg(ctx, [okzg.eqs(i) for i in range(17)])
+    info, instances, w = H.rand_vanilla_plonk_circuit(k, 77)
+    nz, expr = compose(k, info.constraints, info.num_poly, info.permutation_polys)
+    ohp = O.HyperPlonk(okzg, k, expr, len(instances), 3, [O.fr_from_ints(p) for p in info.preprocess_polys],
+                       info.permutation_polys, info.permutations, nz)
+    xs = O.rand_u64s(9, 1 << mu)
+    xs[1::2] = xs[0::2]
+    inst = O.fr_from_ints(instances)
+    to = O.Transcript()
+    assert ohp.prove(to, inst, [O.fr_from_ints(c) for c in w])
+    assert O.lasso_prove(okzg, to, O.TABLE_RANGE, chunks, mu, xs, None)
+    hp = H.HyperPlonk(ctx, kzg, info)
+    tr = hl.Keccak256Transcript(ctx)
+    hp.prove(instances, witness_ints=w)
+    hl.LassoProver(ctx, kzg, O.TABLE_RANGE, chunks).prove(xs)
+    assert tr.into_proof() == to.proof()
+    ctx.close()
