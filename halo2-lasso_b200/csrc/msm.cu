@@ -22,7 +22,7 @@ namespace b200 {
 
 static const int TASK_LEN = 64;
 static const int SEQ_TASKS = 8;     // buckets with more task partials than this go to the warp kernel
-static const int GROUP = 8;        // buckets per thread in the window reduction
+static const int GROUP = 16;       // buckets per thread in the window reduction
 static const int MSM_MAX_JOBS = 64;
 static const int MSM_MAX_WINDOWS = 128;
 
@@ -95,10 +95,16 @@ __global__ void __launch_bounds__(256) msm_digits_kernel(MsmPlanDev plan, uint32
                                                          uint32_t* __restrict__ sorted) {
   const MsmJobDev& jb = plan.job[blockIdx.y];
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= jb.n) return;
   if (PASS == 0) {
-    uint32_t s[8];
-    load_scalar(jb, i, s);
+    // Small-integer scalars (Lasso counters, 8-/16-bit subtable values) hit a handful of buckets: aggregate
+    // the population atomics per warp (one atomicAdd per distinct bucket in the warp) instead of 32 colliding ones.
+    const bool aggregate = jb.kind == MSM_U32 || jb.kind == MSM_U64;
+    if (!aggregate && i >= jb.n) return;
+    if ((i & ~31u) >= jb.n) return;  // whole warp past the end (warp-uniform)
+    const bool valid = i < jb.n;
+    uint32_t s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (valid) load_scalar(jb, i, s);
+    const uint32_t lane = threadIdx.x & 31;
     uint32_t carry = 0;
     for (int w = 0; w < jb.W; ++w) {
       uint32_t raw = bits_at(s, w * jb.c, jb.c) + carry;
@@ -110,20 +116,31 @@ __global__ void __launch_bounds__(256) msm_digits_kernel(MsmPlanDev plan, uint32
         d = (int32_t)raw;
         carry = 0;
       }
-      uint32_t code = 0xffffffffu;
-      if (d != 0) {
+      uint32_t code = 0xffffffffu, gb = 0xffffffffu;
+      if (valid && d != 0) {
         const uint32_t mag = d < 0 ? (uint32_t)(-d) : (uint32_t)d;
-        const uint32_t gb = jb.bucket_base + (jb.precomp ? 0u : (uint32_t)w * jb.B) + (mag - 1);
-        const uint32_t rank = atomicAdd(&cnt[gb], 1u);
+        gb = jb.bucket_base + (jb.precomp ? 0u : (uint32_t)w * jb.B) + (mag - 1);
+      }
+      uint32_t rank = 0;
+      if (aggregate) {
+        const uint32_t peers = __match_any_sync(0xffffffffu, gb);
+        const int leader = __ffs(peers) - 1;
+        uint32_t base = 0;
+        if (gb != 0xffffffffu && (int)lane == leader) base = atomicAdd(&cnt[gb], (uint32_t)__popc(peers));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        rank = base + __popc(peers & ((1u << lane) - 1));
+      } else if (gb != 0xffffffffu) {
+        rank = atomicAdd(&cnt[gb], 1u);
+      }
+      if (valid) {
+        if (gb != 0xffffffffu) code = rank | (d < 0 ? 0x80000000u : 0u);
         // 2 words per pair: bucket, rank|sign
         ranks[2 * (jb.pair_base + (uint64_t)w * jb.n + i)] = gb;
-        code = rank | (d < 0 ? 0x80000000u : 0u);
-      } else {
-        ranks[2 * (jb.pair_base + (uint64_t)w * jb.n + i)] = 0xffffffffu;
+        ranks[2 * (jb.pair_base + (uint64_t)w * jb.n + i) + 1] = code;
       }
-      ranks[2 * (jb.pair_base + (uint64_t)w * jb.n + i) + 1] = code;
     }
   } else {
+    if (i >= jb.n) return;
     for (int w = 0; w < jb.W; ++w) {
       const uint64_t p = 2 * (jb.pair_base + (uint64_t)w * jb.n + i);
       const uint32_t gb = ranks[p];
