@@ -56,7 +56,9 @@ __device__ __forceinline__ void load_pair(const Fr* __restrict__ in, Fr* __restr
   }
 }
 
-template <int NP, bool BIND>
+// EQPRE: the eq table of this round was already bound by a separate (tiny) kernel, so the T grid rows do not
+// each redo its two binding products per pair (used for the batched grand-product layers, T >= 4).
+template <int NP, bool BIND, bool EQPRE = false>
 __global__ void __launch_bounds__(SC_THREADS) sc_eval_round_kernel(ScEvalArgs a) {
   constexpr int D = NP + 1;  // degree; evaluations at 1..D are computed, p(0) derived
   __shared__ Fr smem[(SC_THREADS / 32) * D];
@@ -76,7 +78,8 @@ __global__ void __launch_bounds__(SC_THREADS) sc_eval_round_kernel(ScEvalArgs a)
 
   for (uint32_t b = blockIdx.x * blockDim.x + threadIdx.x; b < a.pairs; b += gridDim.x * blockDim.x) {
     Fr e0, e1, p0, p1, q0, q1;
-    load_pair<BIND>(a.eq_in, a.eq_out, b, r, t == 0, e0, e1);
+    if (EQPRE) load_pair<false>(a.eq_out, nullptr, b, r, false, e0, e1);
+    else load_pair<BIND>(a.eq_in, a.eq_out, b, r, t == 0, e0, e1);
     load_pair<BIND>(in0, out0, b, r, true, p0, p1);
     if (NP == 2) load_pair<BIND>(in1, out1, b, r, true, q0, q1);
     // eval = t[2b+1], step = t[2b+1] - t[2b]; x -> x+1 adds the step (eval.rs:228-286)
@@ -273,6 +276,13 @@ int sumcheck_prove_evals(Ctx* c, const ScEvalJob& job) {
     if (round == 0) {
       if (NP == 1) sc_eval_round_kernel<1, false><<<grid, SC_THREADS, 0, s>>>(a);
       else sc_eval_round_kernel<2, false><<<grid, SC_THREADS, 0, s>>>(a);
+    } else if (NP == 2 && T >= 4 && a.pairs >= 2048) {
+      int lg = 0;
+      while (((size_t)1 << lg) < 4 * (size_t)a.pairs) ++lg;
+      rc = fix_var(c, a.eq_in, lg, &c->d_sc->r, a.eq_out);
+      if (rc) return rc;
+      sc_eval_round_kernel<2, true, true><<<grid, SC_THREADS, 0, s>>>(a);
+      for (int i = 0; i <= ntab; ++i) cur[i] = (i < ntab) ? a.out[i] : a.eq_out;
     } else {
       if (NP == 1) sc_eval_round_kernel<1, true><<<grid, SC_THREADS, 0, s>>>(a);
       else sc_eval_round_kernel<2, true><<<grid, SC_THREADS, 0, s>>>(a);
