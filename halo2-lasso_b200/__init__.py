@@ -21,13 +21,14 @@ _DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_DIR, "libb200lasso.so")
 HEADER_PATH = os.path.join(os.path.dirname(_DIR), "include", "b200_lasso.h")
 
-B200_OK, B200_ERR_CUDA, B200_ERR_ARG, B200_ERR_TRANSCRIPT, B200_ERR_NOMEM = range(5)
+B200_OK, B200_ERR_CUDA, B200_ERR_ARG, B200_ERR_TRANSCRIPT, B200_ERR_NOMEM, B200_ERR_LOOKUP = range(6)
 
 
 class B200Error(RuntimeError):
     """Maps the C status codes onto the reference's `Error` variants (pb/lib.rs:12-20)."""
 
-    NAMES = {1: "Cuda", 2: "InvalidPcsParam/InvalidSumcheck (bad argument)", 3: "Transcript", 4: "OutOfMemory"}
+    NAMES = {1: "Cuda", 2: "InvalidPcsParam/InvalidSumcheck (bad argument)", 3: "Transcript", 4: "OutOfMemory",
+             5: "InvalidSnark (Invalid lookup input)"}
 
     def __init__(self, code, where):
         super().__init__(f"{where}: {self.NAMES.get(code, code)}")
@@ -476,15 +477,12 @@ def _mont_consts(ctx, ints):
     return p.evals()[:n]
 
 
-def prove_expression(ctx, num_vars, expression, polys, challenges, ys, claimed_sum):
-    """`ClassicSumCheck::<EvaluationsProver>::prove(num_vars, VirtualPolynomial::new(expression, polys, challenges,
-    ys), sum, transcript)`. challenges: canonical Python ints; ys: list of (num_vars, 4) Montgomery arrays.
-    Returns (challenges, evals) with evals = every input polynomial bound at the challenges."""
-    from .expression import BooleanHypercube, compile_expression
+def _leaf_tables(ctx, num_vars, leaves, polys, ys=()):
+    """Every leaf of a compiled expression as a dense device table (rotated queries gathered through the
+    BooleanHypercube map, eq_xy tables, the identity polynomial, one-hot Lagrange tables)."""
+    from .expression import BooleanHypercube
 
-    leaves, consts, prog = compile_expression(expression, challenges)
-    bh_order = None
-    tables, keep = [], []
+    tables = []
     for leaf in leaves:
         kind = leaf[0]
         if kind == "poly":
@@ -506,6 +504,50 @@ def prove_expression(ctx, num_vars, expression, polys, challenges, ys, claimed_s
             t = MultilinearPolynomial.alloc(ctx, num_vars)
             _chk(lib().b200_poly_onehot(ctx.h, C.c_int(num_vars), C.c_uint64(idx), t.dev), "poly_onehot")
             tables.append(t)
+    return tables
+
+
+def expression_rows(ctx, num_vars, expression, polys, challenges=()):
+    """`Expression::evaluate` on every hypercube row (prover.rs:96-117) -> device polynomial. challenges: canonical
+    Python ints. `lookup_compressed_poly` is this applied to distribute_powers(columns, beta)."""
+    from .expression import compile_expression
+
+    leaves, consts, prog = compile_expression(expression, list(challenges))
+    if not leaves:
+        raise B200Error("expression_rows: the expression has no polynomial leaf")
+    tables = _leaf_tables(ctx, num_vars, leaves, polys)
+    cm = _mont_consts(ctx, consts)
+    ops = np.asarray(prog, dtype=np.int32).reshape(-1, 4)
+    ptrs = (C.c_void_p * len(tables))(*[t.dev for t in tables])
+    out = MultilinearPolynomial.alloc(ctx, num_vars)
+    _chk(lib().b200_expression_rows(ctx.h, C.c_int(num_vars), C.c_int(len(tables)), ptrs, C.c_int(len(consts)), _p(cm),
+                                    C.c_int(ops.shape[0]), _p(ops), out.dev), "expression_rows")
+    return out
+
+
+def lookup_m_poly(ctx, num_vars, compressed_input, compressed_table):
+    """`lookup_m_poly` (prover.rs:143-192); raises B200Error (code B200_ERR_LOOKUP) for an input missing from the table."""
+    m = MultilinearPolynomial.alloc(ctx, num_vars)
+    _chk(lib().b200_lookup_m(ctx.h, C.c_int(num_vars), compressed_input.dev, compressed_table.dev, m.dev), "lookup_m")
+    return m
+
+
+def lookup_h_poly(ctx, num_vars, compressed_input, compressed_table, m, gamma):
+    """`lookup_h_poly` (prover.rs:206-250); gamma: Montgomery (4,) uint64"""
+    h = MultilinearPolynomial.alloc(ctx, num_vars)
+    _chk(lib().b200_lookup_h(ctx.h, C.c_int(num_vars), compressed_input.dev, compressed_table.dev, m.dev,
+                             _p(_fr(gamma)), h.dev), "lookup_h")
+    return h
+
+
+def prove_expression(ctx, num_vars, expression, polys, challenges, ys, claimed_sum):
+    """`ClassicSumCheck::<EvaluationsProver>::prove(num_vars, VirtualPolynomial::new(expression, polys, challenges,
+    ys), sum, transcript)`. challenges: canonical Python ints; ys: list of (num_vars, 4) Montgomery arrays.
+    Returns (challenges, evals) with evals = every input polynomial bound at the challenges."""
+    from .expression import compile_expression
+
+    leaves, consts, prog = compile_expression(expression, challenges)
+    tables = _leaf_tables(ctx, num_vars, leaves, polys, ys)
     # polynomials that the expression never queries at rotation 0 are still bound and returned (classic.rs:143-149)
     extra = [p for p in range(len(polys)) if ("poly", p, 0) not in leaves]
     K = len(tables)

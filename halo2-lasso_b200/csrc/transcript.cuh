@@ -193,9 +193,10 @@ static __device__ __noinline__ void keccak_f1600_warp(uint64_t* s) {
   const unsigned RHO[25] = {0, 1, 62, 28, 27, 36, 44, 6, 55, 20, 3, 10, 43, 25, 39, 41, 45, 15, 21, 8, 18, 2, 61, 56, 14};
   const unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31;
-  const int l = lane < 25 ? lane : 0;  // lanes 25..31 shadow lane 0 and never store
+  const int l = lane < 25 ? lane : 0;  // lanes 25..31 idle along (never read by the others, never store)
   const int x = l % 5, y = l / 5;
-  uint64_t a = s[l];
+  __syncwarp();
+  uint64_t a = lane < 25 ? s[lane] : 0;
   const unsigned rho = RHO[l];
   // pi: dest (X, Y) <- src ((X + 3Y) mod 5, X)
   const int pi_src = ((x + 3 * y) % 5) + 5 * x;
@@ -216,6 +217,7 @@ static __device__ __noinline__ void keccak_f1600_warp(uint64_t* s) {
     if (l == 0) a ^= RC[round];
   }
   if (lane < 25) s[lane] = a;
+  __syncwarp();
 }
 
 // `t` must be in shared memory (or global) visible to the whole warp

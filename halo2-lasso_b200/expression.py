@@ -315,12 +315,28 @@ def permutation_constraints(num_vars, num_poly, permutation_polys, max_degree, b
     return nchunks, cons
 
 
-def compose(num_vars, constraints, num_poly, permutation_polys, num_challenges=0, max_degree=4):
-    """preprocessor.rs:25-60 without lookups: (num_permutation_z_polys, zero-check expression)."""
+def lookup_constraints(lookups, num_poly, num_permutation_polys, beta, gamma):
+    """preprocessor.rs:78-109 (LogUp): per lookup  h (input+γ)(table+γ) - (table+γ) + m (input+γ)  on every row,
+    plus the plain sum check Σ_b h(b) = 0. Polynomial order: ... | permutation | m polys | h polys | z polys."""
+    m_off = num_poly + num_permutation_polys
+    h_off = m_off + len(lookups)
+    cons = []
+    for i, lookup in enumerate(lookups):
+        m, h = Expression.polynomial(m_off + i), Expression.polynomial(h_off + i)
+        inp = Expression.distribute_powers([a for a, _ in lookup], beta)
+        tab = Expression.distribute_powers([b for _, b in lookup], beta)
+        cons.append(h * (inp + gamma) * (tab + gamma) - (tab + gamma) + m * (inp + gamma))
+    return cons, [Expression.polynomial(h_off + i) for i in range(len(lookups))]
+
+
+def compose(num_vars, constraints, num_poly, permutation_polys, num_challenges=0, max_degree=4, lookups=()):
+    """preprocessor.rs:25-60: (num_permutation_z_polys, zero-check expression)."""
     beta, gamma, alpha = (Expression.challenge(num_challenges + i) for i in range(3))
-    md = max([c.degree() for c in constraints] + [max_degree, 2])
-    nz, perm = permutation_constraints(num_vars, num_poly, permutation_polys, md, beta, gamma)
-    return nz, Expression.distribute_powers(list(constraints) + perm, alpha) * Expression.eq_xy(0)
+    lookup_cons, lookup_sums = lookup_constraints(lookups, num_poly, len(permutation_polys), beta, gamma)
+    md = max([c.degree() for c in constraints] + [c.degree() for c in lookup_cons] + [max_degree, 2])
+    nz, perm = permutation_constraints(num_vars, num_poly, permutation_polys, md, beta, gamma, 2 * len(lookups))
+    on_every_row = Expression.distribute_powers(list(constraints) + lookup_cons + perm, alpha) * Expression.eq_xy(0)
+    return nz, Expression.distribute_powers(lookup_sums + [on_every_row], alpha)
 
 
 def vanilla_plonk_expression(num_vars):

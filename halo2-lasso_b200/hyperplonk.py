@@ -18,7 +18,8 @@ import random
 
 import numpy as np
 
-from . import (Keccak256Transcript, MultilinearPolynomial, _chk, _fr, _p, evaluate_many, lib, prove_expression)
+from . import (Keccak256Transcript, MultilinearPolynomial, _chk, _fr, _p, evaluate_many, expression_rows, lib,
+               lookup_h_poly, lookup_m_poly, prove_expression)
 from .expression import BooleanHypercube, Expression, R_MOD, compose
 
 R_INV = pow(1 << 256, -1, R_MOD)
@@ -65,6 +66,69 @@ class VanillaPlonkCircuitInfo:
         pi, q_l, q_r, q_m, q_o, q_c, w_l, w_r, w_o = (Expression.polynomial(i) for i in range(9))
         self.constraints = [q_l * w_l + q_r * w_r + q_m * w_l * w_r + q_o * w_o + q_c + pi]
         self.num_poly = 9
+        self.lookups = []
+
+
+class VanillaPlonkWithLookupCircuitInfo:
+    """util.rs:63-86 — polys: 0 pi | 1-9 q_l q_r q_m q_o q_c q_lookup t_l t_r t_o | 10-12 w_l w_r w_o; one lookup of
+    width 3: (q_lookup*w_l, t_l), (q_lookup*w_r, t_r), (q_lookup*w_o, t_o)."""
+
+    def __init__(self, k, num_instances, preprocess_polys, permutations):
+        self.k, self.num_instances = k, num_instances
+        self.preprocess_polys = preprocess_polys  # 9 lists of ints
+        self.permutations = permutations
+        self.permutation_polys = [10, 11, 12]
+        self.num_witness_polys = 3
+        pi, q_l, q_r, q_m, q_o, q_c, q_lookup, t_l, t_r, t_o, w_l, w_r, w_o = (Expression.polynomial(i) for i in range(13))
+        self.constraints = [q_l * w_l + q_r * w_r + q_m * w_l * w_r + q_o * w_o + q_c + pi]
+        self.lookups = [[(q_lookup * w_l, t_l), (q_lookup * w_r, t_r), (q_lookup * w_o, t_o)]]
+        self.num_poly = 13
+
+
+def rand_vanilla_plonk_with_lookup_circuit(k, seed, num_instances=None, lookup_fraction=0.4):
+    """A random SATISFIABLE vanilla-plonk circuit with copy constraints AND lookup rows (same shape as
+    util.rs:216-316: table rows 0 and 1 hold the zero tuple so that gated-off rows look up (0,0,0)).
+    Returns (circuit_info, instances, witness polys [w_l, w_r, w_o]) as canonical ints."""
+    rng = random.Random(seed)
+    N = 1 << k
+    bh = BooleanHypercube(k)
+    num_instances = min(k, N - 2) if num_instances is None else num_instances
+    q = [[0] * N for _ in range(9)]  # q_l q_r q_m q_o q_c q_lookup t_l t_r t_o
+    w = [[0] * N for _ in range(3)]
+    for t in (6, 7, 8):
+        for b in range(2, N):
+            q[t][b] = rng.randrange(R_MOD)
+    instances = [rng.randrange(R_MOD) for _ in range(num_instances)]
+    used = {0}
+    for i, v in enumerate(instances):  # instance rows: -w_l + pi = 0
+        b = bh.nth(i + 1)
+        q[0][b], w[0][b] = R_MOD - 1, v
+        used.add(b)
+    cycles, outputs = [], []
+    for b in range(1, N):
+        if b in used:
+            continue
+        if rng.random() < lookup_fraction or not any(q[5]):  # lookup row: the wire tuple is a table row (repeats give m > 1)
+            idx = rng.randrange(1, N) if rng.random() < 0.7 or b < 3 else rng.randrange(1, min(N, 4))
+            q[5][b] = 1
+            w[0][b], w[1][b], w[2][b] = q[6][idx], q[7][idx], q[8][idx]
+            continue
+        if outputs and rng.random() < 0.5:  # copy an earlier output into w_l
+            src = outputs.pop(rng.randrange(len(outputs)))
+            w[0][b] = w[2][src]
+            cycles.append([(12, src), (10, b)])
+        else:
+            w[0][b] = rng.randrange(R_MOD)
+        w[1][b] = rng.randrange(R_MOD)
+        if rng.randrange(2) == 0:
+            q[0][b] = q[1][b] = 1
+            w[2][b] = (w[0][b] + w[1][b]) % R_MOD
+        else:
+            q[2][b] = 1
+            w[2][b] = w[0][b] * w[1][b] % R_MOD
+        q[3][b] = R_MOD - 1
+        outputs.append(b)
+    return VanillaPlonkWithLookupCircuitInfo(k, num_instances, q, cycles), instances, w
 
 
 def rand_vanilla_plonk_circuit(k, seed, num_instances=None):
@@ -158,7 +222,7 @@ def rotation_eval_points(x, rotation):
 
 
 class HyperPlonk:
-    """`HyperPlonk<MultilinearKzg<Bn256>>` prover for lookup-free circuits."""
+    """`HyperPlonk<MultilinearKzg<Bn256>>` prover (vanilla plonk, with or without the LogUp lookup argument)."""
 
     def __init__(self, ctx, kzg, info):
         """preprocess (hyperplonk.rs:97-162): commit the preprocess and permutation polynomials, compose the
@@ -170,7 +234,8 @@ class HyperPlonk:
         self.perm_ints = permutation_polys(k, info.permutation_polys, info.permutations)
         self.perm = [upload_ints(ctx, p) for p in self.perm_ints]
         self.permutation_comms = kzg.batch_commit(self.perm)
-        self.num_z, self.expression = compose(k, info.constraints, info.num_poly, info.permutation_polys)
+        self.num_z, self.expression = compose(k, info.constraints, info.num_poly, info.permutation_polys,
+                                              lookups=info.lookups)
         assert self.num_z == 1
 
     def prove(self, instances, witness_ints=None, witness_polys=None):
@@ -191,7 +256,20 @@ class HyperPlonk:
         _chk(lib().b200_fr_convert(ctx.h, inst_poly.dev, inst_poly.dev, C.c_uint64(1 << k), C.c_int(1)), "fr_convert")
         wit = witness_polys if witness_polys is not None else [upload_ints(ctx, w) for w in witness_ints]
         kzg.batch_commit_and_write(wit)
-        beta, gamma = tr.squeeze_challenges(2)  # lookup_m commitments: none
+        polys = [inst_poly] + self.preprocess + wit
+        # LogUp (prover.rs:50-250): compressed input/table polys, multiplicities m, then h once gamma is known
+        beta = tr.squeeze_challenge()
+        compressed, ms = [], []
+        for lookup in info.lookups:
+            b_ = Expression.challenge(0)
+            ci = expression_rows(ctx, k, Expression.distribute_powers([a for a, _ in lookup], b_), polys, [mont_to_int(beta)])
+            ct = expression_rows(ctx, k, Expression.distribute_powers([t for _, t in lookup], b_), polys, [mont_to_int(beta)])
+            compressed.append((ci, ct))
+            ms.append(lookup_m_poly(ctx, k, ci, ct))
+        if ms:
+            kzg.batch_commit_and_write(ms)
+        gamma = tr.squeeze_challenge()
+        hs = [lookup_h_poly(ctx, k, ci, ct, m, gamma) for (ci, ct), m in zip(compressed, ms)]
         # permutation_z_polys (prover.rs:252-345)
         z = MultilinearPolynomial.alloc(ctx, k)
         nper = len(info.permutation_polys)
@@ -200,10 +278,10 @@ class HyperPlonk:
         offs = (C.c_uint64 * nper)(*[i << k for i in range(nper)])
         bg = np.ascontiguousarray(np.stack([beta, gamma]))
         _chk(lib().b200_permutation_z(ctx.h, C.c_int(k), C.c_int(nper), wires, sig, offs, _p(bg), z.dev), "permutation_z")
-        kzg.batch_commit_and_write([z])
+        kzg.batch_commit_and_write(hs + [z])
         alpha = tr.squeeze_challenge()
         y = tr.squeeze_challenges(k)
-        polys = [inst_poly] + self.preprocess + wit + self.perm + [z]
+        polys = polys + self.perm + ms + hs + [z]
         challenges = [mont_to_int(c) for c in (beta, gamma, alpha)]
         zero = np.zeros(4, dtype=np.uint64)
         x, evals = prove_expression(ctx, k, self.expression, polys, challenges, [y], zero)

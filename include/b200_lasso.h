@@ -32,6 +32,7 @@ extern "C" {
 #define B200_ERR_ARG 2        /* invalid argument -> Error::InvalidPcsParam / InvalidSumcheck */
 #define B200_ERR_TRANSCRIPT 3 /* identity commitment or proof overflow -> Error::Transcript */
 #define B200_ERR_NOMEM 4
+#define B200_ERR_LOOKUP 5     /* a lookup input is not in its table -> Error::InvalidSnark("Invalid lookup input") */
 
 typedef struct b200_ctx b200_ctx;
 
@@ -123,6 +124,19 @@ int b200_poly_rotate(b200_ctx* ctx, const void* dev_in, int num_vars, int rotati
 int b200_permutation_z(b200_ctx* ctx, int num_vars, int npolys, const void* const* dev_wires,
                        const void* const* dev_sigmas, const uint64_t* id_offsets, const void* host_beta_gamma,
                        void* dev_z_out);
+
+/* LogUp helper polynomials of HyperPlonk's own lookup argument (pb/backend/hyperplonk/prover.rs:50-250).
+ * b200_expression_rows: Expression::evaluate on every hypercube row (prover.rs:96-117) with the bytecode and the
+ * dense leaf tables of b200_sumcheck_prove_generic; the host passes Σ_j beta^j expr_j to obtain a compressed
+ * input / table polynomial (lookup_compressed_poly, :78-134). dev_out[2^num_vars].
+ * b200_lookup_m: multiplicities (lookup_m_poly, :143-192); a value present on several table rows is counted on the
+ * last one; B200_ERR_LOOKUP if some input value is missing from the table.
+ * b200_lookup_h: h = 1/(gamma + input) - m/(gamma + table) (lookup_h_poly, :206-250). */
+int b200_expression_rows(b200_ctx* ctx, int num_vars, int ntables, const void* const* dev_tables, int nconsts,
+                         const void* host_consts_fr, int nops, const int32_t* host_ops, void* dev_out);
+int b200_lookup_m(b200_ctx* ctx, int num_vars, const void* dev_input, const void* dev_table, void* dev_m_out);
+int b200_lookup_h(b200_ctx* ctx, int num_vars, const void* dev_input, const void* dev_table, const void* dev_m,
+                  const void* host_gamma, void* dev_h_out);
 
 /* ---- variable_base_msm (pb/util/arithmetic/msm.rs:84-115) ------------------------------------- */
 /* Σ scalars[i] * bases[i] with HOST inputs (the free function's signature); out = affine point.

@@ -241,13 +241,27 @@ int orc_kzg_batch_verify(void* h, void* tr, int nv, int ncomms, const G1Affine* 
                           *(Transcript*)tr) ? 0 : 1;
 }
 
-// ---- HyperPlonk (no lookups) ---------------------------------------------------------------------
+// ---- HyperPlonk --------------------------------------------------------------------------------------
 // cycles_flat: [len, poly, row, poly, row, ..., len, ...]
+// lookup_tokens: per lookup [width, input_0, table_0, input_1, table_1, ...] with every expression in prefix form
 void* orc_hp_preprocess(void* kzg, int num_vars, const int* tokens, const Fr* consts, int num_instances,
                         int num_witness, int npre, const Fr* const* pre, int nperm, const int* perm_idx,
-                        const int* cycles_flat, int ncycles, int num_z) {
+                        const int* cycles_flat, int ncycles, int num_z, int nlookups, const int* lookup_tokens,
+                        const Fr* lookup_consts) {
   const int* t = tokens;
   ExprP e = parse_expr(t, consts);
+  std::vector<std::vector<std::pair<ExprP, ExprP>>> lookups;
+  const int* lt = lookup_tokens;
+  for (int l = 0; l < nlookups; ++l) {
+    const int width = *lt++;
+    std::vector<std::pair<ExprP, ExprP>> cols;
+    for (int j = 0; j < width; ++j) {
+      ExprP in = parse_expr(lt, lookup_consts);
+      ExprP tb = parse_expr(lt, lookup_consts);
+      cols.push_back({in, tb});
+    }
+    lookups.push_back(cols);
+  }
   std::vector<Poly> pre_polys(npre);
   for (int i = 0; i < npre; ++i) pre_polys[i].assign(pre[i], pre[i] + ((size_t)1 << num_vars));
   std::vector<std::vector<std::pair<int, int>>> cycles;
@@ -262,7 +276,36 @@ void* orc_hp_preprocess(void* kzg, int num_vars, const int* tokens, const Fr* co
     cycles.push_back(cyc);
   }
   return new HyperPlonkParams(hyperplonk_preprocess(*(KzgParams*)kzg, num_vars, e, {num_instances}, num_witness, pre_polys,
-                                                    std::vector<int>(perm_idx, perm_idx + nperm), cycles, num_z));
+                                                    std::vector<int>(perm_idx, perm_idx + nperm), cycles, num_z, lookups));
+}
+// LogUp helper polynomials on their own (kernel-level parity)
+void orc_expression_rows(int num_vars, const int* tokens, const Fr* consts, int npolys, const Fr* const* polys,
+                         const Fr* challenges, int nchal, Fr* out) {
+  const int* t = tokens;
+  ExprP e = parse_expr(t, consts);
+  const size_t N = (size_t)1 << num_vars;
+  std::vector<Poly> ps(npolys);
+  std::vector<const Poly*> pp;
+  for (int i = 0; i < npolys; ++i) ps[i].assign(polys[i], polys[i] + N);
+  for (auto& p : ps) pp.push_back(&p);
+  std::vector<Fr> ch(challenges, challenges + nchal);
+  BooleanHypercube bh(num_vars);
+  const std::vector<uint64_t> order = bh.iter();
+  for (size_t b = 0; b < N; ++b) out[b] = expr_eval_row(e, b, bh, order, pp, ch);
+}
+int orc_lookup_m(int num_vars, const Fr* input, const Fr* table, Fr* m_out) {
+  const size_t N = (size_t)1 << num_vars;
+  std::array<Poly, 2> c = {Poly(input, input + N), Poly(table, table + N)};
+  Poly m;
+  if (!lookup_m_poly(c, &m)) return 1;
+  memcpy(m_out, m.data(), N * sizeof(Fr));
+  return 0;
+}
+void orc_lookup_h(int num_vars, const Fr* input, const Fr* table, const Fr* m, const Fr* gamma, Fr* h_out) {
+  const size_t N = (size_t)1 << num_vars;
+  std::array<Poly, 2> c = {Poly(input, input + N), Poly(table, table + N)};
+  Poly h = lookup_h_poly(c, Poly(m, m + N), *gamma);
+  memcpy(h_out, h.data(), N * sizeof(Fr));
 }
 void orc_hp_free(void* h) { delete (HyperPlonkParams*)h; }
 void orc_hp_permutation_poly(void* h, int i, Fr* out) {

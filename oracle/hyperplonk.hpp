@@ -14,6 +14,8 @@
 // expression.py::compose, which is KAT-tested against preprocessor.rs:216-256) and arrives as a token stream.
 #pragma once
 #include <algorithm>
+#include <array>
+#include <map>
 #include <set>
 
 #include "expression.hpp"
@@ -130,7 +132,94 @@ struct HyperPlonkParams {
   std::vector<Poly> permutation_polys;
   std::vector<G1Affine> permutation_comms;
   int num_permutation_z_polys;
+  std::vector<std::vector<std::pair<ExprP, ExprP>>> lookups;  // LogUp: per lookup the (input, table) column pairs
 };
+
+// ---- LogUp helper polynomials (pb/backend/hyperplonk/prover.rs:50-250) ----------------------------------
+// Expression::evaluate on one hypercube row (prover.rs:96-117): queries read poly[bh.rotate(b, rotation)],
+// Lagrange(i) is 1 on row bh[i mod 2^n], the identity polynomial is F::from(b).
+inline Fr expr_eval_row(const ExprP& e, uint64_t b, const BooleanHypercube& bh, const std::vector<uint64_t>& order,
+                        const std::vector<const Poly*>& polys, const std::vector<Fr>& challenges) {
+  switch (e->kind) {
+    case Expr::CONST: return e->scalar;
+    case Expr::IDENTITY: return Fr::from_u64(b);
+    case Expr::LAGRANGE: {
+      const long N = (long)order.size();
+      return order[((e->a % N) + N) % N] == b ? Fr::one() : Fr::zero();
+    }
+    case Expr::EQXY: return Fr::zero();  // unreachable!() in the reference
+    case Expr::POLY: return (*polys[e->a])[bh.rotate(b, e->b)];
+    case Expr::CHALLENGE: return challenges[e->a];
+    case Expr::NEG: return -expr_eval_row(e->ch[0], b, bh, order, polys, challenges);
+    case Expr::SUM:
+      return expr_eval_row(e->ch[0], b, bh, order, polys, challenges) + expr_eval_row(e->ch[1], b, bh, order, polys, challenges);
+    case Expr::PROD:
+      return expr_eval_row(e->ch[0], b, bh, order, polys, challenges) * expr_eval_row(e->ch[1], b, bh, order, polys, challenges);
+    case Expr::SCALED: return expr_eval_row(e->ch[0], b, bh, order, polys, challenges) * e->scalar;
+    case Expr::DPOW: {
+      const size_t n = e->ch.size() - 1;
+      const Fr base = expr_eval_row(e->ch[n], b, bh, order, polys, challenges);
+      Fr acc = expr_eval_row(e->ch[0], b, bh, order, polys, challenges), pw = base;
+      for (size_t i = 1; i < n; ++i) {
+        acc = acc + pw * expr_eval_row(e->ch[i], b, bh, order, polys, challenges);
+        pw = pw * base;
+      }
+      return acc;
+    }
+  }
+  return Fr::zero();
+}
+
+// lookup_compressed_poly (prover.rs:78-134): [Σ_j beta^j input_j, Σ_j beta^j table_j]
+inline std::array<Poly, 2> lookup_compressed_poly(const std::vector<std::pair<ExprP, ExprP>>& lookup, int num_vars,
+                                                  const std::vector<const Poly*>& polys,
+                                                  const std::vector<Fr>& challenges, const Fr& beta) {
+  const size_t N = (size_t)1 << num_vars;
+  BooleanHypercube bh(num_vars);
+  const std::vector<uint64_t> order = bh.iter();
+  std::array<Poly, 2> out = {Poly(N, Fr::zero()), Poly(N, Fr::zero())};
+  Fr pw = Fr::one();
+  for (auto& col : lookup) {
+    for (size_t b = 0; b < N; ++b) {
+      out[0][b] = out[0][b] + pw * expr_eval_row(col.first, b, bh, order, polys, challenges);
+      out[1][b] = out[1][b] + pw * expr_eval_row(col.second, b, bh, order, polys, challenges);
+    }
+    pw = pw * beta;
+  }
+  return out;
+}
+
+// lookup_m_poly (prover.rs:143-192): multiplicities; a value that occurs on several table rows is counted on
+// the LAST of them (HashMap::from_iter keeps the latest entry). false = "Invalid lookup input".
+inline bool lookup_m_poly(const std::array<Poly, 2>& compressed, Poly* m) {
+  const Poly &input = compressed[0], &table = compressed[1];
+  std::map<std::array<uint64_t, 4>, size_t> index;
+  auto key = [](const Fr& f) { return std::array<uint64_t, 4>{f.l[0], f.l[1], f.l[2], f.l[3]}; };
+  for (size_t i = 0; i < table.size(); ++i) index[key(table[i])] = i;
+  std::vector<uint64_t> counts(input.size(), 0);
+  for (auto& v : input) {
+    auto it = index.find(key(v));
+    if (it == index.end()) return false;
+    counts[it->second] += 1;
+  }
+  m->resize(input.size());
+  for (size_t i = 0; i < counts.size(); ++i) (*m)[i] = Fr::from_u64(counts[i]);
+  return true;
+}
+
+// lookup_h_poly (prover.rs:206-250): h = 1/(gamma + input) - m/(gamma + table)
+inline Poly lookup_h_poly(const std::array<Poly, 2>& compressed, const Poly& m, const Fr& gamma) {
+  const size_t N = m.size();
+  Poly hi(N), ht(N);
+  for (size_t b = 0; b < N; ++b) {
+    hi[b] = gamma + compressed[0][b];
+    ht[b] = gamma + compressed[1][b];
+  }
+  batch_invert(hi.data(), N);
+  batch_invert(ht.data(), N);
+  for (size_t b = 0; b < N; ++b) hi[b] = hi[b] - ht[b] * m[b];
+  return hi;
+}
 
 // hyperplonk.rs:365-369 + prover.rs:32-48
 inline std::vector<Poly> instance_polys(int num_vars, const std::vector<std::vector<Fr>>& instances) {
@@ -210,8 +299,10 @@ inline HyperPlonkParams hyperplonk_preprocess(const KzgParams& kzg, int num_vars
                                               const std::vector<Poly>& preprocess_polys,
                                               const std::vector<int>& perm_idx,
                                               const std::vector<std::vector<std::pair<int, int>>>& cycles,
-                                              int num_permutation_z_polys) {
+                                              int num_permutation_z_polys,
+                                              const std::vector<std::vector<std::pair<ExprP, ExprP>>>& lookups = {}) {
   HyperPlonkParams pp;
+  pp.lookups = lookups;
   pp.kzg = &kzg;
   pp.num_vars = num_vars;
   pp.num_instances = num_instances;
@@ -250,7 +341,7 @@ inline PcsQueryPlan pcs_query_plan(const ExprP& e, int num_instance_poly) {
   return pl;
 }
 
-// hyperplonk.rs:164-291 (lookups empty)
+// hyperplonk.rs:164-291
 inline bool hyperplonk_prove(const HyperPlonkParams& pp, const std::vector<std::vector<Fr>>& instances,
                              const std::vector<Poly>& witness_polys, Transcript& tr) {
   const int n = pp.num_vars;
@@ -264,14 +355,27 @@ inline bool hyperplonk_prove(const HyperPlonkParams& pp, const std::vector<std::
   for (auto& p : pp.preprocess_polys) polys.push_back(&p);
   for (auto& p : witness_polys) polys.push_back(&p);
   const Fr beta = tr.squeeze_challenge();
+  std::vector<std::array<Poly, 2>> compressed;
+  std::vector<Poly> ms(pp.lookups.size()), hs;
+  for (size_t l = 0; l < pp.lookups.size(); ++l) {
+    compressed.push_back(lookup_compressed_poly(pp.lookups[l], n, polys, {}, beta));
+    if (!lookup_m_poly(compressed[l], &ms[l])) return false;  // Error::InvalidSnark("Invalid lookup input")
+  }
+  for (auto& m : ms)
+    if (!tr.write_commitment(kzg_commit(*pp.kzg, m))) return false;
   const Fr gamma = tr.squeeze_challenge();
+  for (size_t l = 0; l < pp.lookups.size(); ++l) hs.push_back(lookup_h_poly(compressed[l], ms[l], gamma));
   std::vector<Poly> zs = permutation_z_polys(pp.num_permutation_z_polys, pp.permutation_poly_idx, pp.permutation_polys,
                                              polys, beta, gamma);
+  for (auto& h : hs)
+    if (!tr.write_commitment(kzg_commit(*pp.kzg, h))) return false;
   for (auto& z : zs)
     if (!tr.write_commitment(kzg_commit(*pp.kzg, z))) return false;
   const Fr alpha = tr.squeeze_challenge();
   std::vector<Fr> y = tr.squeeze_challenges(n);
   for (auto& p : pp.permutation_polys) polys.push_back(&p);
+  for (auto& m : ms) polys.push_back(&m);
+  for (auto& h : hs) polys.push_back(&h);
   for (auto& z : zs) polys.push_back(&z);
   std::vector<Fr> challenges = {beta, gamma, alpha};
   // prove_zero_check (prover.rs:348-409)
@@ -302,8 +406,11 @@ inline bool hyperplonk_verify(const HyperPlonkParams& vp, const std::vector<std:
   for (auto& c : witness_comms)
     if (!tr.read_commitment(&c)) return false;
   const Fr beta = tr.squeeze_challenge();
+  std::vector<G1Affine> m_comms(vp.lookups.size());
+  for (auto& c : m_comms)
+    if (!tr.read_commitment(&c)) return false;
   const Fr gamma = tr.squeeze_challenge();
-  std::vector<G1Affine> z_comms(vp.num_permutation_z_polys);
+  std::vector<G1Affine> z_comms(vp.lookups.size() + vp.num_permutation_z_polys);  // h polys, then z polys
   for (auto& c : z_comms)
     if (!tr.read_commitment(&c)) return false;
   const Fr alpha = tr.squeeze_challenge();
@@ -356,6 +463,7 @@ inline bool hyperplonk_verify(const HyperPlonkParams& vp, const std::vector<std:
   comms.insert(comms.end(), vp.preprocess_comms.begin(), vp.preprocess_comms.end());
   comms.insert(comms.end(), witness_comms.begin(), witness_comms.end());
   comms.insert(comms.end(), vp.permutation_comms.begin(), vp.permutation_comms.end());
+  comms.insert(comms.end(), m_comms.begin(), m_comms.end());
   comms.insert(comms.end(), z_comms.begin(), z_comms.end());
   if (!kzg_batch_verify(*vp.kzg, n, comms, points, evals, tr)) return false;
   return tr.rpos == tr.stream.size();

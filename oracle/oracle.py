@@ -278,9 +278,11 @@ def sumcheck_verify(tr, num_vars, degree, claimed_sum, coeffs=False):
     return fin, ch
 
 
-def serialize_expression(expr):
-    """Expression tree (halo2_lasso_b200.expression.Expression) -> (prefix int tokens, constants as Fr)."""
-    tokens, consts = [], []
+def serialize_expression(expr, tokens=None, consts=None, finish=True):
+    """Expression tree (halo2_lasso_b200.expression.Expression) -> (prefix int tokens, constants as Fr).
+    With finish=False the tokens/constants are appended to the given lists (several expressions, one stream)."""
+    tokens = [] if tokens is None else tokens
+    consts = [] if consts is None else consts
 
     def const_idx(v):
         consts.append(v % R_MOD)
@@ -319,7 +321,48 @@ def serialize_expression(expr):
             raise ValueError(k)
 
     walk(expr.node if hasattr(expr, "node") else expr)
+    if not finish:
+        return tokens, consts
     return np.asarray(tokens, dtype=np.int32), fr_from_ints(consts if consts else [0])
+
+
+def serialize_lookups(lookups):
+    """[[(input, table), ...], ...] -> one token stream: per lookup [width, input_0, table_0, ...]"""
+    tokens, consts = [], []
+    for lookup in lookups:
+        tokens.append(len(lookup))
+        for inp, tab in lookup:
+            serialize_expression(inp, tokens, consts, finish=False)
+            serialize_expression(tab, tokens, consts, finish=False)
+    return np.asarray(tokens if tokens else [0], dtype=np.int32), fr_from_ints(consts if consts else [0])
+
+
+def expression_rows(num_vars, expr, polys, challenges=()):
+    """Expression::evaluate on every hypercube row (prover.rs:96-117)."""
+    tokens, consts = serialize_expression(expr)
+    arrs, ptrs = _ptr_array(polys)
+    ch = np.ascontiguousarray(challenges, dtype=np.uint64).reshape(-1, 4) if len(challenges) else _fr(1)
+    out = _fr(1 << num_vars)
+    lib().orc_expression_rows(C.c_int(num_vars), _p(tokens), _p(consts), C.c_int(len(polys)), ptrs, _p(ch),
+                              C.c_int(len(challenges)), _p(out))
+    return out
+
+
+def lookup_m(input_poly, table_poly):
+    """lookup_m_poly (prover.rs:143-192); None = Invalid lookup input"""
+    a, b = np.ascontiguousarray(input_poly, dtype=np.uint64), np.ascontiguousarray(table_poly, dtype=np.uint64)
+    out = _fr(a.shape[0])
+    rc = lib().orc_lookup_m(C.c_int(a.shape[0].bit_length() - 1), _p(a), _p(b), _p(out))
+    return out if rc == 0 else None
+
+
+def lookup_h(input_poly, table_poly, m, gamma):
+    a, b = np.ascontiguousarray(input_poly, dtype=np.uint64), np.ascontiguousarray(table_poly, dtype=np.uint64)
+    m = np.ascontiguousarray(m, dtype=np.uint64)
+    out = _fr(a.shape[0])
+    lib().orc_lookup_h(C.c_int(a.shape[0].bit_length() - 1), _p(a), _p(b), _p(m),
+                       _p(np.ascontiguousarray(gamma, dtype=np.uint64)), _p(out))
+    return out
 
 
 def sumcheck_prove_generic(tr, num_vars, expr, polys, challenges, ys, claimed_sum):
@@ -441,8 +484,10 @@ class Kzg:
 class HyperPlonk:
     """Oracle `HyperPlonk<MultilinearKzg>`: preprocess at construction, then prove / verify."""
 
-    def __init__(self, kzg, num_vars, expression, num_instances, num_witness, preprocess_polys, perm_idx, cycles, num_z=1):
+    def __init__(self, kzg, num_vars, expression, num_instances, num_witness, preprocess_polys, perm_idx, cycles, num_z=1,
+                 lookups=()):
         tokens, consts = serialize_expression(expression)
+        ltok, lconsts = serialize_lookups(lookups)
         arrs, ptrs = _ptr_array(preprocess_polys)
         flat = []
         for cyc in cycles:
@@ -455,7 +500,7 @@ class HyperPlonk:
         self.h = C.c_void_p(lib().orc_hp_preprocess(kzg.h, C.c_int(num_vars), _p(tokens), _p(consts), C.c_int(num_instances),
                                                     C.c_int(num_witness), C.c_int(len(preprocess_polys)), ptrs,
                                                     C.c_int(len(perm_idx)), _p(pidx), _p(flat), C.c_int(len(cycles)),
-                                                    C.c_int(num_z)))
+                                                    C.c_int(num_z), C.c_int(len(lookups)), _p(ltok), _p(lconsts)))
 
     def __del__(self):
         if getattr(self, "h", None):

@@ -97,3 +97,81 @@ def test_cfg1_hyperplonk_plus_lasso_on_one_transcript(hl):
     hl.LassoProver(ctx, kzg, O.TABLE_RANGE, chunks).prove(xs)
     assert tr.into_proof() == to.proof()
     ctx.close()
+
+
+# ---- LogUp lookup argument (prover.rs:50-250) --------------------------------------------------------------
+@pytest.mark.parametrize("k", [2, 5, 11])
+def test_expression_rows_parity(hl, env, k):
+    from halo2_lasso_b200.expression import Expression as E
+
+    ctx, okzg, kzg = env
+    N = 1 << k
+    polys = [O.rand_fr(30 + k + i, N) for i in range(4)]
+    ch = [O.fr_to_ints(O.rand_fr(50 + k, 2))[i] for i in range(2)]
+    expr = (E.polynomial(0) * E.polynomial(1, 1) + E.challenge(1) * E.polynomial(2, -1) - E.identity() * E.lagrange(2)
+            + E.constant(9) + E.distribute_powers([E.polynomial(3), E.polynomial(0) * E.polynomial(3), E.polynomial(2)], E.challenge(0)))
+    want = O.expression_rows(k, expr, polys, O.fr_from_ints(ch))
+    dev = [hl.MultilinearPolynomial.new(ctx, p) for p in polys]
+    got = hl.expression_rows(ctx, k, expr, dev, ch).evals()
+    assert (got == want).all()
+
+
+@pytest.mark.parametrize("k", [1, 6, 12])
+def test_lookup_m_and_h_parity(hl, env, k):
+    ctx, okzg, kzg = env
+    N = 1 << k
+    table = O.rand_fr(3 + k, N)
+    table[0] = table[1] = 0
+    if N > 32:
+        table[7] = table[20]
+        table[N - 1] = table[20]
+    idx = np.asarray([int(x) % N for x in O.rand_u64s(9 + k, N)])
+    idx[: N // 2] = 1 if N > 2 else 0  # half of the rows gated off -> the zero tuple (heavy contention on one row)
+    if N > 32:
+        idx[-3:] = [7, 20, N - 1]
+    inp = table[idx]
+    want_m = O.lookup_m(inp, table)
+    d_in, d_tab = hl.MultilinearPolynomial.new(ctx, inp), hl.MultilinearPolynomial.new(ctx, table)
+    m = hl.lookup_m_poly(ctx, k, d_in, d_tab)
+    assert (m.evals() == want_m).all()
+    gamma = O.rand_fr(4, 1)[0]
+    h = hl.lookup_h_poly(ctx, k, d_in, d_tab, m, gamma)
+    assert (h.evals() == O.lookup_h(inp, table, want_m, gamma)).all()
+    bad = inp.copy()
+    bad[N - 1] = O.rand_fr(77, 1)[0]
+    with pytest.raises(hl.B200Error) as e:
+        hl.lookup_m_poly(ctx, k, hl.MultilinearPolynomial.new(ctx, bad), d_tab)
+    assert e.value.code == hl.B200_ERR_LOOKUP
+
+
+@pytest.mark.parametrize("k", [3, 5, 9])
+def test_hyperplonk_with_lookup_proof_parity_and_verifies(hl, env, k):
+    """vanilla_plonk_with_lookup (util.rs:63-98, 216-316): 19 polynomials, degree-5 zero check, LogUp m / h polys."""
+    from halo2_lasso_b200 import hyperplonk as H
+    from halo2_lasso_b200.expression import compose
+
+    ctx, okzg, kzg = env
+    info, instances, w = H.rand_vanilla_plonk_with_lookup_circuit(k, 70 + k)
+    nz, expr = compose(k, info.constraints, info.num_poly, info.permutation_polys, lookups=info.lookups)
+    ohp = O.HyperPlonk(okzg, k, expr, len(instances), 3, [O.fr_from_ints(p) for p in info.preprocess_polys],
+                       info.permutation_polys, info.permutations, nz, lookups=info.lookups)
+    inst = O.fr_from_ints(instances)
+    to = O.Transcript()
+    assert ohp.prove(to, inst, [O.fr_from_ints(c) for c in w])
+    hp = H.HyperPlonk(ctx, kzg, info)
+    tr = hl.Keccak256Transcript(ctx)
+    hp.prove(instances, witness_ints=w)
+    proof = tr.into_proof()
+    ref = to.proof()
+    if proof != ref:
+        first = next(i for i in range(min(len(proof), len(ref))) if proof[i] != ref[i])
+        pytest.fail(f"HyperPlonk+lookup proof differs from the oracle at byte {first} (lengths {len(proof)} vs {len(ref)})")
+    assert ohp.verify(O.Transcript(proof), inst)
+    # a lookup row outside the table: Error::InvalidSnark("Invalid lookup input")
+    row = next(b for b in range(1 << k) if info.preprocess_polys[5][b])
+    w_bad = [list(c) for c in w]
+    w_bad[1][row] = (w_bad[1][row] + 1) % H.R_MOD
+    hl.Keccak256Transcript(ctx)
+    with pytest.raises(hl.B200Error) as e:
+        hp.prove(instances, witness_ints=w_bad)
+    assert e.value.code == hl.B200_ERR_LOOKUP

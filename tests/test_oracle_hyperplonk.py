@@ -82,3 +82,100 @@ def test_rotation_eval_points_define_the_rotated_evaluation():
     bh = BooleanHypercube(k)
     rotated = table[[bh.rotate(b, 1) for b in range(1 << k)]]
     assert combined == O.fr_to_ints(O.evaluate(rotated, x_m))[0]
+
+
+# ---- vanilla plonk WITH the LogUp lookup argument (util.rs:216-316, prover.rs:50-250) ---------------------------
+def build_lookup(kz, k, seed):
+    from halo2_lasso_b200.expression import compose
+
+    info, instances, w = H.rand_vanilla_plonk_with_lookup_circuit(k, seed)
+    nz, expr = compose(k, info.constraints, info.num_poly, info.permutation_polys, lookups=info.lookups)
+    hp = O.HyperPlonk(kz, k, expr, len(instances), 3, [O.fr_from_ints(p) for p in info.preprocess_polys],
+                      info.permutation_polys, info.permutations, nz, lookups=info.lookups)
+    return info, instances, w, hp, expr
+
+
+def test_lookup_fixture_rows_are_in_the_table():
+    k = 6
+    info, instances, w = H.rand_vanilla_plonk_with_lookup_circuit(k, 5)
+    q = info.preprocess_polys
+    rows = {(q[6][b], q[7][b], q[8][b]) for b in range(1 << k)}
+    n_lookup = 0
+    for b in range(1 << k):
+        tup = tuple(q[5][b] * w[i][b] % R_MOD for i in range(3))
+        assert tup in rows
+        n_lookup += q[5][b]
+    assert n_lookup > 4
+
+
+def test_lookup_expression_shape():
+    """util.rs:88-98: 13 + 3 sigma + m + h + z = 19 polynomials, degree 5 with the eq factor (BASELINE cfg5 shape)."""
+    from halo2_lasso_b200.expression import compose
+
+    info, _, _ = H.rand_vanilla_plonk_with_lookup_circuit(4, 1)
+    nz, expr = compose(4, info.constraints, info.num_poly, info.permutation_polys, lookups=info.lookups)
+    assert nz == 1 and expr.degree() == 5
+    polys = {l[1] for l in expr.leaves() if l[0] == "poly"}
+    assert polys == set(range(19))
+    assert ("poly", 18, 1) in expr.leaves()  # z(next)
+
+
+def test_lookup_m_counts_on_the_last_duplicate_row_and_h_sums_to_zero():
+    k = 5
+    N = 1 << k
+    table = O.rand_fr(3, N)
+    table[0] = table[1] = 0  # the zero tuple twice, as in the reference fixture
+    table[7] = table[20]     # another duplicate: row 20 wins
+    idx = [1, 1, 20, 20, 20, 5] + [int(x) % N for x in O.rand_u64s(9, N - 6)]
+    inp = table[idx]
+    m = O.fr_to_ints(O.lookup_m(inp, table))
+    exp = [0] * N
+    last = {}
+    for i in range(N):
+        last[tuple(int(x) for x in table[i])] = i
+    for i in idx:
+        exp[last[tuple(int(x) for x in table[i])]] += 1
+    assert m == exp and m[0] == 0 and m[7] == 0 and m[20] >= 3
+    gamma = O.rand_fr(4, 1)[0]
+    h = O.fr_to_ints(O.lookup_h(inp, table, O.fr_from_ints(m), gamma))
+    assert sum(h) % R_MOD == 0
+    # an input that is not in the table is rejected
+    bad = inp.copy()
+    bad[3] = O.rand_fr(77, 1)[0]
+    assert O.lookup_m(bad, table) is None
+
+
+def test_expression_rows_matches_python_evaluation():
+    from halo2_lasso_b200.expression import Expression as E
+
+    k = 4
+    N = 1 << k
+    polys = [O.rand_fr(30 + i, N) for i in range(3)]
+    ints = [O.fr_to_ints(p) for p in polys]
+    ch = [12345, 678]
+    expr = E.polynomial(0) * E.polynomial(1, 1) + E.challenge(1) * E.polynomial(2, -1) - E.identity() * E.lagrange(2) + E.constant(9)
+    got = O.fr_to_ints(O.expression_rows(k, expr, polys, O.fr_from_ints(ch)))
+    bh = BooleanHypercube(k)
+    for b in range(N):
+        want = (ints[0][b] * ints[1][bh.rotate(b, 1)] + ch[1] * ints[2][bh.rotate(b, -1)] - b * (1 if b == bh.nth(2) else 0) + 9) % R_MOD
+        assert got[b] == want, b
+
+
+@pytest.mark.parametrize("k", [3, 5])
+def test_lookup_prove_verify_roundtrip_and_negatives(kz, k):
+    info, instances, w, hp, expr = build_lookup(kz, k, 60 + k)
+    inst = O.fr_from_ints(instances)
+    tr = O.Transcript()
+    assert hp.prove(tr, inst, [O.fr_from_ints(c) for c in w])
+    proof = tr.proof()
+    assert hp.verify(O.Transcript(proof), inst)
+    for pos in (9, len(proof) // 2, len(proof) - 3):
+        bad = bytearray(proof)
+        bad[pos] ^= 4
+        assert not hp.verify(O.Transcript(bytes(bad)), inst)
+    # a lookup row whose tuple is not a table row: the prover fails with "Invalid lookup input"
+    q = info.preprocess_polys
+    row = next(b for b in range(1 << k) if q[5][b])
+    w_bad = [list(c) for c in w]
+    w_bad[1][row] = (w_bad[1][row] + 1) % R_MOD
+    assert not hp.prove(O.Transcript(), inst, [O.fr_from_ints(c) for c in w_bad])
