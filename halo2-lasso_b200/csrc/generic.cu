@@ -33,79 +33,10 @@ struct GenArgs {
   int round;
 };
 
-// slot file in SHARED memory, one column per thread: [K values | K steps | T temporaries] x blockDim.x.
-// Constants are read from global memory (uniform address -> broadcast). The host's liveness-based slot reuse
-// keeps T tiny (5 for the vanilla-plonk zero check), so 128 threads fit in ~160 KB.
-template <bool BIND>
-__global__ void __launch_bounds__(128) sc_generic_round_kernel(GenArgs a) {
-  extern __shared__ __align__(32) unsigned char gen_smem_raw[];
-  Fr* sm = reinterpret_cast<Fr*>(gen_smem_raw);
-  __shared__ Fr smem[4];
-  __shared__ Fr s_tot[GEN_MAX_DEG];
-  Fr acc[GEN_MAX_DEG];
-  const int K = a.K, D = a.D, KC = a.K + a.C;
-  const int nth = blockDim.x, tid = threadIdx.x;
-#pragma unroll
-  for (int x = 0; x < GEN_MAX_DEG; ++x) acc[x] = fe_zero<FrP>();
-  Fr r = fe_zero<FrP>();
-  if (BIND) r = fe_ld(&a.st->r);
-  const int last = a.ops[a.nops - 1].y;
-  auto rd = [&](int idx) -> Fr {
-    if (idx < K) return sm[idx * nth + tid];
-    if (idx < KC) return fe_ld(a.consts + (idx - K));
-    return sm[(2 * K + idx - KC) * nth + tid];
-  };
-
-  for (uint32_t b = blockIdx.x * blockDim.x + threadIdx.x; b < a.pairs; b += gridDim.x * blockDim.x) {
-    for (int k = 0; k < K; ++k) {
-      Fr u0, u1;
-      if (BIND) {
-        const Fr* p = a.in[k] + 4 * (size_t)b;
-        const Fr x0 = fe_ldg(p), x1 = fe_ldg(p + 1), x2 = fe_ldg(p + 2), x3 = fe_ldg(p + 3);
-        u0 = (x1 - x0) * r + x0;
-        u1 = (x3 - x2) * r + x2;
-        fe_st(a.out[k] + 2 * (size_t)b, u0);
-        fe_st(a.out[k] + 2 * (size_t)b + 1, u1);
-      } else {
-        const Fr* p = a.in[k] + 2 * (size_t)b;
-        u0 = fe_ldg(p);
-        u1 = fe_ldg(p + 1);
-      }
-      sm[k * nth + tid] = u1;
-      sm[(K + k) * nth + tid] = u1 - u0;
-    }
-#pragma unroll 1
-    for (int x = 0; x < D; ++x) {
-      if (x > 0)
-        for (int k = 0; k < K; ++k) sm[k * nth + tid] = sm[k * nth + tid] + sm[(K + k) * nth + tid];
-      for (int i = 0; i < a.nops; ++i) {
-        const int4 op = a.ops[i];
-        const Fr lhs = rd(op.z);
-        Fr res;
-        switch (op.x) {
-          case 0: res = lhs + rd(op.w); break;
-          case 1: res = lhs - rd(op.w); break;
-          case 2: res = lhs * rd(op.w); break;
-          default: res = fe_neg<FrP>(lhs); break;
-        }
-        sm[(2 * K + op.y - KC) * nth + tid] = res;
-      }
-      const Fr v = sm[(2 * K + last - KC) * nth + tid];
-#pragma unroll
-      for (int xx = 0; xx < GEN_MAX_DEG; ++xx)
-        if (xx == x) acc[xx] = acc[xx] + v;
-    }
-  }
-  // per-CTA partials
-  for (int x = 0; x < D; ++x) {
-    Fr t[1] = {fe_zero<FrP>()};
-#pragma unroll
-    for (int xx = 0; xx < GEN_MAX_DEG; ++xx)
-      if (xx == x) t[0] = acc[xx];
-    block_reduce_fr<1>(t, smem);
-    if (threadIdx.x == 0) fe_st(a.partial + (size_t)blockIdx.x * D + x, t[0]);
-  }
-  if (!last_cta_ticket(&a.st->counter)) return;
+// Last CTA of a round: total the per-CTA partials, derive p(0), Fiat-Shamir, fold the claim (same scheme as
+// sc_eval_round_kernel). Called by every thread of that CTA; smem holds blockDim.x / 32 elements.
+__device__ __forceinline__ void gen_finalize(const GenArgs& a, Fr* smem, Fr* s_tot) {
+  const int D = a.D;
   for (int x = 0; x < D; ++x) {
     Fr t[1] = {fe_zero<FrP>()};
     for (uint32_t i = threadIdx.x; i < gridDim.x; i += blockDim.x) t[0] = t[0] + fr_ld_cg(a.partial + (size_t)i * D + x);
@@ -149,6 +80,143 @@ __global__ void __launch_bounds__(128) sc_generic_round_kernel(GenArgs a) {
   }
 }
 
+// slot file in SHARED memory, one column per thread: [K values | T temporaries] x blockDim.x. Only the CURRENT
+// evaluation of every table is kept: moving from x to x+1 re-reads the pair (L1/L2 hit: this thread read or wrote it
+// a moment ago) and adds the step, instead of holding K more step slots per thread — the slot file is what limits
+// the resident warps (19 polynomials + eq + rotated z + identity + Lagrange = 23 tables for plonk-with-lookup).
+// Constants are read from global memory (uniform address -> broadcast). The host's liveness-based slot reuse
+// keeps T tiny (5 for the vanilla-plonk zero check).
+static const int GEN_THREADS = 256;
+template <bool BIND>
+__global__ void __launch_bounds__(GEN_THREADS) sc_generic_round_kernel(GenArgs a) {
+  extern __shared__ __align__(32) unsigned char gen_smem_raw[];
+  Fr* sm = reinterpret_cast<Fr*>(gen_smem_raw);
+  __shared__ Fr smem[GEN_THREADS / 32];
+  __shared__ Fr s_tot[GEN_MAX_DEG];
+  Fr acc[GEN_MAX_DEG];
+  const int K = a.K, D = a.D, KC = a.K + a.C;
+  const int nth = blockDim.x, tid = threadIdx.x;
+#pragma unroll
+  for (int x = 0; x < GEN_MAX_DEG; ++x) acc[x] = fe_zero<FrP>();
+  Fr r = fe_zero<FrP>();
+  if (BIND) r = fe_ld(&a.st->r);
+  const int last = a.ops[a.nops - 1].y;
+  auto rd = [&](int idx) -> Fr {
+    if (idx < K) return sm[idx * nth + tid];
+    if (idx < KC) return fe_ld(a.consts + (idx - K));
+    return sm[(K + idx - KC) * nth + tid];
+  };
+
+  for (uint32_t b = blockIdx.x * blockDim.x + threadIdx.x; b < a.pairs; b += gridDim.x * blockDim.x) {
+    if (BIND) {  // fused bind of the previous challenge: 4 -> 2 elements per table, stored for the next round
+      for (int k = 0; k < K; ++k) {
+        const Fr* p = a.in[k] + 4 * (size_t)b;
+        const Fr x0 = fe_ldg(p), x1 = fe_ldg(p + 1), x2 = fe_ldg(p + 2), x3 = fe_ldg(p + 3);
+        fe_st(a.out[k] + 2 * (size_t)b, (x1 - x0) * r + x0);
+        fe_st(a.out[k] + 2 * (size_t)b + 1, (x3 - x2) * r + x2);
+      }
+    }
+#pragma unroll 1
+    for (int x = 0; x < D; ++x) {
+      // eval(1) = t[2b+1]; eval(x+1) = eval(x) + (t[2b+1] - t[2b])   (eval.rs:228-286)
+      for (int k = 0; k < K; ++k) {
+        const Fr* p = (BIND ? (const Fr*)a.out[k] : a.in[k]) + 2 * (size_t)b;
+        const Fr u0 = fe_ld(p), u1 = fe_ld(p + 1);  // coherent loads: with BIND this thread has just written them
+        sm[k * nth + tid] = x == 0 ? u1 : sm[k * nth + tid] + (u1 - u0);
+      }
+      for (int i = 0; i < a.nops; ++i) {
+        const int4 op = a.ops[i];
+        const Fr lhs = rd(op.z);
+        Fr res;
+        switch (op.x) {
+          case 0: res = lhs + rd(op.w); break;
+          case 1: res = lhs - rd(op.w); break;
+          case 2: res = lhs * rd(op.w); break;
+          default: res = fe_neg<FrP>(lhs); break;
+        }
+        sm[(K + op.y - KC) * nth + tid] = res;
+      }
+      const Fr v = sm[(K + last - KC) * nth + tid];
+#pragma unroll
+      for (int xx = 0; xx < GEN_MAX_DEG; ++xx)
+        if (xx == x) acc[xx] = acc[xx] + v;
+    }
+  }
+  // per-CTA partials
+  for (int x = 0; x < D; ++x) {
+    Fr t[1] = {fe_zero<FrP>()};
+#pragma unroll
+    for (int xx = 0; xx < GEN_MAX_DEG; ++xx)
+      if (xx == x) t[0] = acc[xx];
+    block_reduce_fr<1>(t, smem);
+    if (threadIdx.x == 0) fe_st(a.partial + (size_t)blockIdx.x * D + x, t[0]);
+  }
+  if (!last_cta_ticket(&a.st->counter)) return;
+  gen_finalize(a, smem, s_tot);
+}
+
+// Small rounds (pairs <= GEN_SMALL_PAIRS): one thread per pair would run K binds and D program evaluations back to
+// back (~200 dependent multiplications). Here a CTA owns 32 pairs: the binds are spread over (pair, table) items,
+// then warp x evaluates the program at point x+1 for the CTA's pairs, so a round is ~one program evaluation deep.
+static const uint32_t GEN_SMALL_PAIRS = 16384;
+template <bool BIND>
+__global__ void __launch_bounds__(32 * GEN_MAX_DEG) sc_generic_small_kernel(GenArgs a) {
+  extern __shared__ __align__(32) unsigned char gen_smem_raw[];
+  Fr* sm = reinterpret_cast<Fr*>(gen_smem_raw);
+  __shared__ Fr smem[GEN_MAX_DEG];
+  __shared__ Fr s_tot[GEN_MAX_DEG];
+  const int K = a.K, D = a.D, KC = a.K + a.C;
+  const int nth = blockDim.x, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const uint32_t b0 = blockIdx.x * 32u;
+  const uint32_t here = a.pairs - b0 < 32u ? a.pairs - b0 : 32u;
+  if (BIND) {
+    const Fr r = fe_ld(&a.st->r);
+    for (uint32_t it = tid; it < here * (uint32_t)K; it += nth) {
+      const uint32_t k = it / here, b = b0 + it % here;
+      const Fr* p = a.in[k] + 4 * (size_t)b;
+      const Fr x0 = fe_ldg(p), x1 = fe_ldg(p + 1), x2 = fe_ldg(p + 2), x3 = fe_ldg(p + 3);
+      fe_st(a.out[k] + 2 * (size_t)b, (x1 - x0) * r + x0);
+      fe_st(a.out[k] + 2 * (size_t)b + 1, (x3 - x2) * r + x2);
+    }
+    __syncthreads();  // the bound pairs are read back by other threads of this CTA
+  }
+  Fr acc[1] = {fe_zero<FrP>()};
+  if ((uint32_t)lane < here) {
+    const uint32_t b = b0 + lane;
+    const int last = a.ops[a.nops - 1].y;
+    auto rd = [&](int idx) -> Fr {
+      if (idx < K) return sm[idx * nth + tid];
+      if (idx < KC) return fe_ld(a.consts + (idx - K));
+      return sm[(K + idx - KC) * nth + tid];
+    };
+    for (int k = 0; k < K; ++k) {
+      const Fr* p = (BIND ? (const Fr*)a.out[k] : a.in[k]) + 2 * (size_t)b;
+      const Fr u0 = fe_ld(p), u1 = fe_ld(p + 1);
+      const Fr step = u1 - u0;
+      Fr v = u1;
+      for (int j = 0; j < w; ++j) v = v + step;  // evaluation point w + 1
+      sm[k * nth + tid] = v;
+    }
+    for (int i = 0; i < a.nops; ++i) {
+      const int4 op = a.ops[i];
+      const Fr lhs = rd(op.z);
+      Fr res;
+      switch (op.x) {
+        case 0: res = lhs + rd(op.w); break;
+        case 1: res = lhs - rd(op.w); break;
+        case 2: res = lhs * rd(op.w); break;
+        default: res = fe_neg<FrP>(lhs); break;
+      }
+      sm[(K + op.y - KC) * nth + tid] = res;
+    }
+    acc[0] = sm[(K + last - KC) * nth + tid];
+  }
+  warp_reduce_fr<1>(acc);
+  if (lane == 0) fe_st(a.partial + (size_t)blockIdx.x * D + w, acc[0]);
+  if (!last_cta_ticket(&a.st->counter)) return;
+  gen_finalize(a, smem, s_tot);
+}
+
 __global__ void gen_final_bind_kernel(const Fr* const* tabs, int ntabs, const ScState* st, Fr* evals_out) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= ntabs) return;
@@ -189,14 +257,18 @@ int sumcheck_prove_generic(Ctx* c, const GenericJob& job) {
   a.tr = c->d_tr;
   a.bary = c->d_bary;
   a.challenges_out = job.challenges_out;
-  // shared-memory slot file: (2K + T) field elements per thread
-  const int nslots = 2 * K + job.ntemps;
-  int nth = 128;
+  // shared-memory slot file: (K + T) field elements per thread
+  const int nslots = K + job.ntemps;
+  int nth = GEN_THREADS;
   while (nth > 32 && (size_t)nslots * nth * sizeof(Fr) > 200 * 1024) nth -= 32;
   const size_t smem_bytes = (size_t)nslots * nth * sizeof(Fr);
   if (smem_bytes > 220 * 1024) return B200_ERR_ARG;
   CUDA_TRY(cudaFuncSetAttribute(sc_generic_round_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
   CUDA_TRY(cudaFuncSetAttribute(sc_generic_round_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+  const size_t small_bytes = (size_t)nslots * 32 * job.degree * sizeof(Fr);
+  if (small_bytes > 220 * 1024) return B200_ERR_ARG;
+  CUDA_TRY(cudaFuncSetAttribute(sc_generic_small_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)small_bytes));
+  CUDA_TRY(cudaFuncSetAttribute(sc_generic_small_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)small_bytes));
   const Fr* cur[GEN_MAX_TABLES];
   for (int i = 0; i < K; ++i) cur[i] = job.tables[i];
   for (int round = 0; round < n; ++round) {
@@ -208,16 +280,23 @@ int sumcheck_prove_generic(Ctx* c, const GenericJob& job) {
       a.in[i] = cur[i];
       a.out[i] = dst_base + (size_t)i * dst_sz;
     }
-    int blocks = (int)((a.pairs + nth - 1) / nth);
-    if (blocks > NUM_SMS) blocks = NUM_SMS;  // one CTA per SM (the slot file takes most of the shared memory)
+    const bool small = a.pairs <= GEN_SMALL_PAIRS;
+    int blocks = small ? (int)((a.pairs + 31) / 32) : (int)((a.pairs + nth - 1) / nth);
+    if (!small && blocks > NUM_SMS) blocks = NUM_SMS;  // one CTA per SM (the slot file takes most of the shared memory)
     if ((size_t)blocks * job.degree > c->partial_elems) return B200_ERR_NOMEM;
     const int pi = prof_begin(c, round);
-    if (round == 0) {
+    if (small) {
+      const int sth = 32 * job.degree;
+      const size_t sbytes = (size_t)nslots * sth * sizeof(Fr);
+      if (round == 0) sc_generic_small_kernel<false><<<blocks, sth, sbytes, s>>>(a);
+      else sc_generic_small_kernel<true><<<blocks, sth, sbytes, s>>>(a);
+    } else if (round == 0) {
       sc_generic_round_kernel<false><<<blocks, nth, smem_bytes, s>>>(a);
     } else {
       sc_generic_round_kernel<true><<<blocks, nth, smem_bytes, s>>>(a);
-      for (int i = 0; i < K; ++i) cur[i] = a.out[i];
     }
+    if (round > 0)
+      for (int i = 0; i < K; ++i) cur[i] = a.out[i];
     prof_end(c, pi);
     count_launch(c);
   }
