@@ -425,6 +425,12 @@ def dist_init(ctx, rank=None, world=None):
     return rank, world
 
 
+def dist_shard_commits(ctx, on=True):
+    """Split every commitment MSM of the KZG / Lasso provers by point range over the ranks (collective calls from then
+    on: all ranks run the same prover on the same inputs and obtain the identical proof)."""
+    _chk(lib().b200_dist_shard_commits(ctx.h, C.c_int(int(on))), "dist_shard_commits")
+
+
 def exchange_handles(mine: bytes, world: int):
     """all-gather of fixed-size byte strings in rank order (host-side plumbing, testable with gloo)."""
     import torch.distributed as dist

@@ -43,6 +43,12 @@ int b200_dist_init(b200_ctx* h, int rank, int world, const void* handles) {
   return B200_OK;
 }
 
+int b200_dist_shard_commits(b200_ctx* h, int on) {
+  if (on && h->c.peer.world < 2) return B200_ERR_ARG;
+  h->c.shard_commits = on != 0;
+  return B200_OK;
+}
+
 int b200_sumcheck_prove_evals_sharded(b200_ctx* h, int num_vars_total, int nterms, int np,
                                       const void* const* dev_local_tables, const void* host_weights,
                                       const void* host_y, const void* host_sum, void* host_challenges_out,

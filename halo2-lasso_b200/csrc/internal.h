@@ -46,6 +46,7 @@ struct Ctx {
   PeerCtx peer;            // world == 1 when not initialised
   Mailbox* my_mailbox;     // cudaMalloc'ed, exported through CUDA IPC
   unsigned int peer_seq;   // collectives issued so far (identical on every rank)
+  bool shard_commits = false;  // every commitment MSM is split by point range over the ranks (all ranks call)
 };
 static const int EXT_C = 16;        // window bits of the precomputed tables
 static const int EXT_WINDOWS = 16;  // ceil(255 / 16)
@@ -129,8 +130,11 @@ struct MsmJob {
   int kind;             // MsmScalarKind
   int bits;             // significant bits of the largest scalar (254 for arbitrary Fr)
   const G1Aff* ext;     // optional precomputed window multiples of `bases` (Ctx::srs_ext layout), or null
+  uint64_t ext_stride = 0;  // points per window in `ext` (0: n) — larger than n when the job is a point range
 };
 int msm_batch(Ctx* c, const MsmJob* jobs, int J, G1Aff* d_out);
+// shard.cu: msm_batch, point-sharded over the ranks when commit sharding is on (collective), else local
+int msm_batch_dist(Ctx* c, const MsmJob* jobs, int J, G1Aff* d_out);
 int msm_sharded(Ctx* c, const MsmJob& local, G1Aff* d_out);  // shard.cu
 
 // kzg.cu — MultilinearKzg (pb/pcs/multilinear/kzg.rs) + additive::batch_open (pb/pcs/multilinear.rs:134-235)

@@ -8,7 +8,7 @@
 namespace b200 {
 
 int kzg_commit_batch(Ctx* c, const MsmJob* jobs, int J, bool write_transcript, G1Aff* d_out) {
-  int rc = msm_batch(c, jobs, J, d_out);
+  int rc = msm_batch_dist(c, jobs, J, d_out);
   if (rc) return rc;
   if (write_transcript) return transcript_write_points(c, d_out, J);
   return B200_OK;

@@ -417,7 +417,7 @@ int lasso_prove(Ctx* c, int kind, int chunks, int mu, const uint64_t* d_xs, cons
     const int NC = 1 + 4 * C_;
     CUDA_TRY(cudaMallocAsync(&comms, J * sizeof(G1Aff), s));
     CUDA_TRY(cudaMallocAsync(&all, NC * sizeof(G1Aff), s));
-    rc = msm_batch(c, jobs, J, comms);
+    rc = msm_batch_dist(c, jobs, J, comms);
     if (rc) return rc;
     // transcript order: a | dim[c] | E[c] | read_ts[c] | final_cts[c]
     int h_src[1 + 4 * 8];

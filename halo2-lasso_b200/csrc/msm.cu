@@ -34,6 +34,7 @@ struct MsmJobDev {
   int c, W;           // window bits, number of windows
   uint32_t B;         // buckets per window = 2^(c-1)
   int precomp;        // 1: bases = precomputed window multiples, all windows share one bucket set
+  uint32_t ext_stride;  // precomp: entries per window of the extended table
   int Wred;           // windows that need a bucket reduction (1 when precomp, else W)
   uint32_t bucket_base;
   uint64_t pair_base;
@@ -147,7 +148,7 @@ __global__ void __launch_bounds__(256) msm_digits_kernel(MsmPlanDev plan, uint32
       if (gb == 0xffffffffu) continue;
       const uint32_t code = ranks[p + 1];
       // with precomputed tables the point of window w is entry i + w*n of the extended table
-      sorted[boff[gb] + (code & 0x7fffffffu)] = (jb.precomp ? i + (uint32_t)w * jb.n : i) | (code & 0x80000000u);
+      sorted[boff[gb] + (code & 0x7fffffffu)] = (jb.precomp ? i + (uint32_t)w * jb.ext_stride : i) | (code & 0x80000000u);
     }
   }
 }
@@ -438,6 +439,7 @@ int msm_batch(Ctx* c, const MsmJob* jobs, int J, G1Aff* d_out) {
     jb.kind = in.kind;
     const int need = in.bits + 1;  // signed digits may carry one bit past the top
     jb.precomp = (in.ext != nullptr && in.bits > 2 * EXT_C + 2) ? 1 : 0;
+    jb.ext_stride = (uint32_t)(in.ext_stride ? in.ext_stride : in.n);
     if (jb.precomp) {
       jb.bases = in.ext;
       jb.c = EXT_C;

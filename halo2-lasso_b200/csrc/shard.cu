@@ -9,6 +9,9 @@
 // redundantly on every rank. The transcript is byte-identical to the single-GPU / reference proof.
 //
 // MSM: each rank commits its own point range; the G affine partial results are all-gathered and added.
+#include <algorithm>
+#include <vector>
+
 #include "internal.h"
 
 namespace b200 {
@@ -103,6 +106,78 @@ __global__ void shard_point_sum_kernel(PeerCtx pc, unsigned int seq, const G1Aff
     fe_st(&out->x, a.x);
     fe_st(&out->y, a.y);
   }
+}
+
+// all-gather + add up to 16 partial commitments at once: lane 2i / 2i+1 carry x / y of point idx[i]; afterwards
+// lane i adds the `world` partial points of its commitment in rank order (identical result on every rank).
+struct PointIdx {
+  int v[16];
+};
+__global__ void shard_points_sum_kernel(PeerCtx pc, unsigned int seq, G1Aff* pts, PointIdx pidx, int cnt) {
+  const int lane = threadIdx.x;
+  const int* idx = pidx.v;
+  Fr v = fe_zero<FrP>();
+  if (lane < 2 * cnt) {
+    const G1Aff* p = pts + idx[lane >> 1];
+    const Fq c = fe_ld((lane & 1) ? &p->y : &p->x);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v.v[i] = c.v[i];
+  }
+  peer_publish(pc, seq, v, 2 * cnt);
+  if (lane < cnt) {
+    G1Xyzz acc = g1_identity();
+    for (int r = 0; r < pc.world; ++r) {
+      const Fr x = peer_read(pc, seq, r, 2 * lane), y = peer_read(pc, seq, r, 2 * lane + 1);
+      G1Aff p;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        p.x.v[i] = x.v[i];
+        p.y.v[i] = y.v[i];
+      }
+      acc = g1_add_affine(acc, p, false);
+    }
+    const G1Aff a = g1_to_affine(acc);
+    fe_st(&pts[idx[lane]].x, a.x);
+    fe_st(&pts[idx[lane]].y, a.y);
+  }
+}
+
+// Commitment MSMs split by point range: rank r takes scalars / bases [r n/G, (r+1) n/G) of every job that is large
+// enough, the G partial commitments are all-gathered through the peer mailboxes and added. Small jobs (the low
+// quotient levels of an opening) are computed redundantly on every rank. Collective: all ranks call it with
+// identical job lists (the provers run replicated between the commitments).
+static const uint64_t MSM_SHARD_MIN = 1u << 14;
+int msm_batch_dist(Ctx* c, const MsmJob* jobs, int J, G1Aff* d_out) {
+  const int G = c->peer.world;
+  if (G < 2 || !c->shard_commits) return msm_batch(c, jobs, J, d_out);
+  std::vector<MsmJob> loc(jobs, jobs + J);
+  std::vector<int> sharded;
+  for (int j = 0; j < J; ++j) {
+    MsmJob& m = loc[j];
+    if (m.n < MSM_SHARD_MIN || m.n % G) continue;
+    const uint64_t len = m.n / G, off = (uint64_t)c->peer.rank * len;
+    const size_t esz = m.kind == MSM_U32 ? 4 : (m.kind == MSM_U64 ? 8 : sizeof(Fr));
+    m.scalars = (const char*)m.scalars + off * esz;
+    m.bases += off;
+    if (m.ext) {
+      m.ext_stride = m.ext_stride ? m.ext_stride : m.n;
+      m.ext += off;
+    }
+    m.n = len;
+    sharded.push_back(j);
+  }
+  int rc = msm_batch(c, loc.data(), J, d_out);
+  if (rc) return rc;
+  if (sharded.empty()) return B200_OK;
+  for (size_t at = 0; at < sharded.size(); at += 16) {
+    const int cnt = (int)std::min<size_t>(16, sharded.size() - at);
+    PointIdx pidx;
+    for (int i = 0; i < 16; ++i) pidx.v[i] = i < cnt ? sharded[at + i] : 0;
+    shard_points_sum_kernel<<<1, 32, 0, c->stream>>>(c->peer, ++c->peer_seq, d_out, pidx, cnt);
+    count_launch(c);
+  }
+  CUDA_TRY(cudaGetLastError());
+  return B200_OK;
 }
 
 int msm_sharded(Ctx* c, const MsmJob& local, G1Aff* d_out) {

@@ -35,6 +35,29 @@ struct ScEvalArgs {
     if (a.dbg && threadIdx.x == 0) a.dbg[a.round * 16 + (i)] = clock64(); \
   } while (0)
 
+// Programmatic dependent launch: a round kernel lets the NEXT launch of the stream be scheduled at once (its CTAs
+// become resident as SMs drain) and itself waits for the complete previous grid — memory included — before touching
+// anything that grid wrote. Semantics are those of plain stream order; only the launch latency between the strictly
+// sequential Fiat-Shamir rounds overlaps the previous round's tail.
+__device__ __forceinline__ void pdl_prologue() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+template <class Args>
+static cudaError_t launch_pdl(void (*kernel)(Args), dim3 grid, dim3 block, cudaStream_t s, const Args& a) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, a);
+}
+
 // Load the pair (u0, u1) = (t[2b], t[2b+1]) of the CURRENT round. With BIND the table still has the
 // previous round's size: bind 4 consecutive elements with r first and store the bound pair.
 template <bool BIND>
@@ -62,6 +85,7 @@ template <int NP, bool BIND, bool EQPRE = false>
 __global__ void __launch_bounds__(SC_THREADS) sc_eval_round_kernel(ScEvalArgs a) {
   constexpr int D = NP + 1;  // degree; evaluations at 1..D are computed, p(0) derived
   __shared__ Fr smem[(SC_THREADS / 32) * D];
+  pdl_prologue();
   const int t = blockIdx.y;
   Fr acc[D];
 #pragma unroll
@@ -274,18 +298,18 @@ int sumcheck_prove_evals(Ctx* c, const ScEvalJob& job) {
     if ((size_t)grid.x * grid.y * (NP + 1) > c->partial_elems) return B200_ERR_NOMEM;
     const int pi = prof_begin(c, round);
     if (round == 0) {
-      if (NP == 1) sc_eval_round_kernel<1, false><<<grid, SC_THREADS, 0, s>>>(a);
-      else sc_eval_round_kernel<2, false><<<grid, SC_THREADS, 0, s>>>(a);
+      if (NP == 1) CUDA_TRY(launch_pdl(sc_eval_round_kernel<1, false, false>, grid, SC_THREADS, s, a));
+      else CUDA_TRY(launch_pdl(sc_eval_round_kernel<2, false, false>, grid, SC_THREADS, s, a));
     } else if (NP == 2 && T >= 4 && a.pairs >= 2048) {
       int lg = 0;
       while (((size_t)1 << lg) < 4 * (size_t)a.pairs) ++lg;
       rc = fix_var(c, a.eq_in, lg, &c->d_sc->r, a.eq_out);
       if (rc) return rc;
-      sc_eval_round_kernel<2, true, true><<<grid, SC_THREADS, 0, s>>>(a);
+      CUDA_TRY(launch_pdl(sc_eval_round_kernel<2, true, true>, grid, SC_THREADS, s, a));
       for (int i = 0; i <= ntab; ++i) cur[i] = (i < ntab) ? a.out[i] : a.eq_out;
     } else {
-      if (NP == 1) sc_eval_round_kernel<1, true><<<grid, SC_THREADS, 0, s>>>(a);
-      else sc_eval_round_kernel<2, true><<<grid, SC_THREADS, 0, s>>>(a);
+      if (NP == 1) CUDA_TRY(launch_pdl(sc_eval_round_kernel<1, true, false>, grid, SC_THREADS, s, a));
+      else CUDA_TRY(launch_pdl(sc_eval_round_kernel<2, true, false>, grid, SC_THREADS, s, a));
       for (int i = 0; i <= ntab; ++i) cur[i] = (i < ntab) ? a.out[i] : a.eq_out;
     }
     prof_end(c, pi);
@@ -327,6 +351,7 @@ struct ScCoeffArgs {
 template <bool BIND>
 __global__ void __launch_bounds__(SC_THREADS) sc_coeff_round_kernel(ScCoeffArgs a) {
   __shared__ Fr smem[(SC_THREADS / 32) * 2];
+  pdl_prologue();
   const int k = blockIdx.y;
   Fr acc[2] = {fe_zero<FrP>(), fe_zero<FrP>()};
   Fr r = fe_zero<FrP>();
@@ -428,9 +453,9 @@ int sumcheck_prove_coeffs(Ctx* c, const ScCoeffJob& job) {
     dim3 grid(blocks_for(a.pairs, K), K);
     if ((size_t)grid.x * grid.y * 2 > c->partial_elems) return B200_ERR_NOMEM;
     if (round == 0) {
-      sc_coeff_round_kernel<false><<<grid, SC_THREADS, 0, s>>>(a);
+      CUDA_TRY(launch_pdl(sc_coeff_round_kernel<false>, grid, SC_THREADS, s, a));
     } else {
-      sc_coeff_round_kernel<true><<<grid, SC_THREADS, 0, s>>>(a);
+      CUDA_TRY(launch_pdl(sc_coeff_round_kernel<true>, grid, SC_THREADS, s, a));
       for (int k = 0; k < K; ++k) {
         cur[k] = a.out[k];
         cur[K + k] = a.eq_out[k];

@@ -170,6 +170,12 @@ int b200_kzg_batch_open(b200_ctx* ctx, int num_vars, const void* const* dev_poly
  * (e.g. torch.distributed.all_gather), then call b200_dist_init with the `world` handles in rank order. */
 int b200_dist_mailbox_handle(b200_ctx* ctx, void* out_handle64);
 int b200_dist_init(b200_ctx* ctx, int rank, int world, const void* handles);
+/* Point-sharded commitments: after b200_dist_shard_commits(ctx, 1) every commitment MSM issued by b200_kzg_* and
+ * b200_lasso_prove* (variable_base_msm call sites kzg.rs:255,271,292) is split by point range over the ranks and the
+ * partial commitments are all-gathered over NVLink and added, so these calls become COLLECTIVE: all ranks run the same
+ * prover on the same inputs (everything between the commitments is replicated) and produce the identical proof. */
+int b200_dist_shard_commits(b200_ctx* ctx, int on);
+
 /* b200_sumcheck_prove_evals on a hypercube sharded over the TOP log2(world) variables: rank g passes the
  * slices [g*2^n/world, (g+1)*2^n/world) of every table. All ranks must call it; all receive the same
  * challenges / evals and append the same bytes to their transcripts (identical to the unsharded proof). */

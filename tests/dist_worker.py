@@ -45,6 +45,32 @@ def main():
     lo, hi = hl.shard_slice(10, rank, world)
     got = hl.variable_base_msm_sharded(ctx, sc[lo:hi], bases[lo:hi])
     assert (got == O.msm(sc, bases)).all(), f"rank {rank}: sharded MSM differs"
+    # point-sharded commitments inside whole provers (every rank runs the same prover; the commitment MSMs are split
+    # by point range and summed over NVLink): proofs byte-identical to the single-process oracle on every rank
+    NVK = 16
+    okzg = O.Kzg(O.rand_fr(7, NVK))
+    kzg = hl.MultilinearKzg(ctx, [okzg.eqs(k) for k in range(NVK + 1)])
+    hl.dist_shard_commits(ctx, True)
+    poly = O.rand_fr(8100, 1 << 15)
+    point = O.rand_fr(8101, 15)
+    to = O.Transcript()
+    okzg.open(to, poly, point)
+    tr = hl.Keccak256Transcript(ctx)
+    kzg.open(hl.MultilinearPolynomial.new(ctx, poly), point)
+    assert tr.into_proof() == to.proof(), f"rank {rank}: commit-sharded KZG opening differs"
+    for kind, chunks, mu in ((O.TABLE_RANGE, 4, 14), (O.TABLE_AND, 4, 15)):
+        xs, ys = O.rand_u64s(8200 + mu, 1 << mu), O.rand_u64s(8300 + mu, 1 << mu)
+        if kind == O.TABLE_AND:
+            xs &= np.uint64((1 << (8 * chunks)) - 1)
+            ys &= np.uint64((1 << (8 * chunks)) - 1)
+        else:
+            ys = None
+        to = O.Transcript()
+        assert O.lasso_prove(okzg, to, kind, chunks, mu, xs, ys)
+        tr = hl.Keccak256Transcript(ctx)
+        hl.LassoProver(ctx, kzg, kind, chunks).prove(xs, ys)
+        assert tr.into_proof() == to.proof(), f"rank {rank}: commit-sharded Lasso proof differs (kind {kind})"
+    hl.dist_shard_commits(ctx, False)
     dist.barrier()
     if rank == 0:
         print(f"SHARDED_OK world={world}")
