@@ -101,6 +101,32 @@ __device__ __forceinline__ bool last_cta_ticket(unsigned int* counter) {
 }
 #endif
 
+// Programmatic dependent launch: a kernel lets the NEXT launch of the stream be scheduled at once (its CTAs become
+// resident as SMs drain) and itself waits for the complete previous grid — memory included — before touching anything
+// that grid wrote. Semantics are those of plain stream order; only the launch latency between the strictly
+// sequential Fiat-Shamir steps overlaps the previous kernel's tail.
+#if defined(__CUDACC__)
+__device__ __forceinline__ void pdl_prologue() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+template <class... KArgs, class... Args>
+static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s,
+                                     Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#endif
+
 // Barycentric weights for the nodes 0..d, d <= 6: w[d][i] = 1 / Π_{j != i} (i - j) (Montgomery).
 // Lagrange interpolation with these constants is inversion-free and yields the same field element
 // as `barycentric_interpolate` (pb/util/arithmetic.rs:125-136) for every r outside {0..d}.

@@ -165,6 +165,7 @@ __global__ void __launch_bounds__(256) lasso_leaves_s_kernel(int kind, int c, co
 // one tree layer for a group of equally sized trees: V_k[i] = V_{k+1}[i] * V_{k+1}[i + 2^k]; tree
 // arrays are heap-ordered (layer k at [2^k, 2^(k+1)))
 __global__ void __launch_bounds__(256) tree_up_kernel(Fr* __restrict__ trees, size_t tree_stride, uint32_t half) {
+  pdl_prologue();
   Fr* tr = trees + (size_t)blockIdx.y * tree_stride;
   const uint32_t stride = gridDim.x * blockDim.x;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < half; i += stride)
@@ -187,6 +188,7 @@ struct GpTrees {
 
 // write the roots, which are the first claims
 __global__ void gp_roots_kernel(Transcript* tr, GpTrees trees, GpState* st) {
+  pdl_prologue();
   __shared__ Transcript sh_tr;
   trw_copy(&sh_tr, tr);
   for (int t = 0; t < trees.T; ++t) {
@@ -200,6 +202,7 @@ __global__ void gp_roots_kernel(Transcript* tr, GpTrees trees, GpState* st) {
 // Layer k, before the sum-check. k == 0: the two children are the evaluations. k > 0: squeeze gamma,
 // weights = gamma^slot over the ACTIVE trees (height > k, input order), claim = Σ weights * claims.
 __global__ void gp_before_kernel(Transcript* tr, GpTrees trees, int k, GpState* st) {
+  pdl_prologue();
   __shared__ Transcript sh_tr;
   const int lane = threadIdx.x;
   if (k == 0) {
@@ -227,6 +230,7 @@ __global__ void gp_before_kernel(Transcript* tr, GpTrees trees, int k, GpState* 
 }
 // after the sum-check: write the 2A evaluations, squeeze mu, fold the active claims, y = x || mu
 __global__ void gp_after_kernel(Transcript* tr, GpTrees trees, int k, const Fr* x /* k challenges */, GpState* st) {
+  pdl_prologue();
   __shared__ Transcript sh_tr;
   const int lane = threadIdx.x;
   trw_copy(&sh_tr, tr);
@@ -261,6 +265,7 @@ __global__ void gather_points_kernel(const G1Aff* src, const int* idx, int n, G1
   fe_st(&dst[i].y, fe_ld(&src[idx[i]].y));
 }
 __global__ void copy_fr_kernel(const Fr* src, Fr* dst, int n) {
+  pdl_prologue();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) fe_st(dst + i, fe_ld(src + i));
 }
@@ -272,10 +277,10 @@ static int grand_product_prove(Ctx* c, const GpTrees& trees, GpState* st, Fr* sc
   cudaStream_t s = c->stream;
   int h = 0;
   for (int t = 0; t < trees.T; ++t) h = trees.height[t] > h ? trees.height[t] : h;
-  gp_roots_kernel<<<1, 32, 0, s>>>(c->d_tr, trees, st);
+  CUDA_TRY(launch_pdl(gp_roots_kernel, dim3(1), dim3(32), 0, s, c->d_tr, trees, st));
   count_launch(c);
   for (int k = 0; k < h; ++k) {
-    gp_before_kernel<<<1, 32, 0, s>>>(c->d_tr, trees, k, st);
+    CUDA_TRY(launch_pdl(gp_before_kernel, dim3(1), dim3(32), 0, s, c->d_tr, trees, k, st));
     count_launch(c);
     if (k > 0) {
       ScEvalJob job;
@@ -298,10 +303,10 @@ static int grand_product_prove(Ctx* c, const GpTrees& trees, GpState* st, Fr* sc
       int rc = sumcheck_prove_evals(c, job);
       if (rc) return rc;
     }
-    gp_after_kernel<<<1, 32, 0, s>>>(c->d_tr, trees, k, scratch_x, st);
+    CUDA_TRY(launch_pdl(gp_after_kernel, dim3(1), dim3(32), 0, s, c->d_tr, trees, k, scratch_x, st));
     count_launch(c);
     if (point_out[k + 1]) {
-      copy_fr_kernel<<<1, 64, 0, s>>>(st->y, point_out[k + 1], k + 1);
+      CUDA_TRY(launch_pdl(copy_fr_kernel, dim3(1), dim3(64), 0, s, st->y, point_out[k + 1], k + 1));
       count_launch(c);
     }
   }
@@ -489,13 +494,13 @@ int lasso_prove(Ctx* c, int kind, int chunks, int mu, const uint64_t* d_xs, cons
       const uint32_t half = 1u << k;
       int bx = (int)((half + 255) / 256), cap = (4 * NUM_SMS + T - 1) / T;
       if (bx > cap) bx = cap;
-      tree_up_kernel<<<dim3(bx, T), 256, 0, s>>>(mtrees, (size_t)2 * m, half);
+      CUDA_TRY(launch_pdl(tree_up_kernel, dim3(dim3(bx, T)), dim3(256), 0, s, mtrees, (size_t)2 * m, half));
     }
     for (int k = SUB_VARS - 1; k >= 0; --k) {
       const uint32_t half = 1u << k;
       int bx = (int)((half + 255) / 256), cap = (4 * NUM_SMS + T - 1) / T;
       if (bx > cap) bx = cap;
-      tree_up_kernel<<<dim3(bx, T), 256, 0, s>>>(strees, (size_t)2 * S, half);
+      CUDA_TRY(launch_pdl(tree_up_kernel, dim3(dim3(bx, T)), dim3(256), 0, s, strees, (size_t)2 * S, half));
     }
     count_launch(c, mu + SUB_VARS);
     GpTrees trees;
@@ -512,7 +517,7 @@ int lasso_prove(Ctx* c, int kind, int chunks, int mu, const uint64_t* d_xs, cons
     if (mu == SUB_VARS) {  // both leaf layers are reached at the same point
       rc = grand_product_prove(c, trees, gp, x_scratch, point_out);
       if (rc) return rc;
-      copy_fr_kernel<<<1, 64, 0, s>>>(pts + 2 * (size_t)mu, pt_s, SUB_VARS);
+      CUDA_TRY(launch_pdl(copy_fr_kernel, dim3(1), dim3(64), 0, s, pts + 2 * (size_t)mu, pt_s, SUB_VARS));
       count_launch(c);
     } else {
       point_out[SUB_VARS] = pt_s;  // x_s
@@ -545,15 +550,15 @@ int lasso_prove(Ctx* c, int kind, int chunks, int mu, const uint64_t* d_xs, cons
   ph = prof_begin(c, PH_OPEN_M);
   // ---- 10. batch openings ---------------------------------------------------------------------------
   {
-    copy_fr_kernel<<<1, 64, 0, s>>>(r, pts, mu);
-    copy_fr_kernel<<<1, 64, 0, s>>>(x_p, pts + mu, mu);
+    CUDA_TRY(launch_pdl(copy_fr_kernel, dim3(1), dim3(64), 0, s, r, pts, mu));
+    CUDA_TRY(launch_pdl(copy_fr_kernel, dim3(1), dim3(64), 0, s, x_p, pts + mu, mu));
     count_launch(c, 2);
     const int E = 1 + 4 * C_;
     Fr* vals;
     CUDA_TRY(cudaMallocAsync(&vals, E * sizeof(Fr), s));
-    copy_fr_kernel<<<1, 64, 0, s>>>(v_a, vals, 1);
-    copy_fr_kernel<<<1, 64, 0, s>>>(e_p, vals + 1, C_);
-    copy_fr_kernel<<<1, 64, 0, s>>>(ev_m, vals + 1 + C_, 3 * C_);
+    CUDA_TRY(launch_pdl(copy_fr_kernel, dim3(1), dim3(64), 0, s, v_a, vals, 1));
+    CUDA_TRY(launch_pdl(copy_fr_kernel, dim3(1), dim3(64), 0, s, e_p, vals + 1, C_));
+    CUDA_TRY(launch_pdl(copy_fr_kernel, dim3(1), dim3(64), 0, s, ev_m, vals + 1 + C_, 3 * C_));
     count_launch(c, 3);
     const Fr* polys[1 + 3 * 8];
     for (int i = 0; i < NM; ++i) polys[i] = mt + (size_t)i * m;

@@ -13,6 +13,7 @@ namespace b200 {
 
 // half tables: out[b] = Π_{k<nv} (b_k ? y[k] : 1 - y[k]) computed directly (nv <= 16)
 __global__ void eq_direct_kernel(const Fr* __restrict__ y, int nv, Fr* __restrict__ out) {
+  pdl_prologue();
   const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= (1u << nv)) return;
   const Fr one = fe_one<FrP>();
@@ -26,6 +27,7 @@ __global__ void eq_direct_kernel(const Fr* __restrict__ y, int nv, Fr* __restric
 
 __global__ void eq_combine_kernel(const Fr* __restrict__ lo, const Fr* __restrict__ hi, int nlo,
                                   size_t n, Fr* __restrict__ out) {
+  pdl_prologue();
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   const uint32_t mask = (1u << nlo) - 1;
   for (size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x; b < n; b += stride) {
@@ -40,7 +42,7 @@ int eq_build(Ctx* c, const Fr* d_y, int n, Fr* d_out) {
   if (n < 1 || n > 30) return B200_ERR_ARG;
   if (n <= 12) {
     const uint32_t N = 1u << n;
-    eq_direct_kernel<<<(N + 127) / 128, 128, 0, s>>>(d_y, n, d_out);
+    CUDA_TRY(launch_pdl(eq_direct_kernel, dim3((N + 127) / 128), dim3(128), 0, s, d_y, n, d_out));
     count_launch(c);
     CUDA_TRY(cudaGetLastError());
     return B200_OK;
@@ -50,12 +52,12 @@ int eq_build(Ctx* c, const Fr* d_y, int n, Fr* d_out) {
   CUDA_TRY(cudaMallocAsync(&half, (((size_t)1 << nlo) + ((size_t)1 << nhi)) * sizeof(Fr), s));
   Fr* lo = half;
   Fr* hi = half + ((size_t)1 << nlo);
-  eq_direct_kernel<<<((1u << nlo) + 127) / 128, 128, 0, s>>>(d_y, nlo, lo);
-  eq_direct_kernel<<<((1u << nhi) + 127) / 128, 128, 0, s>>>(d_y + nlo, nhi, hi);
+  CUDA_TRY(launch_pdl(eq_direct_kernel, dim3(((1u << nlo) + 127) / 128), dim3(128), 0, s, d_y, nlo, lo));
+  CUDA_TRY(launch_pdl(eq_direct_kernel, dim3(((1u << nhi) + 127) / 128), dim3(128), 0, s, d_y + nlo, nhi, hi));
   const size_t N = (size_t)1 << n;
   int blocks = (int)((N + 255) / 256);
   if (blocks > NUM_SMS * 8) blocks = NUM_SMS * 8;
-  eq_combine_kernel<<<blocks, 256, 0, s>>>(lo, hi, nlo, N, d_out);
+  CUDA_TRY(launch_pdl(eq_combine_kernel, dim3(blocks), dim3(256), 0, s, lo, hi, nlo, N, d_out));
   count_launch(c, 3);
   CUDA_TRY(cudaFreeAsync(half, s));
   CUDA_TRY(cudaGetLastError());
@@ -64,6 +66,7 @@ int eq_build(Ctx* c, const Fr* d_y, int n, Fr* d_out) {
 
 __global__ void fix_var_kernel(const Fr* __restrict__ in, size_t half, const Fr* __restrict__ r_ptr,
                                Fr* __restrict__ out) {
+  pdl_prologue();
   const Fr r = fe_ld(r_ptr);
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   for (size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x; b < half; b += stride) {
@@ -77,7 +80,7 @@ int fix_var(Ctx* c, const Fr* d_in, int n, const Fr* d_r, Fr* d_out) {
   const size_t half = (size_t)1 << (n - 1);
   int blocks = (int)((half + 255) / 256);
   if (blocks > NUM_SMS * 8) blocks = NUM_SMS * 8;
-  fix_var_kernel<<<blocks, 256, 0, c->stream>>>(d_in, half, d_r, d_out);
+  CUDA_TRY(launch_pdl(fix_var_kernel, dim3(blocks), dim3(256), 0, c->stream, d_in, half, d_r, d_out));
   count_launch(c);
   CUDA_TRY(cudaGetLastError());
   return B200_OK;
@@ -93,6 +96,7 @@ struct EvalManyArgs {
   Fr* out;
 };
 __global__ void __launch_bounds__(256) mle_dot_kernel(EvalManyArgs a) {
+  pdl_prologue();
   __shared__ Fr smem[8];
   const int t = blockIdx.y;
   const Fr* __restrict__ tab = a.tables[t];
@@ -132,7 +136,7 @@ int mle_eval_many(Ctx* c, const Fr* const* h_tables, int ntables, int n, const F
   if (bx > cap) bx = cap;
   if (bx < 1) bx = 1;
   if ((size_t)bx * ntables > c->partial_elems) return B200_ERR_NOMEM;
-  mle_dot_kernel<<<dim3(bx, ntables), 256, 0, s>>>(a);
+  CUDA_TRY(launch_pdl(mle_dot_kernel, dim3(dim3(bx, ntables)), dim3(256), 0, s, a));
   count_launch(c);
   CUDA_TRY(cudaFreeAsync(eq, s));
   CUDA_TRY(cudaGetLastError());
@@ -147,6 +151,7 @@ struct LincombArgs {
   Fr* out;
 };
 __global__ void __launch_bounds__(256) lincomb_kernel(LincombArgs a) {
+  pdl_prologue();
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.len; i += stride) {
     Fr acc = fe_zero<FrP>();
@@ -164,7 +169,7 @@ int fr_lincomb(Ctx* c, const Fr* const* h_tables, int k, const Fr* d_scalars, si
   a.out = d_out;
   int blocks = (int)((len + 255) / 256);
   if (blocks > NUM_SMS * 8) blocks = NUM_SMS * 8;
-  lincomb_kernel<<<blocks, 256, 0, c->stream>>>(a);
+  CUDA_TRY(launch_pdl(lincomb_kernel, dim3(blocks), dim3(256), 0, c->stream, a));
   count_launch(c);
   CUDA_TRY(cudaGetLastError());
   return B200_OK;
@@ -219,6 +224,7 @@ int fr_from_u64(Ctx* c, const uint64_t* d_in, Fr* d_out, size_t n) {
 // q[i] = rem[half+i] - rem[i]; rem[i] += (rem[half+i] - rem[i]) * x      (top variable first)
 __global__ void quotient_kernel(Fr* __restrict__ rem, size_t half, const Fr* __restrict__ x_ptr,
                                 Fr* __restrict__ q) {
+  pdl_prologue();
   const Fr x = fe_ld(x_ptr);
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < half; i += stride) {
@@ -232,7 +238,7 @@ int quotient_step(Ctx* c, Fr* d_rem, size_t half, const Fr* d_x, Fr* d_q) {
   int blocks = (int)((half + 255) / 256);
   if (blocks > NUM_SMS * 8) blocks = NUM_SMS * 8;
   if (blocks < 1) blocks = 1;
-  quotient_kernel<<<blocks, 256, 0, c->stream>>>(d_rem, half, d_x, d_q);
+  CUDA_TRY(launch_pdl(quotient_kernel, dim3(blocks), dim3(256), 0, c->stream, d_rem, half, d_x, d_q));
   count_launch(c);
   CUDA_TRY(cudaGetLastError());
   return B200_OK;
@@ -240,6 +246,7 @@ int quotient_step(Ctx* c, Fr* d_rem, size_t half, const Fr* d_x, Fr* d_q) {
 
 // Π_i (2 x_i y_i + 1 - x_i - y_i)
 __global__ void eq_xy_eval_kernel(const Fr* x, const Fr* y, int n, Fr* out) {
+  pdl_prologue();
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   const Fr one = fe_one<FrP>();
   Fr acc = one;
@@ -251,13 +258,14 @@ __global__ void eq_xy_eval_kernel(const Fr* x, const Fr* y, int n, Fr* out) {
   fe_st(out, acc);
 }
 int eq_xy_eval_dev(Ctx* c, const Fr* d_x, const Fr* d_y, int n, Fr* d_out) {
-  eq_xy_eval_kernel<<<1, 32, 0, c->stream>>>(d_x, d_y, n, d_out);
+  CUDA_TRY(launch_pdl(eq_xy_eval_kernel, dim3(1), dim3(32), 0, c->stream, d_x, d_y, n, d_out));
   count_launch(c);
   CUDA_TRY(cudaGetLastError());
   return B200_OK;
 }
 
 __global__ void transcript_kernel(Transcript* tr, int op, const Fr* in, Fr* out, int n) {
+  pdl_prologue();
   __shared__ Transcript sh_tr;  // one warp, warp-cooperative Keccak
   trw_copy(&sh_tr, tr);
   for (int i = 0; i < n; ++i) {
@@ -272,13 +280,14 @@ __global__ void transcript_kernel(Transcript* tr, int op, const Fr* in, Fr* out,
 }
 int transcript_op(Ctx* c, int op, const Fr* d_in, Fr* d_out, int n) {
   if (n <= 0) return B200_OK;
-  transcript_kernel<<<1, 32, 0, c->stream>>>(c->d_tr, op, d_in, d_out, n);
+  CUDA_TRY(launch_pdl(transcript_kernel, dim3(1), dim3(32), 0, c->stream, c->d_tr, op, d_in, d_out, n));
   count_launch(c);
   CUDA_TRY(cudaGetLastError());
   return B200_OK;
 }
 
 __global__ void transcript_points_kernel(Transcript* tr, const G1Aff* pts, int n) {
+  pdl_prologue();
   __shared__ Transcript sh_tr;
   trw_copy(&sh_tr, tr);
   for (int i = 0; i < n; ++i) {
@@ -289,7 +298,7 @@ __global__ void transcript_points_kernel(Transcript* tr, const G1Aff* pts, int n
 }
 int transcript_write_points(Ctx* c, const G1Aff* d_pts, int n) {
   if (n <= 0) return B200_OK;
-  transcript_points_kernel<<<1, 32, 0, c->stream>>>(c->d_tr, d_pts, n);
+  CUDA_TRY(launch_pdl(transcript_points_kernel, dim3(1), dim3(32), 0, c->stream, c->d_tr, d_pts, n));
   count_launch(c);
   CUDA_TRY(cudaGetLastError());
   return B200_OK;

@@ -35,29 +35,6 @@ struct ScEvalArgs {
     if (a.dbg && threadIdx.x == 0) a.dbg[a.round * 16 + (i)] = clock64(); \
   } while (0)
 
-// Programmatic dependent launch: a round kernel lets the NEXT launch of the stream be scheduled at once (its CTAs
-// become resident as SMs drain) and itself waits for the complete previous grid — memory included — before touching
-// anything that grid wrote. Semantics are those of plain stream order; only the launch latency between the strictly
-// sequential Fiat-Shamir rounds overlaps the previous round's tail.
-__device__ __forceinline__ void pdl_prologue() {
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-  asm volatile("griddepcontrol.wait;" ::: "memory");
-}
-template <class Args>
-static cudaError_t launch_pdl(void (*kernel)(Args), dim3 grid, dim3 block, cudaStream_t s, const Args& a) {
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = grid;
-  cfg.blockDim = block;
-  cfg.dynamicSmemBytes = 0;
-  cfg.stream = s;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, kernel, a);
-}
-
 // Load the pair (u0, u1) = (t[2b], t[2b+1]) of the CURRENT round. With BIND the table still has the
 // previous round's size: bind 4 consecutive elements with r first and store the bound pair.
 template <bool BIND>
@@ -222,6 +199,7 @@ __global__ void __launch_bounds__(SC_THREADS) sc_eval_round_kernel(ScEvalArgs a)
 
 // After the last round every table has 2 entries: bind them with the last challenge.
 __global__ void sc_final_bind_kernel(const Fr* const* tabs, int ntabs, const ScState* st, Fr* evals_out) {
+  pdl_prologue();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= ntabs) return;
   const Fr r = fe_ld(&st->r);
@@ -230,6 +208,7 @@ __global__ void sc_final_bind_kernel(const Fr* const* tabs, int ntabs, const ScS
 }
 
 __global__ void sc_init_kernel(ScState* st, const Fr* claim) {
+  pdl_prologue();
   if (threadIdx.x == 0) {
     fe_st(&st->claim, fe_ld(claim));
     fe_st(&st->r, fe_zero<FrP>());
@@ -265,7 +244,7 @@ int sumcheck_prove_evals(Ctx* c, const ScEvalJob& job) {
       if (rc) return rc;
     }
   }
-  sc_init_kernel<<<1, 32, 0, s>>>(c->d_sc, job.claim);
+  CUDA_TRY(launch_pdl(sc_init_kernel, dim3(1), dim3(32), 0, s, c->d_sc, job.claim));
   count_launch(c);
 
   ScEvalArgs a;
@@ -298,18 +277,18 @@ int sumcheck_prove_evals(Ctx* c, const ScEvalJob& job) {
     if ((size_t)grid.x * grid.y * (NP + 1) > c->partial_elems) return B200_ERR_NOMEM;
     const int pi = prof_begin(c, round);
     if (round == 0) {
-      if (NP == 1) CUDA_TRY(launch_pdl(sc_eval_round_kernel<1, false, false>, grid, SC_THREADS, s, a));
-      else CUDA_TRY(launch_pdl(sc_eval_round_kernel<2, false, false>, grid, SC_THREADS, s, a));
+      if (NP == 1) CUDA_TRY(launch_pdl(sc_eval_round_kernel<1, false, false>, grid, SC_THREADS, 0, s, a));
+      else CUDA_TRY(launch_pdl(sc_eval_round_kernel<2, false, false>, grid, SC_THREADS, 0, s, a));
     } else if (NP == 2 && T >= 4 && a.pairs >= 2048) {
       int lg = 0;
       while (((size_t)1 << lg) < 4 * (size_t)a.pairs) ++lg;
       rc = fix_var(c, a.eq_in, lg, &c->d_sc->r, a.eq_out);
       if (rc) return rc;
-      CUDA_TRY(launch_pdl(sc_eval_round_kernel<2, true, true>, grid, SC_THREADS, s, a));
+      CUDA_TRY(launch_pdl(sc_eval_round_kernel<2, true, true>, grid, SC_THREADS, 0, s, a));
       for (int i = 0; i <= ntab; ++i) cur[i] = (i < ntab) ? a.out[i] : a.eq_out;
     } else {
-      if (NP == 1) CUDA_TRY(launch_pdl(sc_eval_round_kernel<1, true, false>, grid, SC_THREADS, s, a));
-      else CUDA_TRY(launch_pdl(sc_eval_round_kernel<2, true, false>, grid, SC_THREADS, s, a));
+      if (NP == 1) CUDA_TRY(launch_pdl(sc_eval_round_kernel<1, true, false>, grid, SC_THREADS, 0, s, a));
+      else CUDA_TRY(launch_pdl(sc_eval_round_kernel<2, true, false>, grid, SC_THREADS, 0, s, a));
       for (int i = 0; i <= ntab; ++i) cur[i] = (i < ntab) ? a.out[i] : a.eq_out;
     }
     prof_end(c, pi);
@@ -320,7 +299,7 @@ int sumcheck_prove_evals(Ctx* c, const ScEvalJob& job) {
   const int nfinal = ntab + (job.want_eq_eval ? 1 : 0);
   CUDA_TRY(cudaMallocAsync(&d_ptrs, nfinal * sizeof(Fr*), s));
   CUDA_TRY(cudaMemcpyAsync(d_ptrs, cur, nfinal * sizeof(Fr*), cudaMemcpyHostToDevice, s));
-  sc_final_bind_kernel<<<(nfinal + 63) / 64, 64, 0, s>>>(d_ptrs, nfinal, c->d_sc, job.evals_out);
+  CUDA_TRY(launch_pdl(sc_final_bind_kernel, dim3((nfinal + 63) / 64), dim3(64), 0, s, d_ptrs, nfinal, c->d_sc, job.evals_out));
   count_launch(c);
   CUDA_TRY(cudaFreeAsync(d_ptrs, s));
   if (eq0) CUDA_TRY(cudaFreeAsync(eq0, s));
@@ -426,7 +405,7 @@ int sumcheck_prove_coeffs(Ctx* c, const ScCoeffJob& job) {
     int rc = eq_build(c, job.eq_points[k], n, eq0 + (size_t)k * N);
     if (rc) return rc;
   }
-  sc_init_kernel<<<1, 32, 0, s>>>(c->d_sc, job.claim);
+  CUDA_TRY(launch_pdl(sc_init_kernel, dim3(1), dim3(32), 0, s, c->d_sc, job.claim));
   count_launch(c);
   ScCoeffArgs a;
   a.scalars = job.scalars;
@@ -453,9 +432,9 @@ int sumcheck_prove_coeffs(Ctx* c, const ScCoeffJob& job) {
     dim3 grid(blocks_for(a.pairs, K), K);
     if ((size_t)grid.x * grid.y * 2 > c->partial_elems) return B200_ERR_NOMEM;
     if (round == 0) {
-      CUDA_TRY(launch_pdl(sc_coeff_round_kernel<false>, grid, SC_THREADS, s, a));
+      CUDA_TRY(launch_pdl(sc_coeff_round_kernel<false>, grid, SC_THREADS, 0, s, a));
     } else {
-      CUDA_TRY(launch_pdl(sc_coeff_round_kernel<true>, grid, SC_THREADS, s, a));
+      CUDA_TRY(launch_pdl(sc_coeff_round_kernel<true>, grid, SC_THREADS, 0, s, a));
       for (int k = 0; k < K; ++k) {
         cur[k] = a.out[k];
         cur[K + k] = a.eq_out[k];
@@ -466,7 +445,7 @@ int sumcheck_prove_coeffs(Ctx* c, const ScCoeffJob& job) {
   const Fr** d_ptrs = nullptr;
   CUDA_TRY(cudaMallocAsync(&d_ptrs, K * sizeof(Fr*), s));
   CUDA_TRY(cudaMemcpyAsync(d_ptrs, cur, K * sizeof(Fr*), cudaMemcpyHostToDevice, s));
-  sc_final_bind_kernel<<<1, 64, 0, s>>>(d_ptrs, K, c->d_sc, job.evals_out);
+  CUDA_TRY(launch_pdl(sc_final_bind_kernel, dim3(1), dim3(64), 0, s, d_ptrs, K, c->d_sc, job.evals_out));
   count_launch(c);
   CUDA_TRY(cudaFreeAsync(d_ptrs, s));
   CUDA_TRY(cudaFreeAsync(eq0, s));
