@@ -546,6 +546,50 @@ def lookup_h_poly(ctx, num_vars, compressed_input, compressed_table, m, gamma):
     return h
 
 
+def prove_expression_native(ctx, num_vars, expression, polys, challenges, ys, claimed_sum):
+    """`ClassicSumCheck::<EvaluationsProver>::prove` for an arbitrary expression, compiled INSIDE the library
+    (b200_sumcheck_prove_expression): the expression crosses the boundary as prefix tokens. challenges: canonical
+    Python ints; ys: list of (num_vars, 4) Montgomery arrays. Returns (challenges, evals)."""
+    from .expression import serialize_expression
+
+    tokens, consts = serialize_expression(expression, [], [])
+    tokens = np.asarray(tokens, dtype=np.int32)
+    cm = _mont_consts(ctx, consts)
+    ch_in = _mont_consts(ctx, list(challenges))
+    ys_in = np.ascontiguousarray(np.concatenate([_fr(y).reshape(-1, 4) for y in ys])) if len(ys) else np.zeros((1, 4), dtype=np.uint64)
+    ptrs = (C.c_void_p * len(polys))(*[p.dev for p in polys])
+    ch = np.zeros((num_vars, 4), dtype=np.uint64)
+    ev = np.zeros((len(polys), 4), dtype=np.uint64)
+    _chk(lib().b200_sumcheck_prove_expression(ctx.h, C.c_int(num_vars), _p(tokens), C.c_int(len(tokens)), _p(cm),
+                                              C.c_int(len(consts)), ptrs, C.c_int(len(polys)), _p(ch_in),
+                                              C.c_int(len(challenges)), _p(ys_in), C.c_int(len(ys)), _p(_fr(claimed_sum)),
+                                              _p(ch), _p(ev)), "sumcheck_prove_expression")
+    return ch, ev
+
+
+def compile_expression_native(expression, const_mont):
+    """`b200_expression_compile` (host only, no GPU): -> (leaves [(kind, a, b)], consts (n, 4) uint64 Montgomery,
+    const_chal [challenge index or -1], ops [(opcode, dst, a, b)], ntemps, degree). const_mont: the expression's
+    constants (serialize_expression order) already in Montgomery form, (n, 4) uint64."""
+    from .expression import serialize_expression
+
+    tokens, consts = serialize_expression(expression, [], [])
+    tokens = np.asarray(tokens, dtype=np.int32)
+    cm = np.ascontiguousarray(const_mont, dtype=np.uint64).reshape(-1, 4) if len(consts) else np.zeros((1, 4), dtype=np.uint64)
+    assert cm.shape[0] >= len(consts)
+    cap = 4096
+    leaves = np.zeros((cap, 3), dtype=np.int32)
+    cout = np.zeros((cap, 4), dtype=np.uint64)
+    cchal = np.zeros(cap, dtype=np.int32)
+    ops = np.zeros((cap, 4), dtype=np.int32)
+    nl, nc, no, nt, deg = C.c_int(), C.c_int(), C.c_int(), C.c_int(), C.c_int()
+    _chk(lib().b200_expression_compile(_p(tokens), C.c_int(len(tokens)), _p(cm), C.c_int(len(consts)), _p(leaves),
+                                       C.c_int(cap), C.byref(nl), _p(cout), _p(cchal), C.c_int(cap), C.byref(nc), _p(ops),
+                                       C.c_int(cap), C.byref(no), C.byref(nt), C.byref(deg)), "expression_compile")
+    return ([tuple(int(v) for v in r) for r in leaves[: nl.value]], cout[: nc.value].copy(), [int(v) for v in cchal[: nc.value]],
+            [tuple(int(v) for v in r) for r in ops[: no.value]], nt.value, deg.value)
+
+
 def prove_expression(ctx, num_vars, expression, polys, challenges, ys, claimed_sum):
     """`ClassicSumCheck::<EvaluationsProver>::prove(num_vars, VirtualPolynomial::new(expression, polys, challenges,
     ys), sum, transcript)`. challenges: canonical Python ints; ys: list of (num_vars, 4) Montgomery arrays.

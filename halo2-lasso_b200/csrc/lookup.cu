@@ -184,6 +184,33 @@ int lookup_h(Ctx* c, int num_vars, const Fr* d_input, const Fr* d_table, const F
   return B200_OK;
 }
 
+// run a compiled program (device constants / ops) on every row
+int expression_rows_prog(Ctx* c, int num_vars, const Fr* const* tables, int ntables, const Fr* d_consts, int nconsts,
+                         const int4* d_ops, int nops, int ntemps, Fr* d_out) {
+  if (ntables < 1 || ntables > ROWS_MAX_TABLES || nops < 1 || ntemps < 1 || ntemps > 64) return B200_ERR_ARG;
+  RowsArgs a;
+  for (int i = 0; i < ntables; ++i) a.in[i] = tables[i];
+  a.consts = d_consts;
+  a.ops = d_ops;
+  a.K = ntables;
+  a.C = nconsts;
+  a.nops = nops;
+  a.out = d_out;
+  a.N = (size_t)1 << num_vars;
+  const int nslots = ntables + ntemps;
+  int nth = 128;
+  while (nth > 32 && (size_t)nslots * nth * sizeof(Fr) > 100 * 1024) nth -= 32;
+  const size_t smem_bytes = (size_t)nslots * nth * sizeof(Fr);
+  if (smem_bytes > 220 * 1024) return B200_ERR_ARG;
+  CUDA_TRY(cudaFuncSetAttribute(expr_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+  size_t blocks = (a.N + nth - 1) / nth;
+  if (blocks > 2 * NUM_SMS) blocks = 2 * NUM_SMS;
+  expr_rows_kernel<<<(unsigned)blocks, nth, smem_bytes, c->stream>>>(a);
+  count_launch(c);
+  CUDA_TRY(cudaGetLastError());
+  return B200_OK;
+}
+
 }  // namespace b200
 
 using namespace b200;
@@ -204,8 +231,6 @@ int b200_expression_rows(b200_ctx* h, int num_vars, int ntables, const void* con
   }
   for (int i = 0; i < nops; ++i)
     if (host_ops[4 * i + 2] > max_dst || host_ops[4 * i + 3] > max_dst) return B200_ERR_ARG;
-  const int ntemps = max_dst - lim + 1;
-  if (ntemps > 64) return B200_ERR_ARG;
   Fr* dconsts = nullptr;
   int4* dops = nullptr;
   CUDA_TRY(cudaMallocAsync(&dconsts, ((size_t)nconsts + 1) * sizeof(Fr), c->stream));
@@ -213,29 +238,11 @@ int b200_expression_rows(b200_ctx* h, int num_vars, int ntables, const void* con
   if (nconsts)
     CUDA_TRY(cudaMemcpyAsync(dconsts, host_consts_fr, (size_t)nconsts * sizeof(Fr), cudaMemcpyHostToDevice, c->stream));
   CUDA_TRY(cudaMemcpyAsync(dops, host_ops, (size_t)nops * sizeof(int4), cudaMemcpyHostToDevice, c->stream));
-  RowsArgs a;
-  for (int i = 0; i < ntables; ++i) a.in[i] = (const Fr*)dev_tables[i];
-  a.consts = dconsts;
-  a.ops = dops;
-  a.K = ntables;
-  a.C = nconsts;
-  a.nops = nops;
-  a.out = (Fr*)dev_out;
-  a.N = (size_t)1 << num_vars;
-  const int nslots = ntables + ntemps;
-  int nth = 128;
-  while (nth > 32 && (size_t)nslots * nth * sizeof(Fr) > 100 * 1024) nth -= 32;
-  const size_t smem_bytes = (size_t)nslots * nth * sizeof(Fr);
-  if (smem_bytes > 220 * 1024) return B200_ERR_ARG;
-  CUDA_TRY(cudaFuncSetAttribute(expr_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
-  size_t blocks = (a.N + nth - 1) / nth;
-  if (blocks > 2 * NUM_SMS) blocks = 2 * NUM_SMS;
-  expr_rows_kernel<<<(unsigned)blocks, nth, smem_bytes, c->stream>>>(a);
-  count_launch(c);
+  const int rc = expression_rows_prog(c, num_vars, (const Fr* const*)dev_tables, ntables, dconsts, nconsts, dops, nops,
+                                      max_dst - lim + 1, (Fr*)dev_out);
   CUDA_TRY(cudaFreeAsync(dconsts, c->stream));
   CUDA_TRY(cudaFreeAsync(dops, c->stream));
-  CUDA_TRY(cudaGetLastError());
-  return B200_OK;
+  return rc;
 }
 
 int b200_lookup_m(b200_ctx* h, int num_vars, const void* dev_input, const void* dev_table, void* dev_m_out) {

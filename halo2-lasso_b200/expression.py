@@ -181,6 +181,48 @@ class Expression:
         return out
 
 
+def serialize_expression(expr, tokens, consts):
+    """Append the prefix-token form of `expr` (include/b200_lasso.h, b200_sumcheck_prove_expression) to `tokens`;
+    constants are appended to `consts` as canonical ints."""
+
+    def const_idx(v):
+        consts.append(v % R_MOD)
+        return len(consts) - 1
+
+    def walk(n):
+        k = n[0]
+        if k == "const":
+            tokens.extend([0, const_idx(n[1])])
+        elif k == "identity":
+            tokens.append(1)
+        elif k == "lagrange":
+            tokens.extend([2, n[1]])
+        elif k == "eq":
+            tokens.extend([3, n[1]])
+        elif k == "poly":
+            tokens.extend([4, n[1], n[2]])
+        elif k == "chal":
+            tokens.extend([5, n[1]])
+        elif k == "neg":
+            tokens.append(6)
+            walk(n[1])
+        elif k in ("sum", "prod"):
+            tokens.append(7 if k == "sum" else 8)
+            walk(n[1])
+            walk(n[2])
+        elif k == "scaled":
+            tokens.extend([9, const_idx(n[2])])
+            walk(n[1])
+        else:  # dpow
+            tokens.extend([10, len(n[1])])
+            for c in n[1]:
+                walk(c)
+            walk(n[2])
+
+    walk(expr.node)
+    return tokens, consts
+
+
 def product(exprs):
     exprs = list(exprs)
     acc = exprs[0]

@@ -1,7 +1,7 @@
-"""Host orchestration of `HyperPlonk::{preprocess, prove}` (pb/backend/hyperplonk.rs:97-291) over the GPU
-primitives, for circuits without lookups (the snapshot's LogUp branch is empty when `lookups` is empty,
-prover.rs:56-58): instance polys, batch commits, permutation grand product, zero check with the generic
-expression kernel, rotated evaluations, additive batch opening. Mirrors
+"""Host mirror of `HyperPlonk::{preprocess, prove}` (pb/backend/hyperplonk.rs:97-291): circuit descriptions, the
+reference's test-circuit fixtures and the binding of the library's HyperPlonk prover (csrc/hyperplonk.cu, which holds
+the orchestration: instance polys, batch commits, LogUp m/h polys, permutation grand product, zero check with the
+generic expression kernel, rotated evaluations, additive batch opening). Mirrors
 
     PlonkishCircuitInfo            pb/backend.rs:46-73               -> VanillaPlonkCircuitInfo
     rand_vanilla_plonk_circuit     pb/backend/hyperplonk/util.rs:100-190 (own satisfiable fixture, same shape)
@@ -18,9 +18,8 @@ import random
 
 import numpy as np
 
-from . import (Keccak256Transcript, MultilinearPolynomial, _chk, _fr, _p, evaluate_many, expression_rows, lib,
-               lookup_h_poly, lookup_m_poly, prove_expression)
-from .expression import BooleanHypercube, Expression, R_MOD, compose
+from . import MultilinearPolynomial, _chk, _mont_consts, _p, lib
+from .expression import BooleanHypercube, Expression, R_MOD, serialize_expression
 
 R_INV = pow(1 << 256, -1, R_MOD)
 
@@ -222,7 +221,9 @@ def rotation_eval_points(x, rotation):
 
 
 class HyperPlonk:
-    """`HyperPlonk<MultilinearKzg<Bn256>>` prover (vanilla plonk, with or without the LogUp lookup argument)."""
+    """`HyperPlonk<MultilinearKzg<Bn256>>` prover (vanilla plonk, with or without the LogUp lookup argument): a thin
+    binding of `b200_hyperplonk_preprocess` / `b200_hyperplonk_prove` — the orchestration (hyperplonk.rs:97-291) runs
+    inside the library (csrc/hyperplonk.cu), the circuit crosses the boundary as prefix-token expressions."""
 
     def __init__(self, ctx, kzg, info):
         """preprocess (hyperplonk.rs:97-162): commit the preprocess and permutation polynomials, compose the
@@ -230,78 +231,61 @@ class HyperPlonk:
         self.ctx, self.kzg, self.info = ctx, kzg, info
         k = info.k
         self.preprocess = [upload_ints(ctx, p) for p in info.preprocess_polys]
-        self.preprocess_comms = kzg.batch_commit(self.preprocess)
-        self.perm_ints = permutation_polys(k, info.permutation_polys, info.permutations)
-        self.perm = [upload_ints(ctx, p) for p in self.perm_ints]
-        self.permutation_comms = kzg.batch_commit(self.perm)
-        self.num_z, self.expression = compose(k, info.constraints, info.num_poly, info.permutation_polys,
-                                              lookups=info.lookups)
-        assert self.num_z == 1
+        ctok, ltok, consts = [], [], []
+        for c in info.constraints:
+            serialize_expression(c, ctok, consts)
+        for lookup in info.lookups:
+            ltok.append(len(lookup))
+            for a, t in lookup:
+                serialize_expression(a, ltok, consts)
+                serialize_expression(t, ltok, consts)
+        cm = _mont_consts(ctx, consts)
+        flat = []
+        for cyc in info.permutations:
+            flat.append(len(cyc))
+            for (p, r) in cyc:
+                flat += [p, r]
+        ctok = np.asarray(ctok, dtype=np.int32)
+        ltok = np.asarray(ltok if ltok else [0], dtype=np.int32)
+        flat = np.asarray(flat if flat else [0], dtype=np.int32)
+        pidx = np.asarray(info.permutation_polys, dtype=np.int32)
+        pre = (C.c_void_p * max(1, len(self.preprocess)))(*[p.dev for p in self.preprocess])
+        self.h = C.c_void_p()
+        _chk(lib().b200_hyperplonk_preprocess(
+            ctx.h, C.c_int(k), C.c_int(info.num_instances), C.c_int(info.num_witness_polys), C.c_int(len(self.preprocess)),
+            pre, C.c_int(len(info.constraints)), _p(ctok), C.c_int(len(ctok)), C.c_int(len(info.lookups)), _p(ltok),
+            C.c_int(len(ltok) if info.lookups else 0), _p(cm), C.c_int(len(consts)), C.c_int(len(pidx)), _p(pidx),
+            C.c_int(len(info.permutations)), _p(flat), C.c_int(getattr(info, "max_degree", 4)), C.byref(self.h)),
+            "hyperplonk_preprocess")
+        nz, deg, npolys = C.c_int(), C.c_int(), C.c_int()
+        _chk(lib().b200_hyperplonk_info(self.h, C.byref(nz), C.byref(deg), C.byref(npolys)), "hyperplonk_info")
+        self.num_z, self.degree, self.num_polys = nz.value, deg.value, npolys.value
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None) and self.ctx.h:
+                lib().b200_hyperplonk_free(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    def commitments(self):
+        """(preprocess_comms, permutation_comms): the verifier parameters (hyperplonk.rs:127-150)"""
+        a = np.zeros((max(1, len(self.preprocess)), 8), dtype=np.uint64)
+        b = np.zeros((max(1, len(self.info.permutation_polys)), 8), dtype=np.uint64)
+        _chk(lib().b200_hyperplonk_commitments(self.h, _p(a), _p(b)), "hyperplonk_commitments")
+        return a[: len(self.preprocess)], b[: len(self.info.permutation_polys)]
+
+    def permutation_poly(self, i):
+        out = np.zeros((1 << self.info.k, 4), dtype=np.uint64)
+        _chk(lib().b200_hyperplonk_permutation_poly(self.h, C.c_int(i), _p(out)), "hyperplonk_permutation_poly")
+        return out
 
     def prove(self, instances, witness_ints=None, witness_polys=None):
         """hyperplonk.rs:164-291; appends to the context transcript (create a Keccak256Transcript first)."""
-        ctx, kzg, info, k = self.ctx, self.kzg, self.info, self.info.k
-        tr = Keccak256Transcript.__new__(Keccak256Transcript)
-        tr.ctx = ctx
-        inst_mont = ints_to_mont(ctx, instances)
-        tr.common_field_elements(inst_mont)
-        # instance_polys (prover.rs:32-48): instance i sits on row bh[i+1]
-        order = BooleanHypercube(k)
-        raw = np.zeros((1 << k, 4), dtype=np.uint64)
-        b = 1
-        for row in ints_to_raw(instances):
-            raw[b] = row
-            b = order.next(b)
-        inst_poly = MultilinearPolynomial.new(ctx, raw)
-        _chk(lib().b200_fr_convert(ctx.h, inst_poly.dev, inst_poly.dev, C.c_uint64(1 << k), C.c_int(1)), "fr_convert")
+        ctx = self.ctx
+        inst = ints_to_mont(ctx, instances) if len(instances) else np.zeros((1, 4), dtype=np.uint64)
         wit = witness_polys if witness_polys is not None else [upload_ints(ctx, w) for w in witness_ints]
-        kzg.batch_commit_and_write(wit)
-        polys = [inst_poly] + self.preprocess + wit
-        # LogUp (prover.rs:50-250): compressed input/table polys, multiplicities m, then h once gamma is known
-        beta = tr.squeeze_challenge()
-        compressed, ms = [], []
-        for lookup in info.lookups:
-            b_ = Expression.challenge(0)
-            ci = expression_rows(ctx, k, Expression.distribute_powers([a for a, _ in lookup], b_), polys, [mont_to_int(beta)])
-            ct = expression_rows(ctx, k, Expression.distribute_powers([t for _, t in lookup], b_), polys, [mont_to_int(beta)])
-            compressed.append((ci, ct))
-            ms.append(lookup_m_poly(ctx, k, ci, ct))
-        if ms:
-            kzg.batch_commit_and_write(ms)
-        gamma = tr.squeeze_challenge()
-        hs = [lookup_h_poly(ctx, k, ci, ct, m, gamma) for (ci, ct), m in zip(compressed, ms)]
-        # permutation_z_polys (prover.rs:252-345)
-        z = MultilinearPolynomial.alloc(ctx, k)
-        nper = len(info.permutation_polys)
-        wires = (C.c_void_p * nper)(*[wit[p - (info.num_poly - info.num_witness_polys)].dev for p in info.permutation_polys])
-        sig = (C.c_void_p * nper)(*[p.dev for p in self.perm])
-        offs = (C.c_uint64 * nper)(*[i << k for i in range(nper)])
-        bg = np.ascontiguousarray(np.stack([beta, gamma]))
-        _chk(lib().b200_permutation_z(ctx.h, C.c_int(k), C.c_int(nper), wires, sig, offs, _p(bg), z.dev), "permutation_z")
-        kzg.batch_commit_and_write(hs + [z])
-        alpha = tr.squeeze_challenge()
-        y = tr.squeeze_challenges(k)
-        polys = polys + self.perm + ms + hs + [z]
-        challenges = [mont_to_int(c) for c in (beta, gamma, alpha)]
-        zero = np.zeros(4, dtype=np.uint64)
-        x, evals = prove_expression(ctx, k, self.expression, polys, challenges, [y], zero)
-        # prove_sum_check tail (prover.rs:388-409): evaluations per pcs_query, rotated ones at rotation_eval_points
-        queries = sorted({(l[1], l[2]) for l in self.expression.leaves() if l[0] == "poly" and l[1] >= 1})
-        rotations = sorted({r for _, r in queries})
-        x_int = [mont_to_int(v) for v in x]
-        points_int, offset = [], {}
-        for r in rotations:
-            offset[r] = len(points_int)
-            points_int += rotation_eval_points(x_int, r)
-        points = [x if r == 0 and i == 0 else None for r in rotations for i in range(1 << abs(r))]
-        pts_mont = ints_to_mont(ctx, [v for p in points_int for v in p]).reshape(len(points_int), k, 4)
-        points = [pts_mont[i] for i in range(len(points_int))]
-        ev_list = []
-        for (p, r) in queries:
-            if r == 0:
-                ev_list.append((p, offset[0], evals[p]))
-            else:
-                for j in range(1 << abs(r)):
-                    ev_list.append((p, offset[r] + j, evaluate_many(ctx, [polys[p]], points[offset[r] + j])[0]))
-        tr.write_field_elements(np.stack([e[2] for e in ev_list]))
-        kzg.batch_open(polys, points, ev_list)
+        ptrs = (C.c_void_p * len(wit))(*[p.dev for p in wit])
+        _chk(lib().b200_hyperplonk_prove(self.h, _p(np.ascontiguousarray(inst)), C.c_int(len(instances)), ptrs),
+             "hyperplonk_prove")

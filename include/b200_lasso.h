@@ -118,6 +118,47 @@ int b200_poly_iota(b200_ctx* ctx, int num_vars, void* dev_out);
 int b200_poly_onehot(b200_ctx* ctx, int num_vars, uint64_t index, void* dev_out);
 int b200_poly_rotate(b200_ctx* ctx, const void* dev_in, int num_vars, int rotation, void* dev_out);
 
+/* The same `SumCheck::prove`, with the expression itself crossing the boundary (what a `VirtualPolynomial` holds,
+ * pb/piop/sum_check.rs:16-37) as prefix tokens (int32): 0 Constant(const_idx) | 1 Identity | 2 Lagrange(i) |
+ * 3 EqXY(idx) | 4 Polynomial(poly, rotation) | 5 Challenge(idx) | 6 Negated e | 7 Sum a b | 8 Product a b |
+ * 9 Scaled(const_idx) e | 10 DistributePowers(n) e_1..e_n base; consts_fr = Montgomery constants. The library
+ * compiles it (the ExpressionRegistry role, pb/util/expression/evaluator.rs:22-228), materialises the leaf tables
+ * and runs the generic round kernels. host_ys = nys points of num_vars elements; host_evals_out[npolys] = every
+ * polynomial bound at the challenges (classic.rs:143-149). */
+int b200_sumcheck_prove_expression(b200_ctx* ctx, int num_vars, const int32_t* tokens, int ntokens,
+                                   const void* consts_fr, int nconsts, const void* const* dev_polys, int npolys,
+                                   const void* host_challenges, int nchallenges, const void* host_ys, int nys,
+                                   const void* host_sum, void* host_challenges_out, void* host_evals_out);
+/* The compiler alone (host only, needs no GPU): leaves_out = (kind, a, b) triples in table order, consts_out /
+ * const_chal_out = constant values and, where >= 0, the challenge index a constant stands for, ops_out =
+ * (opcode, dst, a, b) quadruples over the slots [leaves | constants | temporaries]. */
+int b200_expression_compile(const int32_t* tokens, int ntokens, const void* consts_fr, int nconsts, int32_t* leaves_out,
+                            int leaves_cap, int* nleaves, void* consts_out, int32_t* const_chal_out, int consts_cap,
+                            int* nconsts_out, int32_t* ops_out, int ops_cap, int* nops, int* ntemps, int* degree);
+
+/* ---- HyperPlonk (pb/backend/hyperplonk.rs:97-291) ------------------------------------------------
+ * preprocess: PlonkishCircuitInfo (pb/backend.rs:46-73) -> prover parameters. Polynomial order as in the reference:
+ * instance (one polynomial) | preprocess | witness | permutation | lookup m | lookup h | permutation z.
+ * dev_preprocess: device polynomials (borrowed: keep them alive); constraints: `nconstraints` expressions back to
+ * back in the token format above; lookups: per lookup [width, input_0, table_0, input_1, table_1, ...];
+ * cycles_flat: per copy cycle [len, poly, row, poly, row, ...] (preprocessor.rs:172-203). Commits the preprocess and
+ * permutation polynomials with the SRS of the context and composes the zero-check expression (preprocessor.rs:25-170).
+ * prove: instances as Montgomery field elements, witness polynomials on the device; appends the proof to the context
+ * transcript. B200_ERR_LOOKUP = Error::InvalidSnark("Invalid lookup input"). */
+typedef struct b200_hyperplonk b200_hyperplonk;
+int b200_hyperplonk_preprocess(b200_ctx* ctx, int k, int num_instances, int num_witness_polys, int npreprocess,
+                               const void* const* dev_preprocess, int nconstraints, const int32_t* constraint_tokens,
+                               int nconstraint_tokens, int nlookups, const int32_t* lookup_tokens, int nlookup_tokens,
+                               const void* consts_fr, int nconsts, int nperm, const int32_t* permutation_polys,
+                               int ncycles, const int32_t* cycles_flat, int max_degree, b200_hyperplonk** out);
+void b200_hyperplonk_free(b200_hyperplonk* pp);
+int b200_hyperplonk_info(const b200_hyperplonk* pp, int* num_permutation_z_polys, int* degree, int* num_polys);
+/* verifier parameters: preprocess_out[npreprocess], permutation_out[nperm] affine commitments */
+int b200_hyperplonk_commitments(const b200_hyperplonk* pp, void* preprocess_out, void* permutation_out);
+int b200_hyperplonk_permutation_poly(const b200_hyperplonk* pp, int i, void* host_out);
+int b200_hyperplonk_prove(b200_hyperplonk* pp, const void* host_instances_fr, int ninstances,
+                          const void* const* dev_witness);
+
 /* permutation_z_polys (pb/backend/hyperplonk/prover.rs:252-345) for one chunk of `npolys` wire columns:
  * grand-product polynomial z in BooleanHypercube order; id_offsets[i] = (index of wire i among the permuted
  * columns) << num_vars; host_beta_gamma = {beta, gamma}. dev_z_out[2^num_vars]. */

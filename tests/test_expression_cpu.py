@@ -93,6 +93,43 @@ def test_compiled_program_equals_tree_evaluation():
     assert len(prog) < 60
 
 
+def test_native_compiler_program_equals_tree_evaluation():
+    """The library's own compiler (csrc/expr.hpp through b200_expression_compile, host code: runs without a GPU) on
+    the vanilla-plonk and plonk-with-lookup zero-check expressions and on a small expression with every node kind:
+    interpreting its program over random leaf values gives the value of the expression tree."""
+    import halo2_lasso_b200 as hl
+    from halo2_lasso_b200 import hyperplonk as H
+    from halo2_lasso_b200.expression import compose, serialize_expression
+
+    R = 1 << 256
+    rinv = pow(R, -1, R_MOD)
+    kinds = {1: "identity", 2: "lagrange", 3: "eq", 4: "poly"}
+
+    def to_limbs(v):
+        return [(v >> (64 * j)) & 0xFFFFFFFFFFFFFFFF for j in range(4)]
+
+    info, _, _ = H.rand_vanilla_plonk_with_lookup_circuit(4, 1)
+    _, lookup_expr = compose(4, info.constraints, info.num_poly, info.permutation_polys, lookups=info.lookups)
+    misc = (E.polynomial(0) * E.polynomial(1, 1) - E.identity() * E.lagrange(-1) + E.challenge(1) * 7
+            + E.distribute_powers([E.polynomial(2), -E.polynomial(0), E.constant(5)], E.challenge(0)) + E.eq_xy(1))
+    rng = random.Random(2)
+    for expr, nleaves in ((vanilla_plonk_expression(4), 17), (lookup_expr, 23), (misc, 6), (E.polynomial(3), 1)):
+        _, consts = serialize_expression(expr, [], [])
+        cm = np.asarray([to_limbs(c * R % R_MOD) for c in consts] or [[0, 0, 0, 0]], dtype=np.uint64)
+        leaves, cvals, cchal, ops, ntemps, degree = hl.compile_expression_native(expr, cm)
+        assert degree == expr.degree() and len(leaves) == nleaves
+        py_leaves = [(kinds[k],) if k == 1 else ((kinds[k], a) if k in (2, 3) else (kinds[k], a, b)) for k, a, b in leaves]
+        assert py_leaves == expr.leaves()
+        ch = [rng.randrange(R_MOD) for _ in range(3)]
+        cints = [ch[j] if j >= 0 else sum(int(x) << (64 * i) for i, x in enumerate(v)) * rinv % R_MOD
+                 for v, j in zip(cvals, cchal)]
+        K, C_ = len(leaves), len(cints)
+        assert max(d for _, d, _, _ in ops) - (K + C_) + 1 == ntemps and ntemps <= 8
+        for _ in range(10):
+            lv = {l: rng.randrange(R_MOD) for l in py_leaves}
+            assert run_program(py_leaves, cints, ops, lv) == eval_tree(expr.node, lv, ch)
+
+
 def test_generic_oracle_agrees_with_fixed_shape_oracle():
     n = 6
     a, b, y = O.rand_fr(1, 1 << n), O.rand_fr(2, 1 << n), O.rand_fr(3, n)

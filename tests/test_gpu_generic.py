@@ -32,13 +32,16 @@ def _run(hl, ctx, n, expr, npolys, nch, seed):
     to = O.Transcript()
     ch_o, ev_o, deg = O.sumcheck_prove_generic(to, n, expr, polys, ch, [y], claim)
     assert deg == expr.degree()
-    tr = hl.Keccak256Transcript(ctx)
     dps = [hl.MultilinearPolynomial.new(ctx, p) for p in polys]
-    got_ch, got_ev = hl.prove_expression(ctx, n, expr, dps, O.fr_to_ints(ch) if nch else [], [y], claim)
-    proof = tr.into_proof()
-    assert len(proof) == n * (deg + 1) * 32
-    assert proof == to.proof()
-    assert (got_ch == ch_o).all() and (got_ev == ev_o).all()
+    # both entry points: the expression compiled inside the library (tokens cross the C ABI) and the bytecode-level
+    # call fed by the Python mirror of the compiler
+    for prove in (hl.prove_expression_native, hl.prove_expression):
+        tr = hl.Keccak256Transcript(ctx)
+        got_ch, got_ev = prove(ctx, n, expr, dps, O.fr_to_ints(ch) if nch else [], [y], claim)
+        proof = tr.into_proof()
+        assert len(proof) == n * (deg + 1) * 32
+        assert proof == to.proof(), prove.__name__
+        assert (got_ch == ch_o).all() and (got_ev == ev_o).all(), prove.__name__
 
 
 @pytest.mark.parametrize("n", [2, 3, 6, 11])

@@ -58,6 +58,13 @@ def test_hyperplonk_proof_parity_and_verifies(hl, env, k):
     to = O.Transcript()
     assert ohp.prove(to, inst, [O.fr_from_ints(c) for c in w])
     hp = H.HyperPlonk(ctx, kzg, info)
+    # preprocess: permutation polynomials and the verifier's commitments (hyperplonk.rs:127-150)
+    assert (hp.num_z, hp.degree, hp.num_polys) == (1, 5, 13)
+    for i in range(3):
+        assert (hp.permutation_poly(i) == ohp.permutation_poly(i)).all()
+    pre_c, perm_c = hp.commitments()
+    assert (pre_c == np.stack([okzg.commit(O.fr_from_ints(p)) for p in info.preprocess_polys])).all()
+    assert (perm_c == np.stack([okzg.commit(ohp.permutation_poly(i)) for i in range(3)])).all()
     tr = hl.Keccak256Transcript(ctx)
     hp.prove(instances, witness_ints=w)
     proof = tr.into_proof()
