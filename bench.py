@@ -263,6 +263,19 @@ def main():
             hl.Keccak256Transcript(ctx)
             prover.prove_dev(MU, xs_shared.data_ptr())
 
+    # the reference's own `zero_check` criterion bench shape (plonkish_backend/benches/zero_check.rs): generic
+    # EvaluationsProver on vanilla_plonk_expression, n = 20, expression compiled inside the library
+    from halo2_lasso_b200.expression import vanilla_plonk_expression
+
+    zc_expr = vanilla_plonk_expression(SC_VARS)
+    zc_polys = [to_mont(rand_canonical(100 + i + 20 * rank, N)) for i in range(13)]
+    zc_ch = [int(x) for x in rand_canonical(7, 3)[:, 0]]
+    zc_zero = np.zeros(4, dtype=np.uint64)
+
+    def zero_check_device():
+        hl.Keccak256Transcript(ctx)
+        hl.prove_expression_native(ctx, n, zc_expr, zc_polys, zc_ch, [y], zc_zero)
+
     sampler = ClockSampler(local_rank)
     sampler.start()
     ctx.launch_count(reset=True)
@@ -271,6 +284,7 @@ def main():
     ms_e2e = timed(lasso_e2e, max(3, args.steps // 2), 3)
     ms_sc = timed(sumcheck_device, 20, 5)
     ms_sh = timed(sharded[1], 20, 5) if sharded else 0.0
+    ms_zc = timed(zero_check_device, 5, 3)
     ms_co = 0.0
     if sharded:
         hl.dist_shard_commits(ctx, True)
@@ -311,6 +325,13 @@ def main():
     if prof:
         roof.update(prof)
         roof["frac"] = roof["achieved"] / peak
+        # the same launch against the bound that actually limits it: Montgomery products on the IMAD (fmaheavy) pipe.
+        # Round 1 of cfg2 = 2^(n-2) output pairs x (6 binding + 6 evaluation products). Peak: msm_accumulate sustains
+        # 50 G products/s at 86 % fmaheavy-pipe utilisation (profiles/), i.e. ~58 G/s at 100 %.
+        prods = 12 * (1 << (SC_VARS - 2))
+        roof["imad"] = {"products_per_launch": prods, "achieved_gproducts_s": prods / (roof["launch_ms"] * 1e-3) / 1e9,
+                        "peak_gproducts_s": 58.0, "frac": prods / (roof["launch_ms"] * 1e-3) / 1e9 / 58.0,
+                        "note": "IMAD-bound kernel; launch time includes the ~29 us single-warp Fiat-Shamir tail"}
     # per-launch DRAM traffic of that kernel from the committed `ncu --set full` capture (profiles/), if present
     try:
         roof["traffic"] = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))["dram_bytes_per_launch"]
@@ -340,6 +361,9 @@ def main():
         "sumcheck": {"workload": "cfg2: ClassicSumCheck deg-3 eq*a*b, n=20, 2560 proof bytes", "ms_per_proof": ms_sc,
                      "algorithmic_bytes": SC_ALGO_BYTES, "GBps": world * SC_ALGO_BYTES / (ms_sc * 1e-3) / 1e9,
                      "frac_of_hbm_peak": SC_ALGO_BYTES / (ms_sc * 1e-3) / 1e9 / peak},
+        "zero_check": {"workload": "reference zero_check bench shape: vanilla_plonk_expression (17 tables, degree 5), n=20, "
+                       "generic bytecode kernels, through b200_sumcheck_prove_expression (host call, includes its "
+                       "small H2D/D2H)", "ms_per_proof": ms_zc},
         "sumcheck_sharded": None if not sharded else {
             "workload": f"cfg2 shape sharded on the top {world.bit_length() - 1} variable(s): n={sharded[0]}, 2^20 entries per GPU, "
                         "per-round partials exchanged inside the kernel over NVLink peer memory",
