@@ -20,7 +20,8 @@
 
 namespace b200 {
 
-static const int TASK_LEN = 64;
+static const int TASK_LEN = 64;       // minimum task length; a batch uses a power of two in [64, 1024] so that an
+                                      // average bucket splits into ~8 tasks (keeps the per-bucket reduction short at 2^22+)
 static const int SEQ_TASKS = 8;     // buckets with more task partials than this go to the warp kernel
 static const int GROUP = 16;       // buckets per thread in the window reduction
 static const int MSM_MAX_JOBS = 64;
@@ -43,6 +44,7 @@ struct MsmJobDev {
 };
 struct MsmPlanDev {
   int J;
+  uint32_t task_len;
   MsmJobDev job[MSM_MAX_JOBS];
 };
 
@@ -163,7 +165,7 @@ __global__ void __launch_bounds__(256) scan_local_kernel(const uint32_t* __restr
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
     uint32_t x = base + k < n ? in[base + k] : 0;
-    if (op_tasks) x = (x + TASK_LEN - 1) / TASK_LEN;  // task count of a bucket population
+    if (op_tasks) x = (x + op_tasks - 1) / op_tasks;  // task count of a bucket population (op_tasks = task length)
     v[k] = x;
   }
   uint32_t tsum = v[0] + v[1] + v[2] + v[3];
@@ -281,9 +283,9 @@ __global__ void __launch_bounds__(128) msm_accumulate_kernel(MsmPlanDev plan, ui
     // buckets with zero tasks share their offset with the next one: take the LAST bucket whose offset <= task
     uint32_t gb = upper_bound_u32(toff, nbuckets + 1, task);
     const MsmJobDev& jb = plan.job[job_of_bucket(plan, gb)];
-    const uint32_t first = boff[gb] + (task - toff[gb]) * TASK_LEN;
+    const uint32_t first = boff[gb] + (task - toff[gb]) * plan.task_len;
     const uint32_t end_b = boff[gb] + cnt[gb];
-    const uint32_t last = first + TASK_LEN < end_b ? first + TASK_LEN : end_b;
+    const uint32_t last = first + plan.task_len < end_b ? first + plan.task_len : end_b;
     G1Xyzz acc = g1_identity();
     for (uint32_t k = first; k < last; ++k) {
       const uint32_t v = sorted[k];
@@ -468,7 +470,10 @@ int msm_batch(Ctx* c, const MsmJob* jobs, int J, G1Aff* d_out) {
     if (jb.n > max_n) max_n = jb.n;
   }
   if (pairs >= (1ull << 31)) return B200_ERR_ARG;
-  const uint32_t max_tasks = nbuckets + (uint32_t)(pairs / TASK_LEN) + 1;
+  uint32_t task_len = TASK_LEN;
+  while (task_len < 1024 && (uint64_t)task_len * 8 * nbuckets < pairs) task_len <<= 1;
+  plan.task_len = task_len;
+  const uint32_t max_tasks = nbuckets + (uint32_t)(pairs / task_len) + 1;
   const uint32_t scan_blocks = (nbuckets + 1023) / 1024;
 
   uint32_t *cnt, *boff, *toff, *ranks, *sorted, *scratch, *heavy, *heavy_count;
@@ -494,7 +499,7 @@ int msm_batch(Ctx* c, const MsmJob* jobs, int J, G1Aff* d_out) {
   count_launch(c);
   int rc = exclusive_scan(c, cnt, nbuckets, boff, scratch, 0);
   if (rc) return rc;
-  rc = exclusive_scan(c, cnt, nbuckets, toff, scratch, 1);
+  rc = exclusive_scan(c, cnt, nbuckets, toff, scratch, (int)task_len);
   if (rc) return rc;
   msm_digits_kernel<1><<<grid, 256, 0, s>>>(plan, nullptr, boff, ranks, sorted);
   prof_end(c, pi);
