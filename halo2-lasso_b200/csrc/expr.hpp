@@ -409,7 +409,7 @@ inline int e_permutation_constraints(int num_vars, int num_poly, const std::vect
 // circuit's own `num_challenges`.
 inline ExprP e_compose(int num_vars, const std::vector<ExprP>& constraints, int num_poly,
                        const std::vector<int>& permutation_polys, int num_challenges, int max_degree,
-                       const std::vector<LookupCols>& lookups, int* num_z) {
+                       const std::vector<LookupCols>& lookups, int* num_z, int* chunk_size = nullptr) {
   const ExprP beta = e_chal(num_challenges), gamma = e_chal(num_challenges + 1), alpha = e_chal(num_challenges + 2);
   std::vector<ExprP> lookup_cons, lookup_sums;
   e_lookup_constraints(lookups, num_poly, (int)permutation_polys.size(), beta, gamma, &lookup_cons, &lookup_sums);
@@ -417,6 +417,7 @@ inline ExprP e_compose(int num_vars, const std::vector<ExprP>& constraints, int 
   for (auto& c : constraints) md = std::max(md, e_degree(c));
   for (auto& c : lookup_cons) md = std::max(md, e_degree(c));
   std::vector<ExprP> perm;
+  if (chunk_size) *chunk_size = md - 1;
   *num_z = e_permutation_constraints(num_vars, num_poly, permutation_polys, md, beta, gamma, 2 * (int)lookups.size(), &perm);
   std::vector<ExprP> all(constraints);
   all.insert(all.end(), lookup_cons.begin(), lookup_cons.end());

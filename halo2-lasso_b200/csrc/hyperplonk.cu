@@ -231,7 +231,7 @@ static int expression_rows(Ctx* c, int num_vars, const ExprP& expr, const Fr* co
 
 struct HyperPlonk {
   Ctx* c;
-  int k, num_instances, num_witness, num_poly, num_z;
+  int k, num_instances, num_witness, num_poly, num_z, chunk_size;
   std::vector<const Fr*> preprocess;  // device, borrowed from the caller
   std::vector<int> perm_idx;
   std::vector<Fr*> perm;              // device, owned
@@ -361,8 +361,8 @@ int b200_hyperplonk_preprocess(b200_ctx* h, int k, int num_instances, int num_wi
     }
     hp.lookups.push_back(cols);
   }
-  hp.expression = e_compose(k, constraints, hp.num_poly, hp.perm_idx, 0, max_degree, hp.lookups, &hp.num_z);
-  if (hp.num_z > 1) return fail(B200_ERR_ARG);  // one permutation chunk (b200_permutation_z builds one z polynomial)
+  hp.expression = e_compose(k, constraints, hp.num_poly, hp.perm_idx, 0, max_degree, hp.lookups, &hp.num_z, &hp.chunk_size);
+  if (hp.num_z > 8 || hp.chunk_size > 8) return fail(B200_ERR_ARG);
   // permutation_polys (preprocessor.rs:172-203): identity (i << k) + j, then every cycle rotated by one
   std::vector<std::vector<uint64_t>> perms(nperm, std::vector<uint64_t>(N));
   std::map<int, int> index;
@@ -526,10 +526,12 @@ int b200_hyperplonk_prove(b200_hyperplonk* obj, const void* host_instances_fr, i
     if (rc) return rc;
   }
   std::vector<const Fr*> hz(hs.begin(), hs.end());
-  Fr* z = nullptr;
   if (hp.num_z) {
-    z = ar.alloc<Fr>(N);
-    if (!z) return B200_ERR_NOMEM;
+    std::vector<Fr*> zs(hp.num_z);
+    for (auto& z : zs) {
+      z = ar.alloc<Fr>(N);
+      if (!z) return B200_ERR_NOMEM;
+    }
     std::vector<const Fr*> wires(nper), sigmas(nper);
     std::vector<uint64_t> offs(nper);
     for (int i = 0; i < nper; ++i) {
@@ -537,9 +539,9 @@ int b200_hyperplonk_prove(b200_hyperplonk* obj, const void* host_instances_fr, i
       sigmas[i] = hp.perm[i];
       offs[i] = (uint64_t)i << k;
     }
-    rc = permutation_z(c, k, nper, wires.data(), sigmas.data(), offs.data(), d_ch, z);
+    rc = permutation_z_chunks(c, k, hp.num_z, hp.chunk_size, nper, wires.data(), sigmas.data(), offs.data(), d_ch, zs.data());
     if (rc) return rc;
-    hz.push_back(z);
+    for (Fr* z : zs) hz.push_back(z);
   }
   rc = commit_polys(c, hz, k, true, d_comms);
   if (rc) return rc;

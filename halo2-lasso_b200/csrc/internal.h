@@ -103,6 +103,9 @@ int poly_rotate(Ctx* c, const Fr* d_in, int num_vars, int rotation, Fr* d_out);
 // perm.cu — permutation_z_polys (prover.rs:252-345), one chunk
 int permutation_z(Ctx* c, int num_vars, int npolys, const Fr* const* wires, const Fr* const* sigmas,
                   const uint64_t* id_offsets, const Fr* d_beta_gamma, Fr* d_z);
+// all chunks: nz z polynomials, chunk zi = wire columns [zi * chunk_size, min(npolys, (zi + 1) * chunk_size))
+int permutation_z_chunks(Ctx* c, int num_vars, int nz, int chunk_size, int npolys, const Fr* const* wires,
+                         const Fr* const* sigmas, const uint64_t* id_offsets, const Fr* d_beta_gamma, Fr* const* d_z);
 
 // mle.cu
 int eq_build(Ctx* c, const Fr* d_y, int n, Fr* d_out);                         // eq_xy

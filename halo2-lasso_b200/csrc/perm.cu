@@ -74,15 +74,17 @@ __device__ __forceinline__ uint32_t gf_pow_x(uint64_t e, int n, uint32_t prim) {
 }
 
 // pass 1: product of `products` over the chunk's rows in LFSR order (positions start .. start+SCAN_CHUNK)
+// With nz > 1 z polynomials (prover.rs:308-323) the running product visits (row, z index) in lexicographic order:
+// products[zi * N + b] is the ratio of permutation chunk zi on row b.
 __global__ void __launch_bounds__(128) perm_chunk_prod_kernel(const Fr* __restrict__ products, int n, uint32_t prim,
-                                                              uint32_t nchunks, Fr* __restrict__ chunk_prod) {
+                                                              uint32_t nchunks, int nz, Fr* __restrict__ chunk_prod) {
   const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= nchunks) return;
   const uint64_t N = (uint64_t)1 << n, start = 1 + (uint64_t)c * SCAN_CHUNK;
   uint32_t b = gf_pow_x(start - 1, n, prim);
   Fr acc = fe_one<FrP>();
   for (uint64_t pos = start; pos < start + SCAN_CHUNK && pos < N; ++pos) {
-    acc = acc * fe_ldg(products + b);
+    for (int zi = 0; zi < nz; ++zi) acc = acc * fe_ldg(products + (size_t)zi * N + b);
     b = gf_next(b, n, prim);
   }
   fe_st(chunk_prod + c, acc);
@@ -109,55 +111,76 @@ __global__ void __launch_bounds__(1024) perm_scan_kernel(Fr* chunk_prod, uint32_
     run = run * v;
   }
 }
-// pass 3: z[bh[pos]] = running product before row pos
+// pass 3: z_zi[bh[pos]] = running product before (row pos, zi)
+struct PermZ {
+  Fr* z[PERM_MAX_POLYS];
+};
 __global__ void __launch_bounds__(128) perm_write_kernel(const Fr* __restrict__ products, int n, uint32_t prim,
-                                                         uint32_t nchunks, const Fr* __restrict__ chunk_excl,
-                                                         Fr* __restrict__ z) {
+                                                         uint32_t nchunks, int nz, const Fr* __restrict__ chunk_excl,
+                                                         PermZ out) {
   const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c == 0 && true) fe_st(z, fe_zero<FrP>());  // row 0 (position 0)
+  if (c == 0)
+    for (int zi = 0; zi < nz; ++zi) fe_st(out.z[zi], fe_zero<FrP>());  // row 0 (position 0)
   if (c >= nchunks) return;
   const uint64_t N = (uint64_t)1 << n, start = 1 + (uint64_t)c * SCAN_CHUNK;
   uint32_t b = gf_pow_x(start - 1, n, prim);
   Fr run = fe_ld(chunk_excl + c);
   for (uint64_t pos = start; pos < start + SCAN_CHUNK && pos < N; ++pos) {
-    fe_st(z + b, run);
-    run = run * fe_ldg(products + b);
+    for (int zi = 0; zi < nz; ++zi) {
+      fe_st(out.z[zi] + b, run);
+      run = run * fe_ldg(products + (size_t)zi * N + b);
+    }
     b = gf_next(b, n, prim);
   }
 }
 
-int permutation_z(Ctx* c, int num_vars, int npolys, const Fr* const* wires, const Fr* const* sigmas,
-                  const uint64_t* id_offsets, const Fr* d_beta_gamma, Fr* d_z) {
+// nz z polynomials; permutation chunk zi covers the wire columns [zi * chunk_size, min(npolys, (zi+1) * chunk_size))
+int permutation_z_chunks(Ctx* c, int num_vars, int nz, int chunk_size, int npolys, const Fr* const* wires,
+                         const Fr* const* sigmas, const uint64_t* id_offsets, const Fr* d_beta_gamma, Fr* const* d_z) {
   static const uint32_t PRIM[32] = {1, 3, 7, 11, 19, 37, 67, 131, 285, 529, 1033, 2053, 4179, 8219, 16427, 32771,
                                     65581, 131081, 262183, 524327, 1048585, 2097157, 4194307, 8388641, 16777243,
                                     33554441, 67108935, 134217767, 268435465, 536870917, 1073741907, 2147483657u};
-  if (num_vars < 1 || num_vars > 30 || npolys < 1 || npolys > PERM_MAX_POLYS) return B200_ERR_ARG;
+  if (num_vars < 1 || num_vars > 30 || npolys < 1 || nz < 1 || nz > PERM_MAX_POLYS || chunk_size < 1 ||
+      chunk_size > PERM_MAX_POLYS || (nz - 1) * chunk_size >= npolys || nz * chunk_size < npolys)
+    return B200_ERR_ARG;
   cudaStream_t s = c->stream;
   const size_t N = (size_t)1 << num_vars;
   const uint32_t nchunks = (uint32_t)((N - 1 + SCAN_CHUNK - 1) / SCAN_CHUNK);
   Fr *products = nullptr, *cp = nullptr;
-  CUDA_TRY(cudaMallocAsync(&products, N * sizeof(Fr), s));
+  CUDA_TRY(cudaMallocAsync(&products, (size_t)nz * N * sizeof(Fr), s));
   CUDA_TRY(cudaMallocAsync(&cp, ((size_t)nchunks + 1) * sizeof(Fr), s));
-  PermArgs a;
-  for (int i = 0; i < npolys; ++i) {
-    a.wires[i] = wires[i];
-    a.sigmas[i] = sigmas[i];
-    a.id_offset[i] = id_offsets[i];
-  }
-  a.npolys = npolys;
-  a.num_vars = num_vars;
-  a.beta_gamma = d_beta_gamma;
-  a.products = products;
   const size_t nthreads = (N + INV_CHUNK - 1) / INV_CHUNK;
-  perm_products_kernel<<<(unsigned)((nthreads + 127) / 128), 128, 0, s>>>(a);
-  perm_chunk_prod_kernel<<<(nchunks + 127) / 128, 128, 0, s>>>(products, num_vars, PRIM[num_vars], nchunks, cp);
+  for (int zi = 0; zi < nz; ++zi) {
+    PermArgs a;
+    const int lo = zi * chunk_size, hi = lo + chunk_size < npolys ? lo + chunk_size : npolys;
+    for (int i = lo; i < hi; ++i) {
+      a.wires[i - lo] = wires[i];
+      a.sigmas[i - lo] = sigmas[i];
+      a.id_offset[i - lo] = id_offsets[i];
+    }
+    a.npolys = hi - lo;
+    a.num_vars = num_vars;
+    a.beta_gamma = d_beta_gamma;
+    a.products = products + (size_t)zi * N;
+    perm_products_kernel<<<(unsigned)((nthreads + 127) / 128), 128, 0, s>>>(a);
+  }
+  PermZ out;
+  for (int zi = 0; zi < nz; ++zi) out.z[zi] = d_z[zi];
+  perm_chunk_prod_kernel<<<(nchunks + 127) / 128, 128, 0, s>>>(products, num_vars, PRIM[num_vars], nchunks, nz, cp);
   perm_scan_kernel<<<1, 1024, 0, s>>>(cp, nchunks);
-  perm_write_kernel<<<(nchunks + 127) / 128, 128, 0, s>>>(products, num_vars, PRIM[num_vars], nchunks, cp, d_z);
-  count_launch(c, 4);
+  perm_write_kernel<<<(nchunks + 127) / 128, 128, 0, s>>>(products, num_vars, PRIM[num_vars], nchunks, nz, cp, out);
+  count_launch(c, 3 + nz);
   CUDA_TRY(cudaFreeAsync(products, s));
   CUDA_TRY(cudaFreeAsync(cp, s));
   CUDA_TRY(cudaGetLastError());
   return B200_OK;
+}
+
+int permutation_z(Ctx* c, int num_vars, int npolys, const Fr* const* wires, const Fr* const* sigmas,
+                  const uint64_t* id_offsets, const Fr* d_beta_gamma, Fr* d_z) {
+  if (npolys < 1 || npolys > PERM_MAX_POLYS) return B200_ERR_ARG;
+  Fr* zs[1] = {d_z};
+  return permutation_z_chunks(c, num_vars, 1, npolys, npolys, wires, sigmas, id_offsets, d_beta_gamma, zs);
 }
 
 }  // namespace b200

@@ -182,3 +182,29 @@ def test_hyperplonk_with_lookup_proof_parity_and_verifies(hl, env, k):
     with pytest.raises(hl.B200Error) as e:
         hp.prove(instances, witness_ints=w_bad)
     assert e.value.code == hl.B200_ERR_LOOKUP
+
+
+@pytest.mark.parametrize("k", [4, 8])
+def test_hyperplonk_two_permutation_chunks(hl, env, k):
+    """max_degree = 3 splits the three permuted wire columns into chunks of two (preprocessor.rs:111-170): two z
+    polynomials whose running product interleaves (row, chunk) (prover.rs:308-344)."""
+    from halo2_lasso_b200 import hyperplonk as H
+    from halo2_lasso_b200.expression import compose
+
+    ctx, okzg, kzg = env
+    info, instances, w = H.rand_vanilla_plonk_circuit(k, 90 + k)
+    info.max_degree = 3
+    nz, expr = compose(k, info.constraints, info.num_poly, info.permutation_polys, max_degree=3)
+    assert nz == 2 and expr.degree() == 4
+    ohp = O.HyperPlonk(okzg, k, expr, len(instances), 3, [O.fr_from_ints(p) for p in info.preprocess_polys],
+                       info.permutation_polys, info.permutations, nz)
+    inst = O.fr_from_ints(instances)
+    to = O.Transcript()
+    assert ohp.prove(to, inst, [O.fr_from_ints(c) for c in w])
+    hp = H.HyperPlonk(ctx, kzg, info)
+    assert (hp.num_z, hp.degree, hp.num_polys) == (2, 4, 14)
+    tr = hl.Keccak256Transcript(ctx)
+    hp.prove(instances, witness_ints=w)
+    proof = tr.into_proof()
+    assert proof == to.proof()
+    assert ohp.verify(O.Transcript(proof), inst)
