@@ -168,6 +168,9 @@ def evaluate_many(ctx, polys, x):
     return out
 
 
+_proof_buf = None
+
+
 class Keccak256Transcript:
     """FiatShamirTranscript<Keccak256, Cursor<Vec<u8>>> living on the device inside the context."""
 
@@ -196,11 +199,12 @@ class Keccak256Transcript:
         _chk(lib().b200_transcript_write_commitments(self.ctx.h, _p(pts), C.c_int(pts.shape[0])), "write_commitments")
 
     def into_proof(self) -> bytes:
+        global _proof_buf
         n = C.c_uint64()
-        cap = 8 << 20
-        buf = (C.c_uint8 * cap)()
-        _chk(lib().b200_transcript_proof(self.ctx.h, buf, C.c_uint64(cap), C.byref(n)), "into_proof")
-        return bytes(buf[: n.value])
+        if _proof_buf is None:
+            _proof_buf = np.empty(8 << 20, dtype=np.uint8)  # the device stream's capacity; reused across proofs
+        _chk(lib().b200_transcript_proof(self.ctx.h, _p(_proof_buf), C.c_uint64(_proof_buf.size), C.byref(n)), "into_proof")
+        return _proof_buf[: n.value].tobytes()
 
 
 class ClassicSumCheck:
