@@ -241,6 +241,51 @@ int orc_kzg_batch_verify(void* h, void* tr, int nv, int ncomms, const G1Affine* 
                           *(Transcript*)tr) ? 0 : 1;
 }
 
+// ---- pairing (verifier side) -----------------------------------------------------------------------
+void orc_kzg_set_pairing_check(void* kzg, int on) { ((KzgParams*)kzg)->pairing_check = on != 0; }
+// e(a * G1, b * G2) as 12 x 4 canonical limbs (c0.a0.c0, c0.a0.c1, c0.a1.c0, ...)
+static void fq12_out(const Fq12& f, uint64_t* out) {
+  const Fq2* parts[6] = {&f.c0.a0, &f.c0.a1, &f.c0.a2, &f.c1.a0, &f.c1.a1, &f.c1.a2};
+  for (int i = 0; i < 6; ++i) {
+    parts[i]->c0.to_raw(out + 8 * i);
+    parts[i]->c1.to_raw(out + 8 * i + 4);
+  }
+}
+void orc_pairing_gen_multiples(const Fr* a, const Fr* b, uint64_t* out48) {
+  const G1Affine p = G1::from_affine(G1Affine::generator()).mul(*a).to_affine();
+  const G2Affine q = G2Affine::generator().mul(*b);
+  fq12_out(pairing(p, q), out48);
+}
+// g^e for g = e(G1, G2), e a scalar
+void orc_pairing_gen_pow(const Fr* e, uint64_t* out48) {
+  const Fq12 g = pairing(G1Affine::generator(), G2Affine::generator());
+  uint64_t k[4];
+  e->to_raw(k);
+  Fq12 acc = Fq12::one();
+  for (int i = 255; i >= 0; --i) {
+    acc = acc.sqr();
+    if ((k[i >> 6] >> (i & 63)) & 1) acc = acc * g;
+  }
+  fq12_out(acc, out48);
+}
+int orc_g2_checks(const Fr* k) {  // generator on the twist, [k]G2 on the twist, [r]G2 = O (r = 0 as a scalar: use r-1 and add)
+  const G2Affine g = G2Affine::generator();
+  if (!g.on_curve()) return 1;
+  const G2Affine kg = g.mul(*k);
+  if (!kg.on_curve() || kg.inf) return 2;
+  const Fr minus_one = Fr::zero() - Fr::one();
+  if (!(g.mul(minus_one).add(g)).inf) return 3;  // [r-1]G + G = O
+  if (!(g.mul(*k).add(g.mul(Fr::zero() - *k))).inf) return 4;
+  return 0;
+}
+// Π e(a_i G1, b_i G2) == 1 ?
+int orc_pairing_product_is_identity(const Fr* a, const Fr* b, int n) {
+  std::vector<std::pair<G1Affine, G2Affine>> terms;
+  for (int i = 0; i < n; ++i)
+    terms.push_back({G1::from_affine(G1Affine::generator()).mul(a[i]).to_affine(), G2Affine::generator().mul(b[i])});
+  return pairings_product_is_identity(terms) ? 1 : 0;
+}
+
 // ---- HyperPlonk --------------------------------------------------------------------------------------
 // cycles_flat: [len, poly, row, poly, row, ..., len, ...]
 // lookup_tokens: per lookup [width, input_0, table_0, input_1, table_1, ...] with every expression in prefix form

@@ -8,10 +8,10 @@
 // additive batch     pb/pcs/multilinear.rs:134-275 (batch_open / batch_verify)
 //
 // Deviations, stated: (1) SRS scalars `ss` come from a caller-supplied seed list instead of
-// `F::random(StdRng)` (ChaCha is not restated; SURVEY §7 hard part g). (2) `verify` checks the
-// pairing equation in the exponent with the trapdoor `ss` (G1 scalar muls) instead of a Miller
-// loop: e(C - v*g1, g2) * Π e(Q_i, (s_i - x_i) g2)^{-1} == 1  <=>  C - v*g1 == Σ (s_i - x_i) Q_i.
-// Pairing-based verification is SURVEY §8(f) N2.
+// `F::random(StdRng)` (ChaCha is not restated; SURVEY §7 hard part g). (2) `verify` has two forms: the
+// reference's pairing product e(C - v*g1, -g2) * Π e(Q_i, (s_i - x_i) g2) == 1 (pairing.hpp, SURVEY §8(f) N2;
+// enabled with KzgParams::pairing_check) and, by default because it is ~100x faster, the same equation in the
+// exponent with the trapdoor `ss`:  C - v*g1 == Σ (s_i - x_i) Q_i.
 #pragma once
 #include <cmath>
 #include <vector>
@@ -20,6 +20,7 @@
 
 #include "ff.hpp"
 #include "g1.hpp"
+#include "pairing.hpp"
 #include "mle.hpp"
 #include "sumcheck.hpp"
 #include "transcript.hpp"
@@ -94,8 +95,18 @@ inline G1 variable_base_msm(const Fr* scalars, const G1Affine* bases, size_t n) 
 
 struct KzgParams {
   int num_vars = 0;
-  std::vector<Fr> ss;                      // trapdoor (test SRS; also used by `verify`)
+  std::vector<Fr> ss;                      // trapdoor (test SRS; also used by the fast form of `verify`)
   std::vector<std::vector<G1Affine>> eqs;  // eqs[k]: 2^k points, eqs[k][b] = g1 * Π_j (b_j ? s_j : 1-s_j)
+  // verifier side (kzg.rs:215-225, 240-249): ss_g2[i] = g2 * s_i, built on first use
+  mutable std::vector<G2Affine> ss_g2;
+  bool pairing_check = false;  // verify with the pairing product (as the reference) instead of the trapdoor identity
+  const std::vector<G2Affine>& g2_powers() const {
+    if (ss_g2.size() != ss.size()) {
+      ss_g2.clear();
+      for (const Fr& s : ss) ss_g2.push_back(G2Affine::generator().mul(s));
+    }
+    return ss_g2;
+  }
 };
 
 // kzg.rs:166-213. The newest variable s_i lands on the TOP bit (evals_hi = s_i * last).
@@ -175,7 +186,10 @@ inline Fr kzg_open(const KzgParams& pp, const Poly& poly, const std::vector<Fr>&
   return rem[0];
 }
 
-// kzg.rs:330-361 with the pairing product replaced by the trapdoor identity (see header)
+// kzg.rs:330-361. With vp.pairing_check the reference's check itself:
+//   e(comm - g1 * eval, -g2) * Π_i e(quotient_i, g2 * s_i - g2 * x_i) == 1     (pairings_product_is_identity);
+// otherwise the same equation in the exponent, evaluated with the trapdoor (fast; the SRS of the tests is generated
+// from known scalars). Both forms accept / reject the same openings (tests/test_oracle_pairing.py).
 inline bool kzg_verify(const KzgParams& vp, const G1Affine& comm, const std::vector<Fr>& point,
                        const Fr& eval, Transcript& tr) {
   const int n = (int)point.size();
@@ -183,6 +197,14 @@ inline bool kzg_verify(const KzgParams& vp, const G1Affine& comm, const std::vec
   for (int i = 0; i < n; ++i)
     if (!tr.read_commitment(&qs[i])) return false;
   G1 lhs = G1::from_affine(comm).add(G1::from_affine(G1Affine::generator()).mul(eval).neg());
+  if (vp.pairing_check) {
+    const std::vector<G2Affine>& sg2 = vp.g2_powers();
+    const G2Affine g2 = G2Affine::generator();
+    std::vector<std::pair<G1Affine, G2Affine>> terms;
+    terms.push_back({lhs.to_affine(), g2.neg()});
+    for (int i = 0; i < n; ++i) terms.push_back({qs[i], sg2[i].add(g2.mul(point[i]).neg())});
+    return pairings_product_is_identity(terms);
+  }
   G1 rhs = G1::identity();
   for (int i = 0; i < n; ++i) rhs = rhs.add(G1::from_affine(qs[i]).mul(vp.ss[i] - point[i]));
   return lhs.eq(rhs);

@@ -433,6 +433,10 @@ class Kzg:
         lib().orc_kzg_eqs(self.h, C.c_int(level), _p(out))
         return out
 
+    def set_pairing_check(self, on=True):
+        """verify openings with the pairing product (kzg.rs:330-361) instead of the trapdoor identity"""
+        lib().orc_kzg_set_pairing_check(self.h, C.c_int(int(on)))
+
     def commit(self, poly):
         poly = np.ascontiguousarray(poly, dtype=np.uint64)
         nv = int(poly.shape[0]).bit_length() - 1
@@ -520,6 +524,31 @@ class HyperPlonk:
     def verify(self, tr, instances):
         inst = np.ascontiguousarray(instances, dtype=np.uint64).reshape(-1, 4)
         return lib().orc_hp_verify(self.h, tr.h, _p(inst), C.c_int(inst.shape[0])) == 0
+
+
+# ---- pairing -----------------------------------------------------------------------------------
+def pairing_gen_multiples(a, b):
+    """e(a * G1, b * G2) as 12 canonical Fq coefficients (Python ints)"""
+    out = np.zeros(48, dtype=np.uint64)
+    lib().orc_pairing_gen_multiples(_p(np.ascontiguousarray(a, dtype=np.uint64)), _p(np.ascontiguousarray(b, dtype=np.uint64)), _p(out))
+    return [sum(int(out[4 * i + j]) << (64 * j) for j in range(4)) for i in range(12)]
+
+
+def pairing_gen_pow(e):
+    """e(G1, G2)^e"""
+    out = np.zeros(48, dtype=np.uint64)
+    lib().orc_pairing_gen_pow(_p(np.ascontiguousarray(e, dtype=np.uint64)), _p(out))
+    return [sum(int(out[4 * i + j]) << (64 * j) for j in range(4)) for i in range(12)]
+
+
+def g2_checks(k):
+    return lib().orc_g2_checks(_p(np.ascontiguousarray(k, dtype=np.uint64)))
+
+
+def pairing_product_is_identity(a, b):
+    a = np.ascontiguousarray(a, dtype=np.uint64).reshape(-1, 4)
+    b = np.ascontiguousarray(b, dtype=np.uint64).reshape(-1, 4)
+    return lib().orc_pairing_product_is_identity(_p(a), _p(b), C.c_int(a.shape[0])) == 1
 
 
 def permutation_z(perm_polys, wires, beta, gamma):

@@ -121,3 +121,21 @@ def test_lasso_full_size_2_20_verifies(hl):
     hl.LassoProver(ctx, kzg, O.TABLE_RANGE, chunks).prove(xs)
     assert tr.into_proof() == proof
     ctx.close()
+
+
+def test_gpu_proof_verifies_with_the_pairing_check(hl, env):
+    """The reference's own verification path: SRS in G2 + pairing product (kzg.rs:330-361), no trapdoor."""
+    ctx, okzg, kzg = env
+    kind, chunks, mu = O.TABLE_XOR, 2, 6
+    xs, ys = operands(kind, chunks, mu, 77)
+    tr = hl.Keccak256Transcript(ctx)
+    hl.LassoProver(ctx, kzg, kind, chunks).prove(xs, ys)
+    proof = tr.into_proof()
+    okzg.set_pairing_check(True)
+    try:
+        assert O.lasso_verify(okzg, O.Transcript(proof), kind, chunks, mu)
+        bad = bytearray(proof)
+        bad[len(bad) - 40] ^= 1
+        assert not O.lasso_verify(okzg, O.Transcript(bytes(bad)), kind, chunks, mu)
+    finally:
+        okzg.set_pairing_check(False)
