@@ -32,7 +32,15 @@ struct ScEvalArgs {
 };
 #define DBG_CLK(i)                                                     \
   do {                                                                 \
-    if (a.dbg && threadIdx.x == 0) a.dbg[a.round * 16 + (i)] = clock64(); \
+    if (a.dbg && threadIdx.x == 0) {                                   \
+      a.dbg[a.round * 16 + (i)] = clock64();                           \
+      /* wall-clock (ns) copies of stamps 0, 6, 7, 11 in the spare slots 12..15 */ \
+      if ((i) == 0 || (i) == 6 || (i) == 7 || (i) == 11) {             \
+        unsigned long long ns_;                                        \
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns_));        \
+        a.dbg[a.round * 16 + ((i) == 0 ? 12 : (i) == 6 ? 13 : (i) == 7 ? 14 : 15)] = (long long)ns_; \
+      }                                                                \
+    }                                                                  \
   } while (0)
 
 // Load the pair (u0, u1) = (t[2b], t[2b+1]) of the CURRENT round. With BIND the table still has the

@@ -36,6 +36,6 @@ for r_ in range(world):
             if st[0] == 0:
                 continue
             print(f"rank {rank} round {r}:", " ".join(f"{names[i]}={(st[i]-st[i-1])/1965:.1f}" for i in range(1, 12)),
-                  f"total {(st[11] - st[0])/1965:.1f} us", flush=True)
+                  f"total {(st[11] - st[0])/1965:.1f} us | wall clock: xchg {(out[r*16+14]-out[r*16+13])/1e3:.1f} us, tail {(out[r*16+15]-out[r*16+14])/1e3:.1f} us, total {(out[r*16+15]-out[r*16+12])/1e3:.1f} us", flush=True)
     dist.barrier()
 dist.destroy_process_group()

@@ -10,7 +10,7 @@ __global__ void pingpong(PeerCtx pc, int iters, long long* cycles, Fr* sink, int
   v.v[0] = pc.rank + 1;
   long long t0 = clock64();
   Fr acc = fe_zero<FrP>();
-  long long spent = 0;
+  long long spent = 0, tail = 0;
   for (int k = 1; k <= iters; ++k) {
     if (gap_ns) {  // idle time between collectives, jittered per rank like independent kernels would be
       const long long g0 = clock64();
@@ -22,9 +22,26 @@ __global__ void pingpong(PeerCtx pc, int iters, long long* cycles, Fr* sink, int
     if (lane < 4)
       for (int r = 0; r < pc.world; ++r) acc = acc + peer_read(pc, (unsigned)k, r, lane);
     spent += clock64() - c0;
+    // a tail like the round kernel's: dependent field products + shared-memory traffic + a local global store
+    const long long q0 = clock64();
+    __shared__ Fr sh[32];
+    Fr t = acc;
+    t.v[0] |= 1;
+    for (int j = 0; j < 24; ++j) {
+      sh[lane] = t;
+      __syncwarp();
+      t = t * sh[(lane + 1) & 31];
+      __syncwarp();
+    }
+    if (lane == 0) sink[4] = t;
+    acc = acc + t;
+    tail += clock64() - q0;
   }
   long long t1 = clock64();
-  if (lane == 0) *cycles = gap_ns ? spent : t1 - t0;
+  if (lane == 0) {
+    cycles[0] = gap_ns ? spent : t1 - t0;
+    cycles[1] = tail;
+  }
   if (lane < 4) sink[lane] = acc;
 }
 int main(int argc, char** argv) {
@@ -41,12 +58,12 @@ int main(int argc, char** argv) {
         if (e != d) cudaDeviceEnablePeerAccess(e, 0);
       cudaMalloc(&box[d], sizeof(Mailbox));
       cudaMemset(box[d], 0, sizeof(Mailbox));
-      cudaMallocManaged(&cyc[d], sizeof(long long));
-      cudaMalloc(&sink[d], 4 * sizeof(Fr));
+      cudaMallocManaged(&cyc[d], 2 * sizeof(long long));
+      cudaMalloc(&sink[d], 8 * sizeof(Fr));
       cudaStreamCreate(&st[d]);
     }
     for (int d = 0; d < world; ++d) { cudaSetDevice(d); cudaDeviceSynchronize(); }
-    for (int gap : {0, 5000, 30000, 100000}) {
+    for (int gap : {0, 30000}) {
     const int iters = gap ? 300 : 2000;
     for (int rep = 0; rep < 2; ++rep) {
       for (int d = 0; d < world; ++d) {
@@ -66,6 +83,7 @@ int main(int argc, char** argv) {
     }
     printf("world %d gap %6d ns: %.2f us per collective (rank 0; includes waiting for the slowest rank)  err=%s\n", world, gap,
            (double)*cyc[0] / iters / 1965.0, cudaGetErrorString(cudaGetLastError()));
+    for (int d = 0; d < world; ++d) printf("    rank %d tail %.2f us\n", d, (double)cyc[d][1] / iters / 1965.0);
     }
     for (int d = 0; d < world; ++d) {
       cudaSetDevice(d);
