@@ -53,8 +53,7 @@ __device__ __forceinline__ void peer_publish(const PeerCtx& pc, unsigned int seq
   // release: the payload stores of all lanes (ordered before the flag stores by the warp barrier) become visible
   // to a peer before the sequence number does; one acquire fence after the poll on the reading side.
   // Measured (tools/micro/): 7 us per collective at 2 GPUs and 11 us at 4 inside one long-running kernel; in the
-  // real one-process-per-GPU setting 11 us per round at 2 GPUs but ~125 us at 4 and ~80 us at 8, where rounds
-  // alternate between 30 us and 260 us on each rank with the WHOLE finalize warp slowed down.
+  // one-process-per-GPU prover 11 / 15 / 77 us per round at 2 / 4 / 8 GPUs with peer_spin_while below.
   __syncwarp();
   if (lane < pc.world) {
     unsigned int* f = &pc.box[lane]->slot[pc.rank].seq[par];
@@ -70,6 +69,19 @@ __device__ __forceinline__ void peer_publish(const PeerCtx& pc, unsigned int seq
     asm volatile("fence.acq_rel.sys;" ::: "memory");
   }
   __syncwarp();
+}
+// Keep-busy helper. A GPU whose only activity is one warp polling NVLink-written memory drops into a low-activity
+// state in which the code that FOLLOWS the wait runs ~10x slower for ~120 us (measured at 4 and 8 GPUs, one
+// process per GPU: 125 us per collective instead of 11-15). Warps 1..3 of the CTA (one per other SM
+// sub-partition) therefore issue arithmetic while warp 0 runs the exchange: they call peer_spin_while(flag) after a
+// barrier that publishes *flag = 1, warp 0 clears the flag when it is done.
+__device__ __forceinline__ void peer_spin_while(volatile int* flag, unsigned int* sink) {
+  float x = (float)threadIdx.x;
+  while (*flag) {
+#pragma unroll
+    for (int i = 0; i < 64; ++i) x = fmaf(x, 1.0001f, 0.5f);
+  }
+  if (x == 12345.678f) *sink = 0;  // keeps the loop alive
 }
 __device__ __forceinline__ Fr peer_read(const PeerCtx& pc, unsigned int seq, int src, int idx) {
   return ld_sys_fr(&pc.box[pc.rank]->slot[src].data[seq & 1][idx]);

@@ -29,12 +29,22 @@ __global__ void shard_eq_factor_kernel(const Fr* y_top, int g, int rank, Fr* out
 }
 
 // all-gather `cnt` (<= 32) values per rank; gathered[i * world + r] = value i of rank r
-__global__ void shard_gather_kernel(PeerCtx pc, unsigned int seq, const Fr* vals, int cnt, Fr* gathered) {
+__global__ void shard_gather_kernel(PeerCtx pc, unsigned int seq, const Fr* vals, int cnt, Fr* gathered,
+                                    unsigned int* sink) {
+  __shared__ volatile int s_busy;  // warps 1-3 keep the SM busy during the exchange (peer.cuh)
+  if (threadIdx.x == 0) s_busy = 1;
+  __syncthreads();
+  if (threadIdx.x >= 32) {
+    peer_spin_while(&s_busy, sink);
+    return;
+  }
   const int lane = threadIdx.x;
   const Fr mine = lane < cnt ? fe_ld(vals + lane) : fe_zero<FrP>();
   peer_publish(pc, seq, mine, cnt);
   if (lane < cnt)
     for (int r = 0; r < pc.world; ++r) fe_st(gathered + (size_t)lane * pc.world + r, peer_read(pc, seq, r, lane));
+  __syncwarp();
+  if (lane == 0) s_busy = 0;
 }
 
 int sumcheck_prove_evals_sharded(Ctx* c, const ScEvalJob& job_local, int n) {
@@ -65,7 +75,7 @@ int sumcheck_prove_evals_sharded(Ctx* c, const ScEvalJob& job_local, int n) {
   if (rc) return rc;
 
   // phase 2: rebuild the G-entry tables everywhere and finish redundantly
-  shard_gather_kernel<<<1, 32, 0, s>>>(c->peer, ++c->peer_seq, finals, ntab + 1, gathered);
+  shard_gather_kernel<<<1, 128, 0, s>>>(c->peer, ++c->peer_seq, finals, ntab + 1, gathered, &c->d_sc->pad[0]);
   count_launch(c);
   ScEvalJob j2 = job_local;
   j2.num_vars = g;
@@ -80,7 +90,14 @@ int sumcheck_prove_evals_sharded(Ctx* c, const ScEvalJob& job_local, int n) {
   return B200_OK;
 }
 
-__global__ void shard_point_sum_kernel(PeerCtx pc, unsigned int seq, const G1Aff* mine, G1Aff* out) {
+__global__ void shard_point_sum_kernel(PeerCtx pc, unsigned int seq, const G1Aff* mine, G1Aff* out, unsigned int* sink) {
+  __shared__ volatile int s_busy;
+  if (threadIdx.x == 0) s_busy = 1;
+  __syncthreads();
+  if (threadIdx.x >= 32) {
+    peer_spin_while(&s_busy, sink);
+    return;
+  }
   // the affine point travels as two field-sized values (x, y); Fq and Fr share the 8x32-bit layout
   const int lane = threadIdx.x;
   Fr v = fe_zero<FrP>();
@@ -106,6 +123,8 @@ __global__ void shard_point_sum_kernel(PeerCtx pc, unsigned int seq, const G1Aff
     fe_st(&out->x, a.x);
     fe_st(&out->y, a.y);
   }
+  __syncwarp();
+  if (lane == 0) s_busy = 0;
 }
 
 // all-gather + add up to 16 partial commitments at once: lane 2i / 2i+1 carry x / y of point idx[i]; afterwards
@@ -113,7 +132,15 @@ __global__ void shard_point_sum_kernel(PeerCtx pc, unsigned int seq, const G1Aff
 struct PointIdx {
   int v[16];
 };
-__global__ void shard_points_sum_kernel(PeerCtx pc, unsigned int seq, G1Aff* pts, PointIdx pidx, int cnt) {
+__global__ void shard_points_sum_kernel(PeerCtx pc, unsigned int seq, G1Aff* pts, PointIdx pidx, int cnt,
+                                        unsigned int* sink) {
+  __shared__ volatile int s_busy;
+  if (threadIdx.x == 0) s_busy = 1;
+  __syncthreads();
+  if (threadIdx.x >= 32) {
+    peer_spin_while(&s_busy, sink);
+    return;
+  }
   const int lane = threadIdx.x;
   const int* idx = pidx.v;
   Fr v = fe_zero<FrP>();
@@ -140,6 +167,8 @@ __global__ void shard_points_sum_kernel(PeerCtx pc, unsigned int seq, G1Aff* pts
     fe_st(&pts[idx[lane]].x, a.x);
     fe_st(&pts[idx[lane]].y, a.y);
   }
+  __syncwarp();
+  if (lane == 0) s_busy = 0;
 }
 
 // Commitment MSMs split by point range: rank r takes scalars / bases [r n/G, (r+1) n/G) of every job that is large
@@ -173,7 +202,7 @@ int msm_batch_dist(Ctx* c, const MsmJob* jobs, int J, G1Aff* d_out) {
     const int cnt = (int)std::min<size_t>(16, sharded.size() - at);
     PointIdx pidx;
     for (int i = 0; i < 16; ++i) pidx.v[i] = i < cnt ? sharded[at + i] : 0;
-    shard_points_sum_kernel<<<1, 32, 0, c->stream>>>(c->peer, ++c->peer_seq, d_out, pidx, cnt);
+    shard_points_sum_kernel<<<1, 128, 0, c->stream>>>(c->peer, ++c->peer_seq, d_out, pidx, cnt, &c->d_sc->pad[0]);
     count_launch(c);
   }
   CUDA_TRY(cudaGetLastError());
@@ -186,7 +215,7 @@ int msm_sharded(Ctx* c, const MsmJob& local, G1Aff* d_out) {
   CUDA_TRY(cudaMallocAsync(&part, sizeof(G1Aff), c->stream));
   int rc = msm_batch(c, &local, 1, part);
   if (rc) return rc;
-  shard_point_sum_kernel<<<1, 32, 0, c->stream>>>(c->peer, ++c->peer_seq, part, d_out);
+  shard_point_sum_kernel<<<1, 128, 0, c->stream>>>(c->peer, ++c->peer_seq, part, d_out, &c->d_sc->pad[0]);
   count_launch(c);
   CUDA_TRY(cudaFreeAsync(part, c->stream));
   CUDA_TRY(cudaGetLastError());

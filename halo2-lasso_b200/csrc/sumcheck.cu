@@ -129,19 +129,34 @@ __global__ void __launch_bounds__(SC_THREADS) sc_eval_round_kernel(ScEvalArgs a)
   const uint32_t nparts = gridDim.x * gridDim.y;
 #pragma unroll
   for (int x = 0; x < D; ++x) acc[x] = fe_zero<FrP>();
+  const bool keep_busy = a.peer.world > 1;
   if (nparts <= 32) {  // small rounds: one warp sums the partials, no block-wide barrier
-    if (threadIdx.x >= 32) return;
-    if (threadIdx.x < nparts) {
+    if (threadIdx.x >= 32) {
+      if (!keep_busy) return;
+    } else {
+      if (threadIdx.x < nparts) {
 #pragma unroll
-      for (int x = 0; x < D; ++x) acc[x] = fr_ld_cg(a.partial + (size_t)threadIdx.x * D + x);
+        for (int x = 0; x < D; ++x) acc[x] = fr_ld_cg(a.partial + (size_t)threadIdx.x * D + x);
+      }
+      warp_reduce_fr<D>(acc);
     }
-    warp_reduce_fr<D>(acc);
   } else {
     for (uint32_t i = threadIdx.x; i < nparts; i += blockDim.x) {
 #pragma unroll
       for (int x = 0; x < D; ++x) acc[x] = acc[x] + fr_ld_cg(a.partial + (size_t)i * D + x);
     }
     block_reduce_fr<D>(acc, smem);
+  }
+  // Sharded rounds: warps 1-3 keep the SM busy while warp 0 runs the exchange and the finalize (peer.cuh)
+  __shared__ volatile int s_busy;
+  if (keep_busy) {
+    if (threadIdx.x == 0) s_busy = 1;
+    __syncthreads();
+    if (threadIdx.x >= 128) return;
+    if (threadIdx.x >= 32) {
+      peer_spin_while(&s_busy, &a.st->pad[0]);
+      return;
+    }
   }
   if (threadIdx.x < 32) {  // warp 0, warp-uniform control flow; lane i owns p(i)
     const int lane = threadIdx.x;
@@ -202,6 +217,7 @@ __global__ void __launch_bounds__(SC_THREADS) sc_eval_round_kernel(ScEvalArgs a)
       fe_st(&a.st->claim, term);
     }
     if (dbg_cta) DBG_CLK(11);
+    if (keep_busy && lane == 0) s_busy = 0;
   }
 }
 
