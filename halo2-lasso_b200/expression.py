@@ -2,7 +2,7 @@
 
     Expression / Query / Rotation / CommonPolynomial   pb/util/expression.rs:13-182, 488-560
     BooleanHypercube                                   pb/util/arithmetic/bh.rs:76-153
-    vanilla_plonk_expression / compose (no lookups)    pb/backend/hyperplonk/util.rs:30-62,
+    vanilla_plonk_expression / compose (incl. LogUp)   pb/backend/hyperplonk/util.rs:30-98,
                                                        pb/backend/hyperplonk/preprocessor.rs:25-60, 111-170
     compile()  (the role of ExpressionRegistry,        pb/util/expression/evaluator.rs:22-228)
 

@@ -484,7 +484,7 @@ class Kzg:
                                           C.c_int(len(points)), _p(pts), C.c_int(len(evals)), _p(ep), _p(ept), _p(ev)) == 0
 
 
-# ---- HyperPlonk (no lookups) ----------------------------------------------------------------
+# ---- HyperPlonk (with or without LogUp lookups) ----------------------------------------------------------------
 class HyperPlonk:
     """Oracle `HyperPlonk<MultilinearKzg>`: preprocess at construction, then prove / verify."""
 

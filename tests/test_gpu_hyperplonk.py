@@ -1,4 +1,4 @@
-"""GPU parity of the HyperPlonk prover (lookup-free vanilla plonk) vs the oracle: permutation grand product and
+"""GPU parity of the HyperPlonk prover (vanilla plonk, without and with LogUp lookups) vs the oracle: permutation grand product, lookup polynomials and
 whole proofs byte-for-byte; the oracle verifier accepts the GPU proofs."""
 import numpy as np
 import pytest

@@ -1,4 +1,4 @@
-"""Oracle HyperPlonk (lookup-free vanilla plonk): the reference's e2e test shape (pb/backend.rs:202-241,
+"""Oracle HyperPlonk (vanilla plonk, without and with the LogUp lookup argument): the reference's e2e test shape (pb/backend.rs:202-241,
 hyperplonk.rs:398-426): preprocess -> prove -> verify accepts; tampering / wrong instances are rejected. Also the
 product's host-side helpers (fixture, permutation_polys, rotation_eval_points) against the oracle."""
 import numpy as np
