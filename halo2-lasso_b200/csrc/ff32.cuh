@@ -287,9 +287,9 @@ FF_HD Fe<P> fe_from_u64(uint64_t x) {
   return fe_from_canonical<P>(t);
 }
 
-// Fermat inverse a^(p-2); inv(0) = 0. Used only for the handful of projective->affine conversions.
+// Fermat inverse a^(p-2); inv(0) = 0 (kept as the reference for the unit test of fe_inv).
 template <class P>
-FF_HD Fe<P> fe_inv(const Fe<P>& a) {
+FF_HD Fe<P> fe_inv_fermat(const Fe<P>& a) {
   Fe<P> acc = fe_one<P>();
   for (int i = 255; i >= 0; --i) {
     // exponent p-2: p[0] >= 2 in both fields, so only limb 0 differs from p
@@ -308,6 +308,111 @@ FF_HD Fe<P> fe_inv(const Fe<P>& a) {
     if ((limb >> (i & 31)) & 1) acc = fe_mul<P>(acc, a);
   }
   return acc;
+}
+
+// Montgomery inverse by Kaliski's binary algorithm: inv(0) = 0. ~1.4 * 254 shift / add / subtract steps on the ALU
+// pipe plus two Montgomery products, instead of the ~384 products of the Fermat ladder — 4-5x fewer issue cycles, and
+// it leaves the multiplier pipe alone. Phase 1 ("almost inverse") returns x^-1 * 2^k mod p with 254 <= k <= 508 for
+// the stored residue x = a R; the Montgomery form of a^-1 is x^-1 R^2 = (x^-1 2^k) * R^2 * 2^(512-k) / R / R.
+template <class P>
+FF_HD Fe<P> fe_inv(const Fe<P>& a) {
+  if (fe_is_zero<P>(a)) return a;
+  uint32_t u[8], v[8], r[8], s[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    u[i] = P::mod(i);
+    v[i] = a.v[i];
+    r[i] = 0;
+    s[i] = 0;
+  }
+  s[0] = 1;
+  int k = 0;
+  for (;;) {
+    uint32_t nz = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) nz |= v[i];
+    if (!nz) break;
+    // e = v - u (borrow: u > v), d = u - v = -e, sum = r + s   (r, s < 2p < 2^255: no overflow)
+    uint32_t e[8], d[8], sum[8];
+    uint64_t bw = 0, cy = 0, ng = 1;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const uint64_t t = (uint64_t)v[i] - u[i] - bw;
+      e[i] = (uint32_t)t;
+      bw = (t >> 32) & 1;
+      const uint64_t w = (uint64_t)r[i] + s[i] + cy;
+      sum[i] = (uint32_t)w;
+      cy = w >> 32;
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const uint64_t t = (uint64_t)(~e[i]) + ng;
+      d[i] = (uint32_t)t;
+      ng = t >> 32;
+    }
+    const bool ue = !(u[0] & 1), ve = !(v[0] & 1), ugt = bw != 0;
+    // A: u even | B: v even | C: u > v | D: otherwise        (first match wins)
+    const uint32_t mA = ue ? 0xffffffffu : 0u;
+    const uint32_t mB = (!ue && ve) ? 0xffffffffu : 0u;
+    const uint32_t mC = (!ue && !ve && ugt) ? 0xffffffffu : 0u;
+    const uint32_t mD = ~(mA | mB | mC);
+    // u' = A ? u >> 1 : C ? d >> 1 : u;   v' = B ? v >> 1 : D ? e >> 1 : v
+    // r' = C ? r + s : (B | D) ? r << 1 : r;   s' = D ? r + s : (A | C) ? s << 1 : s
+    uint32_t nu[8], nv[8], nr[8], ns[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const uint32_t uh = i < 7 ? u[i + 1] : 0u, dh = i < 7 ? d[i + 1] : 0u;
+      const uint32_t vh = i < 7 ? v[i + 1] : 0u, eh = i < 7 ? e[i + 1] : 0u;
+      const uint32_t rl = i ? r[i - 1] : 0u, sl = i ? s[i - 1] : 0u;
+      const uint32_t us = (u[i] >> 1) | (uh << 31), ds = (d[i] >> 1) | (dh << 31);
+      const uint32_t vs = (v[i] >> 1) | (vh << 31), es = (e[i] >> 1) | (eh << 31);
+      const uint32_t r2 = (r[i] << 1) | (rl >> 31), s2 = (s[i] << 1) | (sl >> 31);
+      nu[i] = (mA & us) | (mC & ds) | (~(mA | mC) & u[i]);
+      nv[i] = (mB & vs) | (mD & es) | (~(mB | mD) & v[i]);
+      nr[i] = (mC & sum[i]) | ((mB | mD) & r2) | (mA & r[i]);
+      ns[i] = (mD & sum[i]) | ((mA | mC) & s2) | (mB & s[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      u[i] = nu[i];
+      v[i] = nv[i];
+      r[i] = nr[i];
+      s[i] = ns[i];
+    }
+    ++k;
+  }
+  // r < 2p: reduce once, then negate: x^-1 2^k = p - r
+  Fe<P> t;
+  {
+    uint64_t bw = 0;
+    uint32_t w[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const uint64_t x = (uint64_t)r[i] - P::mod(i) - bw;
+      w[i] = (uint32_t)x;
+      bw = (x >> 32) & 1;
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t.v[i] = bw ? r[i] : w[i];
+  }
+  t = fe_neg<P>(t);
+  // * R^2 / R = * R, then * 2^(512-k) / R
+  Fe<P> r2c;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) r2c.v[i] = P::r2(i);
+  t = fe_mul<P>(t, r2c);
+  int j = 512 - k;  // 4 .. 258
+  int extra = 0;
+  if (j > 253) {
+    extra = j - 253;
+    j = 253;
+  }
+  Fe<P> pw = fe_zero<P>();
+#pragma unroll
+  for (int i = 0; i < 8; ++i) pw.v[i] = (j >> 5) == i ? (1u << (j & 31)) : 0u;
+  t = fe_mul<P>(t, pw);
+  for (int i = 0; i < extra; ++i) t = fe_dbl<P>(t);
+  return t;
 }
 
 // ---- 256-bit global memory access --------------------------------------------------------------

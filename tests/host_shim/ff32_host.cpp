@@ -8,6 +8,7 @@ extern "C" {
   void NAME##_add(const Fe<P>* a, const Fe<P>* b, Fe<P>* o, long n) { for (long i = 0; i < n; ++i) o[i] = fe_add<P>(a[i], b[i]); } \
   void NAME##_sub(const Fe<P>* a, const Fe<P>* b, Fe<P>* o, long n) { for (long i = 0; i < n; ++i) o[i] = fe_sub<P>(a[i], b[i]); } \
   void NAME##_inv(const Fe<P>* a, Fe<P>* o, long n) { for (long i = 0; i < n; ++i) o[i] = fe_inv<P>(a[i]); } \
+  void NAME##_inv_fermat(const Fe<P>* a, Fe<P>* o, long n) { for (long i = 0; i < n; ++i) o[i] = fe_inv_fermat<P>(a[i]); } \
   void NAME##_from_canonical(const Fe<P>* a, Fe<P>* o, long n) { for (long i = 0; i < n; ++i) o[i] = fe_from_canonical<P>(a[i]); } \
   void NAME##_to_canonical(const Fe<P>* a, Fe<P>* o, long n) { for (long i = 0; i < n; ++i) o[i] = fe_to_canonical<P>(a[i]); }
 API(h32_fr, FrP)

@@ -57,6 +57,19 @@ def test_limb_arithmetic_matches_bigint(shim, name, p):
     k = 200
     getattr(shim, name + "_inv")(_p(A), _p(O), C.c_long(k))
     assert unpack(O[:k]) == [pow(x * Ri % p, -1, p) * Rm % p for x in a[:k]]
+    # binary (Kaliski) inverse on the edge values too (0 -> 0), and against the Fermat ladder it replaced
+    tail = a[-2 * len(edge):]
+    T = pack(tail)
+    Ot, Of = np.zeros_like(T), np.zeros_like(T)
+    getattr(shim, name + "_inv")(_p(T), _p(Ot), C.c_long(len(tail)))
+    getattr(shim, name + "_inv_fermat")(_p(T), _p(Of), C.c_long(len(tail)))
+    assert unpack(Ot) == [0 if x == 0 else pow(x * Ri % p, -1, p) * Rm % p for x in tail]
+    assert (Ot == Of).all()
+    small = [(v * Rm) % p for v in (1, 2, 3, 4, 2 ** 200, p - 1)] + [1, 2, 4, 2 ** 31, 2 ** 32, 2 ** 253]
+    Sm = pack(small)
+    Os = np.zeros_like(Sm)
+    getattr(shim, name + "_inv")(_p(Sm), _p(Os), C.c_long(len(small)))
+    assert unpack(Os) == [pow(x * Ri % p, -1, p) * Rm % p for x in small]
     getattr(shim, name + "_to_canonical")(_p(A), _p(O), C.c_long(k))
     assert unpack(O[:k]) == [x * Ri % p for x in a[:k]]
     # from_canonical must reduce ANY 256-bit integer (transcript challenges are raw hashes)
