@@ -181,16 +181,20 @@ __device__ __forceinline__ Fr fr_canon_ni(const Fr& a) {
   return fr_mul_ni(a, one);
 }
 
+// round constants and rho offsets (indexed by lane = x + 5y) in the constant bank: no local-memory (stack) traffic in
+// the single-warp Fiat-Shamir tail, whose L1 contents a system-scope acquire fence of the multi-GPU path invalidates
+__constant__ uint64_t KECCAK_RC_DEV[24] = {
+    0x0000000000000001ULL, 0x0000000000008082ULL, 0x800000000000808aULL, 0x8000000080008000ULL,
+    0x000000000000808bULL, 0x0000000080000001ULL, 0x8000000080008081ULL, 0x8000000000008009ULL,
+    0x000000000000008aULL, 0x0000000000000088ULL, 0x0000000080008009ULL, 0x000000008000000aULL,
+    0x000000008000808bULL, 0x800000000000008bULL, 0x8000000000008089ULL, 0x8000000000008003ULL,
+    0x8000000000008002ULL, 0x8000000000000080ULL, 0x000000000000800aULL, 0x800000008000000aULL,
+    0x8000000080008081ULL, 0x8000000000008080ULL, 0x0000000080000001ULL, 0x8000000080008008ULL};
+__constant__ unsigned KECCAK_RHO_DEV[25] = {0,  1,  62, 28, 27, 36, 44, 6,  55, 20, 3,  10, 43,
+                                            25, 39, 41, 45, 15, 21, 8,  18, 2,  61, 56, 14};
 static __device__ __noinline__ void keccak_f1600_warp(uint64_t* s) {
-  const uint64_t RC[24] = {
-      0x0000000000000001ULL, 0x0000000000008082ULL, 0x800000000000808aULL, 0x8000000080008000ULL,
-      0x000000000000808bULL, 0x0000000080000001ULL, 0x8000000080008081ULL, 0x8000000000008009ULL,
-      0x000000000000008aULL, 0x0000000000000088ULL, 0x0000000080008009ULL, 0x000000008000000aULL,
-      0x000000008000808bULL, 0x800000000000008bULL, 0x8000000000008089ULL, 0x8000000000008003ULL,
-      0x8000000000008002ULL, 0x8000000000000080ULL, 0x000000000000800aULL, 0x800000008000000aULL,
-      0x8000000080008081ULL, 0x8000000000008080ULL, 0x0000000080000001ULL, 0x8000000080008008ULL};
-  // rho offsets indexed by lane = x + 5y
-  const unsigned RHO[25] = {0, 1, 62, 28, 27, 36, 44, 6, 55, 20, 3, 10, 43, 25, 39, 41, 45, 15, 21, 8, 18, 2, 61, 56, 14};
+  const uint64_t* RC = KECCAK_RC_DEV;
+  const unsigned* RHO = KECCAK_RHO_DEV;
   const unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   const int l = lane < 25 ? lane : 0;  // lanes 25..31 idle along (never read by the others, never store)
