@@ -334,11 +334,15 @@ int b200_hyperplonk_preprocess(b200_ctx* h, int k, int num_instances, int num_wi
   hp.num_poly = 1 + npreprocess + num_witness_polys;
   for (int i = 0; i < npreprocess; ++i) hp.preprocess.push_back((const Fr*)dev_preprocess[i]);
   hp.perm_idx.assign(permutation_polys, permutation_polys + nperm);
+  uint64_t* d_u64 = nullptr;
   auto fail = [&](int rc) {
     for (Fr* p : hp.perm) cudaFree(p);
+    if (d_u64) cudaFree(d_u64);
     delete obj;
     return rc;
   };
+  for (int i = 0; i < nperm; ++i)
+    if (hp.perm_idx[i] < 0 || hp.perm_idx[i] >= hp.num_poly) return fail(B200_ERR_ARG);
   // constraints and lookups
   std::vector<ExprP> constraints;
   const int32_t *t = constraint_tokens, *tend = constraint_tokens + nconstraint_tokens;
@@ -383,7 +387,6 @@ int b200_hyperplonk_preprocess(b200_ctx* h, int k, int num_instances, int num_wi
     }
     cy += 2 * len;
   }
-  uint64_t* d_u64 = nullptr;
   if (nperm) {
     if (cudaMalloc(&d_u64, N * sizeof(uint64_t)) != cudaSuccess) return fail(B200_ERR_NOMEM);
     for (int i = 0; i < nperm; ++i) {
@@ -393,9 +396,10 @@ int b200_hyperplonk_preprocess(b200_ctx* h, int k, int num_instances, int num_wi
       cudaMemcpyAsync(d_u64, perms[i].data(), N * sizeof(uint64_t), cudaMemcpyHostToDevice, c->stream);
       u64_rows_to_fr_kernel<<<2 * NUM_SMS, 256, 0, c->stream>>>(d_u64, N, d);
       count_launch(c);
-      cudaStreamSynchronize(c->stream);
+      if (cudaStreamSynchronize(c->stream) != cudaSuccess) return fail(B200_ERR_CUDA);
     }
     cudaFree(d_u64);
+    d_u64 = nullptr;
   }
   // commitments (hyperplonk.rs:127-150)
   const int ncomm = npreprocess + nperm;

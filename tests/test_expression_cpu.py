@@ -188,3 +188,31 @@ def test_generic_oracle_vs_materialised_table_model():
     O.sumcheck_prove_generic(to, n, expr, [O.fr_from_ints(p) for p in polys_i], O.fr_from_ints(ch_i), [O.fr_from_ints(y_i)],
                              O.fr_from_ints([claim_i])[0])
     assert to.proof() == tr.stream
+
+
+def test_native_compiler_rejects_malformed_token_streams():
+    """b200_expression_compile (host code, no GPU): truncated / out-of-range streams are B200_ERR_ARG, not a crash."""
+    import ctypes as C
+
+    import halo2_lasso_b200 as hl
+
+    def compile_raw(tokens, nconsts=1):
+        t = np.asarray(tokens, dtype=np.int32)
+        consts = np.zeros((max(1, nconsts), 4), dtype=np.uint64)
+        leaves = np.zeros((64, 3), dtype=np.int32)
+        cout = np.zeros((64, 4), dtype=np.uint64)
+        cchal = np.zeros(64, dtype=np.int32)
+        ops = np.zeros((64, 4), dtype=np.int32)
+        n = [C.c_int() for _ in range(5)]
+        return hl.lib().b200_expression_compile(hl._p(t), C.c_int(len(t)), hl._p(consts), C.c_int(nconsts), hl._p(leaves),
+                                                C.c_int(64), C.byref(n[0]), hl._p(cout), hl._p(cchal), C.c_int(64),
+                                                C.byref(n[1]), hl._p(ops), C.c_int(64), C.byref(n[2]), C.byref(n[3]),
+                                                C.byref(n[4]))
+
+    assert compile_raw([8, 4, 0, 0, 4, 1, 0]) == hl.B200_OK          # poly0 * poly1
+    assert compile_raw([8, 4, 0, 0]) == hl.B200_ERR_ARG               # product with one operand
+    assert compile_raw([8, 4, 0, 0, 4, 1]) == hl.B200_ERR_ARG         # truncated query
+    assert compile_raw([0, 3]) == hl.B200_ERR_ARG                     # constant index out of range
+    assert compile_raw([42]) == hl.B200_ERR_ARG                       # unknown node kind
+    assert compile_raw([4, 0, 0, 4, 1, 0]) == hl.B200_ERR_ARG         # trailing tokens
+    assert compile_raw([10, 0, 4, 0, 0]) == hl.B200_ERR_ARG           # DistributePowers with no terms
