@@ -89,3 +89,20 @@ def test_whole_provers_verify_with_the_pairing_check():
     tr = O.Transcript()
     assert hp.prove(tr, inst, [O.fr_from_ints(c) for c in w])
     assert hp.verify(O.Transcript(tr.proof()), inst)
+
+
+def test_pairing_value_matches_independent_python_model():
+    """oracle/pairing.hpp (2-3-2 tower, twist coordinates, sparse lines) against tests/golden/pymodel_pairing.py (single
+    degree-12 extension, untwisted points, generic Fq12 line functions): e(G1, G2) and e(3 G1, 5 G2) agree coefficient
+    by coefficient after the change of basis."""
+    import os
+    import sys
+
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import pymodel_pairing as M
+
+    want = M.pairing(M.G1, M.G2)
+    got = M.tower_to_w(O.pairing_gen_multiples(fr(1), fr(1)))
+    assert got == want
+    assert M.tower_to_w(O.pairing_gen_multiples(fr(3), fr(5))) == M.fpow(want, 15)
+    assert M.fpow(want, R_MOD) == M.ONE and want != M.ONE
