@@ -11,7 +11,7 @@ import pymodel as M
 import pymodel_lasso as L
 
 cases = []
-for kind, c, mu, seed in ((L.XOR, 2, 2, 41), (L.RANGE, 2, 3, 42)):
+for kind, c, mu, seed in ((L.XOR, 2, 2, 41), (L.RANGE, 2, 3, 42), (L.AND, 3, 2, 43)):
     m = 1 << mu
     bits = (16 if kind == L.RANGE else 8) * c
     xs = [M.sm64(seed, i) & ((1 << bits) - 1) for i in range(m)]
