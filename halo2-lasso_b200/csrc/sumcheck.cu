@@ -221,6 +221,151 @@ __global__ void __launch_bounds__(SC_THREADS) sc_eval_round_kernel(ScEvalArgs a)
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Tail of a sum-check in ONE launch. Once a round has at most TAIL_ITEMS (pair, term) items its kernel is pure
+// latency: launch, per-CTA partials through global memory, the last-CTA ticket, transcript copies in and out. This
+// kernel runs ALL remaining rounds in a single CTA: the tables are bound into shared memory once (<= 32 KB), each
+// thread owns one (pair, term) item per round, warp 0 runs the Fiat-Shamir step on a transcript that stays in shared
+// memory, and the final evaluations (sc_final_bind_kernel's job) are written at the end. Same field operations in
+// the same association as the per-round kernels, hence the same transcript bytes.
+// ---------------------------------------------------------------------------------------------
+static const int TAIL_ITEMS = 256;     // pairs * T of the first tail round
+static const int TAIL_ENTRIES = 1024;  // (ntab + 1) * 2 * pairs: shared-memory table entries (32 KB)
+struct ScTailArgs {
+  const Fr* in[SC_MAX_TABLES + 1];  // tables BEFORE the bind of the first tail round; index ntab = eq table
+  const Fr* weights;
+  ScState* st;
+  Transcript* tr;
+  const BaryTable* bary;
+  Fr* challenges_out;
+  Fr* evals_out;
+  uint32_t pairs;  // pairs of the first tail round
+  int T, first_round, num_rounds, want_eq_eval;
+};
+
+template <int NP>
+__global__ void __launch_bounds__(256) sc_eval_tail_kernel(ScTailArgs a) {
+  constexpr int D = NP + 1;
+  __shared__ Fr tab[TAIL_ENTRIES];
+  __shared__ Fr red[(256 / 32) * D];
+  __shared__ Transcript sh_tr;
+  __shared__ Fr s_ch, s_claim;
+  pdl_prologue();
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int ntab = a.T * NP, ntabs = ntab + 1;
+  uint32_t pairs = a.pairs;
+  Fr r = fe_ld(&a.st->r);
+  if (tid == 0) s_claim = fe_ld(&a.st->claim);
+  // bind of the previous challenge: 4 entries -> 2 per pair and table, into shared memory
+  for (uint32_t e = tid; e < (uint32_t)ntabs * 2 * pairs; e += blockDim.x) {
+    const uint32_t i = e / (2 * pairs), idx = e % (2 * pairs);
+    const Fr x0 = fe_ldg(a.in[i] + 2 * (size_t)idx), x1 = fe_ldg(a.in[i] + 2 * (size_t)idx + 1);
+    tab[e] = (x1 - x0) * r + x0;
+  }
+  if (tid < 32) trw_copy(&sh_tr, a.tr);
+  __syncthreads();
+  for (int round = a.first_round; round < a.num_rounds; ++round) {
+    // ---- evaluate: thread = (term, pair) item ------------------------------------------------------
+    Fr acc[D];
+#pragma unroll
+    for (int x = 0; x < D; ++x) acc[x] = fe_zero<FrP>();
+    if ((uint32_t)tid < pairs * (uint32_t)a.T) {
+      const uint32_t t = tid / pairs, b = tid % pairs;
+      const Fr* et = tab + (size_t)ntab * 2 * pairs;
+      const Fr* pt = tab + (size_t)(t * NP) * 2 * pairs;
+      Fr e0 = et[2 * b], e1 = et[2 * b + 1], p0 = pt[2 * b], p1 = pt[2 * b + 1], q0, q1;
+      if (NP == 2) {
+        const Fr* qt = pt + 2 * pairs;
+        q0 = qt[2 * b];
+        q1 = qt[2 * b + 1];
+      }
+      e0 = e1 - e0;
+      p0 = p1 - p0;
+      if (NP == 2) q0 = q1 - q0;
+      const Fr w = fe_ld(a.weights + t);
+#pragma unroll
+      for (int x = 0; x < D; ++x) {
+        Fr prod = e1 * p1;
+        if (NP == 2) prod = prod * q1;
+        acc[x] = prod * w;
+        if (x + 1 < D) {
+          e1 = e1 + e0;
+          p1 = p1 + p0;
+          if (NP == 2) q1 = q1 + q0;
+        }
+      }
+    }
+    block_reduce_fr<D>(acc, red);
+    // ---- warp 0: message, challenge, next claim (same scheme as sc_eval_round_kernel) -----------------
+    if (tid < 32) {
+      Fr mine = fe_zero<FrP>();  // lane i owns p(i)
+#pragma unroll
+      for (int x = 0; x < D; ++x) {
+        const Fr tmp = fr_bcast(acc[x], 0);
+        if (lane == x + 1) mine = tmp;
+      }
+      const Fr p1v = fr_bcast(mine, 1);
+      if (lane == 0) mine = s_claim - p1v;  // p(0) = sum - p(1)   (eval.rs:129)
+      const Fr canon = fr_canon_ni(mine);
+      for (int x = 0; x <= D; ++x) trw_write_canon_from_lane(&sh_tr, canon, x, true);
+      const Fr ch = trw_squeeze(&sh_tr);
+      const Fr one = fe_one<FrP>();
+      Fr num = lane <= D ? a.bary->w[D][lane <= D ? lane : 0] : fe_zero<FrP>();
+      Fr jf = fe_zero<FrP>();
+      for (int j = 0; j <= D; ++j) {
+        const Fr f = (j == lane) ? one : ch - jf;
+        num = fr_mul_ni(num, f);
+        jf = jf + one;
+      }
+      Fr term = fr_mul_ni(num, mine);
+      if (lane > D) term = fe_zero<FrP>();
+#pragma unroll
+      for (int off = 1; off < 8; off <<= 1) {
+        Fr o;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o.v[i] = __shfl_xor_sync(0xffffffffu, term.v[i], off);
+        term = term + o;
+      }
+      if (lane == 0) {
+        s_ch = ch;
+        s_claim = term;
+        fe_st(a.challenges_out + round, ch);
+      }
+    }
+    __syncthreads();
+    r = s_ch;
+    if (round + 1 == a.num_rounds) break;
+    // ---- bind for the next round: 2 * pairs entries -> pairs entries per table (in place, two phases) ----
+    const uint32_t half = pairs;  // new entries per table
+    Fr nv[4];
+    int cnt = 0;
+    for (uint32_t e = tid; e < (uint32_t)ntabs * half; e += blockDim.x) {
+      const uint32_t i = e / half, idx = e % half;
+      const Fr x0 = tab[(size_t)i * 2 * pairs + 2 * idx], x1 = tab[(size_t)i * 2 * pairs + 2 * idx + 1];
+      nv[cnt++] = (x1 - x0) * r + x0;
+    }
+    __syncthreads();
+    cnt = 0;
+    for (uint32_t e = tid; e < (uint32_t)ntabs * half; e += blockDim.x) tab[e] = nv[cnt++];  // table i at i * half
+    __syncthreads();
+    pairs >>= 1;
+  }
+  // ---- final bind (tables have 2 entries) and state write-back ------------------------------------------
+  const int nfinal = ntab + (a.want_eq_eval ? 1 : 0);
+  for (int i = tid; i < nfinal; i += blockDim.x) {
+    const Fr x0 = tab[2 * i], x1 = tab[2 * i + 1];
+    fe_st(a.evals_out + i, (x1 - x0) * r + x0);
+  }
+  if (tid < 32) {
+    trw_copy(a.tr, &sh_tr);
+    if (lane == 0) {
+      fe_st(&a.st->r, r);
+      fe_st(&a.st->claim, s_claim);
+    }
+  }
+}
+
 // After the last round every table has 2 entries: bind them with the last challenge.
 __global__ void sc_final_bind_kernel(const Fr* const* tabs, int ntabs, const ScState* st, Fr* evals_out) {
   pdl_prologue();
@@ -285,10 +430,11 @@ int sumcheck_prove_evals(Ctx* c, const ScEvalJob& job) {
   const Fr* cur[SC_MAX_TABLES + 1];  // current (unbound) tables; slot ntab = eq
   for (int i = 0; i < ntab; ++i) cur[i] = job.tables[i];
   cur[ntab] = job.eq_table ? job.eq_table : eq0;
+  bool tail_done = false;
   for (int round = 0; round < n; ++round) {
     a.round = round;
-    if (a.peer.world > 1) a.seq = ++c->peer_seq;
     a.pairs = (uint32_t)(N >> (round + 1));
+    if (a.peer.world > 1) a.seq = ++c->peer_seq;
     Fr* dst_base = (round & 1) ? bufA : bufB;  // round 1 writes A, round 2 writes B, ...
     const size_t dst_sz = (round & 1) ? szA : szB;
     a.eq_in = cur[ntab];
@@ -296,6 +442,28 @@ int sumcheck_prove_evals(Ctx* c, const ScEvalJob& job) {
     for (int i = 0; i < ntab; ++i) {
       a.in[i] = cur[i];
       a.out[i] = dst_base + (size_t)i * dst_sz;
+    }
+    if (round >= 1 && !c->profile && !c->dbg_clocks && a.peer.world == 1 && (size_t)a.pairs * T <= TAIL_ITEMS &&
+        (size_t)(ntab + 1) * 2 * a.pairs <= TAIL_ENTRIES) {
+      // all remaining rounds (and the final bind) in one single-CTA launch
+      ScTailArgs ta;
+      for (int i = 0; i <= ntab; ++i) ta.in[i] = cur[i];
+      ta.weights = job.weights;
+      ta.st = c->d_sc;
+      ta.tr = c->d_tr;
+      ta.bary = c->d_bary;
+      ta.challenges_out = job.challenges_out;
+      ta.evals_out = job.evals_out;
+      ta.pairs = a.pairs;
+      ta.T = T;
+      ta.first_round = round;
+      ta.num_rounds = n;
+      ta.want_eq_eval = job.want_eq_eval ? 1 : 0;
+      if (NP == 1) CUDA_TRY(launch_pdl(sc_eval_tail_kernel<1>, dim3(1), dim3(256), 0, s, ta));
+      else CUDA_TRY(launch_pdl(sc_eval_tail_kernel<2>, dim3(1), dim3(256), 0, s, ta));
+      count_launch(c);
+      tail_done = true;
+      break;
     }
     dim3 grid(blocks_for(a.pairs, T), T);
     if ((size_t)grid.x * grid.y * (NP + 1) > c->partial_elems) return B200_ERR_NOMEM;
@@ -319,13 +487,15 @@ int sumcheck_prove_evals(Ctx* c, const ScEvalJob& job) {
     count_launch(c);
   }
   // final bind -> evals (eq excluded: ProverState::into_evals returns the polys only, classic.rs:143-149)
-  const Fr** d_ptrs = nullptr;
-  const int nfinal = ntab + (job.want_eq_eval ? 1 : 0);
-  CUDA_TRY(cudaMallocAsync(&d_ptrs, nfinal * sizeof(Fr*), s));
-  CUDA_TRY(cudaMemcpyAsync(d_ptrs, cur, nfinal * sizeof(Fr*), cudaMemcpyHostToDevice, s));
-  CUDA_TRY(launch_pdl(sc_final_bind_kernel, dim3((nfinal + 63) / 64), dim3(64), 0, s, d_ptrs, nfinal, c->d_sc, job.evals_out));
-  count_launch(c);
-  CUDA_TRY(cudaFreeAsync(d_ptrs, s));
+  if (!tail_done) {
+    const Fr** d_ptrs = nullptr;
+    const int nfinal = ntab + (job.want_eq_eval ? 1 : 0);
+    CUDA_TRY(cudaMallocAsync(&d_ptrs, nfinal * sizeof(Fr*), s));
+    CUDA_TRY(cudaMemcpyAsync(d_ptrs, cur, nfinal * sizeof(Fr*), cudaMemcpyHostToDevice, s));
+    CUDA_TRY(launch_pdl(sc_final_bind_kernel, dim3((nfinal + 63) / 64), dim3(64), 0, s, d_ptrs, nfinal, c->d_sc, job.evals_out));
+    count_launch(c);
+    CUDA_TRY(cudaFreeAsync(d_ptrs, s));
+  }
   if (eq0) CUDA_TRY(cudaFreeAsync(eq0, s));
   CUDA_TRY(cudaFreeAsync(bufA, s));
   CUDA_TRY(cudaFreeAsync(bufB, s));
