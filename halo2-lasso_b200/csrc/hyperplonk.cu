@@ -231,7 +231,9 @@ static int expression_rows(Ctx* c, int num_vars, const ExprP& expr, const Fr* co
 
 struct HyperPlonk {
   Ctx* c;
-  int k, num_instances, num_witness, num_poly, num_z, chunk_size;
+  int k, num_witness, num_poly, num_z, chunk_size;
+  std::vector<int> num_instances;                     // per instance column (pb/backend.rs:50-51)
+  std::vector<int> phase_witness, phase_challenges;   // per witness phase (pb/backend.rs:55-60)
   std::vector<const Fr*> preprocess;  // device, borrowed from the caller
   std::vector<int> perm_idx;
   std::vector<Fr*> perm;              // device, owned
@@ -247,6 +249,15 @@ struct b200_hyperplonk {
 };
 
 using namespace b200;
+
+// every Polynomial / Challenge index of the tree is below the given counts
+static bool indices_in_range(const ExprP& e, int npolys, int nchallenges) {
+  if (e->kind == Expr::POLY && (e->a < 0 || e->a >= npolys)) return false;
+  if (e->kind == Expr::CHALLENGE && (e->a < 0 || e->a >= nchallenges)) return false;
+  for (auto& c : e->ch)
+    if (!indices_in_range(c, npolys, nchallenges)) return false;
+  return true;
+}
 
 static int commit_polys(Ctx* c, const std::vector<const Fr*>& polys, int k, bool write, G1Aff* d_out) {
   if (polys.empty()) return B200_OK;
@@ -315,23 +326,38 @@ int b200_sumcheck_prove_expression(b200_ctx* h, int num_vars, const int32_t* tok
   return B200_OK;
 }
 
-int b200_hyperplonk_preprocess(b200_ctx* h, int k, int num_instances, int num_witness_polys, int npreprocess,
-                               const void* const* dev_preprocess, int nconstraints, const int32_t* constraint_tokens,
-                               int nconstraint_tokens, int nlookups, const int32_t* lookup_tokens, int nlookup_tokens,
-                               const void* consts_fr, int nconsts, int nperm, const int32_t* permutation_polys,
-                               int ncycles, const int32_t* cycles_flat, int max_degree, b200_hyperplonk** out) {
+int b200_hyperplonk_preprocess_phased(b200_ctx* h, int k, int ninstance_cols, const int32_t* num_instances, int nphases,
+                                      const int32_t* num_witness_polys, const int32_t* num_challenges, int npreprocess,
+                                      const void* const* dev_preprocess, int nconstraints,
+                                      const int32_t* constraint_tokens, int nconstraint_tokens, int nlookups,
+                                      const int32_t* lookup_tokens, int nlookup_tokens, const void* consts_fr,
+                                      int nconsts, int nperm, const int32_t* permutation_polys, int ncycles,
+                                      const int32_t* cycles_flat, int max_degree, b200_hyperplonk** out) {
   Ctx* c = &h->c;
-  if (k < 1 || k > 30 || (int)c->srs.size() <= k || num_instances < 0 || num_witness_polys < 1 || npreprocess < 0 ||
-      nconstraints < 1 || nperm < 0 || nperm > 8 || max_degree < 2)
+  if (k < 1 || k > 30 || (int)c->srs.size() <= k || ninstance_cols < 0 || ninstance_cols > 8 || nphases < 1 ||
+      nphases > 8 || npreprocess < 0 || nconstraints < 1 || nperm < 0 || nperm > 8 || max_degree < 2)
     return B200_ERR_ARG;
   const size_t N = (size_t)1 << k;
+  // PlonkishCircuitInfo::is_well_formed (pb/backend.rs:76-105): every phase has witness polynomials, every phase but
+  // the last one has challenges; an instance column fits the rows bh[1..] (prover.rs:32-48)
+  int total_witness = 0, total_challenges = 0;
+  for (int i = 0; i < nphases; ++i) {
+    if (num_witness_polys[i] < 1 || num_challenges[i] < 0 || (i + 1 < nphases && num_challenges[i] == 0)) return B200_ERR_ARG;
+    total_witness += num_witness_polys[i];
+    total_challenges += num_challenges[i];
+  }
+  for (int i = 0; i < ninstance_cols; ++i)
+    if (num_instances[i] < 0 || (size_t)num_instances[i] + 1 > N) return B200_ERR_ARG;
+  if (total_witness > 32 || total_challenges > 64) return B200_ERR_ARG;
   b200_hyperplonk* obj = new b200_hyperplonk();
   HyperPlonk& hp = obj->hp;
   hp.c = c;
   hp.k = k;
-  hp.num_instances = num_instances;
-  hp.num_witness = num_witness_polys;
-  hp.num_poly = 1 + npreprocess + num_witness_polys;
+  hp.num_instances.assign(num_instances, num_instances + ninstance_cols);
+  hp.phase_witness.assign(num_witness_polys, num_witness_polys + nphases);
+  hp.phase_challenges.assign(num_challenges, num_challenges + nphases);
+  hp.num_witness = total_witness;
+  hp.num_poly = ninstance_cols + npreprocess + total_witness;
   for (int i = 0; i < npreprocess; ++i) hp.preprocess.push_back((const Fr*)dev_preprocess[i]);
   hp.perm_idx.assign(permutation_polys, permutation_polys + nperm);
   uint64_t* d_u64 = nullptr;
@@ -365,7 +391,17 @@ int b200_hyperplonk_preprocess(b200_ctx* h, int k, int num_instances, int num_wi
     }
     hp.lookups.push_back(cols);
   }
-  hp.expression = e_compose(k, constraints, hp.num_poly, hp.perm_idx, 0, max_degree, hp.lookups, &hp.num_z, &hp.chunk_size);
+  hp.expression = e_compose(k, constraints, hp.num_poly, hp.perm_idx, total_challenges, max_degree, hp.lookups, &hp.num_z,
+                            &hp.chunk_size);
+  {  // polynomial and challenge indices in range (is_well_formed, pb/backend.rs:94-97)
+    bool ok = true;
+    for (auto& e : constraints) ok = ok && indices_in_range(e, hp.num_poly, total_challenges);
+    for (auto& cols : hp.lookups)
+      for (auto& col : cols)
+        ok = ok && indices_in_range(col.first, hp.num_poly, total_challenges) &&
+             indices_in_range(col.second, hp.num_poly, total_challenges);
+    if (!ok) return fail(B200_ERR_ARG);
+  }
   if (hp.num_z > 8 || hp.chunk_size > 8) return fail(B200_ERR_ARG);
   // permutation_polys (preprocessor.rs:172-203): identity (i << k) + j, then every cycle rotated by one
   std::vector<std::vector<uint64_t>> perms(nperm, std::vector<uint64_t>(N));
@@ -422,6 +458,19 @@ int b200_hyperplonk_preprocess(b200_ctx* h, int k, int num_instances, int num_wi
   return B200_OK;
 }
 
+// one instance column, one witness phase without challenges (the reference's own test circuits, util.rs:30-98)
+int b200_hyperplonk_preprocess(b200_ctx* h, int k, int num_instances, int num_witness_polys, int npreprocess,
+                               const void* const* dev_preprocess, int nconstraints, const int32_t* constraint_tokens,
+                               int nconstraint_tokens, int nlookups, const int32_t* lookup_tokens, int nlookup_tokens,
+                               const void* consts_fr, int nconsts, int nperm, const int32_t* permutation_polys,
+                               int ncycles, const int32_t* cycles_flat, int max_degree, b200_hyperplonk** out) {
+  const int32_t ni = num_instances, nw = num_witness_polys, nc = 0;
+  return b200_hyperplonk_preprocess_phased(h, k, 1, &ni, 1, &nw, &nc, npreprocess, dev_preprocess, nconstraints,
+                                           constraint_tokens, nconstraint_tokens, nlookups, lookup_tokens, nlookup_tokens,
+                                           consts_fr, nconsts, nperm, permutation_polys, ncycles, cycles_flat, max_degree,
+                                           out);
+}
+
 void b200_hyperplonk_free(b200_hyperplonk* obj) {
   if (!obj) return;
   for (Fr* p : obj->hp.perm) cudaFree(p);
@@ -451,50 +500,88 @@ int b200_hyperplonk_permutation_poly(const b200_hyperplonk* obj, int i, void* ho
 }
 
 // hyperplonk.rs:164-291; appends to the context transcript
-int b200_hyperplonk_prove(b200_hyperplonk* obj, const void* host_instances_fr, int ninstances,
-                          const void* const* dev_witness) {
+int b200_hyperplonk_prove_phased(b200_hyperplonk* obj, const void* host_instances_fr, int ninstances,
+                                 b200_synthesize_fn synthesize, void* user) {
   HyperPlonk& hp = obj->hp;
   Ctx* c = hp.c;
   cudaStream_t s = c->stream;
   const int k = hp.k, nwit = hp.num_witness, nlk = (int)hp.lookups.size(), nper = (int)hp.perm.size();
+  const int ncols = (int)hp.num_instances.size(), nphases = (int)hp.phase_witness.size();
   const size_t N = (size_t)1 << k;
-  if (ninstances != hp.num_instances || (size_t)ninstances + 1 > N) return B200_ERR_ARG;
+  int ninst_total = 0, nc = 0;  // nc: the circuit's own challenges; beta, gamma, alpha follow them (preprocessor.rs:28-30)
+  for (int n : hp.num_instances) ninst_total += n;
+  for (int n : hp.phase_challenges) nc += n;
+  if (ninstances != ninst_total || !synthesize) return B200_ERR_ARG;
   Arena ar(c);
   int rc;
-  // instances: absorbed, then the instance polynomial (prover.rs:32-48): instance i sits on row bh[i + 1]
+  // instances: absorbed column by column, then the instance polynomials (prover.rs:32-48): instance i of a column
+  // sits on row bh[i + 1]
   Fr* d_inst = ar.upload<Fr>((const Fr*)host_instances_fr, ninstances);
-  Fr* inst_poly = ar.alloc<Fr>(N);
   std::vector<uint64_t> rows(ninstances ? ninstances : 1);
   {
-    uint64_t b = 1;
-    for (int i = 0; i < ninstances; ++i) {
-      rows[i] = b;
-      b = bh_next(b, k);
+    int o = 0;
+    for (int n : hp.num_instances) {
+      uint64_t b = 1;
+      for (int i = 0; i < n; ++i) {
+        rows[o++] = b;
+        b = bh_next(b, k);
+      }
     }
   }
   uint64_t* d_rows = ar.upload<uint64_t>(rows.data(), rows.size());
-  if (!d_inst || !inst_poly || !d_rows) return B200_ERR_NOMEM;
+  if (!d_inst || !d_rows) return B200_ERR_NOMEM;
   rc = transcript_op(c, TR_COMMON, d_inst, nullptr, ninstances);
   if (rc) return rc;
-  CUDA_TRY(cudaMemsetAsync(inst_poly, 0, N * sizeof(Fr), s));
-  if (ninstances) {
-    scatter_fr_kernel<<<(ninstances + 63) / 64, 64, 0, s>>>(d_inst, d_rows, ninstances, inst_poly);
-    count_launch(c);
-  }
-  // round 0: witness commitments
-  std::vector<const Fr*> wit(nwit);
-  for (int i = 0; i < nwit; ++i) wit[i] = (const Fr*)dev_witness[i];
-  G1Aff* d_comms = ar.alloc<G1Aff>(nwit + 2 * nlk + hp.num_z + 1);
-  Fr* d_ch = ar.alloc<Fr>(3 + k);  // beta, gamma, alpha, y[k]
-  Fr* d_zero = ar.alloc<Fr>(1);
-  if (!d_comms || !d_ch || !d_zero) return B200_ERR_NOMEM;
-  CUDA_TRY(cudaMemsetAsync(d_zero, 0, sizeof(Fr), s));
-  rc = commit_polys(c, wit, k, true, d_comms);
-  if (rc) return rc;
   std::vector<const Fr*> polys;
-  polys.push_back(inst_poly);
+  {
+    int o = 0;
+    for (int n : hp.num_instances) {
+      Fr* inst_poly = ar.alloc<Fr>(N);
+      if (!inst_poly) return B200_ERR_NOMEM;
+      CUDA_TRY(cudaMemsetAsync(inst_poly, 0, N * sizeof(Fr), s));
+      if (n) {
+        scatter_fr_kernel<<<(n + 63) / 64, 64, 0, s>>>(d_inst + o, d_rows + o, n, inst_poly);
+        count_launch(c);
+      }
+      polys.push_back(inst_poly);
+      o += n;
+    }
+  }
   polys.insert(polys.end(), hp.preprocess.begin(), hp.preprocess.end());
-  polys.insert(polys.end(), wit.begin(), wit.end());
+  // rounds 0..n (hyperplonk.rs:183-204): synthesize the phase's witness polynomials (the callback sees the challenges
+  // squeezed so far — the one host read-back of the phase loop), commit, squeeze the phase's challenges
+  G1Aff* d_comms = ar.alloc<G1Aff>(nwit + 2 * nlk + hp.num_z + 1);
+  Fr* d_chal = ar.alloc<Fr>(nc + 3 + k);  // circuit challenges, beta, gamma, alpha, y[k]
+  Fr* d_zero = ar.alloc<Fr>(1);
+  if (!d_comms || !d_chal || !d_zero) return B200_ERR_NOMEM;
+  Fr* d_ch = d_chal + nc;  // beta, gamma, alpha, y[k]
+  CUDA_TRY(cudaMemsetAsync(d_zero, 0, sizeof(Fr), s));
+  {
+    std::vector<Fr> host_chal(nc ? nc : 1);
+    int have = 0;
+    for (int round = 0; round < nphases; ++round) {
+      const int nw = hp.phase_witness[round];
+      if (have) {
+        CUDA_TRY(cudaMemcpyAsync(host_chal.data(), d_chal, have * sizeof(Fr), cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(cudaStreamSynchronize(s));
+      }
+      std::vector<const void*> dev(nw, nullptr);
+      if (synthesize(user, round, host_chal.data(), have, dev.data()) != 0) return B200_ERR_ARG;
+      std::vector<const Fr*> wit(nw);
+      for (int i = 0; i < nw; ++i) {
+        if (!dev[i]) return B200_ERR_ARG;
+        wit[i] = (const Fr*)dev[i];
+      }
+      rc = commit_polys(c, wit, k, true, d_comms);
+      if (rc) return rc;
+      polys.insert(polys.end(), wit.begin(), wit.end());
+      if (hp.phase_challenges[round]) {
+        rc = transcript_op(c, TR_SQUEEZE, nullptr, d_chal + have, hp.phase_challenges[round]);
+        if (rc) return rc;
+        have += hp.phase_challenges[round];
+      }
+    }
+  }
   // round n: beta; LogUp compressed polys and multiplicities (prover.rs:50-192)
   rc = transcript_op(c, TR_SQUEEZE, nullptr, d_ch, 1);
   if (rc) return rc;
@@ -510,10 +597,10 @@ int b200_hyperplonk_prove(b200_hyperplonk* obj, const void* host_instances_fr, i
       ins.push_back(col.first);
       tabs.push_back(col.second);
     }
-    // Σ_j beta^j column_j: beta is "challenge 0" of this little program (the circuit itself has no challenges)
-    rc = expression_rows(c, k, e_distribute_powers(ins, e_chal(0)), polys.data(), (int)polys.size(), d_ch, comp_in[l]);
+    // Σ_j beta^j column_j (prover.rs:78-134): beta is challenge `nc` of this little program, behind the circuit's own
+    rc = expression_rows(c, k, e_distribute_powers(ins, e_chal(nc)), polys.data(), (int)polys.size(), d_chal, comp_in[l]);
     if (rc) return rc;
-    rc = expression_rows(c, k, e_distribute_powers(tabs, e_chal(0)), polys.data(), (int)polys.size(), d_ch, comp_tab[l]);
+    rc = expression_rows(c, k, e_distribute_powers(tabs, e_chal(nc)), polys.data(), (int)polys.size(), d_chal, comp_tab[l]);
     if (rc) return rc;
     rc = lookup_m(c, k, comp_in[l], comp_tab[l], ms[l]);
     if (rc) return rc;
@@ -559,7 +646,7 @@ int b200_hyperplonk_prove(b200_hyperplonk* obj, const void* host_instances_fr, i
   Fr* d_x = ar.alloc<Fr>(k);
   Fr* d_evals = ar.alloc<Fr>(npolys);
   if (!d_x || !d_evals) return B200_ERR_NOMEM;
-  rc = prove_expression(c, k, hp.expression, polys.data(), npolys, d_ch, d_ch + 3, 1, d_zero, d_x, d_evals);
+  rc = prove_expression(c, k, hp.expression, polys.data(), npolys, d_chal, d_ch + 3, 1, d_zero, d_x, d_evals);
   if (rc) return rc;
   // pcs_query / points / evaluations (prover.rs:388-409, verifier.rs:147-182): queries in BTreeSet order
   std::vector<Leaf> leaves;
@@ -567,7 +654,7 @@ int b200_hyperplonk_prove(b200_hyperplonk* obj, const void* host_instances_fr, i
   std::set<std::pair<int, int>> queries;
   std::set<int> rotations;
   for (auto& l : leaves)
-    if (l.kind == Expr::POLY && l.a >= 1) {  // one instance polynomial (index 0): evaluated by the verifier itself
+    if (l.kind == Expr::POLY && l.a >= ncols) {  // instance polynomials: evaluated by the verifier itself (verifier.rs:92-145)
       queries.insert({l.a, l.b});
       rotations.insert(l.b);
     }
@@ -631,6 +718,19 @@ int b200_hyperplonk_prove(b200_hyperplonk* obj, const void* host_instances_fr, i
   if (rc) return rc;
   CUDA_TRY(cudaGetLastError());
   return B200_OK;
+}
+
+// single-phase circuits: the witness is known up front
+static int witness_given(void* user, int, const void*, int, const void** dev_witness_out) {
+  auto* w = (std::pair<const void* const*, int>*)user;
+  for (int i = 0; i < w->second; ++i) dev_witness_out[i] = w->first[i];
+  return 0;
+}
+int b200_hyperplonk_prove(b200_hyperplonk* obj, const void* host_instances_fr, int ninstances,
+                          const void* const* dev_witness) {
+  if (obj->hp.phase_witness.size() != 1) return B200_ERR_ARG;
+  std::pair<const void* const*, int> w{dev_witness, obj->hp.num_witness};
+  return b200_hyperplonk_prove_phased(obj, host_instances_fr, ninstances, witness_given, &w);
 }
 
 }  // extern "C"

@@ -22,6 +22,8 @@ from . import MultilinearPolynomial, _chk, _mont_consts, _p, lib
 from .expression import BooleanHypercube, Expression, R_MOD, serialize_expression
 
 R_INV = pow(1 << 256, -1, R_MOD)
+# b200_synthesize_fn (include/b200_lasso.h)
+SYNTHESIZE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_void_p))
 
 
 def mont_to_int(limbs):
@@ -82,6 +84,91 @@ class VanillaPlonkWithLookupCircuitInfo:
         self.constraints = [q_l * w_l + q_r * w_r + q_m * w_l * w_r + q_o * w_o + q_c + pi]
         self.lookups = [[(q_lookup * w_l, t_l), (q_lookup * w_r, t_r), (q_lookup * w_o, t_o)]]
         self.num_poly = 13
+
+
+class TwoPhaseCircuitInfo:
+    """A circuit with TWO instance columns and TWO witness phases (the shape `Halo2Circuit` yields for circuits with
+    challenges, pb/frontend/halo2.rs:150-160; pb/backend.rs:50-60). polys:
+        0 pi_a | 1 pi_b | 2 q_mix 3 q_io 4 q_io2 5 q_mul 6 q_lk 7 t | 8 a 9 b (phase 0) | 10 c 11 d (phase 1)
+    challenges 0, 1 = r0, r1 squeezed after the phase-0 commitments; c = a + r0*b and d = r1*a*b can only be
+    synthesized once they are known. pi_b is queried at Rotation::next (instance_evals, verifier.rs:92-145); the
+    lookup input q_lk*(c - r0*b) uses a circuit challenge inside a lookup expression (prover.rs:66-76)."""
+
+    def __init__(self, k, num_instances, preprocess_polys, permutations, with_lookup=True):
+        self.k, self.num_instances = k, list(num_instances)
+        self.preprocess_polys = preprocess_polys  # 6 lists of ints
+        self.permutations = permutations
+        self.permutation_polys = [8, 9, 10]
+        self.num_witness_polys = [2, 2]
+        self.num_challenges = [2, 0]
+        P, Ch = Expression.polynomial, Expression.challenge
+        pi_a, pi_b_next = P(0), P(1, 1)
+        q_mix, q_io, q_io2, q_mul, q_lk, t, a, b, c, d = (P(i) for i in range(2, 12))
+        self.constraints = [q_mix * (a + Ch(0) * b - c), q_io * (a - pi_a), q_io2 * (b - pi_b_next),
+                            q_mul * (Ch(1) * a * b - d)]
+        self.lookups = [[(q_lk * (c - Ch(0) * b), t)]] if with_lookup else []
+        self.num_poly = 12
+
+
+def rand_two_phase_circuit(k, seed, with_lookup=True):
+    """A random SATISFIABLE instance of TwoPhaseCircuitInfo. Returns (info, instance columns [pi_a, pi_b],
+    synthesize) where synthesize(round, challenges) -> witness columns of that phase, all canonical ints."""
+    assert k >= 4
+    rng = random.Random(seed)
+    N = 1 << k
+    order = BooleanHypercube(k).iter()
+    q = [[0] * N for _ in range(6)]  # q_mix q_io q_io2 q_mul q_lk t
+    a = [rng.randrange(R_MOD) for _ in range(N)]
+    b = [rng.randrange(R_MOD) for _ in range(N)]
+    for r in range(1, N):
+        q[5][r] = rng.randrange(R_MOD)  # table; row 0 holds 0 for the gated-off rows
+    inst_a = [rng.randrange(R_MOD) for _ in range(2)]
+    inst_b = [rng.randrange(R_MOD) for _ in range(3)]
+    used = {0}
+    for j, v in enumerate(inst_a):  # pi_a at Rotation::cur: instance j sits on row order[j + 1]
+        row = order[j + 1]
+        q[1][row], a[row] = 1, v
+        used.add(row)
+    for j, v in enumerate(inst_b):  # pi_b at Rotation::next: read from the row BEFORE order[j + 1] in the LFSR cycle
+        row = order[j] if j else order[N - 1]
+        q[2][row], b[row] = 1, v
+        used.add(row)
+    free = [r for r in range(1, N) if r not in used]
+    rng.shuffle(free)
+    cycles = []
+    for _ in range(max(1, len(free) // 8)):  # a[t] = b[s]
+        s_, t_ = free.pop(), free.pop()
+        a[t_] = b[s_]
+        cycles.append([(9, s_), (8, t_)])
+    twins = []
+    for _ in range(max(1, len(free) // 8)):  # rows with the same (a, b): their c values are copies of each other
+        s_, t_ = free.pop(), free.pop()
+        a[t_], b[t_] = a[s_], b[s_]
+        cycles.append([(10, s_), (10, t_)])
+        twins.append((s_, t_))
+    twin_rows = {r for tw in twins for r in tw}
+    for r in range(N):
+        q[0][r] = 1 if r in twin_rows else rng.randrange(2)
+        q[3][r] = rng.randrange(2)
+    for r in free[: len(free) // 2]:  # lookup rows: a is a table value
+        q[4][r] = 1
+        a[r] = q[5][rng.randrange(N)]
+        q[0][r] = 1  # the lookup input c - r0*b equals a only where the mix gate holds
+    info = TwoPhaseCircuitInfo(k, [len(inst_a), len(inst_b)], q, cycles, with_lookup)
+
+    fill = [[rng.randrange(R_MOD) for _ in range(N)] for _ in range(2)]  # c, d where their gates are off
+
+    def synthesize(rnd, challenges):
+        """PlonkishCircuit::synthesize (pb/backend.rs:100-110); deterministic: every prover sees the same witness"""
+        if rnd == 0:
+            assert len(challenges) == 0
+            return [list(a), list(b)]
+        r0, r1 = challenges
+        c = [(x + r0 * y) % R_MOD if q[0][r] else fill[0][r] for r, (x, y) in enumerate(zip(a, b))]
+        d = [r1 * x * y % R_MOD if q[3][r] else fill[1][r] for r, (x, y) in enumerate(zip(a, b))]
+        return [c, d]
+
+    return info, [inst_a, inst_b], synthesize
 
 
 def rand_vanilla_plonk_with_lookup_circuit(k, seed, num_instances=None, lookup_fraction=0.4):
@@ -251,12 +338,23 @@ class HyperPlonk:
         pidx = np.asarray(info.permutation_polys, dtype=np.int32)
         pre = (C.c_void_p * max(1, len(self.preprocess)))(*[p.dev for p in self.preprocess])
         self.h = C.c_void_p()
-        _chk(lib().b200_hyperplonk_preprocess(
-            ctx.h, C.c_int(k), C.c_int(info.num_instances), C.c_int(info.num_witness_polys), C.c_int(len(self.preprocess)),
-            pre, C.c_int(len(info.constraints)), _p(ctok), C.c_int(len(ctok)), C.c_int(len(info.lookups)), _p(ltok),
-            C.c_int(len(ltok) if info.lookups else 0), _p(cm), C.c_int(len(consts)), C.c_int(len(pidx)), _p(pidx),
-            C.c_int(len(info.permutations)), _p(flat), C.c_int(getattr(info, "max_degree", 4)), C.byref(self.h)),
-            "hyperplonk_preprocess")
+        # one instance column and one witness phase (the reference's own test circuits), or the general shape
+        self.instance_cols = list(info.num_instances) if isinstance(info.num_instances, (list, tuple)) else [info.num_instances]
+        self.phase_witness = list(info.num_witness_polys) if isinstance(info.num_witness_polys, (list, tuple)) else [info.num_witness_polys]
+        self.phase_challenges = list(getattr(info, "num_challenges", [0] * len(self.phase_witness)))
+        tail = (C.c_int(len(self.preprocess)),
+                pre, C.c_int(len(info.constraints)), _p(ctok), C.c_int(len(ctok)), C.c_int(len(info.lookups)), _p(ltok),
+                C.c_int(len(ltok) if info.lookups else 0), _p(cm), C.c_int(len(consts)), C.c_int(len(pidx)), _p(pidx),
+                C.c_int(len(info.permutations)), _p(flat), C.c_int(getattr(info, "max_degree", 4)), C.byref(self.h))
+        if isinstance(info.num_instances, int) and isinstance(info.num_witness_polys, int):
+            _chk(lib().b200_hyperplonk_preprocess(ctx.h, C.c_int(k), C.c_int(info.num_instances), C.c_int(info.num_witness_polys),
+                                                  *tail), "hyperplonk_preprocess")
+        else:
+            ni, nw, nc = (np.asarray(v if v else [0], dtype=np.int32) for v in
+                          (self.instance_cols, self.phase_witness, self.phase_challenges))
+            _chk(lib().b200_hyperplonk_preprocess_phased(ctx.h, C.c_int(k), C.c_int(len(self.instance_cols)), _p(ni),
+                                                         C.c_int(len(self.phase_witness)), _p(nw), _p(nc), *tail),
+                 "hyperplonk_preprocess_phased")
         nz, deg, npolys = C.c_int(), C.c_int(), C.c_int()
         _chk(lib().b200_hyperplonk_info(self.h, C.byref(nz), C.byref(deg), C.byref(npolys)), "hyperplonk_info")
         self.num_z, self.degree, self.num_polys = nz.value, deg.value, npolys.value
@@ -289,3 +387,35 @@ class HyperPlonk:
         ptrs = (C.c_void_p * len(wit))(*[p.dev for p in wit])
         _chk(lib().b200_hyperplonk_prove(self.h, _p(np.ascontiguousarray(inst)), C.c_int(len(instances)), ptrs),
              "hyperplonk_prove")
+
+    def prove_phased(self, instance_cols, synthesize):
+        """The phase loop of hyperplonk.rs:183-204 through `b200_hyperplonk_prove_phased`: `synthesize(round, challenges)`
+        plays PlonkishCircuit::synthesize — canonical-int challenges in, that phase's witness columns (canonical ints, or
+        device MultilinearPolynomials) out. `instance_cols`: one list per instance column."""
+        ctx = self.ctx
+        flat = [v for col in instance_cols for v in col]
+        inst = ints_to_mont(ctx, flat) if flat else np.zeros((1, 4), dtype=np.uint64)
+        keep, err = [], []
+
+        @SYNTHESIZE_FN
+        def cb(_user, rnd, chal_ptr, nchal, out):
+            try:
+                ch = np.zeros((max(1, nchal), 4), dtype=np.uint64)
+                if nchal:
+                    C.memmove(ch.ctypes.data, chal_ptr, nchal * 32)
+                cols = synthesize(rnd, [mont_to_int(ch[i]) for i in range(nchal)])
+                if len(cols) != self.phase_witness[rnd]:
+                    return 1
+                for i, col in enumerate(cols):
+                    poly = col if isinstance(col, MultilinearPolynomial) else upload_ints(ctx, col)
+                    keep.append(poly)  # alive until prove returns
+                    out[i] = poly.dev.value if hasattr(poly.dev, "value") else poly.dev
+                return 0
+            except Exception as e:  # never unwind through the C frames
+                err.append(e)
+                return 1
+
+        rc = lib().b200_hyperplonk_prove_phased(self.h, _p(np.ascontiguousarray(inst)), C.c_int(len(flat)), cb, None)
+        if err:
+            raise err[0]
+        _chk(rc, "hyperplonk_prove_phased")

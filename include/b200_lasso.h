@@ -159,6 +159,30 @@ int b200_hyperplonk_permutation_poly(const b200_hyperplonk* pp, int i, void* hos
 int b200_hyperplonk_prove(b200_hyperplonk* pp, const void* host_instances_fr, int ninstances,
                           const void* const* dev_witness);
 
+/* Circuits with several instance columns and / or several witness phases (PlonkishCircuitInfo::{num_instances,
+ * num_witness_polys, num_challenges}, pb/backend.rs:50-60; the phase loop of HyperPlonk::prove, hyperplonk.rs:183-204).
+ * Polynomial order: instance columns | preprocess | witness (phase 0, phase 1, ...) | permutation | lookup m | lookup h |
+ * permutation z; challenge order: the phases' challenges, then beta, gamma, alpha (preprocessor.rs:28-30).
+ * preprocess_phased: num_instances[ninstance_cols], num_witness_polys[nphases], num_challenges[nphases]; every phase
+ * needs witness polynomials and every phase but the last needs challenges (is_well_formed, backend.rs:76-105), else
+ * B200_ERR_ARG. The other arguments are those of b200_hyperplonk_preprocess.
+ * prove_phased: host_instances_fr = the instance columns back to back (ninstances = their total length). `synthesize`
+ * plays PlonkishCircuit::synthesize(round, challenges) (backend.rs:100-110): it receives the challenges squeezed so far
+ * (host, Montgomery) and stores the device pointers of that phase's num_witness_polys[round] witness polynomials
+ * (2^k elements each, caller-owned, alive until prove returns; work enqueued on the context stream is ordered before
+ * the commitments) into dev_witness_out; a non-zero return aborts the proof with B200_ERR_ARG. */
+typedef int (*b200_synthesize_fn)(void* user, int round, const void* host_challenges_fr, int nchallenges,
+                                  const void** dev_witness_out);
+int b200_hyperplonk_preprocess_phased(b200_ctx* ctx, int k, int ninstance_cols, const int32_t* num_instances, int nphases,
+                                      const int32_t* num_witness_polys, const int32_t* num_challenges, int npreprocess,
+                                      const void* const* dev_preprocess, int nconstraints,
+                                      const int32_t* constraint_tokens, int nconstraint_tokens, int nlookups,
+                                      const int32_t* lookup_tokens, int nlookup_tokens, const void* consts_fr,
+                                      int nconsts, int nperm, const int32_t* permutation_polys, int ncycles,
+                                      const int32_t* cycles_flat, int max_degree, b200_hyperplonk** out);
+int b200_hyperplonk_prove_phased(b200_hyperplonk* pp, const void* host_instances_fr, int ninstances,
+                                 b200_synthesize_fn synthesize, void* user);
+
 /* permutation_z_polys (pb/backend/hyperplonk/prover.rs:252-345) for one chunk of `npolys` wire columns:
  * grand-product polynomial z in BooleanHypercube order; id_offsets[i] = (index of wire i among the permuted
  * columns) << num_vars; host_beta_gamma = {beta, gamma}. dev_z_out[2^num_vars]. */

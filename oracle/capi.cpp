@@ -357,14 +357,60 @@ void orc_hp_permutation_poly(void* h, int i, Fr* out) {
   auto& p = ((HyperPlonkParams*)h)->permutation_polys[i];
   memcpy(out, p.data(), p.size() * sizeof(Fr));
 }
+// PlonkishCircuitInfo::{num_instances, num_witness_polys, num_challenges} (pb/backend.rs:50-60) for circuits with
+// several instance columns and / or several witness phases; without this call: one column, one phase, no challenges.
+int orc_hp_set_phases(void* h, int ncols, const int* num_instances, int nphases, const int* num_witness, const int* num_challenges) {
+  HyperPlonkParams* pp = (HyperPlonkParams*)h;
+  int total = 0;
+  for (int i = 0; i < nphases; ++i) total += num_witness[i];
+  if (total != pp->num_witness_polys) return 1;
+  pp->num_instances.assign(num_instances, num_instances + ncols);
+  pp->phase_witness_polys.assign(num_witness, num_witness + nphases);
+  pp->phase_challenges.assign(num_challenges, num_challenges + nphases);
+  return 0;
+}
+// instance columns back to back
+static std::vector<std::vector<Fr>> split_instances(const HyperPlonkParams& pp, const Fr* instances, int ninst) {
+  std::vector<std::vector<Fr>> out;
+  int off = 0;
+  for (int n : pp.num_instances) {
+    if (off + n > ninst) return {};
+    out.emplace_back(instances + off, instances + off + n);
+    off += n;
+  }
+  if (off != ninst) return {};
+  return out;
+}
 int orc_hp_prove(void* h, void* tr, const Fr* instances, int ninst, const Fr* const* witness, int nwit) {
   HyperPlonkParams* pp = (HyperPlonkParams*)h;
   std::vector<Poly> wit(nwit);
   for (int i = 0; i < nwit; ++i) wit[i].assign(witness[i], witness[i] + ((size_t)1 << pp->num_vars));
-  return hyperplonk_prove(*pp, {std::vector<Fr>(instances, instances + ninst)}, wit, *(Transcript*)tr) ? 0 : 1;
+  return hyperplonk_prove(*pp, split_instances(*pp, instances, ninst), wit, *(Transcript*)tr) ? 0 : 1;
+}
+// synthesize(user, round, challenges, nchallenges, out): fills out[i] (2^num_vars elements each, preallocated) with the
+// witness polynomials of that phase; returns 0 on success.
+typedef int (*orc_synthesize_fn)(void* user, int round, const Fr* challenges, int nchallenges, Fr* const* out);
+int orc_hp_prove_phased(void* h, void* tr, const Fr* instances, int ninst, orc_synthesize_fn synth, void* user) {
+  HyperPlonkParams* pp = (HyperPlonkParams*)h;
+  const size_t N = (size_t)1 << pp->num_vars;
+  bool synth_failed = false;
+  Synthesize fn = [&](int round, const std::vector<Fr>& challenges) {
+    const int nw = pp->phase_witness_polys.empty() ? pp->num_witness_polys : pp->phase_witness_polys[round];
+    std::vector<Poly> polys(nw, Poly(N, Fr::zero()));
+    std::vector<Fr*> ptrs;
+    for (auto& p : polys) ptrs.push_back(p.data());
+    if (synth(user, round, challenges.data(), (int)challenges.size(), ptrs.data()) != 0) {
+      synth_failed = true;
+      return std::vector<Poly>();
+    }
+    return polys;
+  };
+  const bool ok = hyperplonk_prove_phased(*pp, split_instances(*pp, instances, ninst), fn, *(Transcript*)tr);
+  return ok && !synth_failed ? 0 : 1;
 }
 int orc_hp_verify(void* h, void* tr, const Fr* instances, int ninst) {
-  return hyperplonk_verify(*(HyperPlonkParams*)h, {std::vector<Fr>(instances, instances + ninst)}, *(Transcript*)tr) ? 0 : 1;
+  HyperPlonkParams* pp = (HyperPlonkParams*)h;
+  return hyperplonk_verify(*pp, split_instances(*pp, instances, ninst), *(Transcript*)tr) ? 0 : 1;
 }
 void orc_permutation_z(int num_vars, int nperm, const Fr* const* perm_polys, const Fr* const* wires, const Fr* beta,
                        const Fr* gamma, Fr* out) {

@@ -15,6 +15,7 @@
 #pragma once
 #include <algorithm>
 #include <array>
+#include <functional>
 #include <map>
 #include <set>
 
@@ -123,8 +124,10 @@ inline Fr lagrange_eval(const std::vector<Fr>& x, uint64_t b) {  // sum_check.rs
 struct HyperPlonkParams {
   const KzgParams* kzg;
   int num_vars;
-  std::vector<int> num_instances;
-  int num_witness_polys;
+  std::vector<int> num_instances;     // per instance column (backend.rs:50-51)
+  int num_witness_polys;              // over all phases
+  std::vector<int> phase_witness_polys = {};  // per phase (backend.rs:55-60); empty = one phase without challenges
+  std::vector<int> phase_challenges = {};
   ExprP expression;
   std::vector<Poly> preprocess_polys;
   std::vector<G1Affine> preprocess_comms;
@@ -341,15 +344,34 @@ inline PcsQueryPlan pcs_query_plan(const ExprP& e, int num_instance_poly) {
   return pl;
 }
 
+// `PlonkishCircuit::synthesize(round, challenges)` (backend.rs:100-110): the witness polynomials of one phase
+typedef std::function<std::vector<Poly>(int, const std::vector<Fr>&)> Synthesize;
+
 // hyperplonk.rs:164-291
-inline bool hyperplonk_prove(const HyperPlonkParams& pp, const std::vector<std::vector<Fr>>& instances,
-                             const std::vector<Poly>& witness_polys, Transcript& tr) {
+inline bool hyperplonk_prove_phased(const HyperPlonkParams& pp, const std::vector<std::vector<Fr>>& instances,
+                                    const Synthesize& synthesize, Transcript& tr) {
   const int n = pp.num_vars;
+  if (instances.size() != pp.num_instances.size()) return false;
+  for (size_t i = 0; i < instances.size(); ++i)
+    if ((int)instances[i].size() != pp.num_instances[i]) return false;  // assert_eq! in the reference
   for (auto& inst : instances)
     for (auto& v : inst) tr.common_field_element(v);
   std::vector<Poly> inst_polys = instance_polys(n, instances);
-  for (auto& w : witness_polys)
-    if (!tr.write_commitment(kzg_commit(*pp.kzg, w))) return false;
+  // rounds 0..n (hyperplonk.rs:183-204): synthesize, commit, squeeze the phase's challenges
+  const std::vector<int> phase_w = pp.phase_witness_polys.empty() ? std::vector<int>{pp.num_witness_polys} : pp.phase_witness_polys;
+  const std::vector<int> phase_c = pp.phase_challenges.empty() ? std::vector<int>{0} : pp.phase_challenges;
+  std::vector<Poly> witness_polys;
+  std::vector<Fr> challenges;
+  for (size_t round = 0; round < phase_w.size(); ++round) {
+    std::vector<Poly> ps = synthesize((int)round, challenges);
+    if ((int)ps.size() != phase_w[round]) return false;
+    for (auto& w : ps) {
+      if (w.size() != (size_t)1 << n) return false;
+      if (!tr.write_commitment(kzg_commit(*pp.kzg, w))) return false;
+    }
+    for (auto& w : ps) witness_polys.push_back(std::move(w));
+    for (auto& c : tr.squeeze_challenges(phase_c[round])) challenges.push_back(c);
+  }
   std::vector<const Poly*> polys;
   for (auto& p : inst_polys) polys.push_back(&p);
   for (auto& p : pp.preprocess_polys) polys.push_back(&p);
@@ -358,7 +380,7 @@ inline bool hyperplonk_prove(const HyperPlonkParams& pp, const std::vector<std::
   std::vector<std::array<Poly, 2>> compressed;
   std::vector<Poly> ms(pp.lookups.size()), hs;
   for (size_t l = 0; l < pp.lookups.size(); ++l) {
-    compressed.push_back(lookup_compressed_poly(pp.lookups[l], n, polys, {}, beta));
+    compressed.push_back(lookup_compressed_poly(pp.lookups[l], n, polys, challenges, beta));
     if (!lookup_m_poly(compressed[l], &ms[l])) return false;  // Error::InvalidSnark("Invalid lookup input")
   }
   for (auto& m : ms)
@@ -377,7 +399,7 @@ inline bool hyperplonk_prove(const HyperPlonkParams& pp, const std::vector<std::
   for (auto& m : ms) polys.push_back(&m);
   for (auto& h : hs) polys.push_back(&h);
   for (auto& z : zs) polys.push_back(&z);
-  std::vector<Fr> challenges = {beta, gamma, alpha};
+  challenges.insert(challenges.end(), {beta, gamma, alpha});
   // prove_zero_check (prover.rs:348-409)
   SumCheckOutput sc = sumcheck_prove_generic(n, pp.expression, polys, challenges, {y}, Fr::zero(), tr);
   PcsQueryPlan pl = pcs_query_plan(pp.expression, (int)instances.size());
@@ -397,14 +419,34 @@ inline bool hyperplonk_prove(const HyperPlonkParams& pp, const std::vector<std::
   return kzg_batch_open(*pp.kzg, n, polys, points, evals, tr);
 }
 
+// single-phase circuits: the witness is known up front
+inline bool hyperplonk_prove(const HyperPlonkParams& pp, const std::vector<std::vector<Fr>>& instances,
+                             const std::vector<Poly>& witness_polys, Transcript& tr) {
+  if (pp.phase_witness_polys.size() > 1) return false;
+  return hyperplonk_prove_phased(pp, instances, [&](int, const std::vector<Fr>&) { return witness_polys; }, tr);
+}
+
 // hyperplonk.rs:293-363 + verifier.rs:39-145
 inline bool hyperplonk_verify(const HyperPlonkParams& vp, const std::vector<std::vector<Fr>>& instances, Transcript& tr) {
   const int n = vp.num_vars;
   for (auto& inst : instances)
     for (auto& v : inst) tr.common_field_element(v);
-  std::vector<G1Affine> witness_comms(vp.num_witness_polys);
-  for (auto& c : witness_comms)
-    if (!tr.read_commitment(&c)) return false;
+  if (instances.size() != vp.num_instances.size()) return false;
+  for (size_t i = 0; i < instances.size(); ++i)
+    if ((int)instances[i].size() != vp.num_instances[i]) return false;  // hyperplonk.rs:299-305
+  // rounds 0..n (hyperplonk.rs:307-315)
+  const std::vector<int> phase_w = vp.phase_witness_polys.empty() ? std::vector<int>{vp.num_witness_polys} : vp.phase_witness_polys;
+  const std::vector<int> phase_c = vp.phase_challenges.empty() ? std::vector<int>{0} : vp.phase_challenges;
+  std::vector<G1Affine> witness_comms;
+  std::vector<Fr> challenges;
+  for (size_t round = 0; round < phase_w.size(); ++round) {
+    for (int i = 0; i < phase_w[round]; ++i) {
+      G1Affine c;
+      if (!tr.read_commitment(&c)) return false;
+      witness_comms.push_back(c);
+    }
+    for (auto& c : tr.squeeze_challenges(phase_c[round])) challenges.push_back(c);
+  }
   const Fr beta = tr.squeeze_challenge();
   std::vector<G1Affine> m_comms(vp.lookups.size());
   for (auto& c : m_comms)
@@ -415,7 +457,7 @@ inline bool hyperplonk_verify(const HyperPlonkParams& vp, const std::vector<std:
     if (!tr.read_commitment(&c)) return false;
   const Fr alpha = tr.squeeze_challenge();
   std::vector<Fr> y = tr.squeeze_challenges(n);
-  std::vector<Fr> challenges = {beta, gamma, alpha};
+  challenges.insert(challenges.end(), {beta, gamma, alpha});
   const int d = expr_degree(vp.expression);
   Fr x_eval;
   std::vector<Fr> x;
@@ -431,15 +473,20 @@ inline bool hyperplonk_verify(const HyperPlonkParams& vp, const std::vector<std:
     lv.poly[q] = rotation_eval(x, q.second, ev);
     evals_for_rotation.push_back(ev);
   }
-  // instance_evals (verifier.rs:92-145) for queries (poly < #instances, rotation 0): Σ inst_i * L_{bh[i+1]}(x)
+  // instance_evals (verifier.rs:92-145): Σ_j inst[j] * L_{bh[is_j]}(x) with is = 1 - rot, 2 - rot, ... for rot <= 0
+  // and -rot, ..., -1, 1, 2, ... for rot > 0 (row 0 of the LFSR order is skipped)
   std::vector<uint64_t> order = BooleanHypercube(n).iter();
   std::set<Query> qs;
   collect_queries(vp.expression, &qs);
   for (auto& q : qs)
     if (q.first < (int)instances.size()) {
-      if (q.second != 0) return false;  // rotated instance queries are not used by the supported circuits
+      const long Nrows = 1L << n;
       Fr acc = Fr::zero();
-      for (size_t i = 0; i < instances[q.first].size(); ++i) acc = acc + instances[q.first][i] * lagrange_eval(x, order[i + 1]);
+      long i = q.second > 0 ? -(long)q.second : 1 - (long)q.second;
+      for (size_t j = 0; j < instances[q.first].size(); ++j, ++i) {
+        if (q.second > 0 && i == 0) i = 1;
+        acc = acc + instances[q.first][j] * lagrange_eval(x, order[((i % Nrows) + Nrows) % Nrows]);
+      }
       lv.poly[q] = acc;
     }
   // evaluate (sum_check.rs:60-95)

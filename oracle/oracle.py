@@ -489,7 +489,9 @@ class HyperPlonk:
     """Oracle `HyperPlonk<MultilinearKzg>`: preprocess at construction, then prove / verify."""
 
     def __init__(self, kzg, num_vars, expression, num_instances, num_witness, preprocess_polys, perm_idx, cycles, num_z=1,
-                 lookups=()):
+                 lookups=(), num_challenges=None):
+        """num_instances: int (one instance column) or a list (one entry per column); num_witness: int (one phase) or
+        a list per phase, then num_challenges is the list of challenges squeezed after each phase (backend.rs:50-60)."""
         tokens, consts = serialize_expression(expression)
         ltok, lconsts = serialize_lookups(lookups)
         arrs, ptrs = _ptr_array(preprocess_polys)
@@ -501,10 +503,18 @@ class HyperPlonk:
         flat = np.asarray(flat if flat else [0], dtype=np.int32)
         pidx = np.asarray(perm_idx, dtype=np.int32)
         self.kzg, self.num_vars, self.nperm = kzg, num_vars, len(perm_idx)
-        self.h = C.c_void_p(lib().orc_hp_preprocess(kzg.h, C.c_int(num_vars), _p(tokens), _p(consts), C.c_int(num_instances),
-                                                    C.c_int(num_witness), C.c_int(len(preprocess_polys)), ptrs,
+        cols = [num_instances] if isinstance(num_instances, int) else list(num_instances)
+        phases = [num_witness] if isinstance(num_witness, int) else list(num_witness)
+        chals = [0] * len(phases) if num_challenges is None else list(num_challenges)
+        assert len(chals) == len(phases)
+        self.phase_witness = phases
+        self.h = C.c_void_p(lib().orc_hp_preprocess(kzg.h, C.c_int(num_vars), _p(tokens), _p(consts), C.c_int(cols[0] if cols else 0),
+                                                    C.c_int(sum(phases)), C.c_int(len(preprocess_polys)), ptrs,
                                                     C.c_int(len(perm_idx)), _p(pidx), _p(flat), C.c_int(len(cycles)),
                                                     C.c_int(num_z), C.c_int(len(lookups)), _p(ltok), _p(lconsts)))
+        if len(cols) != 1 or len(phases) != 1 or chals != [0]:
+            a, b, c = (np.asarray(v if v else [0], dtype=np.int32) for v in (cols, phases, chals))
+            assert lib().orc_hp_set_phases(self.h, C.c_int(len(cols)), _p(a), C.c_int(len(phases)), _p(b), _p(c)) == 0
 
     def __del__(self):
         if getattr(self, "h", None):
@@ -520,6 +530,35 @@ class HyperPlonk:
         inst = np.ascontiguousarray(instances, dtype=np.uint64).reshape(-1, 4)
         arrs, ptrs = _ptr_array(witness_polys)
         return lib().orc_hp_prove(self.h, tr.h, _p(inst), C.c_int(inst.shape[0]), ptrs, C.c_int(len(witness_polys))) == 0
+
+    def prove_phased(self, tr, instances, synthesize):
+        """`synthesize(round, challenges) -> list of (2^k, 4) uint64 witness tables` plays PlonkishCircuit::synthesize
+        (hyperplonk.rs:192-199); `instances`: all instance columns back to back."""
+        inst = np.ascontiguousarray(instances, dtype=np.uint64).reshape(-1, 4)
+        N = 1 << self.num_vars
+        err = []
+
+        @C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_void_p))
+        def cb(_user, rnd, chal_ptr, nchal, out):
+            try:
+                ch = np.zeros((nchal, 4), dtype=np.uint64)
+                if nchal:
+                    C.memmove(ch.ctypes.data, chal_ptr, nchal * 32)
+                polys = synthesize(rnd, ch)
+                if len(polys) != self.phase_witness[rnd]:
+                    return 1
+                for i, p in enumerate(polys):
+                    a = np.ascontiguousarray(p, dtype=np.uint64).reshape(N, 4)
+                    C.memmove(out[i], a.ctypes.data, N * 32)
+                return 0
+            except Exception as e:  # never unwind through the C frames
+                err.append(e)
+                return 1
+
+        rc = lib().orc_hp_prove_phased(self.h, tr.h, _p(inst), C.c_int(inst.shape[0]), cb, None)
+        if err:
+            raise err[0]
+        return rc == 0
 
     def verify(self, tr, instances):
         inst = np.ascontiguousarray(instances, dtype=np.uint64).reshape(-1, 4)

@@ -38,14 +38,29 @@ def prove(srs, info, instances, witness, max_degree=4):
     bh = BooleanHypercube(k)
     order = bh.iter()
     tr = M.Transcript()
-    for v in instances:
-        tr.common_fe(v)
-    inst_poly = [0] * N
-    for i, v in enumerate(instances):
-        inst_poly[order[i + 1]] = v
-    for col in witness:
-        tr.write_comm(M.kzg_commit(srs, col))
-    polys = [inst_poly] + [list(p) for p in info.preprocess_polys] + [list(c) for c in witness]
+    # one instance column given as a flat list, or one list per column (pb/backend.rs:50-51)
+    inst_cols = instances if isinstance(info.num_instances, list) else [instances]
+    inst_polys = []
+    for col in inst_cols:
+        for v in col:
+            tr.common_fe(v)
+    for col in inst_cols:
+        poly = [0] * N
+        for i, v in enumerate(col):
+            poly[order[i + 1]] = v
+        inst_polys.append(poly)
+    # witness phases (hyperplonk.rs:183-204): `witness` is the list of columns, or synthesize(round, challenges)
+    phases = info.num_witness_polys if isinstance(info.num_witness_polys, list) else [info.num_witness_polys]
+    phase_challenges = getattr(info, "num_challenges", [0] * len(phases))
+    circuit_ch, witness_cols = [], []
+    for rnd, (nw, nc) in enumerate(zip(phases, phase_challenges)):
+        cols = witness(rnd, list(circuit_ch)) if callable(witness) else witness
+        assert len(cols) == nw
+        for col in cols:
+            tr.write_comm(M.kzg_commit(srs, col))
+        witness_cols += [list(c) for c in cols]
+        circuit_ch += [tr.squeeze() for _ in range(nc)]
+    polys = inst_polys + [list(p) for p in info.preprocess_polys] + witness_cols
 
     def row_leaf(b):
         def leaf(n):
@@ -66,8 +81,8 @@ def prove(srs, info, instances, witness, max_degree=4):
         for b in range(N):
             pw = 1
             for inp, tab in lookup:
-                ci[b] = (ci[b] + pw * eval_tree(inp.node, row_leaf(b), [])) % R
-                ct[b] = (ct[b] + pw * eval_tree(tab.node, row_leaf(b), [])) % R
+                ci[b] = (ci[b] + pw * eval_tree(inp.node, row_leaf(b), circuit_ch)) % R
+                ct[b] = (ct[b] + pw * eval_tree(tab.node, row_leaf(b), circuit_ch)) % R
                 pw = pw * beta % R
         last = {v: i for i, v in enumerate(ct)}
         m = [0] * N
@@ -82,7 +97,8 @@ def prove(srs, info, instances, witness, max_degree=4):
           for (ci, ct), m in zip(compressed, ms)]
     # permutation_z_polys (prover.rs:252-345)
     sigmas = H.permutation_polys(k, info.permutation_polys, info.permutations)
-    nz, expr = compose(k, info.constraints, info.num_poly, info.permutation_polys, max_degree=max_degree, lookups=info.lookups)
+    nz, expr = compose(k, info.constraints, info.num_poly, info.permutation_polys, num_challenges=len(circuit_ch),
+                       max_degree=max_degree, lookups=info.lookups)
     chunk = -(-len(info.permutation_polys) // nz) if nz else 0
     products = []
     for c in range(nz):
@@ -114,7 +130,7 @@ def prove(srs, info, instances, witness, max_degree=4):
     alpha = tr.squeeze()
     y = [tr.squeeze() for _ in range(k)]
     polys = polys + sigmas + ms + hs + zs
-    ch = [beta, gamma, alpha]
+    ch = circuit_ch + [beta, gamma, alpha]
     # zero check: EvaluationsProver over materialised leaf tables (eval.rs:92-131), claimed sum 0
     leaves = expr.leaves()
     tabs = {}
@@ -145,7 +161,7 @@ def prove(srs, info, instances, witness, max_degree=4):
         tabs = {l: M.fix_var(t, r) for l, t in tabs.items()}
         bound = {p: M.fix_var(t, r) for p, t in bound.items()}
     # evaluations in pcs_query order (verifier.rs:147-182), rotated ones at the rotation_eval_points
-    queries = sorted({(l[1], l[2]) for l in leaves if l[0] == "poly" and l[1] >= 1})
+    queries = sorted({(l[1], l[2]) for l in leaves if l[0] == "poly" and l[1] >= len(inst_cols)})
     rotations = sorted({r for _, r in queries})
     points, offset = [], {}
     for r in rotations:

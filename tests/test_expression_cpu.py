@@ -112,15 +112,18 @@ def test_native_compiler_program_equals_tree_evaluation():
     _, lookup_expr = compose(4, info.constraints, info.num_poly, info.permutation_polys, lookups=info.lookups)
     misc = (E.polynomial(0) * E.polynomial(1, 1) - E.identity() * E.lagrange(-1) + E.challenge(1) * 7
             + E.distribute_powers([E.polynomial(2), -E.polynomial(0), E.constant(5)], E.challenge(0)) + E.eq_xy(1))
+    # two witness phases: circuit challenges 0, 1 in front of beta, gamma, alpha; an instance column at Rotation::next
+    info2, _, _ = H.rand_two_phase_circuit(4, 1)
+    _, phased_expr = compose(4, info2.constraints, info2.num_poly, info2.permutation_polys, num_challenges=2, lookups=info2.lookups)
     rng = random.Random(2)
-    for expr, nleaves in ((vanilla_plonk_expression(4), 17), (lookup_expr, 23), (misc, 6), (E.polynomial(3), 1)):
+    for expr, nleaves in ((vanilla_plonk_expression(4), 17), (lookup_expr, 23), (misc, 6), (E.polynomial(3), 1), (phased_expr, 22)):
         _, consts = serialize_expression(expr, [], [])
         cm = np.asarray([to_limbs(c * R % R_MOD) for c in consts] or [[0, 0, 0, 0]], dtype=np.uint64)
         leaves, cvals, cchal, ops, ntemps, degree = hl.compile_expression_native(expr, cm)
         assert degree == expr.degree() and len(leaves) == nleaves
         py_leaves = [(kinds[k],) if k == 1 else ((kinds[k], a) if k in (2, 3) else (kinds[k], a, b)) for k, a, b in leaves]
         assert py_leaves == expr.leaves()
-        ch = [rng.randrange(R_MOD) for _ in range(3)]
+        ch = [rng.randrange(R_MOD) for _ in range(5)]
         cints = [ch[j] if j >= 0 else sum(int(x) << (64 * i) for i, x in enumerate(v)) * rinv % R_MOD
                  for v, j in zip(cvals, cchal)]
         K, C_ = len(leaves), len(cints)

@@ -208,3 +208,80 @@ def test_hyperplonk_two_permutation_chunks(hl, env, k):
     proof = tr.into_proof()
     assert proof == to.proof()
     assert ohp.verify(O.Transcript(proof), inst)
+
+
+@pytest.mark.parametrize("k,with_lookup", [(4, True), (6, False), (9, True)])
+def test_hyperplonk_two_phases_two_instance_columns(hl, env, k, with_lookup):
+    """PlonkishCircuitInfo with two instance columns (one queried at Rotation::next) and two witness phases
+    (pb/backend.rs:50-60, hyperplonk.rs:183-204): the phase-1 witness is synthesized by a host callback from the
+    challenges squeezed after the phase-0 commitments; a circuit challenge also sits inside the lookup input. The
+    proof is byte-identical to the oracle's (which is pinned by the pure-Python model) and the oracle verifies it."""
+    from halo2_lasso_b200 import hyperplonk as H
+    from halo2_lasso_b200.expression import compose
+
+    ctx, okzg, kzg = env
+    info, inst_cols, synth = H.rand_two_phase_circuit(k, 120 + k, with_lookup)
+    nz, expr = compose(k, info.constraints, info.num_poly, info.permutation_polys,
+                       num_challenges=sum(info.num_challenges), lookups=info.lookups)
+    ohp = O.HyperPlonk(okzg, k, expr, info.num_instances, info.num_witness_polys, [O.fr_from_ints(p) for p in info.preprocess_polys],
+                       info.permutation_polys, info.permutations, nz, lookups=info.lookups, num_challenges=info.num_challenges)
+    inst = O.fr_from_ints([v for col in inst_cols for v in col])
+    seen_o, seen_g = [], []
+
+    def synth_o(rnd, ch):
+        ints = O.fr_to_ints(ch) if len(ch) else []
+        seen_o.append((rnd, ints))
+        return [O.fr_from_ints(c) for c in synth(rnd, ints)]
+
+    def synth_g(rnd, ch):
+        seen_g.append((rnd, list(ch)))
+        return synth(rnd, ch)
+
+    to = O.Transcript()
+    assert ohp.prove_phased(to, inst, synth_o)
+    hp = H.HyperPlonk(ctx, kzg, info)
+    assert (hp.num_z, hp.degree, hp.num_polys) == (1, 5, 12 + 3 + 2 * len(info.lookups) + 1)
+    tr = hl.Keccak256Transcript(ctx)
+    hp.prove_phased(inst_cols, synth_g)
+    proof = tr.into_proof()
+    assert seen_g == seen_o, "the synthesize callback must see the same challenges as the oracle's"
+    ref = to.proof()
+    if proof != ref:
+        first = next(i for i in range(min(len(proof), len(ref))) if proof[i] != ref[i])
+        pytest.fail(f"two-phase HyperPlonk proof differs from the oracle at byte {first} (lengths {len(proof)} vs {len(ref)})")
+    assert ohp.verify(O.Transcript(proof), inst)
+    # error behaviour: wrong number of instances, a failing synthesize callback, the single-phase entry point
+    hl.Keccak256Transcript(ctx)
+    with pytest.raises(hl.B200Error) as e:
+        hp.prove_phased([inst_cols[0], inst_cols[1][:-1]], synth_g)
+    assert e.value.code == hl.B200_ERR_ARG
+    hl.Keccak256Transcript(ctx)
+    with pytest.raises(hl.B200Error) as e:
+        hp.prove_phased(inst_cols, lambda rnd, ch: synth(rnd, ch)[:1])
+    assert e.value.code == hl.B200_ERR_ARG
+    hl.Keccak256Transcript(ctx)
+    with pytest.raises(hl.B200Error) as e:
+        hp.prove([v for col in inst_cols for v in col], witness_ints=synth(0, []))
+    assert e.value.code == hl.B200_ERR_ARG
+
+
+def test_hyperplonk_preprocess_phased_rejects_malformed_phases(hl, env):
+    """is_well_formed (pb/backend.rs:76-105): a phase without witness polynomials, a non-final phase without
+    challenges and an out-of-range challenge index are rejected with B200_ERR_ARG."""
+    from halo2_lasso_b200 import hyperplonk as H
+    from halo2_lasso_b200.expression import Expression as E
+
+    ctx, okzg, kzg = env
+    info, inst_cols, synth = H.rand_two_phase_circuit(4, 5, with_lookup=False)
+    for attr, value in (("num_witness_polys", [4, 0]), ("num_challenges", [0, 0])):
+        bad, _, _ = H.rand_two_phase_circuit(4, 5, with_lookup=False)
+        setattr(bad, attr, value)
+        with pytest.raises(hl.B200Error) as e:
+            H.HyperPlonk(ctx, kzg, bad)
+        assert e.value.code == hl.B200_ERR_ARG
+    bad, _, _ = H.rand_two_phase_circuit(4, 5, with_lookup=False)
+    bad.constraints = bad.constraints + [E.polynomial(8) * E.challenge(2)]  # only challenges 0 and 1 exist
+    with pytest.raises(hl.B200Error) as e:
+        H.HyperPlonk(ctx, kzg, bad)
+    assert e.value.code == hl.B200_ERR_ARG
+    H.HyperPlonk(ctx, kzg, info)

@@ -206,3 +206,98 @@ def test_hyperplonk_proof_matches_independent_python_model(lookup, max_degree):
     assert hp.prove(tr, O.fr_from_ints(instances), [O.fr_from_ints(c) for c in w])
     assert tr.proof() == want
     assert hp.verify(O.Transcript(want), O.fr_from_ints(instances))
+
+
+# ---- several instance columns, several witness phases (pb/backend.rs:50-60, hyperplonk.rs:183-204) -----------
+def two_phase_oracle(kz, k, seed, with_lookup=True):
+    from halo2_lasso_b200.expression import compose
+
+    info, inst_cols, synth = H.rand_two_phase_circuit(k, seed, with_lookup)
+    nz, expr = compose(k, info.constraints, info.num_poly, info.permutation_polys,
+                       num_challenges=sum(info.num_challenges), lookups=info.lookups)
+    hp = O.HyperPlonk(kz, k, expr, info.num_instances, info.num_witness_polys, [O.fr_from_ints(p) for p in info.preprocess_polys],
+                      info.permutation_polys, info.permutations, nz, lookups=info.lookups, num_challenges=info.num_challenges)
+    rounds = []
+
+    def synth_fr(rnd, challenges):
+        rounds.append((rnd, len(challenges)))
+        return [O.fr_from_ints(c) for c in synth(rnd, O.fr_to_ints(challenges) if len(challenges) else [])]
+
+    inst = O.fr_from_ints([v for col in inst_cols for v in col])
+    return info, inst_cols, synth, hp, synth_fr, inst, rounds
+
+
+def test_two_phase_fixture_is_satisfiable():
+    k = 5
+    info, inst_cols, synth = H.rand_two_phase_circuit(k, 3)
+    N, bh = 1 << k, BooleanHypercube(k)
+    order = bh.iter()
+    r0, r1 = 1234567, 7654321
+    (a, b), (c, d) = synth(0, []), synth(1, [r0, r1])
+    assert synth(1, [r0, r1]) == [c, d], "synthesize must be deterministic"
+    q_mix, q_io, q_io2, q_mul, q_lk, t = info.preprocess_polys
+    pi = [[0] * N, [0] * N]
+    for col, vals in enumerate(inst_cols):
+        for i, v in enumerate(vals):
+            pi[col][order[i + 1]] = v
+    table = set(t)
+    for row in range(N):
+        assert q_mix[row] * (a[row] + r0 * b[row] - c[row]) % R_MOD == 0
+        assert q_io[row] * (a[row] - pi[0][row]) % R_MOD == 0
+        assert q_io2[row] * (b[row] - pi[1][bh.rotate(row, 1)]) % R_MOD == 0
+        assert q_mul[row] * (r1 * a[row] * b[row] - d[row]) % R_MOD == 0
+        assert q_lk[row] * (c[row] - r0 * b[row]) % R_MOD in table
+    cols = {8: a, 9: b, 10: c}
+    assert sum(q_io) == 2 and sum(q_io2) == 3 and sum(q_lk) > 0 and len(info.permutations) >= 2
+    for cyc in info.permutations:
+        assert len({cols[p][r] for p, r in cyc}) == 1
+
+
+@pytest.mark.parametrize("k,with_lookup", [(4, True), (4, False), (6, True)])
+def test_two_phase_prove_verify_roundtrip_and_negatives(kz, k, with_lookup):
+    info, inst_cols, synth, hp, synth_fr, inst, rounds = two_phase_oracle(kz, k, 50 + k, with_lookup)
+    tr = O.Transcript()
+    assert hp.prove_phased(tr, inst, synth_fr)
+    assert rounds == [(0, 0), (1, 2)]  # phase 1 sees the two challenges squeezed after the phase-0 commitments
+    proof = tr.proof()
+    assert hp.verify(O.Transcript(proof), inst)
+    # proof layout: 4 witness commitments (2 + 2), then m (if any), h + z, sum-check, evaluations, opening
+    for pos in (5, 64 * 3 + 9, len(proof) // 2, len(proof) - 7):
+        bad = bytearray(proof)
+        bad[pos] ^= 4
+        assert not hp.verify(O.Transcript(bytes(bad)), inst)
+    for j in range(inst.shape[0]):  # every instance of BOTH columns is bound (pi_b through its rotated query)
+        wrong = inst.copy()
+        wrong[j] = O.rand_fr(99, 1)[0]
+        assert not hp.verify(O.Transcript(proof), wrong)
+    # instance columns of the wrong shape (hyperplonk.rs:171-173 assert / :299-305 Error::InvalidSnark)
+    assert not hp.verify(O.Transcript(proof), inst[:-1])
+    # a phase-1 witness that ignores the challenges does not verify
+    stale = lambda rnd, ch: synth_fr(rnd, O.fr_from_ints([1, 2]) if rnd else ch)
+    tr2 = O.Transcript()
+    ok = hp.prove_phased(tr2, inst, stale)
+    assert not (ok and hp.verify(O.Transcript(tr2.proof()), inst))
+    # a synthesize callback returning the wrong number of polynomials fails the prover
+    assert not hp.prove_phased(O.Transcript(), inst, lambda rnd, ch: synth_fr(rnd, ch)[:1])
+
+
+@pytest.mark.parametrize("with_lookup", [True, False])
+def test_two_phase_proof_matches_independent_python_model(with_lookup):
+    """Two instance columns (one queried at Rotation::next), two witness phases with circuit challenges (also inside a
+    lookup input): the oracle's proof equals the pure-Python model's byte for byte."""
+    import os
+    import sys
+
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import pymodel as M
+    import pymodel_hyperplonk as MH
+
+    k = 4
+    ss = M.rand_fr(7, k)
+    kz = O.Kzg(O.fr_from_ints(ss))
+    info, inst_cols, synth, hp, synth_fr, inst, rounds = two_phase_oracle(kz, k, 61, with_lookup)
+    want = MH.prove(M.kzg_setup(ss), info, inst_cols, synth)
+    tr = O.Transcript()
+    assert hp.prove_phased(tr, inst, synth_fr)
+    assert tr.proof() == want
+    assert hp.verify(O.Transcript(want), inst)
