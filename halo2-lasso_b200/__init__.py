@@ -435,6 +435,13 @@ def dist_shard_commits(ctx, on=True):
     _chk(lib().b200_dist_shard_commits(ctx.h, C.c_int(int(on))), "dist_shard_commits")
 
 
+def dist_shard_sumchecks(ctx, min_vars=16):
+    """Evaluate every sum-check of the Lasso prover with at least `min_vars` variables on the rank's 1/world slice of
+    the hypercube (round partials exchanged over NVLink inside the round kernels); 0 switches it off. Collective, like
+    dist_shard_commits: all ranks run the same prover on the same inputs and obtain the identical proof."""
+    _chk(lib().b200_dist_shard_sumchecks(ctx.h, C.c_int(int(min_vars))), "dist_shard_sumchecks")
+
+
 def exchange_handles(mine: bytes, world: int):
     """all-gather of fixed-size byte strings in rank order (host-side plumbing, testable with gloo)."""
     import torch.distributed as dist

@@ -49,6 +49,12 @@ int b200_dist_shard_commits(b200_ctx* h, int on) {
   return B200_OK;
 }
 
+int b200_dist_shard_sumchecks(b200_ctx* h, int min_vars) {
+  if (min_vars < 0 || (min_vars && h->c.peer.world < 2)) return B200_ERR_ARG;
+  h->c.shard_sumcheck_min_vars = min_vars;
+  return B200_OK;
+}
+
 int b200_sumcheck_prove_evals_sharded(b200_ctx* h, int num_vars_total, int nterms, int np,
                                       const void* const* dev_local_tables, const void* host_weights,
                                       const void* host_y, const void* host_sum, void* host_challenges_out,

@@ -47,6 +47,8 @@ struct Ctx {
   Mailbox* my_mailbox;     // cudaMalloc'ed, exported through CUDA IPC
   unsigned int peer_seq;   // collectives issued so far (identical on every rank)
   bool shard_commits = false;  // every commitment MSM is split by point range over the ranks (all ranks call)
+  int shard_sumcheck_min_vars = 0;  // > 0: sum-checks of the whole provers with at least that many variables run
+                                    // hypercube-sharded over the ranks (sumcheck_prove_evals_dist, shard.cu)
 };
 static const int EXT_C = 16;        // window bits of the precomputed tables
 static const int EXT_WINDOWS = 16;  // ceil(255 / 16)
@@ -71,6 +73,8 @@ struct ScEvalJob {
 int sumcheck_prove_evals(Ctx* c, const ScEvalJob& job);
 // shard.cu — hypercube-sharded sum-check and point-sharded MSM over peer memory
 int sumcheck_prove_evals_sharded(Ctx* c, const ScEvalJob& job_local, int num_vars_total);
+// replicated full tables in, sharded evaluation when enabled (b200_dist_shard_sumchecks); else sumcheck_prove_evals
+int sumcheck_prove_evals_dist(Ctx* c, const ScEvalJob& job);
 
 
 // COEFF shape  F(x) = Σ_k s_k * eq(x, y_k) * P_k(x)   (CoefficientsProver, degree 2)

@@ -300,7 +300,7 @@ static int grand_product_prove(Ctx* c, const GpTrees& trees, GpState* st, Fr* sc
       job.claim = &st->claim;
       job.challenges_out = scratch_x;
       job.evals_out = st->evals;
-      int rc = sumcheck_prove_evals(c, job);
+      int rc = sumcheck_prove_evals_dist(c, job);
       if (rc) return rc;
     }
     CUDA_TRY(launch_pdl(gp_after_kernel, dim3(1), dim3(32), 0, s, c->d_tr, trees, k, scratch_x, st));
@@ -465,7 +465,7 @@ int lasso_prove(Ctx* c, int kind, int chunks, int mu, const uint64_t* d_xs, cons
     job.claim = v_a;
     job.challenges_out = x_p;
     job.evals_out = e_p;
-    rc = sumcheck_prove_evals(c, job);
+    rc = sumcheck_prove_evals_dist(c, job);
     if (rc) return rc;
   }
   rc = transcript_op(c, TR_WRITE, e_p, nullptr, C_);

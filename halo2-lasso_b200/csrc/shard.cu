@@ -53,7 +53,7 @@ int sumcheck_prove_evals_sharded(Ctx* c, const ScEvalJob& job_local, int n) {
   while ((1 << g) < G) ++g;
   if (G < 2 || (1 << g) != G || n - g < 1) return B200_ERR_ARG;
   const int n_loc = n - g, ntab = job_local.T * job_local.NP;
-  if (ntab + 1 > 32) return B200_ERR_ARG;
+  if (ntab + 1 > SC_MAX_TABLES) return B200_ERR_ARG;
   cudaStream_t s = c->stream;
   Fr* scratch = nullptr;  // factor | finals[ntab+1] | gathered[(ntab+1)*G] | evals2[ntab]
   const size_t nscr = 1 + (ntab + 1) + (size_t)(ntab + 1) * G + ntab + 1;
@@ -75,8 +75,12 @@ int sumcheck_prove_evals_sharded(Ctx* c, const ScEvalJob& job_local, int n) {
   if (rc) return rc;
 
   // phase 2: rebuild the G-entry tables everywhere and finish redundantly
-  shard_gather_kernel<<<1, 128, 0, s>>>(c->peer, ++c->peer_seq, finals, ntab + 1, gathered, &c->d_sc->pad[0]);
-  count_launch(c);
+  for (int at = 0; at < ntab + 1; at += 32) {  // one mailbox message carries up to 32 values per rank
+    const int cnt = std::min(32, ntab + 1 - at);
+    shard_gather_kernel<<<1, 128, 0, s>>>(c->peer, ++c->peer_seq, finals + at, cnt, gathered + (size_t)at * G,
+                                          &c->d_sc->pad[0]);
+    count_launch(c);
+  }
   ScEvalJob j2 = job_local;
   j2.num_vars = g;
   for (int i = 0; i < ntab; ++i) j2.tables[i] = gathered + (size_t)i * G;
@@ -88,6 +92,24 @@ int sumcheck_prove_evals_sharded(Ctx* c, const ScEvalJob& job_local, int n) {
   if (rc) return rc;
   CUDA_TRY(cudaFreeAsync(scratch, s));
   return B200_OK;
+}
+
+// Sum-checks issued INSIDE the replicated whole provers (Lasso: the Surge primary sum-check and the per-layer
+// grand-product sum-checks). Every rank holds the full tables, so rank g simply passes the sub-arrays
+// [g 2^n / G, (g + 1) 2^n / G) of each table to the sharded driver above: the per-pair work of the big rounds is
+// divided by G, nothing moves between GPUs but the D round partials, and every rank still ends with the same
+// transcript, challenges and evaluations. Collective: the decision depends on the job shape only.
+int sumcheck_prove_evals_dist(Ctx* c, const ScEvalJob& job) {
+  const int G = c->peer.world;
+  int g = 0;
+  while ((1 << g) < G) ++g;
+  if (G < 2 || (1 << g) != G || c->shard_sumcheck_min_vars <= 0 || job.num_vars < c->shard_sumcheck_min_vars ||
+      job.num_vars - g < 1 || job.eq_table || job.eq_scale || job.want_eq_eval || job.sharded)
+    return sumcheck_prove_evals(c, job);
+  ScEvalJob loc = job;
+  const size_t off = (size_t)c->peer.rank << (job.num_vars - g);
+  for (int i = 0; i < job.T * job.NP; ++i) loc.tables[i] = job.tables[i] + off;
+  return sumcheck_prove_evals_sharded(c, loc, job.num_vars);
 }
 
 __global__ void shard_point_sum_kernel(PeerCtx pc, unsigned int seq, const G1Aff* mine, G1Aff* out, unsigned int* sink) {

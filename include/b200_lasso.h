@@ -240,6 +240,13 @@ int b200_dist_init(b200_ctx* ctx, int rank, int world, const void* handles);
  * partial commitments are all-gathered over NVLink and added, so these calls become COLLECTIVE: all ranks run the same
  * prover on the same inputs (everything between the commitments is replicated) and produce the identical proof. */
 int b200_dist_shard_commits(b200_ctx* ctx, int on);
+/* Hypercube-sharded sum-checks inside the whole provers: after b200_dist_shard_sumchecks(ctx, min_vars) with
+ * min_vars > 0, every EvaluationsProver sum-check of b200_lasso_prove* (the Surge primary sum-check and the per-layer
+ * grand-product sum-checks) over at least min_vars variables is evaluated on the rank's 1/world slice of the (replicated)
+ * tables, with the round partials exchanged over NVLink as in b200_sumcheck_prove_evals_sharded. Collective like
+ * b200_dist_shard_commits: all ranks run the same prover on the same inputs and produce the identical proof.
+ * min_vars = 0 switches it off. */
+int b200_dist_shard_sumchecks(b200_ctx* ctx, int min_vars);
 
 /* b200_sumcheck_prove_evals on a hypercube sharded over the TOP log2(world) variables: rank g passes the
  * slices [g*2^n/world, (g+1)*2^n/world) of every table. All ranks must call it; all receive the same

@@ -14,6 +14,66 @@ import halo2_lasso_b200 as hl
 import oracle as O
 
 
+def check_sharded_sumchecks_in_lasso(ctx, kzg, okzg, rank, world, cases):
+    """One Lasso proof on all GPUs with BOTH the commitment MSMs point-sharded and the prover's sum-checks
+    hypercube-sharded (b200_dist_shard_sumchecks): byte-identical to the single-process oracle proof on every rank.
+    min_vars = 6 shards nearly every grand-product layer, including the pre-bound-eq round kernels (pairs >= 2048,
+    T >= 4) and, with 8 chunks, the 33-value final gather that needs two mailbox messages."""
+    hl.dist_shard_commits(ctx, True)
+    hl.dist_shard_sumchecks(ctx, 6)
+    for kind, chunks, mu in cases:
+        xs, ys = O.rand_u64s(8400 + mu, 1 << mu), O.rand_u64s(8500 + mu, 1 << mu)
+        if kind == O.TABLE_RANGE:
+            ys = None
+        else:
+            xs &= np.uint64((1 << (8 * chunks)) - 1)
+            ys &= np.uint64((1 << (8 * chunks)) - 1)
+        to = O.Transcript()
+        assert O.lasso_prove(okzg, to, kind, chunks, mu, xs, ys)
+        tr = hl.Keccak256Transcript(ctx)
+        hl.LassoProver(ctx, kzg, kind, chunks).prove(xs, ys)
+        assert tr.into_proof() == to.proof(), f"rank {rank}: sum-check-sharded Lasso proof differs (kind {kind}, c {chunks}, mu {mu})"
+    hl.dist_shard_sumchecks(ctx, 0)
+    hl.dist_shard_commits(ctx, False)
+
+
+def time_cooperative_lasso(ctx, kzg, rank, world, mu=20):
+    """ms per 2^mu-lookup range proof on all GPUs: replicated / commitments sharded / commitments + sum-checks sharded"""
+    prover = hl.LassoProver(ctx, kzg, O.TABLE_RANGE, 4)
+    xs = torch.from_numpy(O.rand_u64s(5, 1 << mu).view(np.int64)).cuda()
+    stream = torch.cuda.ExternalStream(ctx.stream, device=torch.cuda.current_device())
+    out = {}
+    proofs = []
+    for name, commits, min_vars in (("replicated", False, 0), ("commits", True, 0), ("commits+sumchecks", True, 14)):
+        hl.dist_shard_commits(ctx, commits)
+        hl.dist_shard_sumchecks(ctx, min_vars)
+        tr = hl.Keccak256Transcript(ctx)
+        prover.prove_dev(mu, xs.data_ptr())
+        proofs.append(tr.into_proof())
+        for _ in range(2):
+            hl.Keccak256Transcript(ctx)
+            prover.prove_dev(mu, xs.data_ptr())
+        ctx.sync()
+        dist.barrier()
+        steps = 5
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        for a, b in ev:
+            hl.Keccak256Transcript(ctx)
+            a.record(stream)
+            prover.prove_dev(mu, xs.data_ptr())
+            b.record(stream)
+        ctx.sync()
+        torch.cuda.synchronize()
+        t = torch.tensor([sum(a.elapsed_time(b) for a, b in ev) / steps], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        out[name] = round(float(t.item()), 3)
+    hl.dist_shard_sumchecks(ctx, 0)
+    hl.dist_shard_commits(ctx, False)
+    assert proofs[0] == proofs[1] == proofs[2], f"rank {rank}: the 2^{mu} proofs of the three modes differ"
+    if rank == 0:
+        print(f"COOPERATIVE_LASSO world={world} mu={mu} ms={out} proof_bytes={len(proofs[0])}")
+
+
 def main():
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     local = int(os.environ.get("LOCAL_RANK", rank))
@@ -22,6 +82,20 @@ def main():
                             device_id=torch.device("cuda", local))
     ctx = hl.Context(local)
     hl.dist_init(ctx, rank, world)
+    if os.environ.get("DIST_QUICK"):  # only the sum-check-sharded whole prover (+ timing): a short GPU session
+        timing = os.environ.get("DIST_QUICK") == "time"
+        okzg = O.Kzg(O.rand_fr(7, 16))
+        kzg = hl.MultilinearKzg.setup(ctx, O.rand_fr(7, 20 if timing else 16))  # same trapdoor prefix as the oracle's
+        check_sharded_sumchecks_in_lasso(ctx, kzg, okzg, rank, world,
+                                         ((O.TABLE_RANGE, 4, 15), (O.TABLE_AND, 8, 12), (O.TABLE_XOR, 2, 13)))
+        if rank == 0:
+            print(f"SHARDED_SUMCHECKS_OK world={world}", flush=True)
+        if timing:
+            time_cooperative_lasso(ctx, kzg, rank, world)
+        dist.barrier()
+        ctx.close()
+        dist.destroy_process_group()
+        return
     one = O.fr_from_ints([1])[0]
     for n, T, NP in ((6, 1, 2), (12, 1, 2), (11, 5, 2), (10, 4, 1)):
         tabs = [O.rand_fr(7000 + n + i, 1 << n) for i in range(T * NP)]
@@ -71,6 +145,7 @@ def main():
         hl.LassoProver(ctx, kzg, kind, chunks).prove(xs, ys)
         assert tr.into_proof() == to.proof(), f"rank {rank}: commit-sharded Lasso proof differs (kind {kind})"
     hl.dist_shard_commits(ctx, False)
+    check_sharded_sumchecks_in_lasso(ctx, kzg, okzg, rank, world, ((O.TABLE_RANGE, 4, 15), (O.TABLE_AND, 8, 12)))
     dist.barrier()
     if rank == 0:
         print(f"SHARDED_OK world={world}")
