@@ -326,11 +326,13 @@ def main():
         roof.update(prof)
         roof["frac"] = roof["achieved"] / peak
         # the same launch against the bound that actually limits it: Montgomery products on the IMAD (fmaheavy) pipe.
-        # Round 1 of cfg2 = 2^(n-2) output pairs x (6 binding + 6 evaluation products). Peak: msm_accumulate sustains
-        # 50 G products/s at 86 % fmaheavy-pipe utilisation (profiles/), i.e. ~58 G/s at 100 %.
+        # Round 1 of cfg2 = 2^(n-2) output pairs x (6 binding + 6 evaluation products). Peak: the multiplier itself
+        # measured alone on a B200 (tools/micro/pipe_rates.cu, profiles/r01_pipe_rates.txt): 537.8 cycles per warp
+        # product per SM sub-partition with 4 resident warps each -> 148 SMs x 4 x 32 lanes x 1.965 GHz / 537.8.
         prods = 12 * (1 << (SC_VARS - 2))
+        imad_peak = 148 * 4 * 32 * 1.965 / 537.8
         roof["imad"] = {"products_per_launch": prods, "achieved_gproducts_s": prods / (roof["launch_ms"] * 1e-3) / 1e9,
-                        "peak_gproducts_s": 58.0, "frac": prods / (roof["launch_ms"] * 1e-3) / 1e9 / 58.0,
+                        "peak_gproducts_s": round(imad_peak, 1), "frac": prods / (roof["launch_ms"] * 1e-3) / 1e9 / imad_peak,
                         "note": "IMAD-bound kernel; launch time includes the ~29 us single-warp Fiat-Shamir tail"}
     # per-launch DRAM traffic of that kernel from the committed `ncu --set full` capture (profiles/), if present
     try:
