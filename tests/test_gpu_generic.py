@@ -63,3 +63,35 @@ def test_unqueried_polynomial_is_still_bound(hl, ctx):
     n = 4
     expr = E.eq_xy(0) * E.polynomial(0) * E.polynomial(2, 1)
     _run(hl, ctx, n, expr, 3, 0, 7000)
+
+
+def _run_given(hl, ctx, n, expr, polys, seed):
+    """the reference's run_zero_check shape: claimed sum 0, one challenge (alpha), one eq point"""
+    alpha, y = O.rand_fr(seed + 1, 1), O.rand_fr(seed + 2, n)
+    zero = O.fr_from_ints([0])[0]
+    to = O.Transcript()
+    ch_o, ev_o, deg = O.sumcheck_prove_generic(to, n, expr, polys, alpha, [y], zero)
+    dps = [hl.MultilinearPolynomial.new(ctx, p) for p in polys]
+    for prove in (hl.prove_expression_native, hl.prove_expression):
+        tr = hl.Keccak256Transcript(ctx)
+        got_ch, got_ev = prove(ctx, n, expr, dps, O.fr_to_ints(alpha), [y], zero)
+        assert tr.into_proof() == to.proof(), prove.__name__
+        assert (got_ch == ch_o).all() and (got_ev == ev_o).all(), prove.__name__
+
+
+@pytest.mark.parametrize("n", [2, 3])
+def test_reference_sum_check_lagrange_shape(hl, ctx, n):
+    """sum_check_lagrange (pb/piop/sum_check.rs:197-243): 2^n one-hot polynomials against Lagrange(i)"""
+    from ref_shapes import reference_lagrange_case
+
+    expr, polys = reference_lagrange_case(n)
+    _run_given(hl, ctx, n, expr, polys, 8000 + n)
+
+
+@pytest.mark.parametrize("n", [2, 4, 7])
+def test_reference_sum_check_rotation_shape(hl, ctx, n):
+    """sum_check_rotation (pb/piop/sum_check.rs:245-297): 2n - 1 polynomials queried at rotations n-1 .. -(n-1)"""
+    from ref_shapes import reference_rotation_case
+
+    expr, polys = reference_rotation_case(n, 8100 + n)
+    _run_given(hl, ctx, n, expr, polys, 8200 + n)

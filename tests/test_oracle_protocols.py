@@ -145,3 +145,63 @@ def test_lasso_witness_semantics():
         assert O.fr_to_ints(mt[1 + 2 * c + t]) == ts
         cts = O.fr_to_ints(st[t])
         assert all(cts[d] == n for d, n in seen.items()) and sum(cts) == 1 << mu
+
+
+# ---- the reference's own generic sum-check test shapes (pb/piop/sum_check.rs:194-300) on the oracle ---------------
+from ref_shapes import reference_lagrange_case as _reference_lagrange_case, reference_rotation_case as _reference_rotation_case  # noqa: E402
+
+
+def _run_zero_check(n, expr, polys, seed):
+    """run_zero_check / run_sum_check (sum_check.rs:140-192): prove with sum 0, verify, then recompute the expression at
+    x from fresh evaluations of the (rotated) polynomials and compare with the verifier's final claim."""
+    import os
+    import sys
+
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    from pymodel_hyperplonk import eval_tree
+
+    N = 1 << n
+    alpha, y = O.rand_fr(seed + 1, 1), O.rand_fr(seed + 2, n)
+    zero = O.fr_from_ints([0])[0]
+    tr = O.Transcript()
+    x, evals, deg = O.sumcheck_prove_generic(tr, n, expr, polys, alpha, [y], zero)
+    assert deg == expr.degree() and len(tr.proof()) == n * (deg + 1) * 32
+    fin, xv = O.sumcheck_verify(O.Transcript(tr.proof()), n, deg, zero)
+    assert (xv == x).all()
+    for i, p in enumerate(polys):  # ProverState::into_evals: every polynomial at x
+        assert (O.evaluate(p, x) == evals[i]).all()
+    order = [int(b) for b in O.bh_iter(n)]
+
+    def leaf(node):
+        if node[0] == "poly":  # evaluate_for_rotation + rotation_eval == the rotated table evaluated at x
+            rotated = np.ascontiguousarray(polys[node[1]][[O.bh_rotate(n, b, node[2]) for b in range(N)]])
+            return O.fr_to_ints(O.evaluate(rotated, x))[0]
+        if node[0] == "lagrange":
+            onehot = [0] * N
+            onehot[order[node[1] % N]] = 1
+            return O.fr_to_ints(O.evaluate(O.fr_from_ints(onehot), x))[0]
+        if node[0] == "eq":
+            return O.fr_to_ints(O.eq_xy_eval(x, y))[0]
+        if node[0] == "identity":
+            return O.fr_to_ints(O.evaluate(O.fr_from_ints(list(range(N))), x))[0]
+        raise ValueError(node)
+
+    assert eval_tree(expr.node, leaf, O.fr_to_ints(alpha)) == O.fr_to_ints(fin)[0]
+    return tr.proof()
+
+
+@pytest.mark.parametrize("n", [2, 3])
+def test_reference_sum_check_lagrange_shape(n):
+    expr, polys = _reference_lagrange_case(n)
+    _run_zero_check(n, expr, polys, 40 + n)
+
+
+@pytest.mark.parametrize("n", [2, 3, 5, 8])
+def test_reference_sum_check_rotation_shape(n):
+    expr, polys = _reference_rotation_case(n, 50 + n)
+    _run_zero_check(n, expr, polys, 60 + n)
+    # a polynomial that is NOT the rotation of its predecessor breaks the zero check: the final claim no longer matches
+    bad = list(polys)
+    bad[1] = O.rand_fr(99, 1 << n)
+    with pytest.raises(AssertionError):
+        _run_zero_check(n, expr, bad, 60 + n)
