@@ -285,7 +285,7 @@ def main():
     ms_sc = timed(sumcheck_device, 20, 5)
     ms_sh = timed(sharded[1], 20, 5) if sharded else 0.0
     ms_zc = timed(zero_check_device, 5, 3)
-    ms_co = 0.0
+    ms_co = ms_co_sc = 0.0
     if sharded:
         hl.dist_shard_commits(ctx, True)
         ms_co = timed(lasso_cooperative, args.steps, 3)
@@ -294,6 +294,12 @@ def main():
             if tag >= 1000:
                 nm = hl.PHASE_NAMES.get(tag, str(tag))
                 phases_co[nm] = round(phases_co.get(nm, 0.0) + t, 4)
+        # opt-in (B200_BENCH_SHARD_SUMCHECKS=<min_vars>): additionally evaluate the prover's large sum-checks on each
+        # rank's 1/N slice of the hypercube (b200_dist_shard_sumchecks; unverified on hardware in round 1)
+        if os.environ.get("B200_BENCH_SHARD_SUMCHECKS"):
+            hl.dist_shard_sumchecks(ctx, int(os.environ["B200_BENCH_SHARD_SUMCHECKS"]))
+            ms_co_sc = timed(lasso_cooperative, args.steps, 3)
+            hl.dist_shard_sumchecks(ctx, 0)
         hl.dist_shard_commits(ctx, False)
     clocks = sampler.stop()
 
@@ -305,9 +311,9 @@ def main():
             phases[nm] = round(phases.get(nm, 0.0) + t, 4)
 
     if world > 1:
-        t = torch.tensor([ms, ms_e2e, ms_sc, ms_sh, ms_co], device=dev)
+        t = torch.tensor([ms, ms_e2e, ms_sc, ms_sh, ms_co, ms_co_sc], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, ms_e2e, ms_sc, ms_sh, ms_co = t.tolist()
+        ms, ms_e2e, ms_sc, ms_sh, ms_co, ms_co_sc = t.tolist()
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -374,7 +380,8 @@ def main():
         "lasso_commit_sharded": None if not sharded else {
             "workload": f"ONE {WORKLOAD} proof on {world} GPUs: commitment MSMs point-sharded, partial commitments summed "
                         "over NVLink peer memory, sum-checks replicated (strong scaling of the proof latency)",
-            "ms_per_proof": ms_co, "phases_ms": phases_co},
+            "ms_per_proof": ms_co, "phases_ms": phases_co,
+            "ms_per_proof_with_sharded_sumchecks": ms_co_sc if ms_co_sc else None},
         "roofline": roof, "cpu_baseline": cpu}))
     if world > 1:
         dist.destroy_process_group()
