@@ -18,4 +18,11 @@ $FULL -k regex:sc_eval_round_kernel -s 1 -c 1 -o $O/full_sc_round1 python tools/
 $FULL -k regex:msm_accumulate -s 1 -c 1 -o $O/full_msm_acc python tools/prof_lasso.py 20 1 > /dev/null 2>&1
 $FULL -k regex:sc_generic_round_kernel -s 0 -c 1 -o $O/full_generic_round0 python tools/bench_zero_check.py 20 > /dev/null 2>&1
 for f in full_sc_round1 full_msm_acc full_generic_round0; do python tools/ncu_summary.py $O/$f.ncu-rep > $O/ncu_$f.txt 2>&1; done
+# instruction issue rates and the multiplier's own peak (build once: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -o tools/micro/pipe_rates tools/micro/pipe_rates.cu)
+[ -x tools/micro/pipe_rates ] && ./tools/micro/pipe_rates > $O/pipe_rates.txt 2>&1
+# >= 2 GPUs: the sharded provers (incl. b200_dist_shard_sumchecks) against the oracle, with timing of one cooperative 2^20 proof
+if [ "$(nvidia-smi -L | wc -l)" -ge 2 ]; then
+  DIST_QUICK=time python -m torch.distributed.run --nnodes=1 --nproc-per-node=2 --master-addr 127.0.0.1 --master-port 29511 tests/dist_worker.py > $O/dist_quick_2gpu.log 2>&1
+  grep -E "OK|COOPERATIVE|Error|assert" $O/dist_quick_2gpu.log
+fi
 ls -la $O
