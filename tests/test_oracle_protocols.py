@@ -205,3 +205,107 @@ def test_reference_sum_check_rotation_shape(n):
     bad[1] = O.rand_fr(99, 1 << n)
     with pytest.raises(AssertionError):
         _run_zero_check(n, expr, bad, 60 + n)
+
+
+# ---- verified specification of a planned kernel optimisation: eq-factored round polynomial ------
+def _eq_factored_prove(M, tr, n, polys, y, terms, claim, switch_round):
+    """The same messages as sumcheck_prove_evals, computed WITHOUT binding an eq table in the big rounds:
+        p_j(X) = c_j * l_j(X) * Q_j(X),  c_j = Π_{i<j} eq1(y_i, r_i),  l_j(X) = eq1(y_j, X),
+        Q_j(X) = Σ_b E_j[b] * G(X, b),   E_j = eq table of (y_{j+1}, ..., y_{n-1})  (a level of the eq_xy doubling).
+    Q_j has degree d - 1: it is evaluated at X = 1 .. d - 1 and its leading coefficient is accumulated as a third sum,
+    Q_j(d) follows by extrapolation; p(0) stays DERIVED from the claim (eval.rs:129) so that an inconsistent claim
+    gives the reference's bytes too. From `switch_round` on, the bound eq table c_{S-1} * E_{S-2} is materialised and
+    the rounds run exactly as in the reference (small rounds / single-launch tail kernel)."""
+    R = M.R
+    d = 1 + max(len(t[1]) for t in terms)
+    NP = d - 1
+    assert all(len(t[1]) == NP for t in terms) and NP in (1, 2)
+    tabs = [list(p) for p in polys]
+    chal, c, c_prev, eq = [], 1, 1, None
+
+    def eq1(a, b):
+        return (a * b + (1 - a) * (1 - b)) % R
+
+    for j in range(n):
+        pairs = len(tabs[0]) // 2
+        if j < switch_round:
+            E = M.eq_xy(y[j + 1:]) if j + 1 < n else [1]
+            q1 = q2 = lead = 0
+            for b in range(pairs):
+                for coeff, idx in terms:
+                    u0, u1 = tabs[idx[0]][2 * b], tabs[idx[0]][2 * b + 1]
+                    if NP == 2:
+                        v0, v1 = tabs[idx[1]][2 * b], tabs[idx[1]][2 * b + 1]
+                        du, dv = u1 - u0, v1 - v0
+                        eu1, edu = E[b] * u1 % R, E[b] * du % R           # two reduced products
+                        q1 += coeff * (eu1 * v1)                          # three unreduced products, accumulated wide
+                        q2 += coeff * ((eu1 + edu) * (v1 + dv))
+                        lead += coeff * (edu * dv)
+                    else:
+                        q1 += coeff * (E[b] * u1)
+                        lead += coeff * (E[b] * (u1 - u0))                # the slope of the linear Q
+            q1, q2, lead = q1 % R, q2 % R, lead % R
+            s0, s1 = c * (1 - y[j]) % R, c * y[j] % R                     # c_j * l_j(0), c_j * l_j(1)
+            s = [(s0 + k * (s1 - s0)) % R for k in range(d + 1)]
+            if NP == 2:
+                q = [None, q1, q2, (2 * q2 - q1 + 2 * lead) % R]          # Q(3) = 2 Q(2) - Q(1) + 2 * lead
+            else:
+                q = [None, q1, (q1 + lead) % R]
+            ev = [None] + [s[k] * q[k] % R for k in range(1, d + 1)]
+            ev[0] = (claim - ev[1]) % R
+        else:
+            if eq is None:  # the switch: bound eq table of the previous round's size, then the reference's bind
+                eq = [c_prev * e % R for e in M.eq_xy(y[j - 1:])] if j else M.eq_xy(y)
+                if j:
+                    eq = M.fix_var(eq, chal[-1])
+            ev = [0] * (d + 1)
+            for b in range(pairs):
+                for x in range(1, d + 1):
+                    at = lambda t: (t[2 * b] + x * (t[2 * b + 1] - t[2 * b])) % R
+                    sm = 0
+                    for coeff, idx in terms:
+                        p = coeff
+                        for i in idx:
+                            p = p * at(tabs[i]) % R
+                        sm += p
+                    ev[x] = (ev[x] + at(eq) * sm) % R
+            ev[0] = (claim - ev[1]) % R
+        for e in ev:
+            tr.write_fe(e)
+        r = tr.squeeze()
+        chal.append(r)
+        claim = M.interpolate(ev, r)
+        c_prev, c = c, c * eq1(y[j], r) % R
+        if eq is not None:
+            eq = M.fix_var(eq, r)
+        tabs = [M.fix_var(t, r) for t in tabs]
+    return chal, [t[0] for t in tabs]
+
+
+@pytest.mark.parametrize("n,T,NP,switch_round,true_claim", [(5, 1, 2, 5, True), (5, 3, 2, 3, False), (4, 4, 1, 2, False),
+                                                           (4, 2, 2, 1, True), (3, 2, 1, 0, False), (6, 2, 2, 4, False)])
+def test_eq_factored_round_polynomial_reproduces_the_reference_messages(n, T, NP, switch_round, true_claim):
+    import os
+    import sys
+
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import pymodel as M
+
+    seed = 700 + 10 * n + T
+    polys = [M.rand_fr(seed + i, 1 << n) for i in range(T * NP)]
+    w, y = M.rand_fr(seed + 50, T), M.rand_fr(seed + 51, n)
+    terms = [(w[t], list(range(t * NP, (t + 1) * NP))) for t in range(T)]
+    claim = M.rand_fr(seed + 52, 1)[0]
+    if true_claim:
+        eq = M.eq_xy(y)
+        claim = 0
+        for b in range(1 << n):
+            for coeff, idx in terms:
+                p = coeff * eq[b]
+                for i in idx:
+                    p = p * polys[i][b] % M.R
+                claim = (claim + p) % M.R
+    t_ref, t_new = M.Transcript(), M.Transcript()
+    ch_ref, ev_ref = M.sumcheck_prove_evals(t_ref, n, polys, y, terms, claim)
+    ch_new, ev_new = _eq_factored_prove(M, t_new, n, polys, y, terms, claim, switch_round)
+    assert t_new.stream == t_ref.stream and ch_new == ch_ref and ev_new == ev_ref
