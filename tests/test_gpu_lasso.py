@@ -139,3 +139,48 @@ def test_gpu_proof_verifies_with_the_pairing_check(hl, env):
         assert not O.lasso_verify(okzg, O.Transcript(bytes(bad)), kind, chunks, mu)
     finally:
         okzg.set_pairing_check(False)
+
+
+def test_gpu_proofs_verify_with_the_products_own_cpu_verifier(hl, env):
+    """prove on the GPU (libb200lasso.so), verify on the CPU (libb200verify.so, pairing form) — no oracle between
+    them: Lasso proofs of all three tables, a KZG opening, and the full-size 2^20-lookup proof; tampering is rejected."""
+    from halo2_lasso_b200 import verifier as V
+
+    ctx, okzg, kzg = env
+    vk = V.MultilinearKzgVerifier.setup(O.rand_fr(7, NV))
+    for kind, chunks, mu in ((O.TABLE_RANGE, 4, 6), (O.TABLE_AND, 8, 5), (O.TABLE_XOR, 2, 9)):
+        xs, ys = operands(kind, chunks, mu, 90 + mu)
+        tr = hl.Keccak256Transcript(ctx)
+        hl.LassoProver(ctx, kzg, kind, chunks).prove(xs, ys)
+        proof = tr.into_proof()
+        vt = V.ProofTranscript(proof)
+        assert vk.lasso_verify(vt, kind, chunks, mu) and vt.done()
+        bad = bytearray(proof)
+        bad[len(bad) // 2] ^= 8
+        assert not vk.lasso_verify(V.ProofTranscript(bytes(bad)), kind, chunks, mu)
+    nv = 9
+    poly, point = O.rand_fr(610, 1 << nv), O.rand_fr(611, nv)
+    dp = hl.MultilinearPolynomial.new(ctx, poly)
+    comm = kzg.commit(dp)
+    tr = hl.Keccak256Transcript(ctx)
+    kzg.open(dp, point)
+    assert vk.verify(V.ProofTranscript(tr.into_proof()), comm, point, O.evaluate(poly, point))
+
+
+def test_full_size_2_20_proof_verifies_with_the_products_own_cpu_verifier(hl):
+    from halo2_lasso_b200 import verifier as V
+
+    mu, chunks = 20, 4
+    ctx = hl.Context(0)
+    ss = O.rand_fr(7, mu)
+    kzg = hl.MultilinearKzg.setup(ctx, ss)
+    tr = hl.Keccak256Transcript(ctx)
+    hl.LassoProver(ctx, kzg, O.TABLE_RANGE, chunks).prove(O.rand_u64s(5, 1 << mu))
+    proof = tr.into_proof()
+    ctx.close()
+    vk = V.MultilinearKzgVerifier.setup(ss)
+    vt = V.ProofTranscript(proof)
+    assert vk.lasso_verify(vt, O.TABLE_RANGE, chunks, mu) and vt.done()
+    bad = bytearray(proof)
+    bad[2000] ^= 1
+    assert not vk.lasso_verify(V.ProofTranscript(bytes(bad)), O.TABLE_RANGE, chunks, mu)

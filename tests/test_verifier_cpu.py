@@ -1,0 +1,235 @@
+"""The product's CPU verifier (libb200verify.so, include/b200_verify.h; host code, runs without a GPU): it accepts the
+proofs of the oracle provers and the committed golden proofs of the pure-Python models, rejects tampered proofs and
+wrong statements, and reports malformed parameters as argument errors. Mirrors the accept / reject round trips of the
+reference's own tests (pb/piop/sum_check.rs:140-177, pb/pcs/multilinear.rs:293-406, pb/backend.rs:202-241)."""
+import json
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import oracle as O
+from halo2_lasso_b200 import hyperplonk as H
+from halo2_lasso_b200 import verifier as V
+from halo2_lasso_b200.expression import compose
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SS = O.rand_fr(7, 16)
+
+
+@pytest.fixture(scope="module")
+def okzg():
+    return O.Kzg(SS)
+
+
+@pytest.fixture(scope="module")
+def vkzg():
+    return V.MultilinearKzgVerifier.setup(SS)
+
+
+def tampered(proof, pos, bit=1):
+    bad = bytearray(proof)
+    bad[pos] ^= bit
+    return bytes(bad)
+
+
+def test_library_exports_exactly_the_declared_symbols():
+    out = subprocess.run(["nm", "-D", "--defined-only", V.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    exported = sorted(set(re.findall(r"\b(b200v_[a-z0-9_]+)\b", out)))
+    assert exported == V.declared_symbols() and len(exported) == 18
+
+
+def test_transcript_reading_side_matches_the_oracle():
+    to = O.Transcript()
+    fes = O.rand_fr(11, 5)
+    for f in fes[:4]:
+        to.write_fe(f)
+    c1 = to.squeeze()
+    to.common_fe(fes[4])
+    pt = O.g1_mul(O.g1_generator(), O.fr_from_ints([5])[0])
+    to.write_comm(pt)
+    c2 = to.squeeze()
+    tr = V.ProofTranscript(to.proof())
+    assert (tr.read_field_elements(4) == fes[:4]).all()
+    assert (tr.squeeze_challenges(1)[0] == c1).all()
+    tr.common_field_elements(fes[4:5])
+    assert (tr.read_commitments(1)[0] == pt).all()
+    assert (tr.squeeze_challenges(1)[0] == c2).all() and tr.done()
+    # non-canonical field element (>= r) and a point off the curve are rejected (transcript.rs:146-152, 198-208)
+    with pytest.raises(ValueError):
+        V.ProofTranscript(b"\xff" * 32).read_field_elements(1)
+    with pytest.raises(ValueError):
+        V.ProofTranscript(tampered(to.proof()[4 * 32:], 40)).read_commitments(1)
+    with pytest.raises(ValueError):
+        V.ProofTranscript(b"\x01" * 31).read_field_elements(1)  # truncated
+
+
+@pytest.mark.parametrize("n", [1, 5, 9])
+def test_sumcheck_verify_evaluations_and_coefficients(n):
+    a, b, y = O.rand_fr(1, 1 << n), O.rand_fr(2, 1 << n), O.rand_fr(3, n)
+    s = O.sum_eq_ab(y, a, b)
+    one = O.fr_from_ints([1])[0]
+    to = O.Transcript()
+    ch, ev = O.sumcheck_prove_evals(to, n, [a, b], y, [(one, [0, 1])], s)
+    fin_o, _ = O.sumcheck_verify(O.Transcript(to.proof()), n, 3, s)
+    tr = V.ProofTranscript(to.proof())
+    fin, x = V.sumcheck_verify(tr, n, 3, s)
+    assert tr.done() and (x == ch).all() and (fin == fin_o).all()
+    # the caller's final check (sum_check.rs:166-176): claim == eq(x, y) * a(x) * b(x)
+    assert (O.field_op("mul", O.field_op("mul", O.eq_xy_eval(x, y), ev[0]), ev[1])[0] == fin).all()
+    assert V.sumcheck_verify(V.ProofTranscript(tampered(to.proof(), 33)), n, 3, s) is None
+    assert V.sumcheck_verify(V.ProofTranscript(to.proof()), n, 3, O.field_op("add", s, one)[0]) is None
+    # CoefficientsProver messages
+    scal, ys = O.rand_fr(5, 2), [O.rand_fr(6, n), O.rand_fr(7, n)]
+    claim = O.rand_fr(8, 1)[0]
+    tc = O.Transcript()
+    O.sumcheck_prove_coeffs(tc, n, [a, b], [(scal[0], ys[0], 0), (scal[1], ys[1], 1)], claim)
+    want = O.sumcheck_verify(O.Transcript(tc.proof()), n, 2, claim, coeffs=True)
+    got = V.sumcheck_verify(V.ProofTranscript(tc.proof()), n, 2, claim, coefficients_form=True)
+    assert (want is None) == (got is None)
+    if got is not None:
+        assert (got[0] == want[0]).all() and (got[1] == want[1]).all()
+    with pytest.raises(V.VerifierArgError):
+        V.sumcheck_verify(V.ProofTranscript(to.proof()), 0, 3, s)
+
+
+def test_kzg_open_and_batch_open_verify(okzg, vkzg):
+    nv = 6
+    poly, point = O.rand_fr(600, 1 << nv), O.rand_fr(601, nv)
+    comm = okzg.commit(poly)
+    to = O.Transcript()
+    ev = okzg.open(to, poly, point)
+    assert vkzg.verify(V.ProofTranscript(to.proof()), comm, point, ev)
+    assert not vkzg.verify(V.ProofTranscript(to.proof()), comm, point, O.field_op("add", ev, O.fr_from_ints([1]))[0])
+    assert not vkzg.verify(V.ProofTranscript(tampered(to.proof(), 70)), comm, point, ev)
+    assert not vkzg.verify(V.ProofTranscript(to.proof()), okzg.commit(O.rand_fr(602, 1 << nv)), point, ev)
+    # batch: 4 polynomials, 2 points, 5 (poly, point) pairs (pb/pcs/multilinear.rs:345-406 shape)
+    polys = [O.rand_fr(900 + i, 1 << nv) for i in range(4)]
+    points = [O.rand_fr(950 + i, nv) for i in range(2)]
+    evals = [(p, q, O.evaluate(polys[p], points[q])) for p, q in [(0, 0), (1, 1), (2, 1), (3, 0), (0, 1)]]
+    comms = [okzg.commit(p) for p in polys]
+    tb = O.Transcript()
+    okzg.batch_open(tb, polys, points, evals)
+    assert vkzg.batch_verify(V.ProofTranscript(tb.proof()), comms, points, evals)
+    bad = list(evals)
+    bad[2] = (2, 1, O.rand_fr(1, 1)[0])
+    assert not vkzg.batch_verify(V.ProofTranscript(tb.proof()), comms, points, bad)
+    assert not vkzg.batch_verify(V.ProofTranscript(tampered(tb.proof(), len(tb.proof()) - 5)), comms, points, evals)
+    with pytest.raises(V.VerifierArgError):
+        vkzg.batch_verify(V.ProofTranscript(tb.proof()), comms, points, [(7, 0, evals[0][2]), evals[1]])
+    # parameters travel as G2 points: export / import round trip verifies the same opening
+    again = V.MultilinearKzgVerifier.from_g2_powers(vkzg.g2_powers())
+    assert again.verify(V.ProofTranscript(to.proof()), comm, point, ev)
+    broken = vkzg.g2_powers()
+    broken[0, 0] ^= 1
+    with pytest.raises(V.VerifierArgError):
+        V.MultilinearKzgVerifier.from_g2_powers(broken)
+
+
+@pytest.mark.parametrize("kind,chunks,mu", [(O.TABLE_RANGE, 4, 5), (O.TABLE_AND, 8, 4), (O.TABLE_XOR, 2, 6)])
+def test_lasso_verify_accepts_oracle_proofs_and_rejects_tampering(okzg, vkzg, kind, chunks, mu):
+    xs, ys = O.rand_u64s(70 + mu, 1 << mu), O.rand_u64s(80 + mu, 1 << mu)
+    if kind == O.TABLE_RANGE:
+        ys = None
+    else:
+        xs &= np.uint64((1 << (8 * chunks)) - 1)
+        ys &= np.uint64((1 << (8 * chunks)) - 1)
+        ys[1::2] = ys[0::2]
+    xs[1::2] = xs[0::2]  # repeated addresses: read_ts != 0 (an all-zero polynomial commits to the identity, which the
+    to = O.Transcript()  # transcript cannot encode, transcript.rs:174-179)
+    assert O.lasso_prove(okzg, to, kind, chunks, mu, xs, ys)
+    proof = to.proof()
+    tr = V.ProofTranscript(proof)
+    assert vkzg.lasso_verify(tr, kind, chunks, mu) and tr.done()
+    for pos in (7, len(proof) // 3, len(proof) // 2, len(proof) - 9):
+        assert not vkzg.lasso_verify(V.ProofTranscript(tampered(proof, pos, 4)), kind, chunks, mu)
+    assert not vkzg.lasso_verify(V.ProofTranscript(proof), kind, chunks, mu + 1)
+    other = O.TABLE_XOR if kind == O.TABLE_AND else (O.TABLE_AND if kind == O.TABLE_XOR else None)
+    if other is not None:
+        assert not vkzg.lasso_verify(V.ProofTranscript(proof), other, chunks, mu)
+    with pytest.raises(V.VerifierArgError):
+        vkzg.lasso_verify(V.ProofTranscript(proof), 3, chunks, mu)
+
+
+def test_lasso_verify_accepts_the_committed_golden_proofs(vkzg):
+    gold = json.load(open(os.path.join(HERE, "golden", "lasso_golden.json")))
+    for c in gold["cases"]:
+        assert c["srs_seed"] == 7
+        tr = V.ProofTranscript(bytes.fromhex(c["proof"]))
+        assert vkzg.lasso_verify(tr, c["kind"], c["chunks"], c["mu"]) and tr.done()
+
+
+def _hyperplonk_verifier(okzg, vkzg, info, expr, nz):
+    pre = [okzg.commit(O.fr_from_ints(p)) for p in info.preprocess_polys]
+    sig = [okzg.commit(O.fr_from_ints(p)) for p in H.permutation_polys(info.k, info.permutation_polys, info.permutations)]
+    return V.HyperPlonkVerifier(vkzg, info.k, info.num_instances, info.num_witness_polys, getattr(info, "num_challenges", None),
+                                len(info.lookups), nz, expr, pre, sig)
+
+
+def test_hyperplonk_verify_accepts_the_committed_golden_proofs(okzg, vkzg):
+    gold = json.load(open(os.path.join(HERE, "golden", "hyperplonk_golden.json")))
+    for c in gold["cases"]:
+        k, proof = c["k"], bytes.fromhex(c["proof"])
+        if c["circuit"] == "two_phase":
+            info, inst_cols, _ = H.rand_two_phase_circuit(k, c["seed"], c["with_lookup"])
+            nz, expr = compose(k, info.constraints, info.num_poly, info.permutation_polys,
+                               num_challenges=sum(info.num_challenges), lookups=info.lookups)
+            instances = [v for col in inst_cols for v in col]
+        else:
+            fixture = H.rand_vanilla_plonk_with_lookup_circuit if c["circuit"].endswith("lookup") else H.rand_vanilla_plonk_circuit
+            info, instances, _ = fixture(k, c["seed"], num_instances=2)
+            nz, expr = compose(k, info.constraints, info.num_poly, info.permutation_polys, max_degree=c["max_degree"], lookups=info.lookups)
+        hv = _hyperplonk_verifier(okzg, vkzg, info, expr, nz)
+        inst = O.fr_from_ints(instances)
+        tr = V.ProofTranscript(proof)
+        assert hv.verify(tr, inst) and tr.done(), c["circuit"]
+        for pos in (3, len(proof) // 2, len(proof) - 11):
+            assert not hv.verify(V.ProofTranscript(tampered(proof, pos, 2)), inst)
+        for j in range(inst.shape[0]):
+            wrong = inst.copy()
+            wrong[j] = O.rand_fr(99, 1)[0]
+            assert not hv.verify(V.ProofTranscript(proof), wrong)
+        assert not hv.verify(V.ProofTranscript(proof), inst[:-1])
+
+
+def test_cfg1_hyperplonk_then_lasso_on_one_transcript(okzg, vkzg):
+    """BASELINE cfg1 shape at toy size: the HyperPlonk section followed by the Lasso section on one proof stream"""
+    k, mu, chunks = 4, 4, 4
+    info, instances, w = H.rand_vanilla_plonk_circuit(k, 77)
+    nz, expr = compose(k, info.constraints, info.num_poly, info.permutation_polys)
+    ohp = O.HyperPlonk(okzg, k, expr, len(instances), 3, [O.fr_from_ints(p) for p in info.preprocess_polys],
+                       info.permutation_polys, info.permutations, nz)
+    inst = O.fr_from_ints(instances)
+    xs = O.rand_u64s(9, 1 << mu)
+    xs[1::2] = xs[0::2]
+    to = O.Transcript()
+    assert ohp.prove(to, inst, [O.fr_from_ints(c) for c in w])
+    assert O.lasso_prove(okzg, to, O.TABLE_RANGE, chunks, mu, xs, None)
+    hv = _hyperplonk_verifier(okzg, vkzg, info, expr, nz)
+    tr = V.ProofTranscript(to.proof())
+    assert hv.verify(tr, inst) and not tr.done()
+    assert vkzg.lasso_verify(tr, O.TABLE_RANGE, chunks, mu) and tr.done()
+
+
+def test_hyperplonk_verifier_rejects_malformed_parameters(okzg, vkzg):
+    from halo2_lasso_b200.expression import Expression as E
+
+    info, instances, _ = H.rand_vanilla_plonk_circuit(3, 5)
+    nz, expr = compose(3, info.constraints, info.num_poly, info.permutation_polys)
+    pre = [okzg.commit(O.fr_from_ints(p)) for p in info.preprocess_polys]
+    sig = [okzg.commit(O.fr_from_ints(p)) for p in H.permutation_polys(3, info.permutation_polys, info.permutations)]
+    V.HyperPlonkVerifier(vkzg, 3, info.num_instances, 3, None, 0, nz, expr, pre, sig)
+    for bad_expr in (expr * E.polynomial(40), expr + E.challenge(3), expr * E.eq_xy(1), E.polynomial(0, 9) * expr):
+        with pytest.raises(V.VerifierArgError):
+            V.HyperPlonkVerifier(vkzg, 3, info.num_instances, 3, None, 0, nz, bad_expr, pre, sig)
+    with pytest.raises(V.VerifierArgError):
+        V.HyperPlonkVerifier(vkzg, 3, info.num_instances, [2, 1], [0, 0], 0, nz, expr, pre, sig)  # phase 0 without challenges
+    off_curve = [p.copy() for p in pre]
+    off_curve[0][0] ^= 1
+    with pytest.raises(V.VerifierArgError):
+        V.HyperPlonkVerifier(vkzg, 3, info.num_instances, 3, None, 0, nz, expr, off_curve, sig)
+    with pytest.raises(V.VerifierArgError):
+        V.HyperPlonkVerifier(vkzg, 17, info.num_instances, 3, None, 0, nz, expr, pre, sig)  # k beyond the parameters
