@@ -233,3 +233,28 @@ def test_hyperplonk_verifier_rejects_malformed_parameters(okzg, vkzg):
         V.HyperPlonkVerifier(vkzg, 3, info.num_instances, 3, None, 0, nz, expr, off_curve, sig)
     with pytest.raises(V.VerifierArgError):
         V.HyperPlonkVerifier(vkzg, 17, info.num_instances, 3, None, 0, nz, expr, pre, sig)  # k beyond the parameters
+
+
+def test_plain_c_host_program_verifies_a_proof_file(okzg, tmp_path):
+    """examples/verify_demo.c: gcc -std=c99 against include/b200_verify.h only — what a cgo / Rust-FFI binding links"""
+    root = os.path.dirname(HERE)
+    lib_dir = os.path.join(root, "halo2-lasso_b200")
+    exe = str(tmp_path / "verify_demo")
+    subprocess.check_call(["gcc", "-std=c99", "-O2", "-Wall", "-Werror", "-I", os.path.join(root, "include"),
+                           os.path.join(root, "examples", "verify_demo.c"), "-L", lib_dir, "-lb200verify",
+                           f"-Wl,-rpath,{lib_dir}", "-o", exe])
+    mu = 6
+    xs = O.rand_u64s(5, 1 << mu)
+    xs[(1 << mu) // 2:] = xs[: (1 << mu) // 2]
+    to = O.Transcript()
+    assert O.lasso_prove(okzg, to, O.TABLE_RANGE, 4, mu, xs, None)
+    (tmp_path / "proof.bin").write_bytes(to.proof())
+    (tmp_path / "bad.bin").write_bytes(tampered(to.proof(), 500))
+    (tmp_path / "ss.bin").write_bytes(np.ascontiguousarray(SS).tobytes())
+    run = lambda name, *stmt: subprocess.run([exe, str(tmp_path / name), str(tmp_path / "ss.bin"), *map(str, stmt)],
+                                             capture_output=True, text=True, timeout=120)
+    ok = run("proof.bin", 0, 4, mu)
+    assert ok.returncode == 0 and "accepted" in ok.stdout, ok.stdout + ok.stderr
+    assert run("bad.bin", 0, 4, mu).returncode == 1
+    assert run("proof.bin", 0, 4, mu + 1).returncode == 1
+    assert run("proof.bin", 5, 4, mu).returncode == 2
