@@ -601,6 +601,38 @@ def compile_expression_native(expression, const_mont):
             [tuple(int(v) for v in r) for r in ops[: no.value]], nt.value, deg.value)
 
 
+def compose_native(k, constraints, num_poly, permutation_polys, num_challenges=0, max_degree=4, lookups=()):
+    """`b200_expression_compose` (host only, no GPU): preprocessor.rs:25-60 inside the library. Constants cross as
+    Montgomery limbs (converted here with Python ints). Returns (num_permutation_z_polys, tokens int32, consts (n, 4)
+    uint64 Montgomery) — what `b200v_hyperplonk_new` and `b200_sumcheck_prove_expression` take."""
+    from .expression import R_MOD, serialize_expression
+
+    ctok, ltok, consts = [], [], []
+    for c in constraints:
+        serialize_expression(c, ctok, consts)
+    for lookup in lookups:
+        ltok.append(len(lookup))
+        for a, t in lookup:
+            serialize_expression(a, ltok, consts)
+            serialize_expression(t, ltok, consts)
+    cm = np.zeros((max(1, len(consts)), 4), dtype=np.uint64)
+    for i, c in enumerate(consts):
+        v = c * (1 << 256) % R_MOD
+        cm[i] = [(v >> (64 * j)) & 0xFFFFFFFFFFFFFFFF for j in range(4)]
+    ctok = np.asarray(ctok, dtype=np.int32)
+    ltok = np.asarray(ltok if ltok else [0], dtype=np.int32)
+    pidx = np.asarray(list(permutation_polys) if len(permutation_polys) else [0], dtype=np.int32)
+    cap = 1 << 16
+    tout, cout = np.zeros(cap, dtype=np.int32), np.zeros((cap, 4), dtype=np.uint64)
+    nt, nc, nz = C.c_int(), C.c_int(), C.c_int()
+    _chk(lib().b200_expression_compose(C.c_int(k), C.c_int(num_poly), C.c_int(num_challenges), C.c_int(len(constraints)),
+                                       _p(ctok), C.c_int(len(ctok)), C.c_int(len(lookups)), _p(ltok),
+                                       C.c_int(len(ltok) if lookups else 0), _p(cm), C.c_int(len(consts)),
+                                       C.c_int(len(permutation_polys)), _p(pidx), C.c_int(max_degree), _p(tout), C.c_int(cap),
+                                       C.byref(nt), _p(cout), C.c_int(cap), C.byref(nc), C.byref(nz)), "expression_compose")
+    return nz.value, tout[: nt.value].copy(), cout[: nc.value].copy()
+
+
 def prove_expression(ctx, num_vars, expression, polys, challenges, ys, claimed_sum):
     """`ClassicSumCheck::<EvaluationsProver>::prove(num_vars, VirtualPolynomial::new(expression, polys, challenges,
     ys), sum, transcript)`. challenges: canonical Python ints; ys: list of (num_vars, 4) Montgomery arrays.

@@ -143,6 +143,28 @@ inline ExprP e_parse(const int32_t*& t, const int32_t* end, const Fr* consts, in
   return nullptr;
 }
 
+// tree -> prefix tokens + constants (the inverse of e_parse; constants are appended in visiting order)
+inline void e_serialize(const ExprP& e, std::vector<int32_t>* tokens, std::vector<Fr>* consts) {
+  tokens->push_back((int32_t)e->kind);
+  switch (e->kind) {
+    case Expr::CONST:
+    case Expr::SCALED:
+      tokens->push_back((int32_t)consts->size());
+      consts->push_back(e->scalar);
+      break;
+    case Expr::LAGRANGE:
+    case Expr::EQXY:
+    case Expr::CHALLENGE: tokens->push_back(e->a); break;
+    case Expr::POLY:
+      tokens->push_back(e->a);
+      tokens->push_back(e->b);
+      break;
+    case Expr::DPOW: tokens->push_back((int32_t)e->ch.size() - 1); break;
+    default: break;
+  }
+  for (auto& c : e->ch) e_serialize(c, tokens, consts);
+}
+
 inline int e_degree(const ExprP& e) {  // expression.rs:171-182
   switch (e->kind) {
     case Expr::CONST:

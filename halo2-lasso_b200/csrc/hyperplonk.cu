@@ -297,6 +297,59 @@ int b200_expression_compile(const int32_t* tokens, int ntokens, const void* cons
   return B200_OK;
 }
 
+// preprocessor.rs:25-60 as a host-only service: circuit expressions in, composed zero-check expression out
+int b200_expression_compose(int k, int num_poly, int num_challenges, int nconstraints, const int32_t* constraint_tokens,
+                            int nconstraint_tokens, int nlookups, const int32_t* lookup_tokens, int nlookup_tokens,
+                            const void* consts_fr, int nconsts, int nperm, const int32_t* permutation_polys,
+                            int max_degree, int32_t* tokens_out, int tokens_cap, int* ntokens, void* consts_out,
+                            int consts_cap, int* nconsts_out, int* num_permutation_z_polys) {
+  if (k < 1 || k > 30 || num_poly < 1 || num_challenges < 0 || nconstraints < 1 || !constraint_tokens || nlookups < 0 ||
+      (nlookups && !lookup_tokens) || nconsts < 0 || (nconsts && !consts_fr) || nperm < 0 || nperm > 8 ||
+      (nperm && !permutation_polys) || max_degree < 2 || !tokens_out || !ntokens || !consts_out || !nconsts_out ||
+      !num_permutation_z_polys)
+    return B200_ERR_ARG;
+  std::vector<ExprP> constraints;
+  const int32_t *t = constraint_tokens, *tend = constraint_tokens + nconstraint_tokens;
+  for (int i = 0; i < nconstraints; ++i) {
+    ExprP e = e_parse(t, tend, (const Fr*)consts_fr, nconsts);
+    if (!e || !indices_in_range(e, num_poly, num_challenges)) return B200_ERR_ARG;
+    constraints.push_back(e);
+  }
+  if (t != tend) return B200_ERR_ARG;
+  std::vector<LookupCols> lookups;
+  t = lookup_tokens;
+  tend = lookup_tokens + nlookup_tokens;
+  for (int l = 0; l < nlookups; ++l) {
+    if (t >= tend) return B200_ERR_ARG;
+    const int width = *t++;
+    if (width < 1 || width > 64) return B200_ERR_ARG;
+    LookupCols cols;
+    for (int j = 0; j < width; ++j) {
+      ExprP in = e_parse(t, tend, (const Fr*)consts_fr, nconsts);
+      ExprP tb = in ? e_parse(t, tend, (const Fr*)consts_fr, nconsts) : nullptr;
+      if (!tb || !indices_in_range(in, num_poly, num_challenges) || !indices_in_range(tb, num_poly, num_challenges))
+        return B200_ERR_ARG;
+      cols.push_back({in, tb});
+    }
+    lookups.push_back(cols);
+  }
+  std::vector<int> perm(permutation_polys, permutation_polys + nperm);
+  for (int p : perm)
+    if (p < 0 || p >= num_poly) return B200_ERR_ARG;
+  int num_z = 0;
+  ExprP composed = e_compose(k, constraints, num_poly, perm, num_challenges, max_degree, lookups, &num_z);
+  std::vector<int32_t> tok;
+  std::vector<Fr> cs;
+  e_serialize(composed, &tok, &cs);
+  *ntokens = (int)tok.size();
+  *nconsts_out = (int)cs.size();
+  *num_permutation_z_polys = num_z;
+  if ((int)tok.size() > tokens_cap || (int)cs.size() > consts_cap) return B200_ERR_NOMEM;  // sizes reported above
+  memcpy(tokens_out, tok.data(), tok.size() * sizeof(int32_t));
+  if (!cs.empty()) memcpy(consts_out, cs.data(), cs.size() * sizeof(Fr));
+  return B200_OK;
+}
+
 int b200_sumcheck_prove_expression(b200_ctx* h, int num_vars, const int32_t* tokens, int ntokens, const void* consts_fr,
                                    int nconsts, const void* const* dev_polys, int npolys, const void* host_challenges,
                                    int nchallenges, const void* host_ys, int nys, const void* host_sum,

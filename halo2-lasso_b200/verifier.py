@@ -164,13 +164,18 @@ class HyperPlonkVerifier:
         cols = [num_instances] if isinstance(num_instances, int) else list(num_instances)
         phases = [num_witness_polys] if isinstance(num_witness_polys, int) else list(num_witness_polys)
         chals = [0] * len(phases) if num_challenges is None else list(num_challenges)
-        tokens, consts = serialize_expression(expression, [], [])
-        R = 1 << 256
-        cm = np.zeros((max(1, len(consts)), 4), dtype=np.uint64)
-        for i, c in enumerate(consts):  # canonical ints -> Montgomery limbs
-            v = c * R % R_MOD
-            cm[i] = [(v >> (64 * j)) & 0xFFFFFFFFFFFFFFFF for j in range(4)]
-        tok = np.asarray(tokens, dtype=np.int32)
+        if isinstance(expression, tuple):  # (tokens, Montgomery constants), e.g. from b200_expression_compose
+            tok = np.ascontiguousarray(expression[0], dtype=np.int32)
+            consts = np.ascontiguousarray(expression[1], dtype=np.uint64).reshape(-1, 4)
+            cm = consts if len(consts) else np.zeros((1, 4), dtype=np.uint64)
+        else:
+            tokens, consts = serialize_expression(expression, [], [])
+            R = 1 << 256
+            cm = np.zeros((max(1, len(consts)), 4), dtype=np.uint64)
+            for i, c in enumerate(consts):  # canonical ints -> Montgomery limbs
+                v = c * R % R_MOD
+                cm[i] = [(v >> (64 * j)) & 0xFFFFFFFFFFFFFFFF for j in range(4)]
+            tok = np.asarray(tokens, dtype=np.int32)
         a, b, c = (np.asarray(v if v else [0], dtype=np.int32) for v in (cols, phases, chals))
         pre = np.ascontiguousarray(np.asarray(preprocess_comms, dtype=np.uint64).reshape(-1, 8))
         perm = np.ascontiguousarray(np.asarray(permutation_comms, dtype=np.uint64).reshape(-1, 8))

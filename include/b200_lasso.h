@@ -145,6 +145,18 @@ int b200_expression_compile(const int32_t* tokens, int ntokens, const void* cons
  * permutation polynomials with the SRS of the context and composes the zero-check expression (preprocessor.rs:25-170).
  * prove: instances as Montgomery field elements, witness polynomials on the device; appends the proof to the context
  * transcript. B200_ERR_LOOKUP = Error::InvalidSnark("Invalid lookup input"). */
+/* compose (pb/backend/hyperplonk/preprocessor.rs:25-60) as a host-only service (no GPU needed): the circuit's
+ * constraints / lookups / permutation columns (same token streams as b200_hyperplonk_preprocess; num_poly = instance +
+ * preprocess + witness polynomials; num_challenges = the circuit's own) -> the composed zero-check expression as prefix
+ * tokens + constants, and num_permutation_z_polys. This is the `expression` b200v_hyperplonk_new (b200_verify.h) and
+ * b200_sumcheck_prove_expression take. B200_ERR_NOMEM when a capacity is too small (*ntokens / *nconsts_out then hold the
+ * required sizes). */
+int b200_expression_compose(int k, int num_poly, int num_challenges, int nconstraints, const int32_t* constraint_tokens,
+                            int nconstraint_tokens, int nlookups, const int32_t* lookup_tokens, int nlookup_tokens,
+                            const void* consts_fr, int nconsts, int nperm, const int32_t* permutation_polys,
+                            int max_degree, int32_t* tokens_out, int tokens_cap, int* ntokens, void* consts_out,
+                            int consts_cap, int* nconsts_out, int* num_permutation_z_polys);
+
 typedef struct b200_hyperplonk b200_hyperplonk;
 int b200_hyperplonk_preprocess(b200_ctx* ctx, int k, int num_instances, int num_witness_polys, int npreprocess,
                                const void* const* dev_preprocess, int nconstraints, const int32_t* constraint_tokens,

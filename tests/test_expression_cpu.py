@@ -4,6 +4,8 @@ paths (generic ProverState restatement vs fixed-shape prover; oracle vs a pure-P
 expression over MATERIALISED leaf tables — the strategy the GPU uses)."""
 import random
 
+import pytest
+
 import numpy as np
 
 import oracle as O
@@ -219,3 +221,30 @@ def test_native_compiler_rejects_malformed_token_streams():
     assert compile_raw([42]) == hl.B200_ERR_ARG                       # unknown node kind
     assert compile_raw([4, 0, 0, 4, 1, 0]) == hl.B200_ERR_ARG         # trailing tokens
     assert compile_raw([10, 0, 4, 0, 0]) == hl.B200_ERR_ARG           # DistributePowers with no terms
+
+
+def test_native_compose_equals_the_python_compose_token_for_token():
+    """`b200_expression_compose` (csrc/expr.hpp e_compose + e_serialize, host code: runs without a GPU) against
+    expression.py::compose + serialize_expression — two implementations of preprocessor.rs:25-60 — on vanilla plonk
+    (one and two permutation chunks), plonk with the LogUp lookup and the two-phase circuit."""
+    import halo2_lasso_b200 as hl
+    from halo2_lasso_b200 import hyperplonk as H
+    from halo2_lasso_b200.expression import compose, serialize_expression
+
+    rinv = pow(1 << 256, -1, R_MOD)
+    cases = [(H.rand_vanilla_plonk_circuit(4, 1)[0], 0, 4), (H.rand_vanilla_plonk_circuit(5, 2)[0], 0, 3),
+             (H.rand_vanilla_plonk_with_lookup_circuit(4, 1)[0], 0, 4), (H.rand_two_phase_circuit(4, 1)[0], 2, 4),
+             (H.rand_two_phase_circuit(4, 1, with_lookup=False)[0], 2, 4)]
+    for info, nc, md in cases:
+        nz, expr = compose(info.k, info.constraints, info.num_poly, info.permutation_polys, num_challenges=nc, max_degree=md,
+                           lookups=info.lookups)
+        tokens, consts = serialize_expression(expr, [], [])
+        nz2, tok2, cm2 = hl.compose_native(info.k, info.constraints, info.num_poly, info.permutation_polys, nc, md, info.lookups)
+        assert nz2 == nz and list(tok2) == tokens
+        assert [sum(int(c[j]) << (64 * j) for j in range(4)) * rinv % R_MOD for c in cm2] == consts
+    # malformed circuits are argument errors: a polynomial index beyond num_poly, a challenge the circuit does not have
+    info = cases[0][0]
+    for bad in (info.constraints + [E.polynomial(9)], info.constraints + [E.challenge(0) * E.polynomial(1)]):
+        with pytest.raises(hl.B200Error) as e:
+            hl.compose_native(info.k, bad, info.num_poly, info.permutation_polys, 0, 4, info.lookups)
+        assert e.value.code == hl.B200_ERR_ARG

@@ -186,6 +186,13 @@ def test_hyperplonk_verify_accepts_the_committed_golden_proofs(okzg, vkzg):
         inst = O.fr_from_ints(instances)
         tr = V.ProofTranscript(proof)
         assert hv.verify(tr, inst) and tr.done(), c["circuit"]
+        # the same with the expression composed inside the library (b200_expression_compose): C ABI on both sides
+        import halo2_lasso_b200 as hl
+
+        nz2, tok, cm = hl.compose_native(k, info.constraints, info.num_poly, info.permutation_polys,
+                                         sum(getattr(info, "num_challenges", [0])), c.get("max_degree", 4), info.lookups)
+        assert nz2 == nz
+        assert _hyperplonk_verifier(okzg, vkzg, info, (tok, cm), nz).verify(V.ProofTranscript(proof), inst)
         for pos in (3, len(proof) // 2, len(proof) - 11):
             assert not hv.verify(V.ProofTranscript(tampered(proof, pos, 2)), inst)
         for j in range(inst.shape[0]):
