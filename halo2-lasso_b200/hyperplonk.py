@@ -374,6 +374,21 @@ class HyperPlonk:
         _chk(lib().b200_hyperplonk_commitments(self.h, _p(a), _p(b)), "hyperplonk_commitments")
         return a[: len(self.preprocess)], b[: len(self.info.permutation_polys)]
 
+    def verifier(self, kzg_verifier):
+        """The `vp` half of `HyperPlonk::preprocess -> (pp, vp)` (hyperplonk.rs:138-161) for the CPU verifier
+        (verifier.py / include/b200_verify.h): same circuit shape, the commitments of this prover parameter object, the
+        zero-check expression composed by the library (b200_expression_compose)."""
+        from . import compose_native
+        from .verifier import HyperPlonkVerifier
+
+        info = self.info
+        nz, tok, cm = compose_native(info.k, info.constraints, info.num_poly, info.permutation_polys,
+                                     sum(self.phase_challenges), getattr(info, "max_degree", 4), info.lookups)
+        assert nz == self.num_z
+        pre, perm = self.commitments()
+        return HyperPlonkVerifier(kzg_verifier, info.k, self.instance_cols, self.phase_witness, self.phase_challenges,
+                                  len(info.lookups), nz, (tok, cm), pre, perm)
+
     def permutation_poly(self, i):
         out = np.zeros((1 << self.info.k, 4), dtype=np.uint64)
         _chk(lib().b200_hyperplonk_permutation_poly(self.h, C.c_int(i), _p(out)), "hyperplonk_permutation_poly")

@@ -311,3 +311,38 @@ def test_hyperplonk_matches_committed_golden_bytes(hl, env):
             info.max_degree = c["max_degree"]
             H.HyperPlonk(ctx, kzg, info).prove(instances, witness_ints=w)
         assert tr.into_proof() == want, c
+
+
+@pytest.mark.parametrize("circuit", ["vanilla", "lookup", "two_phase"])
+def test_preprocess_prove_on_the_gpu_verify_with_the_products_cpu_verifier(hl, env, circuit):
+    """`preprocess -> (pp, vp)`, `prove(pp)`, `verify(vp)` (pb/backend.rs:202-241 run_plonkish_backend) entirely inside
+    the product: prover parameters and proof on the GPU, verifier parameters derived from them (commitments + the
+    library-composed expression), verification by libb200verify.so — the oracle only supplies the SRS trapdoor stream."""
+    from halo2_lasso_b200 import hyperplonk as H
+    from halo2_lasso_b200 import verifier as V
+
+    ctx, okzg, kzg = env
+    k = 6
+    vk = V.MultilinearKzgVerifier.setup(O.rand_fr(7, NV))
+    tr = hl.Keccak256Transcript(ctx)
+    if circuit == "two_phase":
+        info, inst_cols, synth = H.rand_two_phase_circuit(k, 300)
+        hp = H.HyperPlonk(ctx, kzg, info)
+        hp.prove_phased(inst_cols, synth)
+        instances = [v for col in inst_cols for v in col]
+    else:
+        fixture = H.rand_vanilla_plonk_with_lookup_circuit if circuit == "lookup" else H.rand_vanilla_plonk_circuit
+        info, instances, w = fixture(k, 301)
+        hp = H.HyperPlonk(ctx, kzg, info)
+        hp.prove(instances, witness_ints=w)
+    proof = tr.into_proof()
+    hv = hp.verifier(vk)
+    inst = O.fr_from_ints(instances)
+    vt = V.ProofTranscript(proof)
+    assert hv.verify(vt, inst) and vt.done()
+    bad = bytearray(proof)
+    bad[len(bad) // 2] ^= 1
+    assert not hv.verify(V.ProofTranscript(bytes(bad)), inst)
+    wrong = inst.copy()
+    wrong[0] = O.rand_fr(5, 1)[0]
+    assert not hv.verify(V.ProofTranscript(proof), wrong)

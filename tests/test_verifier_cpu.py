@@ -265,3 +265,37 @@ def test_plain_c_host_program_verifies_a_proof_file(okzg, tmp_path):
     assert run("bad.bin", 0, 4, mu).returncode == 1
     assert run("proof.bin", 0, 4, mu + 1).returncode == 1
     assert run("proof.bin", 5, 4, mu).returncode == 2
+
+
+@pytest.mark.parametrize("circuit", ["vanilla", "lookup", "two_phase"])
+def test_verifier_parameters_derived_from_prover_parameters(okzg, vkzg, circuit):
+    """`HyperPlonk.verifier()` (the vp half of preprocess) without a GPU: the prover-parameter object is stubbed with
+    oracle commitments; the derived verifier accepts the oracle's proof of the same circuit."""
+    k = 4
+    if circuit == "two_phase":
+        info, inst_cols, synth = H.rand_two_phase_circuit(k, 300)
+        instances = [v for col in inst_cols for v in col]
+    else:
+        info, instances, w = (H.rand_vanilla_plonk_with_lookup_circuit if circuit == "lookup" else H.rand_vanilla_plonk_circuit)(k, 301)
+    phases = info.num_witness_polys if isinstance(info.num_witness_polys, list) else [info.num_witness_polys]
+    chals = list(getattr(info, "num_challenges", [0] * len(phases)))
+    nz, expr = compose(k, info.constraints, info.num_poly, info.permutation_polys, num_challenges=sum(chals), lookups=info.lookups)
+    ohp = O.HyperPlonk(okzg, k, expr, info.num_instances, info.num_witness_polys, [O.fr_from_ints(p) for p in info.preprocess_polys],
+                       info.permutation_polys, info.permutations, nz, lookups=info.lookups, num_challenges=chals)
+    inst = O.fr_from_ints(instances)
+    to = O.Transcript()
+    if circuit == "two_phase":
+        assert ohp.prove_phased(to, inst, lambda r, ch: [O.fr_from_ints(c) for c in synth(r, O.fr_to_ints(ch) if len(ch) else [])])
+    else:
+        assert ohp.prove(to, inst, [O.fr_from_ints(c) for c in w])
+    stub = H.HyperPlonk.__new__(H.HyperPlonk)  # no context, no device: only what verifier() reads
+    stub.info, stub.num_z = info, nz
+    stub.instance_cols = list(info.num_instances) if isinstance(info.num_instances, list) else [info.num_instances]
+    stub.phase_witness, stub.phase_challenges = phases, chals
+    pre = np.stack([okzg.commit(O.fr_from_ints(p)) for p in info.preprocess_polys])
+    sig = np.stack([okzg.commit(O.fr_from_ints(p)) for p in H.permutation_polys(k, info.permutation_polys, info.permutations)])
+    stub.commitments = lambda: (pre, sig)
+    hv = stub.verifier(vkzg)
+    vt = V.ProofTranscript(to.proof())
+    assert hv.verify(vt, inst) and vt.done()
+    assert not hv.verify(V.ProofTranscript(tampered(to.proof(), 100)), inst)
