@@ -299,3 +299,41 @@ def test_verifier_parameters_derived_from_prover_parameters(okzg, vkzg, circuit)
     vt = V.ProofTranscript(to.proof())
     assert hv.verify(vt, inst) and vt.done()
     assert not hv.verify(V.ProofTranscript(tampered(to.proof(), 100)), inst)
+
+
+def test_verifier_survives_garbage_and_truncated_proofs(okzg, vkzg):
+    """Untrusted input: truncations at every kind of boundary, random byte flips and plain garbage are rejected (never
+    accepted, never a crash) by the Lasso and HyperPlonk verifiers."""
+    import random
+
+    rng = random.Random(7)
+    mu = 4
+    xs = O.rand_u64s(3, 1 << mu)
+    xs[1::2] = xs[0::2]
+    to = O.Transcript()
+    assert O.lasso_prove(okzg, to, O.TABLE_RANGE, 2, mu, xs, None)
+    lasso = to.proof()
+    gold = json.load(open(os.path.join(HERE, "golden", "hyperplonk_golden.json")))["cases"][1]
+    info, instances, _ = H.rand_vanilla_plonk_with_lookup_circuit(gold["k"], gold["seed"], num_instances=2)
+    nz, expr = compose(gold["k"], info.constraints, info.num_poly, info.permutation_polys, lookups=info.lookups)
+    hv = _hyperplonk_verifier(okzg, vkzg, info, expr, nz)
+    inst = O.fr_from_ints(instances)
+    hp_proof = bytes.fromhex(gold["proof"])
+    checks = [(lasso, lambda p: vkzg.lasso_verify(V.ProofTranscript(p), O.TABLE_RANGE, 2, mu)),
+              (hp_proof, lambda p: hv.verify(V.ProofTranscript(p), inst))]
+    for proof, verify in checks:
+        assert verify(proof)
+        cuts = {0, 1, 31, 32, 63, 64, 65, len(proof) - 1, len(proof) - 32, len(proof) // 2} | {rng.randrange(len(proof)) for _ in range(25)}
+        for cut in cuts:
+            assert not verify(proof[:cut])
+        for _ in range(40):
+            bad = bytearray(proof)
+            for _ in range(rng.randrange(1, 4)):
+                bad[rng.randrange(len(bad))] ^= 1 << rng.randrange(8)
+            assert not verify(bytes(bad))
+        for n in (0, 7, 64, len(proof), 2 * len(proof)):
+            assert not verify(bytes(rng.randrange(256) for _ in range(n)))
+        # trailing bytes: the section verifies, the end-of-proof check fails
+        tr = V.ProofTranscript(proof + b"\\0" * 32)
+        ok = vkzg.lasso_verify(tr, O.TABLE_RANGE, 2, mu) if proof is lasso else hv.verify(tr, inst)
+        assert ok and not tr.done()
