@@ -210,6 +210,8 @@ int b200v_hyperplonk_new(const b200v_kzg* vp, int k, int ninstance_cols, const i
     if (!hp.expression || t != expression_tokens + ntokens) return B200V_ERR_ARG;
     const int npolys = ninstance_cols + npreprocess + nwit + npermutation + 2 * num_lookups + num_permutation_z_polys;
     if (!expr_ok(hp.expression, npolys, nchal + 3, k)) return B200V_ERR_ARG;
+    const int degree = expr_degree(hp.expression);
+    if (degree < 1 || degree > 32) return B200V_ERR_ARG;  // a zero check is eq * (...): at least degree 1
     hp.preprocess_comms.assign((const G1Affine*)preprocess_comms_g1, (const G1Affine*)preprocess_comms_g1 + npreprocess);
     hp.permutation_comms.assign((const G1Affine*)permutation_comms_g1, (const G1Affine*)permutation_comms_g1 + npermutation);
     for (auto* v : {&hp.preprocess_comms, &hp.permutation_comms})

@@ -229,7 +229,7 @@ def test_hyperplonk_verifier_rejects_malformed_parameters(okzg, vkzg):
     pre = [okzg.commit(O.fr_from_ints(p)) for p in info.preprocess_polys]
     sig = [okzg.commit(O.fr_from_ints(p)) for p in H.permutation_polys(3, info.permutation_polys, info.permutations)]
     V.HyperPlonkVerifier(vkzg, 3, info.num_instances, 3, None, 0, nz, expr, pre, sig)
-    for bad_expr in (expr * E.polynomial(40), expr + E.challenge(3), expr * E.eq_xy(1), E.polynomial(0, 9) * expr):
+    for bad_expr in (expr * E.polynomial(40), expr + E.challenge(3), expr * E.eq_xy(1), E.polynomial(0, 9) * expr, E.constant(5)):
         with pytest.raises(V.VerifierArgError):
             V.HyperPlonkVerifier(vkzg, 3, info.num_instances, 3, None, 0, nz, bad_expr, pre, sig)
     with pytest.raises(V.VerifierArgError):
