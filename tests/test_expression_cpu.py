@@ -248,3 +248,60 @@ def test_native_compose_equals_the_python_compose_token_for_token():
         with pytest.raises(hl.B200Error) as e:
             hl.compose_native(info.k, bad, info.num_poly, info.permutation_polys, 0, 4, info.lookups)
         assert e.value.code == hl.B200_ERR_ARG
+
+
+def test_token_parsers_survive_random_streams():
+    """Untrusted token streams through the host-only entry points (b200_expression_compile, b200_expression_compose,
+    b200v_hyperplonk_new): random and mutated streams either parse or are argument errors — never a crash."""
+    import ctypes as C
+
+    import halo2_lasso_b200 as hl
+    from halo2_lasso_b200 import verifier as V
+    from halo2_lasso_b200.expression import serialize_expression
+
+    rng = random.Random(11)
+    good, consts = serialize_expression(vanilla_plonk_expression(4), [], [])
+    cm = np.zeros((max(1, len(consts)), 4), dtype=np.uint64)
+    cap = 4096
+    leaves, cout, cchal, ops = (np.zeros((cap, 3), dtype=np.int32), np.zeros((cap, 4), dtype=np.uint64),
+                                np.zeros(cap, dtype=np.int32), np.zeros((cap, 4), dtype=np.int32))
+    ints = [C.c_int() for _ in range(5)]
+    vk = V.MultilinearKzgVerifier.setup(O.rand_fr(7, 4))
+    one, two = np.asarray([1], dtype=np.int32), np.asarray([3], dtype=np.int32)
+    outcomes = set()
+    for trial in range(1500):
+        if trial % 3 == 0:
+            toks = [rng.randrange(-2, 14) for _ in range(rng.randrange(1, 40))]
+        else:
+            toks = list(good)
+            for _ in range(rng.randrange(1, 4)):
+                toks[rng.randrange(len(toks))] = rng.randrange(-3, 40)
+            if rng.random() < 0.3:
+                toks = toks[: rng.randrange(1, len(toks))]
+        t = np.asarray(toks, dtype=np.int32)
+        rc = hl.lib().b200_expression_compile(hl._p(t), C.c_int(len(t)), hl._p(cm), C.c_int(len(consts)), hl._p(leaves), C.c_int(cap),
+                                              C.byref(ints[0]), hl._p(cout), hl._p(cchal), C.c_int(cap), C.byref(ints[1]), hl._p(ops),
+                                              C.c_int(cap), C.byref(ints[2]), C.byref(ints[3]), C.byref(ints[4]))
+        outcomes.add(rc)
+        assert rc in (hl.B200_OK, hl.B200_ERR_ARG, hl.B200_ERR_NOMEM)
+        tout, nt, nc, nz = np.zeros(1 << 14, dtype=np.int32), C.c_int(), C.c_int(), C.c_int()
+        rc = hl.lib().b200_expression_compose(C.c_int(4), C.c_int(9), C.c_int(0), C.c_int(1), hl._p(t), C.c_int(len(t)), C.c_int(0),
+                                              None, C.c_int(0), hl._p(cm), C.c_int(len(consts)), C.c_int(3),
+                                              hl._p(np.asarray([6, 7, 8], dtype=np.int32)), C.c_int(4), hl._p(tout), C.c_int(len(tout)),
+                                              C.byref(nt), hl._p(cout), C.c_int(cap), C.byref(nc), C.byref(nz))
+        assert rc in (hl.B200_OK, hl.B200_ERR_ARG, hl.B200_ERR_NOMEM)
+        h = C.c_void_p()
+        rc = V.lib().b200v_hyperplonk_new(vk.h, C.c_int(4), C.c_int(1), hl._p(one), C.c_int(1), hl._p(two), hl._p(np.zeros(1, dtype=np.int32)),
+                                          C.c_int(0), C.c_int(1), hl._p(t), C.c_int(len(t)), hl._p(cm), C.c_int(len(consts)), None,
+                                          C.c_int(0), None, C.c_int(0), C.byref(h))
+        assert rc in (V.ACCEPT, V.ERR_ARG)
+        if rc == V.ACCEPT:
+            V.lib().b200v_hyperplonk_free(h)
+    assert hl.B200_ERR_ARG in outcomes and hl.B200_OK in outcomes
+    # a pathologically deep expression is an argument error for the verifier (bounded recursion), not a stack overflow
+    deep = np.asarray([6] * 200000 + [4, 0, 0], dtype=np.int32)
+    h = C.c_void_p()
+    rc = V.lib().b200v_hyperplonk_new(vk.h, C.c_int(4), C.c_int(1), hl._p(one), C.c_int(1), hl._p(two), hl._p(np.zeros(1, dtype=np.int32)),
+                                      C.c_int(0), C.c_int(1), hl._p(deep), C.c_int(len(deep)), hl._p(cm), C.c_int(len(consts)), None,
+                                      C.c_int(0), None, C.c_int(0), C.byref(h))
+    assert rc == V.ERR_ARG
