@@ -143,7 +143,8 @@ inline KzgVerifierParam kzg_verifier_setup(const std::vector<Fr>& ss) {
   return vp;
 }
 
-// kzg.rs:330-361: e(C - g1 * eval, -g2) * Π_i e(Q_i, s_i g2 - x_i g2) == 1
+// kzg.rs:330-361: e(C - g1 * eval, -g2) * Π_i e(Q_i, s_i g2 - x_i g2) == 1, evaluated as
+// e(C - g1 * eval + Σ_i x_i Q_i, -g2) * Π_i e(Q_i, s_i g2) == 1
 inline bool kzg_verify(const KzgVerifierParam& vp, const G1Affine& comm, const std::vector<Fr>& point, const Fr& eval,
                        Transcript& tr) {
   const int n = (int)point.size();
@@ -151,11 +152,13 @@ inline bool kzg_verify(const KzgVerifierParam& vp, const G1Affine& comm, const s
   std::vector<G1Affine> qs(n);
   for (int i = 0; i < n; ++i)
     if (!tr.read_commitment(&qs[i])) return false;
-  const G1 lhs = G1::from_affine(comm).add(G1::from_affine(G1Affine::generator()).mul(eval).neg());
-  const G2Affine g2 = G2Affine::generator();
+  // e(Q_i, s_i g2 - x_i g2) = e(Q_i, s_i g2) * e(-x_i Q_i, g2): the x_i move to G1 (cheap scalar multiplications),
+  // the same n + 1 pairings remain and no G2 arithmetic is needed — the verdict is the reference's by bilinearity
+  G1 lhs = G1::from_affine(comm).add(G1::from_affine(G1Affine::generator()).mul(eval).neg());
+  for (int i = 0; i < n; ++i) lhs = lhs.add(G1::from_affine(qs[i]).mul(point[i]));
   std::vector<std::pair<G1Affine, G2Affine>> terms;
-  terms.push_back({lhs.to_affine(), g2.neg()});
-  for (int i = 0; i < n; ++i) terms.push_back({qs[i], vp.ss_g2[i].add(g2.mul(point[i]).neg())});
+  terms.push_back({lhs.to_affine(), G2Affine::generator().neg()});
+  for (int i = 0; i < n; ++i) terms.push_back({qs[i], vp.ss_g2[i]});
   return pairings_product_is_identity(terms);
 }
 

@@ -337,3 +337,12 @@ def test_verifier_survives_garbage_and_truncated_proofs(okzg, vkzg):
         tr = V.ProofTranscript(proof + b"\\0" * 32)
         ok = vkzg.lasso_verify(tr, O.TABLE_RANGE, 2, mu) if proof is lasso else hv.verify(tr, inst)
         assert ok and not tr.done()
+
+
+def test_pairing_selftest(tmp_path):
+    """tests/host_shim/pairing_selftest.cpp over verifier/pairing.hpp: split final exponentiation == plain power by
+    (p^12 - 1) / r, Fq12 inverse and p^2-Frobenius identities, bilinearity and non-degeneracy."""
+    exe = str(tmp_path / "pairing_selftest")
+    subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", os.path.join(HERE, "host_shim", "pairing_selftest.cpp"), "-o", exe])
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0 and "0 failure(s)" in out.stdout, out.stdout + out.stderr
