@@ -201,6 +201,7 @@ def main():
     xs_dev = xs_host.to(dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
     proof_len = [0]
+    last_proof = [b""]
 
     def lasso_device():
         hl.Keccak256Transcript(ctx)
@@ -209,7 +210,8 @@ def main():
     def lasso_e2e():
         tr = hl.Keccak256Transcript(ctx)
         prover.prove(xs_host.numpy().view(np.uint64))
-        proof_len[0] = len(tr.into_proof())
+        last_proof[0] = tr.into_proof()
+        proof_len[0] = len(last_proof[0])
 
     # cfg2 sum-check on resident tables
     n, N = SC_VARS, 1 << SC_VARS
@@ -346,6 +348,20 @@ def main():
     except Exception:
         pass
 
+    # the proof the end-to-end leg produced, checked by the product's own CPU verifier (libb200verify.so, pairing form);
+    # outside every timed region
+    verified = {"accepted": None, "cpu_verify_ms": None}
+    try:
+        from halo2_lasso_b200 import verifier as V
+
+        t0 = time.perf_counter()
+        vk = V.MultilinearKzgVerifier.setup(ss)
+        vt = V.ProofTranscript(last_proof[0])
+        verified["accepted"] = bool(vk.lasso_verify(vt, KIND_RANGE, CHUNKS, MU) and vt.done())
+        verified["cpu_verify_ms"] = round(1e3 * (time.perf_counter() - t0), 1)
+    except Exception as e:  # never lose the bench line over the extra check
+        verified["error"] = repr(e)[:200]
+
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         srs = [kzg.eqs(k) for k in range(MU + 1)]  # reuse the device SRS so the CPU leg skips its slow setup
@@ -382,7 +398,7 @@ def main():
                         "over NVLink peer memory, sum-checks replicated (strong scaling of the proof latency)",
             "ms_per_proof": ms_co, "phases_ms": phases_co,
             "ms_per_proof_with_sharded_sumchecks": ms_co_sc if ms_co_sc else None},
-        "roofline": roof, "cpu_baseline": cpu}))
+        "proof_verified": verified, "roofline": roof, "cpu_baseline": cpu}))
     if world > 1:
         dist.destroy_process_group()
 
