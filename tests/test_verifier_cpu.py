@@ -202,9 +202,12 @@ def test_hyperplonk_verify_accepts_the_committed_golden_proofs(okzg, vkzg):
         assert not hv.verify(V.ProofTranscript(proof), inst[:-1])
 
 
-def test_cfg1_hyperplonk_then_lasso_on_one_transcript(okzg, vkzg):
-    """BASELINE cfg1 shape at toy size: the HyperPlonk section followed by the Lasso section on one proof stream"""
-    k, mu, chunks = 4, 4, 4
+@pytest.mark.parametrize("k,mu", [(4, 4), (10, 10)])
+def test_cfg1_hyperplonk_then_lasso_on_one_transcript(okzg, vkzg, k, mu):
+    """BASELINE cfg1 (HyperPlonk + Lasso 64-bit range check, 2^10 lookups into 2^16 subtables, bn256 MultilinearKzg, CPU
+    plumbing) at toy size and at its stated size: the HyperPlonk section followed by the Lasso section on one proof
+    stream, proved by the oracle, verified by the product's verifier."""
+    chunks = 4
     info, instances, w = H.rand_vanilla_plonk_circuit(k, 77)
     nz, expr = compose(k, info.constraints, info.num_poly, info.permutation_polys)
     ohp = O.HyperPlonk(okzg, k, expr, len(instances), 3, [O.fr_from_ints(p) for p in info.preprocess_polys],
