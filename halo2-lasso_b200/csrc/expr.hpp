@@ -84,8 +84,10 @@ inline ExprP e_product(const std::vector<ExprP>& xs) {
 }
 
 // prefix tokens -> tree; returns null on a malformed stream
-inline ExprP e_parse(const int32_t*& t, const int32_t* end, const Fr* consts, int nconsts) {
-  if (t >= end) return nullptr;
+// Nesting deeper than E_MAX_DEPTH is rejected: every later pass (compile, degree, leaves, serialize) recurses as deep.
+static const int E_MAX_DEPTH = 2048;
+inline ExprP e_parse(const int32_t*& t, const int32_t* end, const Fr* consts, int nconsts, int depth = 0) {
+  if (t >= end || depth > E_MAX_DEPTH) return nullptr;
   const int k = *t++;
   auto need = [&](int n) { return end - t >= n; };
   switch (k) {
@@ -106,19 +108,19 @@ inline ExprP e_parse(const int32_t*& t, const int32_t* end, const Fr* consts, in
       return e_poly(a, b);
     }
     case Expr::NEG: {
-      ExprP x = e_parse(t, end, consts, nconsts);
+      ExprP x = e_parse(t, end, consts, nconsts, depth + 1);
       return x ? e_unary(Expr::NEG, x) : nullptr;
     }
     case Expr::SUM:
     case Expr::PROD: {
-      ExprP x = e_parse(t, end, consts, nconsts);
-      ExprP y = x ? e_parse(t, end, consts, nconsts) : nullptr;
+      ExprP x = e_parse(t, end, consts, nconsts, depth + 1);
+      ExprP y = x ? e_parse(t, end, consts, nconsts, depth + 1) : nullptr;
       return y ? e_binary((Expr::Kind)k, x, y) : nullptr;
     }
     case Expr::SCALED: {
       if (!need(1) || *t < 0 || *t >= nconsts) return nullptr;
       const Fr s = consts[*t++];
-      ExprP x = e_parse(t, end, consts, nconsts);
+      ExprP x = e_parse(t, end, consts, nconsts, depth + 1);
       if (!x) return nullptr;
       auto e = std::make_shared<Expr>();
       e->kind = Expr::SCALED;
@@ -131,7 +133,7 @@ inline ExprP e_parse(const int32_t*& t, const int32_t* end, const Fr* consts, in
       const int n = *t++;
       std::vector<ExprP> terms;
       for (int i = 0; i <= n; ++i) {
-        ExprP x = e_parse(t, end, consts, nconsts);
+        ExprP x = e_parse(t, end, consts, nconsts, depth + 1);
         if (!x) return nullptr;
         terms.push_back(x);
       }

@@ -298,7 +298,13 @@ def test_token_parsers_survive_random_streams():
         if rc == V.ACCEPT:
             V.lib().b200v_hyperplonk_free(h)
     assert hl.B200_ERR_ARG in outcomes and hl.B200_OK in outcomes
-    # a pathologically deep expression is an argument error for the verifier (bounded recursion), not a stack overflow
+    # a pathologically deep expression is an argument error (bounded recursion), not a stack overflow — in the prover
+    # library's parser as well as in the verifier's
+    deep = np.asarray([6] * 200000 + [4, 0, 0], dtype=np.int32)
+    rc = hl.lib().b200_expression_compile(hl._p(deep), C.c_int(len(deep)), hl._p(cm), C.c_int(len(consts)), hl._p(leaves), C.c_int(cap),
+                                          C.byref(ints[0]), hl._p(cout), hl._p(cchal), C.c_int(cap), C.byref(ints[1]), hl._p(ops),
+                                          C.c_int(cap), C.byref(ints[2]), C.byref(ints[3]), C.byref(ints[4]))
+    assert rc == hl.B200_ERR_ARG
     deep = np.asarray([6] * 200000 + [4, 0, 0], dtype=np.int32)
     h = C.c_void_p()
     rc = V.lib().b200v_hyperplonk_new(vk.h, C.c_int(4), C.c_int(1), hl._p(one), C.c_int(1), hl._p(two), hl._p(np.zeros(1, dtype=np.int32)),
