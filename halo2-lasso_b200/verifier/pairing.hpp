@@ -219,8 +219,13 @@ inline Fq12 pairing(const G1Affine& p, const G2Affine& q) { return final_exponen
 
 // pb/util/arithmetic.rs:25-32
 inline bool pairings_product_is_identity(const std::vector<std::pair<G1Affine, G2Affine>>& terms) {
+  // the Miller loops are independent: one per host thread when built with OpenMP, then ONE final exponentiation
+  std::vector<Fq12> ml(terms.size(), Fq12::one());
+  const long n = (long)terms.size();
+#pragma omp parallel for schedule(dynamic, 1) if (n > 1)
+  for (long i = 0; i < n; ++i) ml[i] = miller_loop(terms[i].first, terms[i].second);
   Fq12 f = Fq12::one();
-  for (auto& t : terms) f = f * miller_loop(t.first, t.second);
+  for (auto& m : ml) f = f * m;
   return final_exponentiation(f) == Fq12::one();
 }
 
