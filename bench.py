@@ -1,18 +1,23 @@
 #!/usr/bin/env python
 """bench.py — one JSON line per run (contract in the task statement).
 
-Headline workload (BASELINE.json configs[2], "cfg3", the configuration the metric "Lasso prove ms
-@2^20 lookups" is quoted on; it fits one GPU): 64-bit range check via Surge, c = 4 chunks of 16 bits,
-one 2^16 identity subtable, m = 2^20 synthetic lookups, bn256 MultilinearKzg; one step = one FULL
-Lasso proof (commitments, primary sum-check, memory-checking grand products, two batch openings).
-  value : prove time in ms with the operands already resident in HBM (lower is better)
-  e2e   : the same proof through b200_lasso_prove with HOST operands (pinned) + proof bytes read back
-The same run also measures BASELINE configs[1] ("cfg2": ClassicSumCheck eq*a*b, n = 20) because the
-metric's second half is "sumcheck GB/s vs HBM peak": reported under "sumcheck" and used for
-`roofline` (dominant sum-check launch, timed live with CUDA events on the library stream).
-N > 1: every rank proves an independent instance (weak scaling; no collective on the data path yet).
+Headline workload = BASELINE.json configs[3] ("cfg4"), the configuration the metric "Lasso prove ms @2^22 lookups at
+1/2/4/8 B200" is quoted on; it fits one GPU: bitwise AND via Surge, c = 8 chunks of (8|8)-bit operand bytes, one 2^16
+subtable, m = 2^22 synthetic lookups, bn256 MultilinearKzg. One step = ONE full Lasso proof (commitments, primary
+sum-check, memory-checking grand products, leaf evaluations, two batch openings).
+  --gpus N : the SAME single proof on N GPUs ("scaling": "strong"): witness tables, fingerprints, product trees, every
+             sum-check and the quotient commitments sharded on an index window, commitments point-sharded, round partials
+             and bound tables exchanged inside the kernels over NVLink peer memory (b200_dist_shard_lasso). The proof
+             bytes are identical at every N (`parity.sha256`); N > 1 also compares against an unsharded proof.
+  value    : prove time in ms with the operands already resident in HBM on every rank (lower is better)
+  e2e      : the same proof through b200_lasso_prove with HOST operands (pinned) + proof bytes read back
+The same run also measures, at N = 1: cfg3 (64-bit range, c = 4 x 16 bit, 2^20 lookups — the metric's "@2^20"), the
+range table at 2^22, BASELINE configs[1] ("cfg2": ClassicSumCheck eq*a*b, n = 20) because the metric's second half is
+"sumcheck GB/s vs HBM peak" (`sumcheck`, `roofline`: dominant sum-check launch timed live with CUDA events on the
+library stream), and the reference's zero_check bench shape. `roofline_msm` is the headline proof's dominant kernel.
 """
 import argparse
+import hashlib
 import json
 import os
 import subprocess
@@ -23,17 +28,18 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-MU = 20
-CHUNKS = 4
-KIND_RANGE = 0
+KIND_RANGE, KIND_AND = 0, 1
+MU = int(os.environ.get("B200_BENCH_MU", "22"))  # override only for the CPU contract test
+KIND, CHUNKS = KIND_AND, 8
+SHARD_K0 = 16
 SC_VARS = 20
 SC_TABLES = 3
 SC_ALGO_BYTES = 32 * SC_TABLES * (4 * (1 << SC_VARS) - 3)  # 402,652,896
-METRIC = "Lasso prove time @2^20 lookups (64-bit range via Surge, c=4x16-bit, bn256 MultilinearKzg)"
+METRIC = f"Lasso prove time @2^{MU} lookups, one proof on N B200 (AND via Surge, c=8x(8|8)-bit, bn256 MultilinearKzg)"
 UNIT = "ms"
-WORKLOAD = ("cfg3: 64-bit range check via Surge, C=4 x 16-bit subtables, 2^20 lookups, full Lasso proof; "
-            "plus cfg2 sum-check (deg-3 eq*a*b, n=20) for the roofline")
-SRS_SEED, X_SEED = 7, 5
+WORKLOAD = (f"cfg4: bitwise AND Surge decomposition, C=8 x (8|8)-bit subtable chunks, 2^{MU} lookups, ONE full Lasso proof "
+            "on all N GPUs (sharded sum-checks + MSM)")
+SRS_SEED, X_SEED, Y_SEED = 7, 5, 6
 
 
 # ---- synthetic inputs without the oracle: the documented splitmix64 stream (oracle/capi.cpp) -------
@@ -114,27 +120,40 @@ def mont_one():
     return np.array([0xAC96341C4FFFFFFB, 0x36FC76959F60CD29, 0x666EA36F7879462E, 0x0E0A77C19A07DF2F], dtype=np.uint64)
 
 
-def cpu_lasso(steps, warmup, srs=None):
-    """Restated reference algorithms (oracle/, C++ + OpenMP, all host threads): full 2^20 Lasso proof."""
+def operands(kind, chunks, mu):
+    import numpy as np
+
+    bits = (16 if kind == KIND_RANGE else 8) * chunks
+    mask = np.uint64((1 << bits) - 1) if bits < 64 else np.uint64(0xFFFFFFFFFFFFFFFF)
+    xs = rand_u64s(X_SEED, 1 << mu) & mask
+    ys = (rand_u64s(Y_SEED, 1 << mu) & mask) if kind != KIND_RANGE else None
+    return xs, ys
+
+
+def cpu_lasso(steps, warmup, srs=None, kind=KIND, chunks=CHUNKS, mu=MU):
+    """Restated reference algorithms (oracle/, C++ + OpenMP, all host threads): one full Lasso proof of the headline
+    instance (same seeds, same SRS). Returns (ms, threads, setup_s, proof bytes)."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import oracle as O
 
-    ss = O.rand_fr(SRS_SEED, MU)
+    # torchrun exports OMP_NUM_THREADS=1: the CPU arm uses every host core it can, explicitly
+    O.set_num_threads(max(1, len(os.sched_getaffinity(0))))
+    ss = O.rand_fr(SRS_SEED, max(mu, 16))
     t0 = time.perf_counter()
     kz = O.Kzg.from_eqs(ss, srs) if srs is not None else O.Kzg(ss)
     setup_s = time.perf_counter() - t0
-    xs = rand_u64s(X_SEED, 1 << MU)
-    times, plen = [], 0
+    xs, ys = operands(kind, chunks, mu)
+    times, proof = [], b""
     for it in range(warmup + steps):
         tr = O.Transcript()
         t0 = time.perf_counter()
-        ok = O.lasso_prove(kz, tr, KIND_RANGE, CHUNKS, MU, xs, None)
+        ok = O.lasso_prove(kz, tr, kind, chunks, mu, xs, ys)
         dt = time.perf_counter() - t0
         assert ok
-        plen = len(tr.proof())
+        proof = tr.proof()
         if it >= warmup:
             times.append(dt)
-    return 1e3 * sum(times) / len(times), O.num_threads(), setup_s, plen
+    return 1e3 * sum(times) / len(times), O.num_threads(), setup_s, proof
 
 
 def main():
@@ -144,6 +163,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-legs", action="store_true", help="headline only (skip the cfg3 / cfg2 / zero_check legs)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -152,16 +172,17 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        steps, warmup = max(1, min(args.steps, 2)), 0
-        ms, cores, setup_s, plen = cpu_lasso(steps, warmup)
+        steps, warmup = 1, 0  # one whole proof: tens of seconds on the host cores
+        ms, cores, setup_s, proof = cpu_lasso(steps, warmup)
         sample = f"whole 2^{MU}-lookup proof, {steps} timed repetition(s); SRS setup {setup_s:.1f} s untimed"
         print(json.dumps({
             "impl": "reference", "metric": METRIC, "value": ms, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
-            "warmup": warmup, "ms_per_step": ms, "higher_is_better": False, "scaling": "weak", "vs_baseline": None,
+            "warmup": warmup, "ms_per_step": ms, "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
             "dtype": "u256 (BN254 Fr/Fq, Montgomery)", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "impl_note": "restated reference algorithms (C++/OpenMP oracle: the Rust "
-                       "rayon prover cannot be built here, no cargo; Lasso itself is absent from the snapshot)",
-                       "proof_bytes": plen},
+            "config": {"workload": WORKLOAD},
+            "impl_note": "restated reference algorithms (C++/OpenMP oracle: the Rust rayon prover cannot be built here, "
+                         "no cargo; Lasso itself is absent from the snapshot)",
+            "parity": {"sha256": hashlib.sha256(proof).hexdigest(), "proof_bytes": len(proof)},
             "cpu_baseline": {"value": ms, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": ms, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
         return
@@ -183,6 +204,8 @@ def main():
     stream = torch.cuda.ExternalStream(ctx.stream, device=local_rank)
     dev = f"cuda:{local_rank}"
     m = 1 << MU
+    sharded = world > 1 and world & (world - 1) == 0 and world <= 8
+    assert world == 1 or sharded, "--gpus must be 1, 2, 4 or 8"
 
     def to_mont(raw):
         p = hl.MultilinearPolynomial.new(ctx, raw)
@@ -190,39 +213,32 @@ def main():
         return p
 
     # SRS: MultilinearKzg::setup on the device from seeded trapdoor scalars (one-off, untimed)
-    ss = to_mont(np.concatenate([rand_canonical(SRS_SEED, MU), np.zeros((32 - MU, 4), dtype=np.uint64)])).evals()[:MU]
+    nv = max(MU, 16)
+    ss = to_mont(np.concatenate([rand_canonical(SRS_SEED, nv), np.zeros((32 - nv, 4), dtype=np.uint64)])).evals()[:nv]
     t0 = time.perf_counter()
     kzg = hl.MultilinearKzg.setup(ctx, ss)
     ctx.sync()
     setup_ms = 1e3 * (time.perf_counter() - t0)
-    prover = hl.LassoProver(ctx, kzg, KIND_RANGE, CHUNKS)
+    prover = hl.LassoProver(ctx, kzg, KIND, CHUNKS)
+    if sharded:
+        hl.dist_init(ctx, rank, world)
+        hl.dist_shard_lasso(ctx, SHARD_K0)
 
-    xs_host = torch.from_numpy(rand_u64s(X_SEED + 100 * rank, m).view(np.int64)).pin_memory()
-    xs_dev = xs_host.to(dev)
+    xs_np, ys_np = operands(KIND, CHUNKS, MU)  # the same lookups on every rank: ONE proof
+    xs_host = torch.from_numpy(xs_np.view(np.int64)).pin_memory()
+    ys_host = torch.from_numpy(ys_np.view(np.int64)).pin_memory()
+    xs_dev, ys_dev = xs_host.to(dev), ys_host.to(dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
-    proof_len = [0]
     last_proof = [b""]
 
     def lasso_device():
         hl.Keccak256Transcript(ctx)
-        prover.prove_dev(MU, xs_dev.data_ptr())
+        prover.prove_dev(MU, xs_dev.data_ptr(), ys_dev.data_ptr())
 
     def lasso_e2e():
         tr = hl.Keccak256Transcript(ctx)
-        prover.prove(xs_host.numpy().view(np.uint64))
+        prover.prove(xs_host.numpy().view(np.uint64), ys_host.numpy().view(np.uint64))
         last_proof[0] = tr.into_proof()
-        proof_len[0] = len(last_proof[0])
-
-    # cfg2 sum-check on resident tables
-    n, N = SC_VARS, 1 << SC_VARS
-    polys = [to_mont(rand_canonical(seed + 10 * rank, N)) for seed in (1, 2)]
-    y = to_mont(np.concatenate([rand_canonical(3 + 10 * rank, n), np.zeros((32 - n, 4), dtype=np.uint64)])).evals()[:n]
-    one = mont_one()
-
-    def sumcheck_device():
-        hl.Keccak256Transcript(ctx)
-        # any claim yields a well-formed transcript (p(0) is derived, eval.rs:129); timing is claim-independent
-        hl.ClassicSumCheck.prove_evals(ctx, n, polys, one.reshape(1, 4), y, one)
 
     def timed(fn, steps, warmup):
         for _ in range(warmup):
@@ -244,78 +260,113 @@ def main():
             dist.barrier()
         return sum(a.elapsed_time(b) for a, b in ev) / steps
 
-    # N > 1: the SAME cfg2 sum-check sharded over the top log2(N) variables (2^20 entries per rank, i.e.
-    # n = 20 + log2 N in total), partial sums exchanged inside the round kernels over NVLink peer memory
-    sharded = None
-    if world > 1 and world & (world - 1) == 0:
-        hl.dist_init(ctx, rank, world)
-        n_tot = SC_VARS + world.bit_length() - 1
-        y_tot = to_mont(np.concatenate([rand_canonical(3, n_tot), np.zeros((32 - n_tot, 4), dtype=np.uint64)])).evals()[:n_tot]
-
-        def sumcheck_sharded():
-            hl.Keccak256Transcript(ctx)
-            hl.sumcheck_prove_evals_sharded(ctx, n_tot, polys, one.reshape(1, 4), y_tot, one)
-
-        sharded = (n_tot, sumcheck_sharded)
-        # ONE proof on all N GPUs: every rank runs the same prover on the same lookups, the commitment MSMs (the
-        # largest single cost) are split by point range and the partial commitments summed over NVLink
-        xs_shared = torch.from_numpy(rand_u64s(X_SEED, m).view(np.int64)).to(dev)
-
-        def lasso_cooperative():
-            hl.Keccak256Transcript(ctx)
-            prover.prove_dev(MU, xs_shared.data_ptr())
-
-    # the reference's own `zero_check` criterion bench shape (plonkish_backend/benches/zero_check.rs): generic
-    # EvaluationsProver on vanilla_plonk_expression, n = 20, expression compiled inside the library
-    from halo2_lasso_b200.expression import vanilla_plonk_expression
-
-    zc_expr = vanilla_plonk_expression(SC_VARS)
-    zc_polys = [to_mont(rand_canonical(100 + i + 20 * rank, N)) for i in range(13)]
-    zc_ch = [int(x) for x in rand_canonical(7, 3)[:, 0]]
-    zc_zero = np.zeros(4, dtype=np.uint64)
-
-    def zero_check_device():
-        hl.Keccak256Transcript(ctx)
-        hl.prove_expression_native(ctx, n, zc_expr, zc_polys, zc_ch, [y], zc_zero)
+    def phases_of(fn):
+        out = {}
+        for tag, t in hl.profile(ctx, fn):
+            if tag >= 1000:
+                nm = hl.PHASE_NAMES.get(tag, str(tag))
+                out[nm] = round(out.get(nm, 0.0) + t, 4)
+        return out
 
     sampler = ClockSampler(local_rank)
     sampler.start()
+    warm = max(3, args.warmup)
     ctx.launch_count(reset=True)
-    ms = timed(lasso_device, args.steps, max(3, args.warmup))
-    launches = ctx.launch_count(reset=True) // (args.steps + max(3, args.warmup))
+    ms = timed(lasso_device, args.steps, warm)
+    launches = ctx.launch_count(reset=True) // (args.steps + warm)
     ms_e2e = timed(lasso_e2e, max(3, args.steps // 2), 3)
-    ms_sc = timed(sumcheck_device, 20, 5)
-    ms_sh = timed(sharded[1], 20, 5) if sharded else 0.0
-    ms_zc = timed(zero_check_device, 5, 3)
-    ms_co = ms_co_sc = 0.0
-    if sharded:
-        hl.dist_shard_commits(ctx, True)
-        ms_co = timed(lasso_cooperative, args.steps, 3)
-        phases_co = {}
-        for tag, t in hl.profile(ctx, lasso_cooperative):
-            if tag >= 1000:
-                nm = hl.PHASE_NAMES.get(tag, str(tag))
-                phases_co[nm] = round(phases_co.get(nm, 0.0) + t, 4)
-        # opt-in (B200_BENCH_SHARD_SUMCHECKS=<min_vars>): additionally evaluate the prover's large sum-checks on each
-        # rank's 1/N slice of the hypercube (b200_dist_shard_sumchecks; unverified on hardware in round 1)
-        if os.environ.get("B200_BENCH_SHARD_SUMCHECKS"):
-            hl.dist_shard_sumchecks(ctx, int(os.environ["B200_BENCH_SHARD_SUMCHECKS"]))
-            ms_co_sc = timed(lasso_cooperative, args.steps, 3)
-            hl.dist_shard_sumchecks(ctx, 0)
-        hl.dist_shard_commits(ctx, False)
     clocks = sampler.stop()
+    phases = phases_of(lasso_device)
+    if sharded:
+        hl.dist_check(ctx)
 
-    prof = hl.profile_rounds(ctx, sumcheck_device, SC_VARS, SC_TABLES)
-    phases = {}
-    for tag, t in hl.profile(ctx, lasso_device):
-        if tag >= 1000:
-            nm = hl.PHASE_NAMES.get(tag, str(tag))
-            phases[nm] = round(phases.get(nm, 0.0) + t, 4)
+    # ---- secondary legs --------------------------------------------------------------------------------------
+    legs = {}
+    ms_sc = ms_sh = ms_zc = 0.0
+    prof = None
+    n, N = SC_VARS, 1 << SC_VARS
+    one = mont_one()
+    if not args.no_legs:
+        polys = [to_mont(rand_canonical(seed + 10 * rank, N)) for seed in (1, 2)]
+        y = to_mont(np.concatenate([rand_canonical(3 + 10 * rank, n), np.zeros((32 - n, 4), dtype=np.uint64)])).evals()[:n]
+
+        def sumcheck_device():
+            hl.Keccak256Transcript(ctx)
+            # any claim yields a well-formed transcript (p(0) is derived, eval.rs:129); timing is claim-independent
+            hl.ClassicSumCheck.prove_evals(ctx, n, polys, one.reshape(1, 4), y, one)
+
+        if world == 1:
+            ms_sc = timed(sumcheck_device, 20, 5)
+            prof = hl.profile_rounds(ctx, sumcheck_device, SC_VARS, SC_TABLES)
+            # the reference's own `zero_check` criterion bench shape (plonkish_backend/benches/zero_check.rs): generic
+            # EvaluationsProver on vanilla_plonk_expression, n = 20, expression compiled inside the library
+            from halo2_lasso_b200.expression import vanilla_plonk_expression
+
+            zc_expr = vanilla_plonk_expression(SC_VARS)
+            zc_polys = [to_mont(rand_canonical(100 + i, N)) for i in range(13)]
+            zc_ch = [int(x) for x in rand_canonical(7, 3)[:, 0]]
+            zc_zero = np.zeros(4, dtype=np.uint64)
+
+            def zero_check_device():
+                hl.Keccak256Transcript(ctx)
+                hl.prove_expression_native(ctx, n, zc_expr, zc_polys, zc_ch, [y], zc_zero)
+
+            ms_zc = timed(zero_check_device, 5, 3)
+            del zc_polys
+            # the other Lasso shapes of the metric, one GPU: cfg3 (2^20 range — "@2^20") and the range table at 2^22
+            for name, kind, chunks, mu in (("cfg3_range_c4_2e20", KIND_RANGE, 4, 20), ("range_c4_2e22", KIND_RANGE, 4, 22)):
+                if mu > MU:
+                    continue
+                lx, _ = operands(kind, chunks, mu)
+                lx_host = torch.from_numpy(lx.view(np.int64)).pin_memory()
+                lx_dev = lx_host.to(dev)
+                lp = hl.LassoProver(ctx, kzg, kind, chunks)
+                plen = [0]
+
+                def leg_device():
+                    hl.Keccak256Transcript(ctx)
+                    lp.prove_dev(mu, lx_dev.data_ptr())
+
+                def leg_e2e():
+                    tr = hl.Keccak256Transcript(ctx)
+                    lp.prove(lx_host.numpy().view(np.uint64))
+                    plen[0] = len(tr.into_proof())
+
+                legs[name] = {"ms_device": round(timed(leg_device, 10, 3), 4), "ms_e2e": round(timed(leg_e2e, 5, 2), 4),
+                              "phases_ms": phases_of(leg_device), "lookups": 1 << mu, "proof_bytes": plen[0]}
+        else:
+            # the SAME cfg2 sum-check sharded over the top log2(N) variables (2^20 entries per rank, n = 20 + log2 N in
+            # total), partial sums exchanged inside the round kernels over NVLink peer memory
+            n_tot = SC_VARS + world.bit_length() - 1
+            y_tot = to_mont(np.concatenate([rand_canonical(3, n_tot), np.zeros((32 - n_tot, 4), dtype=np.uint64)])).evals()[:n_tot]
+
+            def sumcheck_sharded():
+                hl.Keccak256Transcript(ctx)
+                hl.sumcheck_prove_evals_sharded(ctx, n_tot, polys, one.reshape(1, 4), y_tot, one)
+
+            ms_sh = timed(sumcheck_sharded, 20, 5)
+            hl.dist_check(ctx)
+
+    # N > 1: the sharded proof against an UNSHARDED proof of the same instance (rank 0 alone, untimed)
+    unsharded_sha = None
+    if sharded:
+        dist.barrier()
+        if rank == 0:
+            hl.dist_shard_lasso(ctx, 0)
+            tr = hl.Keccak256Transcript(ctx)
+            prover.prove_dev(MU, xs_dev.data_ptr(), ys_dev.data_ptr())
+            unsharded_sha = hashlib.sha256(tr.into_proof()).hexdigest()
+            hl.dist_shard_lasso(ctx, SHARD_K0)
+        dist.barrier()
 
     if world > 1:
-        t = torch.tensor([ms, ms_e2e, ms_sc, ms_sh, ms_co, ms_co_sc], device=dev)
+        t = torch.tensor([ms, ms_e2e, ms_sh], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, ms_e2e, ms_sc, ms_sh, ms_co, ms_co_sc = t.tolist()
+        ms, ms_e2e, ms_sh = t.tolist()
+        shas = [None] * world
+        dist.all_gather_object(shas, hashlib.sha256(last_proof[0]).hexdigest())
+    else:
+        shas = [hashlib.sha256(last_proof[0]).hexdigest()]
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -328,25 +379,39 @@ def main():
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
+    imad_peak = 148 * 4 * 32 * 1.965 / 537.8  # G Montgomery products / s (tools/micro/pipe_rates.cu, builder-measured)
     roof = {"bound": "hbm", "achieved": None, "peak": peak, "unit": "GB/s", "frac": None, "traffic": None,
             "peak_source": peak_src}
     if prof:
         roof.update(prof)
         roof["frac"] = roof["achieved"] / peak
+        roof["round_ms_note"] = "per-launch times with the single-launch tail kernel disabled (profiling mode)"
         # the same launch against the bound that actually limits it: Montgomery products on the IMAD (fmaheavy) pipe.
         # Round 1 of cfg2 = 2^(n-2) output pairs x (6 binding + 6 evaluation products). Peak: the multiplier itself
         # measured alone on a B200 (tools/micro/pipe_rates.cu, profiles/r01_pipe_rates.txt): 537.8 cycles per warp
         # product per SM sub-partition with 4 resident warps each -> 148 SMs x 4 x 32 lanes x 1.965 GHz / 537.8.
         prods = 12 * (1 << (SC_VARS - 2))
-        imad_peak = 148 * 4 * 32 * 1.965 / 537.8
         roof["imad"] = {"products_per_launch": prods, "achieved_gproducts_s": prods / (roof["launch_ms"] * 1e-3) / 1e9,
                         "peak_gproducts_s": round(imad_peak, 1), "frac": prods / (roof["launch_ms"] * 1e-3) / 1e9 / imad_peak,
-                        "note": "IMAD-bound kernel; launch time includes the ~29 us single-warp Fiat-Shamir tail"}
+                        "note": "IMAD-bound kernel; launch time includes the single-warp Fiat-Shamir tail"}
     # per-launch DRAM traffic of that kernel from the committed `ncu --set full` capture (profiles/), if present
     try:
         roof["traffic"] = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))["dram_bytes_per_launch"]
     except Exception:
         pass
+    # the headline proof's dominant kernel, msm_accumulate_kernel (XYZZ mixed additions, 10 Montgomery products each):
+    # additions = non-zero signed digits of the three MSM batches, counted from the plan: commit (dim: 1 window, E: 1,
+    # read_ts: 1 populated window, each c x m; final_cts c x 2^16) + the two batch openings (16 windows x 2^mu, 16 x 2^16)
+    adds = (3 * CHUNKS * m + CHUNKS * (1 << 16) + 16 * (m - 1) + 16 * ((1 << 16) - 1)) / world
+    acc_ms = phases.get("msm_accumulate")
+    roof_msm = None
+    if acc_ms:
+        roof_msm = {"kernel": "msm_accumulate_kernel (3 launches per proof)", "bound": "imad (fmaheavy pipe)",
+                    "mixed_adds_per_rank": int(adds), "ms_per_proof": acc_ms,
+                    "achieved_gproducts_s": 10 * adds / (acc_ms * 1e-3) / 1e9, "peak_gproducts_s": round(imad_peak, 1),
+                    "frac": 10 * adds / (acc_ms * 1e-3) / 1e9 / imad_peak,
+                    "algorithmic_GBps": 68 * adds / (acc_ms * 1e-3) / 1e9,
+                    "note": "upper bound on the additions (zero digits are skipped); 68 B = one affine point + its index"}
 
     # the proof the end-to-end leg produced, checked by the product's own CPU verifier (libb200verify.so, pairing form);
     # outside every timed region
@@ -357,48 +422,52 @@ def main():
         t0 = time.perf_counter()
         vk = V.MultilinearKzgVerifier.setup(ss)
         vt = V.ProofTranscript(last_proof[0])
-        verified["accepted"] = bool(vk.lasso_verify(vt, KIND_RANGE, CHUNKS, MU) and vt.done())
+        verified["accepted"] = bool(vk.lasso_verify(vt, KIND, CHUNKS, MU) and vt.done())
         verified["cpu_verify_ms"] = round(1e3 * (time.perf_counter() - t0), 1)
     except Exception as e:  # never lose the bench line over the extra check
         verified["error"] = repr(e)[:200]
 
+    parity = {"sha256": shas[0], "proof_bytes": len(last_proof[0]), "all_ranks_equal": len(set(shas)) == 1,
+              "equal_to_unsharded_gpu_proof": None if unsharded_sha is None else unsharded_sha == shas[0],
+              "bytes_equal": None, "oracle_sha256": None}
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        srs = [kzg.eqs(k) for k in range(MU + 1)]  # reuse the device SRS so the CPU leg skips its slow setup
-        cms, cores, _, plen = cpu_lasso(1, 0, srs)
+        srs = [kzg.eqs(k) for k in range(nv + 1)]  # reuse the device SRS so the CPU leg skips its slow setup
+        cms, cores, _, oproof = cpu_lasso(1, 0, srs)
         cpu = {"value": cms, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": f"whole 2^{MU}-lookup proof once (C++/OpenMP restatement of the reference algorithms)",
-               "proof_bytes": plen}
+               "sample": f"whole 2^{MU}-lookup proof once (C++/OpenMP restatement of the reference algorithms), same "
+                         "instance and SRS as the GPU arm; its bytes are the parity check"}
+        parity["bytes_equal"] = oproof == last_proof[0]
+        parity["oracle_sha256"] = hashlib.sha256(oproof).hexdigest()
 
     print(json.dumps({
-        "metric": METRIC, "value": ms, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
-        "ms_per_step": ms, "higher_is_better": False, "scaling": "weak", "vs_baseline": None,
+        "metric": METRIC, "value": ms, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warm,
+        "ms_per_step": ms, "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
         "dtype": "u256 (BN254 Fr/Fq, 8x32-bit Montgomery limbs)", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "lookups": m, "chunks": CHUNKS, "subtable": 1 << 16, "proof_bytes": proof_len[0],
-                   "l2": "flushed between timed iterations (256 MiB write)", "replicas_per_gpu": 1,
-                   "srs_setup_ms_untimed": round(setup_ms, 1)},
-        "lookups_per_s": world * m / (ms * 1e-3),
+        "config": {"workload": WORKLOAD}, 
+        "detail": {"lookups": m, "chunks": CHUNKS, "subtable": 1 << 16, "l2": "flushed between timed iterations (256 MiB write)",
+                   "srs_setup_ms_untimed": round(setup_ms, 1),
+                   "sharding": None if not sharded else f"index window [{SHARD_K0 - (world.bit_length() - 1)}, {SHARD_K0}) -> rank; "
+                   "in-kernel NVLink exchange of round partials, bulk all-gather of bound tables, point-sharded MSM"},
+        "lookups_per_s": m / (ms * 1e-3),
         "clocks": clocks,
-        "e2e": {"value": ms_e2e, "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": m * 8,
-                "d2h_bytes_per_step": proof_len[0]},
-        "gpu_launches": launches, "phases_ms": phases,
-        "sumcheck": {"workload": "cfg2: ClassicSumCheck deg-3 eq*a*b, n=20, 2560 proof bytes", "ms_per_proof": ms_sc,
-                     "algorithmic_bytes": SC_ALGO_BYTES, "GBps": world * SC_ALGO_BYTES / (ms_sc * 1e-3) / 1e9,
-                     "frac_of_hbm_peak": SC_ALGO_BYTES / (ms_sc * 1e-3) / 1e9 / peak},
-        "zero_check": {"workload": "reference zero_check bench shape: vanilla_plonk_expression (17 tables, degree 5), n=20, "
-                       "generic bytecode kernels, through b200_sumcheck_prove_expression (host call, includes its "
-                       "small H2D/D2H)", "ms_per_proof": ms_zc},
-        "sumcheck_sharded": None if not sharded else {
-            "workload": f"cfg2 shape sharded on the top {world.bit_length() - 1} variable(s): n={sharded[0]}, 2^20 entries per GPU, "
-                        "per-round partials exchanged inside the kernel over NVLink peer memory",
-            "ms_per_proof": ms_sh, "algorithmic_bytes": 32 * SC_TABLES * (4 * (1 << sharded[0]) - 3),
-            "GBps": 32 * SC_TABLES * (4 * (1 << sharded[0]) - 3) / (ms_sh * 1e-3) / 1e9},
-        "lasso_commit_sharded": None if not sharded else {
-            "workload": f"ONE {WORKLOAD} proof on {world} GPUs: commitment MSMs point-sharded, partial commitments summed "
-                        "over NVLink peer memory, sum-checks replicated (strong scaling of the proof latency)",
-            "ms_per_proof": ms_co, "phases_ms": phases_co,
-            "ms_per_proof_with_sharded_sumchecks": ms_co_sc if ms_co_sc else None},
-        "proof_verified": verified, "roofline": roof, "cpu_baseline": cpu}))
+        "e2e": {"value": ms_e2e, "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": world * 2 * m * 8,
+                "d2h_bytes_per_step": world * len(last_proof[0])},
+        "gpu_launches": launches, "phases_ms": phases, "parity": parity, "legs": legs or None,
+        "sumcheck": None if not ms_sc else {
+            "workload": "cfg2: ClassicSumCheck deg-3 eq*a*b, n=20, 2560 proof bytes", "ms_per_proof": ms_sc,
+            "algorithmic_bytes": SC_ALGO_BYTES, "GBps": SC_ALGO_BYTES / (ms_sc * 1e-3) / 1e9,
+            "frac_of_hbm_peak": SC_ALGO_BYTES / (ms_sc * 1e-3) / 1e9 / peak},
+        "zero_check": None if not ms_zc else {
+            "workload": "reference zero_check bench shape: vanilla_plonk_expression (17 tables, degree 5), n=20, generic "
+                        "bytecode kernels, through b200_sumcheck_prove_expression (host call, includes its small H2D/D2H)",
+            "ms_per_proof": ms_zc},
+        "sumcheck_sharded": None if not ms_sh else {
+            "workload": f"cfg2 shape sharded on the top {world.bit_length() - 1} variable(s): n={SC_VARS + world.bit_length() - 1}, "
+                        "2^20 entries per GPU, per-round partials exchanged inside the kernel over NVLink peer memory",
+            "ms_per_proof": ms_sh,
+            "GBps": 32 * SC_TABLES * (4 * (1 << (SC_VARS + world.bit_length() - 1)) - 3) / (ms_sh * 1e-3) / 1e9},
+        "proof_verified": verified, "roofline": roof, "roofline_msm": roof_msm, "cpu_baseline": cpu}))
     if world > 1:
         dist.destroy_process_group()
 

@@ -21,14 +21,14 @@ _DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_DIR, "libb200lasso.so")
 HEADER_PATH = os.path.join(os.path.dirname(_DIR), "include", "b200_lasso.h")
 
-B200_OK, B200_ERR_CUDA, B200_ERR_ARG, B200_ERR_TRANSCRIPT, B200_ERR_NOMEM, B200_ERR_LOOKUP = range(6)
+B200_OK, B200_ERR_CUDA, B200_ERR_ARG, B200_ERR_TRANSCRIPT, B200_ERR_NOMEM, B200_ERR_LOOKUP, B200_ERR_PEER = range(7)
 
 
 class B200Error(RuntimeError):
     """Maps the C status codes onto the reference's `Error` variants (pb/lib.rs:12-20)."""
 
     NAMES = {1: "Cuda", 2: "InvalidPcsParam/InvalidSumcheck (bad argument)", 3: "Transcript", 4: "OutOfMemory",
-             5: "InvalidSnark (Invalid lookup input)"}
+             5: "InvalidSnark (Invalid lookup input)", 6: "peer wait timed out (a rank left the collective)"}
 
     def __init__(self, code, where):
         super().__init__(f"{where}: {self.NAMES.get(code, code)}")
@@ -414,19 +414,65 @@ class LassoProver:
 
 # ---- multi-GPU (one process per GPU) ---------------------------------------------------------
 def dist_init(ctx, rank=None, world=None):
-    """Map every rank's mailbox over CUDA IPC / NVLink. Needs an initialised torch.distributed group
-    (any backend: only 64-byte handles are exchanged)."""
+    """Map every rank's mailbox and bulk arena over CUDA IPC / NVLink. Needs an initialised torch.distributed group
+    (any backend: only 128-byte handles are exchanged)."""
     import torch.distributed as dist
 
     rank = dist.get_rank() if rank is None else rank
     world = dist.get_world_size() if world is None else world
-    mine = (C.c_uint8 * 64)()
+    mine = (C.c_uint8 * 128)()
     _chk(lib().b200_dist_mailbox_handle(ctx.h, mine), "dist_mailbox_handle")
     handles = exchange_handles(bytes(mine), world)
     blob = b"".join(handles)
     _chk(lib().b200_dist_init(ctx.h, C.c_int(rank), C.c_int(world), blob), "dist_init")
     dist.barrier()
     return rank, world
+
+
+def dist_init_local(ctxs):
+    """The ranks of a group as several contexts of THIS process (same GPU or peer-accessible GPUs); every context must
+    then be driven from its own host thread (`run_ranks`). This is how the sharded provers are tested on one GPU."""
+    arr = (C.c_void_p * len(ctxs))(*[c.h for c in ctxs])
+    _chk(lib().b200_dist_init_local(arr, C.c_int(len(ctxs))), "dist_init_local")
+
+
+def run_ranks(ctxs, fn):
+    """fn(rank, ctx) on one host thread per context (collective calls wait for each other on the device); returns the
+    results in rank order and re-raises the first exception."""
+    import threading
+
+    out, err = [None] * len(ctxs), [None] * len(ctxs)
+
+    def work(r):
+        try:
+            out[r] = fn(r, ctxs[r])
+        except BaseException as e:  # noqa: BLE001 - re-raised below
+            err[r] = e
+
+    th = [threading.Thread(target=work, args=(r,)) for r in range(len(ctxs))]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    for e in err:
+        if e is not None:
+            raise e
+    return out
+
+
+def dist_check(ctx):
+    """Raises B200Error(6) if an in-kernel wait for a peer timed out since the last check."""
+    _chk(lib().b200_dist_check(ctx.h), "dist_check")
+
+
+def dist_shard_lasso(ctx, k0=16):
+    """Fully sharded Lasso prover: witness tables, fingerprints, product-tree layers >= k0 and all sum-checks / openings
+    over them on the rank's 1/world slice (index window [k0 - log2 world, k0)); 0 switches it off."""
+    _chk(lib().b200_dist_shard_lasso(ctx.h, C.c_int(int(k0))), "dist_shard_lasso")
+
+
+def dist_shard_min_items(ctx, items):
+    _chk(lib().b200_dist_shard_min_items(ctx.h, C.c_int(int(items))), "dist_shard_min_items")
 
 
 def dist_shard_commits(ctx, on=True):
@@ -460,13 +506,24 @@ def shard_slice(n_total_vars: int, rank: int, world: int):
     return rank * size, (rank + 1) * size
 
 
-def sumcheck_prove_evals_sharded(ctx, num_vars_total, local_polys, weights, y, claimed_sum, np_per_term=2):
+def shard_window_slice(evals, n_total_vars: int, window_pos: int, rank: int, world: int):
+    """The rank's compact slice of a table sharded on the index bits [window_pos, window_pos + log2 world)."""
+    g = world.bit_length() - 1
+    assert 1 << g == world and 0 <= window_pos <= n_total_vars - g
+    a = np.asarray(evals)
+    return np.ascontiguousarray(a.reshape((1 << (n_total_vars - g - window_pos), world, 1 << window_pos) + a.shape[1:])[:, rank]
+                                .reshape((1 << (n_total_vars - g),) + a.shape[1:]))
+
+
+def sumcheck_prove_evals_sharded(ctx, num_vars_total, local_polys, weights, y, claimed_sum, np_per_term=2, window_pos=-1,
+                                 sharded_rounds=-1):
     nterms = len(local_polys) // np_per_term
     ptrs = (C.c_void_p * len(local_polys))(*[p.dev for p in local_polys])
     ch = np.zeros((num_vars_total, 4), dtype=np.uint64)
     ev = np.zeros((len(local_polys), 4), dtype=np.uint64)
-    _chk(lib().b200_sumcheck_prove_evals_sharded(ctx.h, C.c_int(num_vars_total), C.c_int(nterms), C.c_int(np_per_term),
-                                                 ptrs, _p(_fr(weights)), _p(_fr(y)), _p(_fr(claimed_sum)), _p(ch), _p(ev)),
+    _chk(lib().b200_sumcheck_prove_evals_windowed(ctx.h, C.c_int(num_vars_total), C.c_int(window_pos), C.c_int(sharded_rounds),
+                                                  C.c_int(nterms), C.c_int(np_per_term), ptrs, _p(_fr(weights)), _p(_fr(y)),
+                                                  _p(_fr(claimed_sum)), _p(ch), _p(ev)),
          "sumcheck_prove_evals_sharded")
     return ch, ev
 

@@ -63,6 +63,7 @@ int b200_ctx_create(int device, b200_ctx** out) {
   c->device = device;
   c->launches = 0;
   c->profile = false;
+  memset(&c->peer, 0, sizeof(c->peer));
   c->peer.rank = 0;
   c->peer.world = 1;
   c->my_mailbox = nullptr;
@@ -103,8 +104,13 @@ void b200_ctx_destroy(b200_ctx* h) {
   for (auto p : c->srs) cudaFree(p);
   for (auto p : c->srs_ext) cudaFree(p);
   for (int r = 0; r < c->peer.world; ++r)
-    if (c->my_mailbox && r != c->peer.rank) cudaIpcCloseMemHandle(c->peer.box[r]);
+    if (c->peer_ipc && r != c->peer.rank) {
+      cudaIpcCloseMemHandle(c->peer.box[r]);
+      cudaIpcCloseMemHandle(c->peer.arena[r]);
+    }
   if (c->my_mailbox) cudaFree(c->my_mailbox);
+  if (c->my_arena) cudaFree(c->my_arena);
+  if (c->d_peer_err) cudaFree(c->d_peer_err);
   cudaFree(c->d_tr);
   cudaFree(c->d_proof);
   cudaFree(c->d_bary);

@@ -1,4 +1,5 @@
 // extern "C" boundary, part 3: multi-GPU (one process per GPU; peer mailboxes over CUDA IPC / NVLink).
+#include <stdlib.h>
 #include <string.h>
 
 #include <vector>
@@ -10,36 +11,130 @@ using namespace b200;
 
 extern "C" {
 
-int b200_dist_mailbox_handle(b200_ctx* h, void* out_handle64) {
-  Ctx* c = &h->c;
-  if (!c->my_mailbox) {
-    CUDA_TRY(cudaMalloc(&c->my_mailbox, sizeof(Mailbox)));
-    CUDA_TRY(cudaMemset(c->my_mailbox, 0, sizeof(Mailbox)));
+static const size_t ARENA_HALF_DEFAULT = (size_t)96 << 20;  // per parity; B200_ARENA_MB overrides (both halves)
+
+static int dist_alloc_local(Ctx* c) {
+  if (!c->my_mailbox) CUDA_TRY(cudaMalloc(&c->my_mailbox, sizeof(Mailbox)));
+  CUDA_TRY(cudaMemset(c->my_mailbox, 0, sizeof(Mailbox)));  // stale sequence numbers of an earlier group must not match
+  if (!c->my_arena) {
+    size_t half = ARENA_HALF_DEFAULT;
+    if (const char* e = getenv("B200_ARENA_MB")) half = ((size_t)atol(e) << 20) / 2;
+    if (half < ((size_t)1 << 20)) half = (size_t)1 << 20;
+    CUDA_TRY(cudaMalloc(&c->my_arena, 2 * half));
+    c->peer.arena_half = half;
   }
+  if (!c->d_peer_err) {
+    CUDA_TRY(cudaMalloc(&c->d_peer_err, sizeof(unsigned int)));
+    CUDA_TRY(cudaMemset(c->d_peer_err, 0, sizeof(unsigned int)));
+  }
+  CUDA_TRY(cudaDeviceSynchronize());
+  return B200_OK;
+}
+static void dist_set_common(Ctx* c, int rank, int world) {
+  c->peer.rank = rank;
+  c->peer.world = world;
+  c->peer.err = c->d_peer_err;
+  double secs = 20.0;
+  if (const char* e = getenv("B200_PEER_TIMEOUT_S")) secs = atof(e);
+  c->peer.timeout_ns = (unsigned long long)(secs * 1e9);
+  c->peer_seq = 0;
+  c->bulk_seq = 0;
+}
+
+// out_handle: 128 bytes = CUDA-IPC handle of the mailbox | CUDA-IPC handle of the bulk arena
+int b200_dist_mailbox_handle(b200_ctx* h, void* out_handle128) {
+  Ctx* c = &h->c;
+  int rc = dist_alloc_local(c);
+  if (rc) return rc;
   cudaIpcMemHandle_t hd;
-  CUDA_TRY(cudaIpcGetMemHandle(&hd, c->my_mailbox));
   static_assert(sizeof(hd) == 64, "cudaIpcMemHandle_t is 64 bytes");
-  memcpy(out_handle64, &hd, 64);
+  CUDA_TRY(cudaIpcGetMemHandle(&hd, c->my_mailbox));
+  memcpy(out_handle128, &hd, 64);
+  CUDA_TRY(cudaIpcGetMemHandle(&hd, c->my_arena));
+  memcpy((char*)out_handle128 + 64, &hd, 64);
   return B200_OK;
 }
 
 int b200_dist_init(b200_ctx* h, int rank, int world, const void* handles) {
   Ctx* c = &h->c;
-  if (world < 1 || world > PEER_MAX_WORLD || rank < 0 || rank >= world || !c->my_mailbox) return B200_ERR_ARG;
-  c->peer.rank = rank;
-  c->peer.world = world;
+  if (world < 1 || world > PEER_MAX_WORLD || (world & (world - 1)) || rank < 0 || rank >= world || !c->my_mailbox || !c->my_arena)
+    return B200_ERR_ARG;
+  dist_set_common(c, rank, world);
+  c->peer_ipc = true;
   for (int r = 0; r < world; ++r) {
     if (r == rank) {
       c->peer.box[r] = c->my_mailbox;
+      c->peer.arena[r] = c->my_arena;
       continue;
     }
     cudaIpcMemHandle_t hd;
-    memcpy(&hd, (const char*)handles + 64 * r, 64);
     void* p = nullptr;
+    memcpy(&hd, (const char*)handles + 128 * r, 64);
     CUDA_TRY(cudaIpcOpenMemHandle(&p, hd, cudaIpcMemLazyEnablePeerAccess));
     c->peer.box[r] = (Mailbox*)p;
+    memcpy(&hd, (const char*)handles + 128 * r + 64, 64);
+    CUDA_TRY(cudaIpcOpenMemHandle(&p, hd, cudaIpcMemLazyEnablePeerAccess));
+    c->peer.arena[r] = (unsigned char*)p;
   }
-  c->peer_seq = 0;
+  return B200_OK;
+}
+
+// Several contexts of ONE process as the ranks of a group (contexts on the same GPU, or on GPUs with peer access
+// enabled by the caller): mailboxes and arenas are shared as plain device pointers. Drive every context from its own
+// host thread — collective calls wait for each other on the device. This is how the sharded provers are tested on a
+// single-GPU box (tests/test_gpu_sharded.py); production uses one process per GPU (b200_dist_init).
+int b200_dist_init_local(b200_ctx* const* ctxs, int world) {
+  if (world < 1 || world > PEER_MAX_WORLD || (world & (world - 1))) return B200_ERR_ARG;
+  for (int r = 0; r < world; ++r) {
+    CUDA_TRY(cudaSetDevice(ctxs[r]->c.device));
+    int rc = dist_alloc_local(&ctxs[r]->c);
+    if (rc) return rc;
+  }
+  for (int r = 0; r < world; ++r) {
+    Ctx* c = &ctxs[r]->c;
+    // ranks sharing a device share its stream-ordered memory pool: reusing a block another rank has freed but not yet
+    // passed in ITS stream would make this rank's stream wait for that rank — which may be waiting for this one
+    cudaMemPool_t pool;
+    int zero = 0;
+    CUDA_TRY(cudaDeviceGetDefaultMemPool(&pool, c->device));
+    CUDA_TRY(cudaMemPoolSetAttribute(pool, cudaMemPoolReuseAllowInternalDependencies, &zero));
+    dist_set_common(c, r, world);
+    c->peer_ipc = false;
+    g_use_pdl = false;
+    c->peer.arena_half = ctxs[0]->c.peer.arena_half;
+    for (int k = 0; k < world; ++k) {
+      c->peer.box[k] = ctxs[k]->c.my_mailbox;
+      c->peer.arena[k] = ctxs[k]->c.my_arena;
+    }
+  }
+  return B200_OK;
+}
+
+// 0 when no peer wait has timed out since the last call (the flag is cleared), else B200_ERR_PEER
+int b200_dist_check(b200_ctx* h) {
+  Ctx* c = &h->c;
+  if (!c->d_peer_err) return B200_OK;
+  unsigned int v = 0;
+  CUDA_TRY(cudaMemcpyAsync(&v, c->d_peer_err, 4, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  if (v) CUDA_TRY(cudaMemsetAsync(c->d_peer_err, 0, 4, c->stream));
+  return v ? B200_ERR_PEER : B200_OK;
+}
+
+// Fully sharded Lasso prover: the m-sized witness tables, fingerprints, product-tree layers >= k0 and every sum-check
+// over them live on the rank's 1/world slice (index window [k0 - log2 world, k0)); lookups with mu <= k0 fall back to
+// the replicated prover. k0 = 0 switches it off. Collective like b200_dist_shard_commits (which it implies).
+int b200_dist_shard_lasso(b200_ctx* h, int k0) {
+  Ctx* c = &h->c;
+  int g = 0;
+  while ((1 << g) < c->peer.world) ++g;
+  if (k0 < 0 || (k0 && (c->peer.world < 2 || k0 - g < 1 || k0 > 28))) return B200_ERR_ARG;
+  c->shard_lasso_k0 = k0;
+  return B200_OK;
+}
+int b200_dist_shard_min_items(b200_ctx* h, int items) {
+  if (items < 1) return B200_ERR_ARG;
+  h->c.shard_min_items = items;
   return B200_OK;
 }
 
@@ -59,6 +154,14 @@ int b200_sumcheck_prove_evals_sharded(b200_ctx* h, int num_vars_total, int nterm
                                       const void* const* dev_local_tables, const void* host_weights,
                                       const void* host_y, const void* host_sum, void* host_challenges_out,
                                       void* host_evals_out) {
+  return b200_sumcheck_prove_evals_windowed(h, num_vars_total, -1, -1, nterms, np, dev_local_tables, host_weights, host_y,
+                                            host_sum, host_challenges_out, host_evals_out);
+}
+
+int b200_sumcheck_prove_evals_windowed(b200_ctx* h, int num_vars_total, int window_pos, int sharded_rounds, int nterms,
+                                       int np, const void* const* dev_local_tables, const void* host_weights,
+                                       const void* host_y, const void* host_sum, void* host_challenges_out,
+                                       void* host_evals_out) {
   Ctx* c = &h->c;
   const int n = num_vars_total;
   if (n < 2 || n > 34 || nterms < 1 || nterms > SC_MAX_TERMS || (np != 1 && np != 2)) return B200_ERR_ARG;
@@ -81,7 +184,7 @@ int b200_sumcheck_prove_evals_sharded(b200_ctx* h, int num_vars_total, int nterm
   job.claim = d + nterms + n;
   job.challenges_out = d + nin;
   job.evals_out = d + nin + n;
-  int rc = sumcheck_prove_evals_sharded(c, job, n);
+  int rc = sumcheck_prove_evals_sharded(c, job, n, window_pos, sharded_rounds);
   if (rc) return rc;
   std::vector<Fr> hout(nout);
   CUDA_TRY(cudaMemcpyAsync(hout.data(), d + nin, nout * sizeof(Fr), cudaMemcpyDeviceToHost, c->stream));

@@ -14,6 +14,8 @@ namespace b200 {
 #define B200_ERR_ARG 2
 #define B200_ERR_TRANSCRIPT 3  // identity commitment / proof overflow (Error::Transcript)
 #define B200_ERR_NOMEM 4
+#define B200_ERR_LOOKUP 5      // a lookup operand / input is not in its table
+#define B200_ERR_PEER 6        // a multi-GPU wait timed out (a peer left the collective)
 
 #define CUDA_TRY(x)                                                                      \
   do {                                                                                   \
@@ -110,6 +112,9 @@ __device__ __forceinline__ void pdl_prologue() {
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   asm volatile("griddepcontrol.wait;" ::: "memory");
 }
+// Off when several ranks share ONE GPU (b200_dist_init_local): a dependent grid that is resident early and waits for
+// its predecessor could otherwise occupy the SM slots another rank's kernel needs to make that predecessor finish.
+inline bool g_use_pdl = true;
 template <class... KArgs, class... Args>
 static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s,
                                      Args&&... args) {
@@ -122,7 +127,7 @@ static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 b
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = g_use_pdl ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 #endif

@@ -45,7 +45,13 @@ struct Ctx {
   // multi-GPU (one process per GPU): peer mailboxes mapped over NVLink, see peer.cuh
   PeerCtx peer;            // world == 1 when not initialised
   Mailbox* my_mailbox;     // cudaMalloc'ed, exported through CUDA IPC
-  unsigned int peer_seq;   // collectives issued so far (identical on every rank)
+  bool peer_ipc = false;   // peer pointers are CUDA-IPC mappings (closed on destroy)
+  unsigned int peer_seq;   // small collectives issued so far (identical on every rank)
+  unsigned int bulk_seq = 0;  // bulk all-gathers issued so far
+  unsigned char* my_arena = nullptr;  // bulk arena (2 halves), exported like the mailbox
+  unsigned int* d_peer_err = nullptr;  // device word raised by a timed-out wait (B200_ERR_PEER)
+  int shard_min_items = 1 << 14;  // a sum-check round stays sharded while a rank has at least this many (pair, term) items
+  int shard_lasso_k0 = 0;  // > 0: the Lasso prover shards its tables / trees on the index window [k0 - g, k0) (lasso.cu)
   bool shard_commits = false;  // every commitment MSM is split by point range over the ranks (all ranks call)
   int shard_sumcheck_min_vars = 0;  // > 0: sum-checks of the whole provers with at least that many variables run
                                     // hypercube-sharded over the ranks (sumcheck_prove_evals_dist, shard.cu)
@@ -69,10 +75,20 @@ struct ScEvalJob {
   const Fr* eq_scale = nullptr;     // optional device scalar multiplied into the eq table built from eq_point
   bool sharded = false;             // sum the per-round partials over all ranks (peer mailboxes)
   bool want_eq_eval = false;
+  // stop_after > 0: run only that many rounds and hand the state over (sharded drivers, shard.cu): carry->cur[i] are
+  // the tables as the NEXT round would read them (ntab tables then eq; the last challenge, still unbound, is in
+  // Ctx::d_sc->r), scratch is allocated from carry->scope so that it outlives this call
+  int stop_after = 0;
+  struct ScCarry* carry = nullptr;
+};
+struct ScCarry {
+  struct DevScope* scope;
+  const Fr* cur[2 * SC_MAX_TABLES + 2];
+  uint64_t len;  // entries per table in cur[]
 };
 int sumcheck_prove_evals(Ctx* c, const ScEvalJob& job);
 // shard.cu — hypercube-sharded sum-check and point-sharded MSM over peer memory
-int sumcheck_prove_evals_sharded(Ctx* c, const ScEvalJob& job_local, int num_vars_total);
+int sumcheck_prove_evals_sharded(Ctx* c, const ScEvalJob& job_local, int num_vars_total, int p = -1, int rounds = -1);
 // replicated full tables in, sharded evaluation when enabled (b200_dist_shard_sumchecks); else sumcheck_prove_evals
 int sumcheck_prove_evals_dist(Ctx* c, const ScEvalJob& job);
 
@@ -86,8 +102,17 @@ struct ScCoeffJob {
   const Fr* claim;
   Fr* challenges_out;
   Fr* evals_out;  // K
+  const Fr* eq_tables[SC_MAX_TERMS] = {nullptr};  // optional prebuilt eq tables (all or none); eq_points unused then
+  bool sharded = false;                 // as ScEvalJob
+  int stop_after = 0;                   // carry->cur = K tables then K eq tables
+  struct ScCarry* carry = nullptr;
 };
 int sumcheck_prove_coeffs(Ctx* c, const ScCoeffJob& job);
+int sumcheck_prove_coeffs_sharded(Ctx* c, const ScCoeffJob& job_local, int num_vars_total, int p = -1, int rounds = -1);
+// shard.cu helpers: bulk all-gather into the peer arenas, small all-reduce, evaluate() of sharded polynomials
+int shard_allgather(Ctx* c, const Fr* const* src, int ntab, uint32_t len, int q, bool bind, const Fr** full_out);
+int shard_allreduce(Ctx* c, Fr* d_vals, int cnt);
+int mle_eval_many_sharded(Ctx* c, const Fr* const* h_tables_loc, int ntables, int n, int p, const Fr* d_point, Fr* d_out);
 
 // generic.cu — EvaluationsProver for an arbitrary Expression compiled to bytecode on the host
 struct GenericJob {
@@ -116,6 +141,7 @@ int eq_build(Ctx* c, const Fr* d_y, int n, Fr* d_out);                         /
 int fix_var(Ctx* c, const Fr* d_in, int n, const Fr* d_r, Fr* d_out);          // one bind
 int mle_eval_many(Ctx* c, const Fr* const* h_tables, int ntables, int n, const Fr* d_point,
                   Fr* d_out);                                                   // evaluate
+int mle_dot_many(Ctx* c, const Fr* const* h_tables, int ntables, size_t len, const Fr* d_eq, Fr* d_out);  // <P_t, eq>
 int fr_lincomb(Ctx* c, const Fr* const* h_tables, int k, const Fr* d_scalars, size_t len,
                Fr* d_out);                                                      // Σ s_i P_i
 int fr_convert(Ctx* c, const Fr* d_in, Fr* d_out, size_t n, int to_mont);
@@ -138,10 +164,18 @@ struct MsmJob {
   int bits;             // significant bits of the largest scalar (254 for arbitrary Fr)
   const G1Aff* ext;     // optional precomputed window multiples of `bases` (Ctx::srs_ext layout), or null
   uint64_t ext_stride = 0;  // points per window in `ext` (0: n) — larger than n when the job is a point range
+  // map_g > 0: the scalars are one rank's compact slice of a polynomial sharded on the index bits [map_p, map_p + map_g):
+  // scalar i multiplies base ((i >> p) << (p + g)) | (rank << p) | (i & (2^p - 1))
+  int map_p = 0, map_g = 0, map_rank = 0;
 };
-int msm_batch(Ctx* c, const MsmJob* jobs, int J, G1Aff* d_out);
+// extra result J + i = Σ_t 2^(shift t) * result(src[t]): a commitment that is a linear combination of other commitments
+// of the same batch (Lasso: a = Σ_t 2^(w t) E_t) costs doublings instead of an MSM
+struct MsmDerive {
+  int nsrc, shift, src[8];
+};
+int msm_batch(Ctx* c, const MsmJob* jobs, int J, G1Aff* d_out, const MsmDerive* derive = nullptr, int nderive = 0);
 // shard.cu: msm_batch, point-sharded over the ranks when commit sharding is on (collective), else local
-int msm_batch_dist(Ctx* c, const MsmJob* jobs, int J, G1Aff* d_out);
+int msm_batch_dist(Ctx* c, const MsmJob* jobs, int J, G1Aff* d_out, const MsmDerive* derive = nullptr, int nderive = 0);
 int msm_sharded(Ctx* c, const MsmJob& local, G1Aff* d_out);  // shard.cu
 
 // kzg.cu — MultilinearKzg (pb/pcs/multilinear/kzg.rs) + additive::batch_open (pb/pcs/multilinear.rs:134-235)
@@ -152,9 +186,10 @@ struct BatchOpenJob {
   const int* ev_poly;      // host
   const int* ev_point;     // host
   const Fr* ev_values;     // device, nevals
+  int shard_p = -1;        // >= 0: polys are the rank's slices of polynomials sharded on the window [shard_p, shard_p + g)
 };
 int kzg_commit_batch(Ctx* c, const MsmJob* jobs, int J, bool write_transcript, G1Aff* d_out);
-int kzg_open(Ctx* c, const Fr* d_poly, int n, const Fr* d_point);
+int kzg_open(Ctx* c, const Fr* d_poly, int n, const Fr* d_point, int shard_p = -1);
 int kzg_batch_open(Ctx* c, const BatchOpenJob& job);
 int kzg_setup(Ctx* c, const Fr* d_ss, int n);
 int kzg_build_ext(Ctx* c, int level);  // fills c->srs_ext[level]
@@ -165,6 +200,26 @@ int lasso_witness(Ctx* c, int kind, int chunks, int mu, const uint64_t* d_xs, co
                   Fr* d_st);
 
 inline void count_launch(Ctx* c, int n = 1) { c->launches += n; }
+
+// Stream-ordered scratch released on EVERY exit path of a host function (error returns included).
+struct DevScope {
+  cudaStream_t s;
+  std::vector<void*> ptrs;
+  explicit DevScope(cudaStream_t stream) : s(stream) {}
+  DevScope(const DevScope&) = delete;
+  DevScope& operator=(const DevScope&) = delete;
+  template <class T>
+  cudaError_t alloc(T** p, size_t bytes) {
+    void* q = nullptr;
+    cudaError_t e = cudaMallocAsync(&q, bytes ? bytes : 32, s);
+    *p = reinterpret_cast<T*>(q);
+    if (e == cudaSuccess) ptrs.push_back(q);
+    return e;
+  }
+  ~DevScope() {
+    for (void* p : ptrs) cudaFreeAsync(p, s);
+  }
+};
 // returns the index of the (start, stop) event pair, or -1 when profiling is off; pairs may nest
 inline int prof_begin(Ctx* c, int tag) {
   if (!c->profile) return -1;

@@ -14,30 +14,54 @@ int kzg_commit_batch(Ctx* c, const MsmJob* jobs, int J, bool write_transcript, G
   return B200_OK;
 }
 
-// kzg.rs:276-302 (sanity-check off): quotients top variable first, commit q_i with eqs[i], write them
-int kzg_open(Ctx* c, const Fr* d_poly, int n, const Fr* d_point) {
+// kzg.rs:276-302 (sanity-check off): quotients top variable first, commit q_i with eqs[i], write them.
+// shard_p >= 0: d_poly is the rank's slice (window [p, p + g)): the quotient steps of the variables above the window
+// are local, their commitments are MSMs over the rank's points (MsmJob::map_*) summed over the ranks; then the 2^(p+g)
+// remainder is all-gathered once and the low levels run replicated.
+int kzg_open(Ctx* c, const Fr* d_poly, int n, const Fr* d_point, int shard_p) {
   if (n < 1 || n > 30 || (int)c->srs.size() <= n - 1) return B200_ERR_ARG;
   cudaStream_t s = c->stream;
-  const size_t N = (size_t)1 << n;
-  Fr *rem = nullptr, *q = nullptr;
+  const bool sh = shard_p >= 0 && c->peer.world > 1;
+  int g = 0;
+  while (sh && (1 << g) < c->peer.world) ++g;
+  const int K0 = sh ? shard_p + g : 0;
+  if (sh && K0 > n) return B200_ERR_ARG;
+  const size_t N_loc = (size_t)1 << (n - g);
+  DevScope mem(s);
+  Fr *rem = nullptr, *q = nullptr, *rem_full = nullptr, *q_full = nullptr;
   G1Aff* comms = nullptr;
-  CUDA_TRY(cudaMallocAsync(&rem, N * sizeof(Fr), s));
-  CUDA_TRY(cudaMallocAsync(&q, N * sizeof(Fr), s));  // level nv lives at [2^nv, 2^(nv+1))
-  CUDA_TRY(cudaMallocAsync(&comms, n * sizeof(G1Aff), s));
-  CUDA_TRY(cudaMemcpyAsync(rem, d_poly, N * sizeof(Fr), cudaMemcpyDeviceToDevice, s));
+  CUDA_TRY(mem.alloc(&rem, N_loc * sizeof(Fr)));
+  CUDA_TRY(mem.alloc(&q, N_loc * sizeof(Fr)));  // level nv lives at [2^(nv-g), 2^(nv-g+1))
+  CUDA_TRY(mem.alloc(&comms, n * sizeof(G1Aff)));
+  CUDA_TRY(cudaMemcpyAsync(rem, d_poly, N_loc * sizeof(Fr), cudaMemcpyDeviceToDevice, s));
   MsmJob jobs[32];
-  for (int nv = n - 1; nv >= 0; --nv) {
-    const size_t half = (size_t)1 << nv;
+  for (int nv = n - 1; nv >= K0; --nv) {
+    const size_t half = (size_t)1 << (nv - g);
     int rc = quotient_step(c, rem, half, d_point + nv, q + half);
     if (rc) return rc;
-    jobs[nv] = MsmJob{q + half, c->srs[nv], half, MSM_FR_MONT, 254, c->srs_ext[nv]};
+    jobs[nv] = MsmJob{q + half, c->srs[nv], half, MSM_FR_MONT, 254, c->srs_ext[nv], (uint64_t)1 << nv};
+    if (sh) {
+      jobs[nv].map_p = shard_p;
+      jobs[nv].map_g = g;
+      jobs[nv].map_rank = c->peer.rank;
+    }
   }
-  int rc = kzg_commit_batch(c, jobs, n, true, comms);
-  if (rc) return rc;
-  CUDA_TRY(cudaFreeAsync(rem, s));
-  CUDA_TRY(cudaFreeAsync(q, s));
-  CUDA_TRY(cudaFreeAsync(comms, s));
-  return B200_OK;
+  if (sh && K0 > 0) {
+    CUDA_TRY(mem.alloc(&rem_full, sizeof(Fr) << K0));
+    CUDA_TRY(mem.alloc(&q_full, sizeof(Fr) << K0));
+    const Fr* src[1] = {rem};
+    const Fr* full[1];
+    int rc = shard_allgather(c, src, 1, (uint32_t)1 << shard_p, shard_p, false, full);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(rem_full, full[0], sizeof(Fr) << K0, cudaMemcpyDeviceToDevice, s));
+    for (int nv = K0 - 1; nv >= 0; --nv) {
+      const size_t half = (size_t)1 << nv;
+      rc = quotient_step(c, rem_full, half, d_point + nv, q_full + half);
+      if (rc) return rc;
+      jobs[nv] = MsmJob{q_full + half, c->srs[nv], half, MSM_FR_MONT, 254, c->srs_ext[nv]};
+    }
+  }
+  return kzg_commit_batch(c, jobs, n, true, comms);
 }
 
 __global__ void gather_fr_kernel(const Fr* src, const int* idx, int n, Fr* dst) {
@@ -60,13 +84,17 @@ int kzg_batch_open(Ctx* c, const BatchOpenJob& job) {
   const int n = job.num_vars, P = job.npoints, E = job.nevals;
   if (n < 1 || n > 30 || P < 1 || P > SC_MAX_TERMS || E < 2 || E > SC_MAX_TABLES) return B200_ERR_ARG;
   cudaStream_t s = c->stream;
-  const size_t N = (size_t)1 << n;
+  const bool sh = job.shard_p >= 0 && c->peer.world > 1;
+  int g = 0;
+  while (sh && (1 << g) < c->peer.world) ++g;
+  const size_t N = (size_t)1 << (n - g);  // entries per (local) table
   int ell = 0;
   while ((1 << ell) < E) ++ell;
   // scalar arena: t[ell] | eq_xt[2^ell] | gathered[E] | tilde | ones[P] | challenges[n] | evals[P] | eqev[P]
   const size_t arena_n = (size_t)ell + ((size_t)1 << ell) + E + 1 + P + n + P + P;
+  DevScope mem(s);
   Fr* arena = nullptr;
-  CUDA_TRY(cudaMallocAsync(&arena, arena_n * sizeof(Fr), s));
+  CUDA_TRY(mem.alloc(&arena, arena_n * sizeof(Fr)));
   Fr* t = arena;
   Fr* eq_xt = t + ell;
   Fr* gathered = eq_xt + ((size_t)1 << ell);
@@ -82,10 +110,10 @@ int kzg_batch_open(Ctx* c, const BatchOpenJob& job) {
 
   // merged_i = Σ_{k : point(k) = i} eq_xt[k] * poly(k)      (pb/pcs/multilinear.rs:155-170)
   Fr* merged = nullptr;
-  CUDA_TRY(cudaMallocAsync(&merged, (size_t)P * N * sizeof(Fr), s));
+  CUDA_TRY(mem.alloc(&merged, (size_t)P * N * sizeof(Fr)));
   int h_idx[SC_MAX_TABLES];
   int* d_idx = nullptr;
-  CUDA_TRY(cudaMallocAsync(&d_idx, E * sizeof(int), s));
+  CUDA_TRY(mem.alloc(&d_idx, E * sizeof(int)));
   int pos = 0, start[SC_MAX_TERMS + 1];
   const Fr* tabs[SC_MAX_TABLES];
   std::vector<std::vector<const Fr*>> per_point(P);
@@ -124,7 +152,7 @@ int kzg_batch_open(Ctx* c, const BatchOpenJob& job) {
   sj.claim = tilde;
   sj.challenges_out = challenges;
   sj.evals_out = sc_evals;
-  rc = sumcheck_prove_coeffs(c, sj);
+  rc = sh ? sumcheck_prove_coeffs_sharded(c, sj, n, job.shard_p, -1) : sumcheck_prove_coeffs(c, sj);
   if (rc) return rc;
 
   // g' = Σ_i eq(challenges, point_i) * merged_i      (:203-212)
@@ -134,16 +162,10 @@ int kzg_batch_open(Ctx* c, const BatchOpenJob& job) {
     tabs[i] = merged + (size_t)i * N;
   }
   Fr* gprime = nullptr;
-  CUDA_TRY(cudaMallocAsync(&gprime, N * sizeof(Fr), s));
+  CUDA_TRY(mem.alloc(&gprime, N * sizeof(Fr)));
   rc = fr_lincomb(c, tabs, P, eqev, N, gprime);
   if (rc) return rc;
-  rc = kzg_open(c, gprime, n, challenges);
-  if (rc) return rc;
-  CUDA_TRY(cudaFreeAsync(gprime, s));
-  CUDA_TRY(cudaFreeAsync(merged, s));
-  CUDA_TRY(cudaFreeAsync(d_idx, s));
-  CUDA_TRY(cudaFreeAsync(arena, s));
-  return B200_OK;
+  return kzg_open(c, gprime, n, challenges, sh ? job.shard_p : -1);
 }
 
 // ---------------------------------------------------------------------------------------------

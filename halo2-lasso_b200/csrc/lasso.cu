@@ -30,13 +30,17 @@ __device__ __forceinline__ uint32_t lasso_dim(int kind, uint64_t x, uint64_t y, 
 }
 
 // dims[t][j], e[t][j] (u32) and the lookup output a[j] (u64)
+// *bad is raised when an operand does not fit the table (x >= 2^(16 c) for the range table, x or y >= 2^(8 c) for
+// and / xor): such a lookup is NOT in the decomposed table and must not be proven modulo the chunk width.
 __global__ void lasso_chunks_kernel(int kind, int c, uint32_t m, const uint64_t* __restrict__ xs,
                                     const uint64_t* __restrict__ ys, uint32_t* __restrict__ dims,
-                                    uint32_t* __restrict__ es, uint64_t* __restrict__ a) {
+                                    uint32_t* __restrict__ es, uint64_t* __restrict__ a, unsigned int* bad) {
   const uint32_t stride = gridDim.x * blockDim.x;
   const int out_bits = kind == 0 ? 16 : 8;
+  const int op_bits = (kind == 0 ? 16 : 8) * c;
   for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < m; j += stride) {
     const uint64_t x = xs[j], y = ys ? ys[j] : 0;
+    if (op_bits < 64 && (((x | y) >> op_bits) != 0)) *bad = 1;
     uint64_t out = 0;
     for (int t = 0; t < c; ++t) {
       const uint32_t d = lasso_dim(kind, x, y, t);
@@ -129,6 +133,27 @@ __global__ void u32_to_fr_kernel(const uint32_t* __restrict__ in, Fr* __restrict
     fe_st(out + i, fe_from_u64<FrP>(in[i]));
 }
 
+// Sharded layout (shard.cu): rank r keeps the entries whose index bits [p, p + g) equal r, compactly; local index i
+// stands for the global index below. g = 0 is the identity (single GPU).
+__device__ __forceinline__ uint32_t shard_map(uint32_t i, int p, int g, uint32_t rank) {
+  return g ? (((((i >> p) << g) | rank) << p) | (i & ((1u << p) - 1))) : i;
+}
+// out[t][i] = in[t][map(i)] for ntab integer tables of n entries each (n_loc = n >> g local entries)
+__global__ void u32_to_fr_map_kernel(const uint32_t* __restrict__ in, Fr* __restrict__ out, int ntab, uint32_t n,
+                                     uint32_t n_loc, int p, int g, uint32_t rank) {
+  const size_t total = (size_t)ntab * n_loc, stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
+    const uint32_t t = (uint32_t)(e / n_loc), i = (uint32_t)(e % n_loc);
+    fe_st(out + e, fe_from_u64<FrP>(in[(size_t)t * n + shard_map(i, p, g, rank)]));
+  }
+}
+__global__ void u64_to_fr_map_kernel(const uint64_t* __restrict__ in, Fr* __restrict__ out, uint32_t n_loc, int p, int g,
+                                     uint32_t rank) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_loc; i += stride)
+    fe_st(out + i, fe_from_u64<FrP>(in[shard_map((uint32_t)i, p, g, rank)]));
+}
+
 // m-sized leaves: read = dim*g^2 + e*g + ts - tau, write = read + 1 (trees 2t, 2t+1), stored in the
 // leaf layer [2^h, 2^(h+1)) of each tree array
 __global__ void __launch_bounds__(256) lasso_leaves_m_kernel(int c, uint32_t m, const Fr* __restrict__ dim_fr,
@@ -148,18 +173,21 @@ __global__ void __launch_bounds__(256) lasso_leaves_m_kernel(int c, uint32_t m, 
   }
 }
 // S-sized leaves: init = x*g^2 + T[x]*g - tau, final = init + final_cts
+// (the rank's S_loc = 2^16 >> sg entries when the subtable trees are sharded; cts_fr is always the full table)
 __global__ void __launch_bounds__(256) lasso_leaves_s_kernel(int kind, int c, const Fr* __restrict__ cts_fr,
-                                                             const Fr* __restrict__ gt, Fr* __restrict__ trees) {
+                                                             const Fr* __restrict__ gt, Fr* __restrict__ trees,
+                                                             uint32_t S_loc, int sp, int sg, uint32_t rank) {
   const Fr g = fe_ld(gt), tau = fe_ld(gt + 1);
   const Fr g2 = g * g;
   const int t = blockIdx.y;
-  const uint32_t x = blockIdx.x * blockDim.x + threadIdx.x;
-  if (x >= SUB_SIZE) return;
-  Fr* in = trees + (size_t)(2 * t) * 2 * SUB_SIZE + SUB_SIZE;
-  Fr* fi = trees + (size_t)(2 * t + 1) * 2 * SUB_SIZE + SUB_SIZE;
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= S_loc) return;
+  const uint32_t x = shard_map(i, sp, sg, rank);
+  Fr* in = trees + (size_t)(2 * t) * 2 * S_loc + S_loc;
+  Fr* fi = trees + (size_t)(2 * t + 1) * 2 * S_loc + S_loc;
   const Fr v = fe_from_u64<FrP>(x) * g2 + fe_from_u64<FrP>(lasso_subtable(kind, x)) * g - tau;
-  fe_st(in + x, v);
-  fe_st(fi + x, v + fe_ldg(cts_fr + (size_t)t * SUB_SIZE + x));
+  fe_st(in + i, v);
+  fe_st(fi + i, v + fe_ldg(cts_fr + (size_t)t * SUB_SIZE + x));
 }
 
 // one tree layer for a group of equally sized trees: V_k[i] = V_{k+1}[i] * V_{k+1}[i + 2^k]; tree
@@ -181,9 +209,13 @@ struct GpState {
   Fr evals[2 * SC_MAX_TERMS];  // (l, r) per active slot
 };
 struct GpTrees {
-  const Fr* base[SC_MAX_TERMS];  // heap-ordered tree arrays
+  const Fr* base[SC_MAX_TERMS];  // heap-ordered tree arrays (sharded trees: layers <= k0 only, replicated)
   int height[SC_MAX_TERMS];
   int T;
+  // sharded provers: trees higher than k0 keep their layers >= k0 on the rank's slice only — loc[t] is the local heap
+  // (layer k at [2^(k-g), 2^(k-g+1))), and the sum-checks of the layers k >= k0 run on those slices (shard.cu)
+  const Fr* loc[SC_MAX_TERMS];
+  int k0 = 0, g = 0;
 };
 
 // write the roots, which are the first claims
@@ -300,7 +332,20 @@ static int grand_product_prove(Ctx* c, const GpTrees& trees, GpState* st, Fr* sc
       job.claim = &st->claim;
       job.challenges_out = scratch_x;
       job.evals_out = st->evals;
-      int rc = sumcheck_prove_evals_dist(c, job);
+      int rc;
+      if (trees.k0 > 0 && k >= trees.k0) {  // every active tree is sharded: children halves of the LOCAL layer k + 1
+        A = 0;
+        for (int t = 0; t < trees.T; ++t) {
+          if (trees.height[t] <= k) continue;
+          const Fr* l = trees.loc[t] + ((size_t)2 << (k - trees.g));
+          job.tables[2 * A] = l;
+          job.tables[2 * A + 1] = l + ((size_t)1 << (k - trees.g));
+          ++A;
+        }
+        rc = sumcheck_prove_evals_sharded(c, job, k, trees.k0 - trees.g, -1);
+      } else {
+        rc = sumcheck_prove_evals_dist(c, job);
+      }
       if (rc) return rc;
     }
     CUDA_TRY(launch_pdl(gp_after_kernel, dim3(1), dim3(32), 0, s, c->d_tr, trees, k, scratch_x, st));
@@ -315,66 +360,109 @@ static int grand_product_prove(Ctx* c, const GpTrees& trees, GpState* st, Fr* sc
 }
 
 
+// integer witness of all 2^mu lookups (dims / E / read_ts / final_cts / a), validated operands
+struct LassoWitness {
+  uint32_t *dims, *es, *ts, *cts;
+  uint64_t* a_u64;
+};
+static int lasso_witness_ints(Ctx* c, DevScope& mem, int kind, int C_, int mu, const uint64_t* d_xs, const uint64_t* d_ys,
+                              LassoWitness* w) {
+  cudaStream_t s = c->stream;
+  const uint32_t m = 1u << mu;
+  const size_t S = SUB_SIZE;
+  uint32_t *hist, *base;
+  unsigned int* bad;
+  const uint32_t nch = m >= (1u << 13) ? (m / 32768 > 128 ? m / 32768 : 128) : 1;
+  const uint32_t chunk_len = m / nch;
+  CUDA_TRY(mem.alloc(&w->dims, (size_t)C_ * m * 4));
+  CUDA_TRY(mem.alloc(&w->es, (size_t)C_ * m * 4));
+  CUDA_TRY(mem.alloc(&w->ts, (size_t)C_ * m * 4));
+  CUDA_TRY(mem.alloc(&w->cts, (size_t)C_ * S * 4));
+  CUDA_TRY(mem.alloc(&w->a_u64, (size_t)m * 8));
+  CUDA_TRY(mem.alloc(&hist, (size_t)C_ * nch * (S / 2) * 4));
+  CUDA_TRY(mem.alloc(&base, (size_t)C_ * nch * S * 4));
+  CUDA_TRY(mem.alloc(&bad, 4));
+  CUDA_TRY(cudaMemsetAsync(bad, 0, 4, s));
+  int bx = (int)((m + 255) / 256);
+  if (bx > NUM_SMS * 8) bx = NUM_SMS * 8;
+  lasso_chunks_kernel<<<bx, 256, 0, s>>>(kind, C_, m, d_xs, d_ys, w->dims, w->es, w->a_u64, bad);
+  // an operand outside the table is an error BEFORE anything reaches the transcript (one 4-byte read-back, the only
+  // host round trip of the proof; the witness kernels below are already queued behind it)
+  unsigned int h_bad = 0;
+  CUDA_TRY(cudaMemcpyAsync(&h_bad, bad, 4, cudaMemcpyDeviceToHost, s));
+  const int smem = (int)(S / 2) * 4;  // 128 KiB
+  CUDA_TRY(cudaFuncSetAttribute(lasso_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  CUDA_TRY(cudaFuncSetAttribute(lasso_rank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  lasso_hist_kernel<<<dim3(nch, C_), 256, smem, s>>>(m, chunk_len, w->dims, hist);
+  lasso_colscan_kernel<<<dim3(S / 256, C_), 256, 0, s>>>(nch, hist, base, w->cts);
+  lasso_rank_kernel<<<dim3(nch, C_), 32, smem, s>>>(m, chunk_len, w->dims, base, w->ts);
+  count_launch(c, 4);
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaStreamSynchronize(s));
+  return h_bad ? B200_ERR_LOOKUP : B200_OK;
+}
+
 int lasso_prove(Ctx* c, int kind, int chunks, int mu, const uint64_t* d_xs, const uint64_t* d_ys) {
   if (kind < 0 || kind > 2 || chunks < 1 || chunks > 8 || mu < 1 || mu > 26) return B200_ERR_ARG;
   if (kind == 0 && chunks > 4) return B200_ERR_ARG;
+  if (kind != 0 && !d_ys) return B200_ERR_ARG;  // and / xor need both operands
   if (chunks < 2) return B200_ERR_ARG;  // additive batch_open needs >= 2 evaluations (pcs/multilinear.rs:150)
   if ((int)c->srs.size() <= (mu > SUB_VARS ? mu : SUB_VARS)) return B200_ERR_ARG;
   cudaStream_t s = c->stream;
   const int C_ = chunks;
   const uint32_t m = 1u << mu;
   const size_t S = SUB_SIZE;
+  // ---- sharding geometry (b200_dist_shard_lasso): index window [p, p + g) -> rank -----------------------------
+  const int G = c->peer.world;
+  int g = 0;
+  while ((1 << g) < G) ++g;
+  const int K0 = c->shard_lasso_k0;
+  const bool sh = K0 > 0 && G > 1 && mu > K0;        // m-sized tables / trees live on the rank's slice
+  const bool s_sh = sh && SUB_VARS > K0;              // so do the subtable-sized trees (small K0: tests)
+  const int p = sh ? K0 - g : 0, lg = sh ? g : 0;
+  const uint32_t rank = sh ? (uint32_t)c->peer.rank : 0;
+  const uint32_t m_loc = m >> lg;
+  const uint32_t S_loc = s_sh ? (uint32_t)(S >> g) : (uint32_t)S;
+  const bool saved_shard_commits = c->shard_commits;
+  if (sh) c->shard_commits = true;
+  struct Restore {
+    Ctx* c;
+    bool v;
+    ~Restore() { c->shard_commits = v; }
+  } restore{c, saved_shard_commits};
+  DevScope mem(s);
 
-  // ---- 1. witness -------------------------------------------------------------------------------
+  // ---- 1. witness (integers, all lookups) ------------------------------------------------------------
   int ph = prof_begin(c, PH_WITNESS);
-  uint32_t *dims, *es, *ts, *cts, *hist, *base;
-  uint64_t* a_u64;
-  const uint32_t nch = m >= (1u << 13) ? (m / 32768 > 128 ? m / 32768 : 128) : 1;
-  const uint32_t chunk_len = m / nch;
-  CUDA_TRY(cudaMallocAsync(&dims, (size_t)C_ * m * 4, s));
-  CUDA_TRY(cudaMallocAsync(&es, (size_t)C_ * m * 4, s));
-  CUDA_TRY(cudaMallocAsync(&ts, (size_t)C_ * m * 4, s));
-  CUDA_TRY(cudaMallocAsync(&cts, (size_t)C_ * S * 4, s));
-  CUDA_TRY(cudaMallocAsync(&a_u64, (size_t)m * 8, s));
-  CUDA_TRY(cudaMallocAsync(&hist, (size_t)C_ * nch * (S / 2) * 4, s));
-  CUDA_TRY(cudaMallocAsync(&base, (size_t)C_ * nch * S * 4, s));
-  {
-    int bx = (int)((m + 255) / 256);
-    if (bx > NUM_SMS * 8) bx = NUM_SMS * 8;
-    lasso_chunks_kernel<<<bx, 256, 0, s>>>(kind, C_, m, d_xs, d_ys, dims, es, a_u64);
-    const int smem = (int)(S / 2) * 4;  // 128 KiB
-    CUDA_TRY(cudaFuncSetAttribute(lasso_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    CUDA_TRY(cudaFuncSetAttribute(lasso_rank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    lasso_hist_kernel<<<dim3(nch, C_), 256, smem, s>>>(m, chunk_len, dims, hist);
-    lasso_colscan_kernel<<<dim3(S / 256, C_), 256, 0, s>>>(nch, hist, base, cts);
-    lasso_rank_kernel<<<dim3(nch, C_), 32, smem, s>>>(m, chunk_len, dims, base, ts);
-    count_launch(c, 4);
-  }
-  // field-element tables: a | dim[c] | e[c] | ts[c] (m each), cts[c] (S each)
+  LassoWitness wit;
+  int rc = lasso_witness_ints(c, mem, kind, C_, mu, d_xs, d_ys, &wit);
+  if (rc) return rc;
+  uint32_t *dims = wit.dims, *es = wit.es, *ts = wit.ts, *cts = wit.cts;
+  uint64_t* a_u64 = wit.a_u64;
+  // field-element tables of the rank's slice: a | dim[c] | e[c] | ts[c] (m_loc each); cts[c] (S each, always full)
   const int NM = 1 + 3 * C_;
   Fr *mt, *st_tabs;
-  CUDA_TRY(cudaMallocAsync(&mt, (size_t)NM * m * sizeof(Fr), s));
-  CUDA_TRY(cudaMallocAsync(&st_tabs, (size_t)C_ * S * sizeof(Fr), s));
+  CUDA_TRY(mem.alloc(&mt, (size_t)NM * m_loc * sizeof(Fr)));
+  CUDA_TRY(mem.alloc(&st_tabs, (size_t)C_ * S * sizeof(Fr)));
   Fr* a_fr = mt;
-  Fr* dim_fr = mt + (size_t)m;
-  Fr* e_fr = dim_fr + (size_t)C_ * m;
-  Fr* ts_fr = e_fr + (size_t)C_ * m;
-  int rc = fr_from_u64(c, a_u64, a_fr, m);
-  if (rc) return rc;
+  Fr* dim_fr = mt + (size_t)m_loc;
+  Fr* e_fr = dim_fr + (size_t)C_ * m_loc;
+  Fr* ts_fr = e_fr + (size_t)C_ * m_loc;
   {
     const int bx = NUM_SMS * 8;
-    u32_to_fr_kernel<<<bx, 256, 0, s>>>(dims, dim_fr, (size_t)C_ * m);
-    u32_to_fr_kernel<<<bx, 256, 0, s>>>(es, e_fr, (size_t)C_ * m);
-    u32_to_fr_kernel<<<bx, 256, 0, s>>>(ts, ts_fr, (size_t)C_ * m);
+    u64_to_fr_map_kernel<<<bx, 256, 0, s>>>(a_u64, a_fr, m_loc, p, lg, rank);
+    u32_to_fr_map_kernel<<<bx, 256, 0, s>>>(dims, dim_fr, C_, m, m_loc, p, lg, rank);
+    u32_to_fr_map_kernel<<<bx, 256, 0, s>>>(es, e_fr, C_, m, m_loc, p, lg, rank);
+    u32_to_fr_map_kernel<<<bx, 256, 0, s>>>(ts, ts_fr, C_, m, m_loc, p, lg, rank);
     u32_to_fr_kernel<<<bx, 256, 0, s>>>(cts, st_tabs, (size_t)C_ * S);
-    count_launch(c, 4);
+    count_launch(c, 5);
   }
 
   // ---- scalar arena -------------------------------------------------------------------------------
   // stmt[3] | r[mu] | v_a | pw[c] | x_p[mu] | e_p[c] | gt[2] | x_scratch[32] | ev_m[3c] | ev_s[c] | pts[3*mu]
   const size_t arena_n = 3 + mu + 1 + C_ + mu + C_ + 2 + 32 + 3 * C_ + C_ + 3 * (size_t)mu + SUB_VARS;
   Fr* arena;
-  CUDA_TRY(cudaMallocAsync(&arena, arena_n * sizeof(Fr), s));
+  CUDA_TRY(mem.alloc(&arena, arena_n * sizeof(Fr)));
   Fr* stmt = arena;
   Fr* r = stmt + 3;
   Fr* v_a = r + mu;
@@ -388,13 +476,13 @@ int lasso_prove(Ctx* c, int kind, int chunks, int mu, const uint64_t* d_xs, cons
   Fr* pts = ev_s + C_;
   Fr* pt_s = pts + 3 * (size_t)mu;
   GpState* gp;
-  CUDA_TRY(cudaMallocAsync(&gp, sizeof(GpState), s));
+  CUDA_TRY(mem.alloc(&gp, sizeof(GpState)));
+  const int out_bits = kind == 0 ? 16 : 8;
   {
     Fr h[3 + 8];
     h[0] = fe_from_u64<FrP>((uint64_t)kind);
     h[1] = fe_from_u64<FrP>((uint64_t)C_);
     h[2] = fe_from_u64<FrP>((uint64_t)mu);
-    const int out_bits = kind == 0 ? 16 : 8;
     for (int t = 0; t < C_; ++t) h[3 + t] = fe_from_u64<FrP>((uint64_t)1 << (out_bits * t));
     CUDA_TRY(cudaMemcpyAsync(stmt, h, 3 * sizeof(Fr), cudaMemcpyHostToDevice, s));
     CUDA_TRY(cudaMemcpyAsync(pw, h + 3, C_ * sizeof(Fr), cudaMemcpyHostToDevice, s));
@@ -405,41 +493,48 @@ int lasso_prove(Ctx* c, int kind, int chunks, int mu, const uint64_t* d_xs, cons
   ph = prof_begin(c, PH_COMMIT);
 
   // ---- 2. commitments: a, dim_*, E_*, read_ts_* (level mu), final_cts_* (level 16) -----------------
+  // MSMs run on the integer witness (small scalars populate few windows). Two commitments are free:
+  //  * a = Σ_t 2^(w t) E_t as polynomials, so Com(a) = Σ_t 2^(w t) Com(E_t): doublings instead of an MSM;
+  //  * identity subtable (range): E_t == dim_t, the same point is written twice.
   {
-    MsmJob jobs[1 + 4 * 8];
+    MsmJob jobs[4 * 8];
     int J = 0;
-    const int e_bits = kind == 0 ? 16 : 8;
-    jobs[J++] = MsmJob{a_u64, c->srs[mu], m, MSM_U64, e_bits * C_, c->srs_ext[mu]};
-    for (int t = 0; t < C_; ++t) jobs[J++] = MsmJob{dims + (size_t)t * m, c->srs[mu], m, MSM_U32, 16, nullptr};
-    // identity subtable (range): E_t == dim_t as polynomials, so their commitments are the same point —
-    // the MSM is run once and the point is written twice
     const bool e_is_dim = kind == 0;
+    const int j_dim = J;
+    for (int t = 0; t < C_; ++t) jobs[J++] = MsmJob{dims + (size_t)t * m, c->srs[mu], m, MSM_U32, 16, nullptr};
+    const int j_e = e_is_dim ? j_dim : J;
     if (!e_is_dim)
-      for (int t = 0; t < C_; ++t) jobs[J++] = MsmJob{es + (size_t)t * m, c->srs[mu], m, MSM_U32, e_bits, nullptr};
+      for (int t = 0; t < C_; ++t) jobs[J++] = MsmJob{es + (size_t)t * m, c->srs[mu], m, MSM_U32, out_bits, nullptr};
+    const int j_ts = J;
     for (int t = 0; t < C_; ++t) jobs[J++] = MsmJob{ts + (size_t)t * m, c->srs[mu], m, MSM_U32, mu + 1, nullptr};
+    const int j_cts = J;
     for (int t = 0; t < C_; ++t) jobs[J++] = MsmJob{cts + (size_t)t * S, c->srs[SUB_VARS], S, MSM_U32, mu + 1, nullptr};
+    MsmDerive da;
+    da.nsrc = C_;
+    da.shift = out_bits;
+    for (int t = 0; t < C_; ++t) da.src[t] = j_e + t;
     G1Aff *comms, *all;
     const int NC = 1 + 4 * C_;
-    CUDA_TRY(cudaMallocAsync(&comms, J * sizeof(G1Aff), s));
-    CUDA_TRY(cudaMallocAsync(&all, NC * sizeof(G1Aff), s));
-    rc = msm_batch_dist(c, jobs, J, comms);
+    CUDA_TRY(mem.alloc(&comms, (J + 1) * sizeof(G1Aff)));
+    CUDA_TRY(mem.alloc(&all, NC * sizeof(G1Aff)));
+    rc = msm_batch_dist(c, jobs, J, comms, &da, 1);
     if (rc) return rc;
     // transcript order: a | dim[c] | E[c] | read_ts[c] | final_cts[c]
     int h_src[1 + 4 * 8];
-    for (int i = 0; i < NC; ++i) {
-      if (!e_is_dim) h_src[i] = i;
-      else h_src[i] = i < 1 + C_ ? i : (i < 1 + 2 * C_ ? i - C_ : i - C_);
+    h_src[0] = J;
+    for (int t = 0; t < C_; ++t) {
+      h_src[1 + t] = j_dim + t;
+      h_src[1 + C_ + t] = j_e + t;
+      h_src[1 + 2 * C_ + t] = j_ts + t;
+      h_src[1 + 3 * C_ + t] = j_cts + t;
     }
     int* d_src;
-    CUDA_TRY(cudaMallocAsync(&d_src, NC * sizeof(int), s));
+    CUDA_TRY(mem.alloc(&d_src, NC * sizeof(int)));
     CUDA_TRY(cudaMemcpyAsync(d_src, h_src, NC * sizeof(int), cudaMemcpyHostToDevice, s));
     gather_points_kernel<<<1, 64, 0, s>>>(comms, d_src, NC, all);
     count_launch(c);
     rc = transcript_write_points(c, all, NC);
     if (rc) return rc;
-    CUDA_TRY(cudaFreeAsync(d_src, s));
-    CUDA_TRY(cudaFreeAsync(all, s));
-    CUDA_TRY(cudaFreeAsync(comms, s));
   }
 
   prof_end(c, ph);
@@ -449,7 +544,7 @@ int lasso_prove(Ctx* c, int kind, int chunks, int mu, const uint64_t* d_xs, cons
   if (rc) return rc;
   {
     const Fr* tab[1] = {a_fr};
-    rc = mle_eval_many(c, tab, 1, mu, r, v_a);
+    rc = sh ? mle_eval_many_sharded(c, tab, 1, mu, p, r, v_a) : mle_eval_many(c, tab, 1, mu, r, v_a);
     if (rc) return rc;
   }
   rc = transcript_op(c, TR_WRITE, v_a, nullptr, 1);
@@ -459,13 +554,13 @@ int lasso_prove(Ctx* c, int kind, int chunks, int mu, const uint64_t* d_xs, cons
     job.num_vars = mu;
     job.T = C_;
     job.NP = 1;
-    for (int t = 0; t < C_; ++t) job.tables[t] = e_fr + (size_t)t * m;
+    for (int t = 0; t < C_; ++t) job.tables[t] = e_fr + (size_t)t * m_loc;
     job.weights = pw;
     job.eq_point = r;
     job.claim = v_a;
     job.challenges_out = x_p;
     job.evals_out = e_p;
-    rc = sumcheck_prove_evals_dist(c, job);
+    rc = sh ? sumcheck_prove_evals_sharded(c, job, mu, p, -1) : sumcheck_prove_evals_dist(c, job);
     if (rc) return rc;
   }
   rc = transcript_op(c, TR_WRITE, e_p, nullptr, C_);
@@ -477,43 +572,70 @@ int lasso_prove(Ctx* c, int kind, int chunks, int mu, const uint64_t* d_xs, cons
   rc = transcript_op(c, TR_SQUEEZE, nullptr, gt, 2);
   if (rc) return rc;
   const int T = 2 * C_;
-  Fr *mtrees, *strees;
-  CUDA_TRY(cudaMallocAsync(&mtrees, (size_t)T * 2 * m * sizeof(Fr), s));
-  CUDA_TRY(cudaMallocAsync(&strees, (size_t)T * 2 * S * sizeof(Fr), s));
+  // heaps: the rank's layers (all layers when not sharded), and for sharded trees a replicated heap of the layers <= K0
+  Fr *mtrees, *strees, *mfull = nullptr, *sfull = nullptr;
+  CUDA_TRY(mem.alloc(&mtrees, (size_t)T * 2 * m_loc * sizeof(Fr)));
+  CUDA_TRY(mem.alloc(&strees, (size_t)T * 2 * S_loc * sizeof(Fr)));
+  if (sh) CUDA_TRY(mem.alloc(&mfull, ((size_t)T * 2 << K0) * sizeof(Fr)));
+  if (s_sh) CUDA_TRY(mem.alloc(&sfull, ((size_t)T * 2 << K0) * sizeof(Fr)));
   {
-    int bx = (int)((m + 255) / 256);
+    int bx = (int)((m_loc + 255) / 256);
     int cap = (8 * NUM_SMS + C_ - 1) / C_;
     if (bx > cap) bx = cap;
-    lasso_leaves_m_kernel<<<dim3(bx, C_), 256, 0, s>>>(C_, m, dim_fr, e_fr, ts_fr, gt, mtrees);
-    lasso_leaves_s_kernel<<<dim3(S / 256, C_), 256, 0, s>>>(kind, C_, st_tabs, gt, strees);
+    lasso_leaves_m_kernel<<<dim3(bx, C_), 256, 0, s>>>(C_, m_loc, dim_fr, e_fr, ts_fr, gt, mtrees);
+    lasso_leaves_s_kernel<<<dim3((S_loc + 255) / 256, C_), 256, 0, s>>>(kind, C_, st_tabs, gt, strees, S_loc,
+                                                                        s_sh ? p : 0, s_sh ? g : 0, rank);
     count_launch(c, 2);
   }
   {
-    // product trees (all layers of all trees), then ONE batched GKR over the 4c trees
-    for (int k = mu - 1; k >= 0; --k) {
-      const uint32_t half = 1u << k;
-      int bx = (int)((half + 255) / 256), cap = (4 * NUM_SMS + T - 1) / T;
-      if (bx > cap) bx = cap;
-      CUDA_TRY(launch_pdl(tree_up_kernel, dim3(dim3(bx, T)), dim3(256), 0, s, mtrees, (size_t)2 * m, half));
-    }
-    for (int k = SUB_VARS - 1; k >= 0; --k) {
-      const uint32_t half = 1u << k;
-      int bx = (int)((half + 255) / 256), cap = (4 * NUM_SMS + T - 1) / T;
-      if (bx > cap) bx = cap;
-      CUDA_TRY(launch_pdl(tree_up_kernel, dim3(dim3(bx, T)), dim3(256), 0, s, strees, (size_t)2 * S, half));
-    }
-    count_launch(c, mu + SUB_VARS);
+    // product trees, then ONE batched GKR over the 4c trees. Sharded trees: local layers down to K0, one bulk
+    // all-gather of layer K0 (2^K0 entries per tree), replicated layers above.
+    auto build = [&](Fr* loc, uint32_t n_loc, int height, bool sharded, Fr* full) -> int {
+      const int lgg = sharded ? g : 0, kmin = sharded ? K0 : 0;
+      for (int k = height - 1; k >= kmin; --k) {
+        const uint32_t half = 1u << (k - lgg);
+        int bx = (int)((half + 255) / 256), cap = (4 * NUM_SMS + T - 1) / T;
+        if (bx > cap) bx = cap;
+        CUDA_TRY(launch_pdl(tree_up_kernel, dim3(dim3(bx, T)), dim3(256), 0, s, loc, (size_t)2 * n_loc, half));
+        count_launch(c);
+      }
+      if (!sharded) return B200_OK;
+      const Fr* src[SC_MAX_TERMS];
+      const Fr* gathered[SC_MAX_TERMS];
+      const uint32_t len = 1u << (K0 - g);
+      for (int t = 0; t < T; ++t) src[t] = loc + (size_t)t * 2 * n_loc + len;  // local layer K0
+      int rc2 = shard_allgather(c, src, T, len, K0 - g, false, gathered);
+      if (rc2) return rc2;
+      for (int t = 0; t < T; ++t)
+        CUDA_TRY(cudaMemcpyAsync(full + ((size_t)t * 2 << K0) + ((size_t)1 << K0), gathered[t], sizeof(Fr) << K0,
+                                 cudaMemcpyDeviceToDevice, s));
+      for (int k = K0 - 1; k >= 0; --k) {
+        const uint32_t half = 1u << k;
+        int bx = (int)((half + 255) / 256), cap = (4 * NUM_SMS + T - 1) / T;
+        if (bx > cap) bx = cap;
+        CUDA_TRY(launch_pdl(tree_up_kernel, dim3(dim3(bx, T)), dim3(256), 0, s, full, (size_t)2 << K0, half));
+        count_launch(c);
+      }
+      return B200_OK;
+    };
+    rc = build(mtrees, m_loc, mu, sh, mfull);
+    if (rc) return rc;
+    rc = build(strees, S_loc, SUB_VARS, s_sh, sfull);
+    if (rc) return rc;
     GpTrees trees;
     trees.T = 2 * T;
+    trees.k0 = sh ? K0 : 0;
+    trees.g = sh ? g : 0;
     for (int t = 0; t < T; ++t) {
-      trees.base[t] = mtrees + (size_t)t * 2 * m;
+      trees.base[t] = sh ? mfull + ((size_t)t * 2 << K0) : mtrees + (size_t)t * 2 * m;
+      trees.loc[t] = sh ? mtrees + (size_t)t * 2 * m_loc : nullptr;
       trees.height[t] = mu;
-      trees.base[T + t] = strees + (size_t)t * 2 * S;
+      trees.base[T + t] = s_sh ? sfull + ((size_t)t * 2 << K0) : strees + (size_t)t * 2 * S;
+      trees.loc[T + t] = s_sh ? strees + (size_t)t * 2 * S_loc : nullptr;
       trees.height[T + t] = SUB_VARS;
     }
     Fr* point_out[33] = {nullptr};
     point_out[mu] = pts + 2 * (size_t)mu;  // x_m
-    Fr* xs_tmp = nullptr;
     if (mu == SUB_VARS) {  // both leaf layers are reached at the same point
       rc = grand_product_prove(c, trees, gp, x_scratch, point_out);
       if (rc) return rc;
@@ -524,18 +646,16 @@ int lasso_prove(Ctx* c, int kind, int chunks, int mu, const uint64_t* d_xs, cons
       rc = grand_product_prove(c, trees, gp, x_scratch, point_out);
       if (rc) return rc;
     }
-    (void)xs_tmp;
   }
-  CUDA_TRY(cudaFreeAsync(mtrees, s));
-  CUDA_TRY(cudaFreeAsync(strees, s));
 
   prof_end(c, ph);
   ph = prof_begin(c, PH_LEAF_EVALS);
   // ---- 9. leaf openings -----------------------------------------------------------------------------
   {
     const Fr* tabs[3 * 8];
-    for (int i = 0; i < 3 * C_; ++i) tabs[i] = dim_fr + (size_t)i * m;  // dim*, e*, ts* are contiguous
-    rc = mle_eval_many(c, tabs, 3 * C_, mu, pts + 2 * (size_t)mu, ev_m);
+    for (int i = 0; i < 3 * C_; ++i) tabs[i] = dim_fr + (size_t)i * m_loc;  // dim*, e*, ts* are contiguous
+    rc = sh ? mle_eval_many_sharded(c, tabs, 3 * C_, mu, p, pts + 2 * (size_t)mu, ev_m)
+            : mle_eval_many(c, tabs, 3 * C_, mu, pts + 2 * (size_t)mu, ev_m);
     if (rc) return rc;
     for (int t = 0; t < C_; ++t) tabs[t] = st_tabs + (size_t)t * S;
     rc = mle_eval_many(c, tabs, C_, SUB_VARS, pt_s, ev_s);
@@ -555,13 +675,13 @@ int lasso_prove(Ctx* c, int kind, int chunks, int mu, const uint64_t* d_xs, cons
     count_launch(c, 2);
     const int E = 1 + 4 * C_;
     Fr* vals;
-    CUDA_TRY(cudaMallocAsync(&vals, E * sizeof(Fr), s));
+    CUDA_TRY(mem.alloc(&vals, E * sizeof(Fr)));
     CUDA_TRY(launch_pdl(copy_fr_kernel, dim3(1), dim3(64), 0, s, v_a, vals, 1));
     CUDA_TRY(launch_pdl(copy_fr_kernel, dim3(1), dim3(64), 0, s, e_p, vals + 1, C_));
     CUDA_TRY(launch_pdl(copy_fr_kernel, dim3(1), dim3(64), 0, s, ev_m, vals + 1 + C_, 3 * C_));
     count_launch(c, 3);
     const Fr* polys[1 + 3 * 8];
-    for (int i = 0; i < NM; ++i) polys[i] = mt + (size_t)i * m;
+    for (int i = 0; i < NM; ++i) polys[i] = mt + (size_t)i * m_loc;
     int ev_poly[1 + 4 * 8], ev_point[1 + 4 * 8], k = 0;
     ev_poly[k] = 0, ev_point[k++] = 0;
     for (int t = 0; t < C_; ++t) ev_poly[k] = 1 + C_ + t, ev_point[k++] = 1;
@@ -569,6 +689,7 @@ int lasso_prove(Ctx* c, int kind, int chunks, int mu, const uint64_t* d_xs, cons
     for (int t = 0; t < C_; ++t) ev_poly[k] = 1 + C_ + t, ev_point[k++] = 2;
     for (int t = 0; t < C_; ++t) ev_poly[k] = 1 + 2 * C_ + t, ev_point[k++] = 2;
     BatchOpenJob bj{mu, NM, 3, E, polys, pts, ev_poly, ev_point, vals};
+    bj.shard_p = sh ? p : -1;
     rc = kzg_batch_open(c, bj);
     if (rc) return rc;
     prof_end(c, ph);
@@ -580,11 +701,7 @@ int lasso_prove(Ctx* c, int kind, int chunks, int mu, const uint64_t* d_xs, cons
     rc = kzg_batch_open(c, sj);
     if (rc) return rc;
     prof_end(c, ph);
-    CUDA_TRY(cudaFreeAsync(vals, s));
   }
-  for (void* p : {(void*)dims, (void*)es, (void*)ts, (void*)cts, (void*)a_u64, (void*)hist, (void*)base, (void*)mt,
-                  (void*)st_tabs, (void*)arena, (void*)gp})
-    CUDA_TRY(cudaFreeAsync(p, s));
   CUDA_TRY(cudaGetLastError());
   return B200_OK;
 }
@@ -593,40 +710,23 @@ int lasso_prove(Ctx* c, int kind, int chunks, int mu, const uint64_t* d_xs, cons
 int lasso_witness(Ctx* c, int kind, int chunks, int mu, const uint64_t* d_xs, const uint64_t* d_ys, Fr* d_mt,
                   Fr* d_st) {
   if (kind < 0 || kind > 2 || chunks < 1 || chunks > 8 || mu < 1 || mu > 26) return B200_ERR_ARG;
+  if (kind != 0 && !d_ys) return B200_ERR_ARG;
   cudaStream_t s = c->stream;
   const int C_ = chunks;
   const uint32_t m = 1u << mu;
   const size_t S = SUB_SIZE;
-  uint32_t *dims, *es, *ts, *cts, *hist, *base;
-  uint64_t* a_u64;
-  const uint32_t nch = m >= (1u << 13) ? (m / 32768 > 128 ? m / 32768 : 128) : 1;
-  const uint32_t chunk_len = m / nch;
-  CUDA_TRY(cudaMallocAsync(&dims, (size_t)C_ * m * 4, s));
-  CUDA_TRY(cudaMallocAsync(&es, (size_t)C_ * m * 4, s));
-  CUDA_TRY(cudaMallocAsync(&ts, (size_t)C_ * m * 4, s));
-  CUDA_TRY(cudaMallocAsync(&cts, (size_t)C_ * S * 4, s));
-  CUDA_TRY(cudaMallocAsync(&a_u64, (size_t)m * 8, s));
-  CUDA_TRY(cudaMallocAsync(&hist, (size_t)C_ * nch * (S / 2) * 4, s));
-  CUDA_TRY(cudaMallocAsync(&base, (size_t)C_ * nch * S * 4, s));
-  int bx = (int)((m + 255) / 256);
-  if (bx > NUM_SMS * 8) bx = NUM_SMS * 8;
-  lasso_chunks_kernel<<<bx, 256, 0, s>>>(kind, C_, m, d_xs, d_ys, dims, es, a_u64);
-  const int smem = (int)(S / 2) * 4;
-  CUDA_TRY(cudaFuncSetAttribute(lasso_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  CUDA_TRY(cudaFuncSetAttribute(lasso_rank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  lasso_hist_kernel<<<dim3(nch, C_), 256, smem, s>>>(m, chunk_len, dims, hist);
-  lasso_colscan_kernel<<<dim3(S / 256, C_), 256, 0, s>>>(nch, hist, base, cts);
-  lasso_rank_kernel<<<dim3(nch, C_), 32, smem, s>>>(m, chunk_len, dims, base, ts);
-  int rc = fr_from_u64(c, a_u64, d_mt, m);
+  DevScope mem(s);
+  LassoWitness w;
+  int rc = lasso_witness_ints(c, mem, kind, C_, mu, d_xs, d_ys, &w);
+  if (rc) return rc;
+  rc = fr_from_u64(c, w.a_u64, d_mt, m);
   if (rc) return rc;
   const int gx = NUM_SMS * 8;
-  u32_to_fr_kernel<<<gx, 256, 0, s>>>(dims, d_mt + (size_t)m, (size_t)C_ * m);
-  u32_to_fr_kernel<<<gx, 256, 0, s>>>(es, d_mt + (size_t)(1 + C_) * m, (size_t)C_ * m);
-  u32_to_fr_kernel<<<gx, 256, 0, s>>>(ts, d_mt + (size_t)(1 + 2 * C_) * m, (size_t)C_ * m);
-  u32_to_fr_kernel<<<gx, 256, 0, s>>>(cts, d_st, (size_t)C_ * S);
-  count_launch(c, 9);
-  for (void* p : {(void*)dims, (void*)es, (void*)ts, (void*)cts, (void*)a_u64, (void*)hist, (void*)base})
-    CUDA_TRY(cudaFreeAsync(p, s));
+  u32_to_fr_kernel<<<gx, 256, 0, s>>>(w.dims, d_mt + (size_t)m, (size_t)C_ * m);
+  u32_to_fr_kernel<<<gx, 256, 0, s>>>(w.es, d_mt + (size_t)(1 + C_) * m, (size_t)C_ * m);
+  u32_to_fr_kernel<<<gx, 256, 0, s>>>(w.ts, d_mt + (size_t)(1 + 2 * C_) * m, (size_t)C_ * m);
+  u32_to_fr_kernel<<<gx, 256, 0, s>>>(w.cts, d_st, (size_t)C_ * S);
+  count_launch(c, 4);
   CUDA_TRY(cudaGetLastError());
   return B200_OK;
 }

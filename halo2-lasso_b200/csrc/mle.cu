@@ -116,31 +116,35 @@ __global__ void __launch_bounds__(256) mle_dot_kernel(EvalManyArgs a) {
   }
 }
 
-int mle_eval_many(Ctx* c, const Fr* const* h_tables, int ntables, int n, const Fr* d_point, Fr* d_out) {
+int mle_dot_many(Ctx* c, const Fr* const* h_tables, int ntables, size_t len, const Fr* d_eq, Fr* d_out) {
   if (ntables < 1 || ntables > SC_MAX_TABLES) return B200_ERR_ARG;
-  cudaStream_t s = c->stream;
-  const size_t N = (size_t)1 << n;
-  Fr* eq = nullptr;
-  CUDA_TRY(cudaMallocAsync(&eq, N * sizeof(Fr), s));
-  int rc = eq_build(c, d_point, n, eq);
-  if (rc) return rc;
   EvalManyArgs a;
   for (int i = 0; i < ntables; ++i) a.tables[i] = h_tables[i];
-  a.eq = eq;
-  a.n = N;
+  a.eq = d_eq;
+  a.n = len;
   a.partial = c->d_partial;
   a.counter = &c->d_sc->counter;
   a.out = d_out;
-  int bx = (int)((N + 255) / 256);
+  int bx = (int)((len + 255) / 256);
   int cap = (4 * NUM_SMS + ntables - 1) / ntables;
   if (bx > cap) bx = cap;
   if (bx < 1) bx = 1;
   if ((size_t)bx * ntables > c->partial_elems) return B200_ERR_NOMEM;
-  CUDA_TRY(launch_pdl(mle_dot_kernel, dim3(dim3(bx, ntables)), dim3(256), 0, s, a));
+  CUDA_TRY(launch_pdl(mle_dot_kernel, dim3(dim3(bx, ntables)), dim3(256), 0, c->stream, a));
   count_launch(c);
-  CUDA_TRY(cudaFreeAsync(eq, s));
   CUDA_TRY(cudaGetLastError());
   return B200_OK;
+}
+
+int mle_eval_many(Ctx* c, const Fr* const* h_tables, int ntables, int n, const Fr* d_point, Fr* d_out) {
+  if (ntables < 1 || ntables > SC_MAX_TABLES) return B200_ERR_ARG;
+  const size_t N = (size_t)1 << n;
+  DevScope mem(c->stream);
+  Fr* eq = nullptr;
+  CUDA_TRY(mem.alloc(&eq, N * sizeof(Fr)));
+  int rc = eq_build(c, d_point, n, eq);
+  if (rc) return rc;
+  return mle_dot_many(c, h_tables, ntables, N, eq, d_out);
 }
 
 struct LincombArgs {

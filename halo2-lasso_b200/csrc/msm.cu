@@ -10,9 +10,11 @@
 //   3. scatter  : counting-sort the (point index, sign) pairs by bucket
 //   4. accumulate: one thread per TASK (<= TASK_LEN points of one bucket) sums with XYZZ mixed adds —
 //                 splitting heavy buckets keeps skewed scalars (Lasso counters) load-balanced
-//   5. buckets  : per-bucket sum of its task partials (warp-cooperative for heavy buckets)
-//   6. windows  : running-sum reduction Σ (k+1) B_k in groups, then a block-wide point sum
-//   7. finish   : Horner over windows (c doublings each) and projective -> affine
+//   5. buckets  : per-bucket sum of its task partials (one warp per heavy bucket)
+//   6. windows  : Σ (k+1) B_k without scalar multiplications: running sums over 8 buckets per thread, then two
+//                 warp-per-32-entries levels (suffix scan by shuffles) and a one-warp final combine per window
+//   7. finish   : one warp per commitment: windows shifted in parallel lanes, shuffle sum, projective -> affine;
+//                 derived commitments (linear combinations of other results of the batch) cost only doublings
 // Scalars with few significant bits (dims, counters, subtable values) only populate the windows they
 // need, which the reference cannot exploit. The group element is unique, so any schedule yields the
 // reference's commitment bytes.
@@ -20,10 +22,9 @@
 
 namespace b200 {
 
-static const int TASK_LEN = 64;       // minimum task length; a batch uses a power of two in [64, 1024] so that an
-                                      // average bucket splits into ~8 tasks (keeps the per-bucket reduction short at 2^22+)
+static const int TASK_LEN = 64;       // minimum task length; a batch uses a power of two in [64, 512]: about two tasks
+                                      // per resident thread of the accumulate grid
 static const int SEQ_TASKS = 8;     // buckets with more task partials than this go to the warp kernel
-static const int GROUP = 16;       // buckets per thread in the window reduction
 static const int MSM_MAX_JOBS = 64;
 static const int MSM_MAX_WINDOWS = 128;
 
@@ -39,7 +40,8 @@ struct MsmJobDev {
   int Wred;           // windows that need a bucket reduction (1 when precomp, else W)
   uint32_t bucket_base;
   uint64_t pair_base;
-  uint32_t group_base;  // first reduction group of this job
+  int map_p, map_g;     // map_g > 0: scalar i belongs to base point ((i >> p) << (p + g)) | (rank << p) | (i & (2^p - 1))
+  uint32_t map_rank;    // (the rank's slice of a polynomial sharded on the index bits [p, p + g), shard.cu)
   uint32_t win_base;    // first window slot of this job
 };
 struct MsmPlanDev {
@@ -150,7 +152,8 @@ __global__ void __launch_bounds__(256) msm_digits_kernel(MsmPlanDev plan, uint32
       if (gb == 0xffffffffu) continue;
       const uint32_t code = ranks[p + 1];
       // with precomputed tables the point of window w is entry i + w*n of the extended table
-      sorted[boff[gb] + (code & 0x7fffffffu)] = (jb.precomp ? i + (uint32_t)w * jb.ext_stride : i) | (code & 0x80000000u);
+      const uint32_t bi = jb.map_g ? ((((i >> jb.map_p) << jb.map_g) | jb.map_rank) << jb.map_p) | (i & ((1u << jb.map_p) - 1)) : i;
+      sorted[boff[gb] + (code & 0x7fffffffu)] = (jb.precomp ? bi + (uint32_t)w * jb.ext_stride : bi) | (code & 0x80000000u);
     }
   }
 }
@@ -331,91 +334,183 @@ __device__ __forceinline__ G1Xyzz warp_sum_xyzz(G1Xyzz acc) {
   return acc;  // valid in lane 0
 }
 
-// one CTA per heavy bucket: threads stride over the task partials, then warp + shared-memory reduction
+// one WARP per heavy bucket: lanes stride over the task partials, then a shuffle reduction
 __global__ void __launch_bounds__(128) msm_heavy_kernel(const uint32_t* __restrict__ toff,
                                                         const G1Xyzz* __restrict__ partial,
                                                         G1Xyzz* __restrict__ bucket_sum,
                                                         const uint32_t* __restrict__ heavy,
                                                         const uint32_t* __restrict__ heavy_count) {
-  __shared__ G1Xyzz sh[4];
-  const uint32_t nheavy = *heavy_count;
-  for (uint32_t h = blockIdx.x; h < nheavy; h += gridDim.x) {
+  const uint32_t nheavy = *heavy_count, lane = threadIdx.x & 31;
+  const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (uint32_t h = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; h < nheavy; h += nwarps) {
     const uint32_t gb = heavy[h];
     const uint32_t t0 = toff[gb], nt = toff[gb + 1] - t0;
     G1Xyzz acc = g1_identity();
-    for (uint32_t k = threadIdx.x; k < nt; k += blockDim.x) acc = g1_add(acc, ld_xyzz(partial + t0 + k));
+    for (uint32_t k = lane; k < nt; k += 32) acc = g1_add(acc, ld_xyzz(partial + t0 + k));
     acc = warp_sum_xyzz(acc);
-    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      for (int k = 1; k < 4; ++k) acc = g1_add(acc, sh[k]);
-      st_xyzz(bucket_sum + gb, acc);
-    }
-    __syncthreads();
+    if (lane == 0) st_xyzz(bucket_sum + gb, acc);
   }
 }
 
 // ---- window reduction ----------------------------------------------------------------------------
-// thread per group of GROUP buckets: C_g = Σ_{k in group} (k+1) B_k   (k = bucket index inside window)
-__global__ void __launch_bounds__(128) msm_group_kernel(MsmPlanDev plan, uint32_t ngroups,
-                                                        const G1Xyzz* __restrict__ bucket_sum,
-                                                        G1Xyzz* __restrict__ group_sum) {
+// S_w = Σ_k (k+1) B_k over the B buckets of a window, without any scalar multiplication. Write
+// k = lo + 8 (l1 + 32 (l2 + 32 l3)); then  k + 1 = (lo + 1) + 8 l1 + 256 l2 + 8192 l3  and
+//   S_w = Σ Y + 8 (Σ A + 32 (Σ Bq + 32 C)),   Y = Σ_lo (lo+1) B,  A = Σ l1 R1,  Bq = Σ l2 R2,  C = Σ l3 R3,
+// where R1 / R2 / R3 are the plain sums of 8 / 256 / 8192 consecutive buckets. Four launches:
+//   l0   : one THREAD per 8 buckets, running sums (16 dependent additions)          -> R1, Y1
+//   tree : one WARP per 32 entries: suffix scan by shuffles (Σ l R_l = Σ_{l>=1} suffix_l, 10 add steps) and plain
+//          shuffle sums of the carried streams                                        -> R2, A2, Y2 ; R3, Bq3, A3, Y3
+//   final: one warp per window: the last weighted sum, the stream totals and 13 doublings
+// All windows of all jobs of the batch go through the same launches (the reference reduces each window with a serial
+// running sum, msm.rs:160-181; the group element is the same).
+static const int L0 = 8;
+struct MsmRedDesc {       // per reduction window (device arrays, nwin + 1 prefix entries where noted)
+  const uint32_t* wb;     // first bucket of the window
+  const uint32_t* wB;     // buckets in the window
+  const uint32_t* off1;   // prefix of level-1 entries (groups of 8 buckets)
+  const uint32_t* off2;   // prefix of level-2 entries (32 level-1 entries each)
+  const uint32_t* off3;   // prefix of level-3 entries
+  uint32_t nwin;
+};
+__device__ __forceinline__ uint32_t seg_of(const uint32_t* __restrict__ off, uint32_t n, uint32_t key) {
+  return upper_bound_u32(off, n + 1, key);  // off[seg] <= key < off[seg + 1] (empty segments never match: sizes >= 1)
+}
+
+__global__ void __launch_bounds__(128) msm_red_l0_kernel(MsmRedDesc d, uint32_t n1tot,
+                                                         const G1Xyzz* __restrict__ bucket_sum,
+                                                         G1Xyzz* __restrict__ R1, G1Xyzz* __restrict__ Y1) {
   const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
-  if (g >= ngroups) return;
-  int j = 0;
-  while (j + 1 < plan.J && plan.job[j + 1].group_base <= g) ++j;
-  const MsmJobDev& jb = plan.job[j];
-  const uint32_t gpw = (jb.B + GROUP - 1) / GROUP;  // groups per window
-  const uint32_t local = g - jb.group_base;
-  const uint32_t w = local / gpw, gi = local % gpw;
-  const uint32_t k0 = gi * GROUP;
-  const uint32_t k1 = k0 + GROUP < jb.B ? k0 + GROUP : jb.B;
-  const G1Xyzz* b = bucket_sum + jb.bucket_base + w * jb.B;
+  if (g >= n1tot) return;
+  const uint32_t w = seg_of(d.off1, d.nwin, g);
+  const uint32_t B = d.wB[w], k0 = (g - d.off1[w]) * L0;
+  const uint32_t k1 = k0 + L0 < B ? k0 + L0 : B;
+  const G1Xyzz* b = bucket_sum + d.wb[w];
   G1Xyzz run = g1_identity(), wsum = g1_identity();
   for (uint32_t k = k1; k-- > k0;) {
     run = g1_add(run, ld_xyzz(b + k));
     wsum = g1_add(wsum, run);
   }
-  // wsum = Σ (k - k0 + 1) B_k ; add k0 * Σ B_k
-  if (k0) wsum = g1_add(wsum, g1_mul_small(run, k0));
-  st_xyzz(group_sum + g, wsum);
+  st_xyzz(R1 + g, run);
+  st_xyzz(Y1 + g, wsum);  // Σ (k - k0 + 1) B_k
 }
 
-// CTA per (job, window): sum its groups
-__global__ void __launch_bounds__(128) msm_window_kernel(MsmPlanDev plan, const G1Xyzz* __restrict__ group_sum,
-                                                         G1Xyzz* __restrict__ window_sum) {
-  __shared__ G1Xyzz sh[4];
-  const uint32_t slot = blockIdx.x;
-  int j = 0;
-  while (j + 1 < plan.J && plan.job[j + 1].win_base <= slot) ++j;
-  const MsmJobDev& jb = plan.job[j];
-  const uint32_t w = slot - jb.win_base;
-  const uint32_t gpw = (jb.B + GROUP - 1) / GROUP;
-  const G1Xyzz* g = group_sum + jb.group_base + w * gpw;
+__device__ __forceinline__ G1Xyzz shfl_xyzz(const G1Xyzz& p, int src) {
+  G1Xyzz r;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    r.x.v[i] = __shfl_sync(0xffffffffu, p.x.v[i], src);
+    r.y.v[i] = __shfl_sync(0xffffffffu, p.y.v[i], src);
+    r.zz.v[i] = __shfl_sync(0xffffffffu, p.zz.v[i], src);
+    r.zzz.v[i] = __shfl_sync(0xffffffffu, p.zzz.v[i], src);
+  }
+  return r;
+}
+// lane l holds x_l: returns (in lane 0) plain = Σ_l x_l and weighted = Σ_l l x_l
+__device__ __forceinline__ void warp_weighted_sum(G1Xyzz x, G1Xyzz& plain, G1Xyzz& weighted) {
+  const int lane = threadIdx.x & 31;
+  // inclusive suffix scan: x_l <- Σ_{j >= l} x_j
+  for (int off = 1; off < 32; off <<= 1) {
+    const G1Xyzz o = shfl_down_xyzz(x, off);
+    if (lane + off < 32) x = g1_add(x, o);
+  }
+  plain = x;  // lane 0: the total
+  G1Xyzz s = lane >= 1 ? x : g1_identity();
+  weighted = warp_sum_xyzz(s);
+}
+
+// One warp per 32 consecutive entries of a window at level LV (1 or 2). Streams in: R (weighted), P[0..NP) plain.
+// Streams out: R', Wt' (= Σ l R_l) and the NP plain sums.
+template <int NP>
+__global__ void __launch_bounds__(128) msm_red_tree_kernel(MsmRedDesc d, int lv, uint32_t nout_tot,
+                                                           const G1Xyzz* __restrict__ in, uint32_t nin_tot,
+                                                           G1Xyzz* __restrict__ out) {
+  const uint32_t wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (wid >= nout_tot) return;
+  const uint32_t* offo = lv == 1 ? d.off2 : d.off3;
+  const uint32_t* offi = lv == 1 ? d.off1 : d.off2;
+  const uint32_t w = seg_of(offo, d.nwin, wid);
+  const uint32_t i0 = offi[w] + (wid - offo[w]) * 32, iend = offi[w + 1];
+  const bool valid = i0 + lane < iend;
+  G1Xyzz plain, wt;
+  warp_weighted_sum(valid ? ld_xyzz(in + i0 + lane) : g1_identity(), plain, wt);
+  if (lane == 0) {
+    st_xyzz(out + wid, plain);
+    st_xyzz(out + nout_tot + wid, wt);
+  }
+#pragma unroll
+  for (int s = 0; s < NP; ++s) {
+    const G1Xyzz v = warp_sum_xyzz(valid ? ld_xyzz(in + (size_t)(1 + s) * nin_tot + i0 + lane) : g1_identity());
+    if (lane == 0) st_xyzz(out + (size_t)(2 + s) * nout_tot + wid, v);
+  }
+}
+
+// One warp per window: level-3 streams R3, Bq3, A3, Y3 (<= 32 entries each) -> S_w
+__global__ void __launch_bounds__(128) msm_red_final_kernel(MsmRedDesc d, const G1Xyzz* __restrict__ in, uint32_t n3tot,
+                                                            G1Xyzz* __restrict__ window_sum) {
+  const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (w >= d.nwin) return;
+  const uint32_t i0 = d.off3[w], n = d.off3[w + 1] - i0;
+  const bool valid = lane < n;
+  G1Xyzz r3, c;
+  warp_weighted_sum(valid ? ld_xyzz(in + i0 + lane) : g1_identity(), r3, c);
+  const G1Xyzz bq = warp_sum_xyzz(valid ? ld_xyzz(in + (size_t)1 * n3tot + i0 + lane) : g1_identity());
+  const G1Xyzz a = warp_sum_xyzz(valid ? ld_xyzz(in + (size_t)2 * n3tot + i0 + lane) : g1_identity());
+  const G1Xyzz y = warp_sum_xyzz(valid ? ld_xyzz(in + (size_t)3 * n3tot + i0 + lane) : g1_identity());
+  if (lane == 0) {
+    G1Xyzz acc = c;
+    for (int k = 0; k < 5; ++k) acc = g1_dbl(acc);
+    acc = g1_add(acc, bq);
+    for (int k = 0; k < 5; ++k) acc = g1_dbl(acc);
+    acc = g1_add(acc, a);
+    for (int k = 0; k < 3; ++k) acc = g1_dbl(acc);
+    acc = g1_add(acc, y);
+    st_xyzz(window_sum + w, acc);
+  }
+}
+
+// Derived results: out[J + i] = Σ_t 2^(shift t) * result(src[t]) — commitments that are linear combinations of other
+// commitments of the same batch (Lasso: a = Σ_t 2^(w t) E_t) cost a few doublings instead of an MSM.
+struct MsmDeriveDev {
+  int n;
+  struct {
+    int nsrc, shift, src[8];
+  } d[4];
+};
+
+// warp per job (or derived result): lane w folds the windows w, w + 32, ... (Horner), shifts by w * c doublings,
+// the lanes are summed by shuffles and lane 0 normalises. Warps >= J handle the derived results.
+__global__ void __launch_bounds__(32) msm_finish_kernel(MsmPlanDev plan, MsmDeriveDev dv,
+                                                        const G1Xyzz* __restrict__ window_sum, G1Aff* __restrict__ out) {
+  const int j = blockIdx.x, lane = threadIdx.x;
   G1Xyzz acc = g1_identity();
-  for (uint32_t k = threadIdx.x; k < gpw; k += blockDim.x) acc = g1_add(acc, ld_xyzz(g + k));
+  if (j < plan.J) {
+    const MsmJobDev& jb = plan.job[j];
+    int top = -1;
+    for (int w = lane; w < jb.Wred; w += 32) top = w;
+    for (int w = top; w >= 0; w -= 32) {  // Σ_i 2^(32 c i) S_{lane + 32 i}
+      if (w != top)
+        for (int k = 0; k < 32 * jb.c; ++k) acc = g1_dbl(acc);
+      acc = g1_add(acc, ld_xyzz(window_sum + jb.win_base + w));
+    }
+    if (jb.Wred > 1)
+      for (int k = 0; k < lane * jb.c; ++k) acc = g1_dbl(acc);
+  } else {
+    const auto& d = dv.d[j - plan.J];
+    if (lane < d.nsrc) {  // sources are single-window jobs or short Horner chains: recomputed by this lane
+      const MsmJobDev& jb = plan.job[d.src[lane]];
+      for (int w = jb.Wred - 1; w >= 0; --w) {
+        for (int k = 0; k < jb.c; ++k) acc = g1_dbl(acc);
+        acc = g1_add(acc, ld_xyzz(window_sum + jb.win_base + w));
+      }
+      for (int k = 0; k < lane * d.shift; ++k) acc = g1_dbl(acc);
+    }
+  }
   acc = warp_sum_xyzz(acc);
-  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    for (int k = 1; k < 4; ++k) acc = g1_add(acc, sh[k]);
-    st_xyzz(window_sum + slot, acc);
+  if (lane == 0) {
+    const G1Aff a = g1_to_affine(acc);
+    fe_st(&out[j].x, a.x);
+    fe_st(&out[j].y, a.y);
   }
-}
-
-// thread per job: Horner over windows, then affine
-__global__ void msm_finish_kernel(MsmPlanDev plan, const G1Xyzz* __restrict__ window_sum, G1Aff* __restrict__ out) {
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= plan.J) return;
-  const MsmJobDev& jb = plan.job[j];
-  G1Xyzz acc = g1_identity();
-  for (int w = jb.Wred - 1; w >= 0; --w) {
-    for (int k = 0; k < jb.c; ++k) acc = g1_dbl(acc);
-    acc = g1_add(acc, ld_xyzz(window_sum + jb.win_base + w));
-  }
-  const G1Aff a = g1_to_affine(acc);
-  fe_st(&out[j].x, a.x);
-  fe_st(&out[j].y, a.y);
 }
 
 static int ilog2_floor(uint64_t n) {
@@ -424,13 +519,15 @@ static int ilog2_floor(uint64_t n) {
   return k;
 }
 
-int msm_batch(Ctx* c, const MsmJob* jobs, int J, G1Aff* d_out) {
-  if (J < 1 || J > MSM_MAX_JOBS) return B200_ERR_ARG;
+int msm_batch(Ctx* c, const MsmJob* jobs, int J, G1Aff* d_out, const MsmDerive* derive, int nderive) {
+  if (J < 1 || J > MSM_MAX_JOBS || nderive < 0 || nderive > 4) return B200_ERR_ARG;
   cudaStream_t s = c->stream;
   MsmPlanDev plan;
   plan.J = J;
   uint64_t pairs = 0;
-  uint32_t nbuckets = 0, ngroups = 0, nwin = 0, max_n = 0;
+  uint32_t nbuckets = 0, nwin = 0, max_n = 0;
+  std::vector<uint32_t> desc;  // wb | wB | off1 | off2 | off3, each nwin (+1 for the prefixes)
+  std::vector<uint32_t> wb, wB;
   for (int j = 0; j < J; ++j) {
     const MsmJob& in = jobs[j];
     if (in.n == 0 || in.n > (1u << 30) || in.bits < 1 || in.bits > 256) return B200_ERR_ARG;
@@ -439,6 +536,9 @@ int msm_batch(Ctx* c, const MsmJob* jobs, int J, G1Aff* d_out) {
     jb.bases = in.bases;
     jb.n = (uint32_t)in.n;
     jb.kind = in.kind;
+    jb.map_p = in.map_p;
+    jb.map_g = in.map_g;
+    jb.map_rank = (uint32_t)in.map_rank;
     const int need = in.bits + 1;  // signed digits may carry one bit past the top
     jb.precomp = (in.ext != nullptr && in.bits > 2 * EXT_C + 2) ? 1 : 0;
     jb.ext_stride = (uint32_t)(in.ext_stride ? in.ext_stride : in.n);
@@ -461,34 +561,75 @@ int msm_batch(Ctx* c, const MsmJob* jobs, int J, G1Aff* d_out) {
     jb.B = 1u << (jb.c - 1);
     jb.bucket_base = nbuckets;
     jb.pair_base = pairs;
-    jb.group_base = ngroups;
     jb.win_base = nwin;
+    for (int w = 0; w < jb.Wred; ++w) {
+      wb.push_back(nbuckets + (uint32_t)w * jb.B);
+      wB.push_back(jb.B);
+    }
     nbuckets += jb.B * jb.Wred;
     pairs += (uint64_t)jb.n * jb.W;
-    ngroups += ((jb.B + GROUP - 1) / GROUP) * jb.Wred;
     nwin += jb.Wred;
     if (jb.n > max_n) max_n = jb.n;
   }
   if (pairs >= (1ull << 31)) return B200_ERR_ARG;
+  MsmDeriveDev dv;
+  dv.n = nderive;
+  for (int i = 0; i < nderive; ++i) {
+    if (derive[i].nsrc < 1 || derive[i].nsrc > 8 || derive[i].shift < 0 || derive[i].shift > 32) return B200_ERR_ARG;
+    dv.d[i].nsrc = derive[i].nsrc;
+    dv.d[i].shift = derive[i].shift;
+    for (int t = 0; t < derive[i].nsrc; ++t) {
+      if (derive[i].src[t] < 0 || derive[i].src[t] >= J) return B200_ERR_ARG;
+      dv.d[i].src[t] = derive[i].src[t];
+    }
+  }
+  // task length: about two tasks per resident thread of the accumulate grid (148 x 16 x 128), within [64, 512]
   uint32_t task_len = TASK_LEN;
-  while (task_len < 1024 && (uint64_t)task_len * 8 * nbuckets < pairs) task_len <<= 1;
+  while (task_len < 512 && (uint64_t)task_len * 2 * NUM_SMS * 16 * 128 < pairs) task_len <<= 1;
   plan.task_len = task_len;
   const uint32_t max_tasks = nbuckets + (uint32_t)(pairs / task_len) + 1;
   const uint32_t scan_blocks = (nbuckets + 1023) / 1024;
+  // reduction levels (see msm_red_*): entries per window at level 1 / 2 / 3
+  std::vector<uint32_t> off1(nwin + 1, 0), off2(nwin + 1, 0), off3(nwin + 1, 0);
+  for (uint32_t w = 0; w < nwin; ++w) {
+    const uint32_t n1 = (wB[w] + L0 - 1) / L0, n2 = (n1 + 31) / 32, n3 = (n2 + 31) / 32;
+    if (n3 > 32) return B200_ERR_ARG;
+    off1[w + 1] = off1[w] + n1;
+    off2[w + 1] = off2[w] + n2;
+    off3[w + 1] = off3[w] + n3;
+  }
+  const uint32_t n1tot = off1[nwin], n2tot = off2[nwin], n3tot = off3[nwin];
+  desc.insert(desc.end(), wb.begin(), wb.end());
+  desc.insert(desc.end(), wB.begin(), wB.end());
+  desc.insert(desc.end(), off1.begin(), off1.end());
+  desc.insert(desc.end(), off2.begin(), off2.end());
+  desc.insert(desc.end(), off3.begin(), off3.end());
 
-  uint32_t *cnt, *boff, *toff, *ranks, *sorted, *scratch, *heavy, *heavy_count;
-  G1Xyzz *partial, *bucket_sum, *group_sum, *window_sum;
-  CUDA_TRY(cudaMallocAsync(&cnt, (size_t)nbuckets * 4, s));
-  CUDA_TRY(cudaMallocAsync(&boff, ((size_t)nbuckets + 1) * 4, s));
-  CUDA_TRY(cudaMallocAsync(&toff, ((size_t)nbuckets + 1) * 4, s));
-  CUDA_TRY(cudaMallocAsync(&ranks, (size_t)pairs * 8, s));
-  CUDA_TRY(cudaMallocAsync(&sorted, (size_t)pairs * 4 + 4, s));
-  CUDA_TRY(cudaMallocAsync(&scratch, ((size_t)scan_blocks + 8) * 4, s));
-  CUDA_TRY(cudaMallocAsync(&heavy, ((size_t)nbuckets + 1) * 4, s));
-  CUDA_TRY(cudaMallocAsync(&partial, (size_t)max_tasks * sizeof(G1Xyzz), s));
-  CUDA_TRY(cudaMallocAsync(&bucket_sum, (size_t)nbuckets * sizeof(G1Xyzz), s));
-  CUDA_TRY(cudaMallocAsync(&group_sum, (size_t)ngroups * sizeof(G1Xyzz), s));
-  CUDA_TRY(cudaMallocAsync(&window_sum, (size_t)nwin * sizeof(G1Xyzz), s));
+  DevScope mem(s);
+  uint32_t *cnt, *boff, *toff, *ranks, *sorted, *scratch, *heavy, *heavy_count, *d_desc;
+  G1Xyzz *partial, *bucket_sum, *lvl1, *lvl2, *lvl3, *window_sum;
+  CUDA_TRY(mem.alloc(&cnt, (size_t)nbuckets * 4));
+  CUDA_TRY(mem.alloc(&boff, ((size_t)nbuckets + 1) * 4));
+  CUDA_TRY(mem.alloc(&toff, ((size_t)nbuckets + 1) * 4));
+  CUDA_TRY(mem.alloc(&ranks, (size_t)pairs * 8));
+  CUDA_TRY(mem.alloc(&sorted, (size_t)pairs * 4 + 4));
+  CUDA_TRY(mem.alloc(&scratch, ((size_t)scan_blocks + 8) * 4));
+  CUDA_TRY(mem.alloc(&heavy, ((size_t)nbuckets + 1) * 4));
+  CUDA_TRY(mem.alloc(&partial, (size_t)max_tasks * sizeof(G1Xyzz)));
+  CUDA_TRY(mem.alloc(&bucket_sum, (size_t)nbuckets * sizeof(G1Xyzz)));
+  CUDA_TRY(mem.alloc(&lvl1, (size_t)2 * n1tot * sizeof(G1Xyzz)));
+  CUDA_TRY(mem.alloc(&lvl2, (size_t)3 * n2tot * sizeof(G1Xyzz)));
+  CUDA_TRY(mem.alloc(&lvl3, (size_t)4 * n3tot * sizeof(G1Xyzz)));
+  CUDA_TRY(mem.alloc(&window_sum, (size_t)nwin * sizeof(G1Xyzz)));
+  CUDA_TRY(mem.alloc(&d_desc, desc.size() * 4));
+  CUDA_TRY(cudaMemcpyAsync(d_desc, desc.data(), desc.size() * 4, cudaMemcpyHostToDevice, s));
+  MsmRedDesc rd;
+  rd.wb = d_desc;
+  rd.wB = d_desc + nwin;
+  rd.off1 = d_desc + 2 * nwin;
+  rd.off2 = rd.off1 + nwin + 1;
+  rd.off3 = rd.off2 + nwin + 1;
+  rd.nwin = nwin;
   heavy_count = scratch + scan_blocks + 4;
   CUDA_TRY(cudaMemsetAsync(cnt, 0, (size_t)nbuckets * 4, s));
   CUDA_TRY(cudaMemsetAsync(heavy_count, 0, 4, s));
@@ -509,16 +650,15 @@ int msm_batch(Ctx* c, const MsmJob* jobs, int J, G1Aff* d_out) {
   prof_end(c, pi);
   pi = prof_begin(c, PH_MSM_REDUCE);
   msm_bucket_kernel<<<(nbuckets + 127) / 128, 128, 0, s>>>(nbuckets, toff, partial, bucket_sum, heavy, heavy_count);
-  msm_heavy_kernel<<<NUM_SMS * 4, 128, 0, s>>>(toff, partial, bucket_sum, heavy, heavy_count);
-  msm_group_kernel<<<(ngroups + 127) / 128, 128, 0, s>>>(plan, ngroups, bucket_sum, group_sum);
-  msm_window_kernel<<<nwin, 128, 0, s>>>(plan, group_sum, window_sum);
-  msm_finish_kernel<<<(J + 31) / 32, 32, 0, s>>>(plan, window_sum, d_out);
+  msm_heavy_kernel<<<NUM_SMS * 8, 128, 0, s>>>(toff, partial, bucket_sum, heavy, heavy_count);
+  msm_red_l0_kernel<<<(n1tot + 127) / 128, 128, 0, s>>>(rd, n1tot, bucket_sum, lvl1, lvl1 + n1tot);
+  msm_red_tree_kernel<1><<<(n2tot + 3) / 4, 128, 0, s>>>(rd, 1, n2tot, lvl1, n1tot, lvl2);
+  msm_red_tree_kernel<2><<<(n3tot + 3) / 4, 128, 0, s>>>(rd, 2, n3tot, lvl2, n2tot, lvl3);
+  msm_red_final_kernel<<<(nwin + 3) / 4, 128, 0, s>>>(rd, lvl3, n3tot, window_sum);
+  msm_finish_kernel<<<J + nderive, 32, 0, s>>>(plan, dv, window_sum, d_out);
   prof_end(c, pi);
-  count_launch(c, 7);
+  count_launch(c, 10);
   CUDA_TRY(cudaGetLastError());
-  for (void* p : {(void*)cnt, (void*)boff, (void*)toff, (void*)ranks, (void*)sorted, (void*)scratch, (void*)heavy,
-                  (void*)partial, (void*)bucket_sum, (void*)group_sum, (void*)window_sum})
-    CUDA_TRY(cudaFreeAsync(p, s));
   return B200_OK;
 }
 

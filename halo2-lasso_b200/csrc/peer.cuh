@@ -1,80 +1,102 @@
-// Peer-memory collectives for the hypercube-sharded sum-check and the point-sharded MSM.
-// Every rank owns a small MAILBOX in its own HBM; all ranks map all mailboxes through CUDA IPC (NVLink 5 /
-// NVSwitch P2P). A collective is executed INSIDE the compute kernel by one warp of its last CTA:
-//   write my values into slot[my_rank] of every peer's mailbox  ->  __threadfence_system()  ->  publish the
-//   sequence number  ->  spin until every slot of MY mailbox carries that sequence number  ->  read.
-// Payloads are a few field elements (<= 192 B per round message), so this is latency- not bandwidth-bound;
-// fusing it into the round kernel removes the NCCL launch and the extra kernel a host-driven all-gather
-// would need. Slots are double-buffered on the parity of the sequence number: a rank can be at most one
-// collective ahead of any peer (it needs that peer's data to finish the current one).
+// Peer-memory collectives for the sharded provers. One process (or, in tests, one context) per
+// GPU; every rank owns a MAILBOX and a bulk ARENA in its own HBM and maps those of all peers (CUDA IPC over NVLink 5 /
+// NVSwitch; plain device pointers when several contexts share one GPU). Collectives run INSIDE the compute kernels:
+//
+//  * small messages (round partials, evaluations, commitments; <= 72 field elements): the NCCL-LL idea — every 32-bit
+//    word travels in one 8-byte store together with the collective's sequence number, so data and flag arrive
+//    atomically: no fence, no separate flag store, the reader polls the words themselves. One NVLink one-way latency.
+//  * bulk all-gathers (bound sum-check tables, tree layers): the producing kernel stores straight into every peer's
+//    arena (posted NVLink writes), its last CTA publishes a per-source sequence number with a release store and waits
+//    for the other sources with acquire loads.
+//
+// Both are double-buffered on the parity of their sequence number: a rank can be at most one collective ahead of any
+// peer (it needs that peer's contribution to finish the current one). Every wait is BOUNDED: after `timeout_ns` the
+// waiter raises *err (surfaced as B200_ERR_PEER) and carries on with garbage instead of hanging the GPU.
 #pragma once
 #include "ff32.cuh"
 
 namespace b200 {
 
 static const int PEER_MAX_WORLD = 8;
-static const int PEER_MAX_VALS = 72;  // field elements per message
+static const int PEER_MAX_VALS = 72;  // field elements per small message
 
-struct MailSlot {
-  unsigned int seq[2];
-  unsigned int pad[6];
-  Fr data[2][PEER_MAX_VALS];
-};
 struct Mailbox {
-  MailSlot slot[PEER_MAX_WORLD];  // indexed by SOURCE rank
+  unsigned long long ll[2][PEER_MAX_WORLD][PEER_MAX_VALS * 8];  // [parity][SOURCE rank][word]: data | seq << 32
+  unsigned int bulk_seq[PEER_MAX_WORLD];                         // [SOURCE rank]: last bulk all-gather it has pushed
+  unsigned int pad[8];
 };
 struct PeerCtx {
   int rank, world;
-  Mailbox* box[PEER_MAX_WORLD];  // box[r] = rank r's mailbox as mapped in this process (box[rank] is local)
+  Mailbox* box[PEER_MAX_WORLD];        // box[r] = rank r's mailbox as mapped here (box[rank] is local)
+  unsigned char* arena[PEER_MAX_WORLD];  // arena[r] = rank r's bulk arena (2 halves of arena_half bytes)
+  unsigned long long arena_half;
+  unsigned long long timeout_ns;
+  unsigned int* err;  // local device word, set to 1 when a wait timed out
 };
 
 #if defined(__CUDACC__)
-__device__ __forceinline__ void st_sys_fr(Fr* p, const Fr& v) {
-  volatile uint32_t* q = reinterpret_cast<volatile uint32_t*>(p);
-#pragma unroll
-  for (int i = 0; i < 8; ++i) q[i] = v.v[i];
+__device__ __forceinline__ unsigned long long peer_now_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
 }
-__device__ __forceinline__ Fr ld_sys_fr(const Fr* p) {
-  const volatile uint32_t* q = reinterpret_cast<const volatile uint32_t*>(p);
-  Fr r;
-#pragma unroll
-  for (int i = 0; i < 8; ++i) r.v[i] = q[i];
-  return r;
+__device__ __forceinline__ void st_sys_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_sys_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
 }
 
-// All-gather `cnt` (<= 32) field elements per rank. Called by ALL 32 lanes of one warp; lane i < cnt
-// contributes `mine`. Afterwards lane i < cnt calls peer_read(pc, seq, r, i) for each source rank r.
+// All-gather of `cnt` (<= PEER_MAX_VALS) field elements per rank. Lane / thread i < cnt calls peer_put with its value
+// (no waiting: posted stores to every rank, itself included), then anybody calls peer_get(src, idx), which spins until
+// the 8 words of that element carry `seq`.
+__device__ __forceinline__ void peer_put(const PeerCtx& pc, unsigned int seq, int idx, const Fr& v) {
+  const int par = seq & 1;
+  for (int r = 0; r < pc.world; ++r) {
+    unsigned long long* dst = &pc.box[r]->ll[par][pc.rank][idx * 8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) st_sys_u64(dst + i, (unsigned long long)v.v[i] | ((unsigned long long)seq << 32));
+  }
+}
+__device__ __forceinline__ Fr peer_get(const PeerCtx& pc, unsigned int seq, int src, int idx) {
+  const unsigned long long* p = &pc.box[pc.rank]->ll[seq & 1][src][idx * 8];
+  Fr r;
+  unsigned long long t0 = 0;
+  unsigned int spins = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    unsigned long long w = ld_sys_u64(p + i);
+    while ((unsigned int)(w >> 32) != seq) {
+      if ((++spins & 1023u) == 0) {
+        const unsigned long long now = peer_now_ns();
+        if (!t0) t0 = now;
+        else if (now - t0 > pc.timeout_ns) {
+          *pc.err = 1;
+          break;
+        }
+      }
+      w = ld_sys_u64(p + i);
+    }
+    r.v[i] = (uint32_t)w;
+  }
+  return r;
+}
+// Compatibility wrappers for warp-level callers: lanes < cnt contribute `mine`
 __device__ __forceinline__ void peer_publish(const PeerCtx& pc, unsigned int seq, const Fr& mine, int cnt) {
   const int lane = threadIdx.x & 31;
-  const int par = seq & 1;
-  if (lane < cnt) {
-    for (int r = 0; r < pc.world; ++r) st_sys_fr(&pc.box[r]->slot[pc.rank].data[par][lane], mine);
-  }
-  // release: the payload stores of all lanes (ordered before the flag stores by the warp barrier) become visible
-  // to a peer before the sequence number does; one acquire fence after the poll on the reading side.
-  // Measured (tools/micro/): 7 us per collective at 2 GPUs and 11 us at 4 inside one long-running kernel; in the
-  // one-process-per-GPU prover 11 / 15 / 77 us per round at 2 / 4 / 8 GPUs with peer_spin_while below.
-  __syncwarp();
-  if (lane < pc.world) {
-    unsigned int* f = &pc.box[lane]->slot[pc.rank].seq[par];
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(f), "r"(seq) : "memory");
-  }
-  // wait for every source rank (lane r polls source r in MY mailbox), then acquire once
-  if (lane < pc.world) {
-    const unsigned int* f = &pc.box[pc.rank]->slot[lane].seq[par];
-    unsigned int v;
-    do {
-      asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
-    } while (v != seq);
-    asm volatile("fence.acq_rel.sys;" ::: "memory");
-  }
-  __syncwarp();
+  if (lane < cnt) peer_put(pc, seq, lane, mine);
 }
+__device__ __forceinline__ Fr peer_read(const PeerCtx& pc, unsigned int seq, int src, int idx) {
+  return peer_get(pc, seq, src, idx);
+}
+
 // Keep-busy helper. A GPU whose only activity is one warp polling NVLink-written memory drops into a low-activity
 // state in which the code that FOLLOWS the wait runs ~10x slower for ~120 us (measured at 4 and 8 GPUs, one
-// process per GPU: 125 us per collective instead of 11-15). Warps 1..3 of the CTA (one per other SM
-// sub-partition) therefore issue arithmetic while warp 0 runs the exchange: they call peer_spin_while(flag) after a
-// barrier that publishes *flag = 1, warp 0 clears the flag when it is done.
+// process per GPU). Warps 1..3 of the CTA (one per other SM sub-partition) therefore issue arithmetic
+// while warp 0 runs the exchange: they call peer_spin_while(flag) after a barrier that publishes *flag = 1, warp 0
+// clears the flag when it is done.
 __device__ __forceinline__ void peer_spin_while(volatile int* flag, unsigned int* sink) {
   float x = (float)threadIdx.x;
   while (*flag) {
@@ -83,8 +105,36 @@ __device__ __forceinline__ void peer_spin_while(volatile int* flag, unsigned int
   }
   if (x == 12345.678f) *sink = 0;  // keeps the loop alive
 }
-__device__ __forceinline__ Fr peer_read(const PeerCtx& pc, unsigned int seq, int src, int idx) {
-  return ld_sys_fr(&pc.box[pc.rank]->slot[src].data[seq & 1][idx]);
+
+// ---- bulk all-gather ---------------------------------------------------------------------------------------------
+// peer_bulk_dst: where element `idx` of the gathered buffer lives in rank r's arena for collective `bseq`.
+__device__ __forceinline__ Fr* peer_bulk_dst(const PeerCtx& pc, unsigned int bseq, int r, size_t idx) {
+  return reinterpret_cast<Fr*>(pc.arena[r] + (size_t)(bseq & 1) * pc.arena_half) + idx;
+}
+// Called by ONE warp of the last CTA of the pushing kernel, after every CTA's stores were fenced with
+// __threadfence_system() and counted through the ticket: publish my sequence number everywhere, wait for all sources.
+__device__ __forceinline__ void peer_bulk_commit_and_wait(const PeerCtx& pc, unsigned int bseq) {
+  const int lane = threadIdx.x & 31;
+  if (lane < pc.world) {
+    unsigned int* f = &pc.box[lane]->bulk_seq[pc.rank];
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(f), "r"(bseq) : "memory");
+    const unsigned int* g = &pc.box[pc.rank]->bulk_seq[lane];
+    unsigned int v, spins = 0;
+    unsigned long long t0 = 0;
+    for (;;) {
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(g) : "memory");
+      if ((int)(v - bseq) >= 0) break;
+      if ((++spins & 1023u) == 0) {
+        const unsigned long long now = peer_now_ns();
+        if (!t0) t0 = now;
+        else if (now - t0 > pc.timeout_ns) {
+          *pc.err = 1;
+          break;
+        }
+      }
+    }
+  }
+  __syncwarp();
 }
 #endif
 

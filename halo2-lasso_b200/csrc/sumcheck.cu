@@ -401,11 +401,14 @@ int sumcheck_prove_evals(Ctx* c, const ScEvalJob& job) {
   // scratch: eq table (N) + ping-pong halves for eq and every table
   const size_t szA = N / 2, szB = N / 4 ? N / 4 : 1;
   Fr *eq0 = nullptr, *bufA = nullptr, *bufB = nullptr;
-  CUDA_TRY(cudaMallocAsync(&bufA, (size_t)(ntab + 1) * szA * sizeof(Fr), s));
-  CUDA_TRY(cudaMallocAsync(&bufB, (size_t)(ntab + 1) * szB * sizeof(Fr), s));
+  if ((job.stop_after > 0) != (job.carry != nullptr) || job.stop_after > n) return B200_ERR_ARG;
+  DevScope own(s);
+  DevScope& mem = job.carry ? *job.carry->scope : own;
+  CUDA_TRY(mem.alloc(&bufA, (size_t)(ntab + 1) * szA * sizeof(Fr)));
+  CUDA_TRY(mem.alloc(&bufB, (size_t)(ntab + 1) * szB * sizeof(Fr)));
   int rc;
   if (!job.eq_table) {
-    CUDA_TRY(cudaMallocAsync(&eq0, N * sizeof(Fr), s));
+    CUDA_TRY(mem.alloc(&eq0, N * sizeof(Fr)));
     rc = eq_build(c, job.eq_point, n, eq0);
     if (rc) return rc;
     if (job.eq_scale) {
@@ -431,7 +434,8 @@ int sumcheck_prove_evals(Ctx* c, const ScEvalJob& job) {
   for (int i = 0; i < ntab; ++i) cur[i] = job.tables[i];
   cur[ntab] = job.eq_table ? job.eq_table : eq0;
   bool tail_done = false;
-  for (int round = 0; round < n; ++round) {
+  const int nrounds = job.stop_after > 0 ? job.stop_after : n;
+  for (int round = 0; round < nrounds; ++round) {
     a.round = round;
     a.pairs = (uint32_t)(N >> (round + 1));
     if (a.peer.world > 1) a.seq = ++c->peer_seq;
@@ -443,7 +447,7 @@ int sumcheck_prove_evals(Ctx* c, const ScEvalJob& job) {
       a.in[i] = cur[i];
       a.out[i] = dst_base + (size_t)i * dst_sz;
     }
-    if (round >= 1 && !c->profile && !c->dbg_clocks && a.peer.world == 1 && (size_t)a.pairs * T <= TAIL_ITEMS &&
+    if (round >= 1 && !c->profile && !c->dbg_clocks && a.peer.world == 1 && !job.carry && (size_t)a.pairs * T <= TAIL_ITEMS &&
         (size_t)(ntab + 1) * 2 * a.pairs <= TAIL_ENTRIES) {
       // all remaining rounds (and the final bind) in one single-CTA launch
       ScTailArgs ta;
@@ -486,19 +490,21 @@ int sumcheck_prove_evals(Ctx* c, const ScEvalJob& job) {
     prof_end(c, pi);
     count_launch(c);
   }
+  if (job.carry) {  // hand over: tables as the next round would read them, last challenge pending in d_sc->r
+    for (int i = 0; i <= ntab; ++i) job.carry->cur[i] = cur[i];
+    job.carry->len = nrounds == 1 ? N : (N >> (nrounds - 1));
+    CUDA_TRY(cudaGetLastError());
+    return B200_OK;
+  }
   // final bind -> evals (eq excluded: ProverState::into_evals returns the polys only, classic.rs:143-149)
   if (!tail_done) {
     const Fr** d_ptrs = nullptr;
     const int nfinal = ntab + (job.want_eq_eval ? 1 : 0);
-    CUDA_TRY(cudaMallocAsync(&d_ptrs, nfinal * sizeof(Fr*), s));
+    CUDA_TRY(own.alloc(&d_ptrs, nfinal * sizeof(Fr*)));
     CUDA_TRY(cudaMemcpyAsync(d_ptrs, cur, nfinal * sizeof(Fr*), cudaMemcpyHostToDevice, s));
     CUDA_TRY(launch_pdl(sc_final_bind_kernel, dim3((nfinal + 63) / 64), dim3(64), 0, s, d_ptrs, nfinal, c->d_sc, job.evals_out));
     count_launch(c);
-    CUDA_TRY(cudaFreeAsync(d_ptrs, s));
   }
-  if (eq0) CUDA_TRY(cudaFreeAsync(eq0, s));
-  CUDA_TRY(cudaFreeAsync(bufA, s));
-  CUDA_TRY(cudaFreeAsync(bufB, s));
   CUDA_TRY(cudaGetLastError());
   return B200_OK;
 }
@@ -519,6 +525,8 @@ struct ScCoeffArgs {
   Fr* challenges_out;
   uint32_t pairs;
   int round;
+  PeerCtx peer;  // world > 1: (c0, c2) are summed over all ranks through the peer mailboxes
+  unsigned int seq;
 };
 
 template <bool BIND>
@@ -551,13 +559,15 @@ __global__ void __launch_bounds__(SC_THREADS) sc_coeff_round_kernel(ScCoeffArgs 
   const uint32_t nparts = gridDim.x * gridDim.y;
   acc[0] = fe_zero<FrP>();
   acc[1] = fe_zero<FrP>();
+  const bool keep_busy = a.peer.world > 1;
   if (nparts <= 32) {
-    if (threadIdx.x >= 32) return;
-    if (threadIdx.x < nparts) {
+    if (threadIdx.x >= 32) {
+      if (!keep_busy) return;
+    } else if (threadIdx.x < nparts) {
       acc[0] = fr_ld_cg(a.partial + (size_t)threadIdx.x * 2);
       acc[1] = fr_ld_cg(a.partial + (size_t)threadIdx.x * 2 + 1);
     }
-    warp_reduce_fr<2>(acc);
+    if (threadIdx.x < 32) warp_reduce_fr<2>(acc);
   } else {
     for (uint32_t i = threadIdx.x; i < nparts; i += blockDim.x) {
       acc[0] = acc[0] + fr_ld_cg(a.partial + (size_t)i * 2);
@@ -565,12 +575,30 @@ __global__ void __launch_bounds__(SC_THREADS) sc_coeff_round_kernel(ScCoeffArgs 
     }
     block_reduce_fr<2>(acc, smem);
   }
+  __shared__ volatile int s_busy;
+  if (keep_busy) {  // warps 1-3 keep the SM busy while warp 0 runs the exchange and the finalize (peer.cuh)
+    if (threadIdx.x == 0) s_busy = 1;
+    __syncthreads();
+    if (threadIdx.x >= 128) return;
+    if (threadIdx.x >= 32) {
+      peer_spin_while(&s_busy, &a.st->pad[0]);
+      return;
+    }
+  }
   if (threadIdx.x < 32) {
     const int lane = threadIdx.x;
     __shared__ Transcript sh_tr;
     trw_copy(&sh_tr, a.tr);
     const Fr claim = fe_ld(&a.st->claim);
-    const Fr c0 = fr_bcast(acc[0], 0), c2 = fr_bcast(acc[1], 0);
+    Fr c0 = fr_bcast(acc[0], 0), c2 = fr_bcast(acc[1], 0);
+    if (a.peer.world > 1) {  // fused collective: all-gather (c0, c2) over NVLink and add them
+      peer_publish(a.peer, a.seq, lane == 0 ? c0 : c2, 2);
+      Fr sum = fe_zero<FrP>();
+      if (lane < 2)
+        for (int r = 0; r < a.peer.world; ++r) sum = sum + peer_read(a.peer, a.seq, r, lane);
+      c0 = fr_bcast(sum, 0);
+      c2 = fr_bcast(sum, 1);
+    }
     const Fr c1 = claim - (c0 + c0 + c2);  // coeff.rs:147
     const Fr canon = fr_canon_ni(lane == 0 ? c0 : (lane == 1 ? c1 : c2));
     for (int x = 0; x < 3; ++x) trw_write_canon_from_lane(&sh_tr, canon, x, true);
@@ -582,22 +610,28 @@ __global__ void __launch_bounds__(SC_THREADS) sc_coeff_round_kernel(ScCoeffArgs 
       fe_st(&a.st->r, ch);
       fe_st(&a.st->claim, next);
     }
+    if (keep_busy && lane == 0) s_busy = 0;
   }
 }
 
 int sumcheck_prove_coeffs(Ctx* c, const ScCoeffJob& job) {
   const int n = job.num_vars, K = job.K;
   if (n < 1 || n > 30 || K < 1 || K > SC_MAX_TERMS) return B200_ERR_ARG;
+  if ((job.stop_after > 0) != (job.carry != nullptr) || job.stop_after > n) return B200_ERR_ARG;
   cudaStream_t s = c->stream;
   const size_t N = (size_t)1 << n;
   const size_t szA = N / 2, szB = N / 4 ? N / 4 : 1;
   Fr *eq0 = nullptr, *bufA = nullptr, *bufB = nullptr;
-  CUDA_TRY(cudaMallocAsync(&eq0, (size_t)K * N * sizeof(Fr), s));
-  CUDA_TRY(cudaMallocAsync(&bufA, (size_t)2 * K * szA * sizeof(Fr), s));
-  CUDA_TRY(cudaMallocAsync(&bufB, (size_t)2 * K * szB * sizeof(Fr), s));
-  for (int k = 0; k < K; ++k) {
-    int rc = eq_build(c, job.eq_points[k], n, eq0 + (size_t)k * N);
-    if (rc) return rc;
+  DevScope own(s);
+  DevScope& mem = job.carry ? *job.carry->scope : own;
+  CUDA_TRY(mem.alloc(&bufA, (size_t)2 * K * szA * sizeof(Fr)));
+  CUDA_TRY(mem.alloc(&bufB, (size_t)2 * K * szB * sizeof(Fr)));
+  if (!job.eq_tables[0]) {
+    CUDA_TRY(mem.alloc(&eq0, (size_t)K * N * sizeof(Fr)));
+    for (int k = 0; k < K; ++k) {
+      int rc = eq_build(c, job.eq_points[k], n, eq0 + (size_t)k * N);
+      if (rc) return rc;
+    }
   }
   CUDA_TRY(launch_pdl(sc_init_kernel, dim3(1), dim3(32), 0, s, c->d_sc, job.claim));
   count_launch(c);
@@ -607,14 +641,19 @@ int sumcheck_prove_coeffs(Ctx* c, const ScCoeffJob& job) {
   a.partial = c->d_partial;
   a.tr = c->d_tr;
   a.challenges_out = job.challenges_out;
+  a.peer = c->peer;
+  if (!job.sharded) a.peer.world = 1;
+  a.seq = 0;
   const Fr* cur[2 * SC_MAX_TERMS];  // [k] poly, [K + k] eq
   for (int k = 0; k < K; ++k) {
     cur[k] = job.tables[k];
-    cur[K + k] = eq0 + (size_t)k * N;
+    cur[K + k] = job.eq_tables[0] ? job.eq_tables[k] : eq0 + (size_t)k * N;
   }
-  for (int round = 0; round < n; ++round) {
+  const int nrounds = job.stop_after > 0 ? job.stop_after : n;
+  for (int round = 0; round < nrounds; ++round) {
     a.round = round;
     a.pairs = (uint32_t)(N >> (round + 1));
+    if (a.peer.world > 1) a.seq = ++c->peer_seq;
     Fr* dst_base = (round & 1) ? bufA : bufB;
     const size_t dst_sz = (round & 1) ? szA : szB;
     for (int k = 0; k < K; ++k) {
@@ -636,15 +675,17 @@ int sumcheck_prove_coeffs(Ctx* c, const ScCoeffJob& job) {
     }
     count_launch(c);
   }
+  if (job.carry) {
+    for (int i = 0; i < 2 * K; ++i) job.carry->cur[i] = cur[i];
+    job.carry->len = nrounds == 1 ? N : (N >> (nrounds - 1));
+    CUDA_TRY(cudaGetLastError());
+    return B200_OK;
+  }
   const Fr** d_ptrs = nullptr;
-  CUDA_TRY(cudaMallocAsync(&d_ptrs, K * sizeof(Fr*), s));
+  CUDA_TRY(own.alloc(&d_ptrs, K * sizeof(Fr*)));
   CUDA_TRY(cudaMemcpyAsync(d_ptrs, cur, K * sizeof(Fr*), cudaMemcpyHostToDevice, s));
   CUDA_TRY(launch_pdl(sc_final_bind_kernel, dim3(1), dim3(64), 0, s, d_ptrs, K, c->d_sc, job.evals_out));
   count_launch(c);
-  CUDA_TRY(cudaFreeAsync(d_ptrs, s));
-  CUDA_TRY(cudaFreeAsync(eq0, s));
-  CUDA_TRY(cudaFreeAsync(bufA, s));
-  CUDA_TRY(cudaFreeAsync(bufB, s));
   CUDA_TRY(cudaGetLastError());
   return B200_OK;
 }

@@ -33,6 +33,7 @@ extern "C" {
 #define B200_ERR_TRANSCRIPT 3 /* identity commitment or proof overflow -> Error::Transcript */
 #define B200_ERR_NOMEM 4
 #define B200_ERR_LOOKUP 5     /* a lookup input is not in its table -> Error::InvalidSnark("Invalid lookup input") */
+#define B200_ERR_PEER 6       /* a multi-GPU wait timed out: a peer left the collective */
 
 typedef struct b200_ctx b200_ctx;
 
@@ -243,10 +244,28 @@ int b200_kzg_batch_open(b200_ctx* ctx, int num_vars, const void* const* dev_poly
                         const void* host_ev_values, int nevals);
 
 /* ---- multi-GPU: one process per GPU, collectives through NVLink peer memory --------- */
-/* CUDA-IPC handle (64 bytes) of this context's mailbox; exchange the handles of all ranks out of band
- * (e.g. torch.distributed.all_gather), then call b200_dist_init with the `world` handles in rank order. */
-int b200_dist_mailbox_handle(b200_ctx* ctx, void* out_handle64);
+/* CUDA-IPC handles (128 bytes: mailbox | bulk arena) of this context; exchange the handles of all ranks out of band
+ * (e.g. torch.distributed.all_gather), then call b200_dist_init with the `world` handles in rank order. world must be
+ * a power of two <= 8. The mailbox carries the small in-kernel collectives (round partials, evaluations, partial
+ * commitments), the arena (B200_ARENA_MB, default 192 MiB) the bulk all-gathers of bound sum-check tables. */
+int b200_dist_mailbox_handle(b200_ctx* ctx, void* out_handle128);
 int b200_dist_init(b200_ctx* ctx, int rank, int world, const void* handles);
+/* The same group built from `world` contexts of ONE process (same GPU, or peer-accessible GPUs): plain device
+ * pointers instead of IPC. Every context must then be driven from its own host thread. Used by the tests to run the
+ * sharded provers on a single-GPU box; production is one process per GPU. */
+int b200_dist_init_local(b200_ctx* const* ctxs, int world);
+/* Every in-kernel wait for a peer is bounded (B200_PEER_TIMEOUT_S, default 20 s): returns B200_ERR_PEER if one timed
+ * out since the last call (the results of that collective are garbage), else 0. Synchronises the stream. */
+int b200_dist_check(b200_ctx* ctx);
+/* Fully sharded Lasso prover (cfg4): after b200_dist_shard_lasso(ctx, k0) with k0 > 0, b200_lasso_prove* keeps the
+ * 2^mu-sized witness tables, fingerprints, product-tree layers >= k0 and all sum-checks / openings over them on the
+ * rank's 1/world slice — the entries whose index bits [k0 - log2 world, k0) equal the rank: closed under the LSB-first
+ * binds (multilinear.rs:612-616) and under the top-bit tree halving (fractional_sum_check.rs:41-76). Proofs stay
+ * byte-identical. Implies point-sharded commitments; mu <= k0 falls back to the replicated prover. 0 = off. */
+int b200_dist_shard_lasso(b200_ctx* ctx, int k0);
+/* a sharded sum-check round is exchanged over NVLink while a rank holds at least `items` (pair, term) items; below
+ * that the bound tables are all-gathered once and the remaining rounds run replicated (default 2^14) */
+int b200_dist_shard_min_items(b200_ctx* ctx, int items);
 /* Point-sharded commitments: after b200_dist_shard_commits(ctx, 1) every commitment MSM issued by b200_kzg_* and
  * b200_lasso_prove* (variable_base_msm call sites kzg.rs:255,271,292) is split by point range over the ranks and the
  * partial commitments are all-gathered over NVLink and added, so these calls become COLLECTIVE: all ranks run the same
@@ -267,6 +286,14 @@ int b200_sumcheck_prove_evals_sharded(b200_ctx* ctx, int num_vars_total, int nte
                                       const void* const* dev_local_tables, const void* host_weights,
                                       const void* host_y, const void* host_sum, void* host_challenges_out,
                                       void* host_evals_out);
+/* The general layout: the tables are sharded on the index bits [window_pos, window_pos + log2 world) (rank = those
+ * bits, local index = high bits ‖ low window_pos bits; window_pos = -1 means the top variables as above). The first
+ * `sharded_rounds` <= window_pos rounds exchange their partials over NVLink inside the round kernel (-1: as many as pay,
+ * see b200_dist_shard_min_items), then the bound tables are all-gathered once and the rest runs replicated. */
+int b200_sumcheck_prove_evals_windowed(b200_ctx* ctx, int num_vars_total, int window_pos, int sharded_rounds, int nterms,
+                                       int np, const void* const* dev_local_tables, const void* host_weights,
+                                       const void* host_y, const void* host_sum, void* host_challenges_out,
+                                       void* host_evals_out);
 /* variable_base_msm with the points sharded by range: every rank passes its slice, all get the full sum */
 int b200_variable_base_msm_sharded(b200_ctx* ctx, const void* host_scalars_fr, const void* host_bases_g1,
                                    uint64_t n_local, void* host_out_g1);

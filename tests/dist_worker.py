@@ -21,6 +21,7 @@ def check_sharded_sumchecks_in_lasso(ctx, kzg, okzg, rank, world, cases):
     T >= 4) and, with 8 chunks, the 33-value final gather that needs two mailbox messages."""
     hl.dist_shard_commits(ctx, True)
     hl.dist_shard_sumchecks(ctx, 6)
+    hl.dist_shard_min_items(ctx, 32)
     for kind, chunks, mu in cases:
         xs, ys = O.rand_u64s(8400 + mu, 1 << mu), O.rand_u64s(8500 + mu, 1 << mu)
         if kind == O.TABLE_RANGE:
@@ -33,8 +34,38 @@ def check_sharded_sumchecks_in_lasso(ctx, kzg, okzg, rank, world, cases):
         tr = hl.Keccak256Transcript(ctx)
         hl.LassoProver(ctx, kzg, kind, chunks).prove(xs, ys)
         assert tr.into_proof() == to.proof(), f"rank {rank}: sum-check-sharded Lasso proof differs (kind {kind}, c {chunks}, mu {mu})"
+    hl.dist_check(ctx)
+    hl.dist_shard_min_items(ctx, 1 << 14)
     hl.dist_shard_sumchecks(ctx, 0)
     hl.dist_shard_commits(ctx, False)
+
+
+def check_fully_sharded_lasso(ctx, kzg, okzg, rank, world, cases):
+    """b200_dist_shard_lasso over real CUDA-IPC / NVLink peers: tables, trees, sum-checks and quotient commitments on the
+    rank's index-window slice; byte-identical to the single-process oracle proof on every rank."""
+    g = world.bit_length() - 1
+    for kind, chunks, mu, k0, min_items in cases:
+        if k0 - g < 1:
+            continue
+        xs, ys = O.rand_u64s(8700 + mu, 1 << mu), O.rand_u64s(8800 + mu, 1 << mu)
+        if kind == O.TABLE_RANGE:
+            ys = None
+            if chunks < 4:
+                xs &= np.uint64((1 << (16 * chunks)) - 1)
+        else:
+            xs &= np.uint64((1 << (8 * chunks)) - 1)
+            ys &= np.uint64((1 << (8 * chunks)) - 1)
+        to = O.Transcript()
+        assert O.lasso_prove(okzg, to, kind, chunks, mu, xs, ys)
+        hl.dist_shard_lasso(ctx, k0)
+        hl.dist_shard_min_items(ctx, min_items)
+        tr = hl.Keccak256Transcript(ctx)
+        hl.LassoProver(ctx, kzg, kind, chunks).prove(xs, ys)
+        proof = tr.into_proof()
+        hl.dist_check(ctx)
+        hl.dist_shard_lasso(ctx, 0)
+        hl.dist_shard_min_items(ctx, 1 << 14)
+        assert proof == to.proof(), f"rank {rank}: fully sharded Lasso proof differs (kind {kind}, c {chunks}, mu {mu}, k0 {k0})"
 
 
 def time_cooperative_lasso(ctx, kzg, rank, world, mu=20):
@@ -108,7 +139,8 @@ def main():
         lo, hi = hl.shard_slice(n, rank, world)
         tr = hl.Keccak256Transcript(ctx)
         polys = [hl.MultilinearPolynomial.new(ctx, t[lo:hi]) for t in tabs]
-        ch, ev = hl.sumcheck_prove_evals_sharded(ctx, n, polys, w, y, claim, np_per_term=NP)
+        g = world.bit_length() - 1
+        ch, ev = hl.sumcheck_prove_evals_sharded(ctx, n, polys, w, y, claim, np_per_term=NP, sharded_rounds=max(0, n - g - (n % 3)))
         proof = tr.into_proof()
         assert proof == to.proof(), f"rank {rank}: sharded sum-check transcript differs (n={n}, T={T}, NP={NP})"
         assert (ch == ch_o).all() and (ev == ev_o).all(), f"rank {rank}: outputs differ"
@@ -146,6 +178,8 @@ def main():
         assert tr.into_proof() == to.proof(), f"rank {rank}: commit-sharded Lasso proof differs (kind {kind})"
     hl.dist_shard_commits(ctx, False)
     check_sharded_sumchecks_in_lasso(ctx, kzg, okzg, rank, world, ((O.TABLE_RANGE, 4, 15), (O.TABLE_AND, 8, 12)))
+    check_fully_sharded_lasso(ctx, kzg, okzg, rank, world, ((O.TABLE_RANGE, 4, 14, 12, 64), (O.TABLE_AND, 8, 12, 9, 16),
+                                                             (O.TABLE_XOR, 2, 15, 13, 1 << 14)))
     dist.barrier()
     if rank == 0:
         print(f"SHARDED_OK world={world}")

@@ -1,5 +1,6 @@
 """bench.py's reference arm (the CPU leg the driver runs beside the GPU arm): one JSON line with the contract's keys;
-under torchrun only rank 0 runs it. Needs no GPU (~20 s: it proves the real 2^20-lookup instance once)."""
+under torchrun only rank 0 runs it — with all host threads although torchrun exports OMP_NUM_THREADS=1. Needs no GPU; the
+workload is shrunk to 2^12 lookups through B200_BENCH_MU so that the CPU suite stays short."""
 import json
 import os
 import subprocess
@@ -10,6 +11,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def run(env_extra=None):
     env = dict(os.environ)
+    env["B200_BENCH_MU"] = "12"
+    env["OMP_NUM_THREADS"] = "1"  # what torchrun sets for its workers
     env.update(env_extra or {})
     return subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "1",
                            "--steps", "1", "--warmup", "0"], capture_output=True, text=True, timeout=900, env=env)
@@ -23,10 +26,11 @@ def test_reference_arm_prints_one_contract_line():
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["unit"] == "ms" and d["higher_is_better"] is False
     assert d["value"] > 0 and d["ms_per_step"] == d["value"] and d["vs_baseline"] is None
-    assert "2^20" in d["metric"] and "workload" in d["config"]
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert "2^12" in d["metric"] and list(d["config"]) == ["workload"] and d["scaling"] == "strong"
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] == d["value"]
+    assert d["cpu_baseline"]["cores"] == len(os.sched_getaffinity(0))  # not the 1 thread OMP_NUM_THREADS asked for
     assert d["e2e"] == {"value": d["value"], "unit": "ms", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
-    assert d["config"]["proof_bytes"] == 52704
+    assert d["parity"]["proof_bytes"] == 54112 and len(d["parity"]["sha256"]) == 64
 
 
 def test_reference_arm_other_ranks_exit_quietly():
