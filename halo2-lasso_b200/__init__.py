@@ -102,6 +102,11 @@ class Context:
         return lib().b200_stream(self.h)
 
 
+def sumcheck_eq_factored(ctx, on=True):
+    """Select the eq-factored (default) or the plain EVAL-shape round kernel; both produce the same bytes."""
+    _chk(lib().b200_sumcheck_eq_factored(ctx.h, C.c_int(int(on))), "sumcheck_eq_factored")
+
+
 class MultilinearPolynomial:
     """Device-resident `MultilinearPolynomial<Fr>` (pb/poly/multilinear.rs:20-24)."""
 

@@ -50,6 +50,21 @@ static int check_transcript(Ctx* c) {
   return t.error ? B200_ERR_TRANSCRIPT : B200_OK;
 }
 
+static void preload_all_kernels() {
+  B200_PRELOAD(tr_init_kernel);
+  preload_generic();
+  preload_hyperplonk();
+  preload_kzg();
+  preload_lasso();
+  preload_lookup();
+  preload_mle();
+  preload_msm();
+  preload_perm();
+  preload_shard();
+  preload_sumcheck();
+  cudaGetLastError();
+}
+
 extern "C" {
 
 int b200_ctx_create(int device, b200_ctx** out) {
@@ -58,6 +73,7 @@ int b200_ctx_create(int device, b200_ctx** out) {
   CUDA_TRY(cudaGetDeviceCount(&ndev));
   if (device < 0 || device >= ndev) return B200_ERR_ARG;
   CUDA_TRY(cudaSetDevice(device));
+  preload_all_kernels();  // per device: the load is a no-op once a kernel is resident
   b200_ctx* h = new b200_ctx();
   Ctx* c = &h->c;
   c->device = device;
@@ -132,6 +148,11 @@ uint64_t b200_launch_count(b200_ctx* h, int reset) {
 }
 
 void* b200_stream(b200_ctx* h) { return (void*)h->c.stream; }
+
+int b200_sumcheck_eq_factored(b200_ctx* h, int on) {
+  h->c.eq_factored = on != 0;
+  return B200_OK;
+}
 
 int b200_debug_clocks(b200_ctx* h, long long* out) {
   Ctx* c = &h->c;

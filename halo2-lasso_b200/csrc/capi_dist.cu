@@ -11,7 +11,7 @@ using namespace b200;
 
 extern "C" {
 
-static const size_t ARENA_HALF_DEFAULT = (size_t)96 << 20;  // per parity; B200_ARENA_MB overrides (both halves)
+static const size_t ARENA_HALF_DEFAULT = (size_t)160 << 20;  // per parity; B200_ARENA_MB overrides (both halves)
 
 static int dist_alloc_local(Ctx* c) {
   if (!c->my_mailbox) CUDA_TRY(cudaMalloc(&c->my_mailbox, sizeof(Mailbox)));

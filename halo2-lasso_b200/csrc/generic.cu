@@ -370,4 +370,17 @@ int poly_rotate(Ctx* c, const Fr* d_in, int num_vars, int rotation, Fr* d_out) {
   return B200_OK;
 }
 
+// every kernel of this file, loaded up front (b200_ctx_create -> preload_all_kernels, capi.cu)
+void preload_generic() {
+  B200_PRELOAD(sc_generic_round_kernel<false>);
+  B200_PRELOAD(sc_generic_round_kernel<true>);
+  B200_PRELOAD(sc_generic_small_kernel<false>);
+  B200_PRELOAD(sc_generic_small_kernel<true>);
+  B200_PRELOAD(gen_final_bind_kernel);
+  B200_PRELOAD(gen_init_kernel);
+  B200_PRELOAD(poly_iota_kernel);
+  B200_PRELOAD(poly_onehot_kernel);
+  B200_PRELOAD(poly_rotate_kernel);
+}
+
 }  // namespace b200

@@ -242,6 +242,14 @@ struct HyperPlonk {
   std::vector<G1Aff> preprocess_comms, permutation_comms;  // host copies (the verifier parameters)
 };
 
+// every kernel of this file, loaded up front (b200_ctx_create -> preload_all_kernels, capi.cu)
+void preload_hyperplonk() {
+  B200_PRELOAD(scatter_fr_kernel);
+  B200_PRELOAD(u64_rows_to_fr_kernel);
+  B200_PRELOAD(rotation_points_kernel);
+  B200_PRELOAD(gather_evals_kernel);
+}
+
 }  // namespace b200
 
 struct b200_hyperplonk {
@@ -614,6 +622,7 @@ int b200_hyperplonk_prove_phased(b200_hyperplonk* obj, const void* host_instance
     int have = 0;
     for (int round = 0; round < nphases; ++round) {
       const int nw = hp.phase_witness[round];
+      NvtxRange nvtx_w("witness_collector-%d", round);  // hyperplonk.rs:192
       if (have) {
         CUDA_TRY(cudaMemcpyAsync(host_chal.data(), d_chal, have * sizeof(Fr), cudaMemcpyDeviceToHost, s));
         CUDA_TRY(cudaStreamSynchronize(s));
@@ -639,6 +648,11 @@ int b200_hyperplonk_prove_phased(b200_hyperplonk* obj, const void* host_instance
   rc = transcript_op(c, TR_SQUEEZE, nullptr, d_ch, 1);
   if (rc) return rc;
   std::vector<Fr*> comp_in(nlk), comp_tab(nlk), ms(nlk), hs(nlk);
+  nvtxRangePushA("lookup_compressed_polys+lookup_m_polys");  // hyperplonk.rs:215,223
+  struct Pop {
+    bool armed = true;
+    ~Pop() { if (armed) nvtxRangePop(); }
+  } pop_lookup;
   for (int l = 0; l < nlk; ++l) {
     comp_in[l] = ar.alloc<Fr>(N);
     comp_tab[l] = ar.alloc<Fr>(N);
@@ -658,6 +672,8 @@ int b200_hyperplonk_prove_phased(b200_hyperplonk* obj, const void* host_instance
     rc = lookup_m(c, k, comp_in[l], comp_tab[l], ms[l]);
     if (rc) return rc;
   }
+  nvtxRangePop();
+  pop_lookup.armed = false;
   if (nlk) {
     rc = commit_polys(c, std::vector<const Fr*>(ms.begin(), ms.end()), k, true, d_comms);
     if (rc) return rc;
@@ -666,6 +682,7 @@ int b200_hyperplonk_prove_phased(b200_hyperplonk* obj, const void* host_instance
   rc = transcript_op(c, TR_SQUEEZE, nullptr, d_ch + 1, 1);
   if (rc) return rc;
   for (int l = 0; l < nlk; ++l) {
+    NvtxRange nvtx_h("lookup_h_polys-%d", nlk);  // hyperplonk.rs:233
     rc = lookup_h(c, k, comp_in[l], comp_tab[l], ms[l], d_ch + 1, hs[l]);
     if (rc) return rc;
   }
@@ -683,7 +700,10 @@ int b200_hyperplonk_prove_phased(b200_hyperplonk* obj, const void* host_instance
       sigmas[i] = hp.perm[i];
       offs[i] = (uint64_t)i << k;
     }
-    rc = permutation_z_chunks(c, k, hp.num_z, hp.chunk_size, nper, wires.data(), sigmas.data(), offs.data(), d_ch, zs.data());
+    {
+      NvtxRange nvtx_z("permutation_z_polys-%d", nper);  // hyperplonk.rs:237
+      rc = permutation_z_chunks(c, k, hp.num_z, hp.chunk_size, nper, wires.data(), sigmas.data(), offs.data(), d_ch, zs.data());
+    }
     if (rc) return rc;
     for (Fr* z : zs) hz.push_back(z);
   }
@@ -743,6 +763,7 @@ int b200_hyperplonk_prove_phased(b200_hyperplonk* obj, const void* host_instance
   Fr* d_vals = ar.alloc<Fr>(nevals);
   if (!d_vals) return B200_ERR_NOMEM;
   {
+    NvtxRange nvtx_e("evals-%d", nevals);  // prover.rs:391
     int e = 0;
     for (auto& q : queries)
       for (int j = 0; j < (1 << std::abs(q.second)); ++j, ++e) {

@@ -3,7 +3,10 @@
 // device memory so that no step of a proof needs a host round trip.
 #pragma once
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
+#include <stdarg.h>
 #include <stdint.h>
+#include <stdio.h>
 
 #include <vector>
 
@@ -16,6 +19,7 @@ namespace b200 {
 struct ScState {
   Fr claim;  // running claimed sum
   Fr r;      // challenge of the previous round
+  Fr eqc;    // eq-factored rounds: c_i = scale * Π_{j<i} eq1(r_j, y_j)
   unsigned int counter;
   unsigned int pad[7];
 };
@@ -52,6 +56,7 @@ struct Ctx {
   unsigned int* d_peer_err = nullptr;  // device word raised by a timed-out wait (B200_ERR_PEER)
   int shard_min_items = 1 << 14;  // a sum-check round stays sharded while a rank has at least this many (pair, term) items
   int shard_lasso_k0 = 0;  // > 0: the Lasso prover shards its tables / trees on the index window [k0 - g, k0) (lasso.cu)
+  bool eq_factored = true;  // EVAL-shape sum-checks use the eq-factored round kernel (b200_sumcheck_eq_factored)
   bool shard_commits = false;  // every commitment MSM is split by point range over the ranks (all ranks call)
   int shard_sumcheck_min_vars = 0;  // > 0: sum-checks of the whole provers with at least that many variables run
                                     // hypercube-sharded over the ranks (sumcheck_prove_evals_dist, shard.cu)
@@ -200,6 +205,43 @@ int lasso_witness(Ctx* c, int kind, int chunks, int mu, const uint64_t* d_xs, co
                   Fr* d_st);
 
 inline void count_launch(Ctx* c, int n = 1) { c->launches += n; }
+
+// CUDA loads kernels lazily, on their first launch, and that load may synchronise the whole context. A proof should not
+// stall on it, and ranks that share one context (b200_dist_init_local) would deadlock on it: a rank's kernel waiting in
+// a collective for a peer whose own kernel cannot be loaded before the context drains. cudaFuncGetAttributes forces the
+// load; b200_ctx_create calls preload_all_kernels() once per process.
+#define B200_PRELOAD(...)                                     \
+  do {                                                        \
+    cudaFuncAttributes fa_;                                   \
+    cudaFuncGetAttributes(&fa_, (const void*)(__VA_ARGS__)); \
+  } while (0)
+void preload_generic();
+void preload_hyperplonk();
+void preload_kzg();
+void preload_lasso();
+void preload_lookup();
+void preload_mle();
+void preload_msm();
+void preload_perm();
+void preload_shard();
+void preload_sumcheck();
+
+// NVTX range named like the reference's timer at the same site (pb/util/timer.rs:19-60: start_timer / end_timer around
+// variable_base_msm-N, sum_check_prove-n-d, sum_check_prove_round-i, pcs_batch_open-N, merged_polys, g_prime, quotients,
+// witness_collector-i, lookup_*_polys-N, permutation_z_polys-N, evals-N): shows up on the host timeline of nsys / ncu
+// --nvtx; costs two library calls when no tool is attached.
+struct NvtxRange {
+  explicit NvtxRange(const char* fmt, ...) {
+    char name[96];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(name, sizeof(name), fmt, ap);
+    va_end(ap);
+    nvtxRangePushA(name);
+  }
+  NvtxRange(const NvtxRange&) = delete;
+  ~NvtxRange() { nvtxRangePop(); }
+};
 
 // Stream-ordered scratch released on EVERY exit path of a host function (error returns included).
 struct DevScope {

@@ -20,6 +20,7 @@ int kzg_commit_batch(Ctx* c, const MsmJob* jobs, int J, bool write_transcript, G
 // remainder is all-gathered once and the low levels run replicated.
 int kzg_open(Ctx* c, const Fr* d_poly, int n, const Fr* d_point, int shard_p) {
   if (n < 1 || n > 30 || (int)c->srs.size() <= n - 1) return B200_ERR_ARG;
+  NvtxRange nvtx("quotients");  // pcs/multilinear.rs:85
   cudaStream_t s = c->stream;
   const bool sh = shard_p >= 0 && c->peer.world > 1;
   int g = 0;
@@ -83,6 +84,7 @@ __global__ void fill_one_kernel(Fr* out, int n) {
 int kzg_batch_open(Ctx* c, const BatchOpenJob& job) {
   const int n = job.num_vars, P = job.npoints, E = job.nevals;
   if (n < 1 || n > 30 || P < 1 || P > SC_MAX_TERMS || E < 2 || E > SC_MAX_TABLES) return B200_ERR_ARG;
+  NvtxRange nvtx("pcs_batch_open-%d", E);  // hyperplonk.rs:286
   cudaStream_t s = c->stream;
   const bool sh = job.shard_p >= 0 && c->peer.world > 1;
   int g = 0;
@@ -130,11 +132,14 @@ int kzg_batch_open(Ctx* c, const BatchOpenJob& job) {
   CUDA_TRY(cudaMemcpyAsync(d_idx, h_idx, E * sizeof(int), cudaMemcpyHostToDevice, s));
   gather_fr_kernel<<<1, 64, 0, s>>>(eq_xt, d_idx, E, gathered);
   count_launch(c);
-  for (int i = 0; i < P; ++i) {
-    const int k = start[i + 1] - start[i];
-    for (int j = 0; j < k; ++j) tabs[j] = per_point[i][j];
-    rc = fr_lincomb(c, tabs, k, gathered + start[i], N, merged + (size_t)i * N);
-    if (rc) return rc;
+  {
+    NvtxRange nvtx_m("merged_polys");  // pcs/multilinear.rs:153
+    for (int i = 0; i < P; ++i) {
+      const int k = start[i + 1] - start[i];
+      for (int j = 0; j < k; ++j) tabs[j] = per_point[i][j];
+      rc = fr_lincomb(c, tabs, k, gathered + start[i], N, merged + (size_t)i * N);
+      if (rc) return rc;
+    }
   }
   // tilde_gs_sum = <evals.value, eq_xt[..E]>   (:195-196)
   dot_small_kernel<<<1, 32, 0, s>>>(job.ev_values, eq_xt, E, tilde);
@@ -163,7 +168,10 @@ int kzg_batch_open(Ctx* c, const BatchOpenJob& job) {
   }
   Fr* gprime = nullptr;
   CUDA_TRY(mem.alloc(&gprime, N * sizeof(Fr)));
-  rc = fr_lincomb(c, tabs, P, eqev, N, gprime);
+  {
+    NvtxRange nvtx_g("g_prime");  // pcs/multilinear.rs:203
+    rc = fr_lincomb(c, tabs, P, eqev, N, gprime);
+  }
   if (rc) return rc;
   return kzg_open(c, gprime, n, challenges, sh ? job.shard_p : -1);
 }
@@ -303,6 +311,18 @@ int kzg_setup(Ctx* c, const Fr* d_ss, int n) {
   CUDA_TRY(cudaFreeAsync(eq, s));
   CUDA_TRY(cudaStreamSynchronize(s));
   return B200_OK;
+}
+
+// every kernel of this file, loaded up front (b200_ctx_create -> preload_all_kernels, capi.cu)
+void preload_kzg() {
+  B200_PRELOAD(gather_fr_kernel);
+  B200_PRELOAD(dot_small_kernel);
+  B200_PRELOAD(fill_one_kernel);
+  B200_PRELOAD(srs_window_bases_kernel);
+  B200_PRELOAD(srs_window_table_kernel);
+  B200_PRELOAD(srs_fixed_base_kernel);
+  B200_PRELOAD(srs_ext_kernel);
+  B200_PRELOAD(fill_one_fr_kernel);
 }
 
 }  // namespace b200

@@ -55,14 +55,16 @@ __global__ void lasso_chunks_kernel(int kind, int c, uint32_t m, const uint64_t*
 
 // pass 1: per (chunk-of-lookups, dim) histogram over the 2^16 addresses, 16-bit counters packed in
 // 32-bit shared-memory words (a chunk holds < 65536 lookups)
+// (memories: grid row i handles memory t0 + i * tstep; hist / base / read_ts / final_cts are indexed by the row, so a rank
+// that owns every tstep-th memory keeps compact outputs)
 __global__ void __launch_bounds__(256) lasso_hist_kernel(uint32_t m, uint32_t chunk_len,
                                                          const uint32_t* __restrict__ dims,
-                                                         uint32_t* __restrict__ hist) {
+                                                         uint32_t* __restrict__ hist, int t0, int tstep) {
   extern __shared__ uint32_t sh[];  // 32768 words
   const uint32_t ch = blockIdx.x, t = blockIdx.y, nch = gridDim.x;
   for (uint32_t i = threadIdx.x; i < SUB_SIZE / 2; i += blockDim.x) sh[i] = 0;
   __syncthreads();
-  const uint32_t* d = dims + (size_t)t * m + (size_t)ch * chunk_len;
+  const uint32_t* d = dims + (size_t)(t0 + t * tstep) * m + (size_t)ch * chunk_len;
   for (uint32_t i = threadIdx.x; i < chunk_len; i += blockDim.x) {
     const uint32_t addr = d[i];
     atomicAdd(&sh[addr >> 1], 1u << (16 * (addr & 1)));
@@ -92,13 +94,14 @@ __global__ void lasso_colscan_kernel(uint32_t nch, const uint32_t* __restrict__ 
 __global__ void __launch_bounds__(32) lasso_rank_kernel(uint32_t m, uint32_t chunk_len,
                                                         const uint32_t* __restrict__ dims,
                                                         const uint32_t* __restrict__ base,
-                                                        uint32_t* __restrict__ read_ts) {
+                                                        uint32_t* __restrict__ read_ts, int t0, int tstep) {
   extern __shared__ uint32_t sh[];
   uint16_t* local = reinterpret_cast<uint16_t*>(sh);
   const uint32_t ch = blockIdx.x, t = blockIdx.y, nch = gridDim.x, lane = threadIdx.x;
   for (uint32_t i = lane; i < SUB_SIZE / 2; i += 32) sh[i] = 0;
   __syncwarp();
-  const size_t off = (size_t)t * m + (size_t)ch * chunk_len;
+  const size_t off = (size_t)t * m + (size_t)ch * chunk_len;                          // compact output row
+  const size_t doff = (size_t)(t0 + t * tstep) * m + (size_t)ch * chunk_len;          // the memory's addresses
   const uint32_t* b = base + ((size_t)t * nch + ch) * SUB_SIZE;
   constexpr int U = 8;  // steps whose address + base loads are issued together (hides the global latency)
   for (uint32_t i0 = 0; i0 < chunk_len; i0 += 32 * U) {
@@ -106,7 +109,7 @@ __global__ void __launch_bounds__(32) lasso_rank_kernel(uint32_t m, uint32_t chu
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const uint32_t i = i0 + u * 32 + lane;
-      addr[u] = i < chunk_len ? dims[off + i] : (0x80000000u | lane);  // invalid lanes never match
+      addr[u] = i < chunk_len ? dims[doff + i] : (0x80000000u | lane);  // invalid lanes never match
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) bs[u] = addr[u] < SUB_SIZE ? b[addr[u]] : 0;
@@ -141,11 +144,11 @@ __device__ __forceinline__ uint32_t shard_map(uint32_t i, int p, int g, uint32_t
 // out[t][i] = in[t][map(i)] for ntab integer tables of n entries each (n_loc = n >> g local entries)
 __global__ void u32_to_fr_map_kernel(const uint32_t* __restrict__ in, Fr* __restrict__ out, int ntab, uint32_t n,
                                      uint32_t n_loc, int p, int g, uint32_t rank) {
-  const size_t total = (size_t)ntab * n_loc, stride = (size_t)gridDim.x * blockDim.x;
-  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
-    const uint32_t t = (uint32_t)(e / n_loc), i = (uint32_t)(e % n_loc);
-    fe_st(out + e, fe_from_u64<FrP>(in[(size_t)t * n + shard_map(i, p, g, rank)]));
-  }
+  const uint32_t t = blockIdx.y, stride = gridDim.x * blockDim.x;  // grid row = table
+  const uint32_t* __restrict__ src = in + (size_t)t * n;
+  Fr* __restrict__ dst = out + (size_t)t * n_loc;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_loc; i += stride)
+    fe_st(dst + i, fe_from_u64<FrP>(src[shard_map(i, p, g, rank)]));
 }
 __global__ void u64_to_fr_map_kernel(const uint64_t* __restrict__ in, Fr* __restrict__ out, uint32_t n_loc, int p, int g,
                                      uint32_t rank) {
@@ -365,8 +368,11 @@ struct LassoWitness {
   uint32_t *dims, *es, *ts, *cts;
   uint64_t* a_u64;
 };
+// shard_counters: the read / final counters of the c memories are independent, so rank r computes those of the memories
+// r, r + G, ... only and the integer arrays are all-gathered into the bulk arenas (they are needed by every rank for the
+// point-sharded commitment MSMs and for its slice of the field-element tables)
 static int lasso_witness_ints(Ctx* c, DevScope& mem, int kind, int C_, int mu, const uint64_t* d_xs, const uint64_t* d_ys,
-                              LassoWitness* w) {
+                              LassoWitness* w, bool shard_counters = false) {
   cudaStream_t s = c->stream;
   const uint32_t m = 1u << mu;
   const size_t S = SUB_SIZE;
@@ -374,13 +380,16 @@ static int lasso_witness_ints(Ctx* c, DevScope& mem, int kind, int C_, int mu, c
   unsigned int* bad;
   const uint32_t nch = m >= (1u << 13) ? (m / 32768 > 128 ? m / 32768 : 128) : 1;
   const uint32_t chunk_len = m / nch;
+  const int G = c->peer.world;
+  if (shard_counters && (G < 2 || C_ % G || m < 8 || (size_t)C_ * m * 4 > c->peer.arena_half)) shard_counters = false;
+  const int own = shard_counters ? C_ / G : C_, t0 = shard_counters ? c->peer.rank : 0, tstep = shard_counters ? G : 1;
   CUDA_TRY(mem.alloc(&w->dims, (size_t)C_ * m * 4));
   CUDA_TRY(mem.alloc(&w->es, (size_t)C_ * m * 4));
-  CUDA_TRY(mem.alloc(&w->ts, (size_t)C_ * m * 4));
-  CUDA_TRY(mem.alloc(&w->cts, (size_t)C_ * S * 4));
+  CUDA_TRY(mem.alloc(&w->ts, (size_t)own * m * 4));
+  CUDA_TRY(mem.alloc(&w->cts, (size_t)own * S * 4));
   CUDA_TRY(mem.alloc(&w->a_u64, (size_t)m * 8));
-  CUDA_TRY(mem.alloc(&hist, (size_t)C_ * nch * (S / 2) * 4));
-  CUDA_TRY(mem.alloc(&base, (size_t)C_ * nch * S * 4));
+  CUDA_TRY(mem.alloc(&hist, (size_t)own * nch * (S / 2) * 4));
+  CUDA_TRY(mem.alloc(&base, (size_t)own * nch * S * 4));
   CUDA_TRY(mem.alloc(&bad, 4));
   CUDA_TRY(cudaMemsetAsync(bad, 0, 4, s));
   int bx = (int)((m + 255) / 256);
@@ -393,11 +402,27 @@ static int lasso_witness_ints(Ctx* c, DevScope& mem, int kind, int C_, int mu, c
   const int smem = (int)(S / 2) * 4;  // 128 KiB
   CUDA_TRY(cudaFuncSetAttribute(lasso_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   CUDA_TRY(cudaFuncSetAttribute(lasso_rank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  lasso_hist_kernel<<<dim3(nch, C_), 256, smem, s>>>(m, chunk_len, w->dims, hist);
-  lasso_colscan_kernel<<<dim3(S / 256, C_), 256, 0, s>>>(nch, hist, base, w->cts);
-  lasso_rank_kernel<<<dim3(nch, C_), 32, smem, s>>>(m, chunk_len, w->dims, base, w->ts);
+  lasso_hist_kernel<<<dim3(nch, own), 256, smem, s>>>(m, chunk_len, w->dims, hist, t0, tstep);
+  lasso_colscan_kernel<<<dim3(S / 256, own), 256, 0, s>>>(nch, hist, base, w->cts);
+  lasso_rank_kernel<<<dim3(nch, own), 32, smem, s>>>(m, chunk_len, w->dims, base, w->ts, t0, tstep);
   count_launch(c, 4);
   CUDA_TRY(cudaGetLastError());
+  if (shard_counters) {
+    // 8 counters travel as one field-element-sized word; row i of rank r is memory r + G i, and the gathered layout
+    // (row, rank, entry) is exactly (memory, entry)
+    const Fr* src[8];
+    const Fr* full[8];
+    int lq = 0;
+    while ((8u << lq) < m) ++lq;
+    for (int i = 0; i < own; ++i) src[i] = reinterpret_cast<const Fr*>(w->ts + (size_t)i * m);
+    int rc = shard_allgather(c, src, own, m / 8, lq, false, full);
+    if (rc) return rc;
+    w->ts = const_cast<uint32_t*>(reinterpret_cast<const uint32_t*>(full[0]));
+    for (int i = 0; i < own; ++i) src[i] = reinterpret_cast<const Fr*>(w->cts + (size_t)i * S);
+    rc = shard_allgather(c, src, own, (uint32_t)(S / 8), 13, false, full);
+    if (rc) return rc;
+    w->cts = const_cast<uint32_t*>(reinterpret_cast<const uint32_t*>(full[0]));
+  }
   CUDA_TRY(cudaStreamSynchronize(s));
   return h_bad ? B200_ERR_LOOKUP : B200_OK;
 }
@@ -408,6 +433,7 @@ int lasso_prove(Ctx* c, int kind, int chunks, int mu, const uint64_t* d_xs, cons
   if (kind != 0 && !d_ys) return B200_ERR_ARG;  // and / xor need both operands
   if (chunks < 2) return B200_ERR_ARG;  // additive batch_open needs >= 2 evaluations (pcs/multilinear.rs:150)
   if ((int)c->srs.size() <= (mu > SUB_VARS ? mu : SUB_VARS)) return B200_ERR_ARG;
+  NvtxRange nvtx("lasso_prove-%d", mu);
   cudaStream_t s = c->stream;
   const int C_ = chunks;
   const uint32_t m = 1u << mu;
@@ -435,7 +461,7 @@ int lasso_prove(Ctx* c, int kind, int chunks, int mu, const uint64_t* d_xs, cons
   // ---- 1. witness (integers, all lookups) ------------------------------------------------------------
   int ph = prof_begin(c, PH_WITNESS);
   LassoWitness wit;
-  int rc = lasso_witness_ints(c, mem, kind, C_, mu, d_xs, d_ys, &wit);
+  int rc = lasso_witness_ints(c, mem, kind, C_, mu, d_xs, d_ys, &wit, sh);
   if (rc) return rc;
   uint32_t *dims = wit.dims, *es = wit.es, *ts = wit.ts, *cts = wit.cts;
   uint64_t* a_u64 = wit.a_u64;
@@ -450,10 +476,12 @@ int lasso_prove(Ctx* c, int kind, int chunks, int mu, const uint64_t* d_xs, cons
   Fr* ts_fr = e_fr + (size_t)C_ * m_loc;
   {
     const int bx = NUM_SMS * 8;
+    int by = (int)((m_loc + 255) / 256);
+    if (by > NUM_SMS * 2) by = NUM_SMS * 2;
     u64_to_fr_map_kernel<<<bx, 256, 0, s>>>(a_u64, a_fr, m_loc, p, lg, rank);
-    u32_to_fr_map_kernel<<<bx, 256, 0, s>>>(dims, dim_fr, C_, m, m_loc, p, lg, rank);
-    u32_to_fr_map_kernel<<<bx, 256, 0, s>>>(es, e_fr, C_, m, m_loc, p, lg, rank);
-    u32_to_fr_map_kernel<<<bx, 256, 0, s>>>(ts, ts_fr, C_, m, m_loc, p, lg, rank);
+    u32_to_fr_map_kernel<<<dim3(by, C_), 256, 0, s>>>(dims, dim_fr, C_, m, m_loc, p, lg, rank);
+    u32_to_fr_map_kernel<<<dim3(by, C_), 256, 0, s>>>(es, e_fr, C_, m, m_loc, p, lg, rank);
+    u32_to_fr_map_kernel<<<dim3(by, C_), 256, 0, s>>>(ts, ts_fr, C_, m, m_loc, p, lg, rank);
     u32_to_fr_kernel<<<bx, 256, 0, s>>>(cts, st_tabs, (size_t)C_ * S);
     count_launch(c, 5);
   }
@@ -729,6 +757,25 @@ int lasso_witness(Ctx* c, int kind, int chunks, int mu, const uint64_t* d_xs, co
   count_launch(c, 4);
   CUDA_TRY(cudaGetLastError());
   return B200_OK;
+}
+
+// every kernel of this file, loaded up front (b200_ctx_create -> preload_all_kernels, capi.cu)
+void preload_lasso() {
+  B200_PRELOAD(lasso_chunks_kernel);
+  B200_PRELOAD(lasso_hist_kernel);
+  B200_PRELOAD(lasso_colscan_kernel);
+  B200_PRELOAD(lasso_rank_kernel);
+  B200_PRELOAD(u32_to_fr_kernel);
+  B200_PRELOAD(u32_to_fr_map_kernel);
+  B200_PRELOAD(u64_to_fr_map_kernel);
+  B200_PRELOAD(lasso_leaves_m_kernel);
+  B200_PRELOAD(lasso_leaves_s_kernel);
+  B200_PRELOAD(tree_up_kernel);
+  B200_PRELOAD(gp_roots_kernel);
+  B200_PRELOAD(gp_before_kernel);
+  B200_PRELOAD(gp_after_kernel);
+  B200_PRELOAD(gather_points_kernel);
+  B200_PRELOAD(copy_fr_kernel);
 }
 
 }  // namespace b200

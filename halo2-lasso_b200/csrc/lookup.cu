@@ -211,6 +211,15 @@ int expression_rows_prog(Ctx* c, int num_vars, const Fr* const* tables, int ntab
   return B200_OK;
 }
 
+// every kernel of this file, loaded up front (b200_ctx_create -> preload_all_kernels, capi.cu)
+void preload_lookup() {
+  B200_PRELOAD(expr_rows_kernel);
+  B200_PRELOAD(lookup_insert_kernel);
+  B200_PRELOAD(lookup_count_kernel);
+  B200_PRELOAD(lookup_counts_to_fr_kernel);
+  B200_PRELOAD(lookup_h_kernel);
+}
+
 }  // namespace b200
 
 using namespace b200;

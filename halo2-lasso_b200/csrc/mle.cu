@@ -308,4 +308,20 @@ int transcript_write_points(Ctx* c, const G1Aff* d_pts, int n) {
   return B200_OK;
 }
 
+// every kernel of this file, loaded up front (b200_ctx_create -> preload_all_kernels, capi.cu)
+void preload_mle() {
+  B200_PRELOAD(eq_direct_kernel);
+  B200_PRELOAD(eq_combine_kernel);
+  B200_PRELOAD(fix_var_kernel);
+  B200_PRELOAD(mle_dot_kernel);
+  B200_PRELOAD(lincomb_kernel);
+  B200_PRELOAD(scale_kernel);
+  B200_PRELOAD(convert_kernel);
+  B200_PRELOAD(from_u64_kernel);
+  B200_PRELOAD(quotient_kernel);
+  B200_PRELOAD(eq_xy_eval_kernel);
+  B200_PRELOAD(transcript_kernel);
+  B200_PRELOAD(transcript_points_kernel);
+}
+
 }  // namespace b200

@@ -315,6 +315,41 @@ __global__ void __launch_bounds__(128) msm_bucket_kernel(uint32_t nbuckets, cons
   st_xyzz(bucket_sum + gb, acc);
 }
 
+// One shared, NON-inlined copy of the group operations for the latency-bound reduction kernels (few warps, long
+// dependent chains): inlined, every call site carries 14 Montgomery products (~35 KB of code) and a single warp
+// becomes instruction-fetch bound.
+static __device__ __noinline__ G1Xyzz g1_add_ni(G1Xyzz a, G1Xyzz b) {
+  if (g1_is_identity(a)) return b;
+  if (g1_is_identity(b)) return a;
+  const Fq u1 = fq_mul_ni(a.x, b.zz), u2 = fq_mul_ni(b.x, a.zz);
+  const Fq s1 = fq_mul_ni(a.y, b.zzz), s2 = fq_mul_ni(b.y, a.zzz);
+  const Fq p = u2 - u1, r = s2 - s1;
+  if (fe_is_zero<FqP>(p)) {
+    if (fe_is_zero<FqP>(r)) return g1_dbl(a);
+    return g1_identity();
+  }
+  const Fq pp = fq_mul_ni(p, p), ppp = fq_mul_ni(p, pp), q = fq_mul_ni(u1, pp);
+  G1Xyzz o;
+  o.x = fq_mul_ni(r, r) - ppp - fe_dbl<FqP>(q);
+  o.y = fq_mul_ni(r, q - o.x) - fq_mul_ni(s1, ppp);
+  o.zz = fq_mul_ni(fq_mul_ni(a.zz, b.zz), pp);
+  o.zzz = fq_mul_ni(fq_mul_ni(a.zzz, b.zzz), ppp);
+  return o;
+}
+static __device__ __noinline__ G1Xyzz g1_dbl_ni(G1Xyzz p) {
+  if (g1_is_identity(p)) return p;
+  const Fq u = fe_dbl<FqP>(p.y);
+  const Fq v = fq_mul_ni(u, u), w = fq_mul_ni(u, fq_mul_ni(u, u));
+  const Fq s = fq_mul_ni(p.x, v), xx = fq_mul_ni(p.x, p.x);
+  const Fq m = fe_dbl<FqP>(xx) + xx;
+  G1Xyzz r;
+  r.x = fq_mul_ni(m, m) - fe_dbl<FqP>(s);
+  r.y = fq_mul_ni(m, s - r.x) - fq_mul_ni(w, p.y);
+  r.zz = fq_mul_ni(v, p.zz);
+  r.zzz = fq_mul_ni(w, p.zzz);
+  return r;
+}
+
 __device__ __forceinline__ G1Xyzz shfl_down_xyzz(const G1Xyzz& p, int off) {
   G1Xyzz r;
 #pragma unroll
@@ -329,7 +364,7 @@ __device__ __forceinline__ G1Xyzz shfl_down_xyzz(const G1Xyzz& p, int off) {
 __device__ __forceinline__ G1Xyzz warp_sum_xyzz(G1Xyzz acc) {
   for (int off = 16; off > 0; off >>= 1) {
     const G1Xyzz o = shfl_down_xyzz(acc, off);
-    acc = g1_add(acc, o);
+    acc = g1_add_ni(acc, o);
   }
   return acc;  // valid in lane 0
 }
@@ -346,7 +381,7 @@ __global__ void __launch_bounds__(128) msm_heavy_kernel(const uint32_t* __restri
     const uint32_t gb = heavy[h];
     const uint32_t t0 = toff[gb], nt = toff[gb + 1] - t0;
     G1Xyzz acc = g1_identity();
-    for (uint32_t k = lane; k < nt; k += 32) acc = g1_add(acc, ld_xyzz(partial + t0 + k));
+    for (uint32_t k = lane; k < nt; k += 32) acc = g1_add_ni(acc, ld_xyzz(partial + t0 + k));
     acc = warp_sum_xyzz(acc);
     if (lane == 0) st_xyzz(bucket_sum + gb, acc);
   }
@@ -354,13 +389,14 @@ __global__ void __launch_bounds__(128) msm_heavy_kernel(const uint32_t* __restri
 
 // ---- window reduction ----------------------------------------------------------------------------
 // S_w = Σ_k (k+1) B_k over the B buckets of a window, without any scalar multiplication. Write
-// k = lo + 8 (l1 + 32 (l2 + 32 l3)); then  k + 1 = (lo + 1) + 8 l1 + 256 l2 + 8192 l3  and
-//   S_w = Σ Y + 8 (Σ A + 32 (Σ Bq + 32 C)),   Y = Σ_lo (lo+1) B,  A = Σ l1 R1,  Bq = Σ l2 R2,  C = Σ l3 R3,
-// where R1 / R2 / R3 are the plain sums of 8 / 256 / 8192 consecutive buckets. Four launches:
-//   l0   : one THREAD per 8 buckets, running sums (16 dependent additions)          -> R1, Y1
+// k = lo + 8 (l1 + 8 (l2 + 32 l3)); then  k + 1 = (lo + 1) + 8 l1 + 64 l2 + 2048 l3  and
+//   S_w = Σ Y + 8 (Σ A + 8 (Σ Bq + 32 C)),   Y = Σ_lo (lo+1) B,  A = Σ l1 R1,  Bq = Σ l2 R2,  C = Σ l3 R3,
+// where R1 / R2 / R3 are the plain sums of 8 / 64 / 2048 consecutive buckets. Four launches:
+//   l0, l1: one THREAD per 8 entries, running sums (16 dependent additions; work-efficient while entries are many)
+//                                                                                     -> R1, Y1 ; R2, A2, Y2
 //   tree : one WARP per 32 entries: suffix scan by shuffles (Σ l R_l = Σ_{l>=1} suffix_l, 10 add steps) and plain
-//          shuffle sums of the carried streams                                        -> R2, A2, Y2 ; R3, Bq3, A3, Y3
-//   final: one warp per window: the last weighted sum, the stream totals and 13 doublings
+//          shuffle sums of the carried streams                                        -> R3, Bq3, A3, Y3
+//   final: one warp per window: the last weighted sum, the stream totals and 11 doublings
 // All windows of all jobs of the batch go through the same launches (the reference reduces each window with a serial
 // running sum, msm.rs:160-181; the group element is the same).
 static const int L0 = 8;
@@ -411,11 +447,35 @@ __device__ __forceinline__ void warp_weighted_sum(G1Xyzz x, G1Xyzz& plain, G1Xyz
   // inclusive suffix scan: x_l <- Σ_{j >= l} x_j
   for (int off = 1; off < 32; off <<= 1) {
     const G1Xyzz o = shfl_down_xyzz(x, off);
-    if (lane + off < 32) x = g1_add(x, o);
+    if (lane + off < 32) x = g1_add_ni(x, o);
   }
   plain = x;  // lane 0: the total
   G1Xyzz s = lane >= 1 ? x : g1_identity();
   weighted = warp_sum_xyzz(s);
+}
+
+// level 1 -> level 2: one THREAD per 8 consecutive level-1 entries (work-efficient while there are still many entries):
+// R2 = Σ R1, A2 = Σ l R1_l (l = 0..7), Y2 = Σ Y1
+__global__ void __launch_bounds__(128) msm_red_l1_kernel(MsmRedDesc d, uint32_t n2tot, const G1Xyzz* __restrict__ in,
+                                                         uint32_t n1tot, G1Xyzz* __restrict__ out) {
+  const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n2tot) return;
+  const uint32_t w = seg_of(d.off2, d.nwin, g);
+  const uint32_t i0 = d.off1[w] + (g - d.off2[w]) * 8, iend = d.off1[w + 1];
+  const uint32_t i1 = i0 + 8 < iend ? i0 + 8 : iend;
+  G1Xyzz run = g1_identity(), wsum = g1_identity(), ysum = g1_identity();
+  for (uint32_t i = i1; i-- > i0;) {
+    ysum = g1_add(ysum, ld_xyzz(in + n1tot + i));
+    if (i > i0) {
+      run = g1_add(run, ld_xyzz(in + i));
+      wsum = g1_add(wsum, run);
+    } else {
+      run = g1_add(run, ld_xyzz(in + i));
+    }
+  }
+  st_xyzz(out + g, run);
+  st_xyzz(out + n2tot + g, wsum);
+  st_xyzz(out + (size_t)2 * n2tot + g, ysum);
 }
 
 // One warp per 32 consecutive entries of a window at level LV (1 or 2). Streams in: R (weighted), P[0..NP) plain.
@@ -456,14 +516,14 @@ __global__ void __launch_bounds__(128) msm_red_final_kernel(MsmRedDesc d, const 
   const G1Xyzz bq = warp_sum_xyzz(valid ? ld_xyzz(in + (size_t)1 * n3tot + i0 + lane) : g1_identity());
   const G1Xyzz a = warp_sum_xyzz(valid ? ld_xyzz(in + (size_t)2 * n3tot + i0 + lane) : g1_identity());
   const G1Xyzz y = warp_sum_xyzz(valid ? ld_xyzz(in + (size_t)3 * n3tot + i0 + lane) : g1_identity());
-  if (lane == 0) {
+  if (lane == 0) {  // S = Y + 8 (A + 8 (Bq + 32 C))
     G1Xyzz acc = c;
-    for (int k = 0; k < 5; ++k) acc = g1_dbl(acc);
-    acc = g1_add(acc, bq);
-    for (int k = 0; k < 5; ++k) acc = g1_dbl(acc);
-    acc = g1_add(acc, a);
-    for (int k = 0; k < 3; ++k) acc = g1_dbl(acc);
-    acc = g1_add(acc, y);
+    for (int k = 0; k < 5; ++k) acc = g1_dbl_ni(acc);
+    acc = g1_add_ni(acc, bq);
+    for (int k = 0; k < 3; ++k) acc = g1_dbl_ni(acc);
+    acc = g1_add_ni(acc, a);
+    for (int k = 0; k < 3; ++k) acc = g1_dbl_ni(acc);
+    acc = g1_add_ni(acc, y);
     st_xyzz(window_sum + w, acc);
   }
 }
@@ -489,20 +549,20 @@ __global__ void __launch_bounds__(32) msm_finish_kernel(MsmPlanDev plan, MsmDeri
     for (int w = lane; w < jb.Wred; w += 32) top = w;
     for (int w = top; w >= 0; w -= 32) {  // Σ_i 2^(32 c i) S_{lane + 32 i}
       if (w != top)
-        for (int k = 0; k < 32 * jb.c; ++k) acc = g1_dbl(acc);
-      acc = g1_add(acc, ld_xyzz(window_sum + jb.win_base + w));
+        for (int k = 0; k < 32 * jb.c; ++k) acc = g1_dbl_ni(acc);
+      acc = g1_add_ni(acc, ld_xyzz(window_sum + jb.win_base + w));
     }
     if (jb.Wred > 1)
-      for (int k = 0; k < lane * jb.c; ++k) acc = g1_dbl(acc);
+      for (int k = 0; k < lane * jb.c; ++k) acc = g1_dbl_ni(acc);
   } else {
     const auto& d = dv.d[j - plan.J];
     if (lane < d.nsrc) {  // sources are single-window jobs or short Horner chains: recomputed by this lane
       const MsmJobDev& jb = plan.job[d.src[lane]];
       for (int w = jb.Wred - 1; w >= 0; --w) {
-        for (int k = 0; k < jb.c; ++k) acc = g1_dbl(acc);
-        acc = g1_add(acc, ld_xyzz(window_sum + jb.win_base + w));
+        for (int k = 0; k < jb.c; ++k) acc = g1_dbl_ni(acc);
+        acc = g1_add_ni(acc, ld_xyzz(window_sum + jb.win_base + w));
       }
-      for (int k = 0; k < lane * d.shift; ++k) acc = g1_dbl(acc);
+      for (int k = 0; k < lane * d.shift; ++k) acc = g1_dbl_ni(acc);
     }
   }
   acc = warp_sum_xyzz(acc);
@@ -521,6 +581,7 @@ static int ilog2_floor(uint64_t n) {
 
 int msm_batch(Ctx* c, const MsmJob* jobs, int J, G1Aff* d_out, const MsmDerive* derive, int nderive) {
   if (J < 1 || J > MSM_MAX_JOBS || nderive < 0 || nderive > 4) return B200_ERR_ARG;
+  NvtxRange nvtx("variable_base_msm-%llu x%d", (unsigned long long)jobs[0].n, J);  // msm.rs:92 (batched here)
   cudaStream_t s = c->stream;
   MsmPlanDev plan;
   plan.J = J;
@@ -592,7 +653,7 @@ int msm_batch(Ctx* c, const MsmJob* jobs, int J, G1Aff* d_out, const MsmDerive* 
   // reduction levels (see msm_red_*): entries per window at level 1 / 2 / 3
   std::vector<uint32_t> off1(nwin + 1, 0), off2(nwin + 1, 0), off3(nwin + 1, 0);
   for (uint32_t w = 0; w < nwin; ++w) {
-    const uint32_t n1 = (wB[w] + L0 - 1) / L0, n2 = (n1 + 31) / 32, n3 = (n2 + 31) / 32;
+    const uint32_t n1 = (wB[w] + L0 - 1) / L0, n2 = (n1 + 7) / 8, n3 = (n2 + 31) / 32;
     if (n3 > 32) return B200_ERR_ARG;
     off1[w + 1] = off1[w] + n1;
     off2[w + 1] = off2[w] + n2;
@@ -652,7 +713,7 @@ int msm_batch(Ctx* c, const MsmJob* jobs, int J, G1Aff* d_out, const MsmDerive* 
   msm_bucket_kernel<<<(nbuckets + 127) / 128, 128, 0, s>>>(nbuckets, toff, partial, bucket_sum, heavy, heavy_count);
   msm_heavy_kernel<<<NUM_SMS * 8, 128, 0, s>>>(toff, partial, bucket_sum, heavy, heavy_count);
   msm_red_l0_kernel<<<(n1tot + 127) / 128, 128, 0, s>>>(rd, n1tot, bucket_sum, lvl1, lvl1 + n1tot);
-  msm_red_tree_kernel<1><<<(n2tot + 3) / 4, 128, 0, s>>>(rd, 1, n2tot, lvl1, n1tot, lvl2);
+  msm_red_l1_kernel<<<(n2tot + 127) / 128, 128, 0, s>>>(rd, n2tot, lvl1, n1tot, lvl2);
   msm_red_tree_kernel<2><<<(n3tot + 3) / 4, 128, 0, s>>>(rd, 2, n3tot, lvl2, n2tot, lvl3);
   msm_red_final_kernel<<<(nwin + 3) / 4, 128, 0, s>>>(rd, lvl3, n3tot, window_sum);
   msm_finish_kernel<<<J + nderive, 32, 0, s>>>(plan, dv, window_sum, d_out);
@@ -660,6 +721,23 @@ int msm_batch(Ctx* c, const MsmJob* jobs, int J, G1Aff* d_out, const MsmDerive* 
   count_launch(c, 10);
   CUDA_TRY(cudaGetLastError());
   return B200_OK;
+}
+
+// every kernel of this file, loaded up front (b200_ctx_create -> preload_all_kernels, capi.cu)
+void preload_msm() {
+  B200_PRELOAD(msm_digits_kernel<0>);
+  B200_PRELOAD(msm_digits_kernel<1>);
+  B200_PRELOAD(scan_local_kernel);
+  B200_PRELOAD(scan_blocks_kernel);
+  B200_PRELOAD(scan_add_kernel);
+  B200_PRELOAD(msm_accumulate_kernel);
+  B200_PRELOAD(msm_bucket_kernel);
+  B200_PRELOAD(msm_heavy_kernel);
+  B200_PRELOAD(msm_red_l0_kernel);
+  B200_PRELOAD(msm_red_l1_kernel);
+  B200_PRELOAD(msm_red_tree_kernel<2>);
+  B200_PRELOAD(msm_red_final_kernel);
+  B200_PRELOAD(msm_finish_kernel);
 }
 
 }  // namespace b200

@@ -183,4 +183,12 @@ int permutation_z(Ctx* c, int num_vars, int npolys, const Fr* const* wires, cons
   return permutation_z_chunks(c, num_vars, 1, npolys, npolys, wires, sigmas, id_offsets, d_beta_gamma, zs);
 }
 
+// every kernel of this file, loaded up front (b200_ctx_create -> preload_all_kernels, capi.cu)
+void preload_perm() {
+  B200_PRELOAD(perm_products_kernel);
+  B200_PRELOAD(perm_chunk_prod_kernel);
+  B200_PRELOAD(perm_scan_kernel);
+  B200_PRELOAD(perm_write_kernel);
+}
+
 }  // namespace b200

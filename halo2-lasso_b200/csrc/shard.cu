@@ -168,22 +168,27 @@ int sumcheck_prove_evals_sharded(Ctx* c, const ScEvalJob& job_local, int n, int 
   if (G < 2 || g < 0 || n - g < 1) return B200_ERR_ARG;
   const int n_loc = n - g, ntab = job_local.T * job_local.NP;
   if (p < 0) p = n_loc;
-  if (p > n_loc || ntab + 1 > SC_MAX_TABLES) return B200_ERR_ARG;
+  if (p > n_loc || ntab > SC_MAX_TABLES) return B200_ERR_ARG;
   int R = rounds < 0 ? auto_rounds(c, n_loc, job_local.T, p) : rounds;
   if (R > p) R = p;
   cudaStream_t s = c->stream;
   DevScope mem(s);
-  Fr* eq_loc = nullptr;
-  int rc = shard_eq_build(c, mem, job_local.eq_point, n, p, g, &eq_loc, nullptr);
-  if (rc) return rc;
   const Fr* full[SC_MAX_TABLES + 1];
+  int rc;
   if (R > 0) {
-    // phase 1: R rounds on the local slices, round partials exchanged inside the round kernel
+    // phase 1: R rounds on the local slices, round partials exchanged inside the round kernel. The local eq table is
+    // eq(y_loc, .) * factor: handed over as point + scale so that the eq-factored round kernel applies.
+    Fr* y_loc = nullptr;
+    CUDA_TRY(mem.alloc(&y_loc, (size_t)(n_loc + 1) * sizeof(Fr)));
+    shard_local_point_kernel<<<1, 64, 0, s>>>(job_local.eq_point, n, p, g, c->peer.rank, y_loc, y_loc + n_loc);
+    count_launch(c);
     ScCarry carry;
     carry.scope = &mem;
     ScEvalJob j1 = job_local;
     j1.num_vars = n_loc;
-    j1.eq_table = eq_loc;
+    j1.eq_point = y_loc;
+    j1.eq_scale = y_loc + n_loc;
+    j1.eq_table = nullptr;
     j1.sharded = true;
     j1.stop_after = R;
     j1.carry = &carry;
@@ -191,6 +196,9 @@ int sumcheck_prove_evals_sharded(Ctx* c, const ScEvalJob& job_local, int n, int 
     if (rc) return rc;
     rc = shard_allgather(c, carry.cur, ntab + 1, (uint32_t)(carry.len >> 1), p - R, true, full);
   } else {
+    Fr* eq_loc = nullptr;
+    rc = shard_eq_build(c, mem, job_local.eq_point, n, p, g, &eq_loc, nullptr);
+    if (rc) return rc;
     const Fr* src[SC_MAX_TABLES + 1];
     for (int i = 0; i < ntab; ++i) src[i] = job_local.tables[i];
     src[ntab] = eq_loc;
@@ -434,6 +442,15 @@ int msm_sharded(Ctx* c, const MsmJob& local, G1Aff* d_out) {
   CUDA_TRY(cudaFreeAsync(part, c->stream));
   CUDA_TRY(cudaGetLastError());
   return B200_OK;
+}
+
+// every kernel of this file, loaded up front (b200_ctx_create -> preload_all_kernels, capi.cu)
+void preload_shard() {
+  B200_PRELOAD(shard_local_point_kernel);
+  B200_PRELOAD(shard_push_kernel);
+  B200_PRELOAD(shard_allreduce_kernel);
+  B200_PRELOAD(shard_point_sum_kernel);
+  B200_PRELOAD(shard_points_sum_kernel);
 }
 
 }  // namespace b200

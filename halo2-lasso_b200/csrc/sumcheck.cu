@@ -223,6 +223,275 @@ __global__ void __launch_bounds__(SC_THREADS) sc_eval_round_kernel(ScEvalArgs a)
 
 
 // ---------------------------------------------------------------------------------------------
+// Eq-FACTORED round kernel. eq(x, y) is a product over the variables, so the round polynomial of
+// F = eq * G factors as  p_i(X) = c_i * eq1(X, y_i) * Q_i(X),  c_i = Π_{j<i} eq1(r_j, y_j),
+// Q_i(X) = Σ_x' E_i[x'] * G(r, X, x'),  E_i = eq table of the REMAINING variables i+1..n-1 (a fixed table, never
+// bound). Q_i has degree NP, so per pair the kernel accumulates Q(1), Q(2) and the leading coefficient
+// (Q(3) = 2 Q(2) - Q(1) + 2 lead) with  E*p1, E*dp  (E*p2 is their sum)  then  *q1, *q2, *dq : 5 products plus the
+// 4 binding products = 9 per pair instead of 12, no eq-table bind, and one element read instead of four (and none
+// written) for the eq factor. The message is assembled exactly as the reference's: p(x) for x = 1..D from the
+// formula above — the same field elements as Σ eq * G — and p(0) = claim - p(1) (eval.rs:129); verified against the
+// reference messages, also for inconsistent claims, by tests/test_oracle_protocols.py::test_eq_factored_...
+// c_i and the D factors c_i * eq1(x, y_i) are computed by warp 1 of the last CTA while warp 0 sums the partials.
+// ---------------------------------------------------------------------------------------------
+struct ScFactArgs {
+  const Fr* esuf;      // E_round: 2^(n-1-round) entries
+  const Fr* y;         // device: the eq point (y[round] is this round's coordinate)
+  const Fr* eq_scale;  // optional device scalar folded into c_0
+  const Fr* in[SC_MAX_TABLES];
+  Fr* out[SC_MAX_TABLES];
+  const Fr* weights;
+  ScState* st;
+  Fr* partial;
+  Transcript* tr;
+  const BaryTable* bary;
+  Fr* challenges_out;
+  uint32_t pairs;
+  int round;
+  PeerCtx peer;
+  unsigned int seq;
+};
+
+template <int NP, bool BIND>
+__global__ void __launch_bounds__(SC_THREADS) sc_eval_fact_kernel(ScFactArgs a) {
+  constexpr int D = NP + 1;  // accumulators: NP = 2: Q(1), Q(2), lead;  NP = 1: Q(1), slope
+  __shared__ Fr smem[(SC_THREADS / 32) * D];
+  pdl_prologue();
+  const int t = blockIdx.y;
+  Fr acc[D];
+#pragma unroll
+  for (int x = 0; x < D; ++x) acc[x] = fe_zero<FrP>();
+  Fr r = fe_zero<FrP>();
+  if (BIND) r = fe_ld(&a.st->r);
+  const Fr* __restrict__ in0 = a.in[t * NP];
+  Fr* __restrict__ out0 = a.out[t * NP];
+  const Fr* __restrict__ in1 = NP == 2 ? a.in[t * NP + 1] : nullptr;
+  Fr* __restrict__ out1 = NP == 2 ? a.out[t * NP + 1] : nullptr;
+  const Fr* __restrict__ esuf = a.esuf;
+
+  for (uint32_t b = blockIdx.x * blockDim.x + threadIdx.x; b < a.pairs; b += gridDim.x * blockDim.x) {
+    Fr p0, p1, q0, q1;
+    const Fr e = fe_ldg(esuf + b);
+    load_pair<BIND>(in0, out0, b, r, true, p0, p1);
+    if (NP == 2) load_pair<BIND>(in1, out1, b, r, true, q0, q1);
+    const Fr dp = p1 - p0;
+    const Fr ep1 = e * p1, edp = e * dp;
+    if (NP == 1) {
+      acc[0] = acc[0] + ep1;
+      acc[1] = acc[1] + edp;
+    } else {
+      const Fr dq = q1 - q0;
+      acc[0] = acc[0] + ep1 * q1;
+      acc[1] = acc[1] + (ep1 + edp) * (q1 + dq);
+      acc[NP] = acc[NP] + edp * dq;
+    }
+  }
+  block_reduce_fr<D>(acc, smem);
+  if (threadIdx.x < 32) {  // lane x scales and stores partial x (one multiplication deep, not D)
+    const int lane = threadIdx.x;
+    Fr v = fe_zero<FrP>();
+#pragma unroll
+    for (int x = 0; x < D; ++x) {
+      const Fr tmp = fr_bcast(acc[x], 0);
+      if (lane == x) v = tmp;
+    }
+    v = fr_mul_ni(v, fe_ld(a.weights + t));
+    if (lane < D) fe_st(a.partial + ((size_t)t * gridDim.x + blockIdx.x) * D + lane, v);
+  }
+  if (!last_cta_ticket(&a.st->counter)) return;
+
+  // ---- last CTA: total, eq factor, derive p(0), Fiat-Shamir, fold the claim ---------------------
+  const uint32_t nparts = gridDim.x * gridDim.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __shared__ Fr s_f[4];
+  const bool keep_busy = a.peer.world > 1;
+#pragma unroll
+  for (int x = 0; x < D; ++x) acc[x] = fe_zero<FrP>();
+  if (warp == 1) {  // off the critical path: c_i = c_(i-1) * eq1(r_(i-1), y_(i-1)) and f_x = c_i * eq1(x, y_i)
+    const Fr one = fe_one<FrP>();
+    Fr c;
+    if (a.round == 0) {
+      c = a.eq_scale ? fe_ld(a.eq_scale) : one;
+    } else {
+      const Fr yp = fe_ld(a.y + a.round - 1);
+      const Fr ry = fr_mul_ni(r, yp);
+      c = fr_mul_ni(fe_ld(&a.st->eqc), ry + ry + one - r - yp);
+    }
+    const Fr yi = fe_ld(a.y + a.round);
+    const Fr step = yi + yi - one;  // eq1(x + 1, y) - eq1(x, y)
+    Fr ex = yi;                     // eq1(1, y) = y
+    for (int x = 1; x <= lane && x < D; ++x) ex = ex + step;
+    const Fr f = fr_mul_ni(c, ex);
+    if (lane < D) s_f[lane] = f;
+    if (lane == 0) fe_st(&a.st->eqc, c);
+  }
+  if (nparts <= 32) {  // small rounds: one warp sums the partials
+    if (warp == 0) {
+      if (threadIdx.x < nparts) {
+#pragma unroll
+        for (int x = 0; x < D; ++x) acc[x] = fr_ld_cg(a.partial + (size_t)threadIdx.x * D + x);
+      }
+      warp_reduce_fr<D>(acc);
+    }
+    if (warp < 2) asm volatile("bar.sync 1, 64;" ::: "memory");  // s_f of warp 1 -> warp 0
+    if (warp >= 1 && !keep_busy) return;
+  } else {
+    if (warp != 1) {  // warp 1 is busy with the eq factor: the other 7 warps stride over the partials
+      const uint32_t tid7 = warp == 0 ? threadIdx.x : threadIdx.x - 32;
+      for (uint32_t i = tid7; i < nparts; i += blockDim.x - 32) {
+#pragma unroll
+        for (int x = 0; x < D; ++x) acc[x] = acc[x] + fr_ld_cg(a.partial + (size_t)i * D + x);
+      }
+    }
+    block_reduce_fr<D>(acc, smem);  // its barriers also publish s_f
+  }
+  // Sharded rounds: warps 1-3 keep the SM busy while warp 0 runs the exchange and the finalize (peer.cuh)
+  __shared__ volatile int s_busy;
+  if (keep_busy) {
+    if (threadIdx.x == 0) s_busy = 1;
+    __syncthreads();
+    if (threadIdx.x >= 128) return;
+    if (threadIdx.x >= 32) {
+      peer_spin_while(&s_busy, &a.st->pad[0]);
+      return;
+    }
+  }
+  if (threadIdx.x < 32) {  // warp 0, warp-uniform control flow; lane i owns p(i)
+    __shared__ Transcript sh_tr;
+    trw_copy(&sh_tr, a.tr);
+    Fr tot = fe_zero<FrP>();  // lane x < D owns accumulator x
+#pragma unroll
+    for (int x = 0; x < D; ++x) {
+      const Fr tmp = fr_bcast(acc[x], 0);
+      if (lane == x) tot = tmp;
+    }
+    if (a.peer.world > 1) {  // fused collective: all-gather the D partials over NVLink and add them
+      peer_publish(a.peer, a.seq, tot, D);
+      Fr sum = fe_zero<FrP>();
+      if (lane < D)
+        for (int rr = 0; rr < a.peer.world; ++rr) sum = sum + peer_read(a.peer, a.seq, rr, lane);
+      tot = sum;
+    }
+    // Q(x) for x = 1..D into lane x
+    const Fr q1 = fr_bcast(tot, 0), q2raw = fr_bcast(tot, 1);
+    Fr qx;
+    if (NP == 1) {
+      qx = lane == 2 ? q1 + q2raw : q1;  // Q(2) = Q(1) + slope
+    } else {
+      const Fr lead = fr_bcast(tot, 2);
+      const Fr q3 = q2raw + q2raw - q1 + lead + lead;
+      qx = lane == 1 ? q1 : (lane == 2 ? q2raw : q3);
+    }
+    Fr mine = fe_zero<FrP>();
+    if (lane >= 1 && lane <= D) mine = s_f[lane - 1];
+    mine = fr_mul_ni(mine, qx);  // p(x) = c eq1(x, y_i) Q(x)
+    if (lane > D) mine = fe_zero<FrP>();
+    const Fr p1 = fr_bcast(mine, 1);
+    if (lane == 0) mine = fe_ld(&a.st->claim) - p1;  // p(0) = sum - p(1)   (eval.rs:129)
+    const Fr canon = fr_canon_ni(mine);              // D+1 conversions in parallel lanes
+    for (int x = 0; x <= D; ++x) trw_write_canon_from_lane(&sh_tr, canon, x, true);
+    const Fr ch = trw_squeeze(&sh_tr);
+    // next claim p(ch) = Σ_i p(i) w_i Π_{j != i} (ch - j): lane i builds its own term
+    const Fr one = fe_one<FrP>();
+    Fr num = lane <= D ? a.bary->w[D][lane <= D ? lane : 0] : fe_zero<FrP>();
+    Fr jf = fe_zero<FrP>();
+    for (int j = 0; j <= D; ++j) {
+      const Fr f = (j == lane) ? one : ch - jf;
+      num = fr_mul_ni(num, f);
+      jf = jf + one;
+    }
+    Fr term = fr_mul_ni(num, mine);
+    if (lane > D) term = fe_zero<FrP>();
+#pragma unroll
+    for (int off = 1; off < 8; off <<= 1) {
+      Fr o;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o.v[i] = __shfl_xor_sync(0xffffffffu, term.v[i], off);
+      term = term + o;
+    }
+    trw_copy(a.tr, &sh_tr);
+    if (lane == 0) {
+      fe_st(a.challenges_out + a.round, ch);
+      fe_st(&a.st->r, ch);
+      fe_st(&a.st->claim, term);
+    }
+    if (keep_busy && lane == 0) s_busy = 0;
+  }
+}
+
+// E_i tables of all rounds in one heap: level k (2^k entries, the table of round i = n - 1 - k over the variables
+// n-k..n-1) at [2^k, 2^(k+1)). Levels of at most SUF_DIRECT variables are computed entry by entry; a larger level is
+// L[x' & mask] * H[x' >> shift] with H the SUF_DIRECT-variable level and L the (small) table over the variables between.
+static const int SUF_DIRECT = 11;
+__device__ __forceinline__ Fr eq_entry(const Fr* __restrict__ y, int first_var, int nv, uint32_t bits) {
+  const Fr one = fe_one<FrP>();
+  Fr acc = one;
+  for (int j = 0; j < nv; ++j) {
+    const Fr yj = fe_ld(y + first_var + j);
+    acc = acc * (((bits >> j) & 1) ? yj : one - yj);
+  }
+  return acc;
+}
+// heap[e] for e in [1, 2^(nh+1)) and lheap[e] for e in [2, 2^(iH+1)): lheap level kk (2^kk entries at [2^kk, 2^(kk+1))) is
+// the table over the variables iH+1-kk..iH
+__global__ void __launch_bounds__(128) eq_suffix_small_kernel(const Fr* __restrict__ y, int n, int nh, int iH,
+                                                              Fr* __restrict__ heap, Fr* __restrict__ lheap) {
+  pdl_prologue();
+  const uint32_t nsmall = 1u << (nh + 1), nl = iH >= 0 ? (1u << (iH + 1)) : 0;
+  const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= 1 && e < nsmall) {
+    const int k = 31 - __clz(e);
+    fe_st(heap + e, eq_entry(y, n - k, k, e - (1u << k)));
+  } else if (e >= nsmall + 2 && e < nsmall + nl) {
+    const uint32_t w = e - nsmall;
+    const int kk = 31 - __clz(w);
+    fe_st(lheap + w, eq_entry(y, iH + 1 - kk, kk, w - (1u << kk)));
+  }
+}
+__global__ void __launch_bounds__(256) eq_suffix_big_kernel(int n, int nh, int iH, Fr* __restrict__ heap,
+                                                            const Fr* __restrict__ lheap) {
+  pdl_prologue();
+  const size_t total = (size_t)1 << n, stride = (size_t)gridDim.x * blockDim.x;
+  const Fr* __restrict__ H = heap + ((size_t)1 << nh);
+  for (size_t e = ((size_t)1 << (nh + 1)) + (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
+    const int k = 63 - __clzll((unsigned long long)e);  // level: k variables, n-k..n-1
+    const uint32_t x = (uint32_t)(e - ((size_t)1 << k));
+    const int kk = k - nh;                               // low variables n-k..iH
+    const Fr l = fe_ld(lheap + ((1u << kk) + (x & ((1u << kk) - 1))));
+    fe_st(heap + e, l * fe_ld(H + (x >> kk)));
+  }
+}
+static int eq_suffix_build(Ctx* c, DevScope& mem, const Fr* d_y, int n, Fr** heap_out) {
+  cudaStream_t s = c->stream;
+  const int nh = n - 1 < SUF_DIRECT ? n - 1 : SUF_DIRECT;  // variables of the largest directly computed level
+  const int iH = n - 1 - nh;                               // its round; rounds < iH use the product form
+  Fr *heap = nullptr, *lheap = nullptr;
+  CUDA_TRY(mem.alloc(&heap, sizeof(Fr) << n));
+  CUDA_TRY(mem.alloc(&lheap, sizeof(Fr) << (iH + 1)));
+  const uint32_t nthreads = (1u << (nh + 1)) + (iH > 0 ? (1u << (iH + 1)) : 0);
+  CUDA_TRY(launch_pdl(eq_suffix_small_kernel, dim3((nthreads + 127) / 128), dim3(128), 0, s, d_y, n, nh, iH > 0 ? iH : -1,
+                      heap, lheap));
+  count_launch(c);
+  if (iH > 0) {
+    const size_t big = ((size_t)1 << n) - ((size_t)1 << (nh + 1));
+    int blocks = (int)((big + 255) / 256);
+    if (blocks > NUM_SMS * 8) blocks = NUM_SMS * 8;
+    CUDA_TRY(launch_pdl(eq_suffix_big_kernel, dim3(blocks), dim3(256), 0, s, n, nh, iH, heap, (const Fr*)lheap));
+    count_launch(c);
+  }
+  *heap_out = heap;
+  return B200_OK;
+}
+// out[j] = scalar * in[j]
+__global__ void __launch_bounds__(256) scale_copy_kernel(const Fr* __restrict__ in, const Fr* __restrict__ scalar,
+                                                         Fr* __restrict__ out, size_t n) {
+  pdl_prologue();
+  const Fr sc = fe_ld(scalar);
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) fe_st(out + i, fe_ld(in + i) * sc);
+}
+
+// ---------------------------------------------------------------------------------------------
 // Tail of a sum-check in ONE launch. Once a round has at most TAIL_ITEMS (pair, term) items its kernel is pure
 // latency: launch, per-CTA partials through global memory, the last-CTA ticket, transcript copies in and out. This
 // kernel runs ALL remaining rounds in a single CTA: the tables are bound into shared memory once (<= 32 KB), each
@@ -242,6 +511,7 @@ struct ScTailArgs {
   Fr* evals_out;
   uint32_t pairs;  // pairs of the first tail round
   int T, first_round, num_rounds, want_eq_eval;
+  const Fr* eq_c;  // eq-factored rounds before the tail: in[ntab] is the unscaled E table, multiplied by *eq_c here
 };
 
 template <int NP>
@@ -261,7 +531,9 @@ __global__ void __launch_bounds__(256) sc_eval_tail_kernel(ScTailArgs a) {
   for (uint32_t e = tid; e < (uint32_t)ntabs * 2 * pairs; e += blockDim.x) {
     const uint32_t i = e / (2 * pairs), idx = e % (2 * pairs);
     const Fr x0 = fe_ldg(a.in[i] + 2 * (size_t)idx), x1 = fe_ldg(a.in[i] + 2 * (size_t)idx + 1);
-    tab[e] = (x1 - x0) * r + x0;
+    Fr v = (x1 - x0) * r + x0;
+    if (a.eq_c && i == (uint32_t)ntab) v = v * fe_ld(a.eq_c);
+    tab[e] = v;
   }
   if (tid < 32) trw_copy(&sh_tr, a.tr);
   __syncthreads();
@@ -396,6 +668,7 @@ static inline int blocks_for(uint32_t pairs, int rows) {
 int sumcheck_prove_evals(Ctx* c, const ScEvalJob& job) {
   const int n = job.num_vars, T = job.T, NP = job.NP, ntab = T * NP;
   if (n < 1 || n > 30 || T < 1 || T > SC_MAX_TERMS || (NP != 1 && NP != 2)) return B200_ERR_ARG;
+  NvtxRange nvtx("sum_check_prove-%d-%d", n, NP + 1);  // classic.rs:215-218
   cudaStream_t s = c->stream;
   const size_t N = (size_t)1 << n;
   // scratch: eq table (N) + ping-pong halves for eq and every table
@@ -407,7 +680,13 @@ int sumcheck_prove_evals(Ctx* c, const ScEvalJob& job) {
   CUDA_TRY(mem.alloc(&bufA, (size_t)(ntab + 1) * szA * sizeof(Fr)));
   CUDA_TRY(mem.alloc(&bufB, (size_t)(ntab + 1) * szB * sizeof(Fr)));
   int rc;
-  if (!job.eq_table) {
+  // eq-factored rounds (sc_eval_fact_kernel) whenever the eq table is built here from its point
+  const bool fact = c->eq_factored && !job.eq_table && !job.want_eq_eval && n >= 3;
+  Fr* suf = nullptr;  // heap of the E_i tables
+  if (fact) {
+    rc = eq_suffix_build(c, mem, job.eq_point, n, &suf);
+    if (rc) return rc;
+  } else if (!job.eq_table) {
     CUDA_TRY(mem.alloc(&eq0, N * sizeof(Fr)));
     rc = eq_build(c, job.eq_point, n, eq0);
     if (rc) return rc;
@@ -418,6 +697,18 @@ int sumcheck_prove_evals(Ctx* c, const ScEvalJob& job) {
   }
   CUDA_TRY(launch_pdl(sc_init_kernel, dim3(1), dim3(32), 0, s, c->d_sc, job.claim));
   count_launch(c);
+  ScFactArgs fa;
+  fa.y = job.eq_point;
+  fa.eq_scale = job.eq_scale;
+  fa.weights = job.weights;
+  fa.st = c->d_sc;
+  fa.partial = c->d_partial;
+  fa.tr = c->d_tr;
+  fa.bary = c->d_bary;
+  fa.challenges_out = job.challenges_out;
+  fa.peer = c->peer;
+  if (!job.sharded) fa.peer.world = 1;
+  fa.seq = 0;
 
   ScEvalArgs a;
   a.weights = job.weights;
@@ -447,11 +738,16 @@ int sumcheck_prove_evals(Ctx* c, const ScEvalJob& job) {
       a.in[i] = cur[i];
       a.out[i] = dst_base + (size_t)i * dst_sz;
     }
-    if (round >= 1 && !c->profile && !c->dbg_clocks && a.peer.world == 1 && !job.carry && (size_t)a.pairs * T <= TAIL_ITEMS &&
-        (size_t)(ntab + 1) * 2 * a.pairs <= TAIL_ENTRIES) {
+    if (round >= (fact ? 2 : 1) && !c->profile && !c->dbg_clocks && a.peer.world == 1 && !job.carry &&
+        (size_t)a.pairs * T <= TAIL_ITEMS && (size_t)(ntab + 1) * 2 * a.pairs <= TAIL_ENTRIES) {
       // all remaining rounds (and the final bind) in one single-CTA launch
       ScTailArgs ta;
       for (int i = 0; i <= ntab; ++i) ta.in[i] = cur[i];
+      ta.eq_c = nullptr;
+      if (fact) {  // the eq table before the bind of challenge round-1 is c_(round-1) * E_(round-2)
+        ta.in[ntab] = suf + ((size_t)1 << (n + 1 - round));
+        ta.eq_c = &c->d_sc->eqc;
+      }
       ta.weights = job.weights;
       ta.st = c->d_sc;
       ta.tr = c->d_tr;
@@ -471,8 +767,26 @@ int sumcheck_prove_evals(Ctx* c, const ScEvalJob& job) {
     }
     dim3 grid(blocks_for(a.pairs, T), T);
     if ((size_t)grid.x * grid.y * (NP + 1) > c->partial_elems) return B200_ERR_NOMEM;
+    NvtxRange nvtx_round("sum_check_prove_round-%d", round);  // classic.rs:226 (+ next_round :234, fused into the launch)
     const int pi = prof_begin(c, round);
-    if (round == 0) {
+    if (fact) {
+      fa.esuf = suf + ((size_t)1 << (n - 1 - round));
+      fa.pairs = a.pairs;
+      fa.round = round;
+      fa.seq = a.seq;
+      for (int i = 0; i < ntab; ++i) {
+        fa.in[i] = cur[i];
+        fa.out[i] = a.out[i];
+      }
+      if (round == 0) {
+        if (NP == 1) CUDA_TRY(launch_pdl(sc_eval_fact_kernel<1, false>, grid, SC_THREADS, 0, s, fa));
+        else CUDA_TRY(launch_pdl(sc_eval_fact_kernel<2, false>, grid, SC_THREADS, 0, s, fa));
+      } else {
+        if (NP == 1) CUDA_TRY(launch_pdl(sc_eval_fact_kernel<1, true>, grid, SC_THREADS, 0, s, fa));
+        else CUDA_TRY(launch_pdl(sc_eval_fact_kernel<2, true>, grid, SC_THREADS, 0, s, fa));
+        for (int i = 0; i < ntab; ++i) cur[i] = a.out[i];
+      }
+    } else if (round == 0) {
       if (NP == 1) CUDA_TRY(launch_pdl(sc_eval_round_kernel<1, false, false>, grid, SC_THREADS, 0, s, a));
       else CUDA_TRY(launch_pdl(sc_eval_round_kernel<2, false, false>, grid, SC_THREADS, 0, s, a));
     } else if (NP == 2 && T >= 4 && a.pairs >= 2048) {
@@ -491,8 +805,28 @@ int sumcheck_prove_evals(Ctx* c, const ScEvalJob& job) {
     count_launch(c);
   }
   if (job.carry) {  // hand over: tables as the next round would read them, last challenge pending in d_sc->r
+    const size_t len = nrounds == 1 ? N : (N >> (nrounds - 1));
+    if (fact) {  // materialise the eq table in the same (pre-bind) state: c_(R-1) * E_(R-2); R = 1: scale * eq(y, .)
+      Fr* eq_pre = nullptr;
+      CUDA_TRY(mem.alloc(&eq_pre, len * sizeof(Fr)));
+      if (nrounds == 1) {
+        rc = eq_build(c, job.eq_point, n, eq_pre);
+        if (rc) return rc;
+        if (job.eq_scale) {
+          rc = fr_scale(c, eq_pre, N, job.eq_scale);
+          if (rc) return rc;
+        }
+      } else {
+        int blocks = (int)((len + 255) / 256);
+        if (blocks > NUM_SMS * 8) blocks = NUM_SMS * 8;
+        CUDA_TRY(launch_pdl(scale_copy_kernel, dim3(blocks), dim3(256), 0, s, (const Fr*)(suf + ((size_t)1 << (n + 1 - nrounds))),
+                            (const Fr*)&c->d_sc->eqc, eq_pre, len));
+        count_launch(c);
+      }
+      cur[ntab] = eq_pre;
+    }
     for (int i = 0; i <= ntab; ++i) job.carry->cur[i] = cur[i];
-    job.carry->len = nrounds == 1 ? N : (N >> (nrounds - 1));
+    job.carry->len = len;
     CUDA_TRY(cudaGetLastError());
     return B200_OK;
   }
@@ -618,6 +952,7 @@ int sumcheck_prove_coeffs(Ctx* c, const ScCoeffJob& job) {
   const int n = job.num_vars, K = job.K;
   if (n < 1 || n > 30 || K < 1 || K > SC_MAX_TERMS) return B200_ERR_ARG;
   if ((job.stop_after > 0) != (job.carry != nullptr) || job.stop_after > n) return B200_ERR_ARG;
+  NvtxRange nvtx("sum_check_prove-%d-2", n);
   cudaStream_t s = c->stream;
   const size_t N = (size_t)1 << n;
   const size_t szA = N / 2, szB = N / 4 ? N / 4 : 1;
@@ -688,6 +1023,28 @@ int sumcheck_prove_coeffs(Ctx* c, const ScCoeffJob& job) {
   count_launch(c);
   CUDA_TRY(cudaGetLastError());
   return B200_OK;
+}
+
+// every kernel of this file, loaded up front (b200_ctx_create -> preload_all_kernels, capi.cu)
+void preload_sumcheck() {
+  B200_PRELOAD(sc_eval_round_kernel<1, false, false>);
+  B200_PRELOAD(sc_eval_round_kernel<2, false, false>);
+  B200_PRELOAD(sc_eval_round_kernel<1, true, false>);
+  B200_PRELOAD(sc_eval_round_kernel<2, true, false>);
+  B200_PRELOAD(sc_eval_round_kernel<2, true, true>);
+  B200_PRELOAD(sc_eval_fact_kernel<1, false>);
+  B200_PRELOAD(sc_eval_fact_kernel<2, false>);
+  B200_PRELOAD(sc_eval_fact_kernel<1, true>);
+  B200_PRELOAD(sc_eval_fact_kernel<2, true>);
+  B200_PRELOAD(eq_suffix_small_kernel);
+  B200_PRELOAD(eq_suffix_big_kernel);
+  B200_PRELOAD(scale_copy_kernel);
+  B200_PRELOAD(sc_eval_tail_kernel<1>);
+  B200_PRELOAD(sc_eval_tail_kernel<2>);
+  B200_PRELOAD(sc_final_bind_kernel);
+  B200_PRELOAD(sc_init_kernel);
+  B200_PRELOAD(sc_coeff_round_kernel<false>);
+  B200_PRELOAD(sc_coeff_round_kernel<true>);
 }
 
 }  // namespace b200

@@ -147,9 +147,19 @@ class MultilinearKzgVerifier:
         return _ok(lib().b200v_kzg_batch_verify(self.h, tr.h, C.c_int(nv), _p(comms), C.c_int(comms.shape[0]), _p(pts),
                                                 C.c_int(pts.shape[0]), _p(ep), _p(ept), _p(ev), C.c_int(len(evals))))
 
-    def lasso_verify(self, tr, kind, chunks, mu):
-        """the proof of `LassoProver(ctx, kzg, kind, chunks).prove(...)` for 2^mu lookups"""
-        return _ok(lib().b200v_lasso_verify(self.h, tr.h, C.c_int(kind), C.c_int(chunks), C.c_int(mu)))
+    def lasso_verify(self, tr, kind, chunks, mu, expect_a=None, expect_dims=None, want_commitments=False):
+        """the proof of `LassoProver(ctx, kzg, kind, chunks).prove(...)` for 2^mu lookups. Without `expect_a` /
+        `expect_dims` (commitments to the lookup outputs / to the c chunked operands) ACCEPT only means that SOME
+        committed a decomposes into table entries: bind the proof to your statement, or take the proof's commitments
+        (`want_commitments=True` -> (ok, [1 + 4c points])) and link them yourself."""
+        ea = np.ascontiguousarray(np.asarray(expect_a, dtype=np.uint64).reshape(8)) if expect_a is not None else None
+        ed = (np.ascontiguousarray(np.asarray(expect_dims, dtype=np.uint64).reshape(chunks, 8))
+              if expect_dims is not None else None)
+        out = np.zeros((1 + 4 * chunks, 8), dtype=np.uint64) if want_commitments else None
+        ok = _ok(lib().b200v_lasso_verify_statement(self.h, tr.h, C.c_int(kind), C.c_int(chunks), C.c_int(mu),
+                                                    _p(ea) if ea is not None else None, _p(ed) if ed is not None else None,
+                                                    _p(out) if out is not None else None))
+        return (ok, out) if want_commitments else ok
 
 
 class HyperPlonkVerifier:

@@ -36,7 +36,9 @@ bool g1_ok(const G1Affine& p) { return p.on_curve(); }
 
 // every Polynomial / Challenge / EqXY index and every rotation of the expression is usable by the verifier
 bool expr_ok(const ExprP& e, int npolys, int nchallenges, int num_vars) {
-  if (e->kind == Expr::POLY && (e->a < 0 || e->a >= npolys || std::abs(e->b) > num_vars || std::abs(e->b) > 16)) return false;
+  // (no abs(): abs(INT_MIN) is undefined and stays negative)
+  if (e->kind == Expr::POLY && (e->a < 0 || e->a >= npolys || e->b < -num_vars || e->b > num_vars || e->b < -16 || e->b > 16))
+    return false;
   if (e->kind == Expr::CHALLENGE && (e->a < 0 || e->a >= nchallenges)) return false;
   if (e->kind == Expr::EQXY && e->a != 0) return false;
   for (auto& c : e->ch)
@@ -166,12 +168,25 @@ int b200v_kzg_batch_verify(const b200v_kzg* vp, b200v_transcript* tr, int num_va
 }
 
 int b200v_lasso_verify(const b200v_kzg* vp, b200v_transcript* tr, int kind, int chunks, int mu) {
+  return b200v_lasso_verify_statement(vp, tr, kind, chunks, mu, nullptr, nullptr, nullptr);
+}
+
+int b200v_lasso_verify_statement(const b200v_kzg* vp, b200v_transcript* tr, int kind, int chunks, int mu,
+                                 const void* expect_a_g1, const void* expect_dims_g1, void* out_comms_g1) {
   if (!vp || !tr || kind < 0 || kind > 2 || chunks < 2 || chunks > 8 || (kind == TABLE_RANGE && chunks > 4) || mu < 1 ||
       mu > 30 || vp->vp.num_vars() < (mu > SUBTABLE_VARS ? mu : SUBTABLE_VARS))
     return B200V_ERR_ARG;
+  LassoStatement stm;
+  stm.expect_a = (const G1Affine*)expect_a_g1;
+  stm.expect_dims = (const G1Affine*)expect_dims_g1;
+  stm.out_comms = (G1Affine*)out_comms_g1;
+  if (stm.expect_a && !g1_ok(*stm.expect_a)) return B200V_ERR_ARG;
+  if (stm.expect_dims)
+    for (int t = 0; t < chunks; ++t)
+      if (!g1_ok(stm.expect_dims[t])) return B200V_ERR_ARG;
   return guarded([&] {
     LassoTable tb{kind, chunks};
-    return verdict(lasso_verify(vp->vp, tb, mu, tr->tr));
+    return verdict(lasso_verify(vp->vp, tb, mu, tr->tr, stm));
   });
 }
 

@@ -284,7 +284,19 @@ inline void lasso_absorb_statement(const LassoTable& tb, int mu, Transcript& tr)
   tr.common_field_element(Fr::from_u64((uint64_t)mu));
 }
 
-inline bool lasso_verify(const KzgVerifierParam& vp, const LassoTable& tb, int mu, Transcript& tr) {
+// The STATEMENT of a Lasso proof is "the committed polynomial a holds table values at the committed addresses dim_t":
+// ACCEPT alone only says that SOME committed a decomposes into table entries. A caller that cares which lookups were
+// proven must bind the proof to its own commitments: `expect_a` (the outputs) and / or `expect_dims` (c commitments to
+// the chunked operands) are compared with what the proof carries, and `out_comms` (1 + 4c points: a | dim | E |
+// read_ts | final_cts) returns the proof's commitments for linking to an outer protocol.
+struct LassoStatement {
+  const G1Affine* expect_a = nullptr;
+  const G1Affine* expect_dims = nullptr;
+  G1Affine* out_comms = nullptr;
+};
+
+inline bool lasso_verify(const KzgVerifierParam& vp, const LassoTable& tb, int mu, Transcript& tr,
+                         const LassoStatement& stm = LassoStatement()) {
   const int c = tb.chunks;
   lasso_absorb_statement(tb, mu, tr);
   std::vector<G1Affine> mcomms(1 + 3 * c), scomms(c);
@@ -292,6 +304,14 @@ inline bool lasso_verify(const KzgVerifierParam& vp, const LassoTable& tb, int m
     if (!tr.read_commitment(&p)) return false;
   for (auto& p : scomms)
     if (!tr.read_commitment(&p)) return false;
+  if (stm.out_comms) {
+    for (int i = 0; i < 1 + 3 * c; ++i) stm.out_comms[i] = mcomms[i];
+    for (int i = 0; i < c; ++i) stm.out_comms[1 + 3 * c + i] = scomms[i];
+  }
+  if (stm.expect_a && !(*stm.expect_a == mcomms[0])) return false;
+  if (stm.expect_dims)
+    for (int t = 0; t < c; ++t)
+      if (!(stm.expect_dims[t] == mcomms[1 + t])) return false;
   std::vector<Fr> r = tr.squeeze_challenges(mu);
   Fr v_a;
   if (!tr.read_field_element(&v_a)) return false;

@@ -243,11 +243,17 @@ int b200_kzg_batch_open(b200_ctx* ctx, int num_vars, const void* const* dev_poly
                         const void* host_points, int npoints, const int* ev_poly, const int* ev_point,
                         const void* host_ev_values, int nevals);
 
+/* EVAL-shape sum-checks (b200_sumcheck_prove_evals*, and those inside the Lasso / KZG provers) normally run the
+ * eq-FACTORED round kernel: p_i(X) = c_i eq1(X, y_i) Q_i(X) with Q_i accumulated against the eq table of the remaining
+ * variables (9 instead of 12 Montgomery products per pair for eq*a*b, no eq-table bind). Same messages, same bytes;
+ * on = 0 selects the plain kernel that binds a materialised eq table (kept for A/B measurements and tests). */
+int b200_sumcheck_eq_factored(b200_ctx* ctx, int on);
+
 /* ---- multi-GPU: one process per GPU, collectives through NVLink peer memory --------- */
 /* CUDA-IPC handles (128 bytes: mailbox | bulk arena) of this context; exchange the handles of all ranks out of band
  * (e.g. torch.distributed.all_gather), then call b200_dist_init with the `world` handles in rank order. world must be
  * a power of two <= 8. The mailbox carries the small in-kernel collectives (round partials, evaluations, partial
- * commitments), the arena (B200_ARENA_MB, default 192 MiB) the bulk all-gathers of bound sum-check tables. */
+ * commitments), the arena (B200_ARENA_MB, default 320 MiB) the bulk all-gathers of bound sum-check tables. */
 int b200_dist_mailbox_handle(b200_ctx* ctx, void* out_handle128);
 int b200_dist_init(b200_ctx* ctx, int rank, int world, const void* handles);
 /* The same group built from `world` contexts of ONE process (same GPU, or peer-accessible GPUs): plain device

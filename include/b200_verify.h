@@ -60,6 +60,14 @@ int b200v_kzg_batch_verify(const b200v_kzg* vp, b200v_transcript* tr, int num_va
 /* the proof of b200_lasso_prove(ctx, kind, chunks, mu, ...): kind 0 range / 1 and / 2 xor. Consumes the whole Lasso
  * section; combine with b200v_transcript_done when nothing follows it. */
 int b200v_lasso_verify(const b200v_kzg* vp, b200v_transcript* tr, int kind, int chunks, int mu);
+/* The same check BOUND TO A STATEMENT. b200v_lasso_verify alone only establishes that some committed a decomposes into
+ * table entries at some committed addresses — any prover can satisfy that. Linking the proof to the lookups the caller
+ * cares about is mandatory: pass the expected commitment to a (the lookup outputs; NULL = not compared) and / or the
+ * `chunks` expected commitments to dim_t (the chunked operands; NULL = not compared); a proof carrying other
+ * commitments is REJECTED. out_comms (1 + 4 chunks points: a | dim | E | read_ts | final_cts; NULL = not wanted)
+ * returns the commitments the proof carries so that an outer protocol can open / compare them itself. */
+int b200v_lasso_verify_statement(const b200v_kzg* vp, b200v_transcript* tr, int kind, int chunks, int mu,
+                                 const void* expect_a_g1, const void* expect_dims_g1, void* out_comms_g1);
 
 /* ---- HyperPlonk ---------------------------------------------------------------------------------------- */
 typedef struct b200v_hyperplonk b200v_hyperplonk; /* HyperPlonkVerifierParam (hyperplonk.rs:58-74) */

@@ -87,6 +87,49 @@ def test_lasso_all_distinct_addresses_is_transcript_error(hl, env):
     hl.Keccak256Transcript(ctx)
 
 
+def test_operands_outside_the_table_are_rejected_before_the_transcript(hl, env):
+    """an operand that does not fit the chunks must not be proven modulo the chunk width. Range with 2 chunks
+    and x >= 2^32, and / xor with an operand >= 2^(8c), or without the second operand: error, transcript untouched, and
+    no device memory lost over repeated failing calls (error paths release their stream-ordered scratch)."""
+    import torch
+
+    ctx, okzg, kzg = env
+    mu = 6
+    xs, _ = operands(O.TABLE_RANGE, 2, mu, 91)
+    bad = xs.copy()
+    bad[17] = np.uint64(1 << 32)
+    ctx.sync()
+    free0 = None
+    for it in range(6):
+        tr = hl.Keccak256Transcript(ctx)
+        with pytest.raises(hl.B200Error) as e:
+            hl.LassoProver(ctx, kzg, O.TABLE_RANGE, 2).prove(bad)
+        assert e.value.code == hl.B200_ERR_LOOKUP
+        assert tr.into_proof() == b""
+        ctx.sync()
+        free = torch.cuda.mem_get_info()[0]
+        if it == 1:
+            free0 = free
+        if it > 1:
+            assert free >= free0 - (1 << 20), "failing calls leak device memory"
+    xa, ya = operands(O.TABLE_AND, 4, mu, 93)
+    ya_bad = ya.copy()
+    ya_bad[3] |= np.uint64(1 << 40)
+    hl.Keccak256Transcript(ctx)
+    with pytest.raises(hl.B200Error) as e:
+        hl.LassoProver(ctx, kzg, O.TABLE_AND, 4).prove(xa, ya_bad)
+    assert e.value.code == hl.B200_ERR_LOOKUP
+    with pytest.raises(hl.B200Error) as e:
+        hl.LassoProver(ctx, kzg, O.TABLE_XOR, 4).prove(xa, None)
+    assert e.value.code == hl.B200_ERR_ARG
+    # and the valid instance still proves, byte-identical
+    to = O.Transcript()
+    assert O.lasso_prove(okzg, to, O.TABLE_RANGE, 2, mu, xs, None)
+    tr = hl.Keccak256Transcript(ctx)
+    hl.LassoProver(ctx, kzg, O.TABLE_RANGE, 2).prove(xs)
+    assert tr.into_proof() == to.proof()
+
+
 def test_device_srs_setup_matches_oracle(hl):
     """MultilinearKzg::setup on the device (kzg.rs:166-213) vs the oracle's eqs levels."""
     ctx = hl.Context(0)

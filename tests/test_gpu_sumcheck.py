@@ -119,6 +119,19 @@ def test_sumcheck_linear_g_parity(hl, ctx, n, T):
     _run_evals(hl, ctx, n, T, 1, 3000 + n)
 
 
+@pytest.mark.parametrize("n,T,NP", [(3, 1, 2), (12, 1, 2), (13, 1, 2), (14, 3, 2), (16, 2, 1), (17, 4, 2)])
+def test_sumcheck_eq_factored_and_plain_kernels_agree_with_the_oracle(hl, ctx, n, T, NP):
+    """The default round kernel factors eq out of the round polynomial (suffix eq tables: all-direct levels up to n = 12,
+    product-form levels above); the plain kernel binds a materialised eq table. Same bytes from both (random, i.e.
+    inconsistent, claims included: p(0) is derived from the claim exactly as the reference does)."""
+    _run_evals(hl, ctx, n, T, NP, 5000 + n)
+    hl.sumcheck_eq_factored(ctx, False)
+    try:
+        _run_evals(hl, ctx, n, T, NP, 5000 + n)
+    finally:
+        hl.sumcheck_eq_factored(ctx, True)
+
+
 @pytest.mark.parametrize("n,K", [(1, 1), (6, 3), (12, 2)])
 def test_sumcheck_coefficients_parity(hl, ctx, n, K):
     tabs = [O.rand_fr(4000 + n + i, 1 << n) for i in range(K)]

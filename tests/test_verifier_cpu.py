@@ -39,7 +39,7 @@ def tampered(proof, pos, bit=1):
 def test_library_exports_exactly_the_declared_symbols():
     out = subprocess.run(["nm", "-D", "--defined-only", V.LIB_PATH], capture_output=True, text=True, check=True).stdout
     exported = sorted(set(re.findall(r"\b(b200v_[a-z0-9_]+)\b", out)))
-    assert exported == V.declared_symbols() and len(exported) == 18
+    assert exported == V.declared_symbols() and len(exported) == 19
 
 
 def test_transcript_reading_side_matches_the_oracle():
@@ -154,6 +154,38 @@ def test_lasso_verify_accepts_oracle_proofs_and_rejects_tampering(okzg, vkzg, ki
         vkzg.lasso_verify(V.ProofTranscript(proof), 3, chunks, mu)
 
 
+def test_lasso_verify_binds_the_proof_to_the_callers_statement(okzg, vkzg):
+    """ACCEPT without a statement only says that SOME committed a decomposes into table entries (any prover can do that,
+    e.g. with other lookups): with the expected commitments a proof for different lookups is rejected."""
+    kind, chunks, mu = O.TABLE_AND, 4, 5
+    mask = np.uint64((1 << (8 * chunks)) - 1)
+
+    def instance(seed):
+        xs, ys = O.rand_u64s(seed, 1 << mu) & mask, O.rand_u64s(seed + 1, 1 << mu) & mask
+        xs[1::2], ys[1::2] = xs[0::2], ys[0::2]
+        to = O.Transcript()
+        assert O.lasso_prove(okzg, to, kind, chunks, mu, xs, ys)
+        mt, _ = O.lasso_witness(kind, chunks, mu, xs, ys)
+        return to.proof(), okzg.commit(mt[0]), [okzg.commit(mt[1 + t]) for t in range(chunks)]
+
+    proof, com_a, com_dims = instance(900)
+    other_proof, other_a, other_dims = instance(950)
+    tr = V.ProofTranscript(proof)
+    ok, comms = vkzg.lasso_verify(tr, kind, chunks, mu, expect_a=com_a, expect_dims=com_dims, want_commitments=True)
+    assert ok and tr.done()
+    assert (comms[0] == com_a).all() and all((comms[1 + t] == com_dims[t]).all() for t in range(chunks))
+    # a perfectly valid proof — of other lookups — does not satisfy this statement
+    assert vkzg.lasso_verify(V.ProofTranscript(other_proof), kind, chunks, mu)
+    assert not vkzg.lasso_verify(V.ProofTranscript(other_proof), kind, chunks, mu, expect_a=com_a)
+    assert not vkzg.lasso_verify(V.ProofTranscript(other_proof), kind, chunks, mu, expect_dims=com_dims)
+    assert not vkzg.lasso_verify(V.ProofTranscript(proof), kind, chunks, mu, expect_a=other_a)
+    assert vkzg.lasso_verify(V.ProofTranscript(other_proof), kind, chunks, mu, expect_a=other_a, expect_dims=other_dims)
+    off_curve = com_a.copy()
+    off_curve[0] ^= 1
+    with pytest.raises(V.VerifierArgError):
+        vkzg.lasso_verify(V.ProofTranscript(proof), kind, chunks, mu, expect_a=off_curve)
+
+
 def test_lasso_verify_accepts_the_committed_golden_proofs(vkzg):
     gold = json.load(open(os.path.join(HERE, "golden", "lasso_golden.json")))
     for c in gold["cases"]:
@@ -235,6 +267,13 @@ def test_hyperplonk_verifier_rejects_malformed_parameters(okzg, vkzg):
     for bad_expr in (expr * E.polynomial(40), expr + E.challenge(3), expr * E.eq_xy(1), E.polynomial(0, 9) * expr, E.constant(5)):
         with pytest.raises(V.VerifierArgError):
             V.HyperPlonkVerifier(vkzg, 3, info.num_instances, 3, None, 0, nz, bad_expr, pre, sig)
+    # a rotation of INT_MIN must not slip through an abs() (undefined there, and still negative): raw prefix tokens
+    # PROD [EQXY 0] [POLY 0 rot]
+    for rot in (-(2 ** 31), 2 ** 31 - 1, -17, 17):
+        with pytest.raises(V.VerifierArgError):
+            V.HyperPlonkVerifier(vkzg, 3, info.num_instances, 3, None, 0, nz,
+                                 (np.array([8, 3, 0, 4, 0, rot], dtype=np.int64).astype(np.int32), np.zeros((0, 4), dtype=np.uint64)),
+                                 pre, sig)
     with pytest.raises(V.VerifierArgError):
         V.HyperPlonkVerifier(vkzg, 3, info.num_instances, [2, 1], [0, 0], 0, nz, expr, pre, sig)  # phase 0 without challenges
     off_curve = [p.copy() for p in pre]
