@@ -37,6 +37,10 @@ static void dist_set_common(Ctx* c, int rank, int world) {
   double secs = 20.0;
   if (const char* e = getenv("B200_PEER_TIMEOUT_S")) secs = atof(e);
   c->peer.timeout_ns = (unsigned long long)(secs * 1e9);
+  // small messages: payload + release flag + acquire fence (1, default: 9 us per sharded round at 2 GPUs) or LL words
+  // (0: measured 105 us — relaxed system-scope stores are not pushed out promptly without a release)
+  c->peer.proto = 1;
+  if (const char* e = getenv("B200_PEER_PROTO")) c->peer.proto = atoi(e) ? 1 : 0;
   c->peer_seq = 0;
   c->bulk_seq = 0;
 }
@@ -89,6 +93,20 @@ int b200_dist_init_local(b200_ctx* const* ctxs, int world) {
     CUDA_TRY(cudaSetDevice(ctxs[r]->c.device));
     int rc = dist_alloc_local(&ctxs[r]->c);
     if (rc) return rc;
+  }
+  {
+    // ... and the pool must not have to GROW while collectives are in flight (growing it can wait for the device, i.e.
+    // for a kernel that is itself waiting for this rank): keep a reserve in the pool from the start. Freed blocks stay
+    // cached (the release threshold is unlimited, b200_ctx_create).
+    size_t reserve = (size_t)8 << 30;
+    if (const char* e = getenv("B200_LOCAL_POOL_RESERVE_MB")) reserve = (size_t)atol(e) << 20;
+    Ctx* c0 = &ctxs[0]->c;
+    void* p = nullptr;
+    if (reserve && cudaMallocAsync(&p, reserve, c0->stream) == cudaSuccess) {
+      cudaFreeAsync(p, c0->stream);
+      cudaStreamSynchronize(c0->stream);
+    }
+    cudaGetLastError();
   }
   for (int r = 0; r < world; ++r) {
     Ctx* c = &ctxs[r]->c;

@@ -54,7 +54,7 @@ struct Ctx {
   unsigned int bulk_seq = 0;  // bulk all-gathers issued so far
   unsigned char* my_arena = nullptr;  // bulk arena (2 halves), exported like the mailbox
   unsigned int* d_peer_err = nullptr;  // device word raised by a timed-out wait (B200_ERR_PEER)
-  int shard_min_items = 1 << 14;  // a sum-check round stays sharded while a rank has at least this many (pair, term) items
+  int shard_min_items = 1 << 16;  // a sum-check round stays sharded while a rank has at least this many (pair, term) items
   int shard_lasso_k0 = 0;  // > 0: the Lasso prover shards its tables / trees on the index window [k0 - g, k0) (lasso.cu)
   bool eq_factored = true;  // EVAL-shape sum-checks use the eq-factored round kernel (b200_sumcheck_eq_factored)
   bool shard_commits = false;  // every commitment MSM is split by point range over the ranks (all ranks call)

@@ -35,6 +35,7 @@ struct MsmJobDev {
   int kind;           // MsmScalarKind
   int c, W;           // window bits, number of windows
   uint32_t B;         // buckets per window = 2^(c-1)
+  int hist;           // 1: small-integer scalars into <= HIST_MAX_B buckets per window: digits pass with CTA histograms
   int precomp;        // 1: bases = precomputed window multiples, all windows share one bucket set
   uint32_t ext_stride;  // precomp: entries per window of the extended table
   int Wred;           // windows that need a bucket reduction (1 when precomp, else W)
@@ -101,6 +102,7 @@ __global__ void __launch_bounds__(256) msm_digits_kernel(MsmPlanDev plan, uint32
   const MsmJobDev& jb = plan.job[blockIdx.y];
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (PASS == 0) {
+    if (jb.hist) return;  // msm_digits_hist_kernel
     // Small-integer scalars (Lasso counters, 8-/16-bit subtable values) hit a handful of buckets: aggregate
     // the population atomics per warp (one atomicAdd per distinct bucket in the warp) instead of 32 colliding ones.
     const bool aggregate = jb.kind == MSM_U32 || jb.kind == MSM_U64;
@@ -155,6 +157,75 @@ __global__ void __launch_bounds__(256) msm_digits_kernel(MsmPlanDev plan, uint32
       const uint32_t bi = jb.map_g ? ((((i >> jb.map_p) << jb.map_g) | jb.map_rank) << jb.map_p) | (i & ((1u << jb.map_p) - 1)) : i;
       sorted[boff[gb] + (code & 0x7fffffffu)] = (jb.precomp ? bi + (uint32_t)w * jb.ext_stride : bi) | (code & 0x80000000u);
     }
+  }
+}
+
+// Digits pass for small-integer scalars that fall into few buckets (Lasso counters, 8-bit subtable values: 2^22
+// scalars into a few hundred buckets). Per-bucket global atomics, even warp-aggregated, serialise on those buckets;
+// here a CTA takes 2048 scalars, ranks them inside the CTA with shared-memory atomics (one histogram per window) and
+// claims its range of every non-empty bucket with ONE global atomic. Ranks inside a bucket are unique, not ordered —
+// the bucket sum does not depend on the order.
+static const uint32_t HIST_MAX_B = 4096;
+static const int HIST_K = 8;  // scalars per thread
+__global__ void __launch_bounds__(256) msm_digits_hist_kernel(MsmPlanDev plan, uint32_t* __restrict__ cnt,
+                                                              uint32_t* __restrict__ ranks) {
+  __shared__ uint32_t hist[HIST_MAX_B];
+  const MsmJobDev& jb = plan.job[blockIdx.y];
+  if (!jb.hist) return;
+  const uint32_t base_i = blockIdx.x * (256 * HIST_K), tid = threadIdx.x;
+  if (base_i >= jb.n) return;
+  uint64_t sc[HIST_K];
+#pragma unroll
+  for (int k = 0; k < HIST_K; ++k) {
+    const uint32_t i = base_i + k * 256 + tid;
+    sc[k] = 0;
+    if (i < jb.n)
+      sc[k] = jb.kind == MSM_U64 ? reinterpret_cast<const uint64_t*>(jb.scalars)[i]
+                                 : (uint64_t) reinterpret_cast<const uint32_t*>(jb.scalars)[i];
+  }
+  uint32_t carry = 0;  // bit k: carry of scalar k into the next window
+  for (int w = 0; w < jb.W; ++w) {
+    for (uint32_t b = tid; b < jb.B; b += 256) hist[b] = 0;
+    __syncthreads();
+    uint32_t lr[HIST_K];
+    int32_t dd[HIST_K];
+    const int sh = w * jb.c;
+#pragma unroll
+    for (int k = 0; k < HIST_K; ++k) {
+      const uint32_t raw = (sh < 64 ? (uint32_t)((sc[k] >> sh) & ((1u << jb.c) - 1)) : 0u) + ((carry >> k) & 1u);
+      int32_t d;
+      if (raw > jb.B) {
+        d = (int32_t)raw - (int32_t)(2 * jb.B);
+        carry |= 1u << k;
+      } else {
+        d = (int32_t)raw;
+        carry &= ~(1u << k);
+      }
+      dd[k] = d;
+      lr[k] = 0;
+      if (d != 0 && base_i + k * 256 + tid < jb.n) lr[k] = atomicAdd(&hist[(d < 0 ? -d : d) - 1], 1u);
+    }
+    __syncthreads();
+    const uint32_t gb0 = jb.bucket_base + (uint32_t)w * jb.B;
+    for (uint32_t b = tid; b < jb.B; b += 256) {
+      const uint32_t h = hist[b];
+      if (h) hist[b] = atomicAdd(&cnt[gb0 + b], h);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < HIST_K; ++k) {
+      const uint32_t i = base_i + k * 256 + tid;
+      if (i >= jb.n) continue;
+      uint32_t gb = 0xffffffffu, code = 0xffffffffu;
+      if (dd[k] != 0) {
+        const uint32_t mag = dd[k] < 0 ? (uint32_t)(-dd[k]) : (uint32_t)dd[k];
+        gb = gb0 + mag - 1;
+        code = (hist[mag - 1] + lr[k]) | (dd[k] < 0 ? 0x80000000u : 0u);
+      }
+      ranks[2 * (jb.pair_base + (uint64_t)w * jb.n + i)] = gb;
+      ranks[2 * (jb.pair_base + (uint64_t)w * jb.n + i) + 1] = code;
+    }
+    __syncthreads();
   }
 }
 
@@ -586,7 +657,7 @@ int msm_batch(Ctx* c, const MsmJob* jobs, int J, G1Aff* d_out, const MsmDerive* 
   MsmPlanDev plan;
   plan.J = J;
   uint64_t pairs = 0;
-  uint32_t nbuckets = 0, nwin = 0, max_n = 0;
+  uint32_t nbuckets = 0, nwin = 0, max_n = 0, max_n_hist = 0;
   std::vector<uint32_t> desc;  // wb | wB | off1 | off2 | off3, each nwin (+1 for the prefixes)
   std::vector<uint32_t> wb, wB;
   for (int j = 0; j < J; ++j) {
@@ -620,6 +691,8 @@ int msm_batch(Ctx* c, const MsmJob* jobs, int J, G1Aff* d_out, const MsmDerive* 
     }
     if (jb.W > MSM_MAX_WINDOWS) return B200_ERR_ARG;
     jb.B = 1u << (jb.c - 1);
+    jb.hist = (!jb.precomp && (in.kind == MSM_U32 || in.kind == MSM_U64) && jb.B <= HIST_MAX_B && in.n >= 4096) ? 1 : 0;
+    if (jb.hist && jb.n > max_n_hist) max_n_hist = jb.n;
     jb.bucket_base = nbuckets;
     jb.pair_base = pairs;
     jb.win_base = nwin;
@@ -699,6 +772,10 @@ int msm_batch(Ctx* c, const MsmJob* jobs, int J, G1Aff* d_out, const MsmDerive* 
   int pi = prof_begin(c, PH_MSM_SORT);
   msm_digits_kernel<0><<<grid, 256, 0, s>>>(plan, cnt, nullptr, ranks, nullptr);
   count_launch(c);
+  if (max_n_hist) {
+    msm_digits_hist_kernel<<<dim3((max_n_hist + 256 * HIST_K - 1) / (256 * HIST_K), J), 256, 0, s>>>(plan, cnt, ranks);
+    count_launch(c);
+  }
   int rc = exclusive_scan(c, cnt, nbuckets, boff, scratch, 0);
   if (rc) return rc;
   rc = exclusive_scan(c, cnt, nbuckets, toff, scratch, (int)task_len);
@@ -725,6 +802,7 @@ int msm_batch(Ctx* c, const MsmJob* jobs, int J, G1Aff* d_out, const MsmDerive* 
 
 // every kernel of this file, loaded up front (b200_ctx_create -> preload_all_kernels, capi.cu)
 void preload_msm() {
+  B200_PRELOAD(msm_digits_hist_kernel);
   B200_PRELOAD(msm_digits_kernel<0>);
   B200_PRELOAD(msm_digits_kernel<1>);
   B200_PRELOAD(scan_local_kernel);

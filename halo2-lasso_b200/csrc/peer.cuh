@@ -2,9 +2,12 @@
 // GPU; every rank owns a MAILBOX and a bulk ARENA in its own HBM and maps those of all peers (CUDA IPC over NVLink 5 /
 // NVSwitch; plain device pointers when several contexts share one GPU). Collectives run INSIDE the compute kernels:
 //
-//  * small messages (round partials, evaluations, commitments; <= 72 field elements): the NCCL-LL idea — every 32-bit
-//    word travels in one 8-byte store together with the collective's sequence number, so data and flag arrive
-//    atomically: no fence, no separate flag store, the reader polls the words themselves. One NVLink one-way latency.
+//  * small messages (round partials, evaluations, commitments; <= 32 field elements per warp-level all-gather): payload
+//    stores into slot [my rank] of every peer's mailbox, ONE release store of the collective's sequence number per peer,
+//    every lane r polls source r's number in the local mailbox, one acquire fence (protocol 1, the default: 9 us per
+//    sharded sum-check round at 2 GPUs). Protocol 0 is the NCCL-LL idea — every 32-bit word travels in one 8-byte store
+//    together with the sequence number, no fence at all — and measured 105 us per round on the same box: without a
+//    release the relaxed system-scope stores are not pushed out promptly (tools/micro/shard_rounds.py, profiles/).
 //  * bulk all-gathers (bound sum-check tables, tree layers): the producing kernel stores straight into every peer's
 //    arena (posted NVLink writes), its last CTA publishes a per-source sequence number with a release store and waits
 //    for the other sources with acquire loads.
@@ -23,7 +26,9 @@ static const int PEER_MAX_VALS = 72;  // field elements per small message
 struct Mailbox {
   unsigned long long ll[2][PEER_MAX_WORLD][PEER_MAX_VALS * 8];  // [parity][SOURCE rank][word]: data | seq << 32
   unsigned int bulk_seq[PEER_MAX_WORLD];                         // [SOURCE rank]: last bulk all-gather it has pushed
+  unsigned int flag_seq[2][PEER_MAX_WORLD];                      // protocol 1: [parity][SOURCE rank] sequence number
   unsigned int pad[8];
+  Fr data[2][PEER_MAX_WORLD][32];                                // protocol 1: payload ([parity][SOURCE rank][value])
 };
 struct PeerCtx {
   int rank, world;
@@ -32,6 +37,7 @@ struct PeerCtx {
   unsigned long long arena_half;
   unsigned long long timeout_ns;
   unsigned int* err;  // local device word, set to 1 when a wait timed out
+  int proto;          // small messages: 0 = LL words (data | seq in one 8-byte store), 1 = payload + release flag + acquire
 };
 
 #if defined(__CUDACC__)
@@ -83,13 +89,54 @@ __device__ __forceinline__ Fr peer_get(const PeerCtx& pc, unsigned int seq, int 
   }
   return r;
 }
-// Compatibility wrappers for warp-level callers: lanes < cnt contribute `mine`
+// Warp-level all-gather of cnt <= 32 values: called by ALL 32 lanes of one warp, lane i < cnt contributes `mine`;
+// afterwards any lane calls peer_read(src, idx). Protocol 0: LL words, the wait happens in peer_read. Protocol 1 (the
+// round-1 scheme): payload stores, one release store of the sequence number per peer, every lane r < world polls
+// source r's number in the local mailbox, one acquire fence.
 __device__ __forceinline__ void peer_publish(const PeerCtx& pc, unsigned int seq, const Fr& mine, int cnt) {
   const int lane = threadIdx.x & 31;
-  if (lane < cnt) peer_put(pc, seq, lane, mine);
+  if (pc.proto == 0) {
+    if (lane < cnt) peer_put(pc, seq, lane, mine);
+    return;
+  }
+  const int par = seq & 1;
+  if (lane < cnt) {
+    for (int r = 0; r < pc.world; ++r) {
+      volatile uint32_t* q = reinterpret_cast<volatile uint32_t*>(&pc.box[r]->data[par][pc.rank][lane]);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) q[i] = mine.v[i];
+    }
+  }
+  __syncwarp();
+  if (lane < pc.world) {
+    unsigned int* f = &pc.box[lane]->flag_seq[par][pc.rank];
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(f), "r"(seq) : "memory");
+    const unsigned int* g = &pc.box[pc.rank]->flag_seq[par][lane];
+    unsigned int v, spins = 0;
+    unsigned long long t0 = 0;
+    for (;;) {
+      asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(g) : "memory");
+      if (v == seq) break;
+      if ((++spins & 1023u) == 0) {
+        const unsigned long long now = peer_now_ns();
+        if (!t0) t0 = now;
+        else if (now - t0 > pc.timeout_ns) {
+          *pc.err = 1;
+          break;
+        }
+      }
+    }
+    asm volatile("fence.acq_rel.sys;" ::: "memory");
+  }
+  __syncwarp();
 }
 __device__ __forceinline__ Fr peer_read(const PeerCtx& pc, unsigned int seq, int src, int idx) {
-  return peer_get(pc, seq, src, idx);
+  if (pc.proto == 0) return peer_get(pc, seq, src, idx);
+  const volatile uint32_t* q = reinterpret_cast<const volatile uint32_t*>(&pc.box[pc.rank]->data[seq & 1][src][idx]);
+  Fr r;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) r.v[i] = q[i];
+  return r;
 }
 
 // Keep-busy helper. A GPU whose only activity is one warp polling NVLink-written memory drops into a low-activity

@@ -102,20 +102,20 @@ int shard_allgather(Ctx* c, const Fr* const* src, int ntab, uint32_t len, int q,
   return B200_OK;
 }
 
-// all-reduce (sum) of cnt <= PEER_MAX_VALS field elements: vals[i] <- Σ_ranks vals[i]
+// all-reduce (sum) of cnt <= 32 field elements: vals[i] <- Σ_ranks vals[i]
 __global__ void shard_allreduce_kernel(PeerCtx pc, unsigned int seq, Fr* vals, int cnt, unsigned int* sink) {
   __shared__ volatile int s_busy;
   if (threadIdx.x == 0) s_busy = 1;
   __syncthreads();
-  if (threadIdx.x >= (unsigned)((cnt + 31) & ~31)) {  // spare warps keep the SM busy during the exchange (peer.cuh)
+  if (threadIdx.x >= 32) {  // warps 1-3 keep the SM busy during the exchange (peer.cuh)
     peer_spin_while(&s_busy, sink);
     return;
   }
   const int i = threadIdx.x;
+  peer_publish(pc, seq, i < cnt ? fe_ld(vals + i) : fe_zero<FrP>(), cnt);
   if (i < cnt) {
-    peer_put(pc, seq, i, fe_ld(vals + i));
     Fr sum = fe_zero<FrP>();
-    for (int r = 0; r < pc.world; ++r) sum = sum + peer_get(pc, seq, r, i);
+    for (int r = 0; r < pc.world; ++r) sum = sum + peer_read(pc, seq, r, i);
     fe_st(vals + i, sum);
   }
   __syncwarp();
@@ -123,8 +123,8 @@ __global__ void shard_allreduce_kernel(PeerCtx pc, unsigned int seq, Fr* vals, i
 }
 int shard_allreduce(Ctx* c, Fr* d_vals, int cnt) {
   if (c->peer.world < 2) return B200_OK;
-  for (int at = 0; at < cnt; at += PEER_MAX_VALS) {
-    const int k = std::min(PEER_MAX_VALS, cnt - at);
+  for (int at = 0; at < cnt; at += 32) {
+    const int k = std::min(32, cnt - at);
     shard_allreduce_kernel<<<1, 128, 0, c->stream>>>(c->peer, ++c->peer_seq, d_vals + at, k, &c->d_sc->pad[0]);
     count_launch(c);
   }

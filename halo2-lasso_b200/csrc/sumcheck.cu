@@ -359,33 +359,32 @@ __global__ void __launch_bounds__(SC_THREADS) sc_eval_fact_kernel(ScFactArgs a) 
   if (threadIdx.x < 32) {  // warp 0, warp-uniform control flow; lane i owns p(i)
     __shared__ Transcript sh_tr;
     trw_copy(&sh_tr, a.tr);
-    Fr tot = fe_zero<FrP>();  // lane x < D owns accumulator x
-#pragma unroll
-    for (int x = 0; x < D; ++x) {
-      const Fr tmp = fr_bcast(acc[x], 0);
-      if (lane == x) tot = tmp;
+    // Q(x) for x = 1..D into lane x - 1 (this rank's part)
+    const Fr q1 = fr_bcast(acc[0], 0), q2raw = fr_bcast(acc[1], 0);
+    Fr qx;
+    if (NP == 1) {
+      qx = lane == 1 ? q1 + q2raw : q1;  // Q(2) = Q(1) + slope
+    } else {
+      const Fr lead = fr_bcast(acc[NP], 0);
+      const Fr q3 = q2raw + q2raw - q1 + lead + lead;
+      qx = lane == 0 ? q1 : (lane == 1 ? q2raw : q3);
     }
-    if (a.peer.world > 1) {  // fused collective: all-gather the D partials over NVLink and add them
-      peer_publish(a.peer, a.seq, tot, D);
+    Fr px = fe_zero<FrP>();
+    if (lane < D) px = s_f[lane];
+    px = fr_mul_ni(px, qx);  // p(x) = c eq1(x, y_i) Q(x); c carries the rank's own eq factor of the window bits
+    if (a.peer.world > 1) {  // fused collective: all-gather the D values over NVLink and add them
+      peer_publish(a.peer, a.seq, px, D);
       Fr sum = fe_zero<FrP>();
       if (lane < D)
         for (int rr = 0; rr < a.peer.world; ++rr) sum = sum + peer_read(a.peer, a.seq, rr, lane);
-      tot = sum;
+      px = sum;
     }
-    // Q(x) for x = 1..D into lane x
-    const Fr q1 = fr_bcast(tot, 0), q2raw = fr_bcast(tot, 1);
-    Fr qx;
-    if (NP == 1) {
-      qx = lane == 2 ? q1 + q2raw : q1;  // Q(2) = Q(1) + slope
-    } else {
-      const Fr lead = fr_bcast(tot, 2);
-      const Fr q3 = q2raw + q2raw - q1 + lead + lead;
-      qx = lane == 1 ? q1 : (lane == 2 ? q2raw : q3);
+    Fr mine = fe_zero<FrP>();  // lane i owns p(i)
+#pragma unroll
+    for (int x = 0; x < D; ++x) {
+      const Fr tmp = fr_bcast(px, x);
+      if (lane == x + 1) mine = tmp;
     }
-    Fr mine = fe_zero<FrP>();
-    if (lane >= 1 && lane <= D) mine = s_f[lane - 1];
-    mine = fr_mul_ni(mine, qx);  // p(x) = c eq1(x, y_i) Q(x)
-    if (lane > D) mine = fe_zero<FrP>();
     const Fr p1 = fr_bcast(mine, 1);
     if (lane == 0) mine = fe_ld(&a.st->claim) - p1;  // p(0) = sum - p(1)   (eval.rs:129)
     const Fr canon = fr_canon_ni(mine);              // D+1 conversions in parallel lanes

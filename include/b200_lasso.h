@@ -270,7 +270,7 @@ int b200_dist_check(b200_ctx* ctx);
  * byte-identical. Implies point-sharded commitments; mu <= k0 falls back to the replicated prover. 0 = off. */
 int b200_dist_shard_lasso(b200_ctx* ctx, int k0);
 /* a sharded sum-check round is exchanged over NVLink while a rank holds at least `items` (pair, term) items; below
- * that the bound tables are all-gathered once and the remaining rounds run replicated (default 2^14) */
+ * that the bound tables are all-gathered once and the remaining rounds run replicated (default 2^16) */
 int b200_dist_shard_min_items(b200_ctx* ctx, int items);
 /* Point-sharded commitments: after b200_dist_shard_commits(ctx, 1) every commitment MSM issued by b200_kzg_* and
  * b200_lasso_prove* (variable_base_msm call sites kzg.rs:255,271,292) is split by point range over the ranks and the

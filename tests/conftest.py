@@ -9,5 +9,10 @@ for p in (ROOT, os.path.join(ROOT, "oracle")):
         sys.path.insert(0, p)
 
 
+# several ranks as contexts of this process (tests/test_gpu_sharded_local.py): one hardware queue per stream, so that a
+# kernel waiting for its peers can never sit in front of a peer's kernel (read at CUDA initialisation)
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run with -m gpu on the B200 box)")

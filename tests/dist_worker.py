@@ -35,7 +35,7 @@ def check_sharded_sumchecks_in_lasso(ctx, kzg, okzg, rank, world, cases):
         hl.LassoProver(ctx, kzg, kind, chunks).prove(xs, ys)
         assert tr.into_proof() == to.proof(), f"rank {rank}: sum-check-sharded Lasso proof differs (kind {kind}, c {chunks}, mu {mu})"
     hl.dist_check(ctx)
-    hl.dist_shard_min_items(ctx, 1 << 14)
+    hl.dist_shard_min_items(ctx, 1 << 16)
     hl.dist_shard_sumchecks(ctx, 0)
     hl.dist_shard_commits(ctx, False)
 
@@ -64,7 +64,7 @@ def check_fully_sharded_lasso(ctx, kzg, okzg, rank, world, cases):
         proof = tr.into_proof()
         hl.dist_check(ctx)
         hl.dist_shard_lasso(ctx, 0)
-        hl.dist_shard_min_items(ctx, 1 << 14)
+        hl.dist_shard_min_items(ctx, 1 << 16)
         assert proof == to.proof(), f"rank {rank}: fully sharded Lasso proof differs (kind {kind}, c {chunks}, mu {mu}, k0 {k0})"
 
 

@@ -118,7 +118,7 @@ def test_fully_sharded_lasso_proof_parity(hl, groups, world, kind, chunks, mu, k
             hl.dist_check(ctx)
         finally:
             hl.dist_shard_lasso(ctx, 0)
-            hl.dist_shard_min_items(ctx, 1 << 14)
+            hl.dist_shard_min_items(ctx, 1 << 16)
         return proof
 
     for rank, proof in enumerate(hl.run_ranks(ctxs, run)):
@@ -147,7 +147,7 @@ def test_commit_and_sumcheck_sharding_of_the_replicated_prover(hl, groups, world
         finally:
             hl.dist_shard_commits(ctx, False)
             hl.dist_shard_sumchecks(ctx, 0)
-            hl.dist_shard_min_items(ctx, 1 << 14)
+            hl.dist_shard_min_items(ctx, 1 << 16)
         return proof
 
     for rank, proof in enumerate(hl.run_ranks(ctxs, run)):
