@@ -459,9 +459,13 @@ def run_ranks(ctxs, fn):
         t.start()
     for t in th:
         t.join()
-    for e in err:
-        if e is not None:
-            raise e
+    bad = [(r, e) for r, e in enumerate(err) if e is not None]
+    if bad:
+        # a rank that left early makes every other rank time out in its next collective: report the root cause (the
+        # first error that is not a peer timeout) and name what every rank saw
+        root = next((e for _, e in bad if not (isinstance(e, B200Error) and e.code == 6)), bad[0][1])
+        summary = "; ".join(f"rank {r}: {e!r}" for r, e in bad)
+        raise RuntimeError(f"run_ranks: {summary}") from root
     return out
 
 

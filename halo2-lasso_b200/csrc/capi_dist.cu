@@ -1,6 +1,7 @@
 // extern "C" boundary, part 3: multi-GPU (one process per GPU; peer mailboxes over CUDA IPC / NVLink).
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 
 #include <vector>
 
@@ -8,6 +9,16 @@
 #include "internal.h"
 
 using namespace b200;
+
+namespace b200 {
+void trace_point(Ctx* c, const char* what) {
+  static const bool on = getenv("B200_TRACE") != nullptr;
+  if (!on) return;
+  timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  fprintf(stderr, "[b200 trace] rank %d %-28s %.3f ms\n", c->peer.rank, what, ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6);
+}
+}  // namespace b200
 
 extern "C" {
 
@@ -135,7 +146,12 @@ int b200_dist_check(b200_ctx* h) {
   unsigned int v = 0;
   CUDA_TRY(cudaMemcpyAsync(&v, c->d_peer_err, 4, cudaMemcpyDeviceToHost, c->stream));
   CUDA_TRY(cudaStreamSynchronize(c->stream));
-  if (v) CUDA_TRY(cudaMemsetAsync(c->d_peer_err, 0, 4, c->stream));
+  if (v) {
+    if (getenv("B200_PEER_DEBUG"))
+      fprintf(stderr, "[b200] rank %d/%d: first timed-out wait: kind %u, source rank %u, sequence %u (small collectives issued %u, bulk %u)\n",
+              c->peer.rank, c->peer.world, v >> 28, (v >> 24) & 15u, v & 0xffffffu, c->peer_seq, c->bulk_seq);
+    CUDA_TRY(cudaMemsetAsync(c->d_peer_err, 0, 4, c->stream));
+  }
   return v ? B200_ERR_PEER : B200_OK;
 }
 

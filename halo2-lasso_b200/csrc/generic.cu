@@ -263,12 +263,8 @@ int sumcheck_prove_generic(Ctx* c, const GenericJob& job) {
   while (nth > 32 && (size_t)nslots * nth * sizeof(Fr) > 200 * 1024) nth -= 32;
   const size_t smem_bytes = (size_t)nslots * nth * sizeof(Fr);
   if (smem_bytes > 220 * 1024) return B200_ERR_ARG;
-  CUDA_TRY(cudaFuncSetAttribute(sc_generic_round_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
-  CUDA_TRY(cudaFuncSetAttribute(sc_generic_round_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
   const size_t small_bytes = (size_t)nslots * 32 * job.degree * sizeof(Fr);
   if (small_bytes > 220 * 1024) return B200_ERR_ARG;
-  CUDA_TRY(cudaFuncSetAttribute(sc_generic_small_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)small_bytes));
-  CUDA_TRY(cudaFuncSetAttribute(sc_generic_small_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)small_bytes));
   const Fr* cur[GEN_MAX_TABLES];
   for (int i = 0; i < K; ++i) cur[i] = job.tables[i];
   for (int round = 0; round < n; ++round) {
@@ -372,6 +368,13 @@ int poly_rotate(Ctx* c, const Fr* d_in, int num_vars, int rotation, Fr* d_out) {
 
 // every kernel of this file, loaded up front (b200_ctx_create -> preload_all_kernels, capi.cu)
 void preload_generic() {
+  // dynamic shared memory opt-in (up to the 220 KiB the launch sites allow), once per device: cudaFuncSetAttribute waits
+  // for kernels in flight, so it must not sit in the middle of a proof
+  const int max_smem = 220 * 1024;
+  cudaFuncSetAttribute(sc_generic_round_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+  cudaFuncSetAttribute(sc_generic_round_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+  cudaFuncSetAttribute(sc_generic_small_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+  cudaFuncSetAttribute(sc_generic_small_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
   B200_PRELOAD(sc_generic_round_kernel<false>);
   B200_PRELOAD(sc_generic_round_kernel<true>);
   B200_PRELOAD(sc_generic_small_kernel<false>);

@@ -206,6 +206,9 @@ int lasso_witness(Ctx* c, int kind, int chunks, int mu, const uint64_t* d_xs, co
 
 inline void count_launch(Ctx* c, int n = 1) { c->launches += n; }
 
+// B200_TRACE=1: host-side timeline of a rank (stderr, wall-clock ms) — for chasing stalls between the ranks of a group
+void trace_point(Ctx* c, const char* what);
+
 // CUDA loads kernels lazily, on their first launch, and that load may synchronise the whole context. A proof should not
 // stall on it, and ranks that share one context (b200_dist_init_local) would deadlock on it: a rank's kernel waiting in
 // a collective for a peer whose own kernel cannot be loaded before the context drains. cudaFuncGetAttributes forces the

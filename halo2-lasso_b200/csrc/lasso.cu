@@ -394,14 +394,14 @@ static int lasso_witness_ints(Ctx* c, DevScope& mem, int kind, int C_, int mu, c
   CUDA_TRY(cudaMemsetAsync(bad, 0, 4, s));
   int bx = (int)((m + 255) / 256);
   if (bx > NUM_SMS * 8) bx = NUM_SMS * 8;
+  trace_point(c, "witness: allocated");
   lasso_chunks_kernel<<<bx, 256, 0, s>>>(kind, C_, m, d_xs, d_ys, w->dims, w->es, w->a_u64, bad);
   // an operand outside the table is an error BEFORE anything reaches the transcript (one 4-byte read-back, the only
   // host round trip of the proof; the witness kernels below are already queued behind it)
   unsigned int h_bad = 0;
   CUDA_TRY(cudaMemcpyAsync(&h_bad, bad, 4, cudaMemcpyDeviceToHost, s));
-  const int smem = (int)(S / 2) * 4;  // 128 KiB
-  CUDA_TRY(cudaFuncSetAttribute(lasso_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  CUDA_TRY(cudaFuncSetAttribute(lasso_rank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  trace_point(c, "witness: flag copy queued");
+  const int smem = (int)(S / 2) * 4;  // 128 KiB (opted in once per device, preload_lasso)
   lasso_hist_kernel<<<dim3(nch, own), 256, smem, s>>>(m, chunk_len, w->dims, hist, t0, tstep);
   lasso_colscan_kernel<<<dim3(S / 256, own), 256, 0, s>>>(nch, hist, base, w->cts);
   lasso_rank_kernel<<<dim3(nch, own), 32, smem, s>>>(m, chunk_len, w->dims, base, w->ts, t0, tstep);
@@ -423,7 +423,9 @@ static int lasso_witness_ints(Ctx* c, DevScope& mem, int kind, int C_, int mu, c
     if (rc) return rc;
     w->cts = const_cast<uint32_t*>(reinterpret_cast<const uint32_t*>(full[0]));
   }
+  trace_point(c, "witness: kernels queued");
   CUDA_TRY(cudaStreamSynchronize(s));
+  trace_point(c, "witness: synchronised");
   return h_bad ? B200_ERR_LOOKUP : B200_OK;
 }
 
@@ -434,6 +436,7 @@ int lasso_prove(Ctx* c, int kind, int chunks, int mu, const uint64_t* d_xs, cons
   if (chunks < 2) return B200_ERR_ARG;  // additive batch_open needs >= 2 evaluations (pcs/multilinear.rs:150)
   if ((int)c->srs.size() <= (mu > SUB_VARS ? mu : SUB_VARS)) return B200_ERR_ARG;
   NvtxRange nvtx("lasso_prove-%d", mu);
+  trace_point(c, "lasso_prove: enter");
   cudaStream_t s = c->stream;
   const int C_ = chunks;
   const uint32_t m = 1u << mu;
@@ -545,8 +548,10 @@ int lasso_prove(Ctx* c, int kind, int chunks, int mu, const uint64_t* d_xs, cons
     const int NC = 1 + 4 * C_;
     CUDA_TRY(mem.alloc(&comms, (J + 1) * sizeof(G1Aff)));
     CUDA_TRY(mem.alloc(&all, NC * sizeof(G1Aff)));
+    trace_point(c, "commit: msm enqueue");
     rc = msm_batch_dist(c, jobs, J, comms, &da, 1);
     if (rc) return rc;
+    trace_point(c, "commit: msm enqueued");
     // transcript order: a | dim[c] | E[c] | read_ts[c] | final_cts[c]
     int h_src[1 + 4 * 8];
     h_src[0] = J;
@@ -677,6 +682,7 @@ int lasso_prove(Ctx* c, int kind, int chunks, int mu, const uint64_t* d_xs, cons
   }
 
   prof_end(c, ph);
+  trace_point(c, "gkr enqueued");
   ph = prof_begin(c, PH_LEAF_EVALS);
   // ---- 9. leaf openings -----------------------------------------------------------------------------
   {
@@ -731,6 +737,7 @@ int lasso_prove(Ctx* c, int kind, int chunks, int mu, const uint64_t* d_xs, cons
     prof_end(c, ph);
   }
   CUDA_TRY(cudaGetLastError());
+  trace_point(c, "lasso_prove: all enqueued");
   return B200_OK;
 }
 
@@ -761,6 +768,10 @@ int lasso_witness(Ctx* c, int kind, int chunks, int mu, const uint64_t* d_xs, co
 
 // every kernel of this file, loaded up front (b200_ctx_create -> preload_all_kernels, capi.cu)
 void preload_lasso() {
+  // cudaFuncSetAttribute waits for the device when kernels are in flight (measured: a rank of an in-process group
+  // stalled here until its peers' collective timed out), so the 128 KiB opt-in happens once, at context creation
+  cudaFuncSetAttribute(lasso_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SUB_SIZE / 2) * 4);
+  cudaFuncSetAttribute(lasso_rank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SUB_SIZE / 2) * 4);
   B200_PRELOAD(lasso_chunks_kernel);
   B200_PRELOAD(lasso_hist_kernel);
   B200_PRELOAD(lasso_colscan_kernel);

@@ -202,7 +202,6 @@ int expression_rows_prog(Ctx* c, int num_vars, const Fr* const* tables, int ntab
   while (nth > 32 && (size_t)nslots * nth * sizeof(Fr) > 100 * 1024) nth -= 32;
   const size_t smem_bytes = (size_t)nslots * nth * sizeof(Fr);
   if (smem_bytes > 220 * 1024) return B200_ERR_ARG;
-  CUDA_TRY(cudaFuncSetAttribute(expr_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
   size_t blocks = (a.N + nth - 1) / nth;
   if (blocks > 2 * NUM_SMS) blocks = 2 * NUM_SMS;
   expr_rows_kernel<<<(unsigned)blocks, nth, smem_bytes, c->stream>>>(a);
@@ -213,6 +212,7 @@ int expression_rows_prog(Ctx* c, int num_vars, const Fr* const* tables, int ntab
 
 // every kernel of this file, loaded up front (b200_ctx_create -> preload_all_kernels, capi.cu)
 void preload_lookup() {
+  cudaFuncSetAttribute(expr_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);  // once per device
   B200_PRELOAD(expr_rows_kernel);
   B200_PRELOAD(lookup_insert_kernel);
   B200_PRELOAD(lookup_count_kernel);

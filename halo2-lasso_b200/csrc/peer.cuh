@@ -36,7 +36,8 @@ struct PeerCtx {
   unsigned char* arena[PEER_MAX_WORLD];  // arena[r] = rank r's bulk arena (2 halves of arena_half bytes)
   unsigned long long arena_half;
   unsigned long long timeout_ns;
-  unsigned int* err;  // local device word, set to 1 when a wait timed out
+  unsigned int* err;  // local device word, non-zero once a wait timed out: kind << 28 | source rank << 24 | sequence number
+                      // of the FIRST wait that gave up (kind 1: LL word, 2: small-message flag, 3: bulk all-gather)
   int proto;          // small messages: 0 = LL words (data | seq in one 8-byte store), 1 = payload + release flag + acquire
 };
 
@@ -79,7 +80,7 @@ __device__ __forceinline__ Fr peer_get(const PeerCtx& pc, unsigned int seq, int 
         const unsigned long long now = peer_now_ns();
         if (!t0) t0 = now;
         else if (now - t0 > pc.timeout_ns) {
-          *pc.err = 1;
+          atomicCAS(pc.err, 0u, 0x10000000u | (seq & 0x0fffffffu));
           break;
         }
       }
@@ -121,7 +122,7 @@ __device__ __forceinline__ void peer_publish(const PeerCtx& pc, unsigned int seq
         const unsigned long long now = peer_now_ns();
         if (!t0) t0 = now;
         else if (now - t0 > pc.timeout_ns) {
-          *pc.err = 1;
+          atomicCAS(pc.err, 0u, 0x20000000u | ((unsigned)lane << 24) | (seq & 0x00ffffffu));
           break;
         }
       }
@@ -175,7 +176,7 @@ __device__ __forceinline__ void peer_bulk_commit_and_wait(const PeerCtx& pc, uns
         const unsigned long long now = peer_now_ns();
         if (!t0) t0 = now;
         else if (now - t0 > pc.timeout_ns) {
-          *pc.err = 1;
+          atomicCAS(pc.err, 0u, 0x30000000u | ((unsigned)lane << 24) | (bseq & 0x00ffffffu));
           break;
         }
       }
