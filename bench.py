@@ -387,10 +387,11 @@ def main():
         roof["frac"] = roof["achieved"] / peak
         roof["round_ms_note"] = "per-launch times with the single-launch tail kernel disabled (profiling mode)"
         # the same launch against the bound that actually limits it: Montgomery products on the IMAD (fmaheavy) pipe.
-        # Round 1 of cfg2 = 2^(n-2) output pairs x (6 binding + 6 evaluation products). Peak: the multiplier itself
+        # Round 1 of cfg2 = 2^(n-2) output pairs x (4 binding + 5 evaluation products) in the eq-factored kernel
+        # (the reference's schedule needs 12). Peak: the multiplier itself
         # measured alone on a B200 (tools/micro/pipe_rates.cu, profiles/r01_pipe_rates.txt): 537.8 cycles per warp
         # product per SM sub-partition with 4 resident warps each -> 148 SMs x 4 x 32 lanes x 1.965 GHz / 537.8.
-        prods = 12 * (1 << (SC_VARS - 2))
+        prods = 9 * (1 << (SC_VARS - 2))  # eq-factored: 4 binding + 5 evaluation products per output pair
         roof["imad"] = {"products_per_launch": prods, "achieved_gproducts_s": prods / (roof["launch_ms"] * 1e-3) / 1e9,
                         "peak_gproducts_s": round(imad_peak, 1), "frac": prods / (roof["launch_ms"] * 1e-3) / 1e9 / imad_peak,
                         "note": "IMAD-bound kernel; launch time includes the single-warp Fiat-Shamir tail"}

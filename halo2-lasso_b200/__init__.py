@@ -288,11 +288,14 @@ def profile_rounds(ctx, fn, num_vars=20, tables=3):
     if len(per_round) < 2:
         return None
     # round 1 reads `tables` tables of 2^n and writes them bound to 2^(n-1): the algorithmic bytes of that launch
+    # (the reference algorithm binds the eq table like any other table). The eq-factored kernel that runs
+    # this launch never binds an eq table: it moves tables - 1 tables plus one 2^(n-2)-entry suffix-eq table.
     algo = 32 * tables * ((1 << num_vars) + (1 << (num_vars - 1)))
+    moved = 32 * ((tables - 1) * ((1 << num_vars) + (1 << (num_vars - 1))) + (1 << (num_vars - 2)))
     t = per_round[1]
-    return {"kernel": "sc_eval_round_kernel<2,true> (round 1: fused bind + evaluate)", "launch_ms": t,
-            "algorithmic_bytes_per_launch": algo, "achieved": algo / (t * 1e-3) / 1e9,
-            "round_ms": [round(x, 5) for x in per_round]}
+    return {"kernel": "sc_eval_fact_kernel<2,true> (round 1: fused bind + eq-factored evaluate + Fiat-Shamir step)",
+            "launch_ms": t, "algorithmic_bytes_per_launch": algo, "achieved": algo / (t * 1e-3) / 1e9,
+            "kernel_bytes_per_launch": moved, "round_ms": [round(x, 5) for x in per_round]}
 
 
 def declared_symbols():
@@ -372,6 +375,27 @@ class MultilinearKzg:
 
 
 TABLE_RANGE, TABLE_AND, TABLE_XOR = 0, 1, 2
+
+
+def fractional_sum_check_prove(ctx, ps, qs, claimed_p=None, claimed_q=None):
+    """`prove_fractional_sum_check(claimed_p_0s, claimed_q_0s, ps, qs, transcript)`
+    (pb/piop/gkr/fractional_sum_check.rs:87-190) on the context's transcript. ps / qs: MultilinearPolynomial lists;
+    claimed_*: per element None (the layer-0 value is written) or anything else (Some: it is absorbed).
+    Returns (p_xs, q_xs, x, p_0s, q_0s)."""
+    B = len(ps)
+    n = ps[0].num_vars
+    assert len(qs) == B and all(t.num_vars == n for t in list(ps) + list(qs))
+    mask = 0
+    for b in range(B):
+        mask |= (claimed_p is not None and claimed_p[b] is not None) << b
+        mask |= (claimed_q is not None and claimed_q[b] is not None) << (16 + b)
+    pp = (C.c_void_p * B)(*[t.dev for t in ps])
+    qp = (C.c_void_p * B)(*[t.dev for t in qs])
+    z = lambda k: np.zeros((k, 4), dtype=np.uint64)  # noqa: E731
+    p_xs, q_xs, x, p0, q0 = z(B), z(B), z(n), z(B), z(B)
+    _chk(lib().b200_fractional_sum_check_prove(ctx.h, C.c_int(B), C.c_int(n), pp, qp, C.c_uint32(mask), _p(p_xs), _p(q_xs),
+                                               _p(x), _p(p0), _p(q0)), "fractional_sum_check_prove")
+    return p_xs, q_xs, x, p0, q0
 
 
 class LassoProver:

@@ -53,6 +53,7 @@ static int check_transcript(Ctx* c) {
 static void preload_all_kernels() {
   B200_PRELOAD(tr_init_kernel);
   preload_generic();
+  preload_gkr();
   preload_hyperplonk();
   preload_kzg();
   preload_lasso();
@@ -127,6 +128,9 @@ void b200_ctx_destroy(b200_ctx* h) {
   if (c->my_mailbox) cudaFree(c->my_mailbox);
   if (c->my_arena) cudaFree(c->my_arena);
   if (c->d_peer_err) cudaFree(c->d_peer_err);
+  if (c->hb_stream) cudaStreamDestroy(c->hb_stream);
+  if (c->hb_event) cudaEventDestroy(c->hb_event);
+  if (c->hb_stop) cudaFree(c->hb_stop);
   cudaFree(c->d_tr);
   cudaFree(c->d_proof);
   cudaFree(c->d_bary);

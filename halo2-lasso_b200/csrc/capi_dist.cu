@@ -51,9 +51,26 @@ static void dist_set_common(Ctx* c, int rank, int world) {
   // small messages: payload + release flag + acquire fence (1, default: 9 us per sharded round at 2 GPUs) or LL words
   // (0: measured 105 us — relaxed system-scope stores are not pushed out promptly without a release)
   c->peer.proto = 1;
-  if (const char* e = getenv("B200_PEER_PROTO")) c->peer.proto = atoi(e) ? 1 : 0;
+  if (const char* e = getenv("B200_PEER_PROTO")) c->peer.proto = atoi(e) < 0 || atoi(e) > 2 ? 1 : atoi(e);
   c->peer_seq = 0;
   c->bulk_seq = 0;
+  c->hb_ctas = 0;
+  if (const char* e = getenv("B200_HEARTBEAT")) {  // "ctas,sleep_ns,write_peers"
+    int a = 0, b = 1000, w = 1;
+    if (sscanf(e, "%d,%d,%d", &a, &b, &w) >= 1 && a > 0) {
+      c->hb_ctas = a > 8 ? 8 : a;
+      c->hb_sleep_ns = b < 0 ? 0 : b;
+      c->hb_write = w;
+      if (!c->hb_stream) {
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        cudaStreamCreateWithPriority(&c->hb_stream, cudaStreamNonBlocking, lo);
+        cudaEventCreateWithFlags(&c->hb_event, cudaEventDisableTiming);
+        cudaMalloc(&c->hb_stop, sizeof(unsigned int));
+        cudaMemset(c->hb_stop, 0, sizeof(unsigned int));
+      }
+    }
+  }
 }
 
 // out_handle: 128 bytes = CUDA-IPC handle of the mailbox | CUDA-IPC handle of the bulk arena
@@ -165,6 +182,29 @@ int b200_dist_shard_lasso(b200_ctx* h, int k0) {
   if (k0 < 0 || (k0 && (c->peer.world < 2 || k0 - g < 1 || k0 > 28))) return B200_ERR_ARG;
   c->shard_lasso_k0 = k0;
   return B200_OK;
+}
+// runtime knobs of the exchange (experiments, tools/micro): key 0 = small-message protocol (0 LL words, 1 release flag +
+// fence, 2 release flag + acquire polls), key 1 = heartbeat CTAs (0 = off; needs a context created with B200_HEARTBEAT),
+// key 2 = heartbeat sleep ns, key 3 = heartbeat mode bits
+int b200_dist_tune(b200_ctx* h, int key, int value) {
+  Ctx* c = &h->c;
+  switch (key) {
+    case 0:
+      if (value < 0 || value > 2) return B200_ERR_ARG;
+      c->peer.proto = value;
+      return B200_OK;
+    case 1:
+      if (value < 0 || value > 8 || (value && !c->hb_stream)) return B200_ERR_ARG;
+      c->hb_ctas = value;
+      return B200_OK;
+    case 2:
+      c->hb_sleep_ns = value < 0 ? 0 : value;
+      return B200_OK;
+    case 3:
+      c->hb_write = value;
+      return B200_OK;
+  }
+  return B200_ERR_ARG;
 }
 int b200_dist_shard_min_items(b200_ctx* h, int items) {
   if (items < 1) return B200_ERR_ARG;

@@ -166,6 +166,34 @@ int b200_lasso_prove(b200_ctx* h, int kind, int chunks, int mu, const uint64_t* 
   return t.error ? B200_ERR_TRANSCRIPT : B200_OK;
 }
 
+int b200_fractional_sum_check_prove(b200_ctx* h, int num_batching, int num_vars, const void* const* dev_ps,
+                                    const void* const* dev_qs, uint32_t claimed_mask, void* host_p_xs, void* host_q_xs,
+                                    void* host_x, void* host_p_0s, void* host_q_0s) {
+  Ctx* c = &h->c;
+  const int B = num_batching, n = num_vars;
+  if (B < 1 || B > 10 || n < 1 || n > 28 || !dev_ps || !dev_qs) return B200_ERR_ARG;
+  for (int b = 0; b < B; ++b)
+    if (!dev_ps[b] || !dev_qs[b]) return B200_ERR_ARG;
+  DevScope mem(c->stream);
+  Fr* d_out = nullptr;
+  const size_t nout = (size_t)4 * B + n;
+  CUDA_TRY(mem.alloc(&d_out, nout * sizeof(Fr)));
+  int rc = fractional_sum_check_prove(c, B, n, (const Fr* const*)dev_ps, (const Fr* const*)dev_qs, claimed_mask, d_out);
+  if (rc) return rc;
+  std::vector<Fr> hout(nout);
+  Transcript t;
+  CUDA_TRY(cudaMemcpyAsync(hout.data(), d_out, nout * sizeof(Fr), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(cudaMemcpyAsync(&t, c->d_tr, sizeof(t), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  if (t.error) return B200_ERR_TRANSCRIPT;
+  if (host_p_xs) memcpy(host_p_xs, hout.data(), B * sizeof(Fr));
+  if (host_q_xs) memcpy(host_q_xs, hout.data() + B, B * sizeof(Fr));
+  if (host_x) memcpy(host_x, hout.data() + 2 * B, n * sizeof(Fr));
+  if (host_p_0s) memcpy(host_p_0s, hout.data() + 2 * B + n, B * sizeof(Fr));
+  if (host_q_0s) memcpy(host_q_0s, hout.data() + 3 * B + n, B * sizeof(Fr));
+  return B200_OK;
+}
+
 int b200_lasso_witness(b200_ctx* h, int kind, int chunks, int mu, const uint64_t* host_xs, const uint64_t* host_ys,
                        void* dev_mtabs, void* dev_stabs) {
   Ctx* c = &h->c;

@@ -54,6 +54,13 @@ struct Ctx {
   unsigned int bulk_seq = 0;  // bulk all-gathers issued so far
   unsigned char* my_arena = nullptr;  // bulk arena (2 halves), exported like the mailbox
   unsigned int* d_peer_err = nullptr;  // device word raised by a timed-out wait (B200_ERR_PEER)
+  // heartbeat (B200_HEARTBEAT="ctas,sleep_ns,write_peers"): a low-priority side kernel that keeps SMs and NVLink links
+  // from idling while a sharded proof is latency-bound (shard.cu: HeartbeatScope)
+  cudaStream_t hb_stream = nullptr;
+  cudaEvent_t hb_event = nullptr;
+  unsigned int* hb_stop = nullptr;  // device word: the running heartbeat kernel leaves when it equals its generation
+  unsigned int hb_gen = 0;
+  int hb_ctas = 0, hb_sleep_ns = 1000, hb_write = 1, hb_depth = 0;
   int shard_min_items = 1 << 16;  // a sum-check round stays sharded while a rank has at least this many (pair, term) items
   int shard_lasso_k0 = 0;  // > 0: the Lasso prover shards its tables / trees on the index window [k0 - g, k0) (lasso.cu)
   bool eq_factored = true;  // EVAL-shape sum-checks use the eq-factored round kernel (b200_sumcheck_eq_factored)
@@ -199,6 +206,12 @@ int kzg_batch_open(Ctx* c, const BatchOpenJob& job);
 int kzg_setup(Ctx* c, const Fr* d_ss, int n);
 int kzg_build_ext(Ctx* c, int level);  // fills c->srs_ext[level]
 
+// gkr.cu — GKR for fractional sum-checks (pb/piop/gkr/fractional_sum_check.rs:87-190)
+// d_out: p_xs[B] | q_xs[B] | x[n] | p_0s[B] | q_0s[B]; claimed_mask bit b / 16 + b: the layer-0 value p_b / q_b is a
+// public claim (absorbed) instead of being written to the proof
+int fractional_sum_check_prove(Ctx* c, int B, int n, const Fr* const* d_ps, const Fr* const* d_qs, uint32_t claimed_mask,
+                               Fr* d_out);
+
 // lasso.cu — Lasso / Surge prover (DESIGN.md §Lasso protocol; oracle/lasso.hpp)
 int lasso_prove(Ctx* c, int kind, int chunks, int mu, const uint64_t* d_xs, const uint64_t* d_ys);
 int lasso_witness(Ctx* c, int kind, int chunks, int mu, const uint64_t* d_xs, const uint64_t* d_ys, Fr* d_mt,
@@ -219,6 +232,7 @@ void trace_point(Ctx* c, const char* what);
     cudaFuncGetAttributes(&fa_, (const void*)(__VA_ARGS__)); \
   } while (0)
 void preload_generic();
+void preload_gkr();
 void preload_hyperplonk();
 void preload_kzg();
 void preload_lasso();
@@ -264,6 +278,14 @@ struct DevScope {
   ~DevScope() {
     for (void* p : ptrs) cudaFreeAsync(p, s);
   }
+};
+// Keeps the heartbeat kernel (if configured) running for the lifetime of the scope, in STREAM order: started behind what
+// is already queued on ctx->stream, stopped by a tiny kernel queued when the scope ends. Nested scopes share one.
+struct HeartbeatScope {
+  Ctx* c;
+  explicit HeartbeatScope(Ctx* ctx);
+  ~HeartbeatScope();
+  HeartbeatScope(const HeartbeatScope&) = delete;
 };
 // returns the index of the (start, stop) event pair, or -1 when profiling is off; pairs may nest
 inline int prof_begin(Ctx* c, int tag) {

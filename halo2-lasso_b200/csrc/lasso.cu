@@ -459,6 +459,7 @@ int lasso_prove(Ctx* c, int kind, int chunks, int mu, const uint64_t* d_xs, cons
     bool v;
     ~Restore() { c->shard_commits = v; }
   } restore{c, saved_shard_commits};
+  HeartbeatScope hb(c);
   DevScope mem(s);
 
   // ---- 1. witness (integers, all lookups) ------------------------------------------------------------

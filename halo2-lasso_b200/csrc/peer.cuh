@@ -116,7 +116,8 @@ __device__ __forceinline__ void peer_publish(const PeerCtx& pc, unsigned int seq
     unsigned int v, spins = 0;
     unsigned long long t0 = 0;
     for (;;) {
-      asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(g) : "memory");
+      if (pc.proto == 2) asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(g) : "memory");
+      else asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(g) : "memory");
       if (v == seq) break;
       if ((++spins & 1023u) == 0) {
         const unsigned long long now = peer_now_ns();
@@ -127,7 +128,9 @@ __device__ __forceinline__ void peer_publish(const PeerCtx& pc, unsigned int seq
         }
       }
     }
-    asm volatile("fence.acq_rel.sys;" ::: "memory");
+    // protocol 1: full system-scope fence after the poll. Protocol 2: the poll itself is an acquire load (below) and the
+    // payload is read with L1-bypassing volatile loads, so no fence follows.
+    if (pc.proto != 2) asm volatile("fence.acq_rel.sys;" ::: "memory");
   }
   __syncwarp();
 }

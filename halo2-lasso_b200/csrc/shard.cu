@@ -132,6 +132,65 @@ int shard_allreduce(Ctx* c, Fr* d_vals, int cnt) {
   return B200_OK;
 }
 
+// ---- heartbeat -------------------------------------------------------------------------------------------------
+// Experiment / mitigation for the 8-GPU round latency: between two exchanges a rank's GPU runs ONE warp
+// and its NVLink links carry nothing for tens of microseconds. `ctas` single-warp CTAs issue a few FMAs every
+// `sleep_ns`; lane r of CTA 0 also stores a word into rank r's mailbox pad, so every link stays trained. The kernel
+// leaves when *stop == gen (set in stream order by hb_stop_kernel) or after 2 s, whichever comes first. Keep `ctas`
+// small: a resident heartbeat CTA pins its SM's shared-memory carveout, and a kernel that needs another carveout cannot
+// start there until the heartbeat leaves (measured: 148 CTAs stalled every proof for the full 2 s).
+// mode bit 0: store a word into every rank's mailbox pad (NVLink traffic); bit 1: stream 128-byte reads through the
+// rank's own bulk arena (HBM traffic that misses L2 sooner or later)
+__global__ void __launch_bounds__(32) peer_heartbeat_kernel(PeerCtx pc, const unsigned int* stop, unsigned int gen,
+                                                            unsigned int sleep_ns, int mode, unsigned int* sink) {
+  const int lane = threadIdx.x;
+  const unsigned long long t0 = peer_now_ns();
+  float x = (float)lane;
+  unsigned int beat = 0, junk = 0;
+  const unsigned int* arena = reinterpret_cast<const unsigned int*>(pc.arena[pc.rank]);
+  const size_t arena_words = (size_t)(2 * pc.arena_half / 4);
+  size_t at = (size_t)blockIdx.x * 4096 + lane;
+  for (;;) {
+    unsigned int v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(stop) : "memory");
+    if (v == gen || peer_now_ns() - t0 > 2000000000ull) break;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) x = fmaf(x, 1.0001f, 0.5f);
+    if ((mode & 1) && blockIdx.x == 0 && lane < pc.world) {
+      unsigned int* q = &pc.box[lane]->pad[pc.rank & 7];
+      asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(q), "r"(++beat) : "memory");
+    }
+    if (mode & 2) {
+      unsigned int w;
+      asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(w) : "l"(arena + at) : "memory");
+      junk ^= w;
+      at += 32 * 1024;  // a new 128-byte line (and DRAM page) every beat
+      if (at >= arena_words) at = lane;
+    }
+    if (sleep_ns) __nanosleep(sleep_ns);
+  }
+  if (x == 12345.678f || junk == 0x12345678u) *sink = 0;
+}
+__global__ void hb_stop_kernel(unsigned int* stop, unsigned int gen) {
+  if (threadIdx.x == 0) asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(stop), "r"(gen) : "memory");
+}
+HeartbeatScope::HeartbeatScope(Ctx* ctx) : c(ctx) {
+  if (c->hb_ctas <= 0 || c->peer.world < 2 || !c->hb_stream) return;
+  if (c->hb_depth++ > 0) return;
+  ++c->hb_gen;
+  cudaEventRecord(c->hb_event, c->stream);
+  cudaStreamWaitEvent(c->hb_stream, c->hb_event, 0);
+  peer_heartbeat_kernel<<<c->hb_ctas, 32, 0, c->hb_stream>>>(c->peer, c->hb_stop, c->hb_gen, (unsigned)c->hb_sleep_ns,
+                                                             c->hb_write, &c->d_sc->pad[1]);
+  count_launch(c);
+}
+HeartbeatScope::~HeartbeatScope() {
+  if (c->hb_ctas <= 0 || c->peer.world < 2 || !c->hb_stream) return;
+  if (--c->hb_depth > 0) return;
+  hb_stop_kernel<<<1, 32, 0, c->stream>>>(c->hb_stop, c->hb_gen);
+  count_launch(c);
+}
+
 static int ilog2_exact(int G) {
   int g = 0;
   while ((1 << g) < G) ++g;
@@ -172,6 +231,7 @@ int sumcheck_prove_evals_sharded(Ctx* c, const ScEvalJob& job_local, int n, int 
   int R = rounds < 0 ? auto_rounds(c, n_loc, job_local.T, p) : rounds;
   if (R > p) R = p;
   cudaStream_t s = c->stream;
+  HeartbeatScope hb(c);
   DevScope mem(s);
   const Fr* full[SC_MAX_TABLES + 1];
   int rc;
@@ -451,6 +511,8 @@ void preload_shard() {
   B200_PRELOAD(shard_allreduce_kernel);
   B200_PRELOAD(shard_point_sum_kernel);
   B200_PRELOAD(shard_points_sum_kernel);
+  B200_PRELOAD(peer_heartbeat_kernel);
+  B200_PRELOAD(hb_stop_kernel);
 }
 
 }  // namespace b200

@@ -269,6 +269,9 @@ int b200_dist_check(b200_ctx* ctx);
  * binds (multilinear.rs:612-616) and under the top-bit tree halving (fractional_sum_check.rs:41-76). Proofs stay
  * byte-identical. Implies point-sharded commitments; mu <= k0 falls back to the replicated prover. 0 = off. */
 int b200_dist_shard_lasso(b200_ctx* ctx, int k0);
+/* exchange tuning knobs for experiments (tools/micro/shard_tune.py): key 0 small-message protocol (0, 1, 2), key 1
+ * heartbeat CTAs (0 = off), key 2 heartbeat sleep in ns, key 3 heartbeat mode bits (1 NVLink stores, 2 HBM reads) */
+int b200_dist_tune(b200_ctx* ctx, int key, int value);
 /* a sharded sum-check round is exchanged over NVLink while a rank holds at least `items` (pair, term) items; below
  * that the bound tables are all-gathered once and the remaining rounds run replicated (default 2^16) */
 int b200_dist_shard_min_items(b200_ctx* ctx, int items);
@@ -316,6 +319,14 @@ int b200_lasso_prove(b200_ctx* ctx, int table_kind, int chunks, int mu, const ui
                      const uint64_t* host_ys);
 /* same with operands already on the device (u64 arrays) */
 int b200_lasso_prove_dev(b200_ctx* ctx, int table_kind, int chunks, int mu, const void* dev_xs, const void* dev_ys);
+/* prove_fractional_sum_check (pb/piop/gkr/fractional_sum_check.rs:87-190): GKR argument for Σ_i p_b[i] / q_b[i] over
+ * num_batching (<= 10) pairs of 2^num_vars-entry device tables (Montgomery Fr), on the context's transcript: writes (or,
+ * where bit b / bit 16 + b of claimed_mask marks p_b / q_b as a public claim = Some(_), absorbs) the layer-0 values, then
+ * per layer gamma, the degree-3 ClassicSumCheck<EvaluationsProver> rounds, the 4 * num_batching evaluations and mu, exactly
+ * as the reference. Returns (p_xs, q_xs, x) of the reference plus the layer-0 values (host buffers, may be NULL). */
+int b200_fractional_sum_check_prove(b200_ctx* ctx, int num_batching, int num_vars, const void* const* dev_ps,
+                                    const void* const* dev_qs, uint32_t claimed_mask, void* host_p_xs, void* host_q_xs,
+                                    void* host_x, void* host_p_0s, void* host_q_0s);
 /* witness tables only: dev_mtabs = a | dim[c] | E[c] | read_ts[c] (2^mu each), dev_stabs = final_cts[c] (2^16 each) */
 int b200_lasso_witness(b200_ctx* ctx, int table_kind, int chunks, int mu, const uint64_t* host_xs,
                        const uint64_t* host_ys, void* dev_mtabs, void* dev_stabs);

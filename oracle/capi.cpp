@@ -6,6 +6,7 @@
 #include <cstdio>
 
 #include "expression.hpp"
+#include "gkr.hpp"
 #include "hyperplonk.hpp"
 #include "lasso.hpp"
 
@@ -458,6 +459,49 @@ void orc_grand_product_prove(void* tr, int T, int h, const Fr* const* leaves, Fr
   GrandProductOutput o = grand_product_prove(lv, *(Transcript*)tr, nullptr);
   memcpy(claims, o.claims.data(), T * sizeof(Fr));
   memcpy(point, o.point.data(), h * sizeof(Fr));
+}
+
+// fractional_sum_check.rs: prove. claimed_mask bit b (p) / bit 16 + b (q): Some(claimed) -> absorbed, else written.
+// outputs: p_xs[B], q_xs[B], x[n], p_0s[B], q_0s[B]
+void orc_fractional_prove(void* tr, int B, int n, const Fr* const* ps, const Fr* const* qs, uint32_t claimed_mask,
+                          Fr* p_xs, Fr* q_xs, Fr* x, Fr* p_0s, Fr* q_0s) {
+  std::vector<Poly> P(B), Q(B);
+  std::vector<const Poly*> pp(B), qp(B);
+  for (int b = 0; b < B; ++b) {
+    P[b].assign(ps[b], ps[b] + ((size_t)1 << n));
+    Q[b].assign(qs[b], qs[b] + ((size_t)1 << n));
+    pp[b] = &P[b];
+    qp[b] = &Q[b];
+  }
+  const Fr dummy = Fr::zero();  // Some(_): only the presence matters on the prover side (sanity-check feature off)
+  std::vector<const Fr*> cp(B), cq(B);
+  for (int b = 0; b < B; ++b) {
+    cp[b] = (claimed_mask >> b) & 1 ? &dummy : nullptr;
+    cq[b] = (claimed_mask >> (16 + b)) & 1 ? &dummy : nullptr;
+  }
+  FractionalOutput o = fractional_sum_check_prove(cp, cq, pp, qp, *(Transcript*)tr);
+  memcpy(p_xs, o.p_xs.data(), B * sizeof(Fr));
+  memcpy(q_xs, o.q_xs.data(), B * sizeof(Fr));
+  memcpy(x, o.x.data(), n * sizeof(Fr));
+  memcpy(p_0s, o.p_0s.data(), B * sizeof(Fr));
+  memcpy(q_0s, o.q_0s.data(), B * sizeof(Fr));
+}
+// verify: claimed values are read from claimed_p / claimed_q where the mask bit is set; 0 = accept
+int orc_fractional_verify(void* tr, int B, int n, uint32_t claimed_mask, const Fr* claimed_p, const Fr* claimed_q,
+                          Fr* p_xs, Fr* q_xs, Fr* x, Fr* p_0s, Fr* q_0s) {
+  std::vector<const Fr*> cp(B), cq(B);
+  for (int b = 0; b < B; ++b) {
+    cp[b] = (claimed_mask >> b) & 1 ? claimed_p + b : nullptr;
+    cq[b] = (claimed_mask >> (16 + b)) & 1 ? claimed_q + b : nullptr;
+  }
+  FractionalOutput o;
+  if (!fractional_sum_check_verify(n, cp, cq, *(Transcript*)tr, &o)) return 1;
+  memcpy(p_xs, o.p_xs.data(), B * sizeof(Fr));
+  memcpy(q_xs, o.q_xs.data(), B * sizeof(Fr));
+  memcpy(x, o.x.data(), n * sizeof(Fr));
+  memcpy(p_0s, o.p_0s.data(), B * sizeof(Fr));
+  memcpy(q_0s, o.q_0s.data(), B * sizeof(Fr));
+  return 0;
 }
 
 }  // extern "C"

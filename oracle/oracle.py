@@ -634,3 +634,43 @@ def grand_product_prove(tr, leaves):
     claims, point = _fr(T), _fr(h)
     lib().orc_grand_product_prove(tr.h, C.c_int(T), C.c_int(h), ptrs, _p(claims), _p(point))
     return claims, point
+
+
+def _claimed_mask(claimed_p, claimed_q):
+    mask = 0
+    for b, v in enumerate(claimed_p):
+        mask |= (v is not None) << b
+    for b, v in enumerate(claimed_q):
+        mask |= (v is not None) << (16 + b)
+    return mask
+
+
+def fractional_sum_check_prove(tr, ps, qs, claimed_p=None, claimed_q=None):
+    """prove_fractional_sum_check (pb/piop/gkr/fractional_sum_check.rs:87-190). claimed_*: per batch element None (the
+    layer-0 value is written) or anything else (it is absorbed). Returns (p_xs, q_xs, x, p_0s, q_0s)."""
+    pa, pptr = _ptr_array(ps)
+    qa, qptr = _ptr_array(qs)
+    B = len(ps)
+    n = int(pa[0].shape[0]).bit_length() - 1
+    claimed_p = [None] * B if claimed_p is None else claimed_p
+    claimed_q = [None] * B if claimed_q is None else claimed_q
+    p_xs, q_xs, x, p0, q0 = _fr(B), _fr(B), _fr(n), _fr(B), _fr(B)
+    lib().orc_fractional_prove(tr.h, C.c_int(B), C.c_int(n), pptr, qptr, C.c_uint32(_claimed_mask(claimed_p, claimed_q)),
+                               _p(p_xs), _p(q_xs), _p(x), _p(p0), _p(q0))
+    return p_xs, q_xs, x, p0, q0
+
+
+def fractional_sum_check_verify(tr, num_vars, claimed_p, claimed_q):
+    """verify_fractional_sum_check (:192-265); claimed_*: list of None / Fr. Returns None on reject, else the tuple of
+    fractional_sum_check_prove."""
+    B = len(claimed_p)
+    cp, cq = _fr(B), _fr(B)
+    for b in range(B):
+        if claimed_p[b] is not None:
+            cp[b] = claimed_p[b]
+        if claimed_q[b] is not None:
+            cq[b] = claimed_q[b]
+    p_xs, q_xs, x, p0, q0 = _fr(B), _fr(B), _fr(num_vars), _fr(B), _fr(B)
+    rc = lib().orc_fractional_verify(tr.h, C.c_int(B), C.c_int(num_vars), C.c_uint32(_claimed_mask(claimed_p, claimed_q)),
+                                     _p(cp), _p(cq), _p(p_xs), _p(q_xs), _p(x), _p(p0), _p(q0))
+    return None if rc else (p_xs, q_xs, x, p0, q0)

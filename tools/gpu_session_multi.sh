@@ -7,7 +7,7 @@ timeout 400 $TR --master-port 29511 tests/dist_worker.py > $O/dist_worker_${N}gp
 echo "dist_worker rc=$?"; grep -E "OK|Error|rror:|assert|differs" $O/dist_worker_${N}gpu.log | head -10
 timeout 600 $TR --master-port 29512 bench.py --gpus $N --steps ${3:-5} --warmup 3 > $O/bench_${N}gpu.json 2> $O/bench_${N}gpu.err
 echo "bench rc=$?"; tail -c 2500 $O/bench_${N}gpu.json; tail -5 $O/bench_${N}gpu.err
-for PROTO in 0 1; do
+for PROTO in ${PROTOS:-1}; do
   B200_PEER_PROTO=$PROTO timeout 300 $TR --master-port 2951$((3 + PROTO)) tools/micro/shard_rounds.py 14 18 > $O/shard_rounds_${N}gpu_proto$PROTO.log 2>&1
   echo "proto $PROTO:"; grep SHARD_ROUNDS $O/shard_rounds_${N}gpu_proto$PROTO.log
 done
