@@ -398,15 +398,56 @@ def fractional_sum_check_prove(ctx, ps, qs, claimed_p=None, claimed_q=None):
     return p_xs, q_xs, x, p0, q0
 
 
-class LassoProver:
-    """Lasso / Surge lookup prover (north_star; DESIGN.md "Lasso protocol"). `table` mirrors a
-    `DecomposableTable`: kind (range / and / xor) + number of 16-bit-addressed chunks."""
+class _LassoTableC(C.Structure):
+    _fields_ = [("chunks", C.c_int), ("num_operands", C.c_int), ("operand_bits", C.c_int), ("out_bits", C.c_int),
+                ("subtable", C.c_void_p)]
 
-    def __init__(self, ctx, kzg, kind, chunks):
-        self.ctx, self.kzg, self.kind, self.chunks = ctx, kzg, kind, chunks
+
+class LassoTable:
+    """A decomposable table given as DATA — the role of a `DecomposableTable` implementation in the Lasso frontend
+    (chunk bits, subtable values, the combiner g): `chunks` chunks, each addressing ONE 2^16-entry subtable `values`;
+    one operand (dim_t = chunk t of x) or two (dim_t = chunk t of x << operand_bits | chunk t of y);
+    lookup output g(E) = Σ_t 2^(out_bits t) E_t. `subtable_fn(address) -> value` may be given instead of `values`."""
+
+    def __init__(self, chunks, num_operands, operand_bits, out_bits, values=None, subtable_fn=None):
+        if values is None:
+            values = [subtable_fn(x) for x in range(1 << 16)]
+        self.chunks, self.num_operands, self.operand_bits, self.out_bits = chunks, num_operands, operand_bits, out_bits
+        self.values = np.ascontiguousarray(values, dtype=np.uint32)
+        if self.values.shape != (1 << 16,):
+            raise ValueError("a subtable has 2^16 entries")
+        self._handles = {}
+
+    def handle(self, ctx):
+        """the table uploaded to `ctx`'s device (b200_lasso_table_create), cached per context"""
+        if ctx not in self._handles:
+            desc = _LassoTableC(self.chunks, self.num_operands, self.operand_bits, self.out_bits, self.values.ctypes.data)
+            h = C.c_void_p()
+            _chk(lib().b200_lasso_table_create(ctx.h, C.byref(desc), C.byref(h)), "lasso_table_create")
+            self._handles[ctx] = h
+        return self._handles[ctx]
+
+    def free(self):
+        for h in self._handles.values():
+            lib().b200_lasso_table_free(h)
+        self._handles = {}
+
+
+class LassoProver:
+    """Lasso / Surge lookup prover (north_star; DESIGN.md "Lasso protocol"). The table is either a built-in kind
+    (range / and / xor) + number of 16-bit-addressed chunks, or `table=LassoTable(...)` — a table given as data."""
+
+    def __init__(self, ctx, kzg, kind=None, chunks=None, table=None):
+        self.ctx, self.kzg, self.kind, self.table = ctx, kzg, kind, table
+        self.chunks = table.chunks if table is not None else chunks
+        assert (table is None) != (kind is None), "give either a built-in kind or a table"
 
     def prove_dev(self, mu, dev_xs, dev_ys=None):
         """Operands already resident on the device (raw pointers to u64 arrays); fully asynchronous."""
+        if self.table is not None:
+            _chk(lib().b200_lasso_prove_table_dev(self.ctx.h, self.table.handle(self.ctx), C.c_int(mu), C.c_void_p(dev_xs),
+                                                  C.c_void_p(dev_ys) if dev_ys else None), "lasso_prove_table_dev")
+            return
         _chk(lib().b200_lasso_prove_dev(self.ctx.h, C.c_int(self.kind), C.c_int(self.chunks), C.c_int(mu),
                                         C.c_void_p(dev_xs), C.c_void_p(dev_ys) if dev_ys else None), "lasso_prove_dev")
 
@@ -417,6 +458,10 @@ class LassoProver:
         assert xs.shape[0] == 1 << mu
         if ys is not None:
             ys = np.ascontiguousarray(ys, dtype=np.uint64)
+        if self.table is not None:
+            _chk(lib().b200_lasso_prove_table(self.ctx.h, self.table.handle(self.ctx), C.c_int(mu), _p(xs),
+                                              _p(ys) if ys is not None else None), "lasso_prove_table")
+            return
         _chk(lib().b200_lasso_prove(self.ctx.h, C.c_int(self.kind), C.c_int(self.chunks), C.c_int(mu), _p(xs),
                                     _p(ys) if ys is not None else None), "lasso_prove")
 

@@ -51,14 +51,19 @@ static void dist_set_common(Ctx* c, int rank, int world) {
   // small messages: payload + release flag + acquire fence (1, default: 9 us per sharded round at 2 GPUs) or LL words
   // (0: measured 105 us — relaxed system-scope stores are not pushed out promptly without a release)
   c->peer.proto = 1;
-  if (const char* e = getenv("B200_PEER_PROTO")) c->peer.proto = atoi(e) < 0 || atoi(e) > 2 ? 1 : atoi(e);
+  if (const char* e = getenv("B200_PEER_PROTO")) c->peer.proto = atoi(e) < 0 || atoi(e) > 3 ? 1 : atoi(e);
   c->peer_seq = 0;
   c->bulk_seq = 0;
+  // A sharded round is worth its exchange while the (pair, term) items it takes off every other rank cost more than the
+  // exchange itself: measured per sharded round 5 us at 2 GPUs, 15 us at 4, 115 us at 8 (tools/micro/shard_tune.py,
+  // profiles/r02_shard_tune_*), at ~0.24 ns per item on a whole GPU: (world - 1) * items * 0.24 ns >= cost.
+  // 115 us <-> 2^16 items per rank at 8 GPUs; kept for every world size (the 2- and 4-GPU optimum is lower, but flat).
+  c->shard_min_items = 1 << 16;
   c->hb_ctas = 0;
   if (const char* e = getenv("B200_HEARTBEAT")) {  // "ctas,sleep_ns,write_peers"
     int a = 0, b = 1000, w = 1;
     if (sscanf(e, "%d,%d,%d", &a, &b, &w) >= 1 && a > 0) {
-      c->hb_ctas = a > 8 ? 8 : a;
+      c->hb_ctas = a > 148 ? 148 : a;
       c->hb_sleep_ns = b < 0 ? 0 : b;
       c->hb_write = w;
       if (!c->hb_stream) {
@@ -190,11 +195,11 @@ int b200_dist_tune(b200_ctx* h, int key, int value) {
   Ctx* c = &h->c;
   switch (key) {
     case 0:
-      if (value < 0 || value > 2) return B200_ERR_ARG;
+      if (value < 0 || value > 3) return B200_ERR_ARG;
       c->peer.proto = value;
       return B200_OK;
     case 1:
-      if (value < 0 || value > 8 || (value && !c->hb_stream)) return B200_ERR_ARG;
+      if (value < 0 || value > 148 || (value && !c->hb_stream)) return B200_ERR_ARG;
       c->hb_ctas = value;
       return B200_OK;
     case 2:
@@ -202,6 +207,10 @@ int b200_dist_tune(b200_ctx* h, int key, int value) {
       return B200_OK;
     case 3:
       c->hb_write = value;
+      return B200_OK;
+    case 4:
+      if (value < 1 || value > 10000) return B200_ERR_ARG;
+      c->hb_max_ms = value;  // the heartbeat kernel leaves by itself after this many ms
       return B200_OK;
   }
   return B200_ERR_ARG;

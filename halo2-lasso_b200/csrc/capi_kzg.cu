@@ -166,6 +166,84 @@ int b200_lasso_prove(b200_ctx* h, int kind, int chunks, int mu, const uint64_t* 
   return t.error ? B200_ERR_TRANSCRIPT : B200_OK;
 }
 
+// ---- decomposable tables as data (the role of a DecomposableTable implementation) --------------------------------
+struct b200_lasso_tab {
+  LassoTableDesc d;
+  uint32_t* d_values;
+};
+
+int b200_lasso_table_create(b200_ctx* h, const b200_lasso_table* t, b200_lasso_tab** out) {
+  if (!h || !t || !out || !t->subtable) return B200_ERR_ARG;
+  if (t->chunks < 2 || t->chunks > 8 || t->num_operands < 1 || t->num_operands > 2 || t->operand_bits < 1 ||
+      t->num_operands * t->operand_bits > 16 || t->operand_bits * t->chunks > 64 || t->out_bits < 1 || t->out_bits > 32)
+    return B200_ERR_ARG;
+  const size_t S = (size_t)1 << 16;
+  uint32_t mx = 0;
+  for (size_t i = 0; i < S; ++i) mx = t->subtable[i] > mx ? t->subtable[i] : mx;
+  int vb = 0;
+  while (vb < 32 && (mx >> vb)) ++vb;
+  if (t->out_bits * (t->chunks - 1) + vb > 64) return B200_ERR_ARG;  // the lookup output must fit 64 bits
+  // digest: Keccak-256 (rate 136, pad 0x01 .. 0x80) over the values as little-endian u32 words
+  uint64_t st[25] = {0};
+  uint32_t pos = 0;
+  for (size_t i = 0; i < S; ++i) {
+    st[pos >> 3] ^= (uint64_t)t->subtable[i] << (8 * (pos & 7));  // pos is a multiple of 4: a word never straddles a lane
+    pos += 4;
+    if (pos == 136) {
+      keccak_f1600(st);
+      pos = 0;
+    }
+  }
+  st[pos >> 3] ^= (uint64_t)0x01 << (8 * (pos & 7));
+  st[16] ^= 0x8000000000000000ULL;
+  keccak_f1600(st);
+  Fr raw;
+  for (int i = 0; i < 4; ++i) {
+    raw.v[2 * i] = (uint32_t)st[i];
+    raw.v[2 * i + 1] = (uint32_t)(st[i] >> 32);
+  }
+  b200_lasso_tab* tab = new b200_lasso_tab();
+  tab->d_values = nullptr;
+  if (cudaMalloc(&tab->d_values, S * 4) != cudaSuccess) {
+    delete tab;
+    return B200_ERR_NOMEM;
+  }
+  if (cudaMemcpy(tab->d_values, t->subtable, S * 4, cudaMemcpyHostToDevice) != cudaSuccess) {
+    cudaFree(tab->d_values);
+    delete tab;
+    return B200_ERR_CUDA;
+  }
+  tab->d = LassoTableDesc{t->chunks, t->num_operands, t->operand_bits, t->out_bits, vb, tab->d_values,
+                          fe_from_canonical<FrP>(raw)};  // reduces the 256-bit integer mod r
+  *out = tab;
+  return B200_OK;
+}
+void b200_lasso_table_free(b200_lasso_tab* tab) {
+  if (!tab) return;
+  cudaFree(tab->d_values);
+  delete tab;
+}
+int b200_lasso_prove_table_dev(b200_ctx* h, const b200_lasso_tab* tab, int mu, const void* dev_xs, const void* dev_ys) {
+  if (!h || !tab) return B200_ERR_ARG;
+  return lasso_prove(&h->c, 3, tab->d.chunks, mu, (const uint64_t*)dev_xs, (const uint64_t*)dev_ys, &tab->d);
+}
+int b200_lasso_prove_table(b200_ctx* h, const b200_lasso_tab* tab, int mu, const uint64_t* host_xs, const uint64_t* host_ys) {
+  if (!h || !tab) return B200_ERR_ARG;
+  Ctx* c = &h->c;
+  if (mu < 1 || mu > 26 || !host_xs || (tab->d.num_operands == 2 && !host_ys)) return B200_ERR_ARG;
+  uint64_t *dx, *dy;
+  int rc = upload_operands(c, mu, host_xs, tab->d.num_operands == 2 ? host_ys : nullptr, &dx, &dy);
+  if (rc) return rc;
+  rc = lasso_prove(c, 3, tab->d.chunks, mu, dx, dy, &tab->d);
+  CUDA_TRY(cudaFreeAsync(dx, c->stream));
+  if (dy) CUDA_TRY(cudaFreeAsync(dy, c->stream));
+  if (rc) return rc;
+  Transcript t;
+  CUDA_TRY(cudaMemcpyAsync(&t, c->d_tr, sizeof(t), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  return t.error ? B200_ERR_TRANSCRIPT : B200_OK;
+}
+
 int b200_fractional_sum_check_prove(b200_ctx* h, int num_batching, int num_vars, const void* const* dev_ps,
                                     const void* const* dev_qs, uint32_t claimed_mask, void* host_p_xs, void* host_q_xs,
                                     void* host_x, void* host_p_0s, void* host_q_0s) {

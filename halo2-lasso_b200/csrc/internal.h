@@ -60,7 +60,7 @@ struct Ctx {
   cudaEvent_t hb_event = nullptr;
   unsigned int* hb_stop = nullptr;  // device word: the running heartbeat kernel leaves when it equals its generation
   unsigned int hb_gen = 0;
-  int hb_ctas = 0, hb_sleep_ns = 1000, hb_write = 1, hb_depth = 0;
+  int hb_ctas = 0, hb_sleep_ns = 1000, hb_write = 1, hb_depth = 0, hb_max_ms = 2000;
   int shard_min_items = 1 << 16;  // a sum-check round stays sharded while a rank has at least this many (pair, term) items
   int shard_lasso_k0 = 0;  // > 0: the Lasso prover shards its tables / trees on the index window [k0 - g, k0) (lasso.cu)
   bool eq_factored = true;  // EVAL-shape sum-checks use the eq-factored round kernel (b200_sumcheck_eq_factored)
@@ -213,7 +213,16 @@ int fractional_sum_check_prove(Ctx* c, int B, int n, const Fr* const* d_ps, cons
                                Fr* d_out);
 
 // lasso.cu — Lasso / Surge prover (DESIGN.md §Lasso protocol; oracle/lasso.hpp)
-int lasso_prove(Ctx* c, int kind, int chunks, int mu, const uint64_t* d_xs, const uint64_t* d_ys);
+// A decomposable table given as DATA (b200_lasso_table, include/b200_lasso.h): one 2^16-entry subtable in device memory,
+// 1 or 2 operands of operand_bits bits per chunk, g = Σ_t 2^(out_bits t) E_t; digest = Keccak-256 of the values (LE u32
+// words) as a little-endian integer mod r, absorbed with the statement; value_bits = bit length of the largest value.
+struct LassoTableDesc {
+  int chunks, num_operands, operand_bits, out_bits, value_bits;
+  const uint32_t* d_values;
+  Fr digest;  // Montgomery
+};
+int lasso_prove(Ctx* c, int kind, int chunks, int mu, const uint64_t* d_xs, const uint64_t* d_ys,
+                const LassoTableDesc* desc = nullptr);
 int lasso_witness(Ctx* c, int kind, int chunks, int mu, const uint64_t* d_xs, const uint64_t* d_ys, Fr* d_mt,
                   Fr* d_st);
 

@@ -19,35 +19,47 @@ namespace b200 {
 static const int SUB_VARS = 16;
 static const uint32_t SUB_SIZE = 1u << SUB_VARS;
 
-__device__ __forceinline__ uint32_t lasso_subtable(int kind, uint32_t x) {
-  if (kind == 0) return x;
+// The table as the kernels see it: the three built-in kinds have closed forms; kind 3 (LassoTableDesc, internal.h) is a
+// table given as data — 2^16 subtable values in device memory, 1 or 2 operands of op_bits bits per chunk.
+struct LassoTab {
+  int kind, c, nops, op_bits, out_bits;
+  const uint32_t* values;
+};
+__device__ __forceinline__ uint32_t lasso_subtable(const LassoTab& tb, uint32_t x) {
+  if (tb.kind == 3) return __ldg(tb.values + x);
+  if (tb.kind == 0) return x;
   const uint32_t p = x >> 8, q = x & 0xff;
-  return kind == 1 ? (p & q) : (p ^ q);
+  return tb.kind == 1 ? (p & q) : (p ^ q);
 }
-__device__ __forceinline__ uint32_t lasso_dim(int kind, uint64_t x, uint64_t y, int t) {
-  if (kind == 0) return (uint32_t)((x >> (16 * t)) & 0xffff);
+__device__ __forceinline__ uint32_t lasso_dim(const LassoTab& tb, uint64_t x, uint64_t y, int t) {
+  if (tb.kind == 3) {
+    const uint64_t mask = ((uint64_t)1 << tb.op_bits) - 1;
+    const uint32_t xt = (uint32_t)((x >> (tb.op_bits * t)) & mask), yt = (uint32_t)((y >> (tb.op_bits * t)) & mask);
+    return tb.nops == 1 ? xt : (xt << tb.op_bits) | yt;
+  }
+  if (tb.kind == 0) return (uint32_t)((x >> (16 * t)) & 0xffff);
   return (uint32_t)((((x >> (8 * t)) & 0xff) << 8) | ((y >> (8 * t)) & 0xff));
 }
 
-// dims[t][j], e[t][j] (u32) and the lookup output a[j] (u64)
-// *bad is raised when an operand does not fit the table (x >= 2^(16 c) for the range table, x or y >= 2^(8 c) for
-// and / xor): such a lookup is NOT in the decomposed table and must not be proven modulo the chunk width.
-__global__ void lasso_chunks_kernel(int kind, int c, uint32_t m, const uint64_t* __restrict__ xs,
+// dims[t][j], e[t][j] (u32) and the lookup output a[j] = Σ_t 2^(out_bits t) e[t][j] (u64)
+// *bad is raised when an operand does not fit the table (x >= 2^(16 c) for the range table, x or y >= 2^(op_bits c)
+// otherwise): such a lookup is NOT in the decomposed table and must not be proven modulo the chunk width.
+__global__ void lasso_chunks_kernel(LassoTab tb, uint32_t m, const uint64_t* __restrict__ xs,
                                     const uint64_t* __restrict__ ys, uint32_t* __restrict__ dims,
                                     uint32_t* __restrict__ es, uint64_t* __restrict__ a, unsigned int* bad) {
   const uint32_t stride = gridDim.x * blockDim.x;
-  const int out_bits = kind == 0 ? 16 : 8;
-  const int op_bits = (kind == 0 ? 16 : 8) * c;
+  const int c = tb.c, out_bits = tb.out_bits;
+  const int op_bits = tb.op_bits * c;
   for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < m; j += stride) {
     const uint64_t x = xs[j], y = ys ? ys[j] : 0;
     if (op_bits < 64 && (((x | y) >> op_bits) != 0)) *bad = 1;
     uint64_t out = 0;
     for (int t = 0; t < c; ++t) {
-      const uint32_t d = lasso_dim(kind, x, y, t);
-      const uint32_t e = lasso_subtable(kind, d);
+      const uint32_t d = lasso_dim(tb, x, y, t);
+      const uint32_t e = lasso_subtable(tb, d);
       dims[(size_t)t * m + j] = d;
       es[(size_t)t * m + j] = e;
-      out |= (uint64_t)e << (out_bits * t);
+      out += (uint64_t)e << (out_bits * t);
     }
     a[j] = out;
   }
@@ -177,7 +189,7 @@ __global__ void __launch_bounds__(256) lasso_leaves_m_kernel(int c, uint32_t m, 
 }
 // S-sized leaves: init = x*g^2 + T[x]*g - tau, final = init + final_cts
 // (the rank's S_loc = 2^16 >> sg entries when the subtable trees are sharded; cts_fr is always the full table)
-__global__ void __launch_bounds__(256) lasso_leaves_s_kernel(int kind, int c, const Fr* __restrict__ cts_fr,
+__global__ void __launch_bounds__(256) lasso_leaves_s_kernel(LassoTab tb, const Fr* __restrict__ cts_fr,
                                                              const Fr* __restrict__ gt, Fr* __restrict__ trees,
                                                              uint32_t S_loc, int sp, int sg, uint32_t rank) {
   const Fr g = fe_ld(gt), tau = fe_ld(gt + 1);
@@ -188,7 +200,7 @@ __global__ void __launch_bounds__(256) lasso_leaves_s_kernel(int kind, int c, co
   const uint32_t x = shard_map(i, sp, sg, rank);
   Fr* in = trees + (size_t)(2 * t) * 2 * S_loc + S_loc;
   Fr* fi = trees + (size_t)(2 * t + 1) * 2 * S_loc + S_loc;
-  const Fr v = fe_from_u64<FrP>(x) * g2 + fe_from_u64<FrP>(lasso_subtable(kind, x)) * g - tau;
+  const Fr v = fe_from_u64<FrP>(x) * g2 + fe_from_u64<FrP>(lasso_subtable(tb, x)) * g - tau;
   fe_st(in + i, v);
   fe_st(fi + i, v + fe_ldg(cts_fr + (size_t)t * SUB_SIZE + x));
 }
@@ -371,8 +383,9 @@ struct LassoWitness {
 // shard_counters: the read / final counters of the c memories are independent, so rank r computes those of the memories
 // r, r + G, ... only and the integer arrays are all-gathered into the bulk arenas (they are needed by every rank for the
 // point-sharded commitment MSMs and for its slice of the field-element tables)
-static int lasso_witness_ints(Ctx* c, DevScope& mem, int kind, int C_, int mu, const uint64_t* d_xs, const uint64_t* d_ys,
+static int lasso_witness_ints(Ctx* c, DevScope& mem, const LassoTab& tb, int mu, const uint64_t* d_xs, const uint64_t* d_ys,
                               LassoWitness* w, bool shard_counters = false) {
+  const int C_ = tb.c;
   cudaStream_t s = c->stream;
   const uint32_t m = 1u << mu;
   const size_t S = SUB_SIZE;
@@ -395,7 +408,7 @@ static int lasso_witness_ints(Ctx* c, DevScope& mem, int kind, int C_, int mu, c
   int bx = (int)((m + 255) / 256);
   if (bx > NUM_SMS * 8) bx = NUM_SMS * 8;
   trace_point(c, "witness: allocated");
-  lasso_chunks_kernel<<<bx, 256, 0, s>>>(kind, C_, m, d_xs, d_ys, w->dims, w->es, w->a_u64, bad);
+  lasso_chunks_kernel<<<bx, 256, 0, s>>>(tb, m, d_xs, d_ys, w->dims, w->es, w->a_u64, bad);
   // an operand outside the table is an error BEFORE anything reaches the transcript (one 4-byte read-back, the only
   // host round trip of the proof; the witness kernels below are already queued behind it)
   unsigned int h_bad = 0;
@@ -429,10 +442,29 @@ static int lasso_witness_ints(Ctx* c, DevScope& mem, int kind, int C_, int mu, c
   return h_bad ? B200_ERR_LOOKUP : B200_OK;
 }
 
-int lasso_prove(Ctx* c, int kind, int chunks, int mu, const uint64_t* d_xs, const uint64_t* d_ys) {
-  if (kind < 0 || kind > 2 || chunks < 1 || chunks > 8 || mu < 1 || mu > 26) return B200_ERR_ARG;
-  if (kind == 0 && chunks > 4) return B200_ERR_ARG;
-  if (kind != 0 && !d_ys) return B200_ERR_ARG;  // and / xor need both operands
+// built-in kinds as a LassoTab; a descriptor (kind 3) is validated here
+static int lasso_tab(int kind, int chunks, const LassoTableDesc* desc, LassoTab* tb) {
+  if (desc) {
+    if (desc->chunks < 2 || desc->chunks > 8 || !desc->d_values || desc->num_operands < 1 || desc->num_operands > 2 ||
+        desc->operand_bits < 1 || desc->num_operands * desc->operand_bits > SUB_VARS || desc->operand_bits * desc->chunks > 64 ||
+        desc->out_bits < 1 || desc->out_bits > 32 || desc->out_bits * (desc->chunks - 1) + desc->value_bits > 64)
+      return B200_ERR_ARG;
+    *tb = LassoTab{3, desc->chunks, desc->num_operands, desc->operand_bits, desc->out_bits, desc->d_values};
+    return B200_OK;
+  }
+  if (kind < 0 || kind > 2 || chunks < 1 || chunks > 8 || (kind == 0 && chunks > 4)) return B200_ERR_ARG;
+  *tb = LassoTab{kind, chunks, kind == 0 ? 1 : 2, kind == 0 ? 16 : 8, kind == 0 ? 16 : 8, nullptr};
+  return B200_OK;
+}
+
+int lasso_prove(Ctx* c, int kind, int chunks, int mu, const uint64_t* d_xs, const uint64_t* d_ys,
+                const LassoTableDesc* desc) {
+  LassoTab tb;
+  if (lasso_tab(kind, chunks, desc, &tb)) return B200_ERR_ARG;
+  kind = tb.kind;
+  chunks = tb.c;
+  if (mu < 1 || mu > 26) return B200_ERR_ARG;
+  if (tb.nops == 2 && !d_ys) return B200_ERR_ARG;  // two-operand tables need both operands
   if (chunks < 2) return B200_ERR_ARG;  // additive batch_open needs >= 2 evaluations (pcs/multilinear.rs:150)
   if ((int)c->srs.size() <= (mu > SUB_VARS ? mu : SUB_VARS)) return B200_ERR_ARG;
   NvtxRange nvtx("lasso_prove-%d", mu);
@@ -465,7 +497,7 @@ int lasso_prove(Ctx* c, int kind, int chunks, int mu, const uint64_t* d_xs, cons
   // ---- 1. witness (integers, all lookups) ------------------------------------------------------------
   int ph = prof_begin(c, PH_WITNESS);
   LassoWitness wit;
-  int rc = lasso_witness_ints(c, mem, kind, C_, mu, d_xs, d_ys, &wit, sh);
+  int rc = lasso_witness_ints(c, mem, tb, mu, d_xs, d_ys, &wit, sh);
   if (rc) return rc;
   uint32_t *dims = wit.dims, *es = wit.es, *ts = wit.ts, *cts = wit.cts;
   uint64_t* a_u64 = wit.a_u64;
@@ -491,12 +523,12 @@ int lasso_prove(Ctx* c, int kind, int chunks, int mu, const uint64_t* d_xs, cons
   }
 
   // ---- scalar arena -------------------------------------------------------------------------------
-  // stmt[3] | r[mu] | v_a | pw[c] | x_p[mu] | e_p[c] | gt[2] | x_scratch[32] | ev_m[3c] | ev_s[c] | pts[3*mu]
-  const size_t arena_n = 3 + mu + 1 + C_ + mu + C_ + 2 + 32 + 3 * C_ + C_ + 3 * (size_t)mu + SUB_VARS;
+  // stmt[7] | r[mu] | v_a | pw[c] | x_p[mu] | e_p[c] | gt[2] | x_scratch[32] | ev_m[3c] | ev_s[c] | pts[3*mu]
+  const size_t arena_n = 7 + mu + 1 + C_ + mu + C_ + 2 + 32 + 3 * C_ + C_ + 3 * (size_t)mu + SUB_VARS;
   Fr* arena;
   CUDA_TRY(mem.alloc(&arena, arena_n * sizeof(Fr)));
   Fr* stmt = arena;
-  Fr* r = stmt + 3;
+  Fr* r = stmt + 7;
   Fr* v_a = r + mu;
   Fr* pw = v_a + 1;
   Fr* x_p = pw + C_;
@@ -509,17 +541,24 @@ int lasso_prove(Ctx* c, int kind, int chunks, int mu, const uint64_t* d_xs, cons
   Fr* pt_s = pts + 3 * (size_t)mu;
   GpState* gp;
   CUDA_TRY(mem.alloc(&gp, sizeof(GpState)));
-  const int out_bits = kind == 0 ? 16 : 8;
+  const int out_bits = tb.out_bits;
+  const int nstmt = desc ? 7 : 3;  // a table given as data is part of the statement
   {
-    Fr h[3 + 8];
+    Fr h[7 + 8];
     h[0] = fe_from_u64<FrP>((uint64_t)kind);
     h[1] = fe_from_u64<FrP>((uint64_t)C_);
     h[2] = fe_from_u64<FrP>((uint64_t)mu);
-    for (int t = 0; t < C_; ++t) h[3 + t] = fe_from_u64<FrP>((uint64_t)1 << (out_bits * t));
-    CUDA_TRY(cudaMemcpyAsync(stmt, h, 3 * sizeof(Fr), cudaMemcpyHostToDevice, s));
-    CUDA_TRY(cudaMemcpyAsync(pw, h + 3, C_ * sizeof(Fr), cudaMemcpyHostToDevice, s));
+    if (desc) {
+      h[3] = fe_from_u64<FrP>((uint64_t)tb.nops);
+      h[4] = fe_from_u64<FrP>((uint64_t)tb.op_bits);
+      h[5] = fe_from_u64<FrP>((uint64_t)tb.out_bits);
+      h[6] = desc->digest;
+    }
+    for (int t = 0; t < C_; ++t) h[7 + t] = fe_from_u64<FrP>((uint64_t)1 << (out_bits * t));
+    CUDA_TRY(cudaMemcpyAsync(stmt, h, nstmt * sizeof(Fr), cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(pw, h + 7, C_ * sizeof(Fr), cudaMemcpyHostToDevice, s));
   }
-  rc = transcript_op(c, TR_COMMON, stmt, nullptr, 3);
+  rc = transcript_op(c, TR_COMMON, stmt, nullptr, nstmt);
   if (rc) return rc;
   prof_end(c, ph);
   ph = prof_begin(c, PH_COMMIT);
@@ -536,7 +575,8 @@ int lasso_prove(Ctx* c, int kind, int chunks, int mu, const uint64_t* d_xs, cons
     for (int t = 0; t < C_; ++t) jobs[J++] = MsmJob{dims + (size_t)t * m, c->srs[mu], m, MSM_U32, 16, nullptr};
     const int j_e = e_is_dim ? j_dim : J;
     if (!e_is_dim)
-      for (int t = 0; t < C_; ++t) jobs[J++] = MsmJob{es + (size_t)t * m, c->srs[mu], m, MSM_U32, out_bits, nullptr};
+      for (int t = 0; t < C_; ++t)
+        jobs[J++] = MsmJob{es + (size_t)t * m, c->srs[mu], m, MSM_U32, desc ? (desc->value_bits > 0 ? desc->value_bits : 1) : out_bits, nullptr};
     const int j_ts = J;
     for (int t = 0; t < C_; ++t) jobs[J++] = MsmJob{ts + (size_t)t * m, c->srs[mu], m, MSM_U32, mu + 1, nullptr};
     const int j_cts = J;
@@ -617,7 +657,7 @@ int lasso_prove(Ctx* c, int kind, int chunks, int mu, const uint64_t* d_xs, cons
     int cap = (8 * NUM_SMS + C_ - 1) / C_;
     if (bx > cap) bx = cap;
     lasso_leaves_m_kernel<<<dim3(bx, C_), 256, 0, s>>>(C_, m_loc, dim_fr, e_fr, ts_fr, gt, mtrees);
-    lasso_leaves_s_kernel<<<dim3((S_loc + 255) / 256, C_), 256, 0, s>>>(kind, C_, st_tabs, gt, strees, S_loc,
+    lasso_leaves_s_kernel<<<dim3((S_loc + 255) / 256, C_), 256, 0, s>>>(tb, st_tabs, gt, strees, S_loc,
                                                                         s_sh ? p : 0, s_sh ? g : 0, rank);
     count_launch(c, 2);
   }
@@ -745,7 +785,8 @@ int lasso_prove(Ctx* c, int kind, int chunks, int mu, const uint64_t* d_xs, cons
 // witness only (parity of dims / E / read_ts / final_cts / a against the oracle)
 int lasso_witness(Ctx* c, int kind, int chunks, int mu, const uint64_t* d_xs, const uint64_t* d_ys, Fr* d_mt,
                   Fr* d_st) {
-  if (kind < 0 || kind > 2 || chunks < 1 || chunks > 8 || mu < 1 || mu > 26) return B200_ERR_ARG;
+  LassoTab tb;
+  if (lasso_tab(kind, chunks, nullptr, &tb) || mu < 1 || mu > 26) return B200_ERR_ARG;
   if (kind != 0 && !d_ys) return B200_ERR_ARG;
   cudaStream_t s = c->stream;
   const int C_ = chunks;
@@ -753,7 +794,7 @@ int lasso_witness(Ctx* c, int kind, int chunks, int mu, const uint64_t* d_xs, co
   const size_t S = SUB_SIZE;
   DevScope mem(s);
   LassoWitness w;
-  int rc = lasso_witness_ints(c, mem, kind, C_, mu, d_xs, d_ys, &w);
+  int rc = lasso_witness_ints(c, mem, tb, mu, d_xs, d_ys, &w);
   if (rc) return rc;
   rc = fr_from_u64(c, w.a_u64, d_mt, m);
   if (rc) return rc;

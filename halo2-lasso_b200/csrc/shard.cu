@@ -142,7 +142,8 @@ int shard_allreduce(Ctx* c, Fr* d_vals, int cnt) {
 // mode bit 0: store a word into every rank's mailbox pad (NVLink traffic); bit 1: stream 128-byte reads through the
 // rank's own bulk arena (HBM traffic that misses L2 sooner or later)
 __global__ void __launch_bounds__(32) peer_heartbeat_kernel(PeerCtx pc, const unsigned int* stop, unsigned int gen,
-                                                            unsigned int sleep_ns, int mode, unsigned int* sink) {
+                                                            unsigned int sleep_ns, int mode, unsigned int* sink,
+                                                            unsigned long long max_ns) {
   const int lane = threadIdx.x;
   const unsigned long long t0 = peer_now_ns();
   float x = (float)lane;
@@ -153,7 +154,7 @@ __global__ void __launch_bounds__(32) peer_heartbeat_kernel(PeerCtx pc, const un
   for (;;) {
     unsigned int v;
     asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(stop) : "memory");
-    if (v == gen || peer_now_ns() - t0 > 2000000000ull) break;
+    if (v == gen || peer_now_ns() - t0 > max_ns) break;
 #pragma unroll
     for (int i = 0; i < 32; ++i) x = fmaf(x, 1.0001f, 0.5f);
     if ((mode & 1) && blockIdx.x == 0 && lane < pc.world) {
@@ -181,7 +182,8 @@ HeartbeatScope::HeartbeatScope(Ctx* ctx) : c(ctx) {
   cudaEventRecord(c->hb_event, c->stream);
   cudaStreamWaitEvent(c->hb_stream, c->hb_event, 0);
   peer_heartbeat_kernel<<<c->hb_ctas, 32, 0, c->hb_stream>>>(c->peer, c->hb_stop, c->hb_gen, (unsigned)c->hb_sleep_ns,
-                                                             c->hb_write, &c->d_sc->pad[1]);
+                                                             c->hb_write, &c->d_sc->pad[1],
+                                                             (unsigned long long)c->hb_max_ms * 1000000ull);
   count_launch(c);
 }
 HeartbeatScope::~HeartbeatScope() {
@@ -511,6 +513,9 @@ void preload_shard() {
   B200_PRELOAD(shard_allreduce_kernel);
   B200_PRELOAD(shard_point_sum_kernel);
   B200_PRELOAD(shard_points_sum_kernel);
+  // the heartbeat must not pin a small shared-memory carveout on the SMs it sits on (kernels that need more shared memory
+  // could not start there until it leaves): ask for the largest one
+  cudaFuncSetAttribute(peer_heartbeat_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   B200_PRELOAD(peer_heartbeat_kernel);
   B200_PRELOAD(hb_stop_kernel);
 }

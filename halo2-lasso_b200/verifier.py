@@ -162,6 +162,21 @@ class MultilinearKzgVerifier:
         return (ok, out) if want_commitments else ok
 
 
+    def lasso_verify_table(self, tr, table, mu, expect_a=None, expect_dims=None, want_commitments=False):
+        """the proof of `LassoProver(ctx, kzg, table=table).prove(...)`: `table` is a `LassoTable` (a table given as data,
+        part of the statement). Statement binding as in `lasso_verify`."""
+        c = table.chunks
+        ea = np.ascontiguousarray(np.asarray(expect_a, dtype=np.uint64).reshape(8)) if expect_a is not None else None
+        ed = np.ascontiguousarray(np.asarray(expect_dims, dtype=np.uint64).reshape(c, 8)) if expect_dims is not None else None
+        out = np.zeros((1 + 4 * c, 8), dtype=np.uint64) if want_commitments else None
+        vals = np.ascontiguousarray(table.values, dtype=np.uint32)
+        ok = _ok(lib().b200v_lasso_verify_table(self.h, tr.h, C.c_int(c), C.c_int(table.num_operands),
+                                                C.c_int(table.operand_bits), C.c_int(table.out_bits), _p(vals), C.c_int(mu),
+                                                _p(ea) if ea is not None else None, _p(ed) if ed is not None else None,
+                                                _p(out) if out is not None else None))
+        return (ok, out) if want_commitments else ok
+
+
 class HyperPlonkVerifier:
     """`HyperPlonkVerifierParam` + `HyperPlonk::verify` (hyperplonk.rs:58-74, 293-363). `expression` is the composed
     zero-check expression (expression.py::compose), the commitments are `HyperPlonk.commitments()` of the prover side."""

@@ -190,6 +190,31 @@ int b200v_lasso_verify_statement(const b200v_kzg* vp, b200v_transcript* tr, int 
   });
 }
 
+int b200v_lasso_verify_table(const b200v_kzg* vp, b200v_transcript* tr, int chunks, int num_operands, int operand_bits,
+                             int out_bits, const uint32_t* subtable, int mu, const void* expect_a_g1,
+                             const void* expect_dims_g1, void* out_comms_g1) {
+  if (!vp || !tr || !subtable || chunks < 2 || chunks > 8 || num_operands < 1 || num_operands > 2 || operand_bits < 1 ||
+      num_operands * operand_bits > SUBTABLE_VARS || operand_bits * chunks > 64 || out_bits < 1 || out_bits > 32 || mu < 1 ||
+      mu > 30 || vp->vp.num_vars() < (mu > SUBTABLE_VARS ? mu : SUBTABLE_VARS))
+    return B200V_ERR_ARG;
+  LassoStatement stm;
+  stm.expect_a = (const G1Affine*)expect_a_g1;
+  stm.expect_dims = (const G1Affine*)expect_dims_g1;
+  stm.out_comms = (G1Affine*)out_comms_g1;
+  if (stm.expect_a && !g1_ok(*stm.expect_a)) return B200V_ERR_ARG;
+  if (stm.expect_dims)
+    for (int t = 0; t < chunks; ++t)
+      if (!g1_ok(stm.expect_dims[t])) return B200V_ERR_ARG;
+  return guarded([&] {
+    LassoTable tb{TABLE_CUSTOM, chunks};
+    tb.num_operands = num_operands;
+    tb.operand_bits = operand_bits;
+    tb.custom_out_bits = out_bits;
+    tb.values = subtable;
+    return verdict(lasso_verify(vp->vp, tb, mu, tr->tr, stm));
+  });
+}
+
 int b200v_hyperplonk_new(const b200v_kzg* vp, int k, int ninstance_cols, const int32_t* num_instances, int nphases,
                          const int32_t* num_witness_polys, const int32_t* num_challenges, int num_lookups,
                          int num_permutation_z_polys, const int32_t* expression_tokens, int ntokens,

@@ -196,16 +196,27 @@ inline bool kzg_batch_verify(const KzgVerifierParam& vp, int num_vars, const std
 }
 
 // ---- Lasso: table description as far as the verifier needs it ---------------------------------
-enum TableKind { TABLE_RANGE = 0, TABLE_AND = 1, TABLE_XOR = 2 };
+enum TableKind { TABLE_RANGE = 0, TABLE_AND = 1, TABLE_XOR = 2, TABLE_CUSTOM = 3 };
 static const int SUBTABLE_VARS = 16;
 
 struct LassoTable {
   int kind;    // TableKind
   int chunks;  // c; every chunk addresses one 2^16-entry subtable
+  // TABLE_CUSTOM (b200_lasso_table of the prover side): the table is data — 2^16 values, operand layout, output stride
+  int num_operands = 1, operand_bits = 16, custom_out_bits = 16;
+  const uint32_t* values = nullptr;
   // bits of the lookup output contributed by one chunk (16 for range, 8 for and/xor)
-  int out_bits() const { return kind == TABLE_RANGE ? 16 : 8; }
-  // MLE of the subtable at a 16-variate point: the verifier evaluates the structured subtable itself
+  int out_bits() const { return kind == TABLE_CUSTOM ? custom_out_bits : (kind == TABLE_RANGE ? 16 : 8); }
+  // MLE of the subtable at a 16-variate point: the verifier evaluates the subtable itself (closed forms for the
+  // structured tables, <values, eq(., x)> for a table given as data)
   Fr subtable_mle(const std::vector<Fr>& x) const {
+    if (kind == TABLE_CUSTOM) {
+      const Poly eq = eq_xy(x);
+      Fr acc = Fr::zero();
+      for (size_t i = 0; i < eq.size(); ++i)
+        if (values[i]) acc = acc + eq[i] * Fr::from_u64(values[i]);
+      return acc;
+    }
     if (kind == TABLE_RANGE) return identity_eval(x);
     Fr acc = Fr::zero(), pw = Fr::one();
     for (int k = 0; k < 8; ++k) {
@@ -215,6 +226,14 @@ struct LassoTable {
       pw = pw.dbl();
     }
     return acc;
+  }
+  // statement binding of a table given as data: Keccak-256 of the values (LE u32 words) as an LE integer mod r
+  Fr digest() const {
+    Keccak256 h;
+    h.update(reinterpret_cast<const uint8_t*>(values), ((size_t)4) << 16);
+    uint8_t out[32];
+    h.finalize_reset(out);
+    return Fr::from_le_bytes_mod(out);
   }
 };
 
@@ -282,6 +301,12 @@ inline void lasso_absorb_statement(const LassoTable& tb, int mu, Transcript& tr)
   tr.common_field_element(Fr::from_u64((uint64_t)tb.kind));
   tr.common_field_element(Fr::from_u64((uint64_t)tb.chunks));
   tr.common_field_element(Fr::from_u64((uint64_t)mu));
+  if (tb.kind == TABLE_CUSTOM) {
+    tr.common_field_element(Fr::from_u64((uint64_t)tb.num_operands));
+    tr.common_field_element(Fr::from_u64((uint64_t)tb.operand_bits));
+    tr.common_field_element(Fr::from_u64((uint64_t)tb.custom_out_bits));
+    tr.common_field_element(tb.digest());
+  }
 }
 
 // The STATEMENT of a Lasso proof is "the committed polynomial a holds table values at the committed addresses dim_t":

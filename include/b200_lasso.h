@@ -270,7 +270,7 @@ int b200_dist_check(b200_ctx* ctx);
  * byte-identical. Implies point-sharded commitments; mu <= k0 falls back to the replicated prover. 0 = off. */
 int b200_dist_shard_lasso(b200_ctx* ctx, int k0);
 /* exchange tuning knobs for experiments (tools/micro/shard_tune.py): key 0 small-message protocol (0, 1, 2), key 1
- * heartbeat CTAs (0 = off), key 2 heartbeat sleep in ns, key 3 heartbeat mode bits (1 NVLink stores, 2 HBM reads) */
+ * heartbeat CTAs (0 = off), key 2 heartbeat sleep in ns, key 3 heartbeat mode bits (1 NVLink stores, 2 HBM reads), key 4 heartbeat self-timeout in ms */
 int b200_dist_tune(b200_ctx* ctx, int key, int value);
 /* a sharded sum-check round is exchanged over NVLink while a rank holds at least `items` (pair, term) items; below
  * that the bound tables are all-gathered once and the remaining rounds run replicated (default 2^16) */
@@ -319,6 +319,27 @@ int b200_lasso_prove(b200_ctx* ctx, int table_kind, int chunks, int mu, const ui
                      const uint64_t* host_ys);
 /* same with operands already on the device (u64 arrays) */
 int b200_lasso_prove_dev(b200_ctx* ctx, int table_kind, int chunks, int mu, const void* dev_xs, const void* dev_ys);
+/* Decomposable tables as DATA instead of a built-in kind (the role of a `DecomposableTable` implementation in the Lasso
+ * frontend north_star names: chunk bits, subtable values, the combiner g): every lookup splits into `chunks` chunks, chunk
+ * t addresses ONE 2^16-entry subtable T, and the lookup output is g(E) = sum_t 2^(out_bits t) T[dim_t].
+ *   num_operands = 1: dim_t = chunk t (operand_bits bits) of x;
+ *   num_operands = 2: dim_t = (chunk t of x) << operand_bits | (chunk t of y)   (num_operands * operand_bits <= 16).
+ * The table is part of the proved statement: (3, chunks, mu, num_operands, operand_bits, out_bits, digest) is absorbed,
+ * digest = Keccak-256 of the 2^16 values as little-endian u32 words, as a little-endian integer mod r. Operands that do not
+ * fit operand_bits * chunks bits are rejected with B200_ERR_LOOKUP before anything reaches the transcript. */
+typedef struct {
+  int chunks;               /* 2..8: memories = chunks */
+  int num_operands;         /* 1 or 2 */
+  int operand_bits;         /* bits of one operand chunk */
+  int out_bits;             /* g = sum_t 2^(out_bits t) E_t; out_bits * (chunks - 1) + bits(max T) <= 64 */
+  const uint32_t* subtable; /* host, 2^16 values (all of them: the whole table is committed to by its digest) */
+} b200_lasso_table;
+typedef struct b200_lasso_tab b200_lasso_tab; /* uploaded table (device values + digest) */
+int b200_lasso_table_create(b200_ctx* ctx, const b200_lasso_table* table, b200_lasso_tab** out);
+void b200_lasso_table_free(b200_lasso_tab* tab);
+/* b200_lasso_prove / b200_lasso_prove_dev for an uploaded table (host_ys / dev_ys may be NULL when num_operands = 1) */
+int b200_lasso_prove_table(b200_ctx* ctx, const b200_lasso_tab* tab, int mu, const uint64_t* host_xs, const uint64_t* host_ys);
+int b200_lasso_prove_table_dev(b200_ctx* ctx, const b200_lasso_tab* tab, int mu, const void* dev_xs, const void* dev_ys);
 /* prove_fractional_sum_check (pb/piop/gkr/fractional_sum_check.rs:87-190): GKR argument for Σ_i p_b[i] / q_b[i] over
  * num_batching (<= 10) pairs of 2^num_vars-entry device tables (Montgomery Fr), on the context's transcript: writes (or,
  * where bit b / bit 16 + b of claimed_mask marks p_b / q_b as a public claim = Some(_), absorbs) the layer-0 values, then

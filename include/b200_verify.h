@@ -69,6 +69,14 @@ int b200v_lasso_verify(const b200v_kzg* vp, b200v_transcript* tr, int kind, int 
 int b200v_lasso_verify_statement(const b200v_kzg* vp, b200v_transcript* tr, int kind, int chunks, int mu,
                                  const void* expect_a_g1, const void* expect_dims_g1, void* out_comms_g1);
 
+/* The proof of b200_lasso_prove_table: the table is DATA (b200_lasso_table of b200_lasso.h — chunks, num_operands,
+ * operand_bits, out_bits, 2^16 subtable values) and part of the statement: a proof for another table, operand layout or
+ * output stride is REJECTED. The verifier evaluates the subtable's multilinear extension itself (2^16 products).
+ * expect_a_g1 / expect_dims_g1 / out_comms_g1 as in b200v_lasso_verify_statement (NULL = not used). */
+int b200v_lasso_verify_table(const b200v_kzg* vp, b200v_transcript* tr, int chunks, int num_operands, int operand_bits,
+                             int out_bits, const uint32_t* subtable, int mu, const void* expect_a_g1,
+                             const void* expect_dims_g1, void* out_comms_g1);
+
 /* ---- HyperPlonk ---------------------------------------------------------------------------------------- */
 typedef struct b200v_hyperplonk b200v_hyperplonk; /* HyperPlonkVerifierParam (hyperplonk.rs:58-74) */
 /* expression: the composed zero-check expression (preprocessor.rs:25-60) in the prefix-token format of b200_lasso.h;

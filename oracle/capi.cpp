@@ -440,6 +440,31 @@ int orc_lasso_verify(void* kzg, void* tr, int kind, int chunks, int mu) {
   LassoTable tb{kind, chunks};
   return lasso_verify(*(KzgParams*)kzg, tb, mu, *(Transcript*)tr) ? 0 : 1;
 }
+// TABLE_CUSTOM: the subtable crosses as data (2^16 u32 values). 2 = invalid descriptor / operand outside the table
+static LassoTable custom_table(int chunks, int num_operands, int operand_bits, int out_bits, const uint32_t* values) {
+  LassoTable tb{TABLE_CUSTOM, chunks};
+  tb.num_operands = num_operands;
+  tb.operand_bits = operand_bits;
+  tb.custom_out_bits = out_bits;
+  tb.values = values;
+  return tb;
+}
+int orc_lasso_prove_custom(void* kzg, void* tr, int chunks, int num_operands, int operand_bits, int out_bits,
+                           const uint32_t* values, int mu, const uint64_t* xs, const uint64_t* ys) {
+  LassoTable tb = custom_table(chunks, num_operands, operand_bits, out_bits, values);
+  if (!tb.valid() || (num_operands == 2 && !ys)) return 2;
+  const int bits = operand_bits * chunks;
+  for (size_t j = 0; j < ((size_t)1 << mu); ++j) {
+    if (bits < 64 && ((xs[j] >> bits) || (num_operands == 2 && (ys[j] >> bits)))) return 2;
+  }
+  return lasso_prove(*(KzgParams*)kzg, tb, mu, xs, ys, *(Transcript*)tr) ? 0 : 1;
+}
+int orc_lasso_verify_custom(void* kzg, void* tr, int chunks, int num_operands, int operand_bits, int out_bits,
+                            const uint32_t* values, int mu) {
+  LassoTable tb = custom_table(chunks, num_operands, operand_bits, out_bits, values);
+  if (!tb.valid()) return 2;
+  return lasso_verify(*(KzgParams*)kzg, tb, mu, *(Transcript*)tr) ? 0 : 1;
+}
 // witness tables, flattened: a | dim[c] | e[c] | read_ts[c] (each 2^mu) then final_cts[c] (each 2^16)
 void orc_lasso_witness(int kind, int chunks, int mu, const uint64_t* xs, const uint64_t* ys, Fr* mtabs, Fr* stabs) {
   LassoTable tb{kind, chunks};

@@ -20,25 +20,44 @@
 
 namespace oracle {
 
-enum TableKind { TABLE_RANGE = 0, TABLE_AND = 1, TABLE_XOR = 2 };
+enum TableKind { TABLE_RANGE = 0, TABLE_AND = 1, TABLE_XOR = 2, TABLE_CUSTOM = 3 };
 
+// A decomposable table in Surge form (the role of a `DecomposableTable` implementation): every lookup splits into
+// `chunks` chunks, chunk t addresses ONE 2^16-entry subtable T, output g(E) = Σ_t 2^(out_bits t) E_t.
+// TABLE_CUSTOM carries the subtable as data: `values` (2^16 entries), `num_operands` (1: dim_t = chunk t of x;
+// 2: dim_t = chunk t of x << operand_bits | chunk t of y), `operand_bits` per operand chunk, `out_bits`.
 struct LassoTable {
   int kind;    // TableKind
   int chunks;  // c; every chunk addresses one 2^16-entry subtable
+  int num_operands = 1, operand_bits = 16, custom_out_bits = 16;  // TABLE_CUSTOM only
+  const uint32_t* values = nullptr;                               // TABLE_CUSTOM only: 2^16 entries
   // bits of the lookup output contributed by one chunk (16 for range, 8 for and/xor)
-  int out_bits() const { return kind == TABLE_RANGE ? 16 : 8; }
+  int out_bits() const { return kind == TABLE_CUSTOM ? custom_out_bits : (kind == TABLE_RANGE ? 16 : 8); }
   uint64_t subtable(uint32_t x) const {
+    if (kind == TABLE_CUSTOM) return values[x];
     if (kind == TABLE_RANGE) return x;
     uint32_t p = x >> 8, q = x & 0xff;
     return kind == TABLE_AND ? (p & q) : (p ^ q);
   }
   // chunk t of lookup j; for and/xor the index interleaves operand bytes: (x_t << 8) | y_t
   uint32_t dim(uint64_t x, uint64_t y, int t) const {
+    if (kind == TABLE_CUSTOM) {
+      const uint64_t mask = ((uint64_t)1 << operand_bits) - 1;
+      const uint32_t xt = (uint32_t)((x >> (operand_bits * t)) & mask), yt = (uint32_t)((y >> (operand_bits * t)) & mask);
+      return num_operands == 1 ? xt : (xt << operand_bits) | yt;
+    }
     if (kind == TABLE_RANGE) return (uint32_t)((x >> (16 * t)) & 0xffff);
     return (uint32_t)((((x >> (8 * t)) & 0xff) << 8) | ((y >> (8 * t)) & 0xff));
   }
   // MLE of the subtable at a 16-variate point (verifier side)
   Fr subtable_mle(const std::vector<Fr>& x) const {
+    if (kind == TABLE_CUSTOM) {  // no closed form: <values, eq(., x)>
+      const Poly eq = eq_xy(x);
+      Fr acc = Fr::zero();
+      for (size_t i = 0; i < eq.size(); ++i)
+        if (values[i]) acc = acc + eq[i] * Fr::from_u64(values[i]);
+      return acc;
+    }
     if (kind == TABLE_RANGE) return identity_eval(x);
     Fr acc = Fr::zero(), pw = Fr::one();
     for (int k = 0; k < 8; ++k) {
@@ -48,6 +67,26 @@ struct LassoTable {
       pw = pw.dbl();
     }
     return acc;
+  }
+  // TABLE_CUSTOM: the table is part of the statement — Keccak-256 of the 2^16 values as little-endian u32 words,
+  // read as a little-endian integer mod r (the same map squeeze_challenge uses, transcript.rs:127-131)
+  Fr digest() const {
+    Keccak256 h;
+    h.update(reinterpret_cast<const uint8_t*>(values), ((size_t)4) << 16);
+    uint8_t out[32];
+    h.finalize_reset(out);
+    return Fr::from_le_bytes_mod(out);
+  }
+  bool valid() const {
+    if (chunks < 2 || chunks > 8) return false;
+    if (kind != TABLE_CUSTOM) return kind >= 0 && kind <= 2 && (kind != TABLE_RANGE || chunks <= 4);
+    if (!values || num_operands < 1 || num_operands > 2 || operand_bits < 1 || num_operands * operand_bits > 16) return false;
+    if (operand_bits * chunks > 64 || custom_out_bits < 1 || custom_out_bits > 32) return false;
+    uint32_t mx = 0;
+    for (size_t i = 0; i < ((size_t)1 << 16); ++i) mx = values[i] > mx ? values[i] : mx;
+    int eb = 0;
+    while (eb < 32 && (mx >> eb)) ++eb;
+    return custom_out_bits * (chunks - 1) + eb <= 64;  // the lookup output fits a u64
   }
 };
 
@@ -86,7 +125,7 @@ inline LassoWitness lasso_witness(const LassoTable& tb, int mu, const uint64_t* 
   for (size_t j = 0; j < m; ++j) {
     uint64_t out = 0;
     for (int t = 0; t < c; ++t)
-      out |= tb.subtable(tb.dim(xs[j], ys ? ys[j] : 0, t)) << (tb.out_bits() * t);
+      out += tb.subtable(tb.dim(xs[j], ys ? ys[j] : 0, t)) << (tb.out_bits() * t);  // g = Σ_t 2^(out_bits t) E_t
     w.a[j] = Fr::from_u64(out);
   }
   return w;
@@ -236,6 +275,12 @@ inline void lasso_absorb_statement(const LassoTable& tb, int mu, Transcript& tr)
   tr.common_field_element(Fr::from_u64((uint64_t)tb.kind));
   tr.common_field_element(Fr::from_u64((uint64_t)tb.chunks));
   tr.common_field_element(Fr::from_u64((uint64_t)mu));
+  if (tb.kind == TABLE_CUSTOM) {  // a table given as data is part of the statement
+    tr.common_field_element(Fr::from_u64((uint64_t)tb.num_operands));
+    tr.common_field_element(Fr::from_u64((uint64_t)tb.operand_bits));
+    tr.common_field_element(Fr::from_u64((uint64_t)tb.custom_out_bits));
+    tr.common_field_element(tb.digest());
+  }
 }
 
 // Full Lasso proof (DESIGN.md §Lasso protocol, steps 1-10). Returns false when a commitment is the

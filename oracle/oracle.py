@@ -614,6 +614,29 @@ def lasso_prove(kzg, tr, kind, chunks, mu, xs, ys=None):
                                  _p(ys) if ys is not None else None) == 0
 
 
+class CustomTable:
+    """A decomposable table given as data (TABLE_CUSTOM, oracle/lasso.hpp): 2^16 subtable values, 1 or 2 operands of
+    `operand_bits` bits per chunk, g = Σ_t 2^(out_bits t) E_t."""
+
+    def __init__(self, chunks, num_operands, operand_bits, out_bits, values):
+        self.chunks, self.num_operands, self.operand_bits, self.out_bits = chunks, num_operands, operand_bits, out_bits
+        self.values = np.ascontiguousarray(values, dtype=np.uint32)
+        assert self.values.shape == (1 << 16,)
+
+
+def lasso_prove_custom(kzg, tr, tab, mu, xs, ys=None):
+    """0 = proof written, 1 = identity commitment, 2 = invalid descriptor / operand outside the table"""
+    xs, ys = _u64(xs), _u64(ys)
+    return lib().orc_lasso_prove_custom(kzg.h, tr.h, C.c_int(tab.chunks), C.c_int(tab.num_operands), C.c_int(tab.operand_bits),
+                                        C.c_int(tab.out_bits), _p(tab.values), C.c_int(mu), _p(xs),
+                                        _p(ys) if ys is not None else None)
+
+
+def lasso_verify_custom(kzg, tr, tab, mu):
+    return lib().orc_lasso_verify_custom(kzg.h, tr.h, C.c_int(tab.chunks), C.c_int(tab.num_operands),
+                                         C.c_int(tab.operand_bits), C.c_int(tab.out_bits), _p(tab.values), C.c_int(mu)) == 0
+
+
 def lasso_verify(kzg, tr, kind, chunks, mu):
     return lib().orc_lasso_verify(kzg.h, tr.h, C.c_int(kind), C.c_int(chunks), C.c_int(mu)) == 0
 

@@ -128,12 +128,46 @@ def grand_product(tr, leaves):
     return claims, points
 
 
-def prove(ss, kind, c, mu, xs, ys=None):
-    """-> proof bytes, or None when a commitment is the identity (all-distinct addresses)"""
+CUSTOM = 3
+
+
+class CustomTable:
+    """DESIGN.md §4 "tables as data": the 2^16 subtable values, 1 or 2 operands of operand_bits bits per chunk,
+    g = Σ_t 2^(out_bits t) E_t. The table is part of the statement: (num_operands, operand_bits, out_bits) and the
+    Keccak-256 digest of the values as little-endian u32 words (little-endian integer mod r) are absorbed after (3, c, mu)."""
+
+    def __init__(self, num_operands, operand_bits, out_bits, values):
+        assert len(values) == 1 << SUB_VARS and num_operands * operand_bits <= SUB_VARS
+        self.num_operands, self.operand_bits, self.out_bits, self.values = num_operands, operand_bits, out_bits, values
+
+    def dim(self, x, y, t):
+        mask = (1 << self.operand_bits) - 1
+        xt, yt = (x >> (self.operand_bits * t)) & mask, (y >> (self.operand_bits * t)) & mask
+        return xt if self.num_operands == 1 else (xt << self.operand_bits) | yt
+
+    def digest(self):
+        data = b"".join(v.to_bytes(4, "little") for v in self.values)
+        return int.from_bytes(M.keccak256(data), "little") % R
+
+
+def prove(ss, kind, c, mu, xs, ys=None, table=None):
+    """-> proof bytes, or None when a commitment is the identity (all-distinct addresses); kind == CUSTOM: `table`"""
+    global out_bits, subtable, dim
+    if kind == CUSTOM:  # the same protocol over the table's own maps
+        saved = (out_bits, subtable, dim)
+        out_bits, subtable, dim = (lambda k: table.out_bits), (lambda k, x: table.values[x]), (lambda k, x, y, t: table.dim(x, y, t))
+        try:
+            return _prove(ss, kind, c, mu, xs, ys, [table.num_operands, table.operand_bits, table.out_bits, table.digest()])
+        finally:
+            out_bits, subtable, dim = saved
+    return _prove(ss, kind, c, mu, xs, ys, [])
+
+
+def _prove(ss, kind, c, mu, xs, ys, extra_statement):
     m, S = 1 << mu, 1 << SUB_VARS
     srs = LazySrs(ss)
     tr = M.Transcript()
-    for v in (kind, c, mu):
+    for v in [kind, c, mu] + extra_statement:
         tr.common_fe(v)
     ys = ys if ys is not None else [0] * m
     dims = [[dim(kind, xs[j], ys[j], t) for j in range(m)] for t in range(c)]

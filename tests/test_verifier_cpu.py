@@ -39,7 +39,7 @@ def tampered(proof, pos, bit=1):
 def test_library_exports_exactly_the_declared_symbols():
     out = subprocess.run(["nm", "-D", "--defined-only", V.LIB_PATH], capture_output=True, text=True, check=True).stdout
     exported = sorted(set(re.findall(r"\b(b200v_[a-z0-9_]+)\b", out)))
-    assert exported == V.declared_symbols() and len(exported) == 19
+    assert exported == V.declared_symbols() and len(exported) == 20
 
 
 def test_transcript_reading_side_matches_the_oracle():
@@ -191,7 +191,54 @@ def test_lasso_verify_accepts_the_committed_golden_proofs(vkzg):
     for c in gold["cases"]:
         assert c["srs_seed"] == 7
         tr = V.ProofTranscript(bytes.fromhex(c["proof"]))
+        if c["kind"] == 3:
+            t = c["table"]
+            tab = _or8_table(c["chunks"], t["out_bits"])
+            assert vkzg.lasso_verify_table(tr, tab, c["mu"]) and tr.done()
+            continue
         assert vkzg.lasso_verify(tr, c["kind"], c["chunks"], c["mu"]) and tr.done()
+
+
+class _Tab:  # the fields lasso_verify_table reads (halo2_lasso_b200.LassoTable needs the CUDA library to upload)
+    def __init__(self, chunks, num_operands, operand_bits, out_bits, values):
+        self.chunks, self.num_operands, self.operand_bits, self.out_bits = chunks, num_operands, operand_bits, out_bits
+        self.values = np.ascontiguousarray(values, dtype=np.uint32)
+
+
+def _or8_table(chunks, out_bits=8):
+    return _Tab(chunks, 2, 8, out_bits, [(x >> 8) | (x & 0xFF) for x in range(1 << 16)])
+
+
+def test_lasso_tables_given_as_data_are_part_of_the_statement(okzg, vkzg):
+    """b200v_lasso_verify_table: accepts the oracle's proof for the same descriptor; another subtable value, operand
+    layout or output stride -> REJECT; a one-operand 16-bit table (x -> popcount) works the same way."""
+    mu = 5
+    for tab, two in ((_or8_table(3), True), (_Tab(2, 1, 16, 5, [bin(x).count("1") for x in range(1 << 16)]), False)):
+        bits = tab.operand_bits * tab.chunks
+        xs = O.rand_u64s(91, 1 << mu) & np.uint64((1 << bits) - 1)
+        ys = (O.rand_u64s(92, 1 << mu) & np.uint64((1 << bits) - 1)) if two else None
+        xs[1::2] = xs[0::2]
+        if two:
+            ys[1::2] = ys[0::2]
+        otab = O.CustomTable(tab.chunks, tab.num_operands, tab.operand_bits, tab.out_bits, tab.values)
+        tr = O.Transcript()
+        assert O.lasso_prove_custom(okzg, tr, otab, mu, xs, ys) == 0
+        proof = tr.proof()
+        t = V.ProofTranscript(proof)
+        assert vkzg.lasso_verify_table(t, tab, mu) and t.done()
+        wrong_vals = tab.values.copy()
+        wrong_vals[12345] += 1
+        for bad in (_Tab(tab.chunks, tab.num_operands, tab.operand_bits, tab.out_bits, wrong_vals),
+                    _Tab(tab.chunks, tab.num_operands, tab.operand_bits, tab.out_bits + 1, tab.values),
+                    _Tab(tab.chunks, tab.num_operands, tab.operand_bits - 1, tab.out_bits, tab.values)):
+            assert not vkzg.lasso_verify_table(V.ProofTranscript(proof), bad, mu)
+        # an operand outside the table is refused by the prover (oracle rc 2)
+        big = xs.copy()
+        if bits < 64:
+            big[3] = np.uint64(1 << bits)
+            assert O.lasso_prove_custom(okzg, O.Transcript(), otab, mu, big, ys) == 2
+    with pytest.raises(V.VerifierArgError):
+        vkzg.lasso_verify_table(V.ProofTranscript(proof), _Tab(2, 2, 9, 8, tab.values), mu)  # 2 x 9 bits > 16
 
 
 def _hyperplonk_verifier(okzg, vkzg, info, expr, nz):
