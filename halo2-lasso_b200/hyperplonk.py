@@ -259,6 +259,67 @@ def rand_vanilla_plonk_circuit(k, seed, num_instances=None):
     return VanillaPlonkCircuitInfo(k, num_instances, q, cycles), instances, w
 
 
+def range_checked_plonk_circuit(k, seed, bits=32, num_instances=2):
+    """A satisfiable vanilla-plonk circuit whose output wire w_o holds a `bits`-bit value in EVERY row (additions of two
+    (bits - 1)-bit operands, copies between rows): the circuit shape of BASELINE cfg1, where a Lasso range check over the
+    whole column w_o is the circuit's lookup argument (`HyperPlonkLasso`). Returns (circuit_info, instances, [w_l, w_r, w_o])."""
+    rng = random.Random(seed)
+    N = 1 << k
+    order = BooleanHypercube(k).iter()
+    q = [[0] * N for _ in range(5)]  # q_l q_r q_m q_o q_c
+    w = [[0] * N for _ in range(3)]
+    instances = [rng.randrange(1 << (bits - 1)) for _ in range(num_instances)]
+    used = {0}
+    for i, v in enumerate(instances):  # instance rows: -w_l + pi = 0 (w_o = 0 is in range)
+        b = order[i + 1]
+        q[0][b], w[0][b] = R_MOD - 1, v
+        used.add(b)
+    cycles, outputs = [], []
+    for b in range(1, N):
+        if b in used:
+            continue
+        if outputs and rng.random() < 0.3:  # copy an earlier output (halved so that the sum stays in range) ... as w_r
+            src = outputs[rng.randrange(len(outputs))]
+            w[0][b] = w[2][src] >> 1
+        else:
+            w[0][b] = rng.randrange(1 << (bits - 1))
+        w[1][b] = rng.randrange(1 << (bits - 1))
+        q[0][b] = q[1][b] = 1
+        q[3][b] = R_MOD - 1
+        w[2][b] = w[0][b] + w[1][b]
+        if outputs and rng.random() < 0.25:  # an exact copy constraint between two output cells with equal values
+            src = outputs[rng.randrange(len(outputs))]
+            w[0][b], w[1][b] = w[0][src], w[1][src]
+            w[2][b] = w[2][src]
+            cycles.append([(8, src), (8, b)])
+        outputs.append(b)
+    assert all(v < (1 << bits) for v in w[2])
+    return VanillaPlonkCircuitInfo(k, num_instances, q, cycles), instances, w
+
+
+class HyperPlonkLasso:
+    """Lasso as the lookup argument of a HyperPlonk-proved circuit (BASELINE cfg1): the HyperPlonk section proves the gate
+    and copy constraints, the Lasso section — on the same transcript — proves that EVERY entry of one witness column lies
+    in a decomposable table (range) or is the table's output for two operand columns; the two sections are linked by
+    commitment equality: the commitment to `a` the Lasso section writes must be the commitment to that witness column the
+    HyperPlonk section wrote (same SRS level: one lookup per row, mu = k). `HyperPlonkLassoVerifier` (verifier.py) checks
+    both sections and the link."""
+
+    def __init__(self, ctx, kzg, info, kind, chunks, lookup_witness):
+        from . import LassoProver
+
+        self.hp = HyperPlonk(ctx, kzg, info)
+        self.lasso = LassoProver(ctx, kzg, kind, chunks)
+        self.info, self.lookup_witness = info, lookup_witness
+
+    def prove(self, instances, witness_ints, ys_ints=None):
+        import numpy as np
+
+        self.hp.prove(instances, witness_ints=witness_ints)
+        xs = np.asarray(witness_ints[self.lookup_witness], dtype=np.uint64)
+        self.lasso.prove(xs, None if ys_ints is None else np.asarray(ys_ints, dtype=np.uint64))
+
+
 def permutation_polys(k, permutation_polys_idx, cycles):
     """preprocessor.rs:172-203"""
     N = 1 << k

@@ -219,3 +219,26 @@ class HyperPlonkVerifier:
         """instances: all instance columns back to back, as Montgomery field elements"""
         inst = np.ascontiguousarray(instances, dtype=np.uint64).reshape(-1, 4)
         return _ok(lib().b200v_hyperplonk_verify(self.h, tr.h, _p(inst) if inst.size else None, C.c_int(inst.shape[0])))
+
+
+class HyperPlonkLassoVerifier:
+    """Verifier of `hyperplonk.HyperPlonkLasso` proofs: HyperPlonk::verify, then the Lasso verifier BOUND to the witness
+    commitment the HyperPlonk section carries (the first phase's witness commitments open the proof: 64 bytes each, big-
+    endian coordinates, transcript.rs:216-227), then nothing may be left over."""
+
+    def __init__(self, hp_verifier, kind, chunks, lookup_witness):
+        self.hpv, self.kind, self.chunks, self.lookup_witness = hp_verifier, kind, chunks, lookup_witness
+
+    def witness_commitment(self, proof):
+        off = 64 * self.lookup_witness
+        x = int.from_bytes(proof[off:off + 32], "big")
+        y = int.from_bytes(proof[off + 32:off + 64], "big")
+        q_mod = 0x30644E72E131A029B85045B68181585D97816A916871CA8D3C208C16D87CFD47
+        mont = [(v << 256) % q_mod for v in (x, y)]  # the ABI carries Montgomery limbs (b200_verify.h)
+        return np.array([(v >> (64 * i)) & 0xFFFFFFFFFFFFFFFF for v in mont for i in range(4)], dtype=np.uint64)
+
+    def verify(self, proof, instances, k):
+        tr = ProofTranscript(proof)
+        if not self.hpv.verify(tr, instances):
+            return False
+        return bool(self.hpv.kzg.lasso_verify(tr, self.kind, self.chunks, k, expect_a=self.witness_commitment(proof)) and tr.done())

@@ -106,6 +106,41 @@ def test_cfg1_hyperplonk_plus_lasso_on_one_transcript(hl):
     ctx.close()
 
 
+def test_cfg1_lasso_as_the_lookup_argument_linked_by_commitment(hl):
+    """BASELINE cfg1, linked: k = 10 circuit whose output wire is 32-bit in every row + the Lasso range check over that
+    whole column (2^10 lookups into 2^16 subtables) proved on the GPU on one transcript (`HyperPlonkLasso`); bytes equal
+    the oracle composition, and the product's CPU verifier accepts only because the Lasso section's commitment to `a` IS
+    the HyperPlonk section's commitment to w_o (`HyperPlonkLassoVerifier`)."""
+    from halo2_lasso_b200 import hyperplonk as H
+    from halo2_lasso_b200 import verifier as V
+    from halo2_lasso_b200.expression import compose
+
+    k, chunks, w_o = 10, 2, 2
+    ctx = hl.Context(0)
+    ss = O.rand_fr(7, 16)
+    okzg = O.Kzg(ss)
+    kzg = hl.MultilinearKzg(ctx, [okzg.eqs(i) for i in range(17)])
+    info, instances, w = H.range_checked_plonk_circuit(k, 4242)
+    nz, expr = compose(k, info.constraints, info.num_poly, info.permutation_polys)
+    ohp = O.HyperPlonk(okzg, k, expr, len(instances), 3, [O.fr_from_ints(p) for p in info.preprocess_polys],
+                       info.permutation_polys, info.permutations, nz)
+    inst = O.fr_from_ints(instances)
+    to = O.Transcript()
+    assert ohp.prove(to, inst, [O.fr_from_ints(c) for c in w])
+    assert O.lasso_prove(okzg, to, O.TABLE_RANGE, chunks, k, np.asarray(w[w_o], dtype=np.uint64), None)
+    tr = hl.Keccak256Transcript(ctx)
+    H.HyperPlonkLasso(ctx, kzg, info, O.TABLE_RANGE, chunks, w_o).prove(instances, w)
+    proof = tr.into_proof()
+    assert proof == to.proof()
+    vk = V.MultilinearKzgVerifier.setup(ss)
+    pre = [okzg.commit(O.fr_from_ints(p)) for p in info.preprocess_polys]
+    sig = [okzg.commit(O.fr_from_ints(p)) for p in H.permutation_polys(k, info.permutation_polys, info.permutations)]
+    hpv = V.HyperPlonkVerifier(vk, k, info.num_instances, 3, None, 0, nz, expr, pre, sig)
+    assert V.HyperPlonkLassoVerifier(hpv, O.TABLE_RANGE, chunks, w_o).verify(proof, inst, k)
+    assert not V.HyperPlonkLassoVerifier(hpv, O.TABLE_RANGE, chunks, 1).verify(proof, inst, k)  # linked to the wrong column
+    ctx.close()
+
+
 # ---- LogUp lookup argument (prover.rs:50-250) --------------------------------------------------------------
 @pytest.mark.parametrize("k", [2, 5, 11])
 def test_expression_rows_parity(hl, env, k):

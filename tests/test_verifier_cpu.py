@@ -303,6 +303,40 @@ def test_cfg1_hyperplonk_then_lasso_on_one_transcript(okzg, vkzg, k, mu):
     assert vkzg.lasso_verify(tr, O.TABLE_RANGE, chunks, mu) and tr.done()
 
 
+def test_lasso_as_the_lookup_argument_of_a_hyperplonk_circuit(okzg, vkzg):
+    """BASELINE cfg1 at its stated size, LINKED: a k = 10 vanilla-plonk circuit whose output wire holds 32-bit values in
+    every row, the Lasso range check (c = 2 x 16 bit, 2^10 lookups = one per row, 2^16 subtables) over that whole column
+    on the same transcript, and the verifier requires the Lasso section's commitment to `a` to BE the HyperPlonk
+    section's commitment to w_o. A Lasso section about other values — even in-range ones — is rejected."""
+    k, chunks, w_o = 10, 2, 2
+    info, instances, w = H.range_checked_plonk_circuit(k, 4242)
+    nz, expr = compose(k, info.constraints, info.num_poly, info.permutation_polys)
+    ohp = O.HyperPlonk(okzg, k, expr, len(instances), 3, [O.fr_from_ints(p) for p in info.preprocess_polys],
+                       info.permutation_polys, info.permutations, nz)
+    inst = O.fr_from_ints(instances)
+    xs = np.asarray(w[w_o], dtype=np.uint64)
+
+    def prove(lookups):
+        tr = O.Transcript()
+        assert ohp.prove(tr, inst, [O.fr_from_ints(c) for c in w])
+        assert O.lasso_prove(okzg, tr, O.TABLE_RANGE, chunks, k, lookups, None)
+        return tr.proof()
+
+    hv = V.HyperPlonkLassoVerifier(_hyperplonk_verifier(okzg, vkzg, info, expr, nz), O.TABLE_RANGE, chunks, w_o)
+    proof = prove(xs)
+    assert (hv.witness_commitment(proof) == okzg.commit(O.fr_from_ints(w[w_o]))).all()
+    assert hv.verify(proof, inst, k)
+    other = xs.copy()
+    other[5] ^= np.uint64(1)  # still a 32-bit value, but not the circuit's
+    bad = prove(other)
+    assert not hv.verify(bad, inst, k)
+    # ... although each section of `bad` is valid on its own (the unlinked check accepts it)
+    tr = V.ProofTranscript(bad)
+    assert hv.hpv.verify(tr, inst) and vkzg.lasso_verify(tr, O.TABLE_RANGE, chunks, k) and tr.done()
+    # an out-of-range witness cannot be proven at all: the range table with c = 2 has no entry for 2^32
+    assert not hv.verify(proof[:-1], inst, k) and not hv.verify(tampered(proof, 64 * w_o + 5), inst, k)
+
+
 def test_hyperplonk_verifier_rejects_malformed_parameters(okzg, vkzg):
     from halo2_lasso_b200.expression import Expression as E
 
