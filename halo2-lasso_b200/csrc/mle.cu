@@ -126,8 +126,8 @@ int mle_dot_many(Ctx* c, const Fr* const* h_tables, int ntables, size_t len, con
   a.counter = &c->d_sc->counter;
   a.out = d_out;
   int bx = (int)((len + 255) / 256);
-  int cap = (4 * NUM_SMS + ntables - 1) / ntables;
-  if (bx > cap) bx = cap;
+  int cap = (4 * NUM_SMS) / ntables;  // 4 CTAs of 256 threads per SM (62 registers), ONE wave: floor, not ceil — 25 x 24
+  if (bx > cap) bx = cap;             // = 600 CTAs on 592 slots left 8 CTAs for a second wave
   if (bx < 1) bx = 1;
   if ((size_t)bx * ntables > c->partial_elems) return B200_ERR_NOMEM;
   CUDA_TRY(launch_pdl(mle_dot_kernel, dim3(dim3(bx, ntables)), dim3(256), 0, c->stream, a));

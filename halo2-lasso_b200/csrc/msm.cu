@@ -525,76 +525,87 @@ __device__ __forceinline__ void warp_weighted_sum(G1Xyzz x, G1Xyzz& plain, G1Xyz
   weighted = warp_sum_xyzz(s);
 }
 
-// level 1 -> level 2: one THREAD per 8 consecutive level-1 entries (work-efficient while there are still many entries):
-// R2 = Σ R1, A2 = Σ l R1_l (l = 0..7), Y2 = Σ Y1
+// level 1 -> level 2: TWO threads per 8 consecutive level-1 entries (work-efficient while there are still many entries):
+// the even thread runs the dependent chain R2 = Σ R1, A2 = Σ l R1_l (l = 0..7), the odd thread the independent plain sum
+// Y2 = Σ Y1 — 16 instead of 24 group operations on the critical path of this latency-bound launch
 __global__ void __launch_bounds__(128) msm_red_l1_kernel(MsmRedDesc d, uint32_t n2tot, const G1Xyzz* __restrict__ in,
                                                          uint32_t n1tot, G1Xyzz* __restrict__ out) {
-  const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t g = tid >> 1, role = tid & 1;
   if (g >= n2tot) return;
   const uint32_t w = seg_of(d.off2, d.nwin, g);
   const uint32_t i0 = d.off1[w] + (g - d.off2[w]) * 8, iend = d.off1[w + 1];
   const uint32_t i1 = i0 + 8 < iend ? i0 + 8 : iend;
-  G1Xyzz run = g1_identity(), wsum = g1_identity(), ysum = g1_identity();
+  if (role) {
+    G1Xyzz ysum = g1_identity();
+    for (uint32_t i = i1; i-- > i0;) ysum = g1_add(ysum, ld_xyzz(in + n1tot + i));
+    st_xyzz(out + (size_t)2 * n2tot + g, ysum);
+    return;
+  }
+  G1Xyzz run = g1_identity(), wsum = g1_identity();
   for (uint32_t i = i1; i-- > i0;) {
-    ysum = g1_add(ysum, ld_xyzz(in + n1tot + i));
-    if (i > i0) {
-      run = g1_add(run, ld_xyzz(in + i));
-      wsum = g1_add(wsum, run);
-    } else {
-      run = g1_add(run, ld_xyzz(in + i));
-    }
+    run = g1_add(run, ld_xyzz(in + i));
+    if (i > i0) wsum = g1_add(wsum, run);
   }
   st_xyzz(out + g, run);
   st_xyzz(out + n2tot + g, wsum);
-  st_xyzz(out + (size_t)2 * n2tot + g, ysum);
 }
 
-// One warp per 32 consecutive entries of a window at level LV (1 or 2). Streams in: R (weighted), P[0..NP) plain.
-// Streams out: R', Wt' (= Σ l R_l) and the NP plain sums.
+// 1 + NP warps per 32 consecutive entries of a window at level LV (1 or 2). Streams in: R (weighted), P[0..NP) plain.
+// Streams out: R', Wt' (= Σ l R_l) by the first warp (suffix scan + sum: 10 add steps) and the NP plain sums by one warp
+// each (5 add steps) — the streams are independent, so they do not queue up behind each other in one warp.
 template <int NP>
 __global__ void __launch_bounds__(128) msm_red_tree_kernel(MsmRedDesc d, int lv, uint32_t nout_tot,
                                                            const G1Xyzz* __restrict__ in, uint32_t nin_tot,
                                                            G1Xyzz* __restrict__ out) {
-  const uint32_t wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const uint32_t wid = gw / (1 + NP), role = gw % (1 + NP);
   if (wid >= nout_tot) return;
   const uint32_t* offo = lv == 1 ? d.off2 : d.off3;
   const uint32_t* offi = lv == 1 ? d.off1 : d.off2;
   const uint32_t w = seg_of(offo, d.nwin, wid);
   const uint32_t i0 = offi[w] + (wid - offo[w]) * 32, iend = offi[w + 1];
   const bool valid = i0 + lane < iend;
-  G1Xyzz plain, wt;
-  warp_weighted_sum(valid ? ld_xyzz(in + i0 + lane) : g1_identity(), plain, wt);
-  if (lane == 0) {
-    st_xyzz(out + wid, plain);
-    st_xyzz(out + nout_tot + wid, wt);
-  }
-#pragma unroll
-  for (int s = 0; s < NP; ++s) {
-    const G1Xyzz v = warp_sum_xyzz(valid ? ld_xyzz(in + (size_t)(1 + s) * nin_tot + i0 + lane) : g1_identity());
-    if (lane == 0) st_xyzz(out + (size_t)(2 + s) * nout_tot + wid, v);
+  if (role == 0) {
+    G1Xyzz plain, wt;
+    warp_weighted_sum(valid ? ld_xyzz(in + i0 + lane) : g1_identity(), plain, wt);
+    if (lane == 0) {
+      st_xyzz(out + wid, plain);
+      st_xyzz(out + nout_tot + wid, wt);
+    }
+  } else {
+    const uint32_t sidx = role - 1;
+    const G1Xyzz v = warp_sum_xyzz(valid ? ld_xyzz(in + (size_t)(1 + sidx) * nin_tot + i0 + lane) : g1_identity());
+    if (lane == 0) st_xyzz(out + (size_t)(2 + sidx) * nout_tot + wid, v);
   }
 }
 
-// One warp per window: level-3 streams R3, Bq3, A3, Y3 (<= 32 entries each) -> S_w
+// One CTA of four warps per window: level-3 streams R3, Bq3, A3, Y3 (<= 32 entries each) -> S_w. Warp 0 builds C (weighted
+// sum of R3), warps 1-3 the plain sums of the carried streams in parallel; lane 0 of warp 0 then runs the Horner tail
+// (11 doublings, 3 additions).
 __global__ void __launch_bounds__(128) msm_red_final_kernel(MsmRedDesc d, const G1Xyzz* __restrict__ in, uint32_t n3tot,
                                                             G1Xyzz* __restrict__ window_sum) {
-  const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  __shared__ G1Xyzz s_sum[3];
+  const uint32_t w = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (w >= d.nwin) return;
   const uint32_t i0 = d.off3[w], n = d.off3[w + 1] - i0;
   const bool valid = lane < n;
   G1Xyzz r3, c;
-  warp_weighted_sum(valid ? ld_xyzz(in + i0 + lane) : g1_identity(), r3, c);
-  const G1Xyzz bq = warp_sum_xyzz(valid ? ld_xyzz(in + (size_t)1 * n3tot + i0 + lane) : g1_identity());
-  const G1Xyzz a = warp_sum_xyzz(valid ? ld_xyzz(in + (size_t)2 * n3tot + i0 + lane) : g1_identity());
-  const G1Xyzz y = warp_sum_xyzz(valid ? ld_xyzz(in + (size_t)3 * n3tot + i0 + lane) : g1_identity());
-  if (lane == 0) {  // S = Y + 8 (A + 8 (Bq + 32 C))
+  if (warp == 0) {
+    warp_weighted_sum(valid ? ld_xyzz(in + i0 + lane) : g1_identity(), r3, c);
+  } else {
+    const G1Xyzz v = warp_sum_xyzz(valid ? ld_xyzz(in + (size_t)warp * n3tot + i0 + lane) : g1_identity());
+    if (lane == 0) s_sum[warp - 1] = v;  // 0: Bq, 1: A, 2: Y
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {  // S = Y + 8 (A + 8 (Bq + 32 C))
     G1Xyzz acc = c;
     for (int k = 0; k < 5; ++k) acc = g1_dbl_ni(acc);
-    acc = g1_add_ni(acc, bq);
+    acc = g1_add_ni(acc, s_sum[0]);
     for (int k = 0; k < 3; ++k) acc = g1_dbl_ni(acc);
-    acc = g1_add_ni(acc, a);
+    acc = g1_add_ni(acc, s_sum[1]);
     for (int k = 0; k < 3; ++k) acc = g1_dbl_ni(acc);
-    acc = g1_add_ni(acc, y);
+    acc = g1_add_ni(acc, s_sum[2]);
     st_xyzz(window_sum + w, acc);
   }
 }
@@ -790,9 +801,9 @@ int msm_batch(Ctx* c, const MsmJob* jobs, int J, G1Aff* d_out, const MsmDerive* 
   msm_bucket_kernel<<<(nbuckets + 127) / 128, 128, 0, s>>>(nbuckets, toff, partial, bucket_sum, heavy, heavy_count);
   msm_heavy_kernel<<<NUM_SMS * 8, 128, 0, s>>>(toff, partial, bucket_sum, heavy, heavy_count);
   msm_red_l0_kernel<<<(n1tot + 127) / 128, 128, 0, s>>>(rd, n1tot, bucket_sum, lvl1, lvl1 + n1tot);
-  msm_red_l1_kernel<<<(n2tot + 127) / 128, 128, 0, s>>>(rd, n2tot, lvl1, n1tot, lvl2);
-  msm_red_tree_kernel<2><<<(n3tot + 3) / 4, 128, 0, s>>>(rd, 2, n3tot, lvl2, n2tot, lvl3);
-  msm_red_final_kernel<<<(nwin + 3) / 4, 128, 0, s>>>(rd, lvl3, n3tot, window_sum);
+  msm_red_l1_kernel<<<(2 * n2tot + 127) / 128, 128, 0, s>>>(rd, n2tot, lvl1, n1tot, lvl2);
+  msm_red_tree_kernel<2><<<(3 * n3tot + 3) / 4, 128, 0, s>>>(rd, 2, n3tot, lvl2, n2tot, lvl3);
+  msm_red_final_kernel<<<nwin, 128, 0, s>>>(rd, lvl3, n3tot, window_sum);
   msm_finish_kernel<<<J + nderive, 32, 0, s>>>(plan, dv, window_sum, d_out);
   prof_end(c, pi);
   count_launch(c, 10);

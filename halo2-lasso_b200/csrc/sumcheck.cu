@@ -656,8 +656,15 @@ __global__ void sc_init_kernel(ScState* st, const Fr* claim) {
   }
 }
 
-static inline int blocks_for(uint32_t pairs, int rows) {
-  int per_row = (2 * NUM_SMS + rows - 1) / rows;  // ~2 CTAs per SM over the whole grid
+// Grid of a round kernel: `rows` rows (terms) of equal work, at most ONE wave. `occ` = CTAs of that kernel an SM can hold
+// (register-limited: 2 for the NP = 2 kernels, 3 for NP = 1; measured at preload, g_occ). Round 1 sized the grid as
+// ceil(2 * 148 / rows) * rows, which for 16 rows is 304 CTAs on 296 slots: the 8 CTAs of the second wave ran alone and
+// stretched every big grand-product round by half (38 G products/s at T = 16 against 47 at T = 1 on the same kernel).
+enum { OCC_EVAL = 0, OCC_FACT = 4, OCC_COEFF = 8 };  // + (NP - 1) * 2 + BIND
+static int g_occ[10] = {2, 2, 2, 2, 2, 2, 2, 2, 2, 2};
+static inline int blocks_for(uint32_t pairs, int rows, int occ) {
+  if (occ < 1) occ = 1;
+  int per_row = (occ * NUM_SMS) / rows;
   if (per_row < 1) per_row = 1;
   int need = (int)((pairs + SC_THREADS - 1) / SC_THREADS);
   if (need < 1) need = 1;
@@ -764,7 +771,8 @@ int sumcheck_prove_evals(Ctx* c, const ScEvalJob& job) {
       tail_done = true;
       break;
     }
-    dim3 grid(blocks_for(a.pairs, T), T);
+    const int bind = round > 0 ? 1 : 0;
+    dim3 grid(blocks_for(a.pairs, T, g_occ[(fact ? OCC_FACT : OCC_EVAL) + (NP - 1) * 2 + bind]), T);
     if ((size_t)grid.x * grid.y * (NP + 1) > c->partial_elems) return B200_ERR_NOMEM;
     NvtxRange nvtx_round("sum_check_prove_round-%d", round);  // classic.rs:226 (+ next_round :234, fused into the launch)
     const int pi = prof_begin(c, round);
@@ -996,7 +1004,7 @@ int sumcheck_prove_coeffs(Ctx* c, const ScCoeffJob& job) {
       a.out[k] = dst_base + (size_t)k * dst_sz;
       a.eq_out[k] = dst_base + (size_t)(K + k) * dst_sz;
     }
-    dim3 grid(blocks_for(a.pairs, K), K);
+    dim3 grid(blocks_for(a.pairs, K, g_occ[OCC_COEFF + (round > 0 ? 1 : 0)]), K);
     if ((size_t)grid.x * grid.y * 2 > c->partial_elems) return B200_ERR_NOMEM;
     if (round == 0) {
       CUDA_TRY(launch_pdl(sc_coeff_round_kernel<false>, grid, SC_THREADS, 0, s, a));
@@ -1026,6 +1034,22 @@ int sumcheck_prove_coeffs(Ctx* c, const ScCoeffJob& job) {
 
 // every kernel of this file, loaded up front (b200_ctx_create -> preload_all_kernels, capi.cu)
 void preload_sumcheck() {
+  auto occ_of = [](const void* k) {
+    int o = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, k, SC_THREADS, 0) != cudaSuccess || o < 1) o = 2;
+    return o;
+  };
+  g_occ[OCC_EVAL + 0] = occ_of((const void*)sc_eval_round_kernel<1, false, false>);
+  g_occ[OCC_EVAL + 1] = occ_of((const void*)sc_eval_round_kernel<1, true, false>);
+  g_occ[OCC_EVAL + 2] = occ_of((const void*)sc_eval_round_kernel<2, false, false>);
+  g_occ[OCC_EVAL + 3] = occ_of((const void*)sc_eval_round_kernel<2, true, false>);  // <2, true, true> has the same footprint
+  g_occ[OCC_FACT + 0] = occ_of((const void*)sc_eval_fact_kernel<1, false>);
+  g_occ[OCC_FACT + 1] = occ_of((const void*)sc_eval_fact_kernel<1, true>);
+  g_occ[OCC_FACT + 2] = occ_of((const void*)sc_eval_fact_kernel<2, false>);
+  g_occ[OCC_FACT + 3] = occ_of((const void*)sc_eval_fact_kernel<2, true>);
+  g_occ[OCC_COEFF + 0] = occ_of((const void*)sc_coeff_round_kernel<false>);
+  g_occ[OCC_COEFF + 1] = occ_of((const void*)sc_coeff_round_kernel<true>);
+  cudaGetLastError();
   B200_PRELOAD(sc_eval_round_kernel<1, false, false>);
   B200_PRELOAD(sc_eval_round_kernel<2, false, false>);
   B200_PRELOAD(sc_eval_round_kernel<1, true, false>);
