@@ -401,9 +401,10 @@ def main():
     except Exception:
         pass
     # the headline proof's dominant kernel, msm_accumulate_kernel (XYZZ mixed additions, 10 Montgomery products each):
-    # additions = non-zero signed digits of the three MSM batches, counted from the plan: commit (dim: 1 window, E: 1,
+    # additions = non-zero signed digits of the three MSM batches, counted from the plan: commit (dim: 1 window,
     # read_ts: 1 populated window, each c x m; final_cts c x 2^16) + the two batch openings (16 windows x 2^mu, 16 x 2^16)
-    adds = (3 * CHUNKS * m + CHUNKS * (1 << 16) + 16 * (m - 1) + 16 * ((1 << 16) - 1)) / world
+    # (the E_t commitments add no points: they are regrouped from the dim_t bucket sums, MsmJob::group_*)
+    adds = (2 * CHUNKS * m + CHUNKS * (1 << 16) + 16 * (m - 1) + 16 * ((1 << 16) - 1)) / world
     acc_ms = phases.get("msm_accumulate")
     roof_msm = None
     if acc_ms:

@@ -91,6 +91,15 @@ int b200_ctx_create(int device, b200_ctx** out) {
     CUDA_TRY(cudaMemset(c->dbg_clocks, 0, 32 * 16 * sizeof(long long)));
   }
   CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  for (int kind = 1; kind <= 2; ++kind) {  // value-sorted address lists of the and / xor subtables (grouped E commitments)
+    std::vector<uint32_t> vals((size_t)1 << 16), perm, off;
+    for (uint32_t x = 0; x < (1u << 16); ++x) vals[x] = kind == 1 ? ((x >> 8) & (x & 0xff)) : ((x >> 8) ^ (x & 0xff));
+    if (!lasso_group_lists(vals.data(), &perm, &off)) return B200_ERR_ARG;
+    CUDA_TRY(cudaMalloc(&c->d_group_perm[kind], perm.size() * 4));
+    CUDA_TRY(cudaMalloc(&c->d_group_off[kind], off.size() * 4));
+    CUDA_TRY(cudaMemcpy(c->d_group_perm[kind], perm.data(), perm.size() * 4, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(c->d_group_off[kind], off.data(), off.size() * 4, cudaMemcpyHostToDevice));
+  }
   // keep freed blocks cached in the stream-ordered pool: proofs reuse the same sizes over and over
   cudaMemPool_t pool;
   CUDA_TRY(cudaDeviceGetDefaultMemPool(&pool, device));
@@ -128,6 +137,10 @@ void b200_ctx_destroy(b200_ctx* h) {
   if (c->my_mailbox) cudaFree(c->my_mailbox);
   if (c->my_arena) cudaFree(c->my_arena);
   if (c->d_peer_err) cudaFree(c->d_peer_err);
+  for (int kind = 1; kind <= 2; ++kind) {
+    cudaFree(c->d_group_perm[kind]);
+    cudaFree(c->d_group_off[kind]);
+  }
   if (c->hb_stream) cudaStreamDestroy(c->hb_stream);
   if (c->hb_event) cudaEventDestroy(c->hb_event);
   if (c->hb_stop) cudaFree(c->hb_stop);

@@ -170,6 +170,7 @@ int b200_lasso_prove(b200_ctx* h, int kind, int chunks, int mu, const uint64_t* 
 struct b200_lasso_tab {
   LassoTableDesc d;
   uint32_t* d_values;
+  uint32_t *d_perm = nullptr, *d_off = nullptr;
 };
 
 int b200_lasso_table_create(b200_ctx* h, const b200_lasso_table* t, b200_lasso_tab** out) {
@@ -215,12 +216,25 @@ int b200_lasso_table_create(b200_ctx* h, const b200_lasso_table* t, b200_lasso_t
   }
   tab->d = LassoTableDesc{t->chunks, t->num_operands, t->operand_bits, t->out_bits, vb, tab->d_values,
                           fe_from_canonical<FrP>(raw)};  // reduces the 256-bit integer mod r
+  std::vector<uint32_t> perm, off;
+  if (lasso_group_lists(t->subtable, &perm, &off) && !perm.empty()) {  // grouped E commitments (MsmJob::group_*)
+    if (cudaMalloc(&tab->d_perm, perm.size() * 4) == cudaSuccess && cudaMalloc(&tab->d_off, off.size() * 4) == cudaSuccess &&
+        cudaMemcpy(tab->d_perm, perm.data(), perm.size() * 4, cudaMemcpyHostToDevice) == cudaSuccess &&
+        cudaMemcpy(tab->d_off, off.data(), off.size() * 4, cudaMemcpyHostToDevice) == cudaSuccess) {
+      tab->d.d_group_perm = tab->d_perm;
+      tab->d.d_group_off = tab->d_off;
+      tab->d.ngroups = (int)off.size() - 1;
+    }
+    cudaGetLastError();
+  }
   *out = tab;
   return B200_OK;
 }
 void b200_lasso_table_free(b200_lasso_tab* tab) {
   if (!tab) return;
   cudaFree(tab->d_values);
+  cudaFree(tab->d_perm);
+  cudaFree(tab->d_off);
   delete tab;
 }
 int b200_lasso_prove_table_dev(b200_ctx* h, const b200_lasso_tab* tab, int mu, const void* dev_xs, const void* dev_ys) {

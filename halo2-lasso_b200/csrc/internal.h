@@ -65,6 +65,9 @@ struct Ctx {
   int shard_lasso_k0 = 0;  // > 0: the Lasso prover shards its tables / trees on the index window [k0 - g, k0) (lasso.cu)
   bool eq_factored = true;  // EVAL-shape sum-checks use the eq-factored round kernel (b200_sumcheck_eq_factored)
   bool shard_commits = false;  // every commitment MSM is split by point range over the ranks (all ranks call)
+  // value-sorted address lists of the built-in and / xor subtables for grouped E commitments (MsmJob::group_*), device
+  uint32_t* d_group_perm[3] = {nullptr, nullptr, nullptr};
+  uint32_t* d_group_off[3] = {nullptr, nullptr, nullptr};
   int shard_sumcheck_min_vars = 0;  // > 0: sum-checks of the whole provers with at least that many variables run
                                     // hypercube-sharded over the ranks (sumcheck_prove_evals_dist, shard.cu)
 };
@@ -179,7 +182,17 @@ struct MsmJob {
   // map_g > 0: the scalars are one rank's compact slice of a polynomial sharded on the index bits [map_p, map_p + map_g):
   // scalar i multiplies base ((i >> p) << (p + g)) | (rank << p) | (i & (2^p - 1))
   int map_p = 0, map_g = 0, map_rank = 0;
+  // GROUPED job (no scalars of its own: scalars = nullptr, n = 0): result = Σ_v v * (Σ_{k in group v} B_k) over the bucket
+  // sums B_k of job `group_src` of the same batch, whose scalars are 16-bit addresses d (bucket k = address k + 1) — the
+  // commitment to E = T[dim] falls out of the buckets of the commitment to dim (same bases, E constant per address), so
+  // its 2^mu mixed additions are replaced by one sum per table value. group_perm = the addresses' bucket indices sorted
+  // by table value, group_off[v - 1 .. v] = the range of value v (v = 1 .. ngroups); addresses with T = 0 are left out.
+  int group_src = -1, ngroups = 0;
+  const uint32_t* group_perm = nullptr;
+  const uint32_t* group_off = nullptr;
 };
+// a grouped E commitment pays from this many points on (below, forcing 2^16 buckets on the dim job costs more than it saves)
+uint64_t msm_group_min_points();
 // extra result J + i = Σ_t 2^(shift t) * result(src[t]): a commitment that is a linear combination of other commitments
 // of the same batch (Lasso: a = Σ_t 2^(w t) E_t) costs doublings instead of an MSM
 struct MsmDerive {
@@ -220,7 +233,14 @@ struct LassoTableDesc {
   int chunks, num_operands, operand_bits, out_bits, value_bits;
   const uint32_t* d_values;
   Fr digest;  // Montgomery
+  // grouped E commitments (MsmJob::group_*): set when T[0] = 0 and the values fit 12 bits, else null
+  const uint32_t* d_group_perm = nullptr;
+  const uint32_t* d_group_off = nullptr;
+  int ngroups = 0;
 };
+// host: value-sorted bucket indices of a 2^16-entry table (perm: 65535 entries at most, off: ngroups + 1); false when
+// the table is not eligible (T[0] != 0 or a value above 4095)
+bool lasso_group_lists(const uint32_t* values, std::vector<uint32_t>* perm, std::vector<uint32_t>* off);
 int lasso_prove(Ctx* c, int kind, int chunks, int mu, const uint64_t* d_xs, const uint64_t* d_ys,
                 const LassoTableDesc* desc = nullptr);
 int lasso_witness(Ctx* c, int kind, int chunks, int mu, const uint64_t* d_xs, const uint64_t* d_ys, Fr* d_mt,

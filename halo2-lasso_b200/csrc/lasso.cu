@@ -574,9 +574,25 @@ int lasso_prove(Ctx* c, int kind, int chunks, int mu, const uint64_t* d_xs, cons
     const int j_dim = J;
     for (int t = 0; t < C_; ++t) jobs[J++] = MsmJob{dims + (size_t)t * m, c->srs[mu], m, MSM_U32, 16, nullptr};
     const int j_e = e_is_dim ? j_dim : J;
+    // E_t = T[dim_t] over the same bases as dim_t: its commitment is a regrouping of dim_t's bucket sums by table value
+    // (MsmJob::group_*) — no pass over the points at all. Needs T[0] = 0 and enough points per rank to pay.
+    const uint32_t* gperm = desc ? desc->d_group_perm : c->d_group_perm[kind];
+    const uint32_t* goff = desc ? desc->d_group_off : c->d_group_off[kind];
+    const int ngroups = desc ? desc->ngroups : (kind == 0 ? 0 : 255);
+    const uint64_t pts_per_rank = c->shard_commits && c->peer.world > 1 && m % c->peer.world == 0 ? m / c->peer.world : m;
+    const bool grouped = !e_is_dim && gperm && goff && ngroups > 0 && pts_per_rank >= msm_group_min_points();
     if (!e_is_dim)
-      for (int t = 0; t < C_; ++t)
-        jobs[J++] = MsmJob{es + (size_t)t * m, c->srs[mu], m, MSM_U32, desc ? (desc->value_bits > 0 ? desc->value_bits : 1) : out_bits, nullptr};
+      for (int t = 0; t < C_; ++t) {
+        MsmJob ej{es + (size_t)t * m, c->srs[mu], m, MSM_U32, desc ? (desc->value_bits > 0 ? desc->value_bits : 1) : out_bits, nullptr};
+        if (grouped) {
+          ej = MsmJob{nullptr, nullptr, 0, MSM_U32, 1, nullptr};
+          ej.group_src = j_dim + t;
+          ej.ngroups = ngroups;
+          ej.group_perm = gperm;
+          ej.group_off = goff;
+        }
+        jobs[J++] = ej;
+      }
     const int j_ts = J;
     for (int t = 0; t < C_; ++t) jobs[J++] = MsmJob{ts + (size_t)t * m, c->srs[mu], m, MSM_U32, mu + 1, nullptr};
     const int j_cts = J;

@@ -18,6 +18,8 @@
 // Scalars with few significant bits (dims, counters, subtable values) only populate the windows they
 // need, which the reference cannot exploit. The group element is unique, so any schedule yields the
 // reference's commitment bytes.
+#include <stdlib.h>
+
 #include "internal.h"
 
 namespace b200 {
@@ -44,6 +46,10 @@ struct MsmJobDev {
   int map_p, map_g;     // map_g > 0: scalar i belongs to base point ((i >> p) << (p + g)) | (rank << p) | (i & (2^p - 1))
   uint32_t map_rank;    // (the rank's slice of a polynomial sharded on the index bits [p, p + g), shard.cu)
   uint32_t win_base;    // first window slot of this job
+  // grouped job (MsmJob::group_src >= 0): its single reduction window has `B` = ngroups buckets filled by msm_group_kernel
+  int group_src;
+  const uint32_t* group_perm;
+  const uint32_t* group_off;
 };
 struct MsmPlanDev {
   int J;
@@ -458,6 +464,27 @@ __global__ void __launch_bounds__(128) msm_heavy_kernel(const uint32_t* __restri
   }
 }
 
+// Grouped jobs: bucket v - 1 of the job = Σ_{k in group v} B_k over the bucket sums of its source job. One CTA per
+// (value, job): the threads stride over the member list, then a shuffle + shared-memory reduction.
+__global__ void __launch_bounds__(128) msm_group_kernel(MsmPlanDev plan, G1Xyzz* __restrict__ bucket_sum) {
+  __shared__ G1Xyzz s_part[4];
+  const MsmJobDev& jb = plan.job[blockIdx.y];
+  if (jb.group_src < 0 || blockIdx.x >= jb.B) return;
+  const uint32_t v = blockIdx.x;  // weight v + 1
+  const uint32_t lo = jb.group_off[v], hi = jb.group_off[v + 1];
+  const G1Xyzz* __restrict__ src = bucket_sum + plan.job[jb.group_src].bucket_base;
+  G1Xyzz acc = g1_identity();
+  for (uint32_t i = lo + threadIdx.x; i < hi; i += blockDim.x) acc = g1_add_ni(acc, ld_xyzz(src + jb.group_perm[i]));
+  acc = warp_sum_xyzz(acc);
+  if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    acc = s_part[0];
+    for (int w = 1; w < 4; ++w) acc = g1_add_ni(acc, s_part[w]);
+    st_xyzz(bucket_sum + jb.bucket_base + v, acc);
+  }
+}
+
 // ---- window reduction ----------------------------------------------------------------------------
 // S_w = Σ_k (k+1) B_k over the B buckets of a window, without any scalar multiplication. Write
 // k = lo + 8 (l1 + 8 (l2 + 32 l3)); then  k + 1 = (lo + 1) + 8 l1 + 64 l2 + 2048 l3  and
@@ -671,10 +698,48 @@ int msm_batch(Ctx* c, const MsmJob* jobs, int J, G1Aff* d_out, const MsmDerive* 
   uint32_t nbuckets = 0, nwin = 0, max_n = 0, max_n_hist = 0;
   std::vector<uint32_t> desc;  // wb | wB | off1 | off2 | off3, each nwin (+1 for the prefixes)
   std::vector<uint32_t> wb, wB;
+  bool any_grouped = false;
+  std::vector<char> is_group_src(J, 0);
+  for (int j = 0; j < J; ++j) {
+    if (jobs[j].group_src < 0) continue;
+    const MsmJob& g = jobs[j];
+    // the source comes earlier in the batch, carries 16-bit u32 addresses and is not grouped / precomputed itself
+    if (g.group_src >= j || g.ngroups < 1 || g.ngroups > 4095 || !g.group_perm || !g.group_off) return B200_ERR_ARG;
+    const MsmJob& src = jobs[g.group_src];
+    if (src.group_src >= 0 || src.kind != MSM_U32 || src.bits > 16 || src.ext) return B200_ERR_ARG;
+    is_group_src[g.group_src] = 1;
+    any_grouped = true;
+  }
   for (int j = 0; j < J; ++j) {
     const MsmJob& in = jobs[j];
-    if (in.n == 0 || in.n > (1u << 30) || in.bits < 1 || in.bits > 256) return B200_ERR_ARG;
     MsmJobDev& jb = plan.job[j];
+    jb.group_src = in.group_src;
+    jb.group_perm = in.group_perm;
+    jb.group_off = in.group_off;
+    if (in.group_src >= 0) {  // no points of its own: one reduction window of ngroups buckets, filled by msm_group_kernel
+      jb.scalars = nullptr;
+      jb.bases = nullptr;
+      jb.n = 0;
+      jb.kind = MSM_U32;
+      jb.map_p = jb.map_g = 0;
+      jb.map_rank = 0;
+      jb.precomp = 0;
+      jb.ext_stride = 0;
+      jb.c = 1;
+      jb.W = 0;
+      jb.Wred = 1;
+      jb.B = (uint32_t)in.ngroups;
+      jb.hist = 0;
+      jb.bucket_base = nbuckets;
+      jb.pair_base = pairs;
+      jb.win_base = nwin;
+      wb.push_back(nbuckets);
+      wB.push_back(jb.B);
+      nbuckets += jb.B;
+      nwin += 1;
+      continue;
+    }
+    if (in.n == 0 || in.n > (1u << 30) || in.bits < 1 || in.bits > 256) return B200_ERR_ARG;
     jb.scalars = in.scalars;
     jb.bases = in.bases;
     jb.n = (uint32_t)in.n;
@@ -695,6 +760,7 @@ int msm_batch(Ctx* c, const MsmJob* jobs, int J, G1Aff* d_out, const MsmDerive* 
       int cmax = ilog2_floor(in.n) - 3;
       if (cmax < 3) cmax = 3;
       if (cmax > 17) cmax = 17;
+      if (is_group_src[j]) cmax = 17;  // ONE window whose bucket k is address k + 1, whatever the number of points
       jb.W = (need + cmax - 1) / cmax;
       jb.c = (need + jb.W - 1) / jb.W;
       if (jb.c < 2) jb.c = 2;
@@ -800,6 +866,13 @@ int msm_batch(Ctx* c, const MsmJob* jobs, int J, G1Aff* d_out, const MsmDerive* 
   pi = prof_begin(c, PH_MSM_REDUCE);
   msm_bucket_kernel<<<(nbuckets + 127) / 128, 128, 0, s>>>(nbuckets, toff, partial, bucket_sum, heavy, heavy_count);
   msm_heavy_kernel<<<NUM_SMS * 8, 128, 0, s>>>(toff, partial, bucket_sum, heavy, heavy_count);
+  if (any_grouped) {
+    uint32_t maxg = 0;
+    for (int j = 0; j < J; ++j)
+      if (jobs[j].group_src >= 0 && (uint32_t)jobs[j].ngroups > maxg) maxg = (uint32_t)jobs[j].ngroups;
+    msm_group_kernel<<<dim3(maxg, J), 128, 0, s>>>(plan, bucket_sum);
+    count_launch(c);
+  }
   msm_red_l0_kernel<<<(n1tot + 127) / 128, 128, 0, s>>>(rd, n1tot, bucket_sum, lvl1, lvl1 + n1tot);
   msm_red_l1_kernel<<<(2 * n2tot + 127) / 128, 128, 0, s>>>(rd, n2tot, lvl1, n1tot, lvl2);
   msm_red_tree_kernel<2><<<(3 * n3tot + 3) / 4, 128, 0, s>>>(rd, 2, n3tot, lvl2, n2tot, lvl3);
@@ -809,6 +882,32 @@ int msm_batch(Ctx* c, const MsmJob* jobs, int J, G1Aff* d_out, const MsmDerive* 
   count_launch(c, 10);
   CUDA_TRY(cudaGetLastError());
   return B200_OK;
+}
+
+uint64_t msm_group_min_points() {
+  static const uint64_t v = [] {
+    const char* e = getenv("B200_MSM_GROUP_MIN_POINTS");  // tests lower it to exercise the grouped path at small sizes
+    return e ? (uint64_t)atoll(e) : (uint64_t)1 << 18;
+  }();
+  return v;
+}
+
+bool lasso_group_lists(const uint32_t* values, std::vector<uint32_t>* perm, std::vector<uint32_t>* off) {
+  const uint32_t S = 1u << 16;
+  if (values[0] != 0) return false;  // address 0 has no bucket (digit 0 is skipped)
+  uint32_t mx = 0;
+  for (uint32_t d = 0; d < S; ++d) mx = values[d] > mx ? values[d] : mx;
+  if (mx < 1 || mx > 4095) return false;
+  std::vector<uint32_t> cnt(mx + 2, 0);
+  for (uint32_t d = 1; d < S; ++d)
+    if (values[d]) ++cnt[values[d] + 1];
+  off->assign(mx + 1, 0);  // off[v - 1] = start of value v, off[mx] = end
+  for (uint32_t v = 1; v <= mx; ++v) (*off)[v] = (*off)[v - 1] + cnt[v + 1];
+  perm->assign((*off)[mx], 0);
+  std::vector<uint32_t> at(off->begin(), off->end());
+  for (uint32_t d = 1; d < S; ++d)
+    if (values[d]) (*perm)[at[values[d] - 1]++] = d - 1;  // bucket k holds address k + 1
+  return true;
 }
 
 // every kernel of this file, loaded up front (b200_ctx_create -> preload_all_kernels, capi.cu)
@@ -822,6 +921,7 @@ void preload_msm() {
   B200_PRELOAD(msm_accumulate_kernel);
   B200_PRELOAD(msm_bucket_kernel);
   B200_PRELOAD(msm_heavy_kernel);
+  B200_PRELOAD(msm_group_kernel);
   B200_PRELOAD(msm_red_l0_kernel);
   B200_PRELOAD(msm_red_l1_kernel);
   B200_PRELOAD(msm_red_tree_kernel<2>);

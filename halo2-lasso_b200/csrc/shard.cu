@@ -472,6 +472,11 @@ int msm_batch_dist(Ctx* c, const MsmJob* jobs, int J, G1Aff* d_out, const MsmDer
     sharded.push_back(j);
     is_sharded[j] = 1;
   }
+  for (int j = 0; j < J; ++j)  // a grouped job sums bucket sums of its source: partial exactly when the source is
+    if (loc[j].group_src >= 0 && is_sharded[loc[j].group_src]) {
+      sharded.push_back(j);
+      is_sharded[j] = 1;
+    }
   // a derived result is a partial sum exactly when its sources are (all of them or none: same shape by construction)
   for (int i = 0; i < nderive; ++i) {
     int cnt = 0;
