@@ -207,7 +207,10 @@ static __device__ __noinline__ void keccak_f1600_warp(uint64_t* s) {
   const int col1 = x + 5 * ((y + 1) % 5), col2 = x + 5 * ((y + 2) % 5), col3 = x + 5 * ((y + 3) % 5),
             col4 = x + 5 * ((y + 4) % 5);
   const int cl = (x + 4) % 5, cr = (x + 1) % 5;
-  const int row1 = 5 * y + (x + 1) % 5, row2 = 5 * y + (x + 2) % 5;
+  // chi reads b at the two next lanes of the row, and b is itself a permutation (pi) of the rotated lanes: fetch all
+  // three straight from `rot` through the composed lane maps — one dependent shuffle stage instead of two per round
+  const int x1 = (x + 1) % 5, x2 = (x + 2) % 5;
+  const int pi_src1 = ((x1 + 3 * y) % 5) + 5 * x1, pi_src2 = ((x2 + 3 * y) % 5) + 5 * x2;
 #pragma unroll 1
   for (int round = 0; round < 24; ++round) {
     uint64_t c = a ^ __shfl_sync(FULL, a, col1) ^ __shfl_sync(FULL, a, col2) ^ __shfl_sync(FULL, a, col3) ^
@@ -216,7 +219,7 @@ static __device__ __noinline__ void keccak_f1600_warp(uint64_t* s) {
     a ^= c_l ^ rotl64v(c_r, 1);
     const uint64_t rot = rotl64v(a, rho);
     const uint64_t b = __shfl_sync(FULL, rot, pi_src);
-    const uint64_t b1 = __shfl_sync(FULL, b, row1), b2 = __shfl_sync(FULL, b, row2);
+    const uint64_t b1 = __shfl_sync(FULL, rot, pi_src1), b2 = __shfl_sync(FULL, rot, pi_src2);
     a = b ^ (~b1 & b2);
     if (l == 0) a ^= RC[round];
   }
