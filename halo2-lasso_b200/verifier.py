@@ -221,6 +221,27 @@ class HyperPlonkVerifier:
         return _ok(lib().b200v_hyperplonk_verify(self.h, tr.h, _p(inst) if inst.size else None, C.c_int(inst.shape[0])))
 
 
+def fractional_sum_check_verify(tr, num_vars, claimed_p, claimed_q):
+    """`verify_fractional_sum_check(num_vars, claimed_p_0s, claimed_q_0s, transcript)` (fractional_sum_check.rs:192-265) on a
+    `ProofTranscript`; claimed_*: list with None (read from the proof) or a field element (Some: absorbed). Returns None on
+    REJECT, else (p_xs, q_xs, x, p_0s, q_0s) — the caller still checks p_xs / q_xs against its polynomials at x."""
+    B = len(claimed_p)
+    mask = 0
+    cp, cq = np.zeros((B, 4), dtype=np.uint64), np.zeros((B, 4), dtype=np.uint64)
+    for b in range(B):
+        if claimed_p[b] is not None:
+            mask |= 1 << b
+            cp[b] = np.asarray(claimed_p[b], dtype=np.uint64).reshape(4)
+        if claimed_q[b] is not None:
+            mask |= 1 << (16 + b)
+            cq[b] = np.asarray(claimed_q[b], dtype=np.uint64).reshape(4)
+    z = lambda k: np.zeros((k, 4), dtype=np.uint64)  # noqa: E731
+    p_xs, q_xs, x, p0, q0 = z(B), z(B), z(num_vars), z(B), z(B)
+    ok = _ok(lib().b200v_fractional_sum_check_verify(tr.h, C.c_int(B), C.c_int(num_vars), C.c_uint32(mask), _p(cp), _p(cq),
+                                                     _p(p_xs), _p(q_xs), _p(x), _p(p0), _p(q0)))
+    return (p_xs, q_xs, x, p0, q0) if ok else None
+
+
 class HyperPlonkLassoVerifier:
     """Verifier of `hyperplonk.HyperPlonkLasso` proofs: HyperPlonk::verify, then the Lasso verifier BOUND to the witness
     commitment the HyperPlonk section carries (the first phase's witness commitments open the proof: 64 bytes each, big-

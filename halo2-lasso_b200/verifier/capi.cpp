@@ -33,6 +33,13 @@ int guarded(F&& f) {
 inline int verdict(bool ok) { return ok ? B200V_ACCEPT : B200V_REJECT; }
 
 bool g1_ok(const G1Affine& p) { return p.on_curve(); }
+// field elements cross as Montgomery limbs: every residue is below the modulus; anything else is a malformed argument
+bool fr_ok(const void* fr, size_t n) {
+  const Fr* f = (const Fr*)fr;
+  for (size_t i = 0; i < n; ++i)
+    if (Fr::geq_mod(f[i].l)) return false;
+  return true;
+}
 
 // every Polynomial / Challenge / EqXY index and every rotation of the expression is usable by the verifier
 bool expr_ok(const ExprP& e, int npolys, int nchallenges, int num_vars) {
@@ -60,7 +67,7 @@ int b200v_transcript_new(const uint8_t* proof, uint64_t len, b200v_transcript** 
 void b200v_transcript_free(b200v_transcript* tr) { delete tr; }
 
 int b200v_transcript_common_field_elements(b200v_transcript* tr, const void* fr, int n) {
-  if (!tr || n < 0 || (!fr && n)) return B200V_ERR_ARG;
+  if (!tr || n < 0 || (!fr && n) || !fr_ok(fr, (size_t)n)) return B200V_ERR_ARG;
   for (int i = 0; i < n; ++i) tr->tr.common_field_element(((const Fr*)fr)[i]);
   return B200V_ACCEPT;
 }
@@ -88,7 +95,8 @@ int b200v_transcript_done(const b200v_transcript* tr) {
 
 int b200v_sumcheck_verify(b200v_transcript* tr, int num_vars, int degree, const void* sum_fr, int coefficients_form,
                           void* final_claim_out, void* challenges_out) {
-  if (!tr || num_vars < 1 || num_vars > 40 || degree < 1 || degree > 32 || !sum_fr || !final_claim_out || !challenges_out)
+  if (!tr || num_vars < 1 || num_vars > 40 || degree < 1 || degree > 32 || !sum_fr || !final_claim_out || !challenges_out ||
+      !fr_ok(sum_fr, 1))
     return B200V_ERR_ARG;
   return guarded([&] {
     Fr fin;
@@ -100,8 +108,36 @@ int b200v_sumcheck_verify(b200v_transcript* tr, int num_vars, int degree, const 
   });
 }
 
+int b200v_fractional_sum_check_verify(b200v_transcript* tr, int num_batching, int num_vars, uint32_t claimed_mask,
+                                      const void* claimed_p_fr, const void* claimed_q_fr, void* p_xs_out, void* q_xs_out,
+                                      void* x_out, void* p_0s_out, void* q_0s_out) {
+  const int B = num_batching;
+  if (!tr || B < 1 || B > 16 || num_vars < 1 || num_vars > 40 || !p_xs_out || !q_xs_out || !x_out) return B200V_ERR_ARG;
+  if ((claimed_mask & 0xffffu) >> B || (claimed_mask >> 16) >> B) return B200V_ERR_ARG;
+  if (((claimed_mask & 0xffffu) && !claimed_p_fr) || ((claimed_mask >> 16) && !claimed_q_fr)) return B200V_ERR_ARG;
+  for (int b = 0; b < B; ++b) {
+    if (((claimed_mask >> b) & 1) && !fr_ok((const Fr*)claimed_p_fr + b, 1)) return B200V_ERR_ARG;
+    if (((claimed_mask >> (16 + b)) & 1) && !fr_ok((const Fr*)claimed_q_fr + b, 1)) return B200V_ERR_ARG;
+  }
+  return guarded([&] {
+    std::vector<const Fr*> cp(B), cq(B);
+    for (int b = 0; b < B; ++b) {
+      cp[b] = (claimed_mask >> b) & 1 ? (const Fr*)claimed_p_fr + b : nullptr;
+      cq[b] = (claimed_mask >> (16 + b)) & 1 ? (const Fr*)claimed_q_fr + b : nullptr;
+    }
+    FractionalClaims o;
+    if (!fractional_sum_check_verify(num_vars, cp, cq, tr->tr, &o)) return B200V_REJECT;
+    memcpy(p_xs_out, o.p_xs.data(), B * sizeof(Fr));
+    memcpy(q_xs_out, o.q_xs.data(), B * sizeof(Fr));
+    memcpy(x_out, o.x.data(), num_vars * sizeof(Fr));
+    if (p_0s_out) memcpy(p_0s_out, o.p_0s.data(), B * sizeof(Fr));
+    if (q_0s_out) memcpy(q_0s_out, o.q_0s.data(), B * sizeof(Fr));
+    return B200V_ACCEPT;
+  });
+}
+
 int b200v_kzg_setup(const void* ss_fr, int num_vars, b200v_kzg** out) {
-  if (!ss_fr || !out || num_vars < 1 || num_vars > 40) return B200V_ERR_ARG;
+  if (!ss_fr || !out || num_vars < 1 || num_vars > 40 || !fr_ok(ss_fr, (size_t)num_vars)) return B200V_ERR_ARG;
   return guarded([&] {
     *out = new b200v_kzg{kzg_verifier_setup(std::vector<Fr>((const Fr*)ss_fr, (const Fr*)ss_fr + num_vars))};
     return B200V_ACCEPT;
@@ -136,7 +172,9 @@ void b200v_kzg_free(b200v_kzg* vp) { delete vp; }
 
 int b200v_kzg_verify(const b200v_kzg* vp, b200v_transcript* tr, const void* comm_g1, const void* point_fr, int num_vars,
                      const void* eval_fr) {
-  if (!vp || !tr || !comm_g1 || !point_fr || !eval_fr || num_vars < 1 || num_vars > vp->vp.num_vars()) return B200V_ERR_ARG;
+  if (!vp || !tr || !comm_g1 || !point_fr || !eval_fr || num_vars < 1 || num_vars > vp->vp.num_vars() ||
+      !fr_ok(point_fr, (size_t)num_vars) || !fr_ok(eval_fr, 1))
+    return B200V_ERR_ARG;
   return guarded([&] {
     const G1Affine c = *(const G1Affine*)comm_g1;
     if (!g1_ok(c)) return B200V_ERR_ARG;
@@ -149,7 +187,8 @@ int b200v_kzg_batch_verify(const b200v_kzg* vp, b200v_transcript* tr, int num_va
                            const void* points_fr, int npoints, const int32_t* ev_poly, const int32_t* ev_point,
                            const void* ev_values_fr, int nevals) {
   if (!vp || !tr || !comms_g1 || !points_fr || !ev_poly || !ev_point || !ev_values_fr || num_vars < 1 ||
-      num_vars > vp->vp.num_vars() || ncomms < 1 || npoints < 1 || nevals < 2 || nevals > (1 << 20))
+      num_vars > vp->vp.num_vars() || ncomms < 1 || npoints < 1 || npoints > (1 << 16) || nevals < 2 || nevals > (1 << 20) ||
+      !fr_ok(points_fr, (size_t)npoints * num_vars) || !fr_ok(ev_values_fr, (size_t)nevals))
     return B200V_ERR_ARG;
   return guarded([&] {
     std::vector<G1Affine> comms((const G1Affine*)comms_g1, (const G1Affine*)comms_g1 + ncomms);
@@ -224,7 +263,8 @@ int b200v_hyperplonk_new(const b200v_kzg* vp, int k, int ninstance_cols, const i
       (ninstance_cols && !num_instances) || nphases < 1 || nphases > 64 || !num_witness_polys || !num_challenges ||
       num_lookups < 0 || num_lookups > 64 || num_permutation_z_polys < 0 || num_permutation_z_polys > 64 ||
       !expression_tokens || ntokens < 1 || nconsts < 0 || (nconsts && !consts_fr) || npreprocess < 0 ||
-      (npreprocess && !preprocess_comms_g1) || npermutation < 0 || (npermutation && !permutation_comms_g1))
+      (npreprocess && !preprocess_comms_g1) || npermutation < 0 || (npermutation && !permutation_comms_g1) ||
+      !fr_ok(consts_fr, (size_t)nconsts))
     return B200V_ERR_ARG;
   return guarded([&] {
     HyperPlonkVerifierParam hp;
@@ -264,7 +304,8 @@ int b200v_hyperplonk_new(const b200v_kzg* vp, int k, int ninstance_cols, const i
 void b200v_hyperplonk_free(b200v_hyperplonk* hp) { delete hp; }
 
 int b200v_hyperplonk_verify(const b200v_hyperplonk* hp, b200v_transcript* tr, const void* instances_fr, int ninstances) {
-  if (!hp || !tr || ninstances < 0 || (ninstances && !instances_fr)) return B200V_ERR_ARG;
+  if (!hp || !tr || ninstances < 0 || (ninstances && !instances_fr) || !fr_ok(instances_fr, (size_t)ninstances))
+    return B200V_ERR_ARG;
   return guarded([&] {
     std::vector<std::vector<Fr>> cols;
     int off = 0;

@@ -131,6 +131,81 @@ inline bool sumcheck_verify(int num_vars, int degree, Fr sum, bool coeffs, Trans
   return true;
 }
 
+// verify_fractional_sum_check (pb/piop/gkr/fractional_sum_check.rs:192-265): GKR verifier for Σ_i p_b[i] / q_b[i] over a
+// batch of B (p, q) pairs. claimed_*: Some(value) -> absorbed as common input, None (nullptr) -> read from the proof.
+// Per layer v = 0 .. num_vars - 1: v = 0 reads the four single entries and checks p = p_l q_r + p_r q_l, q = q_l q_r;
+// v > 0: gamma, the degree-3 sum-check of eq * Σ_b [gamma^(2b) (p_l q_r + p_r q_l) + gamma^(2b+1) q_l q_r] for the claim
+// Σ gamma^i (p_0, q_0, p_1, q_1, ...) (sum_check_claim :279-284), the 4B evaluations, and the final check against the
+// expression at x (:246-249); then mu and layer_down_claim (:290-296). Returns the claims at the input layer and x.
+struct FractionalClaims {
+  std::vector<Fr> p_xs, q_xs, x, p_0s, q_0s;
+};
+inline bool fractional_sum_check_verify(int num_vars, const std::vector<const Fr*>& claimed_p_0s,
+                                        const std::vector<const Fr*>& claimed_q_0s, Transcript& tr, FractionalClaims* out) {
+  const int B = (int)claimed_p_0s.size();
+  std::vector<Fr> cp(B), cq(B);
+  for (int pass = 0; pass < 2; ++pass) {
+    const std::vector<const Fr*>& claimed = pass ? claimed_q_0s : claimed_p_0s;
+    std::vector<Fr>& dst = pass ? cq : cp;
+    for (int b = 0; b < B; ++b) {
+      if (claimed[b]) {
+        dst[b] = *claimed[b];
+        tr.common_field_element(dst[b]);
+      } else if (!tr.read_field_element(&dst[b])) {
+        return false;
+      }
+    }
+  }
+  out->p_0s = cp;
+  out->q_0s = cq;
+  std::vector<Fr> y;
+  for (int v = 0; v < num_vars; ++v) {
+    std::vector<Fr> x, evals(4 * B);
+    if (v == 0) {
+      for (auto& e : evals)
+        if (!tr.read_field_element(&e)) return false;
+      for (int b = 0; b < B; ++b) {
+        const Fr &pl = evals[4 * b], &pr = evals[4 * b + 1], &ql = evals[4 * b + 2], &qr = evals[4 * b + 3];
+        if (cp[b] != pl * qr + pr * ql || cq[b] != ql * qr) return false;
+      }
+    } else {
+      const Fr gamma = tr.squeeze_challenge();
+      Fr pw = Fr::one(), claim = Fr::zero();
+      for (int b = 0; b < B; ++b) {
+        claim = claim + pw * cp[b];
+        pw = pw * gamma;
+        claim = claim + pw * cq[b];
+        pw = pw * gamma;
+      }
+      Fr fin;
+      if (!sumcheck_verify(v, 3, claim, false, tr, &fin, &x)) return false;
+      for (auto& e : evals)
+        if (!tr.read_field_element(&e)) return false;
+      Fr s = Fr::zero();
+      pw = Fr::one();
+      for (int b = 0; b < B; ++b) {
+        const Fr &pl = evals[4 * b], &pr = evals[4 * b + 1], &ql = evals[4 * b + 2], &qr = evals[4 * b + 3];
+        s = s + pw * (pl * qr + pr * ql);
+        pw = pw * gamma;
+        s = s + pw * (ql * qr);
+        pw = pw * gamma;
+      }
+      if (fin != s * eq_xy_eval(x, y)) return false;
+    }
+    const Fr mu = tr.squeeze_challenge();
+    for (int b = 0; b < B; ++b) {
+      cp[b] = evals[4 * b] + mu * (evals[4 * b + 1] - evals[4 * b]);
+      cq[b] = evals[4 * b + 2] + mu * (evals[4 * b + 3] - evals[4 * b + 2]);
+    }
+    x.push_back(mu);
+    y = x;
+  }
+  out->p_xs = cp;
+  out->q_xs = cq;
+  out->x = y;
+  return true;
+}
+
 // MultilinearKzgVerifierParam (kzg.rs:79-84): g1, g2 are the curve generators, ss_g2[i] = g2 * s_i
 struct KzgVerifierParam {
   std::vector<G2Affine> ss_g2;

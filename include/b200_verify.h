@@ -42,6 +42,16 @@ int b200v_sumcheck_verify(b200v_transcript* tr, int num_vars, int degree, const 
 
 /* ---- MultilinearKzg verifier ------------------------------------------------------------------------------ */
 typedef struct b200v_kzg b200v_kzg; /* MultilinearKzgVerifierParam (kzg.rs:79-84): ss_g2[i] = g2 * s_i */
+/* verify_fractional_sum_check (pb/piop/gkr/fractional_sum_check.rs:192-265): the GKR argument b200_fractional_sum_check_prove
+ * writes, for num_batching (<= 16) pairs (p_b, q_b) of 2^num_vars-entry tables. Bit b / bit 16 + b of claimed_mask: the
+ * layer-0 value p_b / q_b is a public claim taken from claimed_p_fr[b] / claimed_q_fr[b] (Some(_): absorbed), otherwise it
+ * is read from the proof. ACCEPT returns the claims p_b(x), q_b(x) the caller must still check against its polynomials
+ * (p_xs_out, q_xs_out: num_batching each; x_out: num_vars) and the layer-0 values (p_0s_out / q_0s_out, may be NULL;
+ * sum_i p_b[i] / q_b[i] = p_0s[b] / q_0s[b]). */
+int b200v_fractional_sum_check_verify(b200v_transcript* tr, int num_batching, int num_vars, uint32_t claimed_mask,
+                                      const void* claimed_p_fr, const void* claimed_q_fr, void* p_xs_out, void* q_xs_out,
+                                      void* x_out, void* p_0s_out, void* q_0s_out);
+
 /* the verifier half of the seeded test setup b200_kzg_setup uses (kzg.rs:166-225) */
 int b200v_kzg_setup(const void* ss_fr, int num_vars, b200v_kzg** out);
 /* parameters from elsewhere: num_vars G2Affine points */

@@ -60,6 +60,14 @@ def test_parity_with_the_oracle_and_the_reference_test(hl, ctx, B, n):
     # the reference's test: the verifier accepts and the claims are the inputs' evaluations at x
     res = O.fractional_sum_check_verify(O.Transcript(proof), n, [None] * B, [None] * B)
     assert res is not None
+    # ... and the product's own CPU verifier (libb200verify.so) returns the same claims and point
+    from halo2_lasso_b200 import verifier as V
+
+    vt = V.ProofTranscript(proof)
+    vres = V.fractional_sum_check_verify(vt, n, [None] * B, [None] * B)
+    assert vres is not None and vt.done()
+    for g, w in zip(vres, got):
+        assert (np.asarray(g) == np.asarray(w)).all()
     p_xs, q_xs, x = got[0], got[1], got[2]
     for b in range(B):
         assert (O.evaluate(ps[b], x) == p_xs[b]).all() and (O.evaluate(qs[b], x) == q_xs[b]).all()

@@ -39,7 +39,7 @@ def tampered(proof, pos, bit=1):
 def test_library_exports_exactly_the_declared_symbols():
     out = subprocess.run(["nm", "-D", "--defined-only", V.LIB_PATH], capture_output=True, text=True, check=True).stdout
     exported = sorted(set(re.findall(r"\b(b200v_[a-z0-9_]+)\b", out)))
-    assert exported == V.declared_symbols() and len(exported) == 20
+    assert exported == V.declared_symbols() and len(exported) == 21
 
 
 def test_transcript_reading_side_matches_the_oracle():
@@ -301,6 +301,59 @@ def test_cfg1_hyperplonk_then_lasso_on_one_transcript(okzg, vkzg, k, mu):
     tr = V.ProofTranscript(to.proof())
     assert hv.verify(tr, inst) and not tr.done()
     assert vkzg.lasso_verify(tr, O.TABLE_RANGE, chunks, mu) and tr.done()
+
+
+def test_fractional_sum_check_verify_on_oracle_and_golden_proofs():
+    """b200v_fractional_sum_check_verify (fractional_sum_check.rs:192-265): accepts the oracle prover's proofs and the
+    committed golden proofs of the pure-Python model with the right claims and point, binds public claims (Some), rejects
+    tampered bytes, truncated proofs and wrong public claims."""
+    gold = json.load(open(os.path.join(HERE, "golden", "gkr_golden.json")))
+    for c in gold["cases"]:
+        B, n = c["batch"], c["num_vars"]
+        proof = bytes.fromhex(c["proof"])
+        p0 = O.fr_from_ints([int(v) for v in c["p_0s"]])
+        q0 = O.fr_from_ints([int(v) for v in c["q_0s"]])
+        cl_p = list(p0) if c["claimed"] else [None] * B
+        cl_q = list(q0) if c["claimed"] else [None] * B
+        tr = V.ProofTranscript(proof)
+        res = V.fractional_sum_check_verify(tr, n, cl_p, cl_q)
+        assert res is not None and tr.done()
+        for got, key in zip(res, ("p_xs", "q_xs", "x", "p_0s", "q_0s")):
+            assert O.fr_to_ints(got) == [int(v) for v in c[key]]
+        if n > 1:
+            assert V.fractional_sum_check_verify(V.ProofTranscript(tampered(proof, len(proof) // 2)), n, cl_p, cl_q) is None
+        assert V.fractional_sum_check_verify(V.ProofTranscript(proof[:-32]), n, cl_p, cl_q) is None
+        if c["claimed"]:
+            wrong = list(p0)
+            wrong[0] = O.rand_fr(5, 1)[0]
+            assert V.fractional_sum_check_verify(V.ProofTranscript(proof), n, wrong, cl_q) is None
+    # the reference's own test shape (batch of 3, nothing claimed) on a fresh oracle proof, mixed claims on another
+    B, n = 3, 9
+    ps = [O.rand_fr(7700 + b, 1 << n) for b in range(B)]
+    qs = [O.rand_fr(7800 + b, 1 << n) for b in range(B)]
+    to = O.Transcript()
+    want = O.fractional_sum_check_prove(to, ps, qs, [0, None, None], [None, None, 0])
+    res = V.fractional_sum_check_verify(V.ProofTranscript(to.proof()), n, [want[3][0], None, None], [None, None, want[4][2]])
+    assert res is not None
+    for b in range(B):
+        assert (O.evaluate(ps[b], res[2]) == res[0][b]).all() and (O.evaluate(qs[b], res[2]) == res[1][b]).all()
+    assert V.fractional_sum_check_verify(V.ProofTranscript(to.proof()), n, [None] * B, [None] * B) is None  # claims not bound
+    with pytest.raises(V.VerifierArgError):
+        V.fractional_sum_check_verify(V.ProofTranscript(to.proof()), 0, [None], [None])
+
+
+def test_non_reduced_field_limbs_are_argument_errors(okzg, vkzg):
+    """Fr inputs cross as Montgomery limbs; a residue >= r is malformed, not something to compute with"""
+    bad = np.array([0xFFFFFFFFFFFFFFFF] * 4, dtype=np.uint64)
+    modulus = np.array([(O.R_MOD >> (64 * i)) & 0xFFFFFFFFFFFFFFFF for i in range(4)], dtype=np.uint64)
+    for limbs in (bad, modulus):
+        with pytest.raises(V.VerifierArgError):
+            V.fractional_sum_check_verify(V.ProofTranscript(b"\0" * 64), 1, [limbs], [None])
+        with pytest.raises(V.VerifierArgError):
+            V.MultilinearKzgVerifier.setup(np.stack([limbs] * 3))
+        tr = V.ProofTranscript(b"")
+        with pytest.raises(V.VerifierArgError):
+            tr.common_field_elements(np.stack([limbs]))
 
 
 def test_lasso_as_the_lookup_argument_of_a_hyperplonk_circuit(okzg, vkzg):
