@@ -55,14 +55,24 @@ def test_shard_slice_covers_the_hypercube():
 # all-gathers only the D partial evaluations; after n_loc rounds the one remaining value per table and rank is
 # all-gathered and the last log2 G rounds run redundantly. Field arithmetic = the oracle's vector ops; the collective
 # is a real gloo all_gather between two processes. The transcript must equal the single-process oracle's.
-def _sharded_sumcheck_model(O, dist, rank, world, n, tabs, w, y, claim, NP):
+#
+# Index-WINDOW layout (the fully sharded Lasso prover, shard.cu): rank = index bits [p, p + g); the local tables are the
+# compact slices (hl.shard_window_slice), the local eq point is y[0..p) ++ y[p+g..n) with the eq factor of the window
+# bits, only the first SR <= p rounds are exchanged, then the bound tables are all-gathered in natural index order
+# (full index = ((hi * G + rank) << (p - SR)) | lo) and the remaining n - SR rounds run replicated. p = n - g, SR = n - g
+# is the top-variable layout above.
+def _sharded_sumcheck_model(O, dist, rank, world, n, tabs, w, y, claim, NP, p=None, SR=None):
     import numpy as np
     import torch
+
+    import halo2_lasso_b200 as hl
 
     R = O.R_MOD
     g = world.bit_length() - 1
     n_loc, T, D = n - g, len(tabs) // NP, NP + 1
-    lo, hi = rank << n_loc, (rank + 1) << n_loc
+    p = n_loc if p is None else p
+    SR = p if SR is None else SR
+    assert 0 <= SR <= p <= n_loc
     one = O.fr_from_ints([1])[0]
 
     def fsum(v):  # Σ of a (k, 4) vector of field elements by pairwise halving
@@ -118,26 +128,30 @@ def _sharded_sumcheck_model(O, dist, rank, world, n, tabs, w, y, claim, NP):
         return O.fix_var(t, r) if t.shape[0] > 1 else t
 
     tr = O.Transcript()
-    # local state: eq slice = eq(y[:n_loc]) * Π_j (rank_j ? y_top_j : 1 - y_top_j)
+    # local state: eq slice = eq(y_loc) * Π_j (rank_j ? y_(p+j) : 1 - y_(p+j)),  y_loc = y[0..p) ++ y[p+g..n)
     factor = one
     for j in range(g):
-        yj = y[n_loc + j]
+        yj = y[p + j]
         factor = O.field_op("mul", factor.reshape(1, 4), (yj if (rank >> j) & 1 else O.field_op("sub", one.reshape(1, 4), yj.reshape(1, 4))[0]).reshape(1, 4))[0]
-    eq = O.field_op("mul", O.eq_xy(y[:n_loc]), bcast(factor, 1 << n_loc))
-    tables = [t[lo:hi].copy() for t in tabs]
+    y_loc = np.concatenate([y[:p], y[p + g:]])
+    eq = O.field_op("mul", O.eq_xy(y_loc), bcast(factor, 1 << n_loc))
+    tables = [hl.shard_window_slice(t, n, p, rank, world).copy() for t in tabs]
     challenges = []
     for rnd in range(n):
-        if rnd == n_loc:  # rebuild the G-entry tables on every rank from the one value each rank is left with
+        if rnd == SR:  # all-gather of the (bound) local tables, natural index order: ((hi * G + rank) << q) | lo
+            q = p - SR
             gathered = all_gather(np.stack(tables + [eq]).reshape(-1, 4))
-            stacked = np.stack(gathered)  # (world, ntab + 1, 4)
-            tables = [np.ascontiguousarray(stacked[:, i, :]) for i in range(len(tabs))]
-            eq = np.ascontiguousarray(stacked[:, len(tabs), :])
+            k = len(tabs) + 1
+            stacked = np.stack(gathered).reshape(world, k, -1, 1 << q, 4)  # (rank, table, hi, lo, limbs)
+            full = np.ascontiguousarray(stacked.transpose(1, 2, 0, 3, 4)).reshape(k, -1, 4)  # (table, hi, rank, lo)
+            tables = [np.ascontiguousarray(full[i]) for i in range(len(tabs))]
+            eq = np.ascontiguousarray(full[len(tabs)])
         part = round_partials(eq, tables)
-        if rnd < n_loc:  # the only data that crosses ranks in a sharded round: D field elements
+        if rnd < SR:  # the only data that crosses ranks in a sharded round: D field elements
             parts = all_gather(part)
             total = parts[0]
-            for p in parts[1:]:
-                total = O.field_op("add", total, p)
+            for other in parts[1:]:
+                total = O.field_op("add", total, other)
         else:
             total = part
         p0 = O.field_op("sub", claim.reshape(1, 4), total[0:1])[0]  # p(0) = sum - p(1), eval.rs:129
@@ -172,6 +186,14 @@ def _protocol_worker(rank, world, port, q):
         ch_o, ev_o = O.sumcheck_prove_evals(to, n, tabs, y, terms, claim)
         proof, ch, ev = _sharded_sumcheck_model(O, dist, rank, world, n, tabs, w, y, claim, NP)
         ok = ok and proof == to.proof() and (ch == ch_o).all() and (ev == ev_o).all()
+        # the index-window layouts of the fully sharded Lasso prover: windows in the middle / at the bottom, fewer sharded
+        # rounds than the window allows, and none at all (pure all-gather)
+        g = world.bit_length() - 1
+        for p, SR in ((2, 2), (2, 1), (1, 0), (0, 0), (n - g, 1)):
+            if p > n - g:
+                continue
+            proof, ch, ev = _sharded_sumcheck_model(O, dist, rank, world, n, tabs, w, y, claim, NP, p=p, SR=SR)
+            ok = ok and proof == to.proof() and (ch == ch_o).all() and (ev == ev_o).all()
     # point-sharded MSM (shard.cu msm_sharded / msm_batch_dist): partial commitments all-gathered and added in rank order
     import numpy as np
     import torch
