@@ -11,6 +11,12 @@
 //
 // Every primitive is also implemented for the host with an emulated carry flag, so the exact limb
 // algorithm is unit-tested on the CPU (tests/test_ff32_host.py) before it ever runs on a GPU.
+//
+// Attribution: the even / odd accumulator scheme and the helper decomposition used below (ff_mul_n,
+// ff_cmad_n, ff_madc_n_rshift, ff_mad_n_redc, fe_final_sub) follow the publicly documented design of
+// Supranational's sppark library (`ff/mont_t.cuh`, Apache-2.0): the technique and the helper names
+// are theirs; this file is an independent implementation written for this project (fixed 8-limb
+// BN254 moduli, host emulation of the carry flag, Kaliski inversion), no sppark source is included.
 #pragma once
 #include <stdint.h>
 
