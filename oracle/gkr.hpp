@@ -11,6 +11,10 @@
 //   eq(x, y) * Σ_b [ γ^(2b) (p_l q_r + p_r q_l) + γ^(2b+1) q_l q_r ],
 // i.e. the EVAL shape of sumcheck.hpp with three terms per batch element that SHARE the four tables of that element;
 // its final evaluations come back in poly order [p_l, p_r, q_l, q_r] per element (classic.rs:143-149).
+//
+// parity: UNPINNED against the Rust crate (it cannot be built here and holds no numeric vectors for this module; its
+// own test is a prove -> verify property test, restated in tests/test_oracle_gkr.py). Pinned instead by an independent
+// pure-Python prover written from the same source (tests/golden/pymodel_gkr.py -> gkr_golden.json, byte for byte).
 #pragma once
 #include <vector>
 
