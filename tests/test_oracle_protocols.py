@@ -309,3 +309,38 @@ def test_eq_factored_round_polynomial_reproduces_the_reference_messages(n, T, NP
     ch_ref, ev_ref = M.sumcheck_prove_evals(t_ref, n, polys, y, terms, claim)
     ch_new, ev_new = _eq_factored_prove(M, t_new, n, polys, y, terms, claim, switch_round)
     assert t_new.stream == t_ref.stream and ch_new == ch_ref and ev_new == ev_ref
+
+
+def test_e_commitment_is_a_regrouping_of_the_dim_buckets(kz16):
+    """The identity behind the grouped MSM jobs of the CUDA prover (msm.cu msm_group_kernel): E_t = T[dim_t] is constant
+    per address and shares its bases with dim_t, so with B_d = Σ_{j: dim_t[j] = d} G_j (the bucket sums of the dim_t
+    commitment) Com(dim_t) = Σ_d d B_d and Com(E_t) = Σ_v v Σ_{d: T[d] = v} B_d — no second pass over the points.
+    Checked with the oracle's group arithmetic for the AND and XOR subtables (address 0 has T = 0 in both)."""
+    mu = 7
+    bases = kz16.eqs(mu)
+    for kind in (O.TABLE_AND, O.TABLE_XOR):
+        xs, ys = O.rand_u64s(60 + kind, 1 << mu) & np.uint64(0xFFFF), O.rand_u64s(70 + kind, 1 << mu) & np.uint64(0xFFFF)
+        xs[1::3] = xs[0::3][: len(xs[1::3])]
+        ys[1::3] = ys[0::3][: len(ys[1::3])]
+        mt, _ = O.lasso_witness(kind, 2, mu, xs, ys)
+        dim, e = O.fr_to_ints(mt[1]), O.fr_to_ints(mt[3])  # a | dim_0 dim_1 | e_0 e_1 | ts_0 ts_1
+        table = {d: ((d >> 8) & (d & 0xFF)) if kind == O.TABLE_AND else ((d >> 8) ^ (d & 0xFF)) for d in set(dim)}
+        assert all(table[d] == v for d, v in zip(dim, e))
+        buckets = {}
+        for j, d in enumerate(dim):
+            buckets[d] = bases[j] if d not in buckets else O.g1_add(buckets[d], bases[j])
+        by_value = {}
+        for d, b in buckets.items():
+            v = table[d]
+            if v:
+                by_value[v] = b if v not in by_value else O.g1_add(by_value[v], b)
+        acc_dim = acc_e = None
+        for d, b in buckets.items():
+            if d:
+                t = O.g1_mul(b, O.fr_from_ints([d])[0])
+                acc_dim = t if acc_dim is None else O.g1_add(acc_dim, t)
+        for v, b in by_value.items():
+            t = O.g1_mul(b, O.fr_from_ints([v])[0])
+            acc_e = t if acc_e is None else O.g1_add(acc_e, t)
+        assert (acc_dim == O.msm(mt[1], bases)).all()
+        assert (acc_e == O.msm(mt[3], bases)).all()
