@@ -276,6 +276,9 @@ def main():
     launches = ctx.launch_count(reset=True) // (args.steps + warm)
     ms_e2e = timed(lasso_e2e, max(3, args.steps // 2), 3)
     clocks = sampler.stop()
+    if world > 1:  # the phase profile is one extra proof: start it together, or its first collective absorbs the rank skew
+        torch.cuda.synchronize()
+        dist.barrier()
     phases = phases_of(lasso_device)
     if sharded:
         hl.dist_check(ctx)
