@@ -56,7 +56,7 @@ def test_witness_parity(hl, env, kind, chunks, mu):
 
 @pytest.mark.parametrize("kind,chunks,mu", [(O.TABLE_RANGE, 4, 4), (O.TABLE_AND, 8, 6), (O.TABLE_XOR, 2, 9),
                                             (O.TABLE_RANGE, 4, 13), (O.TABLE_AND, 8, 12), (O.TABLE_XOR, 3, 14),
-                                            (O.TABLE_AND, 2, 16)])  # the last three: grouped E commitments (conftest.py)
+                                            (O.TABLE_AND, 2, 16), (O.TABLE_AND, 8, 16)])  # from (AND, 8, 12) on: grouped E commitments (conftest.py)
 def test_lasso_proof_parity_and_verifies(hl, env, kind, chunks, mu):
     ctx, okzg, kzg = env
     xs, ys = operands(kind, chunks, mu, 60 + mu)
