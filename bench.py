@@ -138,9 +138,10 @@ def cpu_lasso(steps, warmup, srs=None, kind=KIND, chunks=CHUNKS, mu=MU):
 
     # torchrun exports OMP_NUM_THREADS=1: the CPU arm uses every host core it can, explicitly
     O.set_num_threads(max(1, len(os.sched_getaffinity(0))))
-    ss = O.rand_fr(SRS_SEED, max(mu, 16))
+    nv = max(mu, 16)
+    ss = O.rand_fr(SRS_SEED, nv)  # a prefix of the scalars of any larger setup with the same seed
     t0 = time.perf_counter()
-    kz = O.Kzg.from_eqs(ss, srs) if srs is not None else O.Kzg(ss)
+    kz = O.Kzg.from_eqs(ss, srs[:nv + 1]) if srs is not None else O.Kzg(ss)
     setup_s = time.perf_counter() - t0
     xs, ys = operands(kind, chunks, mu)
     times, proof = [], b""
@@ -285,6 +286,7 @@ def main():
 
     # ---- secondary legs --------------------------------------------------------------------------------------
     legs = {}
+    leg_proofs = {}  # name -> (kind, chunks, mu, GPU proof bytes): compared with the oracle's proofs below
     ms_sc = ms_sh = ms_zc = 0.0
     prof = None
     n, N = SC_VARS, 1 << SC_VARS
@@ -324,7 +326,7 @@ def main():
                 lx_host = torch.from_numpy(lx.view(np.int64)).pin_memory()
                 lx_dev = lx_host.to(dev)
                 lp = hl.LassoProver(ctx, kzg, kind, chunks)
-                plen = [0]
+                lproof = [b""]
 
                 def leg_device():
                     hl.Keccak256Transcript(ctx)
@@ -333,10 +335,12 @@ def main():
                 def leg_e2e():
                     tr = hl.Keccak256Transcript(ctx)
                     lp.prove(lx_host.numpy().view(np.uint64))
-                    plen[0] = len(tr.into_proof())
+                    lproof[0] = tr.into_proof()
 
                 legs[name] = {"ms_device": round(timed(leg_device, 10, 3), 4), "ms_e2e": round(timed(leg_e2e, 5, 2), 4),
-                              "phases_ms": phases_of(leg_device), "lookups": 1 << mu, "proof_bytes": plen[0]}
+                              "phases_ms": phases_of(leg_device), "lookups": 1 << mu, "proof_bytes": len(lproof[0]),
+                              "sha256": hashlib.sha256(lproof[0]).hexdigest()}
+                leg_proofs[name] = (kind, chunks, mu, lproof[0])
         else:
             # the SAME cfg2 sum-check sharded over the top log2(N) variables (2^20 entries per rank, n = 20 + log2 N in
             # total), partial sums exchanged inside the round kernels over NVLink peer memory
@@ -444,6 +448,14 @@ def main():
                          "instance and SRS as the GPU arm; its bytes are the parity check"}
         parity["bytes_equal"] = oproof == last_proof[0]
         parity["oracle_sha256"] = hashlib.sha256(oproof).hexdigest()
+        # the other full-size Lasso shapes of this run (cfg3 = "@2^20", the range table at 2^22): the same byte comparison
+        # with the oracle's proofs of the same instances (untimed; a failure here must not cost the bench line)
+        for name, (lkind, lchunks, lmu, gproof) in leg_proofs.items():
+            try:
+                _, _, _, lop = cpu_lasso(1, 0, srs, lkind, lchunks, lmu)
+                legs[name]["bytes_equal"] = lop == gproof
+            except Exception as e:
+                legs[name]["bytes_equal_error"] = repr(e)[:200]
 
     print(json.dumps({
         "metric": METRIC, "value": ms, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warm,
